@@ -1,0 +1,367 @@
+#!/usr/bin/env python
+"""bench.py -- target-steps/s of the punchclock hot path (propagate + vis + UKF).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+
+Workload (BASELINE.json configs[1]): 100 ground sensors x 10 000 mixed LEO/MEO/GEO targets,
+two-body, dt = 100 s, reference-default filter matrices, ~M targets tasked per step by a
+random-visible-target policy.  One "step" = one SSAScheduler physics step over the whole
+catalog: every sensor propagated, every target's truth propagated, every target's UKF
+predictAndUpdate (13 sigma-point propagations), both (N, M) visibility maps.  One
+target-step = that work for one target.
+
+Own arm: catalog resident in HBM (`value`), and end to end through CatalogEngine with host
+actions in / host observation out every step (`e2e`).  At N > 1 every rank owns its own
+catalog of the same size (weak scaling, targets partitioned, sensors replicated) and the
+ranks all-gather the packed estimated vis map + per-target summaries each step.
+
+Reference arm (--impl reference): the CPU oracle port of the reference algorithm
+(oracle/, one scipy DOP853 solve per state, Python loops per pair -- the reference's own
+structure) on all host cores, each step a bounded sample of the same workload.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+SEED = 20240625 + 2
+N_TARGETS, N_SENSORS, DT = 10_000, 100, 100.0
+METRIC = "target-steps/sec (propagate+vis+UKF)"
+UNIT = "target-steps/s"
+# Algorithmic work per unit, SURVEY.md section 8(d) (FMA = 2, add/mul/sqrt/div = 1):
+FLOP_DOP853_STEP = 1150.0          # one fixed DOP853 step: 12 RHS + stage sums + final combination
+FLOP_UKF_NOMEAS, FLOP_UKF_MEAS = 1500.0, 5600.0
+FLOP_VIS_PAIR = 8.0
+BYTES_TARGET_STEP = 1130.0         # truth/est_x/est_p r+w, pred_p w, z r (+ M/4 vis bits)
+
+
+def workload_config(n_targets, n_sensors):
+    return {"workload": f"{n_sensors} ground sensors x {n_targets} mixed LEO/MEO/GEO targets, two-body, "
+                        f"dt={DT:.0f}s, UKF per target (BASELINE.json configs[1])",
+            "targets_per_gpu": n_targets, "sensors": n_sensors, "dt_s": DT,
+            "tasking": "each sensor tasks a random estimated-visible target (<= M per step)",
+            "l2": "256 MiB flush between timed steps (state fits the 126 MB L2)"}
+
+
+# ----------------------------------------------------------------------------- clocks
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-i", str(self.index), "-lms", "100"], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._pump, daemon=True).start()
+        except OSError:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc:
+            self.proc.terminate()
+        sm = [float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
+        reasons = set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            for name, v in zip(names, r[4:8]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ----------------------------------------------------------------------------- CPU reference arm
+def _cpu_chunk(args):
+    """Oracle target-steps for a slice of targets (runs in a worker process)."""
+    from oracle.step import target_step
+    truth, est_x, est_p, Q, R, z, tasked, sensors, t0, tf = args
+    out = 0.0
+    for i in range(truth.shape[1]):
+        r = target_step(truth[:, i], est_x[:, i], est_p[i], Q, R, t0, tf, z[:, i] if tasked[i] else None, sensors)
+        out += float(r[0][0])
+    return out
+
+
+def cpu_reference_run(cat, sample, steps, warmup, cores):
+    """Times `steps` passes over a `sample`-target slice of the workload on `cores` processes."""
+    import multiprocessing as mp
+    rng = np.random.default_rng(SEED)
+    sample = min(sample, cat.N)
+    tasked = np.zeros(sample, bool)
+    tasked[rng.choice(sample, size=max(1, round(sample * cat.M / cat.N)), replace=False)] = True
+    z = cat.targets[:, :sample] + rng.normal(size=(6, sample)) * np.sqrt(np.diag(cat.R))[:, None]
+    bounds = np.linspace(0, sample, cores + 1).astype(int)
+    chunks = [(cat.targets[:, a:b], cat.est_x[:, a:b], cat.est_p[a:b], cat.Q, cat.R, z[:, a:b], tasked[a:b],
+               cat.sensors, 0.0, DT) for a, b in zip(bounds[:-1], bounds[1:]) if b > a]
+    ctx = mp.get_context("fork")
+    with ctx.Pool(cores) as pool:
+        for _ in range(warmup):
+            pool.map(_cpu_chunk, chunks)
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            pool.map(_cpu_chunk, chunks)
+        el = time.perf_counter() - t0
+    return sample * steps / el, el / steps, sample
+
+
+def host_cores():
+    try:
+        return len(os.sched_getaffinity(0))
+    except AttributeError:
+        return os.cpu_count() or 1
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from clockpunch_b200.simulation.catalog import synth_catalog
+    cat = synth_catalog(args.targets, args.sensors, seed=SEED)
+    cores = host_cores()
+    sample = min(cat.N, max(cores, args.cpu_sample_per_core * cores))
+    value, s_per_step, sample = cpu_reference_run(cat, sample, args.steps, args.warmup, cores)
+    desc = (f"{sample} of {cat.N} targets x {cat.M} sensors per step, oracle port (scipy DOP853 per state, "
+            f"python loop per pair), {cores} processes")
+    line = {"metric": METRIC, "value": value, "unit": UNIT, "impl": "reference", "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": s_per_step * 1e3,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": workload_config(args.targets, args.sensors),
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": desc},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line))
+
+
+# ----------------------------------------------------------------------------- own arm
+def run_own(args):
+    import torch
+    import torch.distributed as dist
+    from clockpunch_b200 import _lib
+    from clockpunch_b200.engine import CatalogEngine
+    from clockpunch_b200.simulation.catalog import synth_catalog
+    import ctypes as C
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (no CPU fallback); use --impl reference for the CPU arm")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    dev = torch.device("cuda", local)
+
+    N, M = args.targets, args.sensors
+    # every rank owns its own shard of targets; the sensor network is replicated
+    cat = synth_catalog(N, M, seed=SEED + 1000 * rank, sensor_seed=SEED)
+    eng = CatalogEngine(cat.sensors, cat.sensor_kinds, cat.targets, cat.est_x, cat.est_p, cat.Q, cat.R,
+                        device=local, seed=SEED + rank)
+    ctx, lib = eng.ctx, eng.ctx.lib
+    stream = torch.cuda.current_stream(dev).cuda_stream
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+
+    # per-step summaries every rank needs from every other: packed est vis map,
+    # trace(P_pos), trace(P_vel), staleness source, num_tasked
+    if world > 1:
+        g_vis = torch.empty((world * N, eng.wpr), dtype=torch.int32, device=dev)
+        g_trp = torch.empty((world * N,), dtype=torch.float32, device=dev)
+        g_trv = torch.empty((world * N,), dtype=torch.float32, device=dev)
+        g_ltt = torch.empty((world * N,), dtype=torch.float32, device=dev)
+        g_nt = torch.empty((world * N,), dtype=torch.int64, device=dev)
+
+    def device_step(k):
+        ctx.check(lib.pc_policy_random_visible(ctx.handle, eng.vis_est.data_ptr(), N, M, eng.wpr, SEED, k, 64,
+                                               eng.actions.data_ptr(), stream))
+        eng.task_from_actions(eng.actions)
+        eng.step(dt=DT, tasked=eng.tasked, z=None)
+        if world > 1:
+            dist.all_gather_into_tensor(g_vis, eng.vis_est)
+            dist.all_gather_into_tensor(g_trp, eng.tr_pos)
+            dist.all_gather_into_tensor(g_trv, eng.tr_vel)
+            dist.all_gather_into_tensor(g_ltt, eng.last_time_tasked)
+            dist.all_gather_into_tensor(g_nt, eng.num_tasked)
+
+    def barrier():
+        torch.cuda.synchronize(dev)
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize(dev)
+
+    # ---------------- device-resident throughput (`value`) ----------------
+    for k in range(args.warmup):
+        device_step(k)
+    peak_tf = C.c_double()
+    ctx.check(lib.pc_fp64_peak(ctx.handle, 5, C.byref(peak_tf)))
+    launches0 = ctx.launch_count
+    ctx.check(lib.pc_set_timing(ctx.handle, 1))
+    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    barrier()
+    wall0 = time.perf_counter()
+    tasked_total = 0
+    for k in range(args.steps):
+        flush.zero_()                      # L2 flush, outside the timed events
+        evs[k][0].record()
+        device_step(args.warmup + k)
+        evs[k][1].record()
+    barrier()
+    wall = time.perf_counter() - wall0
+    ms = sum(a.elapsed_time(b) for a, b in evs)
+    ukf_ms, ukf_n = C.c_double(), C.c_int64()
+    ctx.check(lib.pc_get_timing(ctx.handle, C.byref(ukf_ms), C.byref(ukf_n)))
+    ctx.check(lib.pc_set_timing(ctx.handle, 0))
+    launches = ctx.launch_count - launches0
+    tasked_total = int(eng.num_tasked.sum().item())
+    flags_bad = int((eng.flags != 0).sum().item())
+    t_ms = torch.tensor([ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t_ms, op=dist.ReduceOp.MAX)
+    ms_per_step = float(t_ms.item()) / args.steps
+    value = world * N / (ms_per_step * 1e-3)
+
+    # roofline of the dominant kernel (K4: truth + 13 sigma propagations + UKF algebra per target)
+    total_steps = args.warmup + args.steps
+    tasked_frac = tasked_total / max(1, N * total_steps)
+    substeps_used = 1.0 if args.substeps == 0 else float(args.substeps)   # auto rule: 1 at dt=100s, e<=0.01
+    flop_per_target = (14 * FLOP_DOP853_STEP * substeps_used
+                       + (1 - tasked_frac) * FLOP_UKF_NOMEAS + tasked_frac * FLOP_UKF_MEAS)
+    ukf_ms_avg = ukf_ms.value / max(1, ukf_n.value)
+    achieved_tf = flop_per_target * N / (ukf_ms_avg * 1e-3) * 1e-12
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except OSError:
+        pass
+    hbm_peak = peaks.get("hbm_gbs", 6650.0)
+    hbm_ach = (BYTES_TARGET_STEP - 96 + 0) * N / (ukf_ms_avg * 1e-3) * 1e-9
+    roofline = {"bound": "fp64", "kernel": "ukf_step_kernel", "achieved": achieved_tf, "peak": peak_tf.value,
+                "unit": "TFLOP/s", "frac": achieved_tf / peak_tf.value if peak_tf.value else None,
+                "traffic": None, "peak_source": "DFMA probe measured live in this run (pc_fp64_peak); "
+                "MEASURED_PEAKS.json has no FP64 entry; nominal 37 TFLOP/s",
+                "flop_per_target_step": flop_per_target, "substeps_per_propagate": substeps_used,
+                "kernel_ms": ukf_ms_avg, "kernel_share_of_step": ukf_ms_avg / ms_per_step,
+                "hbm": {"achieved": hbm_ach, "peak": hbm_peak, "unit": "GB/s", "frac": hbm_ach / hbm_peak,
+                        "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback"}}
+    clocks = sampler.stop() if rank == 0 else None
+
+    # ---------------- end to end through the public API (`e2e`) ----------------
+    n0, n1, n2 = eng._obs_sizes
+    h_obs = torch.empty((n0 + n1 + n2,), dtype=torch.float32).pin_memory()
+    h_vis = torch.empty((N, eng.wpr), dtype=torch.int32).pin_memory()
+    h_nt = torch.empty((N,), dtype=torch.int64).pin_memory()
+    h_act = torch.empty((M,), dtype=torch.int64).pin_memory()
+    rng = np.random.default_rng(SEED + rank)
+
+    def host_policy(vis_words):
+        probes = rng.integers(0, N, size=(M, 64))
+        j = np.arange(M)[:, None]
+        hit = (vis_words[probes, j >> 5] >> (j & 31)) & 1
+        first = hit.argmax(axis=1)
+        return np.where(hit.any(axis=1), probes[np.arange(M), first], N)
+
+    def e2e_step():
+        act = host_policy(h_vis.numpy().view(np.uint32))               # policy on the host, from the last obs
+        h_act.copy_(torch.from_numpy(act))
+        eng.actions[:M].copy_(h_act, non_blocking=True)                # H2D: this step's actions
+        eng.task_from_actions(eng.actions)
+        eng.step(dt=DT, tasked=eng.tasked, z=None)
+        if world > 1:
+            dist.all_gather_into_tensor(g_vis, eng.vis_est)
+        eng.pack_obs()
+        h_obs.copy_(eng.obs_f32, non_blocking=True)                    # D2H: the observation
+        h_vis.copy_(eng.vis_est, non_blocking=True)
+        h_nt.copy_(eng.num_tasked, non_blocking=True)
+        torch.cuda.current_stream(dev).synchronize()
+
+    h_vis.copy_(eng.vis_est)
+    for _ in range(args.warmup):
+        e2e_step()
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    tw = time.perf_counter()
+    for _ in range(args.steps):
+        e2e_step()
+    e1.record()
+    barrier()
+    e2e_wall = time.perf_counter() - tw
+    e2e_ms = torch.tensor([max(e0.elapsed_time(e1), e2e_wall * 1e3)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(e2e_ms, op=dist.ReduceOp.MAX)
+    e2e_value = world * N * args.steps / (float(e2e_ms.item()) * 1e-3)
+    e2e = {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h_act.numel() * 8),
+           "d2h_bytes_per_step": int(h_obs.numel() * 4 + h_vis.numel() * 4 + h_nt.numel() * 8),
+           "ms_per_step": float(e2e_ms.item()) / args.steps,
+           "path": "CatalogEngine: host actions -> pc_task_from_actions -> pc_step_fused -> pc_obs_pack -> pinned host obs"}
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ---------------- CPU baseline beside it (rank 0, N = 1 only) ----------------
+    cpu = None
+    if world == 1 and not args.no_cpu_baseline:
+        cores = host_cores()
+        sample = min(N, max(cores, args.cpu_sample_per_core * cores))
+        v, s_step, sample = cpu_reference_run(cat, sample, 1, 0, cores)
+        cpu = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
+               "sample": f"{sample} of {N} targets x {M} sensors, one pass ({s_step:.1f} s), oracle port on "
+                         f"{cores} processes (scipy DOP853 per state, python loop per pair)"}
+
+    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": workload_config(N, M),
+            "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu, "clocks": clocks,
+            "extra": {"tasked_per_step": tasked_total / total_steps, "flagged_targets": flags_bad,
+                      "wall_s_timed_region": wall, "launches_per_step": launches / args.steps,
+                      "target_propagation_steps_per_s": 14 * value}}
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="own", choices=["own", "reference"])
+    ap.add_argument("--targets", type=int, default=N_TARGETS)
+    ap.add_argument("--sensors", type=int, default=N_SENSORS)
+    ap.add_argument("--substeps", type=int, default=0)
+    ap.add_argument("--cpu-sample-per-core", type=int, default=32)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "own" else args.warmup
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_own(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,543 @@
+// C-ABI of libpunch_b200 (see include/punch_b200.h for the contract).
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <string>
+#include <utility>
+#include <vector>
+
+#include "pc_common.cuh"
+
+namespace pc {
+struct UkfArgs;
+cudaError_t launch_propagate_agents(const double*, double*, const uint8_t*, int, int64_t, int64_t,
+                                    double, double, int, int, cudaStream_t);
+cudaError_t launch_vismap_packed(const double*, int64_t, int64_t, const uint8_t*, double,
+                                 const double*, const double*, int64_t, int64_t, double, double,
+                                 uint32_t*, uint32_t*, int64_t, cudaStream_t);
+cudaError_t launch_vismap_value(const double*, int64_t, int64_t, const double*, int64_t, int64_t,
+                                double, double, double*, cudaStream_t);
+cudaError_t launch_ukf(double* est_x, double* est_p, double* truth_x, const double* z,
+                       const uint8_t* tasked, int64_t n, int64_t ld, double t0, double tf,
+                       int substeps, int force_model, const pc_ukf_params* p, uint64_t seed,
+                       uint64_t step, double* pred_x, double* pred_p, double* nis, uint32_t* flags,
+                       double* out_z, int64_t* num_tasked, float* last_time_tasked, float* tr_pos,
+                       float* tr_vel, cudaStream_t stream);
+cudaError_t launch_frame_change(const double*, double*, int64_t, int64_t, double, double, cudaStream_t);
+cudaError_t launch_coe2eci(const double*, double*, int64_t, int64_t, double, cudaStream_t);
+cudaError_t launch_lla2eci(const double*, double*, int64_t, int64_t, double, cudaStream_t);
+cudaError_t launch_task_from_actions(const int64_t*, int64_t, const uint32_t*, int64_t, int64_t,
+                                     uint8_t*, cudaStream_t);
+cudaError_t launch_obs_pack(const double*, int64_t, int64_t, const double*, const double*, int64_t,
+                            int64_t, const float*, double, float*, float*, float*, cudaStream_t);
+cudaError_t launch_policy_random_visible(const uint32_t*, int64_t, int64_t, int64_t, uint64_t,
+                                         uint64_t, int, int64_t*, cudaStream_t);
+double launch_dfma_probe(double*, int, int, cudaStream_t, cudaError_t*);
+cudaError_t launch_unpack_bits(const uint32_t* words, int64_t N, int64_t M, int64_t wpr,
+                               int64_t* out, cudaStream_t stream);
+}  // namespace pc
+
+struct pc_ctx {
+  int device = 0;
+  std::string err;
+  int64_t launches = 0;
+  // device workspace for the *_host entry points (grown on demand, freed with the ctx)
+  void* ws = nullptr;
+  size_t ws_bytes = 0;
+  cudaStream_t host_stream = nullptr;
+  // optional per-kernel timing of pc_step_fused (bench.py roofline leg)
+  bool timing = false;
+  std::vector<std::pair<cudaEvent_t, cudaEvent_t>> ev;  // around the UKF kernel
+  size_t ev_used = 0;
+};
+
+int pc_fail(pc_ctx* ctx, int code, const char* msg) {
+  if (ctx) ctx->err = msg;
+  return code;
+}
+int pc_fail_cuda(pc_ctx* ctx, cudaError_t e, const char* what) {
+  if (ctx) ctx->err = std::string(what) + ": " + cudaGetErrorString(e);
+  return PC_ERR_CUDA;
+}
+
+namespace {
+struct DeviceGuard {
+  int prev = -1;
+  explicit DeviceGuard(int dev) {
+    cudaGetDevice(&prev);
+    if (prev != dev) cudaSetDevice(dev);
+  }
+  ~DeviceGuard() {
+    int cur = -1;
+    cudaGetDevice(&cur);
+    if (prev >= 0 && cur != prev) cudaSetDevice(prev);
+  }
+};
+
+int ensure_ws(pc_ctx* ctx, size_t bytes) {
+  if (bytes <= ctx->ws_bytes) return PC_OK;
+  if (ctx->ws) cudaFree(ctx->ws);
+  ctx->ws = nullptr;
+  ctx->ws_bytes = 0;
+  size_t want = bytes + (bytes >> 2) + 4096;
+  PC_CUDA_TRY(ctx, cudaMalloc(&ctx->ws, want));
+  ctx->ws_bytes = want;
+  return PC_OK;
+}
+inline size_t align256(size_t x) { return (x + 255) & ~size_t(255); }
+}  // namespace
+
+#define PC_REQUIRE(ctx, cond, msg) \
+  do {                             \
+    if (!(cond)) return pc_fail((ctx), PC_ERR_BAD_ARG, msg); \
+  } while (0)
+
+extern "C" {
+
+int pc_version(void) { return 100; }
+
+int pc_ctx_create(int device_ordinal, pc_ctx** out) {
+  if (!out) return PC_ERR_BAD_ARG;
+  *out = nullptr;
+  int count = 0;
+  if (cudaGetDeviceCount(&count) != cudaSuccess || count <= 0) return PC_ERR_NO_DEVICE;
+  if (device_ordinal < 0 || device_ordinal >= count) return PC_ERR_BAD_ARG;
+  pc_ctx* ctx = new (std::nothrow) pc_ctx();
+  if (!ctx) return PC_ERR_BAD_ARG;
+  ctx->device = device_ordinal;
+  DeviceGuard g(device_ordinal);
+  if (cudaStreamCreateWithFlags(&ctx->host_stream, cudaStreamNonBlocking) != cudaSuccess) {
+    delete ctx;
+    return PC_ERR_CUDA;
+  }
+  *out = ctx;
+  return PC_OK;
+}
+
+int pc_ctx_destroy(pc_ctx* ctx) {
+  if (!ctx) return PC_OK;
+  {
+    DeviceGuard g(ctx->device);
+    if (ctx->ws) cudaFree(ctx->ws);
+    if (ctx->host_stream) cudaStreamDestroy(ctx->host_stream);
+    for (auto& p : ctx->ev) {
+      cudaEventDestroy(p.first);
+      cudaEventDestroy(p.second);
+    }
+  }
+  delete ctx;
+  return PC_OK;
+}
+
+const char* pc_last_error(pc_ctx* ctx) { return ctx ? ctx->err.c_str() : "null context"; }
+int64_t pc_launch_count(pc_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+/* ---- K1 ---------------------------------------------------------------- */
+static int propagate_common(pc_ctx* ctx, const double* x_in, double* x_out, const uint8_t* kind,
+                            int default_kind, int64_t n, int64_t ld, double t0, double tf,
+                            int substeps, int force_model, pc_stream stream) {
+  PC_REQUIRE(ctx, ctx != nullptr, "null context");
+  PC_REQUIRE(ctx, n >= 0 && ld >= n, "need 0 <= n <= ld");
+  PC_REQUIRE(ctx, n == 0 || (x_in && x_out), "null state pointer");
+  PC_REQUIRE(ctx, substeps >= 0, "substeps must be >= 0 (0 = auto)");
+  PC_REQUIRE(ctx, force_model == PC_FORCE_TWOBODY || force_model == PC_FORCE_TWOBODY_J2,
+             "unknown force model");
+  if (t0 == tf) return pc_fail(ctx, PC_ERR_EQUAL_TIMES, "t0 and tf are equal");
+  DeviceGuard g(ctx->device);
+  PC_CUDA_TRY(ctx, pc::launch_propagate_agents(x_in, x_out, kind, default_kind, n, ld, t0, tf,
+                                               substeps, force_model, (cudaStream_t)stream));
+  if (n) ctx->launches += 1;
+  return PC_OK;
+}
+
+int pc_propagate_twobody(pc_ctx* ctx, const double* x_in, double* x_out, int64_t n, int64_t ld,
+                         double t0, double tf, int substeps, int force_model, pc_stream stream) {
+  return propagate_common(ctx, x_in, x_out, nullptr, PC_KIND_SATELLITE, n, ld, t0, tf, substeps,
+                          force_model, stream);
+}
+
+int pc_rotate_terrestrial(pc_ctx* ctx, const double* x_in, double* x_out, int64_t n, int64_t ld,
+                          double t0, double tf, pc_stream stream) {
+  // The reference's StaticTerrestrial does not reject t0 == tf (identity rotation).
+  if (ctx && t0 == tf && n > 0 && x_in && x_out) {
+    DeviceGuard g(ctx->device);
+    if (x_in != x_out)
+      PC_CUDA_TRY(ctx, cudaMemcpy2DAsync(x_out, ld * sizeof(double), x_in, ld * sizeof(double),
+                                         n * sizeof(double), 6, cudaMemcpyDeviceToDevice,
+                                         (cudaStream_t)stream));
+    return PC_OK;
+  }
+  return propagate_common(ctx, x_in, x_out, nullptr, PC_KIND_TERRESTRIAL, n, ld, t0, tf, 0,
+                          PC_FORCE_TWOBODY, stream);
+}
+
+int pc_propagate_agents(pc_ctx* ctx, const double* x_in, double* x_out, const uint8_t* kind,
+                        int64_t n, int64_t ld, double t0, double tf, int substeps, int force_model,
+                        pc_stream stream) {
+  return propagate_common(ctx, x_in, x_out, kind, PC_KIND_SATELLITE, n, ld, t0, tf, substeps,
+                          force_model, stream);
+}
+
+int pc_propagate_agents_host(pc_ctx* ctx, const double* h_in, double* h_out, const uint8_t* h_kind,
+                             int64_t n, int64_t ld, double t0, double tf, int substeps,
+                             int force_model) {
+  PC_REQUIRE(ctx, ctx != nullptr, "null context");
+  PC_REQUIRE(ctx, n >= 0 && ld >= n, "need 0 <= n <= ld");
+  PC_REQUIRE(ctx, n == 0 || (h_in && h_out), "null state pointer");
+  if (t0 == tf) return pc_fail(ctx, PC_ERR_EQUAL_TIMES, "t0 and tf are equal");
+  if (n == 0) return PC_OK;
+  DeviceGuard g(ctx->device);
+  const size_t xb = align256(6 * (size_t)ld * sizeof(double));
+  const size_t kb = align256((size_t)n);
+  int rc = ensure_ws(ctx, xb + kb);
+  if (rc) return rc;
+  double* d_x = (double*)ctx->ws;
+  uint8_t* d_k = h_kind ? (uint8_t*)ctx->ws + xb : nullptr;
+  cudaStream_t s = ctx->host_stream;
+  PC_CUDA_TRY(ctx, cudaMemcpyAsync(d_x, h_in, 6 * (size_t)ld * sizeof(double), cudaMemcpyHostToDevice, s));
+  if (h_kind) PC_CUDA_TRY(ctx, cudaMemcpyAsync(d_k, h_kind, (size_t)n, cudaMemcpyHostToDevice, s));
+  rc = pc_propagate_agents(ctx, d_x, d_x, d_k, n, ld, t0, tf, substeps, force_model, s);
+  if (rc) return rc;
+  PC_CUDA_TRY(ctx, cudaMemcpyAsync(h_out, d_x, 6 * (size_t)ld * sizeof(double), cudaMemcpyDeviceToHost, s));
+  PC_CUDA_TRY(ctx, cudaStreamSynchronize(s));
+  return PC_OK;
+}
+
+/* ---- frames / initial conditions -------------------------------------- */
+int pc_frame_change(pc_ctx* ctx, const double* x_in, double* x_out, int64_t n, int64_t ld,
+                    double jd, int to_eci, pc_stream stream) {
+  PC_REQUIRE(ctx, ctx != nullptr, "null context");
+  PC_REQUIRE(ctx, n >= 0 && ld >= n, "need 0 <= n <= ld");
+  PC_REQUIRE(ctx, n == 0 || (x_in && x_out), "null state pointer");
+  DeviceGuard g(ctx->device);
+  const double w = to_eci ? pc::kOmegaEarth : -pc::kOmegaEarth;
+  PC_CUDA_TRY(ctx, pc::launch_frame_change(x_in, x_out, n, ld, w * jd, w, (cudaStream_t)stream));
+  if (n) ctx->launches += 1;
+  return PC_OK;
+}
+
+int pc_coe2eci(pc_ctx* ctx, const double* coe, double* x_out, int64_t n, int64_t ld, double mu,
+               pc_stream stream) {
+  PC_REQUIRE(ctx, ctx != nullptr, "null context");
+  PC_REQUIRE(ctx, n >= 0 && ld >= n, "need 0 <= n <= ld");
+  PC_REQUIRE(ctx, n == 0 || (coe && x_out), "null pointer");
+  DeviceGuard g(ctx->device);
+  PC_CUDA_TRY(ctx, pc::launch_coe2eci(coe, x_out, n, ld, mu, (cudaStream_t)stream));
+  if (n) ctx->launches += 1;
+  return PC_OK;
+}
+
+int pc_lla2eci(pc_ctx* ctx, const double* lla, double* x_out, int64_t n, int64_t ld, double jd,
+               pc_stream stream) {
+  PC_REQUIRE(ctx, ctx != nullptr, "null context");
+  PC_REQUIRE(ctx, n >= 0 && ld >= n, "need 0 <= n <= ld");
+  PC_REQUIRE(ctx, n == 0 || (lla && x_out), "null pointer");
+  DeviceGuard g(ctx->device);
+  PC_CUDA_TRY(ctx, pc::launch_lla2eci(lla, x_out, n, ld, jd, (cudaStream_t)stream));
+  if (n) ctx->launches += 1;
+  return PC_OK;
+}
+
+/* ---- K3 ---------------------------------------------------------------- */
+int pc_vismap_packed(pc_ctx* ctx, const double* sens, int64_t M, int64_t ld_s,
+                     const uint8_t* sens_kind, double sens_rot_angle, const double* targ_a,
+                     const double* targ_b, int64_t N, int64_t ld_t, double body_radius, double tol,
+                     uint32_t* out_a, uint32_t* out_b, int64_t words_per_row, pc_stream stream) {
+  PC_REQUIRE(ctx, ctx != nullptr, "null context");
+  PC_REQUIRE(ctx, M >= 0 && N >= 0 && ld_s >= M && ld_t >= N, "bad sizes");
+  PC_REQUIRE(ctx, words_per_row * 32 >= M, "words_per_row too small for M sensors");
+  if (M == 0 || N == 0) return PC_OK;
+  PC_REQUIRE(ctx, sens && targ_a && out_a, "null pointer");
+  PC_REQUIRE(ctx, (targ_b == nullptr) == (out_b == nullptr), "targ_b and out_b go together");
+  PC_REQUIRE(ctx, words_per_row == (M + 31) / 32, "words_per_row must be ceil(M/32)");
+  DeviceGuard g(ctx->device);
+  PC_CUDA_TRY(ctx, pc::launch_vismap_packed(sens, M, ld_s, sens_kind, sens_rot_angle, targ_a, targ_b,
+                                            N, ld_t, body_radius, tol, out_a, out_b, words_per_row,
+                                            (cudaStream_t)stream));
+  ctx->launches += 1;
+  return PC_OK;
+}
+
+int pc_vismap_value(pc_ctx* ctx, const double* sens, int64_t M, int64_t ld_s, const double* targ,
+                    int64_t N, int64_t ld_t, double body_radius, double tol, double* out,
+                    pc_stream stream) {
+  PC_REQUIRE(ctx, ctx != nullptr, "null context");
+  PC_REQUIRE(ctx, M >= 0 && N >= 0 && ld_s >= M && ld_t >= N, "bad sizes");
+  if (M == 0 || N == 0) return PC_OK;
+  PC_REQUIRE(ctx, sens && targ && out, "null pointer");
+  DeviceGuard g(ctx->device);
+  PC_CUDA_TRY(ctx, pc::launch_vismap_value(sens, M, ld_s, targ, N, ld_t, body_radius, tol, out,
+                                           (cudaStream_t)stream));
+  ctx->launches += 1;
+  return PC_OK;
+}
+
+int pc_vismap_host(pc_ctx* ctx, const double* h_sens, int64_t M, const double* h_targ, int64_t N,
+                   double body_radius, double tol, int binary, int64_t* out_i64, double* out_f64) {
+  PC_REQUIRE(ctx, ctx != nullptr, "null context");
+  PC_REQUIRE(ctx, M >= 0 && N >= 0, "bad sizes");
+  if (M == 0 || N == 0) return PC_OK;
+  PC_REQUIRE(ctx, h_sens && h_targ, "null pointer");
+  PC_REQUIRE(ctx, binary ? out_i64 != nullptr : out_f64 != nullptr, "null output");
+  DeviceGuard g(ctx->device);
+  const int64_t wpr = (M + 31) / 32;
+  const size_t sb = align256(6 * (size_t)M * 8), tb = align256(6 * (size_t)N * 8);
+  const size_t wb = align256((size_t)N * wpr * 4), ob = align256((size_t)N * M * 8);
+  int rc = ensure_ws(ctx, sb + tb + wb + ob);
+  if (rc) return rc;
+  char* base = (char*)ctx->ws;
+  double* d_s = (double*)base;
+  double* d_t = (double*)(base + sb);
+  uint32_t* d_w = (uint32_t*)(base + sb + tb);
+  void* d_o = base + sb + tb + wb;
+  cudaStream_t s = ctx->host_stream;
+  PC_CUDA_TRY(ctx, cudaMemcpyAsync(d_s, h_sens, 6 * (size_t)M * 8, cudaMemcpyHostToDevice, s));
+  PC_CUDA_TRY(ctx, cudaMemcpyAsync(d_t, h_targ, 6 * (size_t)N * 8, cudaMemcpyHostToDevice, s));
+  if (binary) {
+    rc = pc_vismap_packed(ctx, d_s, M, M, nullptr, 0.0, d_t, nullptr, N, N, body_radius, tol, d_w,
+                          nullptr, wpr, s);
+    if (rc) return rc;
+    PC_CUDA_TRY(ctx, pc::launch_unpack_bits(d_w, N, M, wpr, (int64_t*)d_o, s));
+    ctx->launches += 1;
+    PC_CUDA_TRY(ctx, cudaMemcpyAsync(out_i64, d_o, (size_t)N * M * 8, cudaMemcpyDeviceToHost, s));
+  } else {
+    rc = pc_vismap_value(ctx, d_s, M, M, d_t, N, N, body_radius, tol, (double*)d_o, s);
+    if (rc) return rc;
+    PC_CUDA_TRY(ctx, cudaMemcpyAsync(out_f64, d_o, (size_t)N * M * 8, cudaMemcpyDeviceToHost, s));
+  }
+  PC_CUDA_TRY(ctx, cudaStreamSynchronize(s));
+  return PC_OK;
+}
+
+/* ---- K4 ---------------------------------------------------------------- */
+static int ukf_check(pc_ctx* ctx, const double* est_x, const double* est_p, const double* truth_x,
+                     const double* z, const uint8_t* tasked, int64_t n, int64_t ld, double t0,
+                     double tf, int substeps, int force_model, const pc_ukf_params* params) {
+  PC_REQUIRE(ctx, ctx != nullptr, "null context");
+  PC_REQUIRE(ctx, n >= 0 && ld >= n, "need 0 <= n <= ld");
+  PC_REQUIRE(ctx, params != nullptr, "null params");
+  PC_REQUIRE(ctx, n == 0 || (est_x && est_p), "null filter state pointer");
+  PC_REQUIRE(ctx, substeps >= 0, "substeps must be >= 0 (0 = auto)");
+  PC_REQUIRE(ctx, force_model == PC_FORCE_TWOBODY || force_model == PC_FORCE_TWOBODY_J2,
+             "unknown force model");
+  PC_REQUIRE(ctx, !(tasked && !z && !truth_x),
+             "tasked targets need z or truth_x (to draw the measurement)");
+  if (t0 == tf) return pc_fail(ctx, PC_ERR_EQUAL_TIMES, "t0 and tf are equal");
+  return PC_OK;
+}
+
+int pc_ukf_predict_update(pc_ctx* ctx, double* est_x, double* est_p, double* truth_x,
+                          const double* z, const uint8_t* tasked, int64_t n, int64_t ld, double t0,
+                          double tf, int substeps, int force_model, const pc_ukf_params* params,
+                          uint64_t rng_seed, uint64_t rng_step, double* out_pred_x,
+                          double* out_pred_p, double* out_nis, uint32_t* out_flags, double* out_z,
+                          pc_stream stream) {
+  int rc = ukf_check(ctx, est_x, est_p, truth_x, z, tasked, n, ld, t0, tf, substeps, force_model, params);
+  if (rc) return rc;
+  if (n == 0) return PC_OK;
+  DeviceGuard g(ctx->device);
+  PC_CUDA_TRY(ctx, pc::launch_ukf(est_x, est_p, truth_x, z, tasked, n, ld, t0, tf, substeps,
+                                  force_model, params, rng_seed, rng_step, out_pred_x, out_pred_p,
+                                  out_nis, out_flags, out_z, nullptr, nullptr, nullptr, nullptr,
+                                  (cudaStream_t)stream));
+  ctx->launches += 1;
+  return PC_OK;
+}
+
+int pc_ukf_predict_update_host(pc_ctx* ctx, double* h_est_x, double* h_est_p, const double* h_z,
+                               const uint8_t* h_tasked, int64_t n, double t0, double tf,
+                               int substeps, int force_model, const pc_ukf_params* params,
+                               double* h_pred_x, double* h_pred_p, double* h_nis,
+                               uint32_t* h_flags) {
+  PC_REQUIRE(ctx, ctx != nullptr, "null context");
+  PC_REQUIRE(ctx, !(h_tasked && !h_z), "tasked targets need z on the host path");
+  int rc = ukf_check(ctx, h_est_x, h_est_p, nullptr, h_z, h_tasked, n, n, t0, tf, substeps, force_model, params);
+  if (rc) return rc;
+  if (n == 0) return PC_OK;
+  DeviceGuard g(ctx->device);
+  const size_t xb = align256(6 * (size_t)n * 8), pb = align256(36 * (size_t)n * 8);
+  const size_t nb = align256((size_t)n * 8), fb = align256((size_t)n * 4), kb = align256((size_t)n);
+  rc = ensure_ws(ctx, 3 * xb + 2 * pb + nb + fb + kb);
+  if (rc) return rc;
+  char* b = (char*)ctx->ws;
+  double* d_x = (double*)b;           b += xb;
+  double* d_z = (double*)b;           b += xb;
+  double* d_px = (double*)b;          b += xb;
+  double* d_p = (double*)b;           b += pb;
+  double* d_pp = (double*)b;          b += pb;
+  double* d_nis = (double*)b;         b += nb;
+  uint32_t* d_f = (uint32_t*)b;       b += fb;
+  uint8_t* d_k = (uint8_t*)b;
+  cudaStream_t s = ctx->host_stream;
+  PC_CUDA_TRY(ctx, cudaMemcpyAsync(d_x, h_est_x, 6 * (size_t)n * 8, cudaMemcpyHostToDevice, s));
+  PC_CUDA_TRY(ctx, cudaMemcpyAsync(d_p, h_est_p, 36 * (size_t)n * 8, cudaMemcpyHostToDevice, s));
+  if (h_z) PC_CUDA_TRY(ctx, cudaMemcpyAsync(d_z, h_z, 6 * (size_t)n * 8, cudaMemcpyHostToDevice, s));
+  if (h_tasked) PC_CUDA_TRY(ctx, cudaMemcpyAsync(d_k, h_tasked, (size_t)n, cudaMemcpyHostToDevice, s));
+  rc = pc_ukf_predict_update(ctx, d_x, d_p, nullptr, h_z ? d_z : nullptr, h_tasked ? d_k : nullptr, n,
+                             n, t0, tf, substeps, force_model, params, 0, 0, d_px, d_pp, d_nis, d_f,
+                             nullptr, s);
+  if (rc) return rc;
+  PC_CUDA_TRY(ctx, cudaMemcpyAsync(h_est_x, d_x, 6 * (size_t)n * 8, cudaMemcpyDeviceToHost, s));
+  PC_CUDA_TRY(ctx, cudaMemcpyAsync(h_est_p, d_p, 36 * (size_t)n * 8, cudaMemcpyDeviceToHost, s));
+  if (h_pred_x) PC_CUDA_TRY(ctx, cudaMemcpyAsync(h_pred_x, d_px, 6 * (size_t)n * 8, cudaMemcpyDeviceToHost, s));
+  if (h_pred_p) PC_CUDA_TRY(ctx, cudaMemcpyAsync(h_pred_p, d_pp, 36 * (size_t)n * 8, cudaMemcpyDeviceToHost, s));
+  if (h_nis) PC_CUDA_TRY(ctx, cudaMemcpyAsync(h_nis, d_nis, (size_t)n * 8, cudaMemcpyDeviceToHost, s));
+  if (h_flags) PC_CUDA_TRY(ctx, cudaMemcpyAsync(h_flags, d_f, (size_t)n * 4, cudaMemcpyDeviceToHost, s));
+  PC_CUDA_TRY(ctx, cudaStreamSynchronize(s));
+  return PC_OK;
+}
+
+/* ---- scheduler glue --------------------------------------------------- */
+int pc_task_from_actions(pc_ctx* ctx, const int64_t* actions, int64_t M, const uint32_t* vis_est,
+                         int64_t N, int64_t words_per_row, uint8_t* tasked, pc_stream stream) {
+  PC_REQUIRE(ctx, ctx != nullptr, "null context");
+  PC_REQUIRE(ctx, M >= 0 && N >= 0, "bad sizes");
+  if (N == 0) return PC_OK;
+  PC_REQUIRE(ctx, tasked && (M == 0 || (actions && vis_est)), "null pointer");
+  PC_REQUIRE(ctx, words_per_row == (M + 31) / 32, "words_per_row must be ceil(M/32)");
+  DeviceGuard g(ctx->device);
+  PC_CUDA_TRY(ctx, pc::launch_task_from_actions(actions, M, vis_est, N, words_per_row, tasked,
+                                                (cudaStream_t)stream));
+  if (M) ctx->launches += 1;
+  return PC_OK;
+}
+
+int pc_obs_pack(pc_ctx* ctx, const double* sens_x, int64_t M, int64_t ld_s, const double* est_x,
+                const double* est_p, int64_t N, int64_t ld, const float* last_time_tasked,
+                double t_now, float* out_eci, float* out_cov, float* out_stale, pc_stream stream) {
+  PC_REQUIRE(ctx, ctx != nullptr, "null context");
+  PC_REQUIRE(ctx, M >= 0 && N >= 0 && ld_s >= M && ld >= N, "bad sizes");
+  PC_REQUIRE(ctx, out_eci && out_cov && out_stale, "null output");
+  PC_REQUIRE(ctx, (M == 0 || sens_x) && (N == 0 || (est_x && est_p && last_time_tasked)), "null input");
+  DeviceGuard g(ctx->device);
+  PC_CUDA_TRY(ctx, pc::launch_obs_pack(sens_x, M, ld_s, est_x, est_p, N, ld, last_time_tasked, t_now,
+                                       out_eci, out_cov, out_stale, (cudaStream_t)stream));
+  ctx->launches += 1;
+  return PC_OK;
+}
+
+int pc_policy_random_visible(pc_ctx* ctx, const uint32_t* vis_est, int64_t N, int64_t M,
+                             int64_t words_per_row, uint64_t seed, uint64_t step, int probes,
+                             int64_t* actions, pc_stream stream) {
+  PC_REQUIRE(ctx, ctx != nullptr, "null context");
+  PC_REQUIRE(ctx, N > 0 && M >= 0 && probes >= 0, "bad sizes");
+  PC_REQUIRE(ctx, M == 0 || (vis_est && actions), "null pointer");
+  PC_REQUIRE(ctx, words_per_row == (M + 31) / 32, "words_per_row must be ceil(M/32)");
+  DeviceGuard g(ctx->device);
+  PC_CUDA_TRY(ctx, pc::launch_policy_random_visible(vis_est, N, M, words_per_row, seed, step, probes,
+                                                    actions, (cudaStream_t)stream));
+  if (M) ctx->launches += 1;
+  return PC_OK;
+}
+
+/* ---- measurement helpers ------------------------------------------------ */
+int pc_set_timing(pc_ctx* ctx, int enabled) {
+  PC_REQUIRE(ctx, ctx != nullptr, "null context");
+  ctx->timing = enabled != 0;
+  ctx->ev_used = 0;
+  return PC_OK;
+}
+
+int pc_get_timing(pc_ctx* ctx, double* ukf_ms_total, int64_t* launches) {
+  PC_REQUIRE(ctx, ctx != nullptr && ukf_ms_total && launches, "null pointer");
+  DeviceGuard g(ctx->device);
+  double tot = 0.0;
+  for (size_t i = 0; i < ctx->ev_used; ++i) {
+    float ms = 0.f;
+    PC_CUDA_TRY(ctx, cudaEventSynchronize(ctx->ev[i].second));
+    PC_CUDA_TRY(ctx, cudaEventElapsedTime(&ms, ctx->ev[i].first, ctx->ev[i].second));
+    tot += ms;
+  }
+  *ukf_ms_total = tot;
+  *launches = (int64_t)ctx->ev_used;
+  return PC_OK;
+}
+
+int pc_fp64_peak(pc_ctx* ctx, int repeats, double* tflops) {
+  PC_REQUIRE(ctx, ctx != nullptr && tflops, "null pointer");
+  DeviceGuard g(ctx->device);
+  cudaDeviceProp prop;
+  PC_CUDA_TRY(ctx, cudaGetDeviceProperties(&prop, ctx->device));
+  int rc = ensure_ws(ctx, 4096);
+  if (rc) return rc;
+  cudaEvent_t e0, e1;
+  PC_CUDA_TRY(ctx, cudaEventCreate(&e0));
+  PC_CUDA_TRY(ctx, cudaEventCreate(&e1));
+  const int blocks = prop.multiProcessorCount * 8;
+  cudaError_t err;
+  pc::launch_dfma_probe((double*)ctx->ws, blocks, 256, ctx->host_stream, &err);  // warm-up
+  PC_CUDA_TRY(ctx, err);
+  double best = 0.0;
+  for (int r = 0; r < (repeats > 0 ? repeats : 5); ++r) {
+    PC_CUDA_TRY(ctx, cudaEventRecord(e0, ctx->host_stream));
+    const double flop = pc::launch_dfma_probe((double*)ctx->ws, blocks, 4096, ctx->host_stream, &err);
+    PC_CUDA_TRY(ctx, err);
+    PC_CUDA_TRY(ctx, cudaEventRecord(e1, ctx->host_stream));
+    PC_CUDA_TRY(ctx, cudaEventSynchronize(e1));
+    float ms = 0.f;
+    PC_CUDA_TRY(ctx, cudaEventElapsedTime(&ms, e0, e1));
+    const double tf = flop / (ms * 1e-3) * 1e-12;
+    if (tf > best) best = tf;
+    ctx->launches += 1;
+  }
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  *tflops = best;
+  return PC_OK;
+}
+
+/* ---- fused step -------------------------------------------------------- */
+int pc_step_fused(pc_ctx* ctx, const pc_step_args* a, const pc_ukf_params* params,
+                  pc_stream stream) {
+  PC_REQUIRE(ctx, ctx != nullptr, "null context");
+  PC_REQUIRE(ctx, a != nullptr && params != nullptr, "null args");
+  PC_REQUIRE(ctx, a->M >= 0 && a->ld_s >= a->M, "bad sensor sizes");
+  PC_REQUIRE(ctx, a->truth_x != nullptr || a->N == 0, "step needs truth_x");
+  int rc = ukf_check(ctx, a->est_x, a->est_p, a->truth_x, a->z, a->tasked, a->N, a->ld, a->t0, a->tf,
+                     a->substeps, a->force_model, params);
+  if (rc) return rc;
+  PC_REQUIRE(ctx, a->M == 0 || (a->sens_x && a->sens_kind), "null sensor pointer");
+  const bool want_vis = a->vis_truth || a->vis_est;
+  PC_REQUIRE(ctx, !want_vis || (a->vis_truth && a->vis_est), "vis_truth and vis_est go together");
+  PC_REQUIRE(ctx, !want_vis || a->words_per_row == (a->M + 31) / 32, "words_per_row must be ceil(M/32)");
+  DeviceGuard g(ctx->device);
+  cudaStream_t s = (cudaStream_t)stream;
+  // 1. sensors (Agent.propagate per sensor; terrestrial ones are a rotation)
+  if (a->M > 0) {
+    PC_CUDA_TRY(ctx, pc::launch_propagate_agents(a->sens_x, a->sens_x, a->sens_kind, PC_KIND_SATELLITE,
+                                                 a->M, a->ld_s, a->t0, a->tf, a->substeps,
+                                                 a->force_model, s));
+    ctx->launches += 1;
+  }
+  // 2. targets: truth + UKF + summaries
+  if (a->N > 0) {
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    if (ctx->timing) {
+      if (ctx->ev_used == ctx->ev.size()) {
+        PC_CUDA_TRY(ctx, cudaEventCreate(&e0));
+        PC_CUDA_TRY(ctx, cudaEventCreate(&e1));
+        ctx->ev.emplace_back(e0, e1);
+      }
+      e0 = ctx->ev[ctx->ev_used].first;
+      e1 = ctx->ev[ctx->ev_used].second;
+      ctx->ev_used += 1;
+      PC_CUDA_TRY(ctx, cudaEventRecord(e0, s));
+    }
+    PC_CUDA_TRY(ctx, pc::launch_ukf(a->est_x, a->est_p, a->truth_x, a->z, a->tasked, a->N, a->ld,
+                                    a->t0, a->tf, a->substeps, a->force_model, params, a->rng_seed,
+                                    a->rng_step, nullptr, a->pred_p, a->nis, a->flags, nullptr,
+                                    a->num_tasked, a->last_time_tasked, a->tr_pos, a->tr_vel, s));
+    if (e1) PC_CUDA_TRY(ctx, cudaEventRecord(e1, s));
+    ctx->launches += 1;
+  }
+  // 3. both visibility maps for the next step (env.py:455-462)
+  if (want_vis && a->M > 0 && a->N > 0) {
+    PC_CUDA_TRY(ctx, pc::launch_vismap_packed(a->sens_x, a->M, a->ld_s, nullptr, 0.0, a->truth_x,
+                                              a->est_x, a->N, a->ld, a->body_radius, a->vis_tol,
+                                              a->vis_truth, a->vis_est, a->words_per_row, s));
+    ctx->launches += 1;
+  }
+  return PC_OK;
+}
+
+}  // extern "C"

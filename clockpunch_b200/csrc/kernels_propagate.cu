@@ -1,0 +1,146 @@
+// K1 / K2: batched agent propagation, one thread per state vector.
+// Layout: SoA (6, ld) FP64 -> each component row is read/written fully coalesced.
+#include "propagate.cuh"
+
+namespace pc {
+
+template <bool J2>
+__global__ void __launch_bounds__(128)
+propagate_agents_kernel(const double* __restrict__ x_in, double* __restrict__ x_out,
+                        const uint8_t* __restrict__ kind, int default_kind, int64_t n, int64_t ld,
+                        double dt, int substeps, double cs, double sn) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  double r[3], v[3];
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    r[c] = x_in[(int64_t)c * ld + i];
+    v[c] = x_in[(int64_t)(c + 3) * ld + i];
+  }
+  const int k = kind ? (int)kind[i] : default_kind;
+  if (k == PC_KIND_TERRESTRIAL) {
+    rotate_z(r, v, cs, sn);
+  } else {
+    const int nsub = substeps > 0 ? substeps : auto_substeps(r, v, dt, nullptr);
+    propagate_state<J2>(r, v, dt, nsub);
+  }
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    x_out[(int64_t)c * ld + i] = r[c];
+    x_out[(int64_t)(c + 3) * ld + i] = v[c];
+  }
+}
+
+cudaError_t launch_propagate_agents(const double* x_in, double* x_out, const uint8_t* kind,
+                                    int default_kind, int64_t n, int64_t ld, double t0, double tf,
+                                    int substeps, int force_model, cudaStream_t stream) {
+  if (n <= 0) return cudaSuccess;
+  const double dt = tf - t0;
+  const double ang = kOmegaEarth * dt;
+  const double cs = cos(ang), sn = sin(ang);
+  const int threads = 128;
+  const unsigned blocks = (unsigned)((n + threads - 1) / threads);
+  if (force_model == PC_FORCE_TWOBODY_J2)
+    propagate_agents_kernel<true><<<blocks, threads, 0, stream>>>(x_in, x_out, kind, default_kind, n,
+                                                                  ld, dt, substeps, cs, sn);
+  else
+    propagate_agents_kernel<false><<<blocks, threads, 0, stream>>>(x_in, x_out, kind, default_kind,
+                                                                   n, ld, dt, substeps, cs, sn);
+  return cudaGetLastError();
+}
+
+// ---- frame transforms / initial-condition generation (transforms.py:34-292) -----------
+
+// r1 = R3(angle) r0 ; v1 = R3(angle) v0 + (0,0,omega) x r1   (_transport_theorem_posvel,
+// transforms.py:143-178; ecef2eci: angle = +w JD, omega = +w; eci2ecef: both negated)
+__global__ void __launch_bounds__(128)
+frame_change_kernel(const double* __restrict__ x_in, double* __restrict__ x_out, int64_t n,
+                    int64_t ld, double cs, double sn, double omega) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const double x = x_in[i], y = x_in[ld + i], z = x_in[2 * ld + i];
+  const double vx = x_in[3 * ld + i], vy = x_in[4 * ld + i], vz = x_in[5 * ld + i];
+  const double rx = cs * x - sn * y, ry = sn * x + cs * y;
+  x_out[i] = rx;
+  x_out[ld + i] = ry;
+  x_out[2 * ld + i] = z;
+  x_out[3 * ld + i] = (cs * vx - sn * vy) - omega * ry;
+  x_out[4 * ld + i] = (sn * vx + cs * vy) + omega * rx;
+  x_out[5 * ld + i] = vz;
+}
+
+// coe2eci (transforms.py:240-292): COE -> PQW -> ECI, rot3(-raan) rot1(-inc) rot3(-argp).
+__global__ void __launch_bounds__(128)
+coe2eci_kernel(const double* __restrict__ coe, double* __restrict__ x_out, int64_t n, int64_t ld,
+               double mu) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const double sma = coe[i], ecc = coe[ld + i], inc = coe[2 * ld + i];
+  const double raan = coe[3 * ld + i], argp = coe[4 * ld + i], ta = coe[5 * ld + i];
+  double sa, ca, so, co, si, ci, sw, cw;
+  sincos(ta, &sa, &ca);
+  sincos(raan, &so, &co);
+  sincos(inc, &si, &ci);
+  sincos(argp, &sw, &cw);
+  const double p = sma * (1.0 - ecc * ecc);
+  const double rr = p / (1.0 + ecc * ca);
+  const double vv = sqrt(mu / p);
+  const double rp = rr * ca, rq = rr * sa;
+  const double vp = -vv * sa, vq = vv * (ecc + ca);
+  // columns 1 and 2 of rot3(-raan) rot1(-inc) rot3(-argp) with the reference's rot1/rot3
+  // (transforms.py:186-237: active-rotation matrices, so this is NOT the textbook PQW->ECI
+  // matrix but its counterpart with the three angles negated -- the reference is the spec).
+  const double Px = co * cw - so * ci * sw, Py = -so * cw - co * ci * sw, Pz = si * sw;
+  const double Qx = co * sw + so * ci * cw, Qy = -so * sw + co * ci * cw, Qz = -si * cw;
+  x_out[i] = Px * rp + Qx * rq;
+  x_out[ld + i] = Py * rp + Qy * rq;
+  x_out[2 * ld + i] = Pz * rp + Qz * rq;
+  x_out[3 * ld + i] = Px * vp + Qx * vq;
+  x_out[4 * ld + i] = Py * vp + Qy * vq;
+  x_out[5 * ld + i] = Pz * vp + Qz * vq;
+}
+
+// lla2ecef (transforms.py:34-52, spherical Earth, zero ECEF velocity) then ecef2eci(., JD).
+__global__ void __launch_bounds__(128)
+lla2eci_kernel(const double* __restrict__ lla, double* __restrict__ x_out, int64_t n, int64_t ld,
+               double cs, double sn, double omega) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const double lat = lla[i], lon = lla[ld + i], alt = lla[2 * ld + i];
+  double slat, clat, slon, clon;
+  sincos(lat, &slat, &clat);
+  sincos(lon, &slon, &clon);
+  const double rd = (kRE + alt) * clat;
+  const double x = rd * clon, y = rd * slon, z = (kRE + alt) * slat;
+  const double rx = cs * x - sn * y, ry = sn * x + cs * y;
+  x_out[i] = rx;
+  x_out[ld + i] = ry;
+  x_out[2 * ld + i] = z;
+  x_out[3 * ld + i] = -omega * ry;
+  x_out[4 * ld + i] = omega * rx;
+  x_out[5 * ld + i] = 0.0;
+}
+
+cudaError_t launch_frame_change(const double* x_in, double* x_out, int64_t n, int64_t ld,
+                                double angle, double omega, cudaStream_t stream) {
+  if (n <= 0) return cudaSuccess;
+  frame_change_kernel<<<(unsigned)((n + 127) / 128), 128, 0, stream>>>(x_in, x_out, n, ld, cos(angle),
+                                                                      sin(angle), omega);
+  return cudaGetLastError();
+}
+cudaError_t launch_coe2eci(const double* coe, double* x_out, int64_t n, int64_t ld, double mu,
+                           cudaStream_t stream) {
+  if (n <= 0) return cudaSuccess;
+  coe2eci_kernel<<<(unsigned)((n + 127) / 128), 128, 0, stream>>>(coe, x_out, n, ld, mu);
+  return cudaGetLastError();
+}
+cudaError_t launch_lla2eci(const double* lla, double* x_out, int64_t n, int64_t ld, double jd,
+                           cudaStream_t stream) {
+  if (n <= 0) return cudaSuccess;
+  const double ang = kOmegaEarth * jd;
+  lla2eci_kernel<<<(unsigned)((n + 127) / 128), 128, 0, stream>>>(lla, x_out, n, ld, cos(ang),
+                                                                 sin(ang), kOmegaEarth);
+  return cudaGetLastError();
+}
+
+}  // namespace pc

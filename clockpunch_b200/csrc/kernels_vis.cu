@@ -1,0 +1,161 @@
+// K3: Earth-occlusion visibility between every (sensor, target) pair.
+//
+// Reference: calcVisMap (punchclock/common/visibility.py:56-116) loops over all pairs and
+// calls satvis.isVis / satvis.visibilityFunc (satvis==0.2.4, not vendored: parity unpinned,
+// restated in oracle/visibility.py):
+//     V = acos(RE/|r1|) + acos(RE/|r2|) - acos(r1.r2 / (|r1||r2|)),   visible <=> V > 0.
+// Binary mode here uses the equivalent acos-free predicate
+//     r1.r2 > RE^2 - sqrt((|r1|^2 - RE^2)(|r2|^2 - RE^2))
+// (both sides are cos() of angles in [0, pi], where cos is monotone), which differs from
+// the acos form only inside |V| <~ 1e-9 rad of grazing.
+//
+// Mapping: sensors (position + horizon term q = sqrt(|r|^2 - RE^2)) are staged once per
+// CTA in shared memory; one thread owns one 32-bit output word = (target i, 32 sensors) of
+// the truth map and, when a second target set (the filter estimates) is given, of the
+// estimate map, so N * ceil(M/32) threads fill the machine even for small catalogs and the
+// packed words are written fully coalesced.  (The fused step kernel in kernels_ukf.cu packs
+// the same words with warp ballots, lanes = sensors.)
+#include "pc_common.cuh"
+
+namespace pc {
+
+// Horizon term of one agent with the reference's below-surface semantics:
+// |r| >= RE -> sqrt(|r|^2 - RE^2); RE - |r| <= tol -> 0 (clamped to the surface);
+// deeper -> NaN (acos(>1) in the reference: the pair is never visible).
+__device__ __forceinline__ double horizon_q(double x, double y, double z, double RE, double tol) {
+  const double rm = sqrt(fma(z, z, fma(y, y, x * x)));
+  if (rm >= RE) return sqrt((rm - RE) * (rm + RE));
+  if (RE - rm <= tol) return 0.0;
+  return __longlong_as_double(0x7ff8000000000000LL);
+}
+
+constexpr int kVisThreads = 128;
+constexpr int kSensTile = 1024;  // sensors staged per pass: 1024 * 32 B = 32 KB
+
+// One thread per output word: (target i, sensors 32w .. 32w+31), both maps.
+template <bool TWO>
+__global__ void __launch_bounds__(kVisThreads)
+vismap_packed_kernel(const double* __restrict__ sens, int64_t M, int64_t ld_s,
+                     const uint8_t* __restrict__ sens_kind, double cs, double sn,
+                     const double* __restrict__ ta, const double* __restrict__ tb, int64_t N,
+                     int64_t ld_t, double RE, double tol, uint32_t* __restrict__ out_a,
+                     uint32_t* __restrict__ out_b, int64_t wpr) {
+  __shared__ double4 tile[kSensTile];
+  const int64_t idx = (int64_t)blockIdx.x * kVisThreads + threadIdx.x;
+  const bool live = idx < N * wpr;
+  const int64_t i = live ? idx / wpr : 0;
+  const int64_t w = live ? idx - i * wpr : 0;
+  const double RE2 = RE * RE;
+
+  const double ax = ta[i], ay = ta[ld_t + i], az = ta[2 * ld_t + i];
+  const double aq = horizon_q(ax, ay, az, RE, tol);
+  double bx = 0, by = 0, bz = 0, bq = 0;
+  if (TWO) {
+    bx = tb[i];
+    by = tb[ld_t + i];
+    bz = tb[2 * ld_t + i];
+    bq = horizon_q(bx, by, bz, RE, tol);
+  }
+
+  uint32_t wa = 0, wb = 0;
+  for (int64_t j0 = 0; j0 < M; j0 += kSensTile) {
+    const int cnt = (int)min((int64_t)kSensTile, M - j0);
+    if (j0) __syncthreads();
+    for (int j = threadIdx.x; j < cnt; j += kVisThreads) {
+      double x = sens[j0 + j], y = sens[ld_s + j0 + j];
+      const double z = sens[2 * ld_s + j0 + j];
+      if (sens_kind && sens_kind[j0 + j] == PC_KIND_TERRESTRIAL) {  // fused K2: Earth-fixed rotation
+        const double xr = cs * x - sn * y;
+        y = sn * x + cs * y;
+        x = xr;
+      }
+      tile[j] = make_double4(x, y, z, horizon_q(x, y, z, RE, tol));
+    }
+    __syncthreads();
+    const int64_t s0 = w * 32 - j0;  // first sensor of this word, relative to the tile
+    if (live && s0 >= 0 && s0 < cnt) {
+      const int lim = min(32, cnt - (int)s0);
+#pragma unroll 4
+      for (int b = 0; b < lim; ++b) {
+        const double4 s = tile[s0 + b];
+        const double da = fma(s.z, az, fma(s.y, ay, s.x * ax));
+        wa |= (uint32_t)(da > fma(-s.w, aq, RE2)) << b;
+        if (TWO) {
+          const double db = fma(s.z, bz, fma(s.y, by, s.x * bx));
+          wb |= (uint32_t)(db > fma(-s.w, bq, RE2)) << b;
+        }
+      }
+    }
+  }
+  if (live) {
+    out_a[idx] = wa;
+    if (TWO) out_b[idx] = wb;
+  }
+}
+
+// Continuous visibility value (calcVisMap(binary=False) -> visibilityFunc(...)[0]).
+__global__ void __launch_bounds__(kVisThreads)
+vismap_value_kernel(const double* __restrict__ sens, int64_t M, int64_t ld_s,
+                    const double* __restrict__ targ, int64_t N, int64_t ld_t, double RE, double tol,
+                    double* __restrict__ out) {
+  const int64_t idx = (int64_t)blockIdx.x * kVisThreads + threadIdx.x;
+  if (idx >= N * M) return;
+  const int64_t i = idx / M, j = idx - i * M;
+  const double sx = sens[j], sy = sens[ld_s + j], sz = sens[2 * ld_s + j];
+  const double tx = targ[i], ty = targ[ld_t + i], tz = targ[2 * ld_t + i];
+  double m1 = sqrt(fma(sz, sz, fma(sy, sy, sx * sx)));
+  double m2 = sqrt(fma(tz, tz, fma(ty, ty, tx * tx)));
+  if (m1 < RE && RE - m1 <= tol) m1 = RE;
+  if (m2 < RE && RE - m2 <= tol) m2 = RE;
+  double c = fma(sz, tz, fma(sy, ty, sx * tx)) / (m1 * m2);
+  c = fmin(1.0, fmax(-1.0, c));
+  out[idx] = acos(RE / m1) + acos(RE / m2) - acos(c);
+}
+
+// Expand packed words to the reference's (N, M) int64 map (visibility.py:112-114).
+__global__ void __launch_bounds__(256)
+unpack_bits_kernel(const uint32_t* __restrict__ words, int64_t N, int64_t M, int64_t wpr,
+                   int64_t* __restrict__ out) {
+  const int64_t idx = (int64_t)blockIdx.x * 256 + threadIdx.x;
+  if (idx >= N * M) return;
+  const int64_t i = idx / M, j = idx - i * M;
+  out[idx] = (words[i * wpr + (j >> 5)] >> (j & 31)) & 1u;
+}
+
+cudaError_t launch_unpack_bits(const uint32_t* words, int64_t N, int64_t M, int64_t wpr,
+                               int64_t* out, cudaStream_t stream) {
+  const int64_t total = N * M;
+  if (total <= 0) return cudaSuccess;
+  unpack_bits_kernel<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(words, N, M, wpr, out);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_vismap_packed(const double* sens, int64_t M, int64_t ld_s,
+                                 const uint8_t* sens_kind, double rot_angle, const double* ta,
+                                 const double* tb, int64_t N, int64_t ld_t, double RE, double tol,
+                                 uint32_t* out_a, uint32_t* out_b, int64_t wpr,
+                                 cudaStream_t stream) {
+  if (N <= 0 || M <= 0) return cudaSuccess;
+  const unsigned blocks = (unsigned)((N * wpr + kVisThreads - 1) / kVisThreads);
+  const double cs = cos(rot_angle), sn = sin(rot_angle);
+  if (tb)
+    vismap_packed_kernel<true><<<blocks, kVisThreads, 0, stream>>>(
+        sens, M, ld_s, sens_kind, cs, sn, ta, tb, N, ld_t, RE, tol, out_a, out_b, wpr);
+  else
+    vismap_packed_kernel<false><<<blocks, kVisThreads, 0, stream>>>(
+        sens, M, ld_s, sens_kind, cs, sn, ta, nullptr, N, ld_t, RE, tol, out_a, nullptr, wpr);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_vismap_value(const double* sens, int64_t M, int64_t ld_s, const double* targ,
+                                int64_t N, int64_t ld_t, double RE, double tol, double* out,
+                                cudaStream_t stream) {
+  if (N <= 0 || M <= 0) return cudaSuccess;
+  const int64_t total = N * M;
+  const unsigned blocks = (unsigned)((total + kVisThreads - 1) / kVisThreads);
+  vismap_value_kernel<<<blocks, kVisThreads, 0, stream>>>(sens, M, ld_s, targ, N, ld_t, RE, tol,
+                                                         out);
+  return cudaGetLastError();
+}
+
+}  // namespace pc

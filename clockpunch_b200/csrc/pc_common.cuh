@@ -1,0 +1,42 @@
+// Shared definitions for libpunch_b200 (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/punch_b200.h"
+
+namespace pc {
+
+// Reference constants (punchclock/common/constants.py:21-27).  The reference
+// deliberately uses the low-precision values below; they are the spec.
+constexpr double kMu = 398600.0;
+constexpr double kRE = 6378.1363;
+constexpr double kOmegaEarth = 7.27e-5;
+// J2 is NOT in the reference (dynamics.py:16-40 is two-body only); opt-in.
+constexpr double kJ2 = 1.08262668e-3;
+
+// Auto-substep rule: fixed-step DOP853 substeps = ceil(|dt| * Omega / kTheta),
+// Omega = sqrt(mu / rp^3) (1 + e)^2 with rp, e from the osculating orbit.
+// kTheta is chosen so that the truncation error stays at the FP64 round-off
+// floor of the state (measured: DESIGN.md "integrator").
+constexpr double kTheta = 0.12;
+constexpr int kMaxAutoSubsteps = 1 << 16;
+
+struct UkfWeights {
+  double gamma;    // sqrt(n + lambda)                      ukf_v2.py:117
+  double wm0;      // lambda / (n + lambda)                 ukf_v2.py:120
+  double wi;       // 1 / (2 (n + lambda))                  ukf_v2.py:121
+  double wc0;      // wm0 + 1 - alpha^2 + beta              ukf_v2.py:128
+  double eps_w;    // (wm0 + 12 wi) - 1 evaluated exactly from the float64 weights
+};
+
+}  // namespace pc
+
+#define PC_CUDA_TRY(ctx, expr)                                        \
+  do {                                                                \
+    cudaError_t _e = (expr);                                          \
+    if (_e != cudaSuccess) return pc_fail_cuda((ctx), _e, #expr);     \
+  } while (0)
+
+int pc_fail(pc_ctx* ctx, int code, const char* msg);
+int pc_fail_cuda(pc_ctx* ctx, cudaError_t e, const char* what);

@@ -1,0 +1,179 @@
+"""Device-resident catalog engine: the batched form of SSAScheduler's physics step.
+
+One ``CatalogEngine`` holds M sensors and N targets (truth states, one 6-D UKF per
+target) in HBM and advances them with ``pc_step_fused``:
+
+    sensors propagate (K1/K2) -> targets truth + UKF (K4) -> both packed vis maps (K3)
+
+which is the arithmetic of SSAScheduler.step (punchclock/environment/env.py:533-597):
+_propagateAgents (:503), _taskAgents (:464), updateInfoPostTasking (:392).  PyTorch
+tensors are used only as device buffers (allocation, stream, copies); every kernel is in
+libpunch_b200.  Layouts are those of include/punch_b200.h: states (6, ld) SoA, covariances
+(N, 6, 6), vis maps bit-packed (N, ceil(M/32)) uint32.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import _buffers as B
+from . import _lib
+from .common.visibility import BINARY_TOL, unpack_vis_words
+
+RE = 6378.1363
+
+
+def _pad(n: int, mult: int = 16) -> int:
+    return max(mult, (n + mult - 1) // mult * mult)
+
+
+class CatalogEngine:
+    def __init__(self, sensor_states, sensor_kinds, target_states, est_x, est_p, Q, R, time: float = 0.0,
+                 device: int | None = None, substeps: int = 0, force_model: int = _lib.FORCE_TWOBODY,
+                 seed: int = 0, alpha: float = 0.001, beta: float = 2.0, kappa=None,
+                 body_radius: float = RE, vis_tol: float = BINARY_TOL,
+                 init_num_tasked=None, init_last_time_tasked=None):
+        torch = B.torch_mod()
+        self.ctx = _lib.get_ctx(device)
+        self.dev = B.device_of(self.ctx)
+        self.torch = torch
+        sensor_states = np.asarray(sensor_states, dtype=np.float64).reshape(6, -1)
+        target_states = np.asarray(target_states, dtype=np.float64).reshape(6, -1)
+        self.M, self.N = sensor_states.shape[1], target_states.shape[1]
+        self.ld_s, self.ld = _pad(self.M), _pad(self.N)
+        self.wpr = max(1, (self.M + 31) // 32)
+        self.time = float(time)
+        self.step_count = 0
+        self.substeps, self.force_model, self.seed = int(substeps), int(force_model), int(seed)
+        self.body_radius, self.vis_tol = float(body_radius), float(vis_tol)
+        self.params = _lib.make_ukf_params(Q, R, alpha, beta, kappa)
+        f64, dev = torch.float64, self.dev
+
+        def state_buf(a, ld):
+            t = torch.zeros((6, ld), dtype=f64, device=dev)
+            t[:, : a.shape[1]] = torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+            return t
+
+        self.sens_x = state_buf(sensor_states, self.ld_s)
+        self.sens_kind = torch.from_numpy(np.ascontiguousarray(sensor_kinds, dtype=np.uint8)).to(dev)
+        self.truth_x = state_buf(target_states, self.ld)
+        self.est_x = state_buf(np.asarray(est_x, dtype=np.float64).reshape(6, -1), self.ld)
+        self.est_p = torch.from_numpy(np.ascontiguousarray(est_p, dtype=np.float64).reshape(self.N, 36)).to(dev)
+        self.pred_p = self.est_p.clone()
+        self.nis = torch.full((self.N,), float("nan"), dtype=f64, device=dev)
+        self.flags = torch.zeros((self.N,), dtype=torch.int32, device=dev)
+        self.vis_truth = torch.zeros((self.N, self.wpr), dtype=torch.int32, device=dev)
+        self.vis_est = torch.zeros((self.N, self.wpr), dtype=torch.int32, device=dev)
+        self.tasked = torch.zeros((self.N,), dtype=torch.uint8, device=dev)
+        self.z = torch.zeros((6, self.ld), dtype=f64, device=dev)
+        nt = np.zeros(self.N, np.int64) if init_num_tasked is None else np.asarray(init_num_tasked, np.int64)
+        lt = np.zeros(self.N, np.float32) if init_last_time_tasked is None else np.asarray(init_last_time_tasked, np.float32)
+        self.num_tasked = torch.from_numpy(nt.copy()).to(dev)
+        self.last_time_tasked = torch.from_numpy(lt.copy()).to(dev)
+        self.tr_pos = torch.zeros((self.N,), dtype=torch.float32, device=dev)
+        self.tr_vel = torch.zeros((self.N,), dtype=torch.float32, device=dev)
+        self.actions = torch.zeros((max(1, self.M),), dtype=torch.int64, device=dev)
+        # float32 observation block (one contiguous buffer -> one D2H copy)
+        A = self.M + self.N
+        self._obs_sizes = (6 * A, 36 * self.N, self.N)
+        self.obs_f32 = torch.zeros((sum(self._obs_sizes),), dtype=torch.float32, device=dev)
+        self._args = _lib.StepArgs()
+        self._snapshot = None
+        self.compute_vis()
+        self.snapshot()
+
+    # -- helpers -----------------------------------------------------------
+    def _stream(self):
+        return self.torch.cuda.current_stream(self.dev).cuda_stream
+
+    def _fill_args(self, t0, tf, z, tasked, want_vis=True):
+        a = self._args
+        a.sens_x, a.sens_kind, a.M, a.ld_s = self.sens_x.data_ptr(), self.sens_kind.data_ptr(), self.M, self.ld_s
+        a.truth_x, a.est_x, a.est_p = self.truth_x.data_ptr(), self.est_x.data_ptr(), self.est_p.data_ptr()
+        a.z = None if z is None else z.data_ptr()
+        a.tasked = None if tasked is None else tasked.data_ptr()
+        a.N, a.ld, a.t0, a.tf = self.N, self.ld, float(t0), float(tf)
+        a.substeps, a.force_model = self.substeps, self.force_model
+        a.rng_seed, a.rng_step = self.seed, self.step_count
+        a.pred_p, a.nis, a.flags = self.pred_p.data_ptr(), self.nis.data_ptr(), self.flags.data_ptr()
+        a.vis_truth = self.vis_truth.data_ptr() if want_vis else None
+        a.vis_est = self.vis_est.data_ptr() if want_vis else None
+        a.words_per_row, a.body_radius, a.vis_tol = self.wpr, self.body_radius, self.vis_tol
+        a.num_tasked, a.last_time_tasked = self.num_tasked.data_ptr(), self.last_time_tasked.data_ptr()
+        a.tr_pos, a.tr_vel = self.tr_pos.data_ptr(), self.tr_vel.data_ptr()
+        return a
+
+    # -- physics -------------------------------------------------------------
+    def compute_vis(self):
+        """Both packed maps from the current states (reset path, env.py:212)."""
+        c = self.ctx
+        c.check(c.lib.pc_vismap_packed(c.handle, self.sens_x.data_ptr(), self.M, self.ld_s, None, 0.0,
+                                       self.truth_x.data_ptr(), self.est_x.data_ptr(), self.N, self.ld,
+                                       self.body_radius, self.vis_tol, self.vis_truth.data_ptr(),
+                                       self.vis_est.data_ptr(), self.wpr, self._stream()))
+
+    def task_from_actions(self, actions):
+        """(M,) MultiDiscrete actions (host or device) -> device tasking mask, masked by the
+        estimated visibility of the previous step (env.py:564-571)."""
+        if isinstance(actions, np.ndarray) or not hasattr(actions, "data_ptr"):
+            self.actions[: self.M].copy_(self.torch.from_numpy(np.ascontiguousarray(actions, dtype=np.int64)),
+                                         non_blocking=True)
+            actions = self.actions
+        c = self.ctx
+        c.check(c.lib.pc_task_from_actions(c.handle, actions.data_ptr(), self.M, self.vis_est.data_ptr(),
+                                           self.N, self.wpr, self.tasked.data_ptr(), self._stream()))
+        return self.tasked
+
+    def step(self, t_next: float | None = None, tasked=None, z=None, dt: float | None = None):
+        """Advance every agent to t_next.  tasked: (N,) uint8 device tensor / numpy bool or None;
+        z: (6,N) measurements (numpy or (6,ld) device tensor) or None -> drawn on device."""
+        if t_next is None:
+            t_next = self.time + float(dt)
+        if tasked is not None and not hasattr(tasked, "data_ptr"):
+            self.tasked.copy_(self.torch.from_numpy(np.ascontiguousarray(tasked, dtype=np.uint8)))
+            tasked = self.tasked
+        if z is not None and not hasattr(z, "data_ptr"):
+            self.z[:, : self.N].copy_(self.torch.from_numpy(np.ascontiguousarray(z, dtype=np.float64)))
+            z = self.z
+        a = self._fill_args(self.time, t_next, z, tasked)
+        c = self.ctx
+        c.check(c.lib.pc_step_fused(c.handle, C.byref(a), C.byref(self.params), self._stream()))
+        self.time = float(t_next)
+        self.step_count += 1
+
+    def pack_obs(self):
+        """float32 eci_state / est_cov / obs_staleness into self.obs_f32 (device)."""
+        c = self.ctx
+        n0, n1, _ = self._obs_sizes
+        base = self.obs_f32.data_ptr()
+        c.check(c.lib.pc_obs_pack(c.handle, self.sens_x.data_ptr(), self.M, self.ld_s, self.est_x.data_ptr(),
+                                  self.est_p.data_ptr(), self.N, self.ld, self.last_time_tasked.data_ptr(),
+                                  self.time, base, base + 4 * n0, base + 4 * (n0 + n1), self._stream()))
+        return self.obs_f32
+
+    # -- reset snapshot (env.py:142,208: deepcopy of the agent list) ---------------
+    _STATE = ("sens_x", "truth_x", "est_x", "est_p", "pred_p", "nis", "flags", "vis_truth", "vis_est",
+              "num_tasked", "last_time_tasked", "tr_pos", "tr_vel")
+
+    def snapshot(self):
+        self._snapshot = ({k: getattr(self, k).clone() for k in self._STATE}, self.time, self.step_count)
+
+    def reset(self):
+        bufs, t, sc = self._snapshot
+        for k, v in bufs.items():
+            getattr(self, k).copy_(v)
+        self.time, self.step_count = t, sc
+
+    # -- host views --------------------------------------------------------------
+    def host(self, name: str) -> np.ndarray:
+        t = getattr(self, name)
+        if name in ("sens_x",):
+            return t[:, : self.M].cpu().numpy()
+        if name in ("truth_x", "est_x", "z"):
+            return t[:, : self.N].cpu().numpy()
+        if name in ("est_p", "pred_p"):
+            return t.cpu().numpy().reshape(self.N, 6, 6)
+        if name in ("vis_truth", "vis_est"):
+            return unpack_vis_words(t.cpu().numpy().view(np.uint32), self.M)
+        return t.cpu().numpy()

@@ -1,0 +1,215 @@
+/* libpunch_b200 -- C-ABI of the B200-native punchclock hot path.
+ *
+ * The reference (punchclock v0.8.5) is pure Python and has no FFI layer; its
+ * boundary for this path is the Python module API.  Each entry
+ * point below names the reference function(s) whose arithmetic it replaces; the
+ * Python mirror in clockpunch_b200/ binds them with ctypes.
+ *
+ * Conventions
+ *   - All arithmetic is FP64.  State arrays are structure-of-arrays `(6, ld)`
+ *     row-major (component c of agent i at `x[c*ld + i]`), i.e. exactly a C-order
+ *     numpy `(6, N)` array when ld == N.  Covariances are `(N, 6, 6)` row-major
+ *     (`p[i*36 + a*6 + b]`), exactly the reference's `est_cov` layout.
+ *   - Pointers are DEVICE pointers unless the function name ends in `_host`.
+ *     The library never frees or retains caller arrays past the call.
+ *   - Every call is asynchronous on `stream` (a cudaStream_t; NULL = legacy
+ *     default stream); `_host` variants synchronise before returning.
+ *   - Return value: 0 = OK, < 0 = pc_status.  `pc_last_error(ctx)` gives text.
+ *   - Per-target numerical trouble (non-PD covariance, NaN) is DATA, reported
+ *     in `out_flags`, never an error code.
+ */
+#ifndef PUNCH_B200_H
+#define PUNCH_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct pc_ctx pc_ctx;
+typedef void* pc_stream; /* cudaStream_t */
+
+enum pc_status {
+  PC_OK = 0,
+  PC_ERR_BAD_ARG = -1,
+  PC_ERR_CUDA = -2,
+  PC_ERR_EQUAL_TIMES = -3, /* t0 == tf: reference raises ValueError (propagator.py:40-41) */
+  PC_ERR_NO_DEVICE = -4
+};
+
+enum pc_agent_kind { PC_KIND_SATELLITE = 0, PC_KIND_TERRESTRIAL = 1 };
+enum pc_force_model { PC_FORCE_TWOBODY = 0, PC_FORCE_TWOBODY_J2 = 1 };
+
+enum pc_flag_bits {
+  PC_FLAG_NONPD_EST = 1,     /* cholesky(est_p) failed   (reference: nearestPD fallback, ukf_v2.py:170-176) */
+  PC_FLAG_NONPD_PRED = 2,    /* cholesky(pred_p) failed in the measurement update */
+  PC_FLAG_NONPD_INNOV = 4,   /* innovation covariance not PD */
+  PC_FLAG_NONFINITE = 8,     /* NaN/Inf in an output of this target */
+  PC_FLAG_SUBSTEP_CLAMP = 16 /* auto substep count hit the clamp */
+};
+
+/* UKF constants, evaluated by the caller in the reference's own float64
+ * operation order (ukf_v2.py:113-128) so that the weights are bit-identical. */
+typedef struct pc_ukf_params {
+  double gamma;   /* sqrt(n + lambda) */
+  double wm0;     /* mean weight of the centre point */
+  double wi;      /* weight of the other 2n points */
+  double wc0;     /* covariance weight of the centre point */
+  double eps_w;   /* (wm0 + 2n*wi) - 1, exact value for the float64 weights above */
+  double Q[36];   /* process noise   (ukf_v2.py:291) */
+  double R[36];   /* measurement noise (ukf_v2.py:328) */
+  double Lr[36];  /* lower Cholesky factor of R; only used to draw z on device */
+} pc_ukf_params;
+
+/* ---- lifetime -------------------------------------------------------- */
+int pc_version(void);
+int pc_ctx_create(int device_ordinal, pc_ctx** out);
+int pc_ctx_destroy(pc_ctx* ctx);
+const char* pc_last_error(pc_ctx* ctx);
+/* number of kernels this ctx has launched since creation (bench.py: gpu_launches) */
+int64_t pc_launch_count(pc_ctx* ctx);
+
+/* ---- K1: propagation -------------------------------------------------
+ * pc_propagate_twobody   replaces SatDynamicsModel.propagate / simplePropagate(satelliteDynamics)
+ *                        (dynamics_classes.py:51-76, propagator.py:12-81, dynamics.py:16-40,71-86)
+ * pc_rotate_terrestrial  replaces StaticTerrestrial.propagate (dynamics_classes.py:79-121,
+ *                        dynamics.py:43-68, transforms.py:55-129)
+ * pc_propagate_agents    both, selected per agent by kind[] (Agent.propagate, agents.py:59-71;
+ *                        SSAScheduler._propagateAgents, env.py:503-506)
+ * substeps: >0 fixed number of DOP853 steps per call; 0 = choose per state
+ * from its osculating orbit.  x_out may alias x_in. */
+int pc_propagate_twobody(pc_ctx* ctx, const double* x_in, double* x_out, int64_t n, int64_t ld,
+                         double t0, double tf, int substeps, int force_model, pc_stream stream);
+int pc_rotate_terrestrial(pc_ctx* ctx, const double* x_in, double* x_out, int64_t n, int64_t ld,
+                          double t0, double tf, pc_stream stream);
+int pc_propagate_agents(pc_ctx* ctx, const double* x_in, double* x_out, const uint8_t* kind,
+                        int64_t n, int64_t ld, double t0, double tf, int substeps,
+                        int force_model, pc_stream stream);
+int pc_propagate_agents_host(pc_ctx* ctx, const double* h_x_in, double* h_x_out,
+                             const uint8_t* h_kind, int64_t n, int64_t ld, double t0, double tf,
+                             int substeps, int force_model);
+
+/* ---- frames and initial conditions -------------------------------------
+ * pc_frame_change replaces ecef2eci (to_eci != 0) / eci2ecef (to_eci == 0)
+ *                 (common/transforms.py:55-129,143-178); jd = seconds since the frames were aligned.
+ * pc_coe2eci      replaces coe2eci (transforms.py:240-292); coe is (6, ld) rows
+ *                 [sma, ecc, inc, raan, argp, true_anom].  Range checks (ValueError in the
+ *                 reference, transforms.py:268-279) are done by the caller.
+ * pc_lla2eci      replaces ecef2eci(lla2ecef(x), jd) (transforms.py:34-52; the ground-sensor
+ *                 IC path of genInitStates, simulation/sim_utils.py:96-101); lla is (3, ld). */
+int pc_frame_change(pc_ctx* ctx, const double* x_in, double* x_out, int64_t n, int64_t ld,
+                    double jd, int to_eci, pc_stream stream);
+int pc_coe2eci(pc_ctx* ctx, const double* coe, double* x_out, int64_t n, int64_t ld, double mu,
+               pc_stream stream);
+int pc_lla2eci(pc_ctx* ctx, const double* lla, double* x_out, int64_t n, int64_t ld, double jd,
+               pc_stream stream);
+
+/* ---- K3: visibility ----------------------------------------------------
+ * pc_vismap_packed replaces calcVisMap(binary=True) (common/visibility.py:56-116) and the two
+ * calls per step in updateInfoPostTasking (env.py:455-462).  Output is bit-packed:
+ * bit (j % 32) of word out[i*words_per_row + j/32] is 1 iff sensor j sees target i.
+ * targ_b / out_b may be NULL; when given, a second map (e.g. estimated states) is
+ * produced in the same pass.  Sensors with sens_kind[j] == PC_KIND_TERRESTRIAL are
+ * rotated about +z by sens_rot_angle while the sensor tile is staged (fused K2);
+ * pass sens_kind = NULL for "use as given".
+ * pc_vismap_value replaces calcVisMap(binary=False): out is (N, M) float64. */
+int pc_vismap_packed(pc_ctx* ctx, const double* sens, int64_t M, int64_t ld_s,
+                     const uint8_t* sens_kind, double sens_rot_angle, const double* targ_a,
+                     const double* targ_b, int64_t N, int64_t ld_t, double body_radius, double tol,
+                     uint32_t* out_a, uint32_t* out_b, int64_t words_per_row, pc_stream stream);
+int pc_vismap_value(pc_ctx* ctx, const double* sens, int64_t M, int64_t ld_s, const double* targ,
+                    int64_t N, int64_t ld_t, double body_radius, double tol, double* out,
+                    pc_stream stream);
+/* Host-buffer variant behind calcVisMap(): binary != 0 writes int64 (N, M) into out_i64,
+ * otherwise float64 (N, M) into out_f64. */
+int pc_vismap_host(pc_ctx* ctx, const double* h_sens, int64_t M, const double* h_targ, int64_t N,
+                   double body_radius, double tol, int binary, int64_t* out_i64, double* out_f64);
+
+/* ---- K4: UKF predict + update -------------------------------------------
+ * Replaces UnscentedKalmanFilter.predictAndUpdate for the 6-D identity-measurement
+ * filter built by ezUKF (ukf_v2.py:185-375, ez_ukf.py:17-95), one filter per target.
+ * If truth_x != NULL the target's truth state is propagated in the same launch
+ * (Agent.propagate, agents.py:59-71).  tasked[i] != 0 selects the measurement update;
+ * the measurement is z[:, i] when z != NULL, else truth' + Lr * N(0, I) drawn with
+ * Philox(rng_seed, rng_step, i) (Target.getMeasurement, agents.py:173-183; distributional
+ * parity only -- the reference draws from numpy's legacy global RNG). */
+int pc_ukf_predict_update(pc_ctx* ctx, double* est_x, double* est_p, double* truth_x,
+                          const double* z, const uint8_t* tasked, int64_t n, int64_t ld, double t0,
+                          double tf, int substeps, int force_model, const pc_ukf_params* params,
+                          uint64_t rng_seed, uint64_t rng_step, double* out_pred_x,
+                          double* out_pred_p, double* out_nis, uint32_t* out_flags,
+                          double* out_z, pc_stream stream);
+int pc_ukf_predict_update_host(pc_ctx* ctx, double* h_est_x, double* h_est_p, const double* h_z,
+                               const uint8_t* h_tasked, int64_t n, double t0, double tf,
+                               int substeps, int force_model, const pc_ukf_params* params,
+                               double* h_pred_x, double* h_pred_p, double* h_nis,
+                               uint32_t* h_flags);
+
+/* ---- scheduler glue on the packed maps -----------------------------------
+ * pc_task_from_actions replaces actionSpace2Array (common/utilities.py:147-172) + the masking
+ *   loop of SSAScheduler._taskAgents (env.py:487-501): tasked[i] = 1 iff some sensor j has
+ *   actions[j] == i and bit (i, j) of the ESTIMATED vis map is set (actions[j] == N: inaction).
+ * pc_obs_pack writes the float32 observation arrays of SSAScheduler._getObs: eci_state
+ *   (6, M+N) = [sensor truth | target estimates] (env.py:508-530), est_cov (N, 6, 6)
+ *   (env.py:419-429), obs_staleness (N) = t_now - last_time_tasked (env.py:446-452). */
+int pc_task_from_actions(pc_ctx* ctx, const int64_t* actions, int64_t M, const uint32_t* vis_est,
+                         int64_t N, int64_t words_per_row, uint8_t* tasked, pc_stream stream);
+int pc_obs_pack(pc_ctx* ctx, const double* sens_x, int64_t M, int64_t ld_s, const double* est_x,
+                const double* est_p, int64_t N, int64_t ld, const float* last_time_tasked,
+                double t_now, float* out_eci, float* out_cov, float* out_stale, pc_stream stream);
+
+/* Benchmark stand-in policy: each sensor takes the first of `probes` random
+ * targets that its column of the estimated map shows visible, else inaction (N). */
+int pc_policy_random_visible(pc_ctx* ctx, const uint32_t* vis_est, int64_t N, int64_t M,
+                             int64_t words_per_row, uint64_t seed, uint64_t step, int probes,
+                             int64_t* actions, pc_stream stream);
+
+/* ---- measurement helpers (bench.py) ------------------------------------
+ * pc_set_timing(1) makes pc_step_fused bracket its UKF kernel with CUDA events on the launch
+ * stream; pc_get_timing sums them (synchronises).  pc_fp64_peak runs a register-resident DFMA
+ * probe and returns the best TFLOP/s of `repeats` launches: the FP64 roofline denominator. */
+int pc_set_timing(pc_ctx* ctx, int enabled);
+int pc_get_timing(pc_ctx* ctx, double* ukf_ms_total, int64_t* launches);
+int pc_fp64_peak(pc_ctx* ctx, int repeats, double* tflops);
+
+/* ---- fused step ---------------------------------------------------------
+ * One SSAScheduler physics step (env.py:533-597 minus host bookkeeping): sensors
+ * propagated (kind per sensor), targets' truth + UKF, both packed vis maps, and the
+ * per-target scheduler summaries.  All pointers device; see pc_step_args. */
+typedef struct pc_step_args {
+  /* sensors */
+  double* sens_x;            /* (6, ld_s) in/out */
+  const uint8_t* sens_kind;  /* (M) */
+  int64_t M, ld_s;
+  /* targets */
+  double* truth_x;           /* (6, ld) in/out */
+  double* est_x;             /* (6, ld) in/out */
+  double* est_p;             /* (N, 36) in/out */
+  const double* z;           /* (6, ld) or NULL -> drawn on device */
+  const uint8_t* tasked;     /* (N) or NULL */
+  int64_t N, ld;
+  double t0, tf;
+  int substeps, force_model;
+  uint64_t rng_seed, rng_step;
+  /* outputs */
+  double* pred_p;            /* (N, 36) or NULL */
+  double* nis;               /* (N) or NULL */
+  uint32_t* flags;           /* (N) or NULL */
+  uint32_t* vis_truth;       /* (N, words_per_row) */
+  uint32_t* vis_est;         /* (N, words_per_row) */
+  int64_t words_per_row;
+  double body_radius, vis_tol;
+  /* scheduler summaries (Target.updateNonPhysical agents.py:144-171, env.py:437-452,599-609) */
+  int64_t* num_tasked;       /* (N) in/out or NULL */
+  float* last_time_tasked;   /* (N) in/out or NULL */
+  float* tr_pos;             /* (N) trace est_p[:3,:3] or NULL */
+  float* tr_vel;             /* (N) trace est_p[3:,3:] or NULL */
+} pc_step_args;
+int pc_step_fused(pc_ctx* ctx, const pc_step_args* args, const pc_ukf_params* params,
+                  pc_stream stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PUNCH_B200_H */

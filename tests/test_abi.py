@@ -1,0 +1,113 @@
+"""CPU-side checks of the drop-in boundary: the C-ABI library builds, loads and exports
+every symbol include/punch_b200.h declares; host-side argument logic; no CPU fallback."""
+import os
+import re
+
+import numpy as np
+import pytest
+
+import clockpunch_b200 as cpb
+from clockpunch_b200 import _lib, build
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def lib():
+    build.build()
+    return _lib.load_library()
+
+
+def test_header_symbols_exported(lib):
+    hdr = open(os.path.join(ROOT, "include", "punch_b200.h")).read()
+    declared = set(re.findall(r"^\s*(?:int|int64_t|const char\*)\s+(pc_\w+)\s*\(", hdr, flags=re.M))
+    assert len(declared) >= 20
+    for name in declared:
+        assert hasattr(lib, name), f"{name} declared in punch_b200.h but not exported"
+    assert declared == set(_lib.EXPORTED_SYMBOLS), declared ^ set(_lib.EXPORTED_SYMBOLS)
+    assert lib.pc_version() == 100
+
+
+def test_struct_layouts_match_header():
+    """ctypes mirrors vs the C structs, measured by compiling the header with the host compiler."""
+    import ctypes as C
+    import subprocess
+    import tempfile
+    src = ('#include "%s"\n#include <cstdio>\n#include <cstddef>\nint main(){printf("%%zu %%zu %%zu %%zu %%zu %%zu",'
+           'sizeof(pc_step_args), sizeof(pc_ukf_params), offsetof(pc_step_args, rng_seed),'
+           'offsetof(pc_step_args, words_per_row), offsetof(pc_step_args, tr_vel), offsetof(pc_ukf_params, R));}'
+           % os.path.join(ROOT, "include", "punch_b200.h"))
+    with tempfile.TemporaryDirectory() as d:
+        cpp, exe = os.path.join(d, "a.cpp"), os.path.join(d, "a.out")
+        open(cpp, "w").write(src)
+        subprocess.check_call(["g++", cpp, "-o", exe])
+        got = [int(v) for v in subprocess.check_output([exe]).split()]
+    S, U = _lib.StepArgs, _lib.UkfParams
+    assert got == [C.sizeof(S), C.sizeof(U), S.rng_seed.offset, S.words_per_row.offset, S.tr_vel.offset,
+                   U.R.offset]
+
+
+def test_reference_weights_bit_exact(golden):
+    g = golden("ukf")
+    gamma, wm0, wi, wc0, eps = _lib.reference_ukf_weights()
+    assert gamma == float(g["w_gamma"])
+    assert wm0 == g["w_mean"][0] and wi == g["w_mean"][1] and wc0 == g["w_cvr_diag"][0]
+    assert abs(eps) < 1e-9 and eps != 0.0
+    p = _lib.make_ukf_params(np.eye(6), 4 * np.eye(6))
+    assert p.Lr[0] == 2.0 and p.Lr[1] == 0.0 and p.Q[35] == 1.0
+
+
+@pytest.mark.skipif(__import__("torch").cuda.is_available(), reason="CPU-only check")
+def test_no_cpu_fallback():
+    """Without a GPU every physics entry point must raise, never compute on the host."""
+    from clockpunch_b200.common.visibility import calcVisMap
+    from clockpunch_b200.dynamics.dynamics_classes import SatDynamicsModel
+    with pytest.raises(_lib.PunchError):
+        SatDynamicsModel().propagate(np.array([7000.0, 0, 0, 0, 7.5, 0]), 0, 10)
+    with pytest.raises(_lib.PunchError):
+        calcVisMap(np.ones((6, 2)) * 7000, np.ones((6, 3)) * 8000)
+
+
+def test_argument_errors_before_device():
+    from clockpunch_b200.common.transforms import coe2eci, ecef2eci
+    from clockpunch_b200.common.visibility import calcVisMap
+    from clockpunch_b200.dynamics.propagator import simplePropagate
+    from clockpunch_b200.dynamics.dynamics import satelliteDynamics
+    with pytest.raises(ValueError):
+        simplePropagate(satelliteDynamics, np.zeros(6), 1.0, 1.0)
+    with pytest.raises(NotImplementedError):
+        simplePropagate(lambda t, x: x, np.zeros(6), 0.0, 1.0)
+    with pytest.raises(ValueError):
+        calcVisMap(np.zeros((5, 2)), np.zeros((6, 2)))
+    with pytest.raises(ValueError):
+        ecef2eci(np.zeros((5, 3)))
+    with pytest.raises(ValueError):
+        coe2eci(6000.0, 0, 0, 0, 0, 0)
+
+
+def test_catalog_synthesis_matches_oracle_transforms():
+    from clockpunch_b200.simulation.catalog import coe_to_eci, lla_to_eci, synth_catalog
+    from oracle import dynamics as od
+    rng = np.random.default_rng(1)
+    coe = np.stack([rng.uniform(7000, 42000, 8), rng.uniform(0, 0.7, 8), rng.uniform(0, np.pi, 8),
+                    *rng.uniform(0, 2 * np.pi, (3, 8))])
+    got = coe_to_eci(coe)
+    for i in range(8):
+        np.testing.assert_allclose(got[:, i], od.coe2eci(*coe[:, i]), rtol=1e-14, atol=1e-11)
+    lla = np.stack([rng.uniform(-1.5, 1.5, 5), rng.uniform(-3, 3, 5), np.full(5, 1e-6)])
+    got = lla_to_eci(lla, 50.0)
+    for i in range(5):
+        np.testing.assert_allclose(got[:, i], od.ecef2eci(od.lla2ecef(lla[:, i]), 50.0), rtol=1e-14, atol=1e-11)
+    cat = synth_catalog(100, 7, seed=3)
+    assert cat.targets.shape == (6, 100) and cat.sensors.shape == (6, 7) and cat.est_p.shape == (100, 6, 6)
+    r = np.linalg.norm(cat.targets[:3], axis=0)
+    assert r.min() > 6378.1363 + 300 and set(np.unique(cat.regime)) <= {0, 1, 2}
+    cat2 = synth_catalog(100, 7, seed=3)
+    np.testing.assert_array_equal(cat.targets, cat2.targets)
+
+
+def test_install_as_punchclock():
+    cpb.install_as_punchclock()
+    import punchclock.dynamics.dynamics_classes as dc
+    from punchclock.estimation.ez_ukf import ezUKF  # noqa: F401
+    assert dc.SatDynamicsModel.__module__.startswith("clockpunch_b200")

@@ -1,0 +1,351 @@
+"""Parity of the CUDA path (through the C-ABI) against the oracle and the golden vectors
+from the live reference.  Tolerances are the ones SURVEY.md section 8d / BASELINE.md state:
+truth states <= 1e-9 km, vis bits identical outside |V| <= 1e-9 rad, est_p / pred_p <= 1e-8
+max-relative and est_x <= 1e-5 km after one step with the same injected measurement."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+POS_TOL = 1e-9      # km
+VEL_TOL = 1e-11     # km/s
+COV_RTOL = 1e-8
+ESTX_TOL = 1e-5     # km (and km/s, looser than needed for velocity)
+GRAZE = 1e-9        # rad
+
+
+def relmax(a, b):
+    return np.max(np.abs(a - b)) / np.max(np.abs(b))
+
+
+def cov_close(a, b, rtol=COV_RTOL):
+    scale = np.sqrt(np.abs(np.einsum("...ii,...jj->...ij", b, b)))     # sqrt(b_ii b_jj)
+    return np.max(np.abs(a - b) / scale) <= rtol
+
+
+@pytest.fixture(scope="module")
+def dyn():
+    from clockpunch_b200.dynamics.dynamics_classes import SatDynamicsModel, StaticTerrestrial
+    return SatDynamicsModel(), StaticTerrestrial()
+
+
+def test_propagate_golden(golden, dyn):
+    sat, _ = dyn
+    g = golden("propagate")
+    out = sat.propagate(g["single_x0"], 0, 5)
+    assert out.shape == (6,)
+    assert np.abs(out - g["single_out"])[:3].max() <= POS_TOL and np.abs(out - g["single_out"])[3:].max() <= VEL_TOL
+    x0 = g["cat_x0"]
+    for key, t0, tf in (("cat_dt60", 0.0, 60.0), ("cat_dt100", 0.0, 100.0), ("cat_dt600", 0.0, 600.0),
+                        ("cat_back", 100.0, 40.0)):
+        out = sat.propagate(x0, t0, tf)
+        assert out.shape == x0.shape
+        err = np.abs(out - g[key])
+        assert err[:3].max() <= POS_TOL, (key, err[:3].max())
+        assert err[3:].max() <= VEL_TOL, (key, err[3:].max())
+    assert sat.propagate(x0[:, :1], 0.0, 60.0).shape == (6,)
+    with pytest.raises(ValueError):
+        sat.propagate(x0, 5.0, 5.0)
+    # 49-step chain of the reference's test_dynamics_classes.py:143-149
+    ts, xs = g["chain_t"], g["chain_x"]
+    y = xs[:, 0]
+    for k in range(1, len(ts)):
+        y = sat.propagate(y, ts[k - 1], ts[k])
+    assert np.abs(y - xs[:, -1])[:3].max() <= 5e-9      # 48 chained calls: both sides accumulate
+
+
+def test_propagate_substep_override_and_j2(dyn):
+    from clockpunch_b200.dynamics.propagator import propagate_batch
+    from clockpunch_b200 import _lib
+    from oracle.dynamics import propagate_satellite
+    x = np.array([[7000.0, 100.0, 50.0, 0.1, 7.4, 1.0]]).T
+    ref = propagate_satellite(x[:, 0], 0.0, 300.0)
+    for ns in (0, 3, 8):
+        out = propagate_batch(x, 0.0, 300.0, substeps=ns)[:, 0]
+        assert np.abs(out - ref)[:3].max() <= POS_TOL
+    # J2 is an opt-in extension with no reference counterpart: check against scipy DOP853
+    from scipy.integrate import solve_ivp
+    MU, RE, J2 = 398600.0, 6378.1363, 1.08262668e-3
+
+    def rhs(t, s):
+        r = s[:3]; rm = np.linalg.norm(r); z2 = 5 * r[2] ** 2 / rm**2
+        k = 1.5 * J2 * (RE / rm) ** 2
+        a = -MU * r / rm**3 * (1 + k * np.array([1 - z2, 1 - z2, 3 - z2]))
+        return np.r_[s[3:], a]
+    sol = solve_ivp(rhs, [0, 300.0], x[:, 0], method="DOP853", rtol=1e-12, atol=1e-12)
+    out = propagate_batch(x, 0.0, 300.0, force_model=_lib.FORCE_TWOBODY_J2)[:, 0]
+    assert np.abs(out - sol.y[:, -1])[:3].max() <= 1e-8
+    assert np.abs(out - ref)[:3].max() > 1e-3           # J2 really is on
+
+
+def test_transforms_golden(golden, dyn):
+    from clockpunch_b200.common import transforms as T
+    _, ter = dyn
+    g = golden("transforms")
+    for i in range(10):
+        np.testing.assert_allclose(T.lla2ecef(g["lla"][:, i]), g["lla_ecef"][:, i], rtol=0, atol=1e-11)
+    for tag, jd in ((0, 0.0), (1234, 1234.5), (259200, 259200.0)):
+        np.testing.assert_allclose(T.ecef2eci(g["x"], jd), g[f"ecef2eci_{tag}"], rtol=0, atol=2e-11)
+        np.testing.assert_allclose(T.eci2ecef(g["x"], jd), g[f"eci2ecef_{tag}"], rtol=0, atol=2e-11)
+    assert T.ecef2eci(g["x"][:, :1], 3.0).shape == (6,)
+    np.testing.assert_allclose(ter.propagate(g["ter_x0"], 0.0, 100.0), g["ter_dt100"], rtol=0, atol=1e-11)
+    np.testing.assert_allclose(ter.propagate(ter.propagate(g["ter_x0"], 0.0, 100.0), 100.0, 4000.0),
+                               g["ter_chain"], rtol=0, atol=1e-11)
+    np.testing.assert_allclose(ter.propagate(g["ter_x0"][:, 0], 50.0, 110.0), g["ter_single"], rtol=0, atol=1e-11)
+    for i in range(16):
+        np.testing.assert_allclose(T.coe2eci(*g["coe"][:, i]), g["coe_eci"][:, i], rtol=1e-14, atol=1e-10)
+    np.testing.assert_allclose(T.coe2eci_batch(g["coe"]), g["coe_eci"], rtol=1e-14, atol=1e-10)
+
+
+def _v_values(sens, targ, RE=6378.1363):
+    from oracle.visibility import visibility_func
+    return np.array([[visibility_func(sens[:3, j], targ[:3, i], RE)[0] for j in range(sens.shape[1])]
+                     for i in range(targ.shape[1])])
+
+
+def test_vismap_known_answer_and_oracle():
+    from clockpunch_b200.common.visibility import calcVisMap
+    from clockpunch_b200.simulation.catalog import synth_catalog
+    from oracle.visibility import calc_vis_map
+    RE = 6378.1363
+    sens = np.zeros((6, 3)); sens[0] = [RE, RE + 1, RE + 2]
+    targ = np.zeros((6, 4)); targ[0] = [RE + 400, -RE - 500, RE + 600, RE + 700]
+    vm = calcVisMap(sens, targ)
+    assert vm.shape == (4, 3) and vm.dtype == np.int64
+    np.testing.assert_array_equal(vm, [[1, 1, 1], [0, 0, 0], [1, 1, 1], [1, 1, 1]])   # test_env.py:132-136
+    # ragged sizes around the 32-sensor word boundary and the 128-thread CTA boundary
+    for (n, m, seed) in ((1, 1, 1), (5, 31, 2), (7, 32, 3), (33, 33, 4), (130, 65, 5), (257, 100, 6)):
+        cat = synth_catalog(n, m, seed=seed, space_sensor_frac=0.3)
+        got = calcVisMap(cat.sensors, cat.targets)
+        want = calc_vis_map(cat.sensors, cat.targets)
+        V = _v_values(cat.sensors, cat.targets)
+        bad = (got != want) & (np.abs(V) > GRAZE)
+        assert not bad.any(), (n, m, int(bad.sum()))
+        cont = calcVisMap(cat.sensors, cat.targets, binary=False)
+        assert cont.dtype == np.float64 and cont.shape == (n, m)
+        np.testing.assert_allclose(cont, calc_vis_map(cat.sensors, cat.targets, binary=False), rtol=0, atol=1e-12)
+    # 1-D inputs and below-surface agents
+    one = calcVisMap(sens[:, 0], targ[:, 0])
+    assert one.shape == (1, 1) and one[0, 0] == 1
+    under = targ.copy(); under[0, 0] = RE - 5.0
+    assert calcVisMap(sens, under)[0].sum() == 0
+    assert np.isnan(calcVisMap(sens, under, binary=False)[0]).all()
+
+
+def _golden_step_inputs(g, mode, dt):
+    key = f"cat_{mode}_dt{dt}"
+    est_x, est_p, pred_p = g[key + "_est_x"], g[key + "_est_p"], g[key + "_pred_p"]
+    z, nis = g[key + "_z"], g[key + "_nis"]
+    return est_x, est_p, pred_p, z, nis
+
+
+def test_ukf_one_step_golden(golden):
+    """Every stored step of the reference rollouts, restarted from the reference's own
+    previous state: 16 targets (LEO/MEO/GEO/HEO) x 4 steps x {tasked, untasked, mixed}."""
+    from clockpunch_b200 import _lib
+    from clockpunch_b200.estimation.ukf_v2 import ukf_batch_host
+    g = golden("ukf")
+    params = _lib.make_ukf_params(g["cat_Q"], g["cat_R"])
+    worst = dict(est_x=0.0, est_p=0.0, pred_p=0.0)
+    for mode in ("tasked", "untasked", "mixed"):
+        for dt in (60, 100):
+            est_x, est_p, pred_p, z, nis = _golden_step_inputs(g, mode, dt)
+            nt, ns = est_x.shape[:2]
+            for s in range(ns):
+                x_in = g["cat_est0"] if s == 0 else est_x[:, s - 1].T
+                p_in = np.broadcast_to(g["cat_P0"], (nt, 6, 6)) if s == 0 else est_p[:, s - 1]
+                tasked = ~np.isnan(z[:, s, 0])
+                zz = np.where(np.isnan(z[:, s]), 0.0, z[:, s]).T
+                out = ukf_batch_host(x_in, p_in, zz, tasked, s * float(dt), (s + 1) * float(dt), params)
+                assert (out["flags"] == 0).all()
+                assert cov_close(out["pred_p"], pred_p[:, s]), (mode, dt, s)
+                assert cov_close(out["est_p"], est_p[:, s]), (mode, dt, s)
+                ex = np.abs(out["est_x"].T - est_x[:, s]).max()
+                assert ex <= ESTX_TOL, (mode, dt, s, ex)
+                np.testing.assert_allclose(out["nis"][tasked], nis[tasked, s], rtol=1e-6)
+                assert np.isnan(out["nis"][~tasked]).all()
+                worst["est_x"] = max(worst["est_x"], ex)
+    print("worst est_x deviation [km]:", worst["est_x"])
+
+
+def test_ukf_object_api_golden(golden):
+    """The reference's own scenarios through the mirrored class API
+    (tests/estimation/test_ez_ukf.py:25-40, test_ukf_v2.py:254-313,408-478)."""
+    from clockpunch_b200.dynamics.dynamics_classes import SatDynamicsModel
+    from clockpunch_b200.estimation.ez_ukf import ezUKF
+    from clockpunch_b200.estimation.ukf_v2 import UnscentedKalmanFilter
+    g = golden("ukf")
+    x = np.array([8000.0, 0, 0, 0, 8, 0])
+    f = ezUKF({"x_init": x, "p_init": 0.1, "dynamics_type": "satellite", "Q": 0.1, "R": 0.1})
+    assert f.gamma == float(g["w_gamma"]) and np.array_equal(f.mean_weight, g["w_mean"])
+    assert np.array_equal(np.diag(f.cvr_weight), g["w_cvr_diag"])
+    f.predictAndUpdate(5, x)
+    assert np.abs(f.est_x - g["ez_est_x"]).max() <= ESTX_TOL
+    assert cov_close(f.est_p, g["ez_est_p"]) and cov_close(f.pred_p, g["ez_pred_p"])
+    assert f.nis == pytest.approx(float(g["ez_nis"]), rel=1e-6)
+    assert f.time == 5 and f.last_measurement_time == 5
+    f = UnscentedKalmanFilter(0, g["orbit_x0"], g["orbit_P0"], SatDynamicsModel(), lambda s: s,
+                              g["orbit_Q"], g["orbit_R"])
+    for k, t in enumerate(g["orbit_times"]):
+        z = g["orbit_z"][k]
+        f.predictAndUpdate(t, None if np.isnan(z[0]) else z)
+        if k < 5:                                           # before the first measurement: tight
+            assert np.abs(f.est_x - g["orbit_est_x"][k]).max() <= 1e-8
+            assert cov_close(f.est_p, g["orbit_est_p"][k], 1e-8 * (k + 1))
+    # 25-step rollout drift is reported against the reference's own noise floor, loosely gated
+    assert np.abs(f.est_x - g["orbit_est_x"][-1])[:3].max() <= 1e-3
+    assert cov_close(f.est_p, g["orbit_est_p"][-1], 1e-6)
+    # split predict() / update() equals predictAndUpdate(); reset() restores
+    f.reset()
+    f.predict(100.0)
+    assert cov_close(f.pred_p, g["orbit_pred_p"][0]) and f.time == 100.0
+    np.testing.assert_array_equal(f.est_x, g["orbit_x0"])
+    f.update(None)
+    assert np.abs(f.est_x - g["orbit_est_x"][0]).max() <= 1e-8
+    with pytest.raises(ValueError):
+        f.predictAndUpdate(200.0, np.zeros((6, 1)))
+    with pytest.raises(NotImplementedError):
+        UnscentedKalmanFilter(0, np.zeros(2), np.eye(2), SatDynamicsModel(), lambda s: s, np.eye(2), np.eye(2))
+
+
+def test_ukf_nonpd_is_flagged_not_fatal(golden):
+    from clockpunch_b200 import _lib
+    from clockpunch_b200.estimation.ukf_v2 import ukf_batch_host
+    g = golden("ukf")
+    params = _lib.make_ukf_params(g["cat_Q"], g["cat_R"])
+    x = g["cat_truth0"][:, :3]
+    p = np.broadcast_to(g["cat_P0"], (3, 6, 6)).copy()
+    p[1] = g["npd_cov"]
+    out = ukf_batch_host(x, p, None, None, 0.0, 60.0, params)
+    assert out["flags"][1] & _lib.FLAG_NONPD_EST and out["flags"][1] & _lib.FLAG_NONFINITE
+    assert out["flags"][0] == 0 and out["flags"][2] == 0
+    assert np.isfinite(out["est_p"][[0, 2]]).all()
+
+
+def _engine_and_oracle(n, m, seed, space_frac=0.25):
+    from clockpunch_b200.engine import CatalogEngine
+    from clockpunch_b200.simulation.catalog import synth_catalog
+    from oracle.step import OracleCatalog
+    cat = synth_catalog(n, m, seed=seed, space_sensor_frac=space_frac)
+    eng = CatalogEngine(cat.sensors, cat.sensor_kinds, cat.targets, cat.est_x, cat.est_p, cat.Q, cat.R)
+    kinds = ["terrestrial" if k else "satellite" for k in cat.sensor_kinds]
+    orc = OracleCatalog(cat.sensors, kinds, cat.targets, cat.est_x, cat.est_p, cat.Q, cat.R)
+    return cat, eng, orc
+
+
+def test_engine_steps_match_oracle():
+    """Full fused step (sensors, truth, UKF, both vis maps, tasking bookkeeping) vs the oracle's
+    restatement of SSAScheduler.step on the same inputs and injected measurements."""
+    cat, eng, orc = _engine_and_oracle(21, 5, seed=11)
+    rng = np.random.default_rng(5)
+    vt0, ve0 = orc.vis_maps()
+    np.testing.assert_array_equal(eng.host("vis_truth"), vt0)
+    for s in range(4):
+        t1 = 100.0 * (s + 1)
+        actions = rng.integers(0, cat.N + 1, size=cat.M)
+        ve_prev = orc.vis_maps()[1]
+        tasked = np.zeros(cat.N, bool)
+        for j, a in enumerate(actions):
+            if a < cat.N and ve_prev[a, j]:
+                tasked[a] = True
+        got_mask = eng.task_from_actions(actions).cpu().numpy().astype(bool)
+        np.testing.assert_array_equal(got_mask, tasked)
+        truth_next = np.stack([__import__("oracle.dynamics", fromlist=["x"]).propagate_satellite(orc.targets[:, i], orc.time, t1)
+                               for i in range(cat.N)], axis=1)
+        z = truth_next + rng.normal(size=(6, cat.N)) * np.sqrt(np.diag(cat.R))[:, None]
+        vt, ve = orc.step(t1, tasked, z)
+        eng.step(t1, tasked=eng.tasked, z=z)
+        assert np.abs(eng.host("truth_x") - orc.targets)[:3].max() <= POS_TOL * (s + 1)
+        assert np.abs(eng.host("sens_x") - orc.sensors)[:3].max() <= POS_TOL * (s + 1)
+        assert np.abs(eng.host("est_x") - orc.est_x).max() <= ESTX_TOL * (s + 1)
+        assert cov_close(eng.host("est_p"), orc.est_p, COV_RTOL * 10 * (s + 1))
+        assert cov_close(eng.host("pred_p"), orc.pred_p, COV_RTOL * 10 * (s + 1))
+        Vt = _v_values(orc.sensors, orc.targets)
+        Ve = _v_values(orc.sensors, orc.est_x)
+        assert not ((eng.host("vis_truth") != vt) & (np.abs(Vt) > 1e-7)).any()
+        assert not ((eng.host("vis_est") != ve) & (np.abs(Ve) > 1e-7)).any()
+        np.testing.assert_array_equal(eng.host("num_tasked"), orc.num_tasked)
+        np.testing.assert_array_equal(eng.host("last_time_tasked"), orc.last_time_tasked)
+    assert (eng.host("flags") == 0).all()
+    # reset restores the construction-time snapshot exactly
+    eng.reset()
+    np.testing.assert_array_equal(eng.host("truth_x"), cat.targets)
+    np.testing.assert_array_equal(eng.host("vis_truth"), vt0)
+    assert eng.time == 0.0 and eng.host("num_tasked").sum() == 0
+
+
+def test_device_measurement_draw_is_distributionally_right():
+    """agents.py:173-183 draws z ~ N(truth, R) from numpy's global RNG; the device path draws
+    with Philox: check moments, determinism per (seed, step) and that tasked targets move."""
+    from clockpunch_b200 import _lib, _buffers as B
+    from clockpunch_b200.simulation.catalog import synth_catalog
+    import ctypes as C, torch
+    cat = synth_catalog(20000, 1, seed=21)
+    ctx = _lib.get_ctx()
+    params = _lib.make_ukf_params(cat.Q, cat.R)
+    dev = B.device_of(ctx)
+    n = cat.N
+
+    def run(seed, step):
+        ex = torch.from_numpy(cat.est_x).to(dev); ep = torch.from_numpy(cat.est_p.reshape(n, 36)).to(dev)
+        tx = torch.from_numpy(cat.targets).to(dev); zo = torch.zeros((6, n), dtype=torch.float64, device=dev)
+        tk = torch.ones(n, dtype=torch.uint8, device=dev)
+        ctx.check(ctx.lib.pc_ukf_predict_update(ctx.handle, ex.data_ptr(), ep.data_ptr(), tx.data_ptr(), None,
+                                                tk.data_ptr(), n, n, 0.0, 60.0, 0, 0, C.byref(params), seed, step,
+                                                None, None, None, None, zo.data_ptr(), None))
+        return (zo - tx).cpu().numpy(), ex.cpu().numpy()
+    d1, ex1 = run(7, 3)
+    d2, _ = run(7, 3)
+    d3, _ = run(7, 4)
+    np.testing.assert_array_equal(d1, d2)
+    assert np.abs(d1 - d3).max() > 0.1
+    sd = np.sqrt(np.diag(cat.R))
+    assert np.abs(d1.mean(axis=1) / sd).max() < 0.05
+    np.testing.assert_allclose(d1.std(axis=1), sd, rtol=0.03)
+    assert np.abs(np.corrcoef(d1)[np.triu_indices(6, 1)]).max() < 0.05
+    assert np.abs(ex1 - cat.est_x)[:3].max() > 1.0
+
+
+def test_full_size_properties():
+    """BASELINE.json configs[1] size (100 sensors x 10k mixed targets): size-independent
+    invariants instead of an oracle that would take hours."""
+    from clockpunch_b200.engine import CatalogEngine
+    from clockpunch_b200.dynamics.propagator import propagate_batch
+    from clockpunch_b200.simulation.catalog import synth_catalog, MU
+    cat = synth_catalog(10000, 100, seed=20240627)
+    eng = CatalogEngine(cat.sensors, cat.sensor_kinds, cat.targets, cat.est_x, cat.est_p, cat.Q, cat.R, seed=9)
+    x0 = cat.targets
+    tasked = np.zeros(cat.N, np.uint8); tasked[::97] = 1
+    eng.step(100.0, tasked=tasked, z=None)
+    x1 = eng.host("truth_x")
+    # two-body invariants: specific energy and angular momentum
+    def energy(x): return 0.5 * (x[3:] ** 2).sum(0) - MU / np.linalg.norm(x[:3], axis=0)
+    def hvec(x): return np.cross(x[:3].T, x[3:].T)
+    assert np.abs(energy(x1) / energy(x0) - 1).max() < 1e-13
+    assert np.abs(hvec(x1) - hvec(x0)).max() / np.abs(hvec(x0)).max() < 1e-13
+    # the fused kernel's truth lane equals the standalone propagator bit for bit
+    np.testing.assert_array_equal(x1, propagate_batch(x0, 0.0, 100.0))
+    # forward then backward returns to the start
+    back = propagate_batch(x1, 100.0, 0.0)
+    assert np.abs(back - x0)[:3].max() < 1e-8
+    # untasked targets: est_x is the propagated centre point; covariances symmetric PD
+    ex = eng.host("est_x"); ep = eng.host("est_p"); pp = eng.host("pred_p")
+    un = tasked == 0
+    np.testing.assert_array_equal(ex[:, un], propagate_batch(cat.est_x, 0.0, 100.0)[:, un])
+    np.testing.assert_array_equal(ep[un], pp[un])
+    np.testing.assert_array_equal(ep, ep.transpose(0, 2, 1))
+    assert np.linalg.eigvalsh(ep).min() > 0
+    # a measurement can only shrink the covariance: pred_p - est_p is PSD for tasked targets
+    diff = pp[~un] - ep[~un]
+    assert np.linalg.eigvalsh(diff).min() > -1e-9 and np.trace(diff, axis1=1, axis2=2).min() > 0
+    assert (eng.host("flags") == 0).all()
+    assert eng.host("num_tasked").sum() == tasked.sum()
+    # packed map: padding bits beyond M are zero, every row consistent with a 2nd standalone call
+    words = eng.vis_truth.cpu().numpy().view(np.uint32)
+    assert (words[:, -1] >> (cat.M - 32 * (eng.wpr - 1))).max() == 0
+    from clockpunch_b200.common.visibility import calcVisMap
+    np.testing.assert_array_equal(eng.host("vis_truth"), calcVisMap(eng.host("sens_x"), x1))
+    np.testing.assert_array_equal(eng.host("vis_est"), calcVisMap(eng.host("sens_x"), ex))
+    # GEO targets see ~40% of ground sites, LEO far fewer; antipodal check
+    vt = eng.host("vis_truth")
+    assert vt[cat.regime == 2].mean() > 3 * vt[cat.regime == 0].mean() > 0
