@@ -42,7 +42,7 @@ class StepArgs(C.Structure):
         ("vis_truth", C.c_void_p), ("vis_est", C.c_void_p), ("words_per_row", C.c_int64),
         ("body_radius", C.c_double), ("vis_tol", C.c_double),
         ("num_tasked", C.c_void_p), ("last_time_tasked", C.c_void_p), ("tr_pos", C.c_void_p),
-        ("tr_vel", C.c_void_p),
+        ("tr_vel", C.c_void_p), ("clock", C.c_void_p),
     ]
 
 
@@ -69,10 +69,10 @@ _SIGNATURES = {
     "pc_ukf_predict_update_host": ([_vp, _vp, _vp, _vp, _vp, _i64, _dbl, _dbl, _int, _int,
                                     C.POINTER(UkfParams), _vp, _vp, _vp, _vp], _int),
     "pc_task_from_actions": ([_vp, _vp, _i64, _vp, _i64, _i64, _vp, _vp], _int),
-    "pc_obs_pack": ([_vp, _vp, _i64, _i64, _vp, _vp, _i64, _i64, _vp, _dbl, _vp, _vp, _vp, _vp], _int),
-    "pc_policy_random_visible": ([_vp, _vp, _i64, _i64, _i64, _u64, _u64, _int, _vp, _vp], _int),
+    "pc_obs_pack": ([_vp, _vp, _i64, _i64, _vp, _vp, _i64, _i64, _vp, _dbl, _vp, _vp, _vp, _vp, _vp], _int),
+    "pc_policy_random_visible": ([_vp, _vp, _i64, _i64, _i64, _u64, _u64, _vp, _int, _vp, _vp], _int),
     "pc_set_timing": ([_vp, _int], _int),
-    "pc_get_timing": ([_vp, C.POINTER(_dbl), C.POINTER(_i64)], _int),
+    "pc_get_timing": ([_vp, C.POINTER(_dbl)], _int),
     "pc_fp64_peak": ([_vp, _int, C.POINTER(_dbl)], _int),
     "pc_step_fused": ([_vp, C.POINTER(StepArgs), C.POINTER(UkfParams), _vp], _int),
 }

@@ -22,16 +22,18 @@ cudaError_t launch_ukf(double* est_x, double* est_p, double* truth_x, const doub
                        int substeps, int force_model, const pc_ukf_params* p, uint64_t seed,
                        uint64_t step, double* pred_x, double* pred_p, double* nis, uint32_t* flags,
                        double* out_z, int64_t* num_tasked, float* last_time_tasked, float* tr_pos,
-                       float* tr_vel, cudaStream_t stream);
+                       float* tr_vel, const pc_clock* clock, cudaStream_t stream);
+cudaError_t launch_advance_clock(pc_clock*, double, cudaStream_t);
 cudaError_t launch_frame_change(const double*, double*, int64_t, int64_t, double, double, cudaStream_t);
 cudaError_t launch_coe2eci(const double*, double*, int64_t, int64_t, double, cudaStream_t);
 cudaError_t launch_lla2eci(const double*, double*, int64_t, int64_t, double, cudaStream_t);
 cudaError_t launch_task_from_actions(const int64_t*, int64_t, const uint32_t*, int64_t, int64_t,
                                      uint8_t*, cudaStream_t);
 cudaError_t launch_obs_pack(const double*, int64_t, int64_t, const double*, const double*, int64_t,
-                            int64_t, const float*, double, float*, float*, float*, cudaStream_t);
+                            int64_t, const float*, double, const pc_clock*, float*, float*, float*,
+                            cudaStream_t);
 cudaError_t launch_policy_random_visible(const uint32_t*, int64_t, int64_t, int64_t, uint64_t,
-                                         uint64_t, int, int64_t*, cudaStream_t);
+                                         uint64_t, const pc_clock*, int, int64_t*, cudaStream_t);
 double launch_dfma_probe(double*, int, int, cudaStream_t, cudaError_t*);
 cudaError_t launch_unpack_bits(const uint32_t* words, int64_t N, int64_t M, int64_t wpr,
                                int64_t* out, cudaStream_t stream);
@@ -47,8 +49,7 @@ struct pc_ctx {
   cudaStream_t host_stream = nullptr;
   // optional per-kernel timing of pc_step_fused (bench.py roofline leg)
   bool timing = false;
-  std::vector<std::pair<cudaEvent_t, cudaEvent_t>> ev;  // around the UKF kernel
-  size_t ev_used = 0;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;  // around the UKF kernel
 };
 
 int pc_fail(pc_ctx* ctx, int code, const char* msg) {
@@ -120,10 +121,8 @@ int pc_ctx_destroy(pc_ctx* ctx) {
     DeviceGuard g(ctx->device);
     if (ctx->ws) cudaFree(ctx->ws);
     if (ctx->host_stream) cudaStreamDestroy(ctx->host_stream);
-    for (auto& p : ctx->ev) {
-      cudaEventDestroy(p.first);
-      cudaEventDestroy(p.second);
-    }
+    if (ctx->ev0) cudaEventDestroy(ctx->ev0);
+    if (ctx->ev1) cudaEventDestroy(ctx->ev1);
   }
   delete ctx;
   return PC_OK;
@@ -339,7 +338,7 @@ int pc_ukf_predict_update(pc_ctx* ctx, double* est_x, double* est_p, double* tru
   PC_CUDA_TRY(ctx, pc::launch_ukf(est_x, est_p, truth_x, z, tasked, n, ld, t0, tf, substeps,
                                   force_model, params, rng_seed, rng_step, out_pred_x, out_pred_p,
                                   out_nis, out_flags, out_z, nullptr, nullptr, nullptr, nullptr,
-                                  (cudaStream_t)stream));
+                                  nullptr, (cudaStream_t)stream));
   ctx->launches += 1;
   return PC_OK;
 }
@@ -404,28 +403,29 @@ int pc_task_from_actions(pc_ctx* ctx, const int64_t* actions, int64_t M, const u
 
 int pc_obs_pack(pc_ctx* ctx, const double* sens_x, int64_t M, int64_t ld_s, const double* est_x,
                 const double* est_p, int64_t N, int64_t ld, const float* last_time_tasked,
-                double t_now, float* out_eci, float* out_cov, float* out_stale, pc_stream stream) {
+                double t_now, const pc_clock* clock, float* out_eci, float* out_cov,
+                float* out_stale, pc_stream stream) {
   PC_REQUIRE(ctx, ctx != nullptr, "null context");
   PC_REQUIRE(ctx, M >= 0 && N >= 0 && ld_s >= M && ld >= N, "bad sizes");
   PC_REQUIRE(ctx, out_eci && out_cov && out_stale, "null output");
   PC_REQUIRE(ctx, (M == 0 || sens_x) && (N == 0 || (est_x && est_p && last_time_tasked)), "null input");
   DeviceGuard g(ctx->device);
   PC_CUDA_TRY(ctx, pc::launch_obs_pack(sens_x, M, ld_s, est_x, est_p, N, ld, last_time_tasked, t_now,
-                                       out_eci, out_cov, out_stale, (cudaStream_t)stream));
+                                       clock, out_eci, out_cov, out_stale, (cudaStream_t)stream));
   ctx->launches += 1;
   return PC_OK;
 }
 
 int pc_policy_random_visible(pc_ctx* ctx, const uint32_t* vis_est, int64_t N, int64_t M,
-                             int64_t words_per_row, uint64_t seed, uint64_t step, int probes,
-                             int64_t* actions, pc_stream stream) {
+                             int64_t words_per_row, uint64_t seed, uint64_t step,
+                             const pc_clock* clock, int probes, int64_t* actions, pc_stream stream) {
   PC_REQUIRE(ctx, ctx != nullptr, "null context");
   PC_REQUIRE(ctx, N > 0 && M >= 0 && probes >= 0, "bad sizes");
   PC_REQUIRE(ctx, M == 0 || (vis_est && actions), "null pointer");
   PC_REQUIRE(ctx, words_per_row == (M + 31) / 32, "words_per_row must be ceil(M/32)");
   DeviceGuard g(ctx->device);
-  PC_CUDA_TRY(ctx, pc::launch_policy_random_visible(vis_est, N, M, words_per_row, seed, step, probes,
-                                                    actions, (cudaStream_t)stream));
+  PC_CUDA_TRY(ctx, pc::launch_policy_random_visible(vis_est, N, M, words_per_row, seed, step, clock,
+                                                    probes, actions, (cudaStream_t)stream));
   if (M) ctx->launches += 1;
   return PC_OK;
 }
@@ -433,23 +433,23 @@ int pc_policy_random_visible(pc_ctx* ctx, const uint32_t* vis_est, int64_t N, in
 /* ---- measurement helpers ------------------------------------------------ */
 int pc_set_timing(pc_ctx* ctx, int enabled) {
   PC_REQUIRE(ctx, ctx != nullptr, "null context");
+  DeviceGuard g(ctx->device);
+  if (enabled && !ctx->ev0) {
+    PC_CUDA_TRY(ctx, cudaEventCreate(&ctx->ev0));
+    PC_CUDA_TRY(ctx, cudaEventCreate(&ctx->ev1));
+  }
   ctx->timing = enabled != 0;
-  ctx->ev_used = 0;
   return PC_OK;
 }
 
-int pc_get_timing(pc_ctx* ctx, double* ukf_ms_total, int64_t* launches) {
-  PC_REQUIRE(ctx, ctx != nullptr && ukf_ms_total && launches, "null pointer");
+int pc_get_timing(pc_ctx* ctx, double* ukf_ms_last) {
+  PC_REQUIRE(ctx, ctx != nullptr && ukf_ms_last, "null pointer");
+  PC_REQUIRE(ctx, ctx->ev0 != nullptr, "timing was never enabled");
   DeviceGuard g(ctx->device);
-  double tot = 0.0;
-  for (size_t i = 0; i < ctx->ev_used; ++i) {
-    float ms = 0.f;
-    PC_CUDA_TRY(ctx, cudaEventSynchronize(ctx->ev[i].second));
-    PC_CUDA_TRY(ctx, cudaEventElapsedTime(&ms, ctx->ev[i].first, ctx->ev[i].second));
-    tot += ms;
-  }
-  *ukf_ms_total = tot;
-  *launches = (int64_t)ctx->ev_used;
+  float ms = 0.f;
+  PC_CUDA_TRY(ctx, cudaEventSynchronize(ctx->ev1));
+  PC_CUDA_TRY(ctx, cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
+  *ukf_ms_last = ms;
   return PC_OK;
 }
 
@@ -511,23 +511,19 @@ int pc_step_fused(pc_ctx* ctx, const pc_step_args* a, const pc_ukf_params* param
   }
   // 2. targets: truth + UKF + summaries
   if (a->N > 0) {
-    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    unsigned evflags = cudaEventRecordDefault;
     if (ctx->timing) {
-      if (ctx->ev_used == ctx->ev.size()) {
-        PC_CUDA_TRY(ctx, cudaEventCreate(&e0));
-        PC_CUDA_TRY(ctx, cudaEventCreate(&e1));
-        ctx->ev.emplace_back(e0, e1);
-      }
-      e0 = ctx->ev[ctx->ev_used].first;
-      e1 = ctx->ev[ctx->ev_used].second;
-      ctx->ev_used += 1;
-      PC_CUDA_TRY(ctx, cudaEventRecord(e0, s));
+      cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+      PC_CUDA_TRY(ctx, cudaStreamIsCapturing(s, &cap));
+      if (cap == cudaStreamCaptureStatusActive) evflags = cudaEventRecordExternal;
+      PC_CUDA_TRY(ctx, cudaEventRecordWithFlags(ctx->ev0, s, evflags));
     }
     PC_CUDA_TRY(ctx, pc::launch_ukf(a->est_x, a->est_p, a->truth_x, a->z, a->tasked, a->N, a->ld,
                                     a->t0, a->tf, a->substeps, a->force_model, params, a->rng_seed,
                                     a->rng_step, nullptr, a->pred_p, a->nis, a->flags, nullptr,
-                                    a->num_tasked, a->last_time_tasked, a->tr_pos, a->tr_vel, s));
-    if (e1) PC_CUDA_TRY(ctx, cudaEventRecord(e1, s));
+                                    a->num_tasked, a->last_time_tasked, a->tr_pos, a->tr_vel,
+                                    a->clock, s));
+    if (ctx->timing) PC_CUDA_TRY(ctx, cudaEventRecordWithFlags(ctx->ev1, s, evflags));
     ctx->launches += 1;
   }
   // 3. both visibility maps for the next step (env.py:455-462)
@@ -535,6 +531,10 @@ int pc_step_fused(pc_ctx* ctx, const pc_step_args* a, const pc_ukf_params* param
     PC_CUDA_TRY(ctx, pc::launch_vismap_packed(a->sens_x, a->M, a->ld_s, nullptr, 0.0, a->truth_x,
                                               a->est_x, a->N, a->ld, a->body_radius, a->vis_tol,
                                               a->vis_truth, a->vis_est, a->words_per_row, s));
+    ctx->launches += 1;
+  }
+  if (a->clock) {
+    PC_CUDA_TRY(ctx, pc::launch_advance_clock(a->clock, a->tf - a->t0, s));
     ctx->launches += 1;
   }
   return PC_OK;

@@ -22,9 +22,10 @@ task_from_actions_kernel(const int64_t* __restrict__ actions, int64_t M,
 __global__ void __launch_bounds__(256)
 obs_pack_kernel(const double* __restrict__ sens_x, int64_t M, int64_t ld_s,
                 const double* __restrict__ est_x, const double* __restrict__ est_p, int64_t N,
-                int64_t ld, const float* __restrict__ last_time_tasked, double t_now,
-                float* __restrict__ out_eci, float* __restrict__ out_cov,
-                float* __restrict__ out_stale) {
+                int64_t ld, const float* __restrict__ last_time_tasked, double t_now_arg,
+                const pc_clock* __restrict__ clock, float* __restrict__ out_eci,
+                float* __restrict__ out_cov, float* __restrict__ out_stale) {
+  const double t_now = clock ? clock->t_now : t_now_arg;
   const int64_t idx = (int64_t)blockIdx.x * 256 + threadIdx.x;
   const int64_t A = M + N;
   const int64_t n_eci = 6 * A, n_cov = 36 * N;
@@ -53,10 +54,12 @@ __device__ __forceinline__ uint64_t splitmix64(uint64_t x) {
 
 __global__ void __launch_bounds__(256)
 policy_random_visible_kernel(const uint32_t* __restrict__ vis_est, int64_t N, int64_t M,
-                             int64_t wpr, uint64_t seed, uint64_t step, int probes,
+                             int64_t wpr, uint64_t seed, uint64_t step_arg,
+                             const pc_clock* __restrict__ clock, int probes,
                              int64_t* __restrict__ actions) {
   const int64_t j = (int64_t)blockIdx.x * 256 + threadIdx.x;
   if (j >= M) return;
+  const uint64_t step = clock ? clock->step : step_arg;
   int64_t pick = N;
   uint64_t h = splitmix64(seed ^ splitmix64(step * 0x100000001B3ull + (uint64_t)j));
   for (int k = 0; k < probes; ++k) {
@@ -89,11 +92,21 @@ dfma_probe_kernel(double* __restrict__ out, int iters, double a, double b) {
 }
 
 cudaError_t launch_policy_random_visible(const uint32_t* vis_est, int64_t N, int64_t M, int64_t wpr,
-                                         uint64_t seed, uint64_t step, int probes, int64_t* actions,
-                                         cudaStream_t s) {
+                                         uint64_t seed, uint64_t step, const pc_clock* clock,
+                                         int probes, int64_t* actions, cudaStream_t s) {
   if (M <= 0) return cudaSuccess;
-  policy_random_visible_kernel<<<(unsigned)((M + 255) / 256), 256, 0, s>>>(vis_est, N, M, wpr, seed,
-                                                                          step, probes, actions);
+  policy_random_visible_kernel<<<(unsigned)((M + 255) / 256), 256, 0, s>>>(
+      vis_est, N, M, wpr, seed, step, clock, probes, actions);
+  return cudaGetLastError();
+}
+
+__global__ void advance_clock_kernel(pc_clock* clock, double dt) {
+  clock->t_now += dt;
+  clock->step += 1;
+}
+
+cudaError_t launch_advance_clock(pc_clock* clock, double dt, cudaStream_t s) {
+  advance_clock_kernel<<<1, 1, 0, s>>>(clock, dt);
   return cudaGetLastError();
 }
 
@@ -115,12 +128,13 @@ cudaError_t launch_task_from_actions(const int64_t* actions, int64_t M, const ui
 
 cudaError_t launch_obs_pack(const double* sens_x, int64_t M, int64_t ld_s, const double* est_x,
                             const double* est_p, int64_t N, int64_t ld,
-                            const float* last_time_tasked, double t_now, float* out_eci,
-                            float* out_cov, float* out_stale, cudaStream_t s) {
+                            const float* last_time_tasked, double t_now, const pc_clock* clock,
+                            float* out_eci, float* out_cov, float* out_stale, cudaStream_t s) {
   const int64_t total = 6 * (M + N) + 36 * N + N;
   if (total <= 0) return cudaSuccess;
   obs_pack_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(
-      sens_x, M, ld_s, est_x, est_p, N, ld, last_time_tasked, t_now, out_eci, out_cov, out_stale);
+      sens_x, M, ld_s, est_x, est_p, N, ld, last_time_tasked, t_now, clock, out_eci, out_cov,
+      out_stale);
   return cudaGetLastError();
 }
 

@@ -6,18 +6,19 @@
 // per target per step from Target.updateNonPhysical (common/agents.py:144-171), plus
 // Agent.propagate for the truth state (agents.py:59-71).
 //
-// Mapping (one CTA = T targets, 16 lanes per target, two targets per warp):
-//   phase 0  CTA-wide coalesced load of the est_p tile (T*36 contiguous doubles) and the
-//            SoA state rows into shared memory.
-//   phase 1  one THREAD per target: upper Cholesky of est_p (serial 6x6 algebra is packed
-//            into the lanes of one warp instead of being replicated 16x) + substep count.
-//   phase 2  one LANE per sigma point (lanes 0..12) + the truth state (lane 13): each lane
-//            integrates its own state with every DOP853 stage in registers.
-//   phase 3  unscented transform through shared memory: mean from differences to the centre
-//            point, residuals, and the 21 unique entries of pred_p spread over the 16 lanes.
-//   phase 4  one THREAD per tasked target: measurement update (second Cholesky, S, C, gain
-//            via triangular solves, est_x, est_p, NIS).
-//   phase 5  CTA-wide coalesced stores.
+// Mapping: 16 lanes per target, two targets per warp, and NO block-level synchronisation --
+// every warp owns its two targets from load to store (only __syncwarp), so the 16-20 resident
+// warps of an SM drift through the phases independently and hide each other's latencies:
+//   load     the warp's est_p tile (2*36 contiguous doubles) + SoA state columns -> shared memory
+//   factor   upper Cholesky of est_p, evaluated in every lane of the half-warp (same cost as
+//            one lane: the two targets of the warp are factored in one SIMD pass)
+//   sigma    lanes 0..12 = the 13 sigma points, lane 13 = the truth state: each lane integrates
+//            its own state with every DOP853 stage in registers
+//   unscent  mean from differences to the centre point, residuals, and the 21 unique entries
+//            of pred_p spread over the 16 lanes (13-term sums through shared memory)
+//   update   one lane per tasked target: measurement update (second Cholesky, S, C, gain via
+//            triangular solves, est_x, est_p, NIS)
+//   store    coalesced 2*36-double tiles for est_p / pred_p, SoA columns for the states
 //
 // Numerics: the reference forms pred_x = sum_i w_i X_i with w_0 = -2e6, w_i = +1.67e5, which
 // loses ~1e-6 km to cancellation.  Here the same quantity is evaluated as
@@ -50,24 +51,29 @@ struct UkfArgs {
   float* last_time_tasked;
   float* tr_pos;
   float* tr_vel;
+  const pc_clock* clock;
   pc_ukf_params p;
 };
 
 struct TargetSmem {
-  double P[36];     // in: est_p; after phase 3: pred_p
-  double PE[36];    // out: est_p
-  double U[21];     // packed upper Cholesky factor (row-major, j >= i)
   double X[14][6];  // propagated sigma points (0..12) and truth (13); 0..12 become residuals
+  double U[21];     // packed upper Cholesky factor (row-major, j >= i)
   double x0[6];     // in: est_x; out: est_x
   double xc[6];     // propagated centre point X_0
   double px[6];     // pred_x
   double m[6];      // pred_x - X_0
   double z[6];
   double nis;
-  int nsub;
   int tasked;
   uint32_t flags;
-  int pad;
+  double* P;        // -> this target's 36 doubles of WarpSmem::P  (in: est_p, then pred_p)
+  double* PE;       // -> WarpSmem::PE (out: est_p)
+};
+
+struct WarpSmem {
+  double P[2][36];   // contiguous pair of covariance tiles: coalesced 576-byte load/store
+  double PE[2][36];
+  TargetSmem t[2];
 };
 
 __host__ __device__ constexpr int uidx(int i, int j) { return i * 6 - (i * (i - 1)) / 2 + (j - i); }
@@ -228,93 +234,111 @@ __device__ __noinline__ void measurement_update(TargetSmem* __restrict__ S, cons
   S->flags |= flags;
 }
 
-template <int T, bool J2>
-__global__ void __launch_bounds__(T * 16, 512 / (T * 16))
+// (a, b) of the e-th unique entry of a symmetric 6x6 (row-major upper), 3 bits each.
+__device__ __forceinline__ void sym_index(int e, int& ra, int& rb) {
+  constexpr unsigned long long RA = 0ull | (0ull << 0) | (0ull << 3) | (0ull << 6) | (0ull << 9) |
+      (0ull << 12) | (0ull << 15) | (1ull << 18) | (1ull << 21) | (1ull << 24) | (1ull << 27) |
+      (1ull << 30) | (2ull << 33) | (2ull << 36) | (2ull << 39) | (2ull << 42) | (3ull << 45) |
+      (3ull << 48) | (3ull << 51) | (4ull << 54) | (4ull << 57) | (5ull << 60);
+  constexpr unsigned long long RB = 0ull | (0ull << 0) | (1ull << 3) | (2ull << 6) | (3ull << 9) |
+      (4ull << 12) | (5ull << 15) | (1ull << 18) | (2ull << 21) | (3ull << 24) | (4ull << 27) |
+      (5ull << 30) | (2ull << 33) | (3ull << 36) | (4ull << 39) | (5ull << 42) | (3ull << 45) |
+      (4ull << 48) | (5ull << 51) | (4ull << 54) | (5ull << 57) | (5ull << 60);
+  ra = (int)((RA >> (3 * e)) & 7ull);
+  rb = (int)((RB >> (3 * e)) & 7ull);
+}
+
+template <int WARPS, int MINB, bool J2>
+__global__ void __launch_bounds__(WARPS * 32, MINB)
 ukf_step_kernel(const __grid_constant__ UkfArgs a) {
-  __shared__ TargetSmem sm[T];
-  constexpr int NT = T * 16;
-  const int tid = threadIdx.x;
-  const int64_t base = (int64_t)blockIdx.x * T;
-  const int nact = (int)min((int64_t)T, a.n - base);  // live targets in this CTA
+  __shared__ WarpSmem wsm[WARPS];
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  const int h = lane >> 4, l = lane & 15;
+  const int64_t pair = (int64_t)blockIdx.x * WARPS + wib;  // this warp's pair of targets
+  const int64_t tg = 2 * pair + h;
+  if (2 * pair >= a.n) return;  // whole warp idle (warp-uniform)
+  const bool live = tg < a.n;
+  const int nlive = (2 * pair + 1 < a.n) ? 2 : 1;
+  WarpSmem& W = wsm[wib];
+  TargetSmem* S = &W.t[h];
+  const double t_now = a.clock ? a.clock->t_now + a.dt : a.t_now;
+  const uint64_t rng_step = a.clock ? a.clock->step : a.rng_step;
 
-  // ---- phase 0: coalesced loads -------------------------------------------------
+  // ---- load ---------------------------------------------------------------------------
   {
-    const double* gp = a.est_p + base * 36;
-    for (int k = tid; k < nact * 36; k += NT) sm[k / 36].P[k % 36] = gp[k];
-    for (int k = tid; k < 6 * T; k += NT) {
-      const int c = k / T, t = k % T;
-      if (t < nact) sm[t].x0[c] = a.est_x[(int64_t)c * a.ld + base + t];
-    }
-    if (tid < T) {
-      sm[tid].flags = 0;
-      sm[tid].nis = __longlong_as_double(0x7ff8000000000000LL);
-      sm[tid].tasked = (tid < nact && a.tasked) ? (a.tasked[base + tid] != 0) : 0;
-    }
-  }
-  __syncthreads();
-
-  // ---- phase 1: one thread per target: Cholesky of est_p, substep count ----------
-  if (tid < nact) {
-    TargetSmem* S = &sm[tid];
-    if (!chol_upper6(S->P, S->U)) S->flags |= PC_FLAG_NONPD_EST;
-    int ns = a.substeps;
-    if (ns <= 0) {
-      const double r[3] = {S->x0[0], S->x0[1], S->x0[2]};
-      const double v[3] = {S->x0[3], S->x0[4], S->x0[5]};
-      bool cl;
-      ns = auto_substeps(r, v, a.dt, &cl);
-      if (cl) S->flags |= PC_FLAG_SUBSTEP_CLAMP;
-    }
-    S->nsub = ns;
-  }
-  __syncthreads();
-
-  // ---- phase 2: one lane per sigma point / truth state ---------------------------
-  const int t = tid >> 4, l = tid & 15;
-  const bool live = t < nact;
-  TargetSmem* S = &sm[live ? t : 0];
-  double X0[6];  // propagated centre point (for the transform below)
-  {
-    double r[3], v[3];
-    bool work = false;
-    int ns = 1;
-    if (live && l < 13) {
-      // generateSigmaPoints (ukf_v2.py:158-183): x + gamma * [0, U, -U], COLUMNS of upper U
-      const int j = (l == 0) ? 0 : (l - 1) % 6;
-      const double sg = (l == 0) ? 0.0 : (l <= 6 ? a.p.gamma : -a.p.gamma);
-      double x[6];
-#pragma unroll
-      for (int c = 0; c < 6; ++c) {
-        const double u = (c <= j) ? S->U[uidx(c, j)] : 0.0;
-        x[c] = fma(sg, u, S->x0[c]);
-      }
-      r[0] = x[0]; r[1] = x[1]; r[2] = x[2];
-      v[0] = x[3]; v[1] = x[4]; v[2] = x[5];
-      ns = S->nsub;
-      work = true;
-    } else if (live && l == 13 && a.truth_x) {
-#pragma unroll
-      for (int c = 0; c < 3; ++c) {
-        r[c] = a.truth_x[(int64_t)c * a.ld + base + t];
-        v[c] = a.truth_x[(int64_t)(c + 3) * a.ld + base + t];
-      }
-      ns = a.substeps > 0 ? a.substeps : auto_substeps(r, v, a.dt, nullptr);
-      work = true;
-    }
-    if (work) {
-      propagate_state<J2>(r, v, a.dt, ns);
-#pragma unroll
-      for (int c = 0; c < 3; ++c) {
-        S->X[l][c] = r[c];
-        S->X[l][c + 3] = v[c];
-      }
+    const double* gp = a.est_p + 2 * pair * 36;
+    double* sp = &W.P[0][0];
+    for (int k = lane; k < nlive * 36; k += 32) sp[k] = gp[k];
+    if (live && l < 6) S->x0[l] = a.est_x[(int64_t)l * a.ld + tg];
+    if (l == 6) {
+      S->flags = 0;
+      S->nis = __longlong_as_double(0x7ff8000000000000LL);
+      S->tasked = (live && a.tasked) ? (a.tasked[tg] != 0) : 0;
+      S->P = W.P[h];
+      S->PE = W.PE[h];
     }
   }
   __syncwarp();
 
-  // ---- phase 3: unscented transform (predictStateEstimate / predictCovariance,
-  //      ukf_v2.py:261-292) -----------------------------------------------------------
-  double d[6];
+  // ---- factor + sigma points (generateSigmaPoints, ukf_v2.py:158-183) ---------------------
+  double r[3], v[3];
+  bool work = false;
+  {
+    double U[21];
+    const bool ok = chol_upper6(W.P[h], U);
+    if (l == 0) {
+#pragma unroll
+      for (int k = 0; k < 21; ++k) S->U[k] = U[k];
+      if (live && !ok) S->flags |= PC_FLAG_NONPD_EST;
+    }
+  }
+  __syncwarp();
+  if (live && l < 13) {
+    // x + gamma * [0, U, -U]: COLUMNS of the upper factor
+    const int j = (l == 0) ? 0 : (l - 1) % 6;
+    const double sg = (l == 0) ? 0.0 : (l <= 6 ? a.p.gamma : -a.p.gamma);
+    double x[6];
+#pragma unroll
+    for (int c = 0; c < 6; ++c) {
+      const double u = (c <= j) ? S->U[uidx(c, j)] : 0.0;
+      x[c] = fma(sg, u, S->x0[c]);
+    }
+    r[0] = x[0]; r[1] = x[1]; r[2] = x[2];
+    v[0] = x[3]; v[1] = x[4]; v[2] = x[5];
+    work = true;
+  } else if (live && l == 13 && a.truth_x) {
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      r[c] = a.truth_x[(int64_t)c * a.ld + tg];
+      v[c] = a.truth_x[(int64_t)(c + 3) * a.ld + tg];
+    }
+    work = true;
+  } else {
+    r[0] = 7000.0; r[1] = 0.0; r[2] = 0.0;
+    v[0] = 0.0; v[1] = 7.5; v[2] = 0.0;
+  }
+  // substeps: one SIMD evaluation for all lanes; the 13 sigma points share the centre's count
+  int ns = a.substeps;
+  if (ns <= 0) {
+    bool cl;
+    ns = auto_substeps(r, v, a.dt, &cl);
+    const int nc = __shfl_sync(0xffffffffu, ns, h << 4);
+    const bool clc = __shfl_sync(0xffffffffu, (int)cl, h << 4) != 0;
+    if (l < 13) ns = nc;
+    if (live && l == 0 && clc) S->flags |= PC_FLAG_SUBSTEP_CLAMP;
+  }
+  if (work) {
+    propagate_state<J2>(r, v, a.dt, ns);
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      S->X[l][c] = r[c];
+      S->X[l][c + 3] = v[c];
+    }
+  }
+  __syncwarp();
+
+  // ---- unscented transform (predictStateEstimate / predictCovariance, ukf_v2.py:261-292) ----
+  double X0[6], d[6];
 #pragma unroll
   for (int c = 0; c < 6; ++c) {
     X0[c] = S->X[0][c];
@@ -347,83 +371,83 @@ ukf_step_kernel(const __grid_constant__ UkfArgs a) {
     for (int rep = 0; rep < 2; ++rep) {
       const int e = l + 16 * rep;
       if (e < 21) {
-        int ra = 0, e0 = e;
-        while (e0 >= 6 - ra) { e0 -= 6 - ra; ++ra; }
-        const int rb = ra + e0;
-        double acc = a.p.wc0 * S->X[0][ra] * S->X[0][rb];
+        int ra, rb;
+        sym_index(e, ra, rb);
+        double acc = 0.0;
 #pragma unroll
-        for (int i = 1; i < 13; ++i) acc = fma(a.p.wi * S->X[i][ra], S->X[i][rb], acc);
-        acc += a.p.Q[ra * 6 + rb];
+        for (int i = 1; i < 13; ++i) acc = fma(S->X[i][ra], S->X[i][rb], acc);
+        acc = fma(a.p.wi, acc, (a.p.wc0 * S->X[0][ra]) * S->X[0][rb]) + a.p.Q[ra * 6 + rb];
         S->P[ra * 6 + rb] = acc;
         S->P[rb * 6 + ra] = acc;
       }
     }
   }
-  __syncthreads();
+  __syncwarp();
 
-  // ---- phase 4: measurement / no-measurement update, one thread per target ----------
-  if (tid < nact) {
-    TargetSmem* Q = &sm[tid];
-    if (Q->tasked) {
+  // ---- measurement / no-measurement update, one lane per target ----------------------------
+  if (live && l == 0) {
+    if (S->tasked) {
       if (a.z) {
 #pragma unroll
-        for (int c = 0; c < 6; ++c) Q->z[c] = a.z[(int64_t)c * a.ld + base + tid];
+        for (int c = 0; c < 6; ++c) S->z[c] = a.z[(int64_t)c * a.ld + tg];
       } else {
         // Target.getMeasurement (agents.py:173-183): z ~ N(truth', R)
         double nrm[6];
-        normal6(a.rng_seed, a.rng_step, (uint64_t)(base + tid), nrm);
+        normal6(a.rng_seed, rng_step, (uint64_t)tg, nrm);
 #pragma unroll
         for (int c = 0; c < 6; ++c) {
-          double acc = Q->X[13][c];
+          double acc = S->X[13][c];
 #pragma unroll
           for (int k = 0; k <= c; ++k) acc = fma(a.p.Lr[c * 6 + k], nrm[k], acc);
-          Q->z[c] = acc;
+          S->z[c] = acc;
         }
       }
-      measurement_update(Q, a.p);
+      measurement_update(S, a.p);
     } else {
       // update(None) (ukf_v2.py:238-244): est_x = propagated centre point, est_p = pred_p
 #pragma unroll
-      for (int c = 0; c < 6; ++c) Q->x0[c] = Q->xc[c];
-#pragma unroll
-      for (int k = 0; k < 36; ++k) Q->PE[k] = Q->P[k];
+      for (int c = 0; c < 6; ++c) S->x0[c] = S->xc[c];
     }
+  }
+  __syncwarp();
+  if (live && !S->tasked) {
+    for (int k = l; k < 36; k += 16) S->PE[k] = S->P[k];
+  }
+  __syncwarp();
+  if (live && l == 0) {
     // flags + scheduler summaries (agents.py:157-171; env.py:446-452,599-609)
     bool fin = true;
 #pragma unroll
-    for (int c = 0; c < 6; ++c) fin = fin && isfinite(Q->x0[c]);
+    for (int c = 0; c < 6; ++c) fin = fin && isfinite(S->x0[c]);
 #pragma unroll
-    for (int k = 0; k < 36; k += 7) fin = fin && isfinite(Q->PE[k]);
-    if (!fin) Q->flags |= PC_FLAG_NONFINITE;
-    const int64_t gi = base + tid;
-    if (a.out_flags) a.out_flags[gi] = Q->flags;
-    if (a.out_nis) a.out_nis[gi] = Q->nis;
-    if (a.tr_pos) a.tr_pos[gi] = (float)Q->PE[0] + (float)Q->PE[7] + (float)Q->PE[14];
-    if (a.tr_vel) a.tr_vel[gi] = (float)Q->PE[21] + (float)Q->PE[28] + (float)Q->PE[35];
-    if (Q->tasked) {
-      if (a.num_tasked) a.num_tasked[gi] += 1;
-      if (a.last_time_tasked) a.last_time_tasked[gi] = (float)a.t_now;
+    for (int k = 0; k < 36; k += 7) fin = fin && isfinite(S->PE[k]);
+    if (!fin) S->flags |= PC_FLAG_NONFINITE;
+    if (a.out_flags) a.out_flags[tg] = S->flags;
+    if (a.out_nis) a.out_nis[tg] = S->nis;
+    if (a.tr_pos) a.tr_pos[tg] = (float)S->PE[0] + (float)S->PE[7] + (float)S->PE[14];
+    if (a.tr_vel) a.tr_vel[tg] = (float)S->PE[21] + (float)S->PE[28] + (float)S->PE[35];
+    if (S->tasked) {
+      if (a.num_tasked) a.num_tasked[tg] += 1;
+      if (a.last_time_tasked) a.last_time_tasked[tg] = (float)t_now;
     }
   }
-  __syncthreads();
 
-  // ---- phase 5: coalesced stores -----------------------------------------------------
+  // ---- store ---------------------------------------------------------------------------
   {
-    double* ge = a.est_p + base * 36;
-    for (int k = tid; k < nact * 36; k += NT) ge[k] = sm[k / 36].PE[k % 36];
+    double* ge = a.est_p + 2 * pair * 36;
+    const double* se = &W.PE[0][0];
+    for (int k = lane; k < nlive * 36; k += 32) ge[k] = se[k];
     if (a.out_pred_p) {
-      double* gq = a.out_pred_p + base * 36;
-      for (int k = tid; k < nact * 36; k += NT) gq[k] = sm[k / 36].P[k % 36];
+      double* gq = a.out_pred_p + 2 * pair * 36;
+      const double* sq = &W.P[0][0];
+      for (int k = lane; k < nlive * 36; k += 32) gq[k] = sq[k];
     }
-    for (int k = tid; k < 6 * T; k += NT) {
-      const int c = k / T, tt = k % T;
-      if (tt < nact) {
-        const int64_t g = (int64_t)c * a.ld + base + tt;
-        a.est_x[g] = sm[tt].x0[c];
-        if (a.truth_x) a.truth_x[g] = sm[tt].X[13][c];
-        if (a.out_pred_x) a.out_pred_x[g] = sm[tt].px[c];
-        if (a.out_z && sm[tt].tasked) a.out_z[g] = sm[tt].z[c];
-      }
+    if (live && l < 6) {
+      const int64_t g = (int64_t)l * a.ld + tg;
+      a.est_x[g] = S->x0[l];
+      if (a.truth_x) a.truth_x[g] = S->X[13][l];
+      if (a.out_pred_x) a.out_pred_x[g] = S->px[l];
+      if (a.out_z && S->tasked) a.out_z[g] = S->z[l];
     }
   }
 }
@@ -433,7 +457,7 @@ cudaError_t launch_ukf(double* est_x, double* est_p, double* truth_x, const doub
                        int substeps, int force_model, const pc_ukf_params* p, uint64_t seed,
                        uint64_t step, double* pred_x, double* pred_p, double* nis, uint32_t* flags,
                        double* out_z, int64_t* num_tasked, float* last_time_tasked, float* tr_pos,
-                       float* tr_vel, cudaStream_t stream) {
+                       float* tr_vel, const pc_clock* clock, cudaStream_t stream) {
   if (n <= 0) return cudaSuccess;
   UkfArgs a;
   a.est_x = est_x;
@@ -457,13 +481,15 @@ cudaError_t launch_ukf(double* est_x, double* est_p, double* truth_x, const doub
   a.last_time_tasked = last_time_tasked;
   a.tr_pos = tr_pos;
   a.tr_vel = tr_vel;
+  a.clock = clock;
   a.p = *p;
-  constexpr int T = 8;
-  const unsigned blocks = (unsigned)((n + T - 1) / T);
+  constexpr int WARPS = 2, MINB = 8;  // 2 warps = 4 targets per CTA; 16 warps resident per SM
+  const int64_t pairs = (n + 1) / 2;
+  const unsigned blocks = (unsigned)((pairs + WARPS - 1) / WARPS);
   if (force_model == PC_FORCE_TWOBODY_J2)
-    ukf_step_kernel<T, true><<<blocks, T * 16, 0, stream>>>(a);
+    ukf_step_kernel<WARPS, MINB, true><<<blocks, WARPS * 32, 0, stream>>>(a);
   else
-    ukf_step_kernel<T, false><<<blocks, T * 16, 0, stream>>>(a);
+    ukf_step_kernel<WARPS, MINB, false><<<blocks, WARPS * 32, 0, stream>>>(a);
   return cudaGetLastError();
 }
 

@@ -80,6 +80,10 @@ class CatalogEngine:
         self.obs_f32 = torch.zeros((sum(self._obs_sizes),), dtype=torch.float32, device=dev)
         self._args = _lib.StepArgs()
         self._snapshot = None
+        # device-resident step clock {double t_now; uint64 step} for graph replay
+        self.clock = torch.zeros((16,), dtype=torch.uint8, device=dev)
+        self._graph = None
+        self._sync_clock()
         self.compute_vis()
         self.snapshot()
 
@@ -87,7 +91,12 @@ class CatalogEngine:
     def _stream(self):
         return self.torch.cuda.current_stream(self.dev).cuda_stream
 
-    def _fill_args(self, t0, tf, z, tasked, want_vis=True):
+    def _sync_clock(self):
+        rec = np.zeros(1, dtype=[("t", "<f8"), ("s", "<u8")])
+        rec["t"], rec["s"] = self.time, self.step_count
+        self.clock.copy_(self.torch.from_numpy(rec.view(np.uint8).copy()))
+
+    def _fill_args(self, t0, tf, z, tasked, want_vis=True, use_clock=False):
         a = self._args
         a.sens_x, a.sens_kind, a.M, a.ld_s = self.sens_x.data_ptr(), self.sens_kind.data_ptr(), self.M, self.ld_s
         a.truth_x, a.est_x, a.est_p = self.truth_x.data_ptr(), self.est_x.data_ptr(), self.est_p.data_ptr()
@@ -102,6 +111,7 @@ class CatalogEngine:
         a.words_per_row, a.body_radius, a.vis_tol = self.wpr, self.body_radius, self.vis_tol
         a.num_tasked, a.last_time_tasked = self.num_tasked.data_ptr(), self.last_time_tasked.data_ptr()
         a.tr_pos, a.tr_vel = self.tr_pos.data_ptr(), self.tr_vel.data_ptr()
+        a.clock = self.clock.data_ptr() if use_clock else None
         return a
 
     # -- physics -------------------------------------------------------------
@@ -141,15 +151,55 @@ class CatalogEngine:
         c.check(c.lib.pc_step_fused(c.handle, C.byref(a), C.byref(self.params), self._stream()))
         self.time = float(t_next)
         self.step_count += 1
+        if self._graph is not None:
+            self._sync_clock()
 
-    def pack_obs(self):
+    # -- CUDA-graph replay of the whole step ------------------------------------------
+    def build_graph(self, dt: float, policy_probes: int = 0, policy_seed: int = 0, pack_obs: bool = False):
+        """Capture [optional stand-in policy] -> tasking mask -> pc_step_fused [-> obs pack] into
+        one CUDA graph.  Times and RNG counters come from the device clock, so replay() needs no
+        argument updates.  Measurements are drawn on device (z = None)."""
+        torch, c = self.torch, self.ctx
+        self._sync_clock()
+        before = c.launch_count
+        g = torch.cuda.CUDAGraph()
+        side = torch.cuda.Stream(self.dev)
+        side.wait_stream(torch.cuda.current_stream(self.dev))
+        with torch.cuda.stream(side):
+            with torch.cuda.graph(g, stream=side):
+                if policy_probes > 0:
+                    c.check(c.lib.pc_policy_random_visible(
+                        c.handle, self.vis_est.data_ptr(), self.N, self.M, self.wpr, policy_seed, 0,
+                        self.clock.data_ptr(), policy_probes, self.actions.data_ptr(), self._stream()))
+                c.check(c.lib.pc_task_from_actions(c.handle, self.actions.data_ptr(), self.M,
+                                                   self.vis_est.data_ptr(), self.N, self.wpr,
+                                                   self.tasked.data_ptr(), self._stream()))
+                a = self._fill_args(0.0, float(dt), None, self.tasked, use_clock=True)
+                c.check(c.lib.pc_step_fused(c.handle, C.byref(a), C.byref(self.params), self._stream()))
+                if pack_obs:
+                    self.pack_obs(use_clock=True)
+        torch.cuda.current_stream(self.dev).wait_stream(side)
+        g.pc_dt, g.pc_launches = float(dt), c.launch_count - before
+        self._graph = g
+        return g
+
+    def replay(self, graph=None):
+        """One step through a captured graph (actions must already be in self.actions unless the
+        graph contains the stand-in policy)."""
+        g = graph or self._graph
+        g.replay()
+        self.time += g.pc_dt
+        self.step_count += 1
+
+    def pack_obs(self, use_clock: bool = False):
         """float32 eci_state / est_cov / obs_staleness into self.obs_f32 (device)."""
         c = self.ctx
         n0, n1, _ = self._obs_sizes
         base = self.obs_f32.data_ptr()
         c.check(c.lib.pc_obs_pack(c.handle, self.sens_x.data_ptr(), self.M, self.ld_s, self.est_x.data_ptr(),
                                   self.est_p.data_ptr(), self.N, self.ld, self.last_time_tasked.data_ptr(),
-                                  self.time, base, base + 4 * n0, base + 4 * (n0 + n1), self._stream()))
+                                  self.time, self.clock.data_ptr() if use_clock else None,
+                                  base, base + 4 * n0, base + 4 * (n0 + n1), self._stream()))
         return self.obs_f32
 
     # -- reset snapshot (env.py:142,208: deepcopy of the agent list) ---------------
@@ -164,6 +214,7 @@ class CatalogEngine:
         for k, v in bufs.items():
             getattr(self, k).copy_(v)
         self.time, self.step_count = t, sc
+        self._sync_clock()
 
     # -- host views --------------------------------------------------------------
     def host(self, name: str) -> np.ndarray:

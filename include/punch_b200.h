@@ -62,6 +62,15 @@ typedef struct pc_ukf_params {
   double Lr[36];  /* lower Cholesky factor of R; only used to draw z on device */
 } pc_ukf_params;
 
+/* Device-resident step clock: lets a captured CUDA graph of pc_step_fused be replayed without
+ * touching kernel arguments.  When pc_step_args.clock != NULL the step runs from clock->t_now to
+ * clock->t_now + (tf - t0), draws measurements with clock->step, and the last kernel of the
+ * step advances the clock (t_now += tf - t0, step += 1). */
+typedef struct pc_clock {
+  double t_now;
+  uint64_t step;
+} pc_clock;
+
 /* ---- lifetime -------------------------------------------------------- */
 int pc_version(void);
 int pc_ctx_create(int device_ordinal, pc_ctx** out);
@@ -157,20 +166,25 @@ int pc_task_from_actions(pc_ctx* ctx, const int64_t* actions, int64_t M, const u
                          int64_t N, int64_t words_per_row, uint8_t* tasked, pc_stream stream);
 int pc_obs_pack(pc_ctx* ctx, const double* sens_x, int64_t M, int64_t ld_s, const double* est_x,
                 const double* est_p, int64_t N, int64_t ld, const float* last_time_tasked,
-                double t_now, float* out_eci, float* out_cov, float* out_stale, pc_stream stream);
+                double t_now, const pc_clock* clock /* device or NULL: use t_now */, float* out_eci,
+                float* out_cov, float* out_stale, pc_stream stream);
 
 /* Benchmark stand-in policy: each sensor takes the first of `probes` random
  * targets that its column of the estimated map shows visible, else inaction (N). */
 int pc_policy_random_visible(pc_ctx* ctx, const uint32_t* vis_est, int64_t N, int64_t M,
-                             int64_t words_per_row, uint64_t seed, uint64_t step, int probes,
+                             int64_t words_per_row, uint64_t seed, uint64_t step,
+                             const pc_clock* clock /* device, or NULL: use `step` */, int probes,
                              int64_t* actions, pc_stream stream);
 
 /* ---- measurement helpers (bench.py) ------------------------------------
- * pc_set_timing(1) makes pc_step_fused bracket its UKF kernel with CUDA events on the launch
- * stream; pc_get_timing sums them (synchronises).  pc_fp64_peak runs a register-resident DFMA
- * probe and returns the best TFLOP/s of `repeats` launches: the FP64 roofline denominator. */
+ * pc_set_timing(1) makes pc_step_fused bracket its UKF kernel with one pair of CUDA events on the
+ * launch stream (recorded as external event nodes when the stream is being captured, so the
+ * pair is re-recorded by every replay of the graph); pc_get_timing waits for the pair and
+ * returns the device time of the most recent UKF launch in milliseconds.  pc_fp64_peak runs a
+ * register-resident DFMA probe and returns the best TFLOP/s of `repeats` launches: the FP64
+ * roofline denominator. */
 int pc_set_timing(pc_ctx* ctx, int enabled);
-int pc_get_timing(pc_ctx* ctx, double* ukf_ms_total, int64_t* launches);
+int pc_get_timing(pc_ctx* ctx, double* ukf_ms_last);
 int pc_fp64_peak(pc_ctx* ctx, int repeats, double* tflops);
 
 /* ---- fused step ---------------------------------------------------------
@@ -205,6 +219,7 @@ typedef struct pc_step_args {
   float* last_time_tasked;   /* (N) in/out or NULL */
   float* tr_pos;             /* (N) trace est_p[:3,:3] or NULL */
   float* tr_vel;             /* (N) trace est_p[3:,3:] or NULL */
+  pc_clock* clock;           /* device pointer or NULL (then t0 / tf / rng_step above are used) */
 } pc_step_args;
 int pc_step_fused(pc_ctx* ctx, const pc_step_args* args, const pc_ukf_params* params,
                   pc_stream stream);
