@@ -43,6 +43,8 @@ class StepArgs(C.Structure):
         ("body_radius", C.c_double), ("vis_tol", C.c_double),
         ("num_tasked", C.c_void_p), ("last_time_tasked", C.c_void_p), ("tr_pos", C.c_void_p),
         ("tr_vel", C.c_void_p), ("clock", C.c_void_p),
+        ("actions", C.c_void_p), ("policy_probes", C.c_int), ("reserved0", C.c_int),
+        ("policy_seed", C.c_uint64), ("sens_q", C.c_void_p),
     ]
 
 

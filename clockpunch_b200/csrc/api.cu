@@ -7,9 +7,9 @@
 #include <vector>
 
 #include "pc_common.cuh"
+#include "ukf_args.cuh"
 
 namespace pc {
-struct UkfArgs;
 cudaError_t launch_propagate_agents(const double*, double*, const uint8_t*, int, int64_t, int64_t,
                                     double, double, int, int, cudaStream_t);
 cudaError_t launch_vismap_packed(const double*, int64_t, int64_t, const uint8_t*, double,
@@ -17,13 +17,12 @@ cudaError_t launch_vismap_packed(const double*, int64_t, int64_t, const uint8_t*
                                  uint32_t*, uint32_t*, int64_t, cudaStream_t);
 cudaError_t launch_vismap_value(const double*, int64_t, int64_t, const double*, int64_t, int64_t,
                                 double, double, double*, cudaStream_t);
-cudaError_t launch_ukf(double* est_x, double* est_p, double* truth_x, const double* z,
-                       const uint8_t* tasked, int64_t n, int64_t ld, double t0, double tf,
-                       int substeps, int force_model, const pc_ukf_params* p, uint64_t seed,
-                       uint64_t step, double* pred_x, double* pred_p, double* nis, uint32_t* flags,
-                       double* out_z, int64_t* num_tasked, float* last_time_tasked, float* tr_pos,
-                       float* tr_vel, const pc_clock* clock, cudaStream_t stream);
-cudaError_t launch_advance_clock(pc_clock*, double, cudaStream_t);
+cudaError_t launch_pre_step(double* sens_x, const uint8_t* sens_kind, int64_t M, int64_t ld_s, double t0,
+                            double tf, int substeps, int force_model, double* sens_q,
+                            double body_radius, double vis_tol, pc_clock* clock, int64_t* actions,
+                            const uint32_t* vis_est, uint8_t* tasked, int64_t N, int64_t wpr,
+                            int probes, uint64_t seed, uint64_t step, cudaStream_t s);
+
 cudaError_t launch_frame_change(const double*, double*, int64_t, int64_t, double, double, cudaStream_t);
 cudaError_t launch_coe2eci(const double*, double*, int64_t, int64_t, double, cudaStream_t);
 cudaError_t launch_lla2eci(const double*, double*, int64_t, int64_t, double, cudaStream_t);
@@ -35,6 +34,7 @@ cudaError_t launch_obs_pack(const double*, int64_t, int64_t, const double*, cons
 cudaError_t launch_policy_random_visible(const uint32_t*, int64_t, int64_t, int64_t, uint64_t,
                                          uint64_t, const pc_clock*, int, int64_t*, cudaStream_t);
 double launch_dfma_probe(double*, int, int, cudaStream_t, cudaError_t*);
+cudaError_t launch_advance_clock(pc_clock*, double, cudaStream_t);
 cudaError_t launch_unpack_bits(const uint32_t* words, int64_t N, int64_t M, int64_t wpr,
                                int64_t* out, cudaStream_t stream);
 }  // namespace pc
@@ -335,10 +335,26 @@ int pc_ukf_predict_update(pc_ctx* ctx, double* est_x, double* est_p, double* tru
   if (rc) return rc;
   if (n == 0) return PC_OK;
   DeviceGuard g(ctx->device);
-  PC_CUDA_TRY(ctx, pc::launch_ukf(est_x, est_p, truth_x, z, tasked, n, ld, t0, tf, substeps,
-                                  force_model, params, rng_seed, rng_step, out_pred_x, out_pred_p,
-                                  out_nis, out_flags, out_z, nullptr, nullptr, nullptr, nullptr,
-                                  nullptr, (cudaStream_t)stream));
+  pc::UkfArgs u{};
+  u.est_x = est_x;
+  u.est_p = est_p;
+  u.truth_x = truth_x;
+  u.z = z;
+  u.tasked = const_cast<uint8_t*>(tasked);
+  u.n = n;
+  u.ld = ld;
+  u.dt = tf - t0;
+  u.t_now = tf;
+  u.substeps = substeps;
+  u.rng_seed = rng_seed;
+  u.rng_step = rng_step;
+  u.out_pred_x = out_pred_x;
+  u.out_pred_p = out_pred_p;
+  u.out_nis = out_nis;
+  u.out_flags = out_flags;
+  u.out_z = out_z;
+  u.p = *params;
+  PC_CUDA_TRY(ctx, pc::launch_ukf(u, force_model, (cudaStream_t)stream));
   ctx->launches += 1;
   return PC_OK;
 }
@@ -500,17 +516,57 @@ int pc_step_fused(pc_ctx* ctx, const pc_step_args* a, const pc_ukf_params* param
   const bool want_vis = a->vis_truth || a->vis_est;
   PC_REQUIRE(ctx, !want_vis || (a->vis_truth && a->vis_est), "vis_truth and vis_est go together");
   PC_REQUIRE(ctx, !want_vis || a->words_per_row == (a->M + 31) / 32, "words_per_row must be ceil(M/32)");
+  PC_REQUIRE(ctx, !a->actions || (a->tasked && (a->vis_est || a->M == 0)),
+             "actions need a tasked workspace and the estimated vis map");
+  PC_REQUIRE(ctx, a->policy_probes >= 0 && a->policy_probes <= 4096, "bad policy_probes");
   DeviceGuard g(ctx->device);
   cudaStream_t s = (cudaStream_t)stream;
-  // 1. sensors (Agent.propagate per sensor; terrestrial ones are a rotation)
-  if (a->M > 0) {
-    PC_CUDA_TRY(ctx, pc::launch_propagate_agents(a->sens_x, a->sens_x, a->sens_kind, PC_KIND_SATELLITE,
-                                                 a->M, a->ld_s, a->t0, a->tf, a->substeps,
-                                                 a->force_model, s));
+  const bool fuse_vis = want_vis && a->sens_q != nullptr && a->M > 0 && a->M <= 1024 && a->N > 0;
+  // 1. sensors (Agent.propagate per sensor; terrestrial ones are a rotation), tasking mask from
+  //    the actions and the PREVIOUS estimated vis map, step clock latch
+  if (a->M > 0 || a->clock) {
+    PC_CUDA_TRY(ctx, pc::launch_pre_step(a->sens_x, a->sens_kind, a->M, a->ld_s, a->t0, a->tf, a->substeps,
+                                         a->force_model, fuse_vis ? a->sens_q : nullptr, a->body_radius,
+                                         a->vis_tol, a->clock, a->actions, a->vis_est,
+                                         const_cast<uint8_t*>(a->tasked), a->N, a->words_per_row,
+                                         a->policy_probes, a->policy_seed, a->rng_step, s));
     ctx->launches += 1;
   }
-  // 2. targets: truth + UKF + summaries
+  // 2. targets: truth + UKF + summaries (+ both vis maps when fused)
   if (a->N > 0) {
+    pc::UkfArgs u{};
+    u.est_x = a->est_x;
+    u.est_p = a->est_p;
+    u.truth_x = a->truth_x;
+    u.z = a->z;
+    u.tasked = const_cast<uint8_t*>(a->tasked);
+    u.n = a->N;
+    u.ld = a->ld;
+    u.dt = a->tf - a->t0;
+    u.t_now = a->tf;
+    u.substeps = a->substeps;
+    u.rng_seed = a->rng_seed;
+    u.rng_step = a->rng_step;
+    u.out_pred_p = a->pred_p;
+    u.out_nis = a->nis;
+    u.out_flags = a->flags;
+    u.num_tasked = a->num_tasked;
+    u.last_time_tasked = a->last_time_tasked;
+    u.tr_pos = a->tr_pos;
+    u.tr_vel = a->tr_vel;
+    u.clock = a->clock;
+    u.advance_clock = a->clock != nullptr;
+    u.clear_tasked = a->actions != nullptr;
+    if (fuse_vis) {
+      u.sens_q = reinterpret_cast<const double4*>(a->sens_q);
+      u.M = (int)a->M;
+      u.wpr = (int)a->words_per_row;
+      u.vis_truth = a->vis_truth;
+      u.vis_est = a->vis_est;
+      u.body_radius = a->body_radius;
+      u.vis_tol = a->vis_tol;
+    }
+    u.p = *params;
     unsigned evflags = cudaEventRecordDefault;
     if (ctx->timing) {
       cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
@@ -518,23 +574,18 @@ int pc_step_fused(pc_ctx* ctx, const pc_step_args* a, const pc_ukf_params* param
       if (cap == cudaStreamCaptureStatusActive) evflags = cudaEventRecordExternal;
       PC_CUDA_TRY(ctx, cudaEventRecordWithFlags(ctx->ev0, s, evflags));
     }
-    PC_CUDA_TRY(ctx, pc::launch_ukf(a->est_x, a->est_p, a->truth_x, a->z, a->tasked, a->N, a->ld,
-                                    a->t0, a->tf, a->substeps, a->force_model, params, a->rng_seed,
-                                    a->rng_step, nullptr, a->pred_p, a->nis, a->flags, nullptr,
-                                    a->num_tasked, a->last_time_tasked, a->tr_pos, a->tr_vel,
-                                    a->clock, s));
+    PC_CUDA_TRY(ctx, pc::launch_ukf(u, a->force_model, s));
     if (ctx->timing) PC_CUDA_TRY(ctx, cudaEventRecordWithFlags(ctx->ev1, s, evflags));
     ctx->launches += 1;
+  } else if (a->clock) {
+    PC_CUDA_TRY(ctx, pc::launch_advance_clock(a->clock, a->tf - a->t0, s));
+    ctx->launches += 1;
   }
-  // 3. both visibility maps for the next step (env.py:455-462)
-  if (want_vis && a->M > 0 && a->N > 0) {
+  // 3. both visibility maps for the next step (env.py:455-462) when not fused above
+  if (want_vis && !fuse_vis && a->M > 0 && a->N > 0) {
     PC_CUDA_TRY(ctx, pc::launch_vismap_packed(a->sens_x, a->M, a->ld_s, nullptr, 0.0, a->truth_x,
                                               a->est_x, a->N, a->ld, a->body_radius, a->vis_tol,
                                               a->vis_truth, a->vis_est, a->words_per_row, s));
-    ctx->launches += 1;
-  }
-  if (a->clock) {
-    PC_CUDA_TRY(ctx, pc::launch_advance_clock(a->clock, a->tf - a->t0, s));
     ctx->launches += 1;
   }
   return PC_OK;

@@ -4,7 +4,8 @@
 //     env.py:487-501: target i is tasked iff some sensor j chose i and vis_map_est[i, j] == 1)
 //   * float32 observation buffers exactly as SSAScheduler emits them
 //     (getEstStates env.py:508-530, est_cov env.py:419-429, obs_staleness env.py:446-452)
-#include "pc_common.cuh"
+#include "propagate.cuh"
+#include "vis.cuh"
 
 namespace pc {
 
@@ -52,25 +53,25 @@ __device__ __forceinline__ uint64_t splitmix64(uint64_t x) {
   return x ^ (x >> 31);
 }
 
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(128)
 policy_random_visible_kernel(const uint32_t* __restrict__ vis_est, int64_t N, int64_t M,
                              int64_t wpr, uint64_t seed, uint64_t step_arg,
                              const pc_clock* __restrict__ clock, int probes,
                              int64_t* __restrict__ actions) {
-  const int64_t j = (int64_t)blockIdx.x * 256 + threadIdx.x;
+  const int lane = threadIdx.x & 31;
+  const int64_t j = (int64_t)blockIdx.x * 4 + (threadIdx.x >> 5);  // one warp per sensor
   if (j >= M) return;
   const uint64_t step = clock ? clock->step : step_arg;
+  const uint64_t base = splitmix64(seed ^ splitmix64(step * 0x100000001B3ull + (uint64_t)j));
   int64_t pick = N;
-  uint64_t h = splitmix64(seed ^ splitmix64(step * 0x100000001B3ull + (uint64_t)j));
-  for (int k = 0; k < probes; ++k) {
-    h = splitmix64(h);
-    const int64_t i = (int64_t)(h % (uint64_t)N);
-    if ((vis_est[i * wpr + (j >> 5)] >> (j & 31)) & 1u) {
-      pick = i;
-      break;
-    }
+  for (int k0 = 0; k0 < probes && pick == N; k0 += 32) {
+    const int k = k0 + lane;
+    const int64_t i = (int64_t)(splitmix64(base + (uint64_t)k) % (uint64_t)N);
+    const bool hit = k < probes && ((vis_est[i * wpr + (j >> 5)] >> (j & 31)) & 1u);
+    const unsigned m = __ballot_sync(0xffffffffu, hit);
+    if (m) pick = __shfl_sync(0xffffffffu, i, __ffs(m) - 1);
   }
-  actions[j] = pick;
+  if (lane == 0) actions[j] = pick;
 }
 
 // FP64 FMA throughput probe: the roofline denominator for the propagate / UKF kernels
@@ -95,7 +96,7 @@ cudaError_t launch_policy_random_visible(const uint32_t* vis_est, int64_t N, int
                                          uint64_t seed, uint64_t step, const pc_clock* clock,
                                          int probes, int64_t* actions, cudaStream_t s) {
   if (M <= 0) return cudaSuccess;
-  policy_random_visible_kernel<<<(unsigned)((M + 255) / 256), 256, 0, s>>>(
+  policy_random_visible_kernel<<<(unsigned)((M + 3) / 4), 128, 0, s>>>(
       vis_est, N, M, wpr, seed, step, clock, probes, actions);
   return cudaGetLastError();
 }
@@ -107,6 +108,127 @@ __global__ void advance_clock_kernel(pc_clock* clock, double dt) {
 
 cudaError_t launch_advance_clock(pc_clock* clock, double dt, cudaStream_t s) {
   advance_clock_kernel<<<1, 1, 0, s>>>(clock, dt);
+  return cudaGetLastError();
+}
+
+// ---- pre-step kernel: everything the fused UKF kernel needs from the M sensors ---------------
+//   blocks [0, nb_sens): one thread per sensor -- Agent.propagate (agents.py:59-71; terrestrial
+//       ones are a rotation), result written back and, with its horizon term, to sens_q (4, M)
+//   blocks [nb_sens, ...): one WARP per sensor -- tasking: the sensor's action (given, or the
+//       stand-in policy: the first of `probes` random targets its column of the PREVIOUS
+//       estimated map shows visible, probed 32 at a time) marks tasked[target]
+//   block 0 thread 0 also latches the step clock (t_cur / step_cur) for the kernels that follow.
+struct PreStepArgs {
+  double* sens_x;
+  const uint8_t* sens_kind;
+  int64_t M, ld_s;
+  double dt;
+  int substeps;
+  double cs, sn;            // rotation of Earth-fixed sensors over dt
+  double4* sens_q;          // may be NULL
+  double body_radius, vis_tol;
+  pc_clock* clock;          // may be NULL
+  // tasking (actions == NULL: skip)
+  int64_t* actions;
+  const uint32_t* vis_est;
+  uint8_t* tasked;
+  int64_t N, wpr;
+  int probes;
+  uint64_t seed, step_arg;
+  int nb_sens;
+};
+
+template <bool J2>
+__global__ void __launch_bounds__(128)
+pre_step_kernel(const __grid_constant__ PreStepArgs a) {
+  if ((int)blockIdx.x < a.nb_sens) {
+    if (blockIdx.x == 0 && threadIdx.x == 0 && a.clock) {
+      a.clock->t_cur = a.clock->t_now;
+      a.clock->step_cur = a.clock->step;
+    }
+    const int64_t j = (int64_t)blockIdx.x * 128 + threadIdx.x;
+    if (j >= a.M) return;
+    double r[3], v[3];
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      r[c] = a.sens_x[(int64_t)c * a.ld_s + j];
+      v[c] = a.sens_x[(int64_t)(c + 3) * a.ld_s + j];
+    }
+    if (a.sens_kind[j] == PC_KIND_TERRESTRIAL) {
+      rotate_z(r, v, a.cs, a.sn);
+    } else {
+      const int nsub = a.substeps > 0 ? a.substeps : auto_substeps(r, v, a.dt, nullptr);
+      propagate_state<J2>(r, v, a.dt, nsub);
+    }
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      a.sens_x[(int64_t)c * a.ld_s + j] = r[c];
+      a.sens_x[(int64_t)(c + 3) * a.ld_s + j] = v[c];
+    }
+    if (a.sens_q)
+      a.sens_q[j] = make_double4(r[0], r[1], r[2], horizon_q(r[0], r[1], r[2], a.body_radius, a.vis_tol));
+    return;
+  }
+  // tasking
+  const int lane = threadIdx.x & 31;
+  const int64_t j = (int64_t)((int)blockIdx.x - a.nb_sens) * 4 + (threadIdx.x >> 5);
+  if (j >= a.M || a.actions == nullptr) return;
+  int64_t pick = a.N;
+  if (a.probes > 0) {
+    const uint64_t step = a.clock ? a.clock->step : a.step_arg;
+    const uint64_t base = splitmix64(a.seed ^ splitmix64(step * 0x100000001B3ull + (uint64_t)j));
+    for (int k0 = 0; k0 < a.probes && pick == a.N; k0 += 32) {
+      const int k = k0 + lane;
+      const int64_t i = (int64_t)(splitmix64(base + (uint64_t)k) % (uint64_t)a.N);
+      const bool hit = k < a.probes && ((a.vis_est[i * a.wpr + (j >> 5)] >> (j & 31)) & 1u);
+      const unsigned m = __ballot_sync(0xffffffffu, hit);
+      if (m) pick = __shfl_sync(0xffffffffu, i, __ffs(m) - 1);
+    }
+    if (lane == 0) {
+      a.actions[j] = pick;
+      if (pick < a.N) a.tasked[pick] = 1;  // visible by construction
+    }
+  } else if (lane == 0) {
+    pick = a.actions[j];
+    if (pick >= 0 && pick < a.N && ((a.vis_est[pick * a.wpr + (j >> 5)] >> (j & 31)) & 1u))
+      a.tasked[pick] = 1;
+  }
+}
+
+cudaError_t launch_pre_step(double* sens_x, const uint8_t* sens_kind, int64_t M, int64_t ld_s, double t0,
+                            double tf, int substeps, int force_model, double* sens_q,
+                            double body_radius, double vis_tol, pc_clock* clock, int64_t* actions,
+                            const uint32_t* vis_est, uint8_t* tasked, int64_t N, int64_t wpr,
+                            int probes, uint64_t seed, uint64_t step, cudaStream_t s) {
+  if (M <= 0 && clock == nullptr) return cudaSuccess;
+  PreStepArgs a;
+  a.sens_x = sens_x;
+  a.sens_kind = sens_kind;
+  a.M = M;
+  a.ld_s = ld_s;
+  a.dt = tf - t0;
+  a.substeps = substeps;
+  a.cs = cos(kOmegaEarth * a.dt);
+  a.sn = sin(kOmegaEarth * a.dt);
+  a.sens_q = reinterpret_cast<double4*>(sens_q);
+  a.body_radius = body_radius;
+  a.vis_tol = vis_tol;
+  a.clock = clock;
+  a.actions = actions;
+  a.vis_est = vis_est;
+  a.tasked = tasked;
+  a.N = N;
+  a.wpr = wpr;
+  a.probes = probes;
+  a.seed = seed;
+  a.step_arg = step;
+  a.nb_sens = (int)((M + 127) / 128);
+  if (a.nb_sens < 1) a.nb_sens = 1;
+  const int nb_task = actions ? (int)((M + 3) / 4) : 0;
+  if (force_model == PC_FORCE_TWOBODY_J2)
+    pre_step_kernel<true><<<a.nb_sens + nb_task, 128, 0, s>>>(a);
+  else
+    pre_step_kernel<false><<<a.nb_sens + nb_task, 128, 0, s>>>(a);
   return cudaGetLastError();
 }
 

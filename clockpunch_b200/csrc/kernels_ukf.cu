@@ -29,33 +29,14 @@
 // pred_x, so their weighted sums are expanded analytically in the same exact-weights form
 // (derivation in DESIGN.md "UKF update").
 #include "propagate.cuh"
+#include "ukf_args.cuh"
+#include "vis.cuh"
 
 namespace pc {
 
-struct UkfArgs {
-  double* est_x;
-  double* est_p;
-  double* truth_x;
-  const double* z;
-  const uint8_t* tasked;
-  int64_t n, ld;
-  double dt, t_now;
-  int substeps;
-  uint64_t rng_seed, rng_step;
-  double* out_pred_x;
-  double* out_pred_p;
-  double* out_nis;
-  uint32_t* out_flags;
-  double* out_z;
-  int64_t* num_tasked;
-  float* last_time_tasked;
-  float* tr_pos;
-  float* tr_vel;
-  const pc_clock* clock;
-  pc_ukf_params p;
-};
-
 struct TargetSmem {
+  double P[36];     // in: est_p, then pred_p
+  double PE[36];    // est_p after a measurement update
   double X[14][6];  // propagated sigma points (0..12) and truth (13); 0..12 become residuals
   double U[21];     // packed upper Cholesky factor (row-major, j >= i)
   double x0[6];     // in: est_x; out: est_x
@@ -63,17 +44,11 @@ struct TargetSmem {
   double px[6];     // pred_x
   double m[6];      // pred_x - X_0
   double z[6];
+  double tr[6];     // truth state in
+  double vq[2];     // horizon terms of (truth', est_x') for the fused visibility test
   double nis;
   int tasked;
   uint32_t flags;
-  double* P;        // -> this target's 36 doubles of WarpSmem::P  (in: est_p, then pred_p)
-  double* PE;       // -> WarpSmem::PE (out: est_p)
-};
-
-struct WarpSmem {
-  double P[2][36];   // contiguous pair of covariance tiles: coalesced 576-byte load/store
-  double PE[2][36];
-  TargetSmem t[2];
 };
 
 __host__ __device__ constexpr int uidx(int i, int j) { return i * 6 - (i * (i - 1)) / 2 + (j - i); }
@@ -236,11 +211,11 @@ __device__ __noinline__ void measurement_update(TargetSmem* __restrict__ S, cons
 
 // (a, b) of the e-th unique entry of a symmetric 6x6 (row-major upper), 3 bits each.
 __device__ __forceinline__ void sym_index(int e, int& ra, int& rb) {
-  constexpr unsigned long long RA = 0ull | (0ull << 0) | (0ull << 3) | (0ull << 6) | (0ull << 9) |
+  constexpr unsigned long long RA = (0ull << 0) | (0ull << 3) | (0ull << 6) | (0ull << 9) |
       (0ull << 12) | (0ull << 15) | (1ull << 18) | (1ull << 21) | (1ull << 24) | (1ull << 27) |
       (1ull << 30) | (2ull << 33) | (2ull << 36) | (2ull << 39) | (2ull << 42) | (3ull << 45) |
       (3ull << 48) | (3ull << 51) | (4ull << 54) | (4ull << 57) | (5ull << 60);
-  constexpr unsigned long long RB = 0ull | (0ull << 0) | (1ull << 3) | (2ull << 6) | (3ull << 9) |
+  constexpr unsigned long long RB = (0ull << 0) | (1ull << 3) | (2ull << 6) | (3ull << 9) |
       (4ull << 12) | (5ull << 15) | (1ull << 18) | (2ull << 21) | (3ull << 24) | (4ull << 27) |
       (5ull << 30) | (2ull << 33) | (3ull << 36) | (4ull << 39) | (5ull << 42) | (3ull << 45) |
       (4ull << 48) | (5ull << 51) | (4ull << 54) | (5ull << 57) | (5ull << 60);
@@ -248,44 +223,53 @@ __device__ __forceinline__ void sym_index(int e, int& ra, int& rb) {
   rb = (int)((RB >> (3 * e)) & 7ull);
 }
 
-template <int WARPS, int MINB, bool J2>
-__global__ void __launch_bounds__(WARPS * 32, MINB)
+template <int WARPS, int MAXREG, bool J2>
+__global__ void __launch_bounds__(WARPS * 32) __maxnreg__(MAXREG)
 ukf_step_kernel(const __grid_constant__ UkfArgs a) {
-  __shared__ WarpSmem wsm[WARPS];
+  __shared__ __align__(16) TargetSmem tsm[WARPS][2];
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
   const int h = lane >> 4, l = lane & 15;
   const int64_t pair = (int64_t)blockIdx.x * WARPS + wib;  // this warp's pair of targets
   const int64_t tg = 2 * pair + h;
   if (2 * pair >= a.n) return;  // whole warp idle (warp-uniform)
   const bool live = tg < a.n;
-  const int nlive = (2 * pair + 1 < a.n) ? 2 : 1;
-  WarpSmem& W = wsm[wib];
-  TargetSmem* S = &W.t[h];
-  const double t_now = a.clock ? a.clock->t_now + a.dt : a.t_now;
-  const uint64_t rng_step = a.clock ? a.clock->step : a.rng_step;
+  TargetSmem* S = &tsm[wib][h];
 
-  // ---- load ---------------------------------------------------------------------------
+  // ---- load: every global input of the warp is requested before anything waits -------------
   {
-    const double* gp = a.est_p + 2 * pair * 36;
-    double* sp = &W.P[0][0];
-    for (int k = lane; k < nlive * 36; k += 32) sp[k] = gp[k];
-    if (live && l < 6) S->x0[l] = a.est_x[(int64_t)l * a.ld + tg];
+    const double* gp = a.est_p + tg * 36;
+    double p0 = 0.0, p1 = 0.0, p2 = 0.0, xin = 0.0, tin = 0.0;
+    int tk = 0;
+    if (live) {
+      p0 = gp[l];
+      p1 = gp[l + 16];
+      if (l < 4) p2 = gp[l + 32];
+      if (l < 6) xin = a.est_x[(int64_t)l * a.ld + tg];
+      if (l >= 8 && l < 14 && a.truth_x) tin = a.truth_x[(int64_t)(l - 8) * a.ld + tg];
+      if (l == 6 && a.tasked) {
+        tk = a.tasked[tg] != 0;
+        if (tk && a.clear_tasked) a.tasked[tg] = 0;
+      }
+    }
+    S->P[l] = p0;
+    S->P[l + 16] = p1;
+    if (l < 4) S->P[l + 32] = p2;
+    if (l < 6) S->x0[l] = xin;
+    if (l >= 8 && l < 14) S->tr[l - 8] = tin;
     if (l == 6) {
+      S->tasked = tk;
       S->flags = 0;
       S->nis = __longlong_as_double(0x7ff8000000000000LL);
-      S->tasked = (live && a.tasked) ? (a.tasked[tg] != 0) : 0;
-      S->P = W.P[h];
-      S->PE = W.PE[h];
     }
   }
+  const double t_now = a.clock ? a.clock->t_cur + a.dt : a.t_now;
+  const uint64_t rng_step = a.clock ? a.clock->step_cur : a.rng_step;
   __syncwarp();
 
   // ---- factor + sigma points (generateSigmaPoints, ukf_v2.py:158-183) ---------------------
-  double r[3], v[3];
-  bool work = false;
   {
     double U[21];
-    const bool ok = chol_upper6(W.P[h], U);
+    const bool ok = chol_upper6(S->P, U);
     if (l == 0) {
 #pragma unroll
       for (int k = 0; k < 21; ++k) S->U[k] = U[k];
@@ -293,6 +277,8 @@ ukf_step_kernel(const __grid_constant__ UkfArgs a) {
     }
   }
   __syncwarp();
+  double r[3], v[3];
+  bool work = false;
   if (live && l < 13) {
     // x + gamma * [0, U, -U]: COLUMNS of the upper factor
     const int j = (l == 0) ? 0 : (l - 1) % 6;
@@ -309,8 +295,8 @@ ukf_step_kernel(const __grid_constant__ UkfArgs a) {
   } else if (live && l == 13 && a.truth_x) {
 #pragma unroll
     for (int c = 0; c < 3; ++c) {
-      r[c] = a.truth_x[(int64_t)c * a.ld + tg];
-      v[c] = a.truth_x[(int64_t)(c + 3) * a.ld + tg];
+      r[c] = S->tr[c];
+      v[c] = S->tr[c + 3];
     }
     work = true;
   } else {
@@ -342,7 +328,7 @@ ukf_step_kernel(const __grid_constant__ UkfArgs a) {
 #pragma unroll
   for (int c = 0; c < 6; ++c) {
     X0[c] = S->X[0][c];
-    d[c] = (l >= 1 && l < 13) ? S->X[l][c] - X0[c] : 0.0;
+    d[c] = (l >= 1 && l < 13) ? (work ? (c < 3 ? r[c] : v[c - 3]) : 0.0) - X0[c] : 0.0;
   }
   __syncwarp();
   if (live && l < 13) {
@@ -351,10 +337,13 @@ ukf_step_kernel(const __grid_constant__ UkfArgs a) {
   }
   __syncwarp();
   if (live && l < 6) {
-    double s = 0.0;
+    double s0 = S->X[1][l] + S->X[2][l], s1 = S->X[3][l] + S->X[4][l];
 #pragma unroll
-    for (int i = 1; i < 13; ++i) s += S->X[i][l];
-    const double m = fma(a.p.wi, s, a.p.eps_w * X0[l]);
+    for (int i = 5; i < 13; i += 2) {
+      s0 += S->X[i][l];
+      s1 += S->X[i + 1][l];
+    }
+    const double m = fma(a.p.wi, s0 + s1, a.p.eps_w * X0[l]);
     S->xc[l] = X0[l];
     S->m[l] = m;
     S->px[l] = X0[l] + m;  // pred_x = sigma_points . mean_weight
@@ -373,10 +362,14 @@ ukf_step_kernel(const __grid_constant__ UkfArgs a) {
       if (e < 21) {
         int ra, rb;
         sym_index(e, ra, rb);
-        double acc = 0.0;
+        double acc0 = S->X[1][ra] * S->X[1][rb], acc1 = S->X[2][ra] * S->X[2][rb];
 #pragma unroll
-        for (int i = 1; i < 13; ++i) acc = fma(S->X[i][ra], S->X[i][rb], acc);
-        acc = fma(a.p.wi, acc, (a.p.wc0 * S->X[0][ra]) * S->X[0][rb]) + a.p.Q[ra * 6 + rb];
+        for (int i = 3; i < 13; i += 2) {
+          acc0 = fma(S->X[i][ra], S->X[i][rb], acc0);
+          acc1 = fma(S->X[i + 1][ra], S->X[i + 1][rb], acc1);
+        }
+        const double acc = fma(a.p.wi, acc0 + acc1, (a.p.wc0 * S->X[0][ra]) * S->X[0][rb]) +
+                           a.p.Q[ra * 6 + rb];
         S->P[ra * 6 + rb] = acc;
         S->P[rb * 6 + ra] = acc;
       }
@@ -385,8 +378,9 @@ ukf_step_kernel(const __grid_constant__ UkfArgs a) {
   __syncwarp();
 
   // ---- measurement / no-measurement update, one lane per target ----------------------------
+  const int tasked = S->tasked;
   if (live && l == 0) {
-    if (S->tasked) {
+    if (tasked) {
       if (a.z) {
 #pragma unroll
         for (int c = 0; c < 6; ++c) S->z[c] = a.z[(int64_t)c * a.ld + tg];
@@ -410,81 +404,113 @@ ukf_step_kernel(const __grid_constant__ UkfArgs a) {
     }
   }
   __syncwarp();
-  if (live && !S->tasked) {
-    for (int k = l; k < 36; k += 16) S->PE[k] = S->P[k];
-  }
-  __syncwarp();
-  if (live && l == 0) {
-    // flags + scheduler summaries (agents.py:157-171; env.py:446-452,599-609)
-    bool fin = true;
-#pragma unroll
-    for (int c = 0; c < 6; ++c) fin = fin && isfinite(S->x0[c]);
-#pragma unroll
-    for (int k = 0; k < 36; k += 7) fin = fin && isfinite(S->PE[k]);
-    if (!fin) S->flags |= PC_FLAG_NONFINITE;
-    if (a.out_flags) a.out_flags[tg] = S->flags;
-    if (a.out_nis) a.out_nis[tg] = S->nis;
-    if (a.tr_pos) a.tr_pos[tg] = (float)S->PE[0] + (float)S->PE[7] + (float)S->PE[14];
-    if (a.tr_vel) a.tr_vel[tg] = (float)S->PE[21] + (float)S->PE[28] + (float)S->PE[35];
-    if (S->tasked) {
-      if (a.num_tasked) a.num_tasked[tg] += 1;
-      if (a.last_time_tasked) a.last_time_tasked[tg] = (float)t_now;
-    }
-  }
+  const double* Pout = tasked ? S->PE : S->P;  // est_p of this target
 
-  // ---- store ---------------------------------------------------------------------------
-  {
-    double* ge = a.est_p + 2 * pair * 36;
-    const double* se = &W.PE[0][0];
-    for (int k = lane; k < nlive * 36; k += 32) ge[k] = se[k];
-    if (a.out_pred_p) {
-      double* gq = a.out_pred_p + 2 * pair * 36;
-      const double* sq = &W.P[0][0];
-      for (int k = lane; k < nlive * 36; k += 32) gq[k] = sq[k];
+  // ---- outputs ---------------------------------------------------------------------------------
+  if (live) {
+    // flags + scheduler summaries (agents.py:157-171; env.py:446-452,599-609)
+    double chk = 0.0, dg = 0.0;
+    if (l < 6) {
+      dg = Pout[l * 7];
+      chk = S->x0[l] + dg;
     }
-    if (live && l < 6) {
+    const unsigned hm = 0xffffu << (h << 4);
+    const unsigned bad = __ballot_sync(hm, !isfinite(chk)) & hm;
+    const float dgf = (float)dg;
+    const float t1 = __shfl_down_sync(hm, dgf, 1, 16), t2 = __shfl_down_sync(hm, dgf, 2, 16);
+    const float tr3 = (dgf + t1) + t2;  // lane 0: trace of the position block, lane 3: velocity block
+    if (l == 0) {
+      uint32_t f = S->flags;
+      if (bad) f |= PC_FLAG_NONFINITE;
+      if (a.out_flags) a.out_flags[tg] = f;
+      if (a.out_nis) a.out_nis[tg] = S->nis;
+      if (a.tr_pos) a.tr_pos[tg] = tr3;
+      if (tasked) {
+        if (a.num_tasked) a.num_tasked[tg] += 1;
+        if (a.last_time_tasked) a.last_time_tasked[tg] = (float)t_now;
+      }
+    }
+    if (l == 3 && a.tr_vel) a.tr_vel[tg] = tr3;
+    // covariance tiles: 36 contiguous doubles per target, 16 lanes
+    double* ge = a.est_p + tg * 36;
+    ge[l] = Pout[l];
+    ge[l + 16] = Pout[l + 16];
+    if (l < 4) ge[l + 32] = Pout[l + 32];
+    if (a.out_pred_p) {
+      double* gq = a.out_pred_p + tg * 36;
+      gq[l] = S->P[l];
+      gq[l + 16] = S->P[l + 16];
+      if (l < 4) gq[l + 32] = S->P[l + 32];
+    }
+    if (l < 6) {
       const int64_t g = (int64_t)l * a.ld + tg;
       a.est_x[g] = S->x0[l];
       if (a.truth_x) a.truth_x[g] = S->X[13][l];
       if (a.out_pred_x) a.out_pred_x[g] = S->px[l];
-      if (a.out_z && S->tasked) a.out_z[g] = S->z[l];
+      if (a.out_z && tasked) a.out_z[g] = S->z[l];
     }
+  }
+
+  // ---- fused visibility: both packed maps for the next step (env.py:455-462) -----------------
+  // lanes = sensors, one warp ballot = one 32-bit word of a target's row.
+  if (a.sens_q) {
+    if (live && l < 2) {
+      const double* x = (l == 0) ? S->X[13] : S->x0;
+      S->vq[l] = horizon_q(x[0], x[1], x[2], a.body_radius, a.vis_tol);
+    }
+    __syncwarp();
+    const TargetSmem* T0 = &tsm[wib][0];
+    const TargetSmem* T1 = &tsm[wib][1];
+    const bool two = 2 * pair + 1 < a.n;
+    const double RE2 = a.body_radius * a.body_radius;
+    uint32_t keep[4] = {0u, 0u, 0u, 0u};  // word `lane` of (t0 truth, t0 est, t1 truth, t1 est)
+    for (int j0 = 0, w = 0; j0 < a.M; j0 += 32, ++w) {
+      const int j = j0 + lane;
+      const bool on = j < a.M;
+      double4 s = make_double4(0.0, 0.0, 0.0, 0.0);
+      if (on) {
+        const double2* q = reinterpret_cast<const double2*>(a.sens_q + j);
+        const double2 lo = __ldg(q), hi = __ldg(q + 1);
+        s = make_double4(lo.x, lo.y, hi.x, hi.y);
+      }
+      const uint32_t b0 = __ballot_sync(0xffffffffu, on && sees(s, T0->X[13][0], T0->X[13][1], T0->X[13][2], T0->vq[0], RE2));
+      const uint32_t b1 = __ballot_sync(0xffffffffu, on && sees(s, T0->x0[0], T0->x0[1], T0->x0[2], T0->vq[1], RE2));
+      uint32_t b2 = 0u, b3 = 0u;
+      if (two) {
+        b2 = __ballot_sync(0xffffffffu, on && sees(s, T1->X[13][0], T1->X[13][1], T1->X[13][2], T1->vq[0], RE2));
+        b3 = __ballot_sync(0xffffffffu, on && sees(s, T1->x0[0], T1->x0[1], T1->x0[2], T1->vq[1], RE2));
+      }
+      if ((w & 31) == lane) {
+        keep[0] = b0; keep[1] = b1; keep[2] = b2; keep[3] = b3;
+      }
+      if ((w & 31) == 31 || j0 + 32 >= a.M) {  // flush up to 32 words per row, coalesced
+        const int wbase = w & ~31;
+        if (wbase + lane <= w) {
+          const int64_t o0 = (2 * pair) * a.wpr + wbase + lane;
+          a.vis_truth[o0] = keep[0];
+          a.vis_est[o0] = keep[1];
+          if (two) {
+            a.vis_truth[o0 + a.wpr] = keep[2];
+            a.vis_est[o0 + a.wpr] = keep[3];
+          }
+        }
+      }
+    }
+  }
+
+  if (a.clock && a.advance_clock && blockIdx.x == 0 && threadIdx.x == 0) {
+    // nobody reads t_now / step during this launch (kernels read the t_cur / step_cur copies)
+    a.clock->t_now += a.dt;
+    a.clock->step += 1;
   }
 }
 
-cudaError_t launch_ukf(double* est_x, double* est_p, double* truth_x, const double* z,
-                       const uint8_t* tasked, int64_t n, int64_t ld, double t0, double tf,
-                       int substeps, int force_model, const pc_ukf_params* p, uint64_t seed,
-                       uint64_t step, double* pred_x, double* pred_p, double* nis, uint32_t* flags,
-                       double* out_z, int64_t* num_tasked, float* last_time_tasked, float* tr_pos,
-                       float* tr_vel, const pc_clock* clock, cudaStream_t stream) {
-  if (n <= 0) return cudaSuccess;
-  UkfArgs a;
-  a.est_x = est_x;
-  a.est_p = est_p;
-  a.truth_x = truth_x;
-  a.z = z;
-  a.tasked = tasked;
-  a.n = n;
-  a.ld = ld;
-  a.dt = tf - t0;
-  a.t_now = tf;
-  a.substeps = substeps;
-  a.rng_seed = seed;
-  a.rng_step = step;
-  a.out_pred_x = pred_x;
-  a.out_pred_p = pred_p;
-  a.out_nis = nis;
-  a.out_flags = flags;
-  a.out_z = out_z;
-  a.num_tasked = num_tasked;
-  a.last_time_tasked = last_time_tasked;
-  a.tr_pos = tr_pos;
-  a.tr_vel = tr_vel;
-  a.clock = clock;
-  a.p = *p;
-  constexpr int WARPS = 2, MINB = 8;  // 2 warps = 4 targets per CTA; 16 warps resident per SM
-  const int64_t pairs = (n + 1) / 2;
+cudaError_t launch_ukf(const UkfArgs& a, int force_model, cudaStream_t stream) {
+  if (a.n <= 0) return cudaSuccess;
+  // 1 warp = 2 targets per CTA, 17 CTAs per SM (120 registers): a 10 000-target catalog is
+  // exactly two resident rounds on 148 SMs (148 * 17 * 2 * 2 = 10 064).
+  constexpr int WARPS = 1, MINB = 120;
+  const int64_t pairs = (a.n + 1) / 2;
   const unsigned blocks = (unsigned)((pairs + WARPS - 1) / WARPS);
   if (force_model == PC_FORCE_TWOBODY_J2)
     ukf_step_kernel<WARPS, MINB, true><<<blocks, WARPS * 32, 0, stream>>>(a);

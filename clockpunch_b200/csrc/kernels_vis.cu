@@ -15,19 +15,9 @@
 // estimate map, so N * ceil(M/32) threads fill the machine even for small catalogs and the
 // packed words are written fully coalesced.  (The fused step kernel in kernels_ukf.cu packs
 // the same words with warp ballots, lanes = sensors.)
-#include "pc_common.cuh"
+#include "vis.cuh"
 
 namespace pc {
-
-// Horizon term of one agent with the reference's below-surface semantics:
-// |r| >= RE -> sqrt(|r|^2 - RE^2); RE - |r| <= tol -> 0 (clamped to the surface);
-// deeper -> NaN (acos(>1) in the reference: the pair is never visible).
-__device__ __forceinline__ double horizon_q(double x, double y, double z, double RE, double tol) {
-  const double rm = sqrt(fma(z, z, fma(y, y, x * x)));
-  if (rm >= RE) return sqrt((rm - RE) * (rm + RE));
-  if (RE - rm <= tol) return 0.0;
-  return __longlong_as_double(0x7ff8000000000000LL);
-}
 
 constexpr int kVisThreads = 128;
 constexpr int kSensTile = 1024;  // sensors staged per pass: 1024 * 32 B = 32 KB

@@ -80,8 +80,10 @@ class CatalogEngine:
         self.obs_f32 = torch.zeros((sum(self._obs_sizes),), dtype=torch.float32, device=dev)
         self._args = _lib.StepArgs()
         self._snapshot = None
-        # device-resident step clock {double t_now; uint64 step} for graph replay
-        self.clock = torch.zeros((16,), dtype=torch.uint8, device=dev)
+        # device-resident step clock (pc_clock: t_now, step, t_cur, step_cur) for graph replay
+        self.clock = torch.zeros((32,), dtype=torch.uint8, device=dev)
+        # (4, M) sensor position + horizon term: lets the UKF kernel emit both vis maps itself
+        self.sens_q = torch.zeros((4 * max(1, self.M),), dtype=f64, device=dev)
         self._graph = None
         self._sync_clock()
         self.compute_vis()
@@ -92,11 +94,12 @@ class CatalogEngine:
         return self.torch.cuda.current_stream(self.dev).cuda_stream
 
     def _sync_clock(self):
-        rec = np.zeros(1, dtype=[("t", "<f8"), ("s", "<u8")])
+        rec = np.zeros(1, dtype=[("t", "<f8"), ("s", "<u8"), ("tc", "<f8"), ("sc", "<u8")])
         rec["t"], rec["s"] = self.time, self.step_count
         self.clock.copy_(self.torch.from_numpy(rec.view(np.uint8).copy()))
 
-    def _fill_args(self, t0, tf, z, tasked, want_vis=True, use_clock=False):
+    def _fill_args(self, t0, tf, z, tasked, want_vis=True, use_clock=False, actions=None, policy_probes=0,
+                   policy_seed=0):
         a = self._args
         a.sens_x, a.sens_kind, a.M, a.ld_s = self.sens_x.data_ptr(), self.sens_kind.data_ptr(), self.M, self.ld_s
         a.truth_x, a.est_x, a.est_p = self.truth_x.data_ptr(), self.est_x.data_ptr(), self.est_p.data_ptr()
@@ -112,6 +115,9 @@ class CatalogEngine:
         a.num_tasked, a.last_time_tasked = self.num_tasked.data_ptr(), self.last_time_tasked.data_ptr()
         a.tr_pos, a.tr_vel = self.tr_pos.data_ptr(), self.tr_vel.data_ptr()
         a.clock = self.clock.data_ptr() if use_clock else None
+        a.actions = None if actions is None else actions.data_ptr()
+        a.policy_probes, a.policy_seed = int(policy_probes), int(policy_seed)
+        a.sens_q = self.sens_q.data_ptr()
         return a
 
     # -- physics -------------------------------------------------------------
@@ -135,18 +141,26 @@ class CatalogEngine:
                                            self.N, self.wpr, self.tasked.data_ptr(), self._stream()))
         return self.tasked
 
-    def step(self, t_next: float | None = None, tasked=None, z=None, dt: float | None = None):
+    def step(self, t_next: float | None = None, tasked=None, z=None, dt: float | None = None, actions=None):
         """Advance every agent to t_next.  tasked: (N,) uint8 device tensor / numpy bool or None;
+        actions: (M,) MultiDiscrete actions (numpy or device int64) -- then the step derives the
+        tasking mask itself from the previous estimated vis map (env.py:564-571);
         z: (6,N) measurements (numpy or (6,ld) device tensor) or None -> drawn on device."""
         if t_next is None:
             t_next = self.time + float(dt)
+        if actions is not None:
+            if not hasattr(actions, "data_ptr"):
+                self.actions[: self.M].copy_(self.torch.from_numpy(np.ascontiguousarray(actions, dtype=np.int64)))
+                actions = self.actions
+            self.tasked.zero_()
+            tasked = self.tasked
         if tasked is not None and not hasattr(tasked, "data_ptr"):
             self.tasked.copy_(self.torch.from_numpy(np.ascontiguousarray(tasked, dtype=np.uint8)))
             tasked = self.tasked
         if z is not None and not hasattr(z, "data_ptr"):
             self.z[:, : self.N].copy_(self.torch.from_numpy(np.ascontiguousarray(z, dtype=np.float64)))
             z = self.z
-        a = self._fill_args(self.time, t_next, z, tasked)
+        a = self._fill_args(self.time, t_next, z, tasked, actions=actions)
         c = self.ctx
         c.check(c.lib.pc_step_fused(c.handle, C.byref(a), C.byref(self.params), self._stream()))
         self.time = float(t_next)
@@ -156,9 +170,11 @@ class CatalogEngine:
 
     # -- CUDA-graph replay of the whole step ------------------------------------------
     def build_graph(self, dt: float, policy_probes: int = 0, policy_seed: int = 0, pack_obs: bool = False):
-        """Capture [optional stand-in policy] -> tasking mask -> pc_step_fused [-> obs pack] into
-        one CUDA graph.  Times and RNG counters come from the device clock, so replay() needs no
-        argument updates.  Measurements are drawn on device (z = None)."""
+        """Capture pc_step_fused (tasking from self.actions -- or the stand-in policy when
+        policy_probes > 0 -- masked by the previous estimated vis map, sensors, truth + UKF, both
+        vis maps) [+ obs pack] into one CUDA graph.  Times and RNG counters come from the device
+        clock, so replay() needs no argument updates.  Measurements are drawn on device."""
+        self.tasked.zero_()
         torch, c = self.torch, self.ctx
         self._sync_clock()
         before = c.launch_count
@@ -167,14 +183,8 @@ class CatalogEngine:
         side.wait_stream(torch.cuda.current_stream(self.dev))
         with torch.cuda.stream(side):
             with torch.cuda.graph(g, stream=side):
-                if policy_probes > 0:
-                    c.check(c.lib.pc_policy_random_visible(
-                        c.handle, self.vis_est.data_ptr(), self.N, self.M, self.wpr, policy_seed, 0,
-                        self.clock.data_ptr(), policy_probes, self.actions.data_ptr(), self._stream()))
-                c.check(c.lib.pc_task_from_actions(c.handle, self.actions.data_ptr(), self.M,
-                                                   self.vis_est.data_ptr(), self.N, self.wpr,
-                                                   self.tasked.data_ptr(), self._stream()))
-                a = self._fill_args(0.0, float(dt), None, self.tasked, use_clock=True)
+                a = self._fill_args(0.0, float(dt), None, self.tasked, use_clock=True, actions=self.actions,
+                                    policy_probes=policy_probes, policy_seed=policy_seed)
                 c.check(c.lib.pc_step_fused(c.handle, C.byref(a), C.byref(self.params), self._stream()))
                 if pack_obs:
                     self.pack_obs(use_clock=True)

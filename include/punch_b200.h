@@ -64,11 +64,13 @@ typedef struct pc_ukf_params {
 
 /* Device-resident step clock: lets a captured CUDA graph of pc_step_fused be replayed without
  * touching kernel arguments.  When pc_step_args.clock != NULL the step runs from clock->t_now to
- * clock->t_now + (tf - t0), draws measurements with clock->step, and the last kernel of the
- * step advances the clock (t_now += tf - t0, step += 1). */
+ * clock->t_now + (tf - t0), draws measurements with clock->step, and advances the clock
+ * (t_now += tf - t0, step += 1) for the next replay. */
 typedef struct pc_clock {
-  double t_now;
+  double t_now;       /* persistent: time / index of the NEXT step to run */
   uint64_t step;
+  double t_cur;       /* copy taken by the running step's first kernel; what its kernels read */
+  uint64_t step_cur;
 } pc_clock;
 
 /* ---- lifetime -------------------------------------------------------- */
@@ -220,6 +222,19 @@ typedef struct pc_step_args {
   float* tr_pos;             /* (N) trace est_p[:3,:3] or NULL */
   float* tr_vel;             /* (N) trace est_p[3:,3:] or NULL */
   pc_clock* clock;           /* device pointer or NULL (then t0 / tf / rng_step above are used) */
+  /* tasking inside the step (SSAScheduler.step: actionSpace2Array + _taskAgents masking,
+   * env.py:564-571).  With actions != NULL the step itself builds the tasking mask in `tasked`
+   * (which must then be a writable, zero-initialised N-byte workspace; the step leaves it zeroed):
+   * policy_probes == 0 reads actions[j] in [0, N] (N = inaction); policy_probes > 0 first fills
+   * actions[] with the benchmark stand-in policy (pc_policy_random_visible).  Either way a target
+   * is tasked only where the PREVIOUS step's estimated vis map shows the pair visible. */
+  int64_t* actions;          /* (M) or NULL */
+  int policy_probes;
+  int reserved0;
+  uint64_t policy_seed;
+  /* (4, M) workspace for sensor position + horizon term.  When given (and M <= 1024) the vis
+   * maps are produced inside the UKF kernel with warp ballots instead of a separate launch. */
+  double* sens_q;
 } pc_step_args;
 int pc_step_fused(pc_ctx* ctx, const pc_step_args* args, const pc_ukf_params* params,
                   pc_stream stream);
