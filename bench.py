@@ -224,7 +224,8 @@ def run_own(args):
     tasked_total = 0
     ukf_ms_sum, ukf_last = 0.0, C.c_double()
     for k in range(args.steps):
-        flush.zero_()                      # L2 flush, outside the timed events
+        if args.l2 == "flush":
+            flush.zero_()                  # L2 flush, outside the timed events
         evs[k][0].record()
         device_step()
         evs[k][1].record()
@@ -356,6 +357,7 @@ def main():
     ap.add_argument("--substeps", type=int, default=0)
     ap.add_argument("--cpu-sample-per-core", type=int, default=32)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--l2", default="flush", choices=["flush", "none"])
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "own" else args.warmup
     if args.impl == "reference":

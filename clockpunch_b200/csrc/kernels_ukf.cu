@@ -6,19 +6,25 @@
 // per target per step from Target.updateNonPhysical (common/agents.py:144-171), plus
 // Agent.propagate for the truth state (agents.py:59-71).
 //
-// Mapping: 16 lanes per target, two targets per warp, and NO block-level synchronisation --
-// every warp owns its two targets from load to store (only __syncwarp), so the 16-20 resident
-// warps of an SM drift through the phases independently and hide each other's latencies:
-//   load     the warp's est_p tile (2*36 contiguous doubles) + SoA state columns -> shared memory
-//   factor   upper Cholesky of est_p, evaluated in every lane of the half-warp (same cost as
-//            one lane: the two targets of the warp are factored in one SIMD pass)
-//   sigma    lanes 0..12 = the 13 sigma points, lane 13 = the truth state: each lane integrates
-//            its own state with every DOP853 stage in registers
-//   unscent  mean from differences to the centre point, residuals, and the 21 unique entries
-//            of pred_p spread over the 16 lanes (13-term sums through shared memory)
-//   update   one lane per tasked target: measurement update (second Cholesky, S, C, gain via
-//            triangular solves, est_x, est_p, NIS)
-//   store    coalesced 2*36-double tiles for est_p / pred_p, SoA columns for the states
+// Mapping: FOUR lanes per target ("quad"), eight targets per warp, one warp per CTA, nothing
+// but warp-level synchronisation.  The 13 sigma points are handled as 6 (+,-) pairs plus the
+// centre point; lanes 0..2 of a quad integrate two pairs each and lane 3 integrates the centre
+// point together with the target's TRUTH state.  A pair is advanced by one interleaved
+// two-state DOP853 (same step size), which gives every lane two independent dependency chains
+// and keeps every stage in registers.  Because x+ and x- of a pair live in the same lane the
+// unscented transform needs no data exchange until the very end:
+//   load     coalesced CTA-wide copy of the 8 covariance tiles (8*36 contiguous doubles) and
+//            the SoA state columns into shared memory
+//   factor   upper Cholesky of est_p, evaluated by all four lanes of the quad (SIMD: the eight
+//            targets of the warp are factored in one pass)
+//   sigma    per pair: s = x+ + x-,  D = x+ - x-   (kept in registers)
+//   unscent  pred_x from sum(s) and the centre point (quad shuffle all-reduce of 6 values);
+//            pred_p = wc0 m m^T + w sum_j [2 a_j a_j^T + D_j D_j^T / 2] + Q with
+//            a_j = s_j/2 - pred_x, reduced over the quad (21 values)
+//   update   tasked targets only: one lane per target runs the measurement update on a
+//            shared-memory copy (second Cholesky, S, C, gain via triangular solves, NIS)
+//   vis      lanes = sensors: each warp ballot is one 32-bit word of a packed vis-map row
+//   store    coalesced copies of the est_p / pred_p tiles, SoA columns for the states
 //
 // Numerics: the reference forms pred_x = sum_i w_i X_i with w_0 = -2e6, w_i = +1.67e5, which
 // loses ~1e-6 km to cancellation.  Here the same quantity is evaluated as
@@ -34,21 +40,29 @@
 
 namespace pc {
 
-struct TargetSmem {
-  double P[36];     // in: est_p, then pred_p
-  double PE[36];    // est_p after a measurement update
-  double X[14][6];  // propagated sigma points (0..12) and truth (13); 0..12 become residuals
-  double U[21];     // packed upper Cholesky factor (row-major, j >= i)
-  double x0[6];     // in: est_x; out: est_x
-  double xc[6];     // propagated centre point X_0
-  double px[6];     // pred_x
-  double m[6];      // pred_x - X_0
+constexpr int kTPW = 8;  // targets per warp
+
+struct TargetSmem {   // scratch of the measurement update (tasked targets)
+  double D[6][6];     // D[j][a] = (X_{1+j} - X_{7+j})[a]: difference of the propagated +/- pair j
+  double U[21];       // packed upper Cholesky factor (row-major, j >= i)
+  double px[6];       // pred_x
+  double m[6];        // pred_x - X_0
   double z[6];
-  double tr[6];     // truth state in
-  double vq[2];     // horizon terms of (truth', est_x') for the fused visibility test
+  double xo[6];       // est_x out
   double nis;
-  int tasked;
   uint32_t flags;
+  int pad;
+  double* P;          // pred_p tile (36)
+  double* PE;         // est_p tile out (36)
+};
+
+struct WarpSmem {
+  double P[kTPW][36];    // in: est_p tiles; out: pred_p tiles       (contiguous: coalesced copies)
+  double PE[kTPW][36];   // out: est_p tiles
+  double xs[kTPW][6];    // est_x in / out
+  double tr[kTPW][6];    // truth in / out
+  double4 tv[kTPW][2];   // (truth', est_x') position + horizon term for the fused vis test
+  TargetSmem t[kTPW];
 };
 
 __host__ __device__ constexpr int uidx(int i, int j) { return i * 6 - (i * (i - 1)) / 2 + (j - i); }
@@ -63,7 +77,7 @@ __device__ __forceinline__ bool chol_upper6(const double* __restrict__ A, double
 #pragma unroll
     for (int k = 0; k < i; ++k) s = fma(-U[uidx(k, i)], U[uidx(k, i)], s);
     ok = ok && (s > 0.0);
-    const double d = rsqrt(s);
+    const double d = rsqrt_fast(s);
     U[uidx(i, i)] = s * d;
 #pragma unroll
     for (int j = i + 1; j < 6; ++j) {
@@ -171,7 +185,7 @@ __device__ __noinline__ void measurement_update(TargetSmem* __restrict__ S, cons
   for (int a = 0; a < 6; ++a) {
     double D[6];
 #pragma unroll
-    for (int j = 0; j < 6; ++j) D[j] = S->X[1 + j][a] - S->X[7 + j][a];
+    for (int j = 0; j < 6; ++j) D[j] = S->D[j][a];
     const double sa = delta[a] + c3 * S->m[a];
     double g[6];
 #pragma unroll
@@ -190,7 +204,7 @@ __device__ __noinline__ void measurement_update(TargetSmem* __restrict__ S, cons
       xe = fma(g[b], y[b], xe);
       S->PE[a * 6 + b] = g[b];  // stash G row; est_p assembled below
     }
-    S->x0[a] = xe;  // est_x = pred_x + K nu  (ukf_v2.py:373-375)
+    S->xo[a] = xe;  // est_x = pred_x + K nu  (ukf_v2.py:373-375)
   }
   // est_p = pred_p - K S K^T = pred_p - G G^T  (ukf_v2.py:367-371)
   double Gm[36];
@@ -209,178 +223,237 @@ __device__ __noinline__ void measurement_update(TargetSmem* __restrict__ S, cons
   S->flags |= flags;
 }
 
-// (a, b) of the e-th unique entry of a symmetric 6x6 (row-major upper), 3 bits each.
-__device__ __forceinline__ void sym_index(int e, int& ra, int& rb) {
-  constexpr unsigned long long RA = (0ull << 0) | (0ull << 3) | (0ull << 6) | (0ull << 9) |
-      (0ull << 12) | (0ull << 15) | (1ull << 18) | (1ull << 21) | (1ull << 24) | (1ull << 27) |
-      (1ull << 30) | (2ull << 33) | (2ull << 36) | (2ull << 39) | (2ull << 42) | (3ull << 45) |
-      (3ull << 48) | (3ull << 51) | (4ull << 54) | (4ull << 57) | (5ull << 60);
-  constexpr unsigned long long RB = (0ull << 0) | (1ull << 3) | (2ull << 6) | (3ull << 9) |
-      (4ull << 12) | (5ull << 15) | (1ull << 18) | (2ull << 21) | (3ull << 24) | (4ull << 27) |
-      (5ull << 30) | (2ull << 33) | (3ull << 36) | (4ull << 39) | (5ull << 42) | (3ull << 45) |
-      (4ull << 48) | (5ull << 51) | (4ull << 54) | (5ull << 57) | (5ull << 60);
-  ra = (int)((RA >> (3 * e)) & 7ull);
-  rb = (int)((RB >> (3 * e)) & 7ull);
+__device__ __forceinline__ double quad_sum(double x) {
+  x += __shfl_xor_sync(0xffffffffu, x, 1);
+  x += __shfl_xor_sync(0xffffffffu, x, 2);
+  return x;
 }
 
-template <int WARPS, int MAXREG, bool J2>
-__global__ void __launch_bounds__(WARPS * 32) __maxnreg__(MAXREG)
-ukf_step_kernel(const __grid_constant__ UkfArgs a) {
-  __shared__ __align__(16) TargetSmem tsm[WARPS][2];
-  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-  const int h = lane >> 4, l = lane & 15;
-  const int64_t pair = (int64_t)blockIdx.x * WARPS + wib;  // this warp's pair of targets
-  const int64_t tg = 2 * pair + h;
-  if (2 * pair >= a.n) return;  // whole warp idle (warp-uniform)
-  const bool live = tg < a.n;
-  TargetSmem* S = &tsm[wib][h];
+// One (+,-) sigma pair: x +- col, both members advanced in lock-step; returns sum and
+// difference of the propagated members.
+template <bool J2>
+__device__ __forceinline__ void propagate_pair(const double (&x)[6], const double (&col)[6], double dt,
+                                               int ns, double (&sum)[6], double (&dif)[6]) {
+  double r[2][3], v[2][3];
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    r[0][c] = x[c] + col[c];
+    r[1][c] = x[c] - col[c];
+    v[0][c] = x[c + 3] + col[c + 3];
+    v[1][c] = x[c + 3] - col[c + 3];
+  }
+  propagate_states<2, J2>(r, v, dt, ns);
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    sum[c] = r[0][c] + r[1][c];
+    dif[c] = r[0][c] - r[1][c];
+    sum[c + 3] = v[0][c] + v[1][c];
+    dif[c + 3] = v[0][c] - v[1][c];
+  }
+}
 
-  // ---- load: every global input of the warp is requested before anything waits -------------
+template <int MAXREG, bool J2>
+__global__ void __launch_bounds__(32) __maxnreg__(MAXREG)
+ukf_step_kernel(const __grid_constant__ UkfArgs a) {
+  __shared__ __align__(16) WarpSmem W;
+  const int lane = threadIdx.x;
+  const int tl = lane >> 2, q = lane & 3;       // target within the warp, lane within the quad
+  const int64_t first = (int64_t)blockIdx.x * kTPW;
+  const int64_t tg = first + tl;
+  const int nlive = (int)min((int64_t)kTPW, a.n - first);
+  const bool live = tl < nlive;
+  const bool have_truth = a.truth_x != nullptr;
+
+  // ---- load: coalesced, everything requested before anything waits ---------------------------
   {
-    const double* gp = a.est_p + tg * 36;
-    double p0 = 0.0, p1 = 0.0, p2 = 0.0, xin = 0.0, tin = 0.0;
-    int tk = 0;
-    if (live) {
-      p0 = gp[l];
-      p1 = gp[l + 16];
-      if (l < 4) p2 = gp[l + 32];
-      if (l < 6) xin = a.est_x[(int64_t)l * a.ld + tg];
-      if (l >= 8 && l < 14 && a.truth_x) tin = a.truth_x[(int64_t)(l - 8) * a.ld + tg];
-      if (l == 6 && a.tasked) {
-        tk = a.tasked[tg] != 0;
-        if (tk && a.clear_tasked) a.tasked[tg] = 0;
+    const double* gp = a.est_p + first * 36;
+    double* sp = &W.P[0][0];
+    double pv[9];
+#pragma unroll
+    for (int i = 0; i < 9; ++i) pv[i] = (lane + 32 * i < nlive * 36) ? gp[lane + 32 * i] : 0.0;
+    double xv[2] = {0.0, 0.0}, tv[2] = {0.0, 0.0};
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      const int k = lane + 32 * i, c = k >> 3, t = k & 7;
+      if (k < 48 && t < nlive) {
+        xv[i] = a.est_x[(int64_t)c * a.ld + first + t];
+        if (have_truth) tv[i] = a.truth_x[(int64_t)c * a.ld + first + t];
       }
     }
-    S->P[l] = p0;
-    S->P[l + 16] = p1;
-    if (l < 4) S->P[l + 32] = p2;
-    if (l < 6) S->x0[l] = xin;
-    if (l >= 8 && l < 14) S->tr[l - 8] = tin;
-    if (l == 6) {
-      S->tasked = tk;
-      S->flags = 0;
-      S->nis = __longlong_as_double(0x7ff8000000000000LL);
+    int tk = 0;
+    if (live && q == 0 && a.tasked) {
+      tk = a.tasked[tg] != 0;
+      if (tk && a.clear_tasked) a.tasked[tg] = 0;
+    }
+#pragma unroll
+    for (int i = 0; i < 9; ++i) sp[lane + 32 * i] = pv[i];
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      const int k = lane + 32 * i, c = k >> 3, t = k & 7;
+      if (k < 48) {
+        W.xs[t][c] = xv[i];
+        W.tr[t][c] = tv[i];
+      }
+    }
+    if (q == 0) {
+      W.t[tl].flags = (uint32_t)tk << 31;  // bit 31: tasked (internal)
+      W.t[tl].nis = __longlong_as_double(0x7ff8000000000000LL);
+      W.t[tl].P = W.P[tl];
+      W.t[tl].PE = W.PE[tl];
     }
   }
   const double t_now = a.clock ? a.clock->t_cur + a.dt : a.t_now;
   const uint64_t rng_step = a.clock ? a.clock->step_cur : a.rng_step;
   __syncwarp();
 
-  // ---- factor + sigma points (generateSigmaPoints, ukf_v2.py:158-183) ---------------------
+  // ---- factor (generateSigmaPoints, ukf_v2.py:158-183) ---------------------------------------
+  double x[6];
+#pragma unroll
+  for (int c = 0; c < 6; ++c) x[c] = W.xs[tl][c];
+  double col0[6], col1[6];  // gamma * columns (2q) and (2q+1) of the upper factor
+  bool chol_ok;
   {
     double U[21];
-    const bool ok = chol_upper6(S->P, U);
-    if (l == 0) {
-#pragma unroll
-      for (int k = 0; k < 21; ++k) S->U[k] = U[k];
-      if (live && !ok) S->flags |= PC_FLAG_NONPD_EST;
-    }
-  }
-  __syncwarp();
-  double r[3], v[3];
-  bool work = false;
-  if (live && l < 13) {
-    // x + gamma * [0, U, -U]: COLUMNS of the upper factor
-    const int j = (l == 0) ? 0 : (l - 1) % 6;
-    const double sg = (l == 0) ? 0.0 : (l <= 6 ? a.p.gamma : -a.p.gamma);
-    double x[6];
+    chol_ok = chol_upper6(W.P[tl], U);
 #pragma unroll
     for (int c = 0; c < 6; ++c) {
-      const double u = (c <= j) ? S->U[uidx(c, j)] : 0.0;
-      x[c] = fma(sg, u, S->x0[c]);
-    }
-    r[0] = x[0]; r[1] = x[1]; r[2] = x[2];
-    v[0] = x[3]; v[1] = x[4]; v[2] = x[5];
-    work = true;
-  } else if (live && l == 13 && a.truth_x) {
-#pragma unroll
-    for (int c = 0; c < 3; ++c) {
-      r[c] = S->tr[c];
-      v[c] = S->tr[c + 3];
-    }
-    work = true;
-  } else {
-    r[0] = 7000.0; r[1] = 0.0; r[2] = 0.0;
-    v[0] = 0.0; v[1] = 7.5; v[2] = 0.0;
-  }
-  // substeps: one SIMD evaluation for all lanes; the 13 sigma points share the centre's count
-  int ns = a.substeps;
-  if (ns <= 0) {
-    bool cl;
-    ns = auto_substeps(r, v, a.dt, &cl);
-    const int nc = __shfl_sync(0xffffffffu, ns, h << 4);
-    const bool clc = __shfl_sync(0xffffffffu, (int)cl, h << 4) != 0;
-    if (l < 13) ns = nc;
-    if (live && l == 0 && clc) S->flags |= PC_FLAG_SUBSTEP_CLAMP;
-  }
-  if (work) {
-    propagate_state<J2>(r, v, a.dt, ns);
-#pragma unroll
-    for (int c = 0; c < 3; ++c) {
-      S->X[l][c] = r[c];
-      S->X[l][c + 3] = v[c];
+      // column j has entries U[c][j] for c <= j
+      const double u0 = (c <= 0) ? U[uidx(c, c <= 0 ? 0 : c)] : 0.0;
+      const double u1 = (c <= 1) ? U[uidx(c, c <= 1 ? 1 : c)] : 0.0;
+      const double u2 = (c <= 2) ? U[uidx(c, c <= 2 ? 2 : c)] : 0.0;
+      const double u3 = (c <= 3) ? U[uidx(c, c <= 3 ? 3 : c)] : 0.0;
+      const double u4 = (c <= 4) ? U[uidx(c, c <= 4 ? 4 : c)] : 0.0;
+      const double u5 = U[uidx(c, 5)];
+      col0[c] = a.p.gamma * (q == 0 ? u0 : (q == 1 ? u2 : u4));
+      col1[c] = a.p.gamma * (q == 0 ? u1 : (q == 1 ? u3 : u5));
     }
   }
-  __syncwarp();
 
-  // ---- unscented transform (predictStateEstimate / predictCovariance, ukf_v2.py:261-292) ----
-  double X0[6], d[6];
-#pragma unroll
-  for (int c = 0; c < 6; ++c) {
-    X0[c] = S->X[0][c];
-    d[c] = (l >= 1 && l < 13) ? (work ? (c < 3 ? r[c] : v[c - 3]) : 0.0) - X0[c] : 0.0;
+  // ---- sigma points --------------------------------------------------------------------------
+  int ns = a.substeps;
+  bool clamp = false;
+  {
+    const double r0[3] = {x[0], x[1], x[2]}, v0[3] = {x[3], x[4], x[5]};
+    if (ns <= 0) ns = auto_substeps(r0, v0, a.dt, &clamp);  // identical in the four lanes
   }
-  __syncwarp();
-  if (live && l < 13) {
+  double s0[6], d0[6], s1[6], d1[6];  // lanes 0..2: two pairs; lane 3: s0 = centre, s1 = truth
+  if (q < 3) {
+    propagate_pair<J2>(x, col0, a.dt, ns, s0, d0);
+    propagate_pair<J2>(x, col1, a.dt, ns, s1, d1);
+  } else {
+    double tr[6];
 #pragma unroll
-    for (int c = 0; c < 6; ++c) S->X[l][c] = d[c];
-  }
-  __syncwarp();
-  if (live && l < 6) {
-    double s0 = S->X[1][l] + S->X[2][l], s1 = S->X[3][l] + S->X[4][l];
+    for (int c = 0; c < 6; ++c) tr[c] = have_truth ? W.tr[tl][c] : x[c];
+    const double rt[3] = {tr[0], tr[1], tr[2]}, vt[3] = {tr[3], tr[4], tr[5]};
+    const int nt = a.substeps > 0 ? a.substeps : auto_substeps(rt, vt, a.dt, nullptr);
+    if (nt == ns) {
+      double r[2][3] = {{x[0], x[1], x[2]}, {tr[0], tr[1], tr[2]}};
+      double v[2][3] = {{x[3], x[4], x[5]}, {tr[3], tr[4], tr[5]}};
+      propagate_states<2, J2>(r, v, a.dt, ns);
 #pragma unroll
-    for (int i = 5; i < 13; i += 2) {
-      s0 += S->X[i][l];
-      s1 += S->X[i + 1][l];
-    }
-    const double m = fma(a.p.wi, s0 + s1, a.p.eps_w * X0[l]);
-    S->xc[l] = X0[l];
-    S->m[l] = m;
-    S->px[l] = X0[l] + m;  // pred_x = sigma_points . mean_weight
-  }
-  __syncwarp();
-  if (live && l < 13) {
+      for (int c = 0; c < 3; ++c) {
+        s0[c] = r[0][c]; s0[c + 3] = v[0][c];
+        s1[c] = r[1][c]; s1[c + 3] = v[1][c];
+      }
+    } else {  // centre and truth want different step counts: integrate them one after the other
+      double r[3] = {x[0], x[1], x[2]}, v[3] = {x[3], x[4], x[5]};
+      propagate_state<J2>(r, v, a.dt, ns);
+      double r2[3] = {tr[0], tr[1], tr[2]}, v2[3] = {tr[3], tr[4], tr[5]};
+      propagate_state<J2>(r2, v2, a.dt, nt);
 #pragma unroll
-    for (int c = 0; c < 6; ++c) S->X[l][c] = d[c] - S->m[c];  // sigma_x_res
-  }
-  __syncwarp();
-  if (live) {
-    // pred_p = Xres Wc Xres^T + Q: 21 unique entries over 16 lanes
-#pragma unroll
-    for (int rep = 0; rep < 2; ++rep) {
-      const int e = l + 16 * rep;
-      if (e < 21) {
-        int ra, rb;
-        sym_index(e, ra, rb);
-        double acc0 = S->X[1][ra] * S->X[1][rb], acc1 = S->X[2][ra] * S->X[2][rb];
-#pragma unroll
-        for (int i = 3; i < 13; i += 2) {
-          acc0 = fma(S->X[i][ra], S->X[i][rb], acc0);
-          acc1 = fma(S->X[i + 1][ra], S->X[i + 1][rb], acc1);
-        }
-        const double acc = fma(a.p.wi, acc0 + acc1, (a.p.wc0 * S->X[0][ra]) * S->X[0][rb]) +
-                           a.p.Q[ra * 6 + rb];
-        S->P[ra * 6 + rb] = acc;
-        S->P[rb * 6 + ra] = acc;
+      for (int c = 0; c < 3; ++c) {
+        s0[c] = r[c]; s0[c + 3] = v[c];
+        s1[c] = r2[c]; s1[c + 3] = v2[c];
       }
     }
+#pragma unroll
+    for (int c = 0; c < 6; ++c) {
+      d0[c] = 0.0;
+      d1[c] = 0.0;
+    }
   }
   __syncwarp();
 
-  // ---- measurement / no-measurement update, one lane per target ----------------------------
-  const int tasked = S->tasked;
-  if (live && l == 0) {
+  // ---- unscented transform (predictStateEstimate / predictCovariance, ukf_v2.py:261-292) ------
+  // X_0 from lane 3; sum over the 12 outer points of (X_i - X_0) = sum_j s_j - 12 X_0
+  double X0[6], m[6], px[6];
+  const int l3 = lane | 3;
+#pragma unroll
+  for (int c = 0; c < 6; ++c) {
+    X0[c] = __shfl_sync(0xffffffffu, s0[c], l3);
+    // each pair contributes (s_j - 2 X_0): differences first, then the (small) sum
+    const double part = (q < 3) ? (s0[c] - 2.0 * X0[c]) + (s1[c] - 2.0 * X0[c]) : 0.0;
+    m[c] = fma(a.p.wi, quad_sum(part), a.p.eps_w * X0[c]);
+    px[c] = X0[c] + m[c];  // pred_x = sigma_points . mean_weight
+  }
+  // pred_p = Xres Wc Xres^T + Q; for a pair  Xres+ Xres+^T + Xres- Xres-^T = 2 a a^T + D D^T / 2
+  double E[21];
+  {
+    double a0[6], a1[6];
+#pragma unroll
+    for (int c = 0; c < 6; ++c) {
+      a0[c] = 0.5 * (s0[c] - 2.0 * X0[c]) - m[c];
+      a1[c] = 0.5 * (s1[c] - 2.0 * X0[c]) - m[c];
+    }
+#pragma unroll
+    for (int ra = 0; ra < 6; ++ra)
+#pragma unroll
+      for (int rb = ra; rb < 6; ++rb) {
+        double e;
+        if (q < 3) {
+          e = fma(0.5 * d0[ra], d0[rb], 2.0 * a0[ra] * a0[rb]);
+          e = fma(0.5 * d1[ra], d1[rb], fma(2.0 * a1[ra], a1[rb], e));
+          e *= a.p.wi;
+        } else {
+          e = fma(a.p.wc0 * m[ra], m[rb], a.p.Q[ra * 6 + rb]);
+        }
+        E[uidx(ra, rb)] = quad_sum(e);
+      }
+  }
+
+  // ---- no-measurement result (update(None), ukf_v2.py:238-244) ----------------------------------
+  const unsigned fl = W.t[tl].flags;
+  const bool tasked = (fl >> 31) != 0;
+  const unsigned any_tasked = __ballot_sync(0xffffffffu, live && tasked);
+  if (q == 0) {
+    // pred_p tile (and est_p = pred_p for untasked targets)
+#pragma unroll
+    for (int ra = 0; ra < 6; ++ra)
+#pragma unroll
+      for (int rb = 0; rb < 6; ++rb) {
+        const double e = E[ra <= rb ? uidx(ra, rb) : uidx(rb, ra)];
+        W.P[tl][ra * 6 + rb] = e;
+        W.PE[tl][ra * 6 + rb] = e;
+      }
+  }
+  if (q == 3) {
+#pragma unroll
+    for (int c = 0; c < 6; ++c) {
+      W.xs[tl][c] = X0[c];   // est_x = propagated centre point
+      W.tr[tl][c] = s1[c];   // truth'
+    }
+  }
+
+  // ---- measurement update (tasked targets only) ------------------------------------------------
+  if (any_tasked) {
+    TargetSmem* S = &W.t[tl];
     if (tasked) {
+      if (q < 3) {
+#pragma unroll
+        for (int c = 0; c < 6; ++c) {
+          S->D[2 * q][c] = d0[c];
+          S->D[2 * q + 1][c] = d1[c];
+        }
+      } else {
+#pragma unroll
+        for (int c = 0; c < 6; ++c) {
+          S->px[c] = px[c];
+          S->m[c] = m[c];
+        }
+      }
+    }
+    __syncwarp();
+    if (live && tasked && q == 0) {
       if (a.z) {
 #pragma unroll
         for (int c = 0; c < 6; ++c) S->z[c] = a.z[(int64_t)c * a.ld + tg];
@@ -390,108 +463,106 @@ ukf_step_kernel(const __grid_constant__ UkfArgs a) {
         normal6(a.rng_seed, rng_step, (uint64_t)tg, nrm);
 #pragma unroll
         for (int c = 0; c < 6; ++c) {
-          double acc = S->X[13][c];
+          double acc = W.tr[tl][c];
 #pragma unroll
           for (int k = 0; k <= c; ++k) acc = fma(a.p.Lr[c * 6 + k], nrm[k], acc);
           S->z[c] = acc;
         }
       }
       measurement_update(S, a.p);
-    } else {
-      // update(None) (ukf_v2.py:238-244): est_x = propagated centre point, est_p = pred_p
 #pragma unroll
-      for (int c = 0; c < 6; ++c) S->x0[c] = S->xc[c];
+      for (int c = 0; c < 6; ++c) W.xs[tl][c] = S->xo[c];
     }
   }
   __syncwarp();
-  const double* Pout = tasked ? S->PE : S->P;  // est_p of this target
 
-  // ---- outputs ---------------------------------------------------------------------------------
-  if (live) {
-    // flags + scheduler summaries (agents.py:157-171; env.py:446-452,599-609)
-    double chk = 0.0, dg = 0.0;
-    if (l < 6) {
-      dg = Pout[l * 7];
-      chk = S->x0[l] + dg;
-    }
-    const unsigned hm = 0xffffu << (h << 4);
-    const unsigned bad = __ballot_sync(hm, !isfinite(chk)) & hm;
-    const float dgf = (float)dg;
-    const float t1 = __shfl_down_sync(hm, dgf, 1, 16), t2 = __shfl_down_sync(hm, dgf, 2, 16);
-    const float tr3 = (dgf + t1) + t2;  // lane 0: trace of the position block, lane 3: velocity block
-    if (l == 0) {
-      uint32_t f = S->flags;
-      if (bad) f |= PC_FLAG_NONFINITE;
-      if (a.out_flags) a.out_flags[tg] = f;
-      if (a.out_nis) a.out_nis[tg] = S->nis;
-      if (a.tr_pos) a.tr_pos[tg] = tr3;
-      if (tasked) {
-        if (a.num_tasked) a.num_tasked[tg] += 1;
-        if (a.last_time_tasked) a.last_time_tasked[tg] = (float)t_now;
-      }
-    }
-    if (l == 3 && a.tr_vel) a.tr_vel[tg] = tr3;
-    // covariance tiles: 36 contiguous doubles per target, 16 lanes
-    double* ge = a.est_p + tg * 36;
-    ge[l] = Pout[l];
-    ge[l + 16] = Pout[l + 16];
-    if (l < 4) ge[l + 32] = Pout[l + 32];
-    if (a.out_pred_p) {
-      double* gq = a.out_pred_p + tg * 36;
-      gq[l] = S->P[l];
-      gq[l + 16] = S->P[l + 16];
-      if (l < 4) gq[l + 32] = S->P[l + 32];
-    }
-    if (l < 6) {
-      const int64_t g = (int64_t)l * a.ld + tg;
-      a.est_x[g] = S->x0[l];
-      if (a.truth_x) a.truth_x[g] = S->X[13][l];
-      if (a.out_pred_x) a.out_pred_x[g] = S->px[l];
-      if (a.out_z && tasked) a.out_z[g] = S->z[l];
+  // ---- flags + scheduler summaries (agents.py:157-171; env.py:446-452,599-609) -------------------
+  if (live && q == 0) {
+    const double* Pout = W.PE[tl];
+    double chk = 0.0;
+#pragma unroll
+    for (int c = 0; c < 6; ++c) chk += W.xs[tl][c] + Pout[c * 7];
+    uint32_t f = W.t[tl].flags & 0x7fffffffu;
+    if (!chol_ok) f |= PC_FLAG_NONPD_EST;
+    if (clamp) f |= PC_FLAG_SUBSTEP_CLAMP;
+    if (!isfinite(chk)) f |= PC_FLAG_NONFINITE;
+    if (a.out_flags) a.out_flags[tg] = f;
+    if (a.out_nis) a.out_nis[tg] = W.t[tl].nis;
+    if (a.tr_pos) a.tr_pos[tg] = ((float)Pout[0] + (float)Pout[7]) + (float)Pout[14];
+    if (a.tr_vel) a.tr_vel[tg] = ((float)Pout[21] + (float)Pout[28]) + (float)Pout[35];
+    if (tasked) {
+      if (a.num_tasked) a.num_tasked[tg] += 1;
+      if (a.last_time_tasked) a.last_time_tasked[tg] = (float)t_now;
     }
   }
 
-  // ---- fused visibility: both packed maps for the next step (env.py:455-462) -----------------
+  // ---- store: coalesced tiles + SoA columns -------------------------------------------------------
+  {
+    double* ge = a.est_p + first * 36;
+    const double* se = &W.PE[0][0];
+#pragma unroll
+    for (int i = 0; i < 9; ++i)
+      if (lane + 32 * i < nlive * 36) ge[lane + 32 * i] = se[lane + 32 * i];
+    if (a.out_pred_p) {
+      double* gq = a.out_pred_p + first * 36;
+      const double* sq = &W.P[0][0];
+#pragma unroll
+      for (int i = 0; i < 9; ++i)
+        if (lane + 32 * i < nlive * 36) gq[lane + 32 * i] = sq[lane + 32 * i];
+    }
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      const int k = lane + 32 * i, c = k >> 3, t = k & 7;
+      if (k < 48 && t < nlive) {
+        const int64_t g = (int64_t)c * a.ld + first + t;
+        a.est_x[g] = W.xs[t][c];
+        if (have_truth) a.truth_x[g] = W.tr[t][c];
+        const bool tk = (W.t[t].flags >> 31) != 0;
+        if (a.out_z && tk) a.out_z[g] = W.t[t].z[c];
+      }
+    }
+    if (a.out_pred_x && live && q == 1) {
+#pragma unroll
+      for (int c = 0; c < 6; ++c) a.out_pred_x[(int64_t)c * a.ld + tg] = px[c];
+    }
+  }
+
+  // ---- fused visibility: both packed maps for the next step (env.py:455-462) ---------------------
   // lanes = sensors, one warp ballot = one 32-bit word of a target's row.
   if (a.sens_q) {
-    if (live && l < 2) {
-      const double* x = (l == 0) ? S->X[13] : S->x0;
-      S->vq[l] = horizon_q(x[0], x[1], x[2], a.body_radius, a.vis_tol);
+    if (live && q < 2) {
+      const double* xx = (q == 0) ? W.tr[tl] : W.xs[tl];
+      W.tv[tl][q] = make_double4(xx[0], xx[1], xx[2], horizon_q(xx[0], xx[1], xx[2], a.body_radius, a.vis_tol));
     }
     __syncwarp();
-    const TargetSmem* T0 = &tsm[wib][0];
-    const TargetSmem* T1 = &tsm[wib][1];
-    const bool two = 2 * pair + 1 < a.n;
     const double RE2 = a.body_radius * a.body_radius;
-    uint32_t keep[4] = {0u, 0u, 0u, 0u};  // word `lane` of (t0 truth, t0 est, t1 truth, t1 est)
-    for (int j0 = 0, w = 0; j0 < a.M; j0 += 32, ++w) {
-      const int j = j0 + lane;
-      const bool on = j < a.M;
-      double4 s = make_double4(0.0, 0.0, 0.0, 0.0);
-      if (on) {
-        const double2* q = reinterpret_cast<const double2*>(a.sens_q + j);
-        const double2 lo = __ldg(q), hi = __ldg(q + 1);
-        s = make_double4(lo.x, lo.y, hi.x, hi.y);
+    for (int w0 = 0; w0 < a.wpr; w0 += 32) {      // 32 words (1024 sensors) per pass
+      uint32_t keep[2 * kTPW];
+#pragma unroll
+      for (int k = 0; k < 2 * kTPW; ++k) keep[k] = 0u;
+      const int wend = min(a.wpr, w0 + 32);
+      for (int w = w0; w < wend; ++w) {
+        const int j = w * 32 + lane;
+        const bool on = j < a.M;
+        double4 s = make_double4(0.0, 0.0, 0.0, 0.0);
+        if (on) {
+          const double2* qq = reinterpret_cast<const double2*>(a.sens_q + j);
+          const double2 lo = __ldg(qq), hi = __ldg(qq + 1);
+          s = make_double4(lo.x, lo.y, hi.x, hi.y);
+        }
+#pragma unroll
+        for (int k = 0; k < 2 * kTPW; ++k) {
+          const double4 t = W.tv[k >> 1][k & 1];
+          const uint32_t b = __ballot_sync(0xffffffffu, on && sees(s, t.x, t.y, t.z, t.w, RE2));
+          if ((w - w0) == lane) keep[k] = b;
+        }
       }
-      const uint32_t b0 = __ballot_sync(0xffffffffu, on && sees(s, T0->X[13][0], T0->X[13][1], T0->X[13][2], T0->vq[0], RE2));
-      const uint32_t b1 = __ballot_sync(0xffffffffu, on && sees(s, T0->x0[0], T0->x0[1], T0->x0[2], T0->vq[1], RE2));
-      uint32_t b2 = 0u, b3 = 0u;
-      if (two) {
-        b2 = __ballot_sync(0xffffffffu, on && sees(s, T1->X[13][0], T1->X[13][1], T1->X[13][2], T1->vq[0], RE2));
-        b3 = __ballot_sync(0xffffffffu, on && sees(s, T1->x0[0], T1->x0[1], T1->x0[2], T1->vq[1], RE2));
-      }
-      if ((w & 31) == lane) {
-        keep[0] = b0; keep[1] = b1; keep[2] = b2; keep[3] = b3;
-      }
-      if ((w & 31) == 31 || j0 + 32 >= a.M) {  // flush up to 32 words per row, coalesced
-        const int wbase = w & ~31;
-        if (wbase + lane <= w) {
-          const int64_t o0 = (2 * pair) * a.wpr + wbase + lane;
-          a.vis_truth[o0] = keep[0];
-          a.vis_est[o0] = keep[1];
-          if (two) {
-            a.vis_truth[o0 + a.wpr] = keep[2];
-            a.vis_est[o0 + a.wpr] = keep[3];
+      if (w0 + lane < wend) {
+#pragma unroll
+        for (int k = 0; k < 2 * kTPW; ++k) {
+          if ((k >> 1) < nlive) {
+            uint32_t* dst = (k & 1) ? a.vis_est : a.vis_truth;
+            dst[(first + (k >> 1)) * a.wpr + w0 + lane] = keep[k];
           }
         }
       }
@@ -507,15 +578,14 @@ ukf_step_kernel(const __grid_constant__ UkfArgs a) {
 
 cudaError_t launch_ukf(const UkfArgs& a, int force_model, cudaStream_t stream) {
   if (a.n <= 0) return cudaSuccess;
-  // 1 warp = 2 targets per CTA, 17 CTAs per SM (120 registers): a 10 000-target catalog is
-  // exactly two resident rounds on 148 SMs (148 * 17 * 2 * 2 = 10 064).
-  constexpr int WARPS = 1, MINB = 120;
-  const int64_t pairs = (a.n + 1) / 2;
-  const unsigned blocks = (unsigned)((pairs + WARPS - 1) / WARPS);
+  // one warp (8 targets) per CTA; 224 registers -> 9 warps resident per SM, each lane running
+  // two interleaved integrations.
+  constexpr int MAXREG = 224;
+  const unsigned blocks = (unsigned)((a.n + kTPW - 1) / kTPW);
   if (force_model == PC_FORCE_TWOBODY_J2)
-    ukf_step_kernel<WARPS, MINB, true><<<blocks, WARPS * 32, 0, stream>>>(a);
+    ukf_step_kernel<MAXREG, true><<<blocks, 32, 0, stream>>>(a);
   else
-    ukf_step_kernel<WARPS, MINB, false><<<blocks, WARPS * 32, 0, stream>>>(a);
+    ukf_step_kernel<MAXREG, false><<<blocks, 32, 0, stream>>>(a);
   return cudaGetLastError();
 }
 

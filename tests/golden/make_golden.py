@@ -80,6 +80,7 @@ def gold_propagate():
         chain.append(sat.propagate(chain[-1], t0, t1))
     d["chain_t"] = ts
     d["chain_x"] = np.array(chain).T
+    d["chain_truth_end"] = mp_truth(x, 10000.0)
     # seeded catalogs, (6,K) batch API
     x0 = np.concatenate([catalog(rng, 12, r) for r in ("LEO", "MEO", "GEO", "HEO")], axis=1)
     d["cat_x0"] = x0

@@ -61,7 +61,12 @@ def test_propagate_golden(golden, dyn):
     y = xs[:, 0]
     for k in range(1, len(ts)):
         y = sat.propagate(y, ts[k - 1], ts[k])
-    assert np.abs(y - xs[:, -1])[:3].max() <= 5e-9      # 48 chained calls: both sides accumulate
+    # 48 chained calls over 1.7 orbits: the reference accumulates its own 1e-10-relative step errors,
+    # so parity is its drift band; against the closed-form truth the kernel is far closer.
+    ref_drift = np.abs(xs[:, -1] - g["chain_truth_end"])[:3].max()
+    assert np.abs(y - xs[:, -1])[:3].max() <= 2 * ref_drift + POS_TOL
+    assert np.abs(y - g["chain_truth_end"])[:3].max() <= 1e-8
+    assert np.abs(y - g["chain_truth_end"])[:3].max() <= ref_drift
 
 
 def test_propagate_substep_override_and_j2(dyn):
