@@ -244,12 +244,15 @@ def run_own(args):
     ms_per_step = float(t_ms.item()) / args.steps
     value = world * N / (ms_per_step * 1e-3)
 
-    # roofline of the dominant kernel (K4: truth + 13 sigma propagations + UKF algebra per target)
+    # roofline of the dominant kernel: propagate_sigma_kernel (all 13 sigma points + the truth state of
+    # every target, one thread per state).  Algorithmic work: SURVEY.md section 8(d), 1150 flop per
+    # fixed DOP853 step x substeps used; algorithmic bytes: each 6-vector read and written once.
     total_steps = args.warmup + args.steps
     tasked_frac = tasked_total / max(1, N * total_steps)
     substeps_used = 1.0 if args.substeps == 0 else float(args.substeps)   # auto rule: 1 at dt=100s, e<=0.01
-    flop_per_target = (14 * FLOP_DOP853_STEP * substeps_used
-                       + (1 - tasked_frac) * FLOP_UKF_NOMEAS + tasked_frac * FLOP_UKF_MEAS)
+    flop_per_target = 14 * FLOP_DOP853_STEP * substeps_used
+    flop_per_target_step = flop_per_target + (1 - tasked_frac) * FLOP_UKF_NOMEAS + tasked_frac * FLOP_UKF_MEAS \
+        + 2 * M * FLOP_VIS_PAIR
     ukf_ms_avg = ukf_ms_sum / args.steps
     achieved_tf = flop_per_target * N / (ukf_ms_avg * 1e-3) * 1e-12
     peaks = {}
@@ -258,14 +261,17 @@ def run_own(args):
     except OSError:
         pass
     hbm_peak = peaks.get("hbm_gbs", 6650.0)
-    hbm_ach = (BYTES_TARGET_STEP - 96 + 0) * N / (ukf_ms_avg * 1e-3) * 1e-9
-    roofline = {"bound": "fp64", "kernel": "ukf_step_kernel", "achieved": achieved_tf, "peak": peak_tf.value,
+    hbm_ach = 14 * 96.0 * N / (ukf_ms_avg * 1e-3) * 1e-9
+    roofline = {"bound": "fp64", "kernel": "propagate_sigma_kernel", "achieved": achieved_tf, "peak": peak_tf.value,
                 "unit": "TFLOP/s", "frac": achieved_tf / peak_tf.value if peak_tf.value else None,
                 "traffic": None, "peak_source": "DFMA probe measured live in this run (pc_fp64_peak); "
                 "MEASURED_PEAKS.json has no FP64 entry; nominal 37 TFLOP/s",
-                "flop_per_target_step": flop_per_target, "substeps_per_propagate": substeps_used,
+                "flop_per_launch": flop_per_target * N, "substeps_per_propagate": substeps_used,
                 "kernel_ms": ukf_ms_avg, "kernel_share_of_step": ukf_ms_avg / ms_per_step,
+                "whole_step_flop_per_target_step": flop_per_target_step,
+                "whole_step_achieved": flop_per_target_step * N / (ms_per_step * 1e-3) * 1e-12,
                 "hbm": {"achieved": hbm_ach, "peak": hbm_peak, "unit": "GB/s", "frac": hbm_ach / hbm_peak,
+                        "bytes_per_launch": 14 * 96.0 * N,
                         "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback"}}
     clocks = sampler.stop() if rank == 0 else None
 
@@ -317,7 +323,7 @@ def run_own(args):
     e2e = {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h_act.numel() * 8),
            "d2h_bytes_per_step": int(h_obs.numel() * 4 + h_vis.numel() * 4 + h_nt.numel() * 8),
            "ms_per_step": float(e2e_ms.item()) / args.steps,
-           "path": "CatalogEngine: pinned host actions -> [graph: pc_task_from_actions -> pc_step_fused -> pc_obs_pack] -> pinned host obs"}
+           "path": "CatalogEngine: pinned host actions -> [CUDA graph: pc_step_fused (tasking, sensors, sigma propagate, UKF finish, vis maps) -> pc_obs_pack] -> pinned host obs"}
 
     if rank != 0:
         if world > 1:

@@ -43,8 +43,8 @@ class StepArgs(C.Structure):
         ("body_radius", C.c_double), ("vis_tol", C.c_double),
         ("num_tasked", C.c_void_p), ("last_time_tasked", C.c_void_p), ("tr_pos", C.c_void_p),
         ("tr_vel", C.c_void_p), ("clock", C.c_void_p),
-        ("actions", C.c_void_p), ("policy_probes", C.c_int), ("reserved0", C.c_int),
-        ("policy_seed", C.c_uint64), ("sens_q", C.c_void_p),
+        ("actions", C.c_void_p), ("policy_probes", C.c_int), ("sigma_valid", C.c_int),
+        ("policy_seed", C.c_uint64), ("sigma_ws", C.c_void_p), ("sig_flags", C.c_void_p),
     ]
 
 
@@ -68,6 +68,7 @@ _SIGNATURES = {
     "pc_vismap_host": ([_vp, _vp, _i64, _vp, _i64, _dbl, _dbl, _int, _vp, _vp], _int),
     "pc_ukf_predict_update": ([_vp, _vp, _vp, _vp, _vp, _vp, _i64, _i64, _dbl, _dbl, _int, _int,
                                C.POINTER(UkfParams), _u64, _u64, _vp, _vp, _vp, _vp, _vp, _vp], _int),
+    "pc_sigma_points": ([_vp, _vp, _vp, _i64, _i64, _dbl, _vp, _vp, _vp], _int),
     "pc_ukf_predict_update_host": ([_vp, _vp, _vp, _vp, _vp, _i64, _dbl, _dbl, _int, _int,
                                     C.POINTER(UkfParams), _vp, _vp, _vp, _vp], _int),
     "pc_task_from_actions": ([_vp, _vp, _i64, _vp, _i64, _i64, _vp, _vp], _int),

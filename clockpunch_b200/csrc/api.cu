@@ -47,6 +47,10 @@ struct pc_ctx {
   void* ws = nullptr;
   size_t ws_bytes = 0;
   cudaStream_t host_stream = nullptr;
+  // sigma-point workspace for UKF calls whose caller does not bring one (not graph-capture safe)
+  double* sb = nullptr;
+  uint32_t* sbf = nullptr;
+  size_t sb_states = 0;
   // optional per-kernel timing of pc_step_fused (bench.py roofline leg)
   bool timing = false;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;  // around the UKF kernel
@@ -86,6 +90,20 @@ int ensure_ws(pc_ctx* ctx, size_t bytes) {
   return PC_OK;
 }
 inline size_t align256(size_t x) { return (x + 255) & ~size_t(255); }
+
+int ensure_sb(pc_ctx* ctx, int64_t ld) {
+  if ((size_t)ld <= ctx->sb_states) return PC_OK;
+  if (ctx->sb) cudaFree(ctx->sb);
+  if (ctx->sbf) cudaFree(ctx->sbf);
+  ctx->sb = nullptr;
+  ctx->sbf = nullptr;
+  ctx->sb_states = 0;
+  const size_t want = (size_t)ld + (size_t)(ld >> 2) + 64;
+  PC_CUDA_TRY(ctx, cudaMalloc(&ctx->sb, 14 * 6 * want * sizeof(double)));
+  PC_CUDA_TRY(ctx, cudaMalloc(&ctx->sbf, want * sizeof(uint32_t)));
+  ctx->sb_states = want;
+  return PC_OK;
+}
 }  // namespace
 
 #define PC_REQUIRE(ctx, cond, msg) \
@@ -120,6 +138,8 @@ int pc_ctx_destroy(pc_ctx* ctx) {
   {
     DeviceGuard g(ctx->device);
     if (ctx->ws) cudaFree(ctx->ws);
+    if (ctx->sb) cudaFree(ctx->sb);
+    if (ctx->sbf) cudaFree(ctx->sbf);
     if (ctx->host_stream) cudaStreamDestroy(ctx->host_stream);
     if (ctx->ev0) cudaEventDestroy(ctx->ev0);
     if (ctx->ev1) cudaEventDestroy(ctx->ev1);
@@ -335,17 +355,24 @@ int pc_ukf_predict_update(pc_ctx* ctx, double* est_x, double* est_p, double* tru
   if (rc) return rc;
   if (n == 0) return PC_OK;
   DeviceGuard g(ctx->device);
+  cudaStream_t st = (cudaStream_t)stream;
+  rc = ensure_sb(ctx, ld);
+  if (rc) return rc;
+  // stage 1: Cholesky + sigma points into the context's sigma buffer (ld == row stride there too)
+  PC_CUDA_TRY(ctx, pc::launch_sigma_gen(est_x, est_p, truth_x, ctx->sb, n, ld, params->gamma, ctx->sbf, st));
+  // stage 2: all 13 (+1) n states
+  PC_CUDA_TRY(ctx, pc::launch_propagate_sigma(ctx->sb, n, ld, truth_x != nullptr, t0, tf, substeps,
+                                              force_model, ctx->sbf, st));
+  // stage 3: unscented transform + update
   pc::UkfArgs u{};
-  u.est_x = est_x;
+  u.sb = ctx->sb;
   u.est_p = est_p;
-  u.truth_x = truth_x;
   u.z = z;
   u.tasked = const_cast<uint8_t*>(tasked);
   u.n = n;
   u.ld = ld;
   u.dt = tf - t0;
   u.t_now = tf;
-  u.substeps = substeps;
   u.rng_seed = rng_seed;
   u.rng_step = rng_step;
   u.out_pred_x = out_pred_x;
@@ -353,8 +380,25 @@ int pc_ukf_predict_update(pc_ctx* ctx, double* est_x, double* est_p, double* tru
   u.out_nis = out_nis;
   u.out_flags = out_flags;
   u.out_z = out_z;
+  u.sig_flags = ctx->sbf;
+  u.est_x_out = est_x;
+  u.truth_out = truth_x;
   u.p = *params;
-  PC_CUDA_TRY(ctx, pc::launch_ukf(u, force_model, (cudaStream_t)stream));
+  PC_CUDA_TRY(ctx, pc::launch_ukf_finish(u, st));
+  ctx->launches += 2;
+  ctx->launches += 1;
+  return PC_OK;
+}
+
+int pc_sigma_points(pc_ctx* ctx, const double* est_x, const double* est_p, int64_t n, int64_t ld,
+                    double gamma, double* sigma_ws, uint32_t* sig_flags, pc_stream stream) {
+  PC_REQUIRE(ctx, ctx != nullptr, "null context");
+  PC_REQUIRE(ctx, n >= 0 && ld >= n, "need 0 <= n <= ld");
+  if (n == 0) return PC_OK;
+  PC_REQUIRE(ctx, est_x && est_p && sigma_ws && sig_flags, "null pointer");
+  DeviceGuard g(ctx->device);
+  PC_CUDA_TRY(ctx, pc::launch_sigma_gen(est_x, est_p, nullptr, sigma_ws, n, ld, gamma, sig_flags,
+                                        (cudaStream_t)stream));
   ctx->launches += 1;
   return PC_OK;
 }
@@ -519,54 +563,37 @@ int pc_step_fused(pc_ctx* ctx, const pc_step_args* a, const pc_ukf_params* param
   PC_REQUIRE(ctx, !a->actions || (a->tasked && (a->vis_est || a->M == 0)),
              "actions need a tasked workspace and the estimated vis map");
   PC_REQUIRE(ctx, a->policy_probes >= 0 && a->policy_probes <= 4096, "bad policy_probes");
+  const bool own_sb = a->sigma_ws != nullptr;
+  if (own_sb && a->N > 0) {
+    PC_REQUIRE(ctx, a->sig_flags != nullptr, "sigma_ws needs sig_flags");
+    PC_REQUIRE(ctx, a->est_x == a->sigma_ws && a->truth_x == a->sigma_ws + 13 * 6 * a->ld,
+               "with sigma_ws, est_x must be its block 0 and truth_x its block 13");
+  }
   DeviceGuard g(ctx->device);
   cudaStream_t s = (cudaStream_t)stream;
-  const bool fuse_vis = want_vis && a->sens_q != nullptr && a->M > 0 && a->M <= 1024 && a->N > 0;
+  if (!own_sb && a->N > 0) {
+    rc = ensure_sb(ctx, a->ld);
+    if (rc) return rc;
+  }
+  double* sb = own_sb ? a->sigma_ws : ctx->sb;
+  uint32_t* sbf = own_sb ? a->sig_flags : ctx->sbf;
   // 1. sensors (Agent.propagate per sensor; terrestrial ones are a rotation), tasking mask from
   //    the actions and the PREVIOUS estimated vis map, step clock latch
   if (a->M > 0 || a->clock) {
     PC_CUDA_TRY(ctx, pc::launch_pre_step(a->sens_x, a->sens_kind, a->M, a->ld_s, a->t0, a->tf, a->substeps,
-                                         a->force_model, fuse_vis ? a->sens_q : nullptr, a->body_radius,
-                                         a->vis_tol, a->clock, a->actions, a->vis_est,
-                                         const_cast<uint8_t*>(a->tasked), a->N, a->words_per_row,
-                                         a->policy_probes, a->policy_seed, a->rng_step, s));
+                                         a->force_model, nullptr, a->body_radius, a->vis_tol, a->clock,
+                                         a->actions, a->vis_est, const_cast<uint8_t*>(a->tasked), a->N,
+                                         a->words_per_row, a->policy_probes, a->policy_seed, a->rng_step, s));
     ctx->launches += 1;
   }
-  // 2. targets: truth + UKF + summaries (+ both vis maps when fused)
+  // 2. targets: sigma points (only when not carried over from the previous step), all 14 N
+  //    states propagated, then transform + update + summaries + next step's sigma points
   if (a->N > 0) {
-    pc::UkfArgs u{};
-    u.est_x = a->est_x;
-    u.est_p = a->est_p;
-    u.truth_x = a->truth_x;
-    u.z = a->z;
-    u.tasked = const_cast<uint8_t*>(a->tasked);
-    u.n = a->N;
-    u.ld = a->ld;
-    u.dt = a->tf - a->t0;
-    u.t_now = a->tf;
-    u.substeps = a->substeps;
-    u.rng_seed = a->rng_seed;
-    u.rng_step = a->rng_step;
-    u.out_pred_p = a->pred_p;
-    u.out_nis = a->nis;
-    u.out_flags = a->flags;
-    u.num_tasked = a->num_tasked;
-    u.last_time_tasked = a->last_time_tasked;
-    u.tr_pos = a->tr_pos;
-    u.tr_vel = a->tr_vel;
-    u.clock = a->clock;
-    u.advance_clock = a->clock != nullptr;
-    u.clear_tasked = a->actions != nullptr;
-    if (fuse_vis) {
-      u.sens_q = reinterpret_cast<const double4*>(a->sens_q);
-      u.M = (int)a->M;
-      u.wpr = (int)a->words_per_row;
-      u.vis_truth = a->vis_truth;
-      u.vis_est = a->vis_est;
-      u.body_radius = a->body_radius;
-      u.vis_tol = a->vis_tol;
+    if (!own_sb || !a->sigma_valid) {
+      PC_CUDA_TRY(ctx, pc::launch_sigma_gen(a->est_x, a->est_p, a->truth_x, sb, a->N, a->ld, params->gamma,
+                                            sbf, s));
+      ctx->launches += 1;
     }
-    u.p = *params;
     unsigned evflags = cudaEventRecordDefault;
     if (ctx->timing) {
       cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
@@ -574,15 +601,43 @@ int pc_step_fused(pc_ctx* ctx, const pc_step_args* a, const pc_ukf_params* param
       if (cap == cudaStreamCaptureStatusActive) evflags = cudaEventRecordExternal;
       PC_CUDA_TRY(ctx, cudaEventRecordWithFlags(ctx->ev0, s, evflags));
     }
-    PC_CUDA_TRY(ctx, pc::launch_ukf(u, a->force_model, s));
+    PC_CUDA_TRY(ctx, pc::launch_propagate_sigma(sb, a->N, a->ld, 1, a->t0, a->tf, a->substeps,
+                                                a->force_model, sbf, s));
     if (ctx->timing) PC_CUDA_TRY(ctx, cudaEventRecordWithFlags(ctx->ev1, s, evflags));
-    ctx->launches += 1;
+    pc::UkfArgs u{};
+    u.sb = sb;
+    u.est_p = a->est_p;
+    u.z = a->z;
+    u.tasked = const_cast<uint8_t*>(a->tasked);
+    u.clear_tasked = a->actions != nullptr;
+    u.n = a->N;
+    u.ld = a->ld;
+    u.dt = a->tf - a->t0;
+    u.t_now = a->tf;
+    u.rng_seed = a->rng_seed;
+    u.rng_step = a->rng_step;
+    u.clock = a->clock;
+    u.advance_clock = a->clock != nullptr;
+    u.out_pred_p = a->pred_p;
+    u.out_nis = a->nis;
+    u.out_flags = a->flags;
+    u.num_tasked = a->num_tasked;
+    u.last_time_tasked = a->last_time_tasked;
+    u.tr_pos = a->tr_pos;
+    u.tr_vel = a->tr_vel;
+    u.sig_flags = sbf;
+    u.gen_next = own_sb ? 1 : 0;
+    u.est_x_out = own_sb ? nullptr : a->est_x;
+    u.truth_out = own_sb ? nullptr : a->truth_x;
+    u.p = *params;
+    PC_CUDA_TRY(ctx, pc::launch_ukf_finish(u, s));
+    ctx->launches += 2;
   } else if (a->clock) {
     PC_CUDA_TRY(ctx, pc::launch_advance_clock(a->clock, a->tf - a->t0, s));
     ctx->launches += 1;
   }
-  // 3. both visibility maps for the next step (env.py:455-462) when not fused above
-  if (want_vis && !fuse_vis && a->M > 0 && a->N > 0) {
+  // 3. both visibility maps for the next step (env.py:455-462)
+  if (want_vis && a->M > 0 && a->N > 0) {
     PC_CUDA_TRY(ctx, pc::launch_vismap_packed(a->sens_x, a->M, a->ld_s, nullptr, 0.0, a->truth_x,
                                               a->est_x, a->N, a->ld, a->body_radius, a->vis_tol,
                                               a->vis_truth, a->vis_est, a->words_per_row, s));

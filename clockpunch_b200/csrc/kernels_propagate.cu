@@ -5,7 +5,7 @@
 namespace pc {
 
 template <bool J2>
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(128, 5)
 propagate_agents_kernel(const double* __restrict__ x_in, double* __restrict__ x_out,
                         const uint8_t* __restrict__ kind, int default_kind, int64_t n, int64_t ld,
                         double dt, int substeps, double cs, double sn) {
@@ -46,6 +46,58 @@ cudaError_t launch_propagate_agents(const double* x_in, double* x_out, const uin
   else
     propagate_agents_kernel<false><<<blocks, threads, 0, stream>>>(x_in, x_out, kind, default_kind,
                                                                    n, ld, dt, substeps, cs, sn);
+  return cudaGetLastError();
+}
+
+// K_b of the UKF pipeline: every state of the sigma buffer (14 blocks of (6, ld): 13 sigma points
+// + the truth state per target) advanced in place, one thread per state, blockIdx.y = block.
+// All 13 sigma points of a target must take the SAME number of substeps (their differences are
+// multiplied by weights of order 1e5..1e6), so blocks 1..12 derive the count from the centre point.
+template <bool J2>
+__global__ void __launch_bounds__(128, 5)
+propagate_sigma_kernel(double* __restrict__ sb, int64_t n, int64_t ld, double dt, int substeps,
+                       uint32_t* __restrict__ sig_flags) {
+  const int64_t t = (int64_t)blockIdx.x * 128 + threadIdx.x;
+  if (t >= n) return;
+  const int i = blockIdx.y;
+  double* base = sb + (int64_t)i * 6 * ld + t;
+  int nsub = substeps;
+  if (nsub <= 0) {
+    // blocks 1..12 take the centre point's count; the centre (0) and the truth (13) their own
+    const double* src = (i == 13) ? base : sb + t;
+    double rc[3], vc[3];
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      rc[c] = src[(int64_t)c * ld];
+      vc[c] = src[(int64_t)(c + 3) * ld];
+    }
+    bool cl = false;
+    nsub = auto_substeps(rc, vc, dt, &cl);
+    if (i == 0 && cl && sig_flags) sig_flags[t] |= PC_FLAG_SUBSTEP_CLAMP;
+  }
+  double r[3], v[3];
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    r[c] = base[(int64_t)c * ld];
+    v[c] = base[(int64_t)(c + 3) * ld];
+  }
+  propagate_state<J2>(r, v, dt, nsub);
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    base[(int64_t)c * ld] = r[c];
+    base[(int64_t)(c + 3) * ld] = v[c];
+  }
+}
+
+cudaError_t launch_propagate_sigma(double* sb, int64_t n, int64_t ld, int have_truth, double t0,
+                                   double tf, int substeps, int force_model, uint32_t* sig_flags,
+                                   cudaStream_t stream) {
+  if (n <= 0) return cudaSuccess;
+  const dim3 grid((unsigned)((n + 127) / 128), have_truth ? 14 : 13);
+  if (force_model == PC_FORCE_TWOBODY_J2)
+    propagate_sigma_kernel<true><<<grid, 128, 0, stream>>>(sb, n, ld, tf - t0, substeps, sig_flags);
+  else
+    propagate_sigma_kernel<false><<<grid, 128, 0, stream>>>(sb, n, ld, tf - t0, substeps, sig_flags);
   return cudaGetLastError();
 }
 

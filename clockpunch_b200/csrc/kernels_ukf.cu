@@ -6,25 +6,20 @@
 // per target per step from Target.updateNonPhysical (common/agents.py:144-171), plus
 // Agent.propagate for the truth state (agents.py:59-71).
 //
-// Mapping: FOUR lanes per target ("quad"), eight targets per warp, one warp per CTA, nothing
-// but warp-level synchronisation.  The 13 sigma points are handled as 6 (+,-) pairs plus the
-// centre point; lanes 0..2 of a quad integrate two pairs each and lane 3 integrates the centre
-// point together with the target's TRUTH state.  A pair is advanced by one interleaved
-// two-state DOP853 (same step size), which gives every lane two independent dependency chains
-// and keeps every stage in registers.  Because x+ and x- of a pair live in the same lane the
-// unscented transform needs no data exchange until the very end:
-//   load     coalesced CTA-wide copy of the 8 covariance tiles (8*36 contiguous doubles) and
-//            the SoA state columns into shared memory
-//   factor   upper Cholesky of est_p, evaluated by all four lanes of the quad (SIMD: the eight
-//            targets of the warp are factored in one pass)
-//   sigma    per pair: s = x+ + x-,  D = x+ - x-   (kept in registers)
-//   unscent  pred_x from sum(s) and the centre point (quad shuffle all-reduce of 6 values);
-//            pred_p = wc0 m m^T + w sum_j [2 a_j a_j^T + D_j D_j^T / 2] + Q with
-//            a_j = s_j/2 - pred_x, reduced over the quad (21 values)
-//   update   tasked targets only: one lane per target runs the measurement update on a
-//            shared-memory copy (second Cholesky, S, C, gain via triangular solves, NIS)
-//   vis      lanes = sensors: each warp ballot is one 32-bit word of a packed vis-map row
-//   store    coalesced copies of the est_p / pred_p tiles, SoA columns for the states
+// Mapping -- a staged pipeline, each stage with the thread mapping that suits it (measured:
+// profiles/r1_notes.md; single fused kernels with 16 or 4 lanes per target spent 2/3 of their
+// issue slots on cross-lane scaffolding and thrashed the instruction cache):
+//   sigma_gen_kernel      one THREAD per target: upper Cholesky of est_p, 13 sigma points written
+//                         to the sigma buffer SB (14 blocks of (6, ld) SoA: block 0 = centre =
+//                         est_x, 1..6 = +gamma U[:, j], 7..12 = -gamma U[:, j], 13 = truth state)
+//   propagate_sigma_kernel (kernels_propagate.cu) one THREAD per state: all 14 N states advanced
+//                         in place, every DOP853 stage in registers, fully coalesced
+//   ukf_finish_kernel     one THREAD per target: unscented transform streamed over the 6 (+,-)
+//                         pairs, measurement update for tasked targets, outputs, and -- so that
+//                         the next step starts at the propagation stage -- the Cholesky factor and
+//                         sigma points of the NEW estimate (gen_next)
+// In steady state a step is therefore propagate -> finish; est_x IS block 0 and the truth state IS
+// block 13 of SB, so nothing is copied.
 //
 // Numerics: the reference forms pred_x = sum_i w_i X_i with w_0 = -2e6, w_i = +1.67e5, which
 // loses ~1e-6 km to cancellation.  Here the same quantity is evaluated as
@@ -33,16 +28,17 @@
 // eps_w = sum w - 1 is computed exactly from them) but carries no cancellation noise.  The
 // resampled measurement sigma points of forecast() (ukf_v2.py:211-228) are symmetric about
 // pred_x, so their weighted sums are expanded analytically in the same exact-weights form
-// (derivation in DESIGN.md "UKF update").
+// (derivation in DESIGN.md "UKF update").  With x+ and x- of pair j in hand,
+//   Xres+ Xres+^T + Xres- Xres-^T = 2 a_j a_j^T + D_j D_j^T / 2,
+//   a_j = (x+ + x-)/2 - pred_x,  D_j = x+ - x-,
+// which is how pred_p is accumulated (again algebraically identical to ukf_v2.py:286-292).
 #include "propagate.cuh"
 #include "ukf_args.cuh"
 #include "vis.cuh"
 
 namespace pc {
 
-constexpr int kTPW = 8;  // targets per warp
-
-struct TargetSmem {   // scratch of the measurement update (tasked targets)
+struct TargetSmem {   // scratch of the measurement update (thread-local for tasked targets)
   double D[6][6];     // D[j][a] = (X_{1+j} - X_{7+j})[a]: difference of the propagated +/- pair j
   double U[21];       // packed upper Cholesky factor (row-major, j >= i)
   double px[6];       // pred_x
@@ -52,17 +48,8 @@ struct TargetSmem {   // scratch of the measurement update (tasked targets)
   double nis;
   uint32_t flags;
   int pad;
-  double* P;          // pred_p tile (36)
-  double* PE;         // est_p tile out (36)
-};
-
-struct WarpSmem {
-  double P[kTPW][36];    // in: est_p tiles; out: pred_p tiles       (contiguous: coalesced copies)
-  double PE[kTPW][36];   // out: est_p tiles
-  double xs[kTPW][6];    // est_x in / out
-  double tr[kTPW][6];    // truth in / out
-  double4 tv[kTPW][2];   // (truth', est_x') position + horizon term for the fused vis test
-  TargetSmem t[kTPW];
+  double P[36];       // pred_p
+  double PE[36];      // est_p out
 };
 
 __host__ __device__ constexpr int uidx(int i, int j) { return i * 6 - (i * (i - 1)) / 2 + (j - i); }
@@ -223,369 +210,250 @@ __device__ __noinline__ void measurement_update(TargetSmem* __restrict__ S, cons
   S->flags |= flags;
 }
 
-__device__ __forceinline__ double quad_sum(double x) {
-  x += __shfl_xor_sync(0xffffffffu, x, 1);
-  x += __shfl_xor_sync(0xffffffffu, x, 2);
-  return x;
+// Upper Cholesky of a symmetric 6x6 given by its packed upper triangle E (uidx order).
+__device__ __forceinline__ bool chol_upper6_packed(const double (&E)[21], double (&U)[21]) {
+  bool ok = true;
+#pragma unroll
+  for (int i = 0; i < 6; ++i) {
+    double s = E[uidx(i, i)];
+#pragma unroll
+    for (int k = 0; k < i; ++k) s = fma(-U[uidx(k, i)], U[uidx(k, i)], s);
+    ok = ok && (s > 0.0);
+    const double d = rsqrt_fast(s);
+    U[uidx(i, i)] = s * d;
+#pragma unroll
+    for (int j = i + 1; j < 6; ++j) {
+      double a = E[uidx(i, j)];
+#pragma unroll
+      for (int k = 0; k < i; ++k) a = fma(-U[uidx(k, i)], U[uidx(k, j)], a);
+      U[uidx(i, j)] = a * d;
+    }
+  }
+  return ok;
 }
 
-// One (+,-) sigma pair: x +- col, both members advanced in lock-step; returns sum and
-// difference of the propagated members.
-template <bool J2>
-__device__ __forceinline__ void propagate_pair(const double (&x)[6], const double (&col)[6], double dt,
-                                               int ns, double (&sum)[6], double (&dif)[6]) {
-  double r[2][3], v[2][3];
+// generateSigmaPoints (ukf_v2.py:158-183): x + gamma * [0, U, -U], COLUMNS of the upper factor.
+__device__ __forceinline__ void write_sigma_blocks(double* __restrict__ sb, int64_t ld, int64_t t,
+                                                   const double (&x)[6], const double (&U)[21],
+                                                   double gamma) {
+  const int64_t blk = 6 * ld;
 #pragma unroll
-  for (int c = 0; c < 3; ++c) {
-    r[0][c] = x[c] + col[c];
-    r[1][c] = x[c] - col[c];
-    v[0][c] = x[c + 3] + col[c + 3];
-    v[1][c] = x[c + 3] - col[c + 3];
-  }
-  propagate_states<2, J2>(r, v, dt, ns);
+  for (int c = 0; c < 6; ++c) sb[(int64_t)c * ld + t] = x[c];
 #pragma unroll
-  for (int c = 0; c < 3; ++c) {
-    sum[c] = r[0][c] + r[1][c];
-    dif[c] = r[0][c] - r[1][c];
-    sum[c + 3] = v[0][c] + v[1][c];
-    dif[c + 3] = v[0][c] - v[1][c];
-  }
+  for (int j = 0; j < 6; ++j)
+#pragma unroll
+    for (int c = 0; c < 6; ++c) {
+      const double g = (c <= j) ? gamma * U[uidx(c <= j ? c : j, j)] : 0.0;
+      sb[(1 + j) * blk + (int64_t)c * ld + t] = x[c] + g;
+      sb[(7 + j) * blk + (int64_t)c * ld + t] = x[c] - g;
+    }
 }
 
-template <int MAXREG, bool J2>
-__global__ void __launch_bounds__(32) __maxnreg__(MAXREG)
-ukf_step_kernel(const __grid_constant__ UkfArgs a) {
-  __shared__ __align__(16) WarpSmem W;
-  const int lane = threadIdx.x;
-  const int tl = lane >> 2, q = lane & 3;       // target within the warp, lane within the quad
-  const int64_t first = (int64_t)blockIdx.x * kTPW;
-  const int64_t tg = first + tl;
-  const int nlive = (int)min((int64_t)kTPW, a.n - first);
-  const bool live = tl < nlive;
-  const bool have_truth = a.truth_x != nullptr;
+__global__ void __launch_bounds__(128)
+sigma_gen_kernel(const double* __restrict__ est_x, const double* __restrict__ est_p,
+                 const double* __restrict__ truth_x, double* __restrict__ sb, int64_t n, int64_t ld,
+                 double gamma, uint32_t* __restrict__ sig_flags) {
+  const int64_t t = (int64_t)blockIdx.x * 128 + threadIdx.x;
+  if (t >= n) return;
+  double x[6], E[21], U[21];
+#pragma unroll
+  for (int c = 0; c < 6; ++c) x[c] = est_x[(int64_t)c * ld + t];
+  const double* P = est_p + t * 36;
+#pragma unroll
+  for (int i = 0; i < 6; ++i)
+#pragma unroll
+    for (int j = i; j < 6; ++j) E[uidx(i, j)] = P[i * 6 + j];
+  const bool ok = chol_upper6_packed(E, U);
+  write_sigma_blocks(sb, ld, t, x, U, gamma);
+  if (truth_x && truth_x != sb + 13 * 6 * ld) {
+#pragma unroll
+    for (int c = 0; c < 6; ++c) sb[13 * 6 * ld + (int64_t)c * ld + t] = truth_x[(int64_t)c * ld + t];
+  }
+  sig_flags[t] = ok ? 0u : (uint32_t)PC_FLAG_NONPD_EST;
+}
 
-  // ---- load: coalesced, everything requested before anything waits ---------------------------
-  {
-    const double* gp = a.est_p + first * 36;
-    double* sp = &W.P[0][0];
-    double pv[9];
-#pragma unroll
-    for (int i = 0; i < 9; ++i) pv[i] = (lane + 32 * i < nlive * 36) ? gp[lane + 32 * i] : 0.0;
-    double xv[2] = {0.0, 0.0}, tv[2] = {0.0, 0.0};
-#pragma unroll
-    for (int i = 0; i < 2; ++i) {
-      const int k = lane + 32 * i, c = k >> 3, t = k & 7;
-      if (k < 48 && t < nlive) {
-        xv[i] = a.est_x[(int64_t)c * a.ld + first + t];
-        if (have_truth) tv[i] = a.truth_x[(int64_t)c * a.ld + first + t];
-      }
-    }
-    int tk = 0;
-    if (live && q == 0 && a.tasked) {
-      tk = a.tasked[tg] != 0;
-      if (tk && a.clear_tasked) a.tasked[tg] = 0;
-    }
-#pragma unroll
-    for (int i = 0; i < 9; ++i) sp[lane + 32 * i] = pv[i];
-#pragma unroll
-    for (int i = 0; i < 2; ++i) {
-      const int k = lane + 32 * i, c = k >> 3, t = k & 7;
-      if (k < 48) {
-        W.xs[t][c] = xv[i];
-        W.tr[t][c] = tv[i];
-      }
-    }
-    if (q == 0) {
-      W.t[tl].flags = (uint32_t)tk << 31;  // bit 31: tasked (internal)
-      W.t[tl].nis = __longlong_as_double(0x7ff8000000000000LL);
-      W.t[tl].P = W.P[tl];
-      W.t[tl].PE = W.PE[tl];
-    }
+__global__ void __launch_bounds__(128)
+ukf_finish_kernel(const __grid_constant__ UkfArgs a) {
+  const int64_t t = (int64_t)blockIdx.x * 128 + threadIdx.x;
+  if (a.clock && a.advance_clock && t == 0) {
+    // nobody reads t_now / step during this launch (kernels read the t_cur / step_cur copies)
+    a.clock->t_now += a.dt;
+    a.clock->step += 1;
   }
-  const double t_now = a.clock ? a.clock->t_cur + a.dt : a.t_now;
-  const uint64_t rng_step = a.clock ? a.clock->step_cur : a.rng_step;
-  __syncwarp();
-
-  // ---- factor (generateSigmaPoints, ukf_v2.py:158-183) ---------------------------------------
-  double x[6];
-#pragma unroll
-  for (int c = 0; c < 6; ++c) x[c] = W.xs[tl][c];
-  double col0[6], col1[6];  // gamma * columns (2q) and (2q+1) of the upper factor
-  bool chol_ok;
-  {
-    double U[21];
-    chol_ok = chol_upper6(W.P[tl], U);
-#pragma unroll
-    for (int c = 0; c < 6; ++c) {
-      // column j has entries U[c][j] for c <= j
-      const double u0 = (c <= 0) ? U[uidx(c, c <= 0 ? 0 : c)] : 0.0;
-      const double u1 = (c <= 1) ? U[uidx(c, c <= 1 ? 1 : c)] : 0.0;
-      const double u2 = (c <= 2) ? U[uidx(c, c <= 2 ? 2 : c)] : 0.0;
-      const double u3 = (c <= 3) ? U[uidx(c, c <= 3 ? 3 : c)] : 0.0;
-      const double u4 = (c <= 4) ? U[uidx(c, c <= 4 ? 4 : c)] : 0.0;
-      const double u5 = U[uidx(c, 5)];
-      col0[c] = a.p.gamma * (q == 0 ? u0 : (q == 1 ? u2 : u4));
-      col1[c] = a.p.gamma * (q == 0 ? u1 : (q == 1 ? u3 : u5));
-    }
-  }
-
-  // ---- sigma points --------------------------------------------------------------------------
-  int ns = a.substeps;
-  bool clamp = false;
-  {
-    const double r0[3] = {x[0], x[1], x[2]}, v0[3] = {x[3], x[4], x[5]};
-    if (ns <= 0) ns = auto_substeps(r0, v0, a.dt, &clamp);  // identical in the four lanes
-  }
-  double s0[6], d0[6], s1[6], d1[6];  // lanes 0..2: two pairs; lane 3: s0 = centre, s1 = truth
-  if (q < 3) {
-    propagate_pair<J2>(x, col0, a.dt, ns, s0, d0);
-    propagate_pair<J2>(x, col1, a.dt, ns, s1, d1);
-  } else {
-    double tr[6];
-#pragma unroll
-    for (int c = 0; c < 6; ++c) tr[c] = have_truth ? W.tr[tl][c] : x[c];
-    const double rt[3] = {tr[0], tr[1], tr[2]}, vt[3] = {tr[3], tr[4], tr[5]};
-    const int nt = a.substeps > 0 ? a.substeps : auto_substeps(rt, vt, a.dt, nullptr);
-    if (nt == ns) {
-      double r[2][3] = {{x[0], x[1], x[2]}, {tr[0], tr[1], tr[2]}};
-      double v[2][3] = {{x[3], x[4], x[5]}, {tr[3], tr[4], tr[5]}};
-      propagate_states<2, J2>(r, v, a.dt, ns);
-#pragma unroll
-      for (int c = 0; c < 3; ++c) {
-        s0[c] = r[0][c]; s0[c + 3] = v[0][c];
-        s1[c] = r[1][c]; s1[c + 3] = v[1][c];
-      }
-    } else {  // centre and truth want different step counts: integrate them one after the other
-      double r[3] = {x[0], x[1], x[2]}, v[3] = {x[3], x[4], x[5]};
-      propagate_state<J2>(r, v, a.dt, ns);
-      double r2[3] = {tr[0], tr[1], tr[2]}, v2[3] = {tr[3], tr[4], tr[5]};
-      propagate_state<J2>(r2, v2, a.dt, nt);
-#pragma unroll
-      for (int c = 0; c < 3; ++c) {
-        s0[c] = r[c]; s0[c + 3] = v[c];
-        s1[c] = r2[c]; s1[c + 3] = v2[c];
-      }
-    }
-#pragma unroll
-    for (int c = 0; c < 6; ++c) {
-      d0[c] = 0.0;
-      d1[c] = 0.0;
-    }
-  }
-  __syncwarp();
+  if (t >= a.n) return;
+  const int64_t ld = a.ld, blk = 6 * a.ld;
+  const double* __restrict__ sb = a.sb;
 
   // ---- unscented transform (predictStateEstimate / predictCovariance, ukf_v2.py:261-292) ------
-  // X_0 from lane 3; sum over the 12 outer points of (X_i - X_0) = sum_j s_j - 12 X_0
-  double X0[6], m[6], px[6];
-  const int l3 = lane | 3;
+  double X0[6];
 #pragma unroll
-  for (int c = 0; c < 6; ++c) {
-    X0[c] = __shfl_sync(0xffffffffu, s0[c], l3);
-    // each pair contributes (s_j - 2 X_0): differences first, then the (small) sum
-    const double part = (q < 3) ? (s0[c] - 2.0 * X0[c]) + (s1[c] - 2.0 * X0[c]) : 0.0;
-    m[c] = fma(a.p.wi, quad_sum(part), a.p.eps_w * X0[c]);
-    px[c] = X0[c] + m[c];  // pred_x = sigma_points . mean_weight
+  for (int c = 0; c < 6; ++c) X0[c] = sb[(int64_t)c * ld + t];
+  double Sb[6], Ebb[21], EDD[21];
+#pragma unroll
+  for (int c = 0; c < 6; ++c) Sb[c] = 0.0;
+#pragma unroll
+  for (int k = 0; k < 21; ++k) {
+    Ebb[k] = 0.0;
+    EDD[k] = 0.0;
   }
-  // pred_p = Xres Wc Xres^T + Q; for a pair  Xres+ Xres+^T + Xres- Xres-^T = 2 a a^T + D D^T / 2
-  double E[21];
-  {
-    double a0[6], a1[6];
+#pragma unroll 2
+  for (int j = 0; j < 6; ++j) {
+    double b[6], D[6];
 #pragma unroll
     for (int c = 0; c < 6; ++c) {
-      a0[c] = 0.5 * (s0[c] - 2.0 * X0[c]) - m[c];
-      a1[c] = 0.5 * (s1[c] - 2.0 * X0[c]) - m[c];
+      const double xp = sb[(1 + j) * blk + (int64_t)c * ld + t];
+      const double xm = sb[(7 + j) * blk + (int64_t)c * ld + t];
+      b[c] = 0.5 * ((xp - X0[c]) + (xm - X0[c]));  // (x+ + x-)/2 - X_0
+      D[c] = xp - xm;
+      Sb[c] += b[c];
     }
 #pragma unroll
     for (int ra = 0; ra < 6; ++ra)
 #pragma unroll
       for (int rb = ra; rb < 6; ++rb) {
-        double e;
-        if (q < 3) {
-          e = fma(0.5 * d0[ra], d0[rb], 2.0 * a0[ra] * a0[rb]);
-          e = fma(0.5 * d1[ra], d1[rb], fma(2.0 * a1[ra], a1[rb], e));
-          e *= a.p.wi;
-        } else {
-          e = fma(a.p.wc0 * m[ra], m[rb], a.p.Q[ra * 6 + rb]);
-        }
-        E[uidx(ra, rb)] = quad_sum(e);
+        Ebb[uidx(ra, rb)] = fma(b[ra], b[rb], Ebb[uidx(ra, rb)]);
+        EDD[uidx(ra, rb)] = fma(D[ra], D[rb], EDD[uidx(ra, rb)]);
       }
   }
+  double m[6], px[6];
+#pragma unroll
+  for (int c = 0; c < 6; ++c) {
+    m[c] = fma(2.0 * a.p.wi, Sb[c], a.p.eps_w * X0[c]);  // sum_i (X_i - X_0) = 2 sum_j b_j
+    px[c] = X0[c] + m[c];                                  // pred_x = sigma_points . mean_weight
+  }
+  double E[21];  // pred_p = Xres Wc Xres^T + Q
+#pragma unroll
+  for (int ra = 0; ra < 6; ++ra)
+#pragma unroll
+    for (int rb = ra; rb < 6; ++rb) {
+      const int k = uidx(ra, rb);
+      // sum_j a_j a_j^T with a_j = b_j - m
+      const double aa = fma(6.0 * m[ra], m[rb], Ebb[k] - (Sb[ra] * m[rb] + m[ra] * Sb[rb]));
+      E[k] = fma(a.p.wi, fma(2.0, aa, 0.5 * EDD[k]), fma(a.p.wc0 * m[ra], m[rb], a.p.Q[ra * 6 + rb]));
+    }
 
-  // ---- no-measurement result (update(None), ukf_v2.py:238-244) ----------------------------------
-  const unsigned fl = W.t[tl].flags;
-  const bool tasked = (fl >> 31) != 0;
-  const unsigned any_tasked = __ballot_sync(0xffffffffu, live && tasked);
-  if (q == 0) {
-    // pred_p tile (and est_p = pred_p for untasked targets)
+  // ---- update ----------------------------------------------------------------------------------
+  int tasked = 0;
+  if (a.tasked) {
+    tasked = a.tasked[t] != 0;
+    if (tasked && a.clear_tasked) a.tasked[t] = 0;
+  }
+  uint32_t flags = a.sig_flags ? a.sig_flags[t] : 0u;
+  double xe[6], PE[21];
+  double nis = __longlong_as_double(0x7ff8000000000000LL);
+  if (a.out_pred_p) {
+    double* gq = a.out_pred_p + t * 36;
 #pragma unroll
     for (int ra = 0; ra < 6; ++ra)
 #pragma unroll
-      for (int rb = 0; rb < 6; ++rb) {
-        const double e = E[ra <= rb ? uidx(ra, rb) : uidx(rb, ra)];
-        W.P[tl][ra * 6 + rb] = e;
-        W.PE[tl][ra * 6 + rb] = e;
-      }
+      for (int rb = 0; rb < 6; ++rb) gq[ra * 6 + rb] = E[ra <= rb ? uidx(ra, rb) : uidx(rb, ra)];
   }
-  if (q == 3) {
+  if (tasked) {
+    const double t_now = a.clock ? a.clock->t_cur + a.dt : a.t_now;
+    const uint64_t rng_step = a.clock ? a.clock->step_cur : a.rng_step;
+    TargetSmem L;
+#pragma unroll 1
+    for (int j = 0; j < 6; ++j)
+#pragma unroll
+      for (int c = 0; c < 6; ++c)
+        L.D[j][c] = sb[(1 + j) * blk + (int64_t)c * ld + t] - sb[(7 + j) * blk + (int64_t)c * ld + t];
 #pragma unroll
     for (int c = 0; c < 6; ++c) {
-      W.xs[tl][c] = X0[c];   // est_x = propagated centre point
-      W.tr[tl][c] = s1[c];   // truth'
+      L.px[c] = px[c];
+      L.m[c] = m[c];
     }
-  }
-
-  // ---- measurement update (tasked targets only) ------------------------------------------------
-  if (any_tasked) {
-    TargetSmem* S = &W.t[tl];
-    if (tasked) {
-      if (q < 3) {
 #pragma unroll
-        for (int c = 0; c < 6; ++c) {
-          S->D[2 * q][c] = d0[c];
-          S->D[2 * q + 1][c] = d1[c];
-        }
-      } else {
+    for (int ra = 0; ra < 6; ++ra)
 #pragma unroll
-        for (int c = 0; c < 6; ++c) {
-          S->px[c] = px[c];
-          S->m[c] = m[c];
-        }
+      for (int rb = 0; rb < 6; ++rb) L.P[ra * 6 + rb] = E[ra <= rb ? uidx(ra, rb) : uidx(rb, ra)];
+    L.flags = 0;
+    if (a.z) {
+#pragma unroll
+      for (int c = 0; c < 6; ++c) L.z[c] = a.z[(int64_t)c * ld + t];
+    } else {
+      // Target.getMeasurement (agents.py:173-183): z ~ N(truth', R)
+      double nrm[6];
+      normal6(a.rng_seed, rng_step, (uint64_t)t, nrm);
+#pragma unroll
+      for (int c = 0; c < 6; ++c) {
+        double acc = sb[13 * blk + (int64_t)c * ld + t];
+#pragma unroll
+        for (int k = 0; k <= c; ++k) acc = fma(a.p.Lr[c * 6 + k], nrm[k], acc);
+        L.z[c] = acc;
       }
     }
-    __syncwarp();
-    if (live && tasked && q == 0) {
-      if (a.z) {
+    measurement_update(&L, a.p);
+    flags |= L.flags;
+    nis = L.nis;
 #pragma unroll
-        for (int c = 0; c < 6; ++c) S->z[c] = a.z[(int64_t)c * a.ld + tg];
-      } else {
-        // Target.getMeasurement (agents.py:173-183): z ~ N(truth', R)
-        double nrm[6];
-        normal6(a.rng_seed, rng_step, (uint64_t)tg, nrm);
+    for (int c = 0; c < 6; ++c) xe[c] = L.xo[c];
 #pragma unroll
-        for (int c = 0; c < 6; ++c) {
-          double acc = W.tr[tl][c];
+    for (int ra = 0; ra < 6; ++ra)
 #pragma unroll
-          for (int k = 0; k <= c; ++k) acc = fma(a.p.Lr[c * 6 + k], nrm[k], acc);
-          S->z[c] = acc;
-        }
-      }
-      measurement_update(S, a.p);
+      for (int rb = ra; rb < 6; ++rb) PE[uidx(ra, rb)] = L.PE[ra * 6 + rb];
+    if (a.out_z) {
 #pragma unroll
-      for (int c = 0; c < 6; ++c) W.xs[tl][c] = S->xo[c];
+      for (int c = 0; c < 6; ++c) a.out_z[(int64_t)c * ld + t] = L.z[c];
     }
-  }
-  __syncwarp();
-
-  // ---- flags + scheduler summaries (agents.py:157-171; env.py:446-452,599-609) -------------------
-  if (live && q == 0) {
-    const double* Pout = W.PE[tl];
-    double chk = 0.0;
+    if (a.num_tasked) a.num_tasked[t] += 1;
+    if (a.last_time_tasked) a.last_time_tasked[t] = (float)t_now;
+  } else {
+    // update(None) (ukf_v2.py:238-244): est_x = propagated centre point, est_p = pred_p
 #pragma unroll
-    for (int c = 0; c < 6; ++c) chk += W.xs[tl][c] + Pout[c * 7];
-    uint32_t f = W.t[tl].flags & 0x7fffffffu;
-    if (!chol_ok) f |= PC_FLAG_NONPD_EST;
-    if (clamp) f |= PC_FLAG_SUBSTEP_CLAMP;
-    if (!isfinite(chk)) f |= PC_FLAG_NONFINITE;
-    if (a.out_flags) a.out_flags[tg] = f;
-    if (a.out_nis) a.out_nis[tg] = W.t[tl].nis;
-    if (a.tr_pos) a.tr_pos[tg] = ((float)Pout[0] + (float)Pout[7]) + (float)Pout[14];
-    if (a.tr_vel) a.tr_vel[tg] = ((float)Pout[21] + (float)Pout[28]) + (float)Pout[35];
-    if (tasked) {
-      if (a.num_tasked) a.num_tasked[tg] += 1;
-      if (a.last_time_tasked) a.last_time_tasked[tg] = (float)t_now;
-    }
+    for (int c = 0; c < 6; ++c) xe[c] = X0[c];
+#pragma unroll
+    for (int k = 0; k < 21; ++k) PE[k] = E[k];
   }
 
-  // ---- store: coalesced tiles + SoA columns -------------------------------------------------------
+  // ---- outputs -----------------------------------------------------------------------------------
   {
-    double* ge = a.est_p + first * 36;
-    const double* se = &W.PE[0][0];
+    double* ge = a.est_p + t * 36;
 #pragma unroll
-    for (int i = 0; i < 9; ++i)
-      if (lane + 32 * i < nlive * 36) ge[lane + 32 * i] = se[lane + 32 * i];
-    if (a.out_pred_p) {
-      double* gq = a.out_pred_p + first * 36;
-      const double* sq = &W.P[0][0];
+    for (int ra = 0; ra < 6; ++ra)
 #pragma unroll
-      for (int i = 0; i < 9; ++i)
-        if (lane + 32 * i < nlive * 36) gq[lane + 32 * i] = sq[lane + 32 * i];
-    }
-#pragma unroll
-    for (int i = 0; i < 2; ++i) {
-      const int k = lane + 32 * i, c = k >> 3, t = k & 7;
-      if (k < 48 && t < nlive) {
-        const int64_t g = (int64_t)c * a.ld + first + t;
-        a.est_x[g] = W.xs[t][c];
-        if (have_truth) a.truth_x[g] = W.tr[t][c];
-        const bool tk = (W.t[t].flags >> 31) != 0;
-        if (a.out_z && tk) a.out_z[g] = W.t[t].z[c];
-      }
-    }
-    if (a.out_pred_x && live && q == 1) {
-#pragma unroll
-      for (int c = 0; c < 6; ++c) a.out_pred_x[(int64_t)c * a.ld + tg] = px[c];
-    }
+      for (int rb = 0; rb < 6; ++rb) ge[ra * 6 + rb] = PE[ra <= rb ? uidx(ra, rb) : uidx(rb, ra)];
   }
-
-  // ---- fused visibility: both packed maps for the next step (env.py:455-462) ---------------------
-  // lanes = sensors, one warp ballot = one 32-bit word of a target's row.
-  if (a.sens_q) {
-    if (live && q < 2) {
-      const double* xx = (q == 0) ? W.tr[tl] : W.xs[tl];
-      W.tv[tl][q] = make_double4(xx[0], xx[1], xx[2], horizon_q(xx[0], xx[1], xx[2], a.body_radius, a.vis_tol));
-    }
-    __syncwarp();
-    const double RE2 = a.body_radius * a.body_radius;
-    for (int w0 = 0; w0 < a.wpr; w0 += 32) {      // 32 words (1024 sensors) per pass
-      uint32_t keep[2 * kTPW];
+  double chk = 0.0;
 #pragma unroll
-      for (int k = 0; k < 2 * kTPW; ++k) keep[k] = 0u;
-      const int wend = min(a.wpr, w0 + 32);
-      for (int w = w0; w < wend; ++w) {
-        const int j = w * 32 + lane;
-        const bool on = j < a.M;
-        double4 s = make_double4(0.0, 0.0, 0.0, 0.0);
-        if (on) {
-          const double2* qq = reinterpret_cast<const double2*>(a.sens_q + j);
-          const double2 lo = __ldg(qq), hi = __ldg(qq + 1);
-          s = make_double4(lo.x, lo.y, hi.x, hi.y);
-        }
+  for (int c = 0; c < 6; ++c) chk += xe[c] + PE[uidx(c, c)];
+  if (!isfinite(chk)) flags |= PC_FLAG_NONFINITE;
+  if (a.out_flags) a.out_flags[t] = flags;
+  if (a.out_nis) a.out_nis[t] = nis;
+  // scheduler summaries (env.py:599-609: traces of the float32 est_cov blocks)
+  if (a.tr_pos) a.tr_pos[t] = ((float)PE[uidx(0, 0)] + (float)PE[uidx(1, 1)]) + (float)PE[uidx(2, 2)];
+  if (a.tr_vel) a.tr_vel[t] = ((float)PE[uidx(3, 3)] + (float)PE[uidx(4, 4)]) + (float)PE[uidx(5, 5)];
+  if (a.out_pred_x) {
 #pragma unroll
-        for (int k = 0; k < 2 * kTPW; ++k) {
-          const double4 t = W.tv[k >> 1][k & 1];
-          const uint32_t b = __ballot_sync(0xffffffffu, on && sees(s, t.x, t.y, t.z, t.w, RE2));
-          if ((w - w0) == lane) keep[k] = b;
-        }
-      }
-      if (w0 + lane < wend) {
-#pragma unroll
-        for (int k = 0; k < 2 * kTPW; ++k) {
-          if ((k >> 1) < nlive) {
-            uint32_t* dst = (k & 1) ? a.vis_est : a.vis_truth;
-            dst[(first + (k >> 1)) * a.wpr + w0 + lane] = keep[k];
-          }
-        }
-      }
-    }
+    for (int c = 0; c < 6; ++c) a.out_pred_x[(int64_t)c * ld + t] = px[c];
   }
-
-  if (a.clock && a.advance_clock && blockIdx.x == 0 && threadIdx.x == 0) {
-    // nobody reads t_now / step during this launch (kernels read the t_cur / step_cur copies)
-    a.clock->t_now += a.dt;
-    a.clock->step += 1;
+  if (a.truth_out) {
+#pragma unroll
+    for (int c = 0; c < 6; ++c) a.truth_out[(int64_t)c * ld + t] = sb[13 * blk + (int64_t)c * ld + t];
+  }
+  if (a.gen_next) {
+    // factor the NEW estimate and lay out next step's sigma points (block 0 = est_x)
+    double U[21];
+    const bool ok = chol_upper6_packed(PE, U);
+    write_sigma_blocks(a.sb, ld, t, xe, U, a.p.gamma);
+    if (a.sig_flags) a.sig_flags[t] = ok ? 0u : (uint32_t)PC_FLAG_NONPD_EST;
+  } else if (a.est_x_out) {
+#pragma unroll
+    for (int c = 0; c < 6; ++c) a.est_x_out[(int64_t)c * ld + t] = xe[c];
   }
 }
 
-cudaError_t launch_ukf(const UkfArgs& a, int force_model, cudaStream_t stream) {
+cudaError_t launch_sigma_gen(const double* est_x, const double* est_p, const double* truth_x, double* sb,
+                             int64_t n, int64_t ld, double gamma, uint32_t* sig_flags,
+                             cudaStream_t stream) {
+  if (n <= 0) return cudaSuccess;
+  sigma_gen_kernel<<<(unsigned)((n + 127) / 128), 128, 0, stream>>>(est_x, est_p, truth_x, sb, n, ld,
+                                                                   gamma, sig_flags);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_ukf_finish(const UkfArgs& a, cudaStream_t stream) {
   if (a.n <= 0) return cudaSuccess;
-  // one warp (8 targets) per CTA; 224 registers -> 9 warps resident per SM, each lane running
-  // two interleaved integrations.
-  constexpr int MAXREG = 224;
-  const unsigned blocks = (unsigned)((a.n + kTPW - 1) / kTPW);
-  if (force_model == PC_FORCE_TWOBODY_J2)
-    ukf_step_kernel<MAXREG, true><<<blocks, 32, 0, stream>>>(a);
-  else
-    ukf_step_kernel<MAXREG, false><<<blocks, 32, 0, stream>>>(a);
+  ukf_finish_kernel<<<(unsigned)((a.n + 127) / 128), 128, 0, stream>>>(a);
   return cudaGetLastError();
 }
 

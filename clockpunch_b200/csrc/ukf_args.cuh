@@ -5,15 +5,16 @@
 namespace pc {
 
 struct UkfArgs {
-  double* est_x;
-  double* est_p;
-  double* truth_x;
+  double* sb;              // sigma buffer: 14 blocks of (6, ld)
+  double* est_p;           // (N, 36) out
   const double* z;
-  uint8_t* tasked;          // read; cleared after reading when clear_tasked != 0
+  uint8_t* tasked;         // read; cleared after reading when clear_tasked != 0
+  int clear_tasked;
   int64_t n, ld;
   double dt, t_now;
-  int substeps;
   uint64_t rng_seed, rng_step;
+  pc_clock* clock;         // NULL, or: kernels read t_cur / step_cur (latched by the pre-step kernel)
+  int advance_clock;       // thread 0 advances clock->t_now / step (nobody reads those in this launch)
   double* out_pred_x;
   double* out_pred_p;
   double* out_nis;
@@ -23,18 +24,19 @@ struct UkfArgs {
   float* last_time_tasked;
   float* tr_pos;
   float* tr_vel;
-  pc_clock* clock;         // NULL, or: kernels read t_cur / step_cur (copied by the pre-step kernel)
-  int advance_clock;       // block 0 advances clock->t_now / step (nobody reads those in this launch)
-  int clear_tasked;        // reset tasked[i] after reading it (graph replay: the mask is rebuilt per step)
-  // fused visibility (both maps for the next step); sens_q == NULL disables it
-  const double4* sens_q;   // (M) sensor ECI position + horizon term, from the pre-step kernel
-  int M, wpr;
-  uint32_t* vis_truth;
-  uint32_t* vis_est;
-  double body_radius, vis_tol;
+  uint32_t* sig_flags;     // in: flags raised while generating / propagating; out: next generation
+  int gen_next;            // write the next step's sigma points (est_x = block 0) instead of est_x_out
+  double* est_x_out;       // (6, ld) when !gen_next
+  double* truth_out;       // (6, ld) copy of block 13, or NULL
   pc_ukf_params p;
 };
 
-cudaError_t launch_ukf(const UkfArgs& a, int force_model, cudaStream_t stream);
+cudaError_t launch_sigma_gen(const double* est_x, const double* est_p, const double* truth_x, double* sb,
+                             int64_t n, int64_t ld, double gamma, uint32_t* sig_flags,
+                             cudaStream_t stream);
+cudaError_t launch_propagate_sigma(double* sb, int64_t n, int64_t ld, int have_truth, double t0,
+                                   double tf, int substeps, int force_model, uint32_t* sig_flags,
+                                   cudaStream_t stream);
+cudaError_t launch_ukf_finish(const UkfArgs& a, cudaStream_t stream);
 
 }  // namespace pc

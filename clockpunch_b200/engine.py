@@ -57,8 +57,13 @@ class CatalogEngine:
 
         self.sens_x = state_buf(sensor_states, self.ld_s)
         self.sens_kind = torch.from_numpy(np.ascontiguousarray(sensor_kinds, dtype=np.uint8)).to(dev)
-        self.truth_x = state_buf(target_states, self.ld)
-        self.est_x = state_buf(np.asarray(est_x, dtype=np.float64).reshape(6, -1), self.ld)
+        # sigma buffer: 14 blocks of (6, ld); est_x IS block 0 and the truth state IS block 13
+        self.sigma = torch.zeros((14, 6, self.ld), dtype=f64, device=dev)
+        self.est_x, self.truth_x = self.sigma[0], self.sigma[13]
+        self.truth_x.copy_(state_buf(target_states, self.ld))
+        self.est_x.copy_(state_buf(np.asarray(est_x, dtype=np.float64).reshape(6, -1), self.ld))
+        self.sig_flags = torch.zeros((self.N,), dtype=torch.int32, device=dev)
+        self._sigma_valid = False   # blocks 1..12 match (est_x, est_p)?
         self.est_p = torch.from_numpy(np.ascontiguousarray(est_p, dtype=np.float64).reshape(self.N, 36)).to(dev)
         self.pred_p = self.est_p.clone()
         self.nis = torch.full((self.N,), float("nan"), dtype=f64, device=dev)
@@ -82,8 +87,6 @@ class CatalogEngine:
         self._snapshot = None
         # device-resident step clock (pc_clock: t_now, step, t_cur, step_cur) for graph replay
         self.clock = torch.zeros((32,), dtype=torch.uint8, device=dev)
-        # (4, M) sensor position + horizon term: lets the UKF kernel emit both vis maps itself
-        self.sens_q = torch.zeros((4 * max(1, self.M),), dtype=f64, device=dev)
         self._graph = None
         self._sync_clock()
         self.compute_vis()
@@ -117,7 +120,8 @@ class CatalogEngine:
         a.clock = self.clock.data_ptr() if use_clock else None
         a.actions = None if actions is None else actions.data_ptr()
         a.policy_probes, a.policy_seed = int(policy_probes), int(policy_seed)
-        a.sens_q = self.sens_q.data_ptr()
+        a.sigma_ws, a.sig_flags = self.sigma.data_ptr(), self.sig_flags.data_ptr()
+        a.sigma_valid = 1 if self._sigma_valid else 0
         return a
 
     # -- physics -------------------------------------------------------------
@@ -163,6 +167,7 @@ class CatalogEngine:
         a = self._fill_args(self.time, t_next, z, tasked, actions=actions)
         c = self.ctx
         c.check(c.lib.pc_step_fused(c.handle, C.byref(a), C.byref(self.params), self._stream()))
+        self._sigma_valid = True
         self.time = float(t_next)
         self.step_count += 1
         if self._graph is not None:
@@ -177,6 +182,7 @@ class CatalogEngine:
         self.tasked.zero_()
         torch, c = self.torch, self.ctx
         self._sync_clock()
+        self.ensure_sigma()
         before = c.launch_count
         g = torch.cuda.CUDAGraph()
         side = torch.cuda.Stream(self.dev)
@@ -193,10 +199,24 @@ class CatalogEngine:
         self._graph = g
         return g
 
+    def ensure_sigma(self):
+        """(Re)generate sigma-point blocks 1..12 from the current (est_x, est_p) if stale."""
+        if not self._sigma_valid:
+            c = self.ctx
+            c.check(c.lib.pc_sigma_points(c.handle, self.est_x.data_ptr(), self.est_p.data_ptr(), self.N,
+                                          self.ld, self.params.gamma, self.sigma.data_ptr(),
+                                          self.sig_flags.data_ptr(), self._stream()))
+            self._sigma_valid = True
+
+    def invalidate_sigma(self):
+        """Call after writing est_x / est_p from outside the step kernels."""
+        self._sigma_valid = False
+
     def replay(self, graph=None):
         """One step through a captured graph (actions must already be in self.actions unless the
         graph contains the stand-in policy)."""
         g = graph or self._graph
+        self.ensure_sigma()
         g.replay()
         self.time += g.pc_dt
         self.step_count += 1
@@ -213,17 +233,18 @@ class CatalogEngine:
         return self.obs_f32
 
     # -- reset snapshot (env.py:142,208: deepcopy of the agent list) ---------------
-    _STATE = ("sens_x", "truth_x", "est_x", "est_p", "pred_p", "nis", "flags", "vis_truth", "vis_est",
+    _STATE = ("sens_x", "sigma", "sig_flags", "est_p", "pred_p", "nis", "flags", "vis_truth", "vis_est",
               "num_tasked", "last_time_tasked", "tr_pos", "tr_vel")
 
     def snapshot(self):
-        self._snapshot = ({k: getattr(self, k).clone() for k in self._STATE}, self.time, self.step_count)
+        self._snapshot = ({k: getattr(self, k).clone() for k in self._STATE}, self.time, self.step_count,
+                          self._sigma_valid)
 
     def reset(self):
-        bufs, t, sc = self._snapshot
+        bufs, t, sc, sv = self._snapshot
         for k, v in bufs.items():
             getattr(self, k).copy_(v)
-        self.time, self.step_count = t, sc
+        self.time, self.step_count, self._sigma_valid = t, sc, sv
         self._sync_clock()
 
     # -- host views --------------------------------------------------------------

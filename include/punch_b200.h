@@ -151,6 +151,12 @@ int pc_ukf_predict_update(pc_ctx* ctx, double* est_x, double* est_p, double* tru
                           uint64_t rng_seed, uint64_t rng_step, double* out_pred_x,
                           double* out_pred_p, double* out_nis, uint32_t* out_flags,
                           double* out_z, pc_stream stream);
+/* Stage 1 of the UKF on its own: upper Cholesky of est_p and the 13 sigma points
+ * x + gamma [0, U, -U] (generateSigmaPoints, ukf_v2.py:158-183) into blocks 0..12 of a sigma
+ * buffer (layout: pc_step_args.sigma_ws).  est_x may be block 0 of sigma_ws itself.  sig_flags[i]
+ * receives PC_FLAG_NONPD_EST where the factorisation failed. */
+int pc_sigma_points(pc_ctx* ctx, const double* est_x, const double* est_p, int64_t n, int64_t ld,
+                    double gamma, double* sigma_ws, uint32_t* sig_flags, pc_stream stream);
 int pc_ukf_predict_update_host(pc_ctx* ctx, double* h_est_x, double* h_est_p, const double* h_z,
                                const uint8_t* h_tasked, int64_t n, double t0, double tf,
                                int substeps, int force_model, const pc_ukf_params* params,
@@ -230,11 +236,18 @@ typedef struct pc_step_args {
    * is tasked only where the PREVIOUS step's estimated vis map shows the pair visible. */
   int64_t* actions;          /* (M) or NULL */
   int policy_probes;
-  int reserved0;
+  int sigma_valid;           /* see sigma_ws */
   uint64_t policy_seed;
-  /* (4, M) workspace for sensor position + horizon term.  When given (and M <= 1024) the vis
-   * maps are produced inside the UKF kernel with warp ballots instead of a separate launch. */
-  double* sens_q;
+  /* Sigma-point buffer carried from step to step: 14 blocks of (6, ld) -- block 0 = centre point =
+   * est_x, blocks 1..6 / 7..12 = est_x +- gamma U[:, j], block 13 = truth state.  When given,
+   * est_x MUST be sigma_ws and truth_x MUST be sigma_ws + 13*6*ld (the step then copies nothing,
+   * and finishes by laying out the sigma points of the new estimate for the next step).
+   * sigma_valid != 0 promises that blocks 1..12 already hold the sigma points of the current
+   * (est_x, est_p), i.e. nothing touched them since the previous pc_step_fused on these buffers;
+   * with 0 they are regenerated first.  sig_flags is an (N) uint32 companion workspace.
+   * With sigma_ws == NULL a context-owned buffer is used and est_x / truth_x are ordinary arrays. */
+  double* sigma_ws;
+  uint32_t* sig_flags;
 } pc_step_args;
 int pc_step_fused(pc_ctx* ctx, const pc_step_args* args, const pc_ukf_params* params,
                   pc_stream stream);
