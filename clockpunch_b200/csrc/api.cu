@@ -100,7 +100,7 @@ int ensure_sb(pc_ctx* ctx, int64_t ld) {
   ctx->sb_states = 0;
   const size_t want = (size_t)ld + (size_t)(ld >> 2) + 64;
   PC_CUDA_TRY(ctx, cudaMalloc(&ctx->sb, 14 * 6 * want * sizeof(double)));
-  PC_CUDA_TRY(ctx, cudaMalloc(&ctx->sbf, want * sizeof(uint32_t)));
+  PC_CUDA_TRY(ctx, cudaMalloc(&ctx->sbf, 2 * want * sizeof(uint32_t)));
   ctx->sb_states = want;
   return PC_OK;
 }

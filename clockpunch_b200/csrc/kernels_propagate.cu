@@ -52,34 +52,30 @@ cudaError_t launch_propagate_agents(const double* x_in, double* x_out, const uin
 // K_b of the UKF pipeline: every state of the sigma buffer (14 blocks of (6, ld): 13 sigma points
 // + the truth state per target) advanced in place, one thread per state, blockIdx.y = block.
 // All 13 sigma points of a target must take the SAME number of substeps (their differences are
-// multiplied by weights of order 1e5..1e6), so blocks 1..12 derive the count from the centre point.
+// multiplied by weights of order 1e5..1e6), so blocks 0..12 derive the count from one orbit rate
+// per target, stored in sig_aux[n + t] when the sigma points were generated.
 template <bool J2>
 __global__ void __launch_bounds__(128, 5)
 propagate_sigma_kernel(double* __restrict__ sb, int64_t n, int64_t ld, double dt, int substeps,
-                       uint32_t* __restrict__ sig_flags) {
+                       uint32_t* __restrict__ sig_aux) {
   const int64_t t = (int64_t)blockIdx.x * 128 + threadIdx.x;
   if (t >= n) return;
   const int i = blockIdx.y;
   double* base = sb + (int64_t)i * 6 * ld + t;
-  int nsub = substeps;
-  if (nsub <= 0) {
-    // blocks 1..12 take the centre point's count; the centre (0) and the truth (13) their own
-    const double* src = (i == 13) ? base : sb + t;
-    double rc[3], vc[3];
-#pragma unroll
-    for (int c = 0; c < 3; ++c) {
-      rc[c] = src[(int64_t)c * ld];
-      vc[c] = src[(int64_t)(c + 3) * ld];
-    }
-    bool cl = false;
-    nsub = auto_substeps(rc, vc, dt, &cl);
-    if (i == 0 && cl && sig_flags) sig_flags[t] |= PC_FLAG_SUBSTEP_CLAMP;
-  }
   double r[3], v[3];
 #pragma unroll
   for (int c = 0; c < 3; ++c) {
     r[c] = base[(int64_t)c * ld];
     v[c] = base[(int64_t)(c + 3) * ld];
+  }
+  int nsub = substeps;
+  if (nsub <= 0) {
+    // blocks 0..12 use the orbit rate stored with the sigma points (computed from the centre point
+    // when they were generated); the truth state (13) uses its own
+    bool cl = false;
+    const float om = (i == 13) ? orbit_rate(r, v) : __uint_as_float(sig_aux[n + t]);
+    nsub = substeps_from_rate(om, dt, &cl);
+    if (i == 0 && cl) sig_aux[t] |= PC_FLAG_SUBSTEP_CLAMP;
   }
   propagate_state<J2>(r, v, dt, nsub);
 #pragma unroll

@@ -270,6 +270,8 @@ sigma_gen_kernel(const double* __restrict__ est_x, const double* __restrict__ es
     for (int c = 0; c < 6; ++c) sb[13 * 6 * ld + (int64_t)c * ld + t] = truth_x[(int64_t)c * ld + t];
   }
   sig_flags[t] = ok ? 0u : (uint32_t)PC_FLAG_NONPD_EST;
+  const double r0[3] = {x[0], x[1], x[2]}, v0[3] = {x[3], x[4], x[5]};
+  sig_flags[n + t] = __float_as_uint(orbit_rate(r0, v0));  // substep rule input for all 13 points
 }
 
 __global__ void __launch_bounds__(128)
@@ -435,7 +437,9 @@ ukf_finish_kernel(const __grid_constant__ UkfArgs a) {
     double U[21];
     const bool ok = chol_upper6_packed(PE, U);
     write_sigma_blocks(a.sb, ld, t, xe, U, a.p.gamma);
-    if (a.sig_flags) a.sig_flags[t] = ok ? 0u : (uint32_t)PC_FLAG_NONPD_EST;
+    a.sig_flags[t] = ok ? 0u : (uint32_t)PC_FLAG_NONPD_EST;
+    const double r0[3] = {xe[0], xe[1], xe[2]}, v0[3] = {xe[3], xe[4], xe[5]};
+    a.sig_flags[a.n + t] = __float_as_uint(orbit_rate(r0, v0));
   } else if (a.est_x_out) {
 #pragma unroll
     for (int c = 0; c < 6; ++c) a.est_x_out[(int64_t)c * ld + t] = xe[c];

@@ -62,7 +62,7 @@ class CatalogEngine:
         self.est_x, self.truth_x = self.sigma[0], self.sigma[13]
         self.truth_x.copy_(state_buf(target_states, self.ld))
         self.est_x.copy_(state_buf(np.asarray(est_x, dtype=np.float64).reshape(6, -1), self.ld))
-        self.sig_flags = torch.zeros((self.N,), dtype=torch.int32, device=dev)
+        self.sig_flags = torch.zeros((2, self.N), dtype=torch.int32, device=dev)
         self._sigma_valid = False   # blocks 1..12 match (est_x, est_p)?
         self.est_p = torch.from_numpy(np.ascontiguousarray(est_p, dtype=np.float64).reshape(self.N, 36)).to(dev)
         self.pred_p = self.est_p.clone()
