@@ -139,7 +139,10 @@ def run_reference(args):
     from clockpunch_b200.simulation.catalog import synth_catalog
     cat = synth_catalog(args.targets, args.sensors, seed=SEED)
     cores = host_cores()
-    sample = min(cat.N, max(cores, args.cpu_sample_per_core * cores))
+    # bounded sample per step: the whole --steps/--warmup run is sized to ~2 minutes of CPU work
+    # (the oracle port does ~40 target-steps/s per core)
+    per_core = args.cpu_sample_per_core or int(np.clip(120.0 / max(1, args.steps + args.warmup) * 40.0, 4, 640))
+    sample = min(cat.N, max(cores, per_core * cores))
     value, s_per_step, sample = cpu_reference_run(cat, sample, args.steps, args.warmup, cores)
     desc = (f"{sample} of {cat.N} targets x {cat.M} sensors per step, oracle port (scipy DOP853 per state, "
             f"python loop per pair), {cores} processes")
@@ -182,25 +185,22 @@ def run_own(args):
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
 
     # per-step summaries every rank needs from every other: packed est vis map,
-    # trace(P_pos), trace(P_vel), staleness source, num_tasked
+    # trace(P_pos), trace(P_vel), last_time_tasked, num_tasked -- all-gathered straight out of the
+    # buffers the kernels write (equal shards: no staging copy)
+    sg = None
     if world > 1:
-        g_vis = torch.empty((world * N, eng.wpr), dtype=torch.int32, device=dev)
-        g_trp = torch.empty((world * N,), dtype=torch.float32, device=dev)
-        g_trv = torch.empty((world * N,), dtype=torch.float32, device=dev)
-        g_ltt = torch.empty((world * N,), dtype=torch.float32, device=dev)
-        g_nt = torch.empty((world * N,), dtype=torch.int64, device=dev)
+        from clockpunch_b200.sharding import StepGather, TargetPartition
+        sg = StepGather(TargetPartition(world * N, world), rank,
+                        {"vis_est": eng.vis_est, "tr_pos": eng.tr_pos, "tr_vel": eng.tr_vel,
+                         "last_time_tasked": eng.last_time_tasked, "num_tasked": eng.num_tasked})
 
     # policy -> tasking mask -> sensors -> truth + UKF -> vis maps, captured once, replayed per step
     g_value = None
 
     def device_step():
         eng.replay(g_value)
-        if world > 1:
-            dist.all_gather_into_tensor(g_vis, eng.vis_est)
-            dist.all_gather_into_tensor(g_trp, eng.tr_pos)
-            dist.all_gather_into_tensor(g_trv, eng.tr_vel)
-            dist.all_gather_into_tensor(g_ltt, eng.last_time_tasked)
-            dist.all_gather_into_tensor(g_nt, eng.num_tasked)
+        if sg is not None:
+            sg.gather(unpad=False)
 
     def barrier():
         torch.cuda.synchronize(dev)
@@ -209,7 +209,6 @@ def run_own(args):
             torch.cuda.synchronize(dev)
 
     # ---------------- device-resident throughput (`value`) ----------------
-    ctx.check(lib.pc_set_timing(ctx.handle, 1))        # before capture: the event pair is part of the graph
     g_value = eng.build_graph(DT, policy_probes=64, policy_seed=SEED)
     for k in range(args.warmup):
         device_step()
@@ -221,40 +220,72 @@ def run_own(args):
         sampler.start()
     barrier()
     wall0 = time.perf_counter()
-    tasked_total = 0
-    ukf_ms_sum, ukf_last = 0.0, C.c_double()
     for k in range(args.steps):
         if args.l2 == "flush":
             flush.zero_()                  # L2 flush, outside the timed events
         evs[k][0].record()
         device_step()
         evs[k][1].record()
-        ctx.check(lib.pc_get_timing(ctx.handle, C.byref(ukf_last)))   # waits for this step's UKF kernel
-        ukf_ms_sum += ukf_last.value
     barrier()
     wall = time.perf_counter() - wall0
     ms = sum(a.elapsed_time(b) for a, b in evs)
-    ctx.check(lib.pc_set_timing(ctx.handle, 0))
     launches = g_value.pc_launches * args.steps
-    tasked_total = int(eng.num_tasked.sum().item())
-    flags_bad = int((eng.flags != 0).sum().item())
     t_ms = torch.tensor([ms], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t_ms, op=dist.ReduceOp.MAX)
     ms_per_step = float(t_ms.item()) / args.steps
     value = world * N / (ms_per_step * 1e-3)
 
-    # roofline of the dominant kernel: propagate_sigma_kernel (all 13 sigma points + the truth state of
-    # every target, one thread per state).  Algorithmic work: SURVEY.md section 8(d), 1150 flop per
-    # fixed DOP853 step x substeps used; algorithmic bytes: each 6-vector read and written once.
-    total_steps = args.warmup + args.steps
+    # ---------------- roofline of the dominant kernel (separate pass) ----------------
+    # propagate_sigma_kernel: all 13 sigma points + the truth state of every target, one thread per
+    # state.  Its launch is bracketed by a CUDA-event pair recorded by the library on the launch
+    # stream (event-record nodes inside the graph, so this pass is NOT the one `value` comes from).
+    # Algorithmic work: SURVEY.md section 8(d), 1150 flop per fixed DOP853 step x the substeps each state
+    # actually takes (read back from the per-target orbit rates the step itself uses); algorithmic
+    # bytes: each 6-vector read and written once.
+    # Every pass (value, roofline, e2e) starts from the same catalog state: reset + warm-up.
+    eng.reset()
+    ctx.check(lib.pc_set_timing(ctx.handle, 1))        # before capture: the event pair is part of the graph
+    g_timed = eng.build_graph(DT, policy_probes=64, policy_seed=SEED)
+    for k in range(args.warmup):
+        eng.replay(g_timed)
+    inv_theta = np.float32(1.0 / 0.12)
+
+    def substeps_now():
+        om = eng.sig_flags[1].cpu().numpy().view(np.float32)
+        est = np.maximum(1.0, np.ceil(np.float32(DT) * om * inv_theta)).astype(np.float64)
+        return 13.0 * est.sum() + truth_sub.sum(), est.mean()
+
+    tx = eng.host("truth_x")
+    hv = np.cross(tx[:3].T, tx[3:].T)
+    h2, r2, v2 = (hv * hv).sum(1), (tx[:3] ** 2).sum(0), (tx[3:] ** 2).sum(0)
+    e1 = 1.0 + np.sqrt(np.maximum(0.0, 1.0 + 2.0 * (0.5 * v2 - 398600.0 / np.sqrt(r2)) * h2 / 398600.0 ** 2))
+    truth_sub = np.maximum(1.0, np.ceil(DT * (398600.0 ** 2 * e1 ** 3.5 / h2 ** 1.5) / 0.12))
+    ukf_ms_sum, state_steps_sum, est_sub_sum, ukf_last = 0.0, 0.0, 0.0, C.c_double()
+    n_roof = max(3, min(args.steps, 50))
+    for k in range(n_roof + 2):
+        ss, es = substeps_now()
+        if args.l2 == "flush":
+            flush.zero_()
+        eng.replay(g_timed)
+        torch.cuda.synchronize(dev)                                   # both events are this replay's
+        ctx.check(lib.pc_get_timing(ctx.handle, C.byref(ukf_last)))
+        if k >= 2:
+            ukf_ms_sum += ukf_last.value
+            state_steps_sum += ss
+            est_sub_sum += es
+    ctx.check(lib.pc_set_timing(ctx.handle, 0))
+    tasked_total = int(eng.num_tasked.sum().item())
+    flags_bad = int((eng.flags != 0).sum().item())
+    total_steps = args.warmup + n_roof + 2
     tasked_frac = tasked_total / max(1, N * total_steps)
-    substeps_used = 1.0 if args.substeps == 0 else float(args.substeps)   # auto rule: 1 at dt=100s, e<=0.01
-    flop_per_target = 14 * FLOP_DOP853_STEP * substeps_used
-    flop_per_target_step = flop_per_target + (1 - tasked_frac) * FLOP_UKF_NOMEAS + tasked_frac * FLOP_UKF_MEAS \
+    state_steps = state_steps_sum / n_roof                  # DOP853 steps per launch, summed over 14 N states
+    substeps_used = est_sub_sum / n_roof
+    flop_per_launch = FLOP_DOP853_STEP * state_steps
+    flop_per_target_step = flop_per_launch / N + (1 - tasked_frac) * FLOP_UKF_NOMEAS + tasked_frac * FLOP_UKF_MEAS \
         + 2 * M * FLOP_VIS_PAIR
-    ukf_ms_avg = ukf_ms_sum / args.steps
-    achieved_tf = flop_per_target * N / (ukf_ms_avg * 1e-3) * 1e-12
+    ukf_ms_avg = ukf_ms_sum / n_roof
+    achieved_tf = flop_per_launch / (ukf_ms_avg * 1e-3) * 1e-12
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
@@ -264,9 +295,10 @@ def run_own(args):
     hbm_ach = 14 * 96.0 * N / (ukf_ms_avg * 1e-3) * 1e-9
     roofline = {"bound": "fp64", "kernel": "propagate_sigma_kernel", "achieved": achieved_tf, "peak": peak_tf.value,
                 "unit": "TFLOP/s", "frac": achieved_tf / peak_tf.value if peak_tf.value else None,
-                "traffic": None, "peak_source": "DFMA probe measured live in this run (pc_fp64_peak); "
-                "MEASURED_PEAKS.json has no FP64 entry; nominal 37 TFLOP/s",
-                "flop_per_launch": flop_per_target * N, "substeps_per_propagate": substeps_used,
+                "traffic": None, "peak_source": "FP64 DFMA probe measured live in this run (pc_fp64_peak); "
+                "MEASURED_PEAKS.json has no FP64 entry (HBM/bf16 only); nominal 37 TFLOP/s",
+                "flop_per_launch": flop_per_launch, "dop853_steps_per_launch": state_steps,
+                "mean_substeps_per_sigma_propagate": substeps_used,
                 "kernel_ms": ukf_ms_avg, "kernel_share_of_step": ukf_ms_avg / ms_per_step,
                 "whole_step_flop_per_target_step": flop_per_target_step,
                 "whole_step_achieved": flop_per_target_step * N / (ms_per_step * 1e-3) * 1e-12,
@@ -276,54 +308,53 @@ def run_own(args):
     clocks = sampler.stop() if rank == 0 else None
 
     # ---------------- end to end through the public API (`e2e`) ----------------
-    n0, n1, n2 = eng._obs_sizes
-    h_obs = torch.empty((n0 + n1 + n2,), dtype=torch.float32).pin_memory()
-    h_vis = torch.empty((N, eng.wpr), dtype=torch.int32).pin_memory()
-    h_nt = torch.empty((N,), dtype=torch.int64).pin_memory()
-    h_act = torch.empty((M,), dtype=torch.int64).pin_memory()
+    # CatalogEngine.step_host -> pc_step_host: pinned host actions -> device, the step + observation
+    # pack (CUDA graph inside the library), observation + packed vis map + num_tasked -> pinned host,
+    # stream synchronise.  The policy runs on the host from the previous step's observation.
+    eng.reset()
+    eng._graph = None
+    hb = eng.host_buffers()
     rng = np.random.default_rng(SEED + rank)
+    n_e2e = args.warmup + args.steps
+    probe_tab = rng.integers(0, N, size=(n_e2e, M, 64))
+    jcol = np.arange(M)[:, None]
+    jw, jb = jcol >> 5, (jcol & 31).astype(np.uint32)
+    rows = np.arange(M)
+    h_vis_np = hb["vis_est"].numpy().view(np.uint32)
+    h_act_np = hb["actions"].numpy()
 
-    def host_policy(vis_words):
-        probes = rng.integers(0, N, size=(M, 64))
-        j = np.arange(M)[:, None]
-        hit = (vis_words[probes, j >> 5] >> (j & 31)) & 1
+    def host_policy(k):
+        probes = probe_tab[k]
+        hit = (h_vis_np[probes, jw] >> jb) & 1
         first = hit.argmax(axis=1)
-        return np.where(hit.any(axis=1), probes[np.arange(M), first], N)
+        h_act_np[:M] = np.where(hit[rows, first] != 0, probes[rows, first], N)
 
-    g_e2e = eng.build_graph(DT, policy_probes=0, pack_obs=True)       # tasking -> step -> obs pack
-
-    def e2e_step():
-        act = host_policy(h_vis.numpy().view(np.uint32))               # policy on the host, from the last obs
-        h_act.copy_(torch.from_numpy(act))
-        eng.actions[:M].copy_(h_act, non_blocking=True)                # H2D: this step's actions
-        eng.replay(g_e2e)
+    def e2e_step(k):
+        host_policy(k)
+        eng.step_host(hb, DT)
         if world > 1:
-            dist.all_gather_into_tensor(g_vis, eng.vis_est)
-        h_obs.copy_(eng.obs_f32, non_blocking=True)                    # D2H: the observation
-        h_vis.copy_(eng.vis_est, non_blocking=True)
-        h_nt.copy_(eng.num_tasked, non_blocking=True)
-        torch.cuda.current_stream(dev).synchronize()
+            sg.gather(unpad=False)
+            torch.cuda.current_stream(dev).synchronize()
 
-    h_vis.copy_(eng.vis_est)
-    for _ in range(args.warmup):
-        e2e_step()
+    hb["vis_est"].copy_(eng.vis_est)
+    for k in range(args.warmup):
+        e2e_step(k)
     barrier()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
     tw = time.perf_counter()
-    for _ in range(args.steps):
-        e2e_step()
-    e1.record()
+    for k in range(args.steps):
+        e2e_step(args.warmup + k)
+    e2e_wall = time.perf_counter() - tw                 # every step ends in a stream synchronise
     barrier()
-    e2e_wall = time.perf_counter() - tw
-    e2e_ms = torch.tensor([max(e0.elapsed_time(e1), e2e_wall * 1e3)], dtype=torch.float64, device=dev)
+    e2e_ms = torch.tensor([e2e_wall * 1e3], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(e2e_ms, op=dist.ReduceOp.MAX)
     e2e_value = world * N * args.steps / (float(e2e_ms.item()) * 1e-3)
-    e2e = {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h_act.numel() * 8),
-           "d2h_bytes_per_step": int(h_obs.numel() * 4 + h_vis.numel() * 4 + h_nt.numel() * 8),
+    e2e = {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(M * 8),
+           "d2h_bytes_per_step": int(hb["obs"].numel() * 4 + hb["vis_est"].numel() * 4 + hb["num_tasked"].numel() * 8),
            "ms_per_step": float(e2e_ms.item()) / args.steps,
-           "path": "CatalogEngine: pinned host actions -> [CUDA graph: pc_step_fused (tasking, sensors, sigma propagate, UKF finish, vis maps) -> pc_obs_pack] -> pinned host obs"}
+           "path": "host policy (numpy, previous obs) -> CatalogEngine.step_host -> pc_step_host: pinned host actions "
+                   "-> [CUDA graph: pc_step_fused + pc_obs_pack] -> pinned host float32 obs + packed vis map + "
+                   "num_tasked, stream sync; timed by the host clock around the loop"}
 
     if rank != 0:
         if world > 1:
@@ -334,7 +365,7 @@ def run_own(args):
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
         cores = host_cores()
-        sample = min(N, max(cores, args.cpu_sample_per_core * cores))
+        sample = min(N, max(cores, (args.cpu_sample_per_core or 640) * cores))    # ~15 s of CPU work
         v, s_step, sample = cpu_reference_run(cat, sample, 1, 0, cores)
         cpu = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
                "sample": f"{sample} of {N} targets x {M} sensors, one pass ({s_step:.1f} s), oracle port on "
@@ -361,7 +392,7 @@ def main():
     ap.add_argument("--targets", type=int, default=N_TARGETS)
     ap.add_argument("--sensors", type=int, default=N_SENSORS)
     ap.add_argument("--substeps", type=int, default=0)
-    ap.add_argument("--cpu-sample-per-core", type=int, default=32)
+    ap.add_argument("--cpu-sample-per-core", type=int, default=0, help="0 = sized for the time budget")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--l2", default="flush", choices=["flush", "none"])
     args = ap.parse_args()

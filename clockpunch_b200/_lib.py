@@ -45,7 +45,14 @@ class StepArgs(C.Structure):
         ("tr_vel", C.c_void_p), ("clock", C.c_void_p),
         ("actions", C.c_void_p), ("policy_probes", C.c_int), ("sigma_valid", C.c_int),
         ("policy_seed", C.c_uint64), ("sigma_ws", C.c_void_p), ("sig_flags", C.c_void_p),
+        ("sens_q", C.c_void_p),
     ]
+
+
+class StepIO(C.Structure):
+    """pc_step_io."""
+    _fields_ = [("h_actions", C.c_void_p), ("d_obs", C.c_void_p), ("h_obs", C.c_void_p),
+                ("h_vis_est", C.c_void_p), ("h_num_tasked", C.c_void_p)]
 
 
 _vp, _i64, _dbl, _int, _u64 = C.c_void_p, C.c_int64, C.c_double, C.c_int, C.c_uint64
@@ -78,6 +85,7 @@ _SIGNATURES = {
     "pc_get_timing": ([_vp, C.POINTER(_dbl)], _int),
     "pc_fp64_peak": ([_vp, _int, C.POINTER(_dbl)], _int),
     "pc_step_fused": ([_vp, C.POINTER(StepArgs), C.POINTER(UkfParams), _vp], _int),
+    "pc_step_host": ([_vp, C.POINTER(StepArgs), C.POINTER(UkfParams), C.POINTER(StepIO), _vp], _int),
 }
 EXPORTED_SYMBOLS = tuple(_SIGNATURES)
 

@@ -54,6 +54,22 @@ struct pc_ctx {
   // optional per-kernel timing of pc_step_fused (bench.py roofline leg)
   bool timing = false;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;  // around the UKF kernel
+  // pc_step_fused: the sensor / tasking kernel runs on a side stream next to the target
+  // propagation (fork / join with two events; parallel branches when captured into a graph)
+  cudaStream_t side_stream = nullptr;
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+  // sensor positions + horizon terms for the fused visibility phase when the caller brings no
+  // pc_step_args.sens_q (not graph-capture safe)
+  double* sq = nullptr;
+  size_t sq_sensors = 0;
+  // pc_step_host: the captured step (pc_step_fused + pc_obs_pack) and the arguments it was
+  // captured with; replayed while the caller keeps passing the same buffers
+  cudaGraphExec_t hs_exec = nullptr;
+  pc_step_args hs_args;
+  pc_ukf_params hs_params;
+  float* hs_dobs = nullptr;
+  cudaStream_t hs_stream = nullptr;
+  int64_t hs_launches = 0;
 };
 
 int pc_fail(pc_ctx* ctx, int code, const char* msg) {
@@ -91,6 +107,17 @@ int ensure_ws(pc_ctx* ctx, size_t bytes) {
 }
 inline size_t align256(size_t x) { return (x + 255) & ~size_t(255); }
 
+int ensure_sq(pc_ctx* ctx, int64_t M) {
+  if ((size_t)M <= ctx->sq_sensors) return PC_OK;
+  if (ctx->sq) cudaFree(ctx->sq);
+  ctx->sq = nullptr;
+  ctx->sq_sensors = 0;
+  const size_t want = (size_t)M + (size_t)(M >> 2) + 64;
+  PC_CUDA_TRY(ctx, cudaMalloc(&ctx->sq, 4 * want * sizeof(double)));
+  ctx->sq_sensors = want;
+  return PC_OK;
+}
+
 int ensure_sb(pc_ctx* ctx, int64_t ld) {
   if ((size_t)ld <= ctx->sb_states) return PC_OK;
   if (ctx->sb) cudaFree(ctx->sb);
@@ -125,7 +152,10 @@ int pc_ctx_create(int device_ordinal, pc_ctx** out) {
   if (!ctx) return PC_ERR_BAD_ARG;
   ctx->device = device_ordinal;
   DeviceGuard g(device_ordinal);
-  if (cudaStreamCreateWithFlags(&ctx->host_stream, cudaStreamNonBlocking) != cudaSuccess) {
+  if (cudaStreamCreateWithFlags(&ctx->host_stream, cudaStreamNonBlocking) != cudaSuccess ||
+      cudaStreamCreateWithFlags(&ctx->side_stream, cudaStreamNonBlocking) != cudaSuccess ||
+      cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming) != cudaSuccess ||
+      cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming) != cudaSuccess) {
     delete ctx;
     return PC_ERR_CUDA;
   }
@@ -141,8 +171,13 @@ int pc_ctx_destroy(pc_ctx* ctx) {
     if (ctx->sb) cudaFree(ctx->sb);
     if (ctx->sbf) cudaFree(ctx->sbf);
     if (ctx->host_stream) cudaStreamDestroy(ctx->host_stream);
+    if (ctx->side_stream) cudaStreamDestroy(ctx->side_stream);
+    if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
+    if (ctx->ev_join) cudaEventDestroy(ctx->ev_join);
+    if (ctx->sq) cudaFree(ctx->sq);
     if (ctx->ev0) cudaEventDestroy(ctx->ev0);
     if (ctx->ev1) cudaEventDestroy(ctx->ev1);
+    if (ctx->hs_exec) cudaGraphExecDestroy(ctx->hs_exec);
   }
   delete ctx;
   return PC_OK;
@@ -577,17 +612,36 @@ int pc_step_fused(pc_ctx* ctx, const pc_step_args* a, const pc_ukf_params* param
   }
   double* sb = own_sb ? a->sigma_ws : ctx->sb;
   uint32_t* sbf = own_sb ? a->sig_flags : ctx->sbf;
-  // 1. sensors (Agent.propagate per sensor; terrestrial ones are a rotation), tasking mask from
-  //    the actions and the PREVIOUS estimated vis map, step clock latch
-  if (a->M > 0 || a->clock) {
+  const bool fuse_vis = want_vis && a->M > 0 && a->N > 0;
+  double* sq = a->sens_q;
+  if (fuse_vis && !sq) {
+    rc = ensure_sq(ctx, a->M);
+    if (rc) return rc;
+    sq = ctx->sq;
+  }
+  // 1. sensors (Agent.propagate per sensor; terrestrial ones are a rotation), their horizon terms,
+  //    tasking mask from the actions and the PREVIOUS estimated vis map, step clock latch.
+  //    Independent of the target propagation, so it runs beside it on the side stream.
+  const bool pre = a->M > 0 || a->clock;
+  const bool fork = pre && a->N > 0;
+  if (pre) {
+    cudaStream_t ps = s;
+    if (fork) {
+      PC_CUDA_TRY(ctx, cudaEventRecord(ctx->ev_fork, s));
+      PC_CUDA_TRY(ctx, cudaStreamWaitEvent(ctx->side_stream, ctx->ev_fork, 0));
+      ps = ctx->side_stream;
+    }
     PC_CUDA_TRY(ctx, pc::launch_pre_step(a->sens_x, a->sens_kind, a->M, a->ld_s, a->t0, a->tf, a->substeps,
-                                         a->force_model, nullptr, a->body_radius, a->vis_tol, a->clock,
-                                         a->actions, a->vis_est, const_cast<uint8_t*>(a->tasked), a->N,
-                                         a->words_per_row, a->policy_probes, a->policy_seed, a->rng_step, s));
+                                         a->force_model, fuse_vis ? sq : nullptr, a->body_radius, a->vis_tol,
+                                         a->clock, a->actions, a->vis_est, const_cast<uint8_t*>(a->tasked),
+                                         a->N, a->words_per_row, a->policy_probes, a->policy_seed,
+                                         a->rng_step, ps));
     ctx->launches += 1;
+    if (fork) PC_CUDA_TRY(ctx, cudaEventRecord(ctx->ev_join, ps));
   }
   // 2. targets: sigma points (only when not carried over from the previous step), all 14 N
-  //    states propagated, then transform + update + summaries + next step's sigma points
+  //    states propagated, then transform + update + summaries + next step's sigma points + both
+  //    visibility rows of every target (env.py:455-462)
   if (a->N > 0) {
     if (!own_sb || !a->sigma_valid) {
       PC_CUDA_TRY(ctx, pc::launch_sigma_gen(a->est_x, a->est_p, a->truth_x, sb, a->N, a->ld, params->gamma,
@@ -604,6 +658,7 @@ int pc_step_fused(pc_ctx* ctx, const pc_step_args* a, const pc_ukf_params* param
     PC_CUDA_TRY(ctx, pc::launch_propagate_sigma(sb, a->N, a->ld, 1, a->t0, a->tf, a->substeps,
                                                 a->force_model, sbf, s));
     if (ctx->timing) PC_CUDA_TRY(ctx, cudaEventRecordWithFlags(ctx->ev1, s, evflags));
+    if (fork) PC_CUDA_TRY(ctx, cudaStreamWaitEvent(s, ctx->ev_join, 0));
     pc::UkfArgs u{};
     u.sb = sb;
     u.est_p = a->est_p;
@@ -629,6 +684,15 @@ int pc_step_fused(pc_ctx* ctx, const pc_step_args* a, const pc_ukf_params* param
     u.gen_next = own_sb ? 1 : 0;
     u.est_x_out = own_sb ? nullptr : a->est_x;
     u.truth_out = own_sb ? nullptr : a->truth_x;
+    if (fuse_vis) {
+      u.sens_q = reinterpret_cast<const double4*>(sq);
+      u.M = a->M;
+      u.wpr = a->words_per_row;
+      u.vis_truth = a->vis_truth;
+      u.vis_est = a->vis_est;
+      u.body_radius = a->body_radius;
+      u.vis_tol = a->vis_tol;
+    }
     u.p = *params;
     PC_CUDA_TRY(ctx, pc::launch_ukf_finish(u, s));
     ctx->launches += 2;
@@ -636,13 +700,94 @@ int pc_step_fused(pc_ctx* ctx, const pc_step_args* a, const pc_ukf_params* param
     PC_CUDA_TRY(ctx, pc::launch_advance_clock(a->clock, a->tf - a->t0, s));
     ctx->launches += 1;
   }
-  // 3. both visibility maps for the next step (env.py:455-462)
-  if (want_vis && a->M > 0 && a->N > 0) {
-    PC_CUDA_TRY(ctx, pc::launch_vismap_packed(a->sens_x, a->M, a->ld_s, nullptr, 0.0, a->truth_x,
-                                              a->est_x, a->N, a->ld, a->body_radius, a->vis_tol,
-                                              a->vis_truth, a->vis_est, a->words_per_row, s));
-    ctx->launches += 1;
+  return PC_OK;
+}
+
+/* ---- the step with host buffers (reference-facing call: actions in, observation out) ---- */
+static int step_and_pack(pc_ctx* ctx, const pc_step_args* a, const pc_ukf_params* params,
+                         float* d_obs, cudaStream_t s) {
+  int rc = pc_step_fused(ctx, a, params, s);
+  if (rc) return rc;
+  if (d_obs) {
+    const int64_t n0 = 6 * (a->M + a->N), n1 = 36 * a->N;
+    rc = pc_obs_pack(ctx, a->sens_x, a->M, a->ld_s, a->est_x, a->est_p, a->N, a->ld,
+                     a->last_time_tasked, a->tf, a->clock, d_obs, d_obs + n0, d_obs + n0 + n1, s);
   }
+  return rc;
+}
+
+int pc_step_host(pc_ctx* ctx, const pc_step_args* a, const pc_ukf_params* params,
+                 const pc_step_io* io, pc_stream stream) {
+  PC_REQUIRE(ctx, ctx != nullptr, "null context");
+  PC_REQUIRE(ctx, a != nullptr && params != nullptr && io != nullptr, "null args");
+  PC_REQUIRE(ctx, !io->h_actions || a->actions, "h_actions needs a device actions buffer in the step args");
+  PC_REQUIRE(ctx, !io->h_obs || (io->d_obs && a->last_time_tasked), "h_obs needs d_obs and last_time_tasked");
+  PC_REQUIRE(ctx, !io->h_vis_est || a->vis_est, "h_vis_est needs vis_est in the step args");
+  PC_REQUIRE(ctx, !io->h_num_tasked || a->num_tasked, "h_num_tasked needs num_tasked in the step args");
+  DeviceGuard g(ctx->device);
+  cudaStream_t s = stream ? (cudaStream_t)stream : ctx->host_stream;
+  if (io->h_actions && a->M > 0)
+    PC_CUDA_TRY(ctx, cudaMemcpyAsync(a->actions, io->h_actions, (size_t)a->M * sizeof(int64_t),
+                                     cudaMemcpyHostToDevice, s));
+  // Replayable only when nothing in the argument block changes from step to step: device clock,
+  // caller-owned sigma buffer already holding the current sigma points, measurements drawn on device.
+  const bool replayable = a->clock && a->sigma_ws && a->sigma_valid && !a->z && !ctx->timing;
+  int rc = PC_OK;
+  pc_step_args key;
+  if (!replayable) {
+    rc = step_and_pack(ctx, a, params, io->d_obs, s);
+    if (rc) return rc;
+  } else {
+    // with a device clock the kernels take the step's start time and RNG counter from it; only
+    // tf - t0 matters, so the key is normalised and a caller that advances t0 / rng_step still hits
+    key = *a;
+    key.tf = a->tf - a->t0;
+    key.t0 = 0.0;
+    key.rng_step = 0;
+    a = &key;
+    const bool hit = ctx->hs_exec && ctx->hs_stream == s && ctx->hs_dobs == io->d_obs &&
+                     std::memcmp(&ctx->hs_args, a, sizeof(*a)) == 0 &&
+                     std::memcmp(&ctx->hs_params, params, sizeof(*params)) == 0;
+    if (!hit) {
+      if (ctx->hs_exec) {
+        cudaGraphExecDestroy(ctx->hs_exec);
+        ctx->hs_exec = nullptr;
+      }
+      const int64_t before = ctx->launches;
+      cudaGraph_t graph = nullptr;
+      PC_CUDA_TRY(ctx, cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal));
+      rc = step_and_pack(ctx, a, params, io->d_obs, s);
+      cudaError_t e = cudaStreamEndCapture(s, &graph);
+      ctx->hs_launches = ctx->launches - before;
+      ctx->launches = before;
+      if (rc) {
+        if (graph) cudaGraphDestroy(graph);
+        return rc;
+      }
+      PC_CUDA_TRY(ctx, e);
+      e = cudaGraphInstantiate(&ctx->hs_exec, graph, 0);
+      cudaGraphDestroy(graph);
+      PC_CUDA_TRY(ctx, e);
+      std::memcpy(&ctx->hs_args, a, sizeof(*a));
+      std::memcpy(&ctx->hs_params, params, sizeof(*params));
+      ctx->hs_dobs = io->d_obs;
+      ctx->hs_stream = s;
+    }
+    PC_CUDA_TRY(ctx, cudaGraphLaunch(ctx->hs_exec, s));
+    ctx->launches += ctx->hs_launches;
+  }
+  if (io->h_obs)
+    PC_CUDA_TRY(ctx, cudaMemcpyAsync(io->h_obs, io->d_obs,
+                                     (size_t)(6 * (a->M + a->N) + 37 * a->N) * sizeof(float),
+                                     cudaMemcpyDeviceToHost, s));
+  if (io->h_vis_est)
+    PC_CUDA_TRY(ctx, cudaMemcpyAsync(io->h_vis_est, a->vis_est,
+                                     (size_t)a->N * a->words_per_row * sizeof(uint32_t),
+                                     cudaMemcpyDeviceToHost, s));
+  if (io->h_num_tasked)
+    PC_CUDA_TRY(ctx, cudaMemcpyAsync(io->h_num_tasked, a->num_tasked, (size_t)a->N * sizeof(int64_t),
+                                     cudaMemcpyDeviceToHost, s));
+  PC_CUDA_TRY(ctx, cudaStreamSynchronize(s));
   return PC_OK;
 }
 

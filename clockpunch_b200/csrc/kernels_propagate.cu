@@ -5,7 +5,7 @@
 namespace pc {
 
 template <bool J2>
-__global__ void __launch_bounds__(128, 5)
+__global__ void __launch_bounds__(128, 4)
 propagate_agents_kernel(const double* __restrict__ x_in, double* __restrict__ x_out,
                         const uint8_t* __restrict__ kind, int default_kind, int64_t n, int64_t ld,
                         double dt, int substeps, double cs, double sn) {
@@ -54,28 +54,77 @@ cudaError_t launch_propagate_agents(const double* x_in, double* x_out, const uin
 // All 13 sigma points of a target must take the SAME number of substeps (their differences are
 // multiplied by weights of order 1e5..1e6), so blocks 0..12 derive the count from one orbit rate
 // per target, stored in sig_aux[n + t] when the sigma points were generated.
+//
+// Substep counts differ between neighbouring targets (a mixed LEO/MEO/GEO catalog, estimates of
+// differing quality), and a warp runs as long as its slowest lane.  So each CTA first does a
+// stable counting sort of its 128 targets by substep count (ballot + popc, one smem round trip)
+// and every thread then takes the target at its sorted position: warps become homogeneous
+// (at most one mixed warp per count boundary) while all accesses stay inside the CTA's own
+// 128-target window of each component row, so DRAM traffic is unchanged.
+constexpr int kPropThreads = 128;
+constexpr int kSortBuckets = 6;  // 0 = no work (past n), 1..4 = that many substeps, 5 = more
+
 template <bool J2>
-__global__ void __launch_bounds__(128, 5)
+__global__ void __launch_bounds__(kPropThreads, 4)
 propagate_sigma_kernel(double* __restrict__ sb, int64_t n, int64_t ld, double dt, int substeps,
                        uint32_t* __restrict__ sig_aux) {
-  const int64_t t = (int64_t)blockIdx.x * 128 + threadIdx.x;
-  if (t >= n) return;
+  __shared__ int s_wcnt[kPropThreads / 32][kSortBuckets];
+  __shared__ uint16_t s_perm[kPropThreads];
+  __shared__ int s_nsub[kPropThreads];
+  const int tid = threadIdx.x;
+  const int64_t t0 = (int64_t)blockIdx.x * kPropThreads;
   const int i = blockIdx.y;
-  double* base = sb + (int64_t)i * 6 * ld + t;
+  double* blk = sb + (int64_t)i * 6 * ld;
+  int slot = tid, nsub = substeps;
+  if (substeps <= 0) {
+    // blocks 0..12 use the orbit rate stored with the sigma points (computed from the centre point
+    // when they were generated); the truth state (13) uses its own
+    const int64_t t = t0 + tid;
+    int mine = 0;
+    if (t < n) {
+      float om;
+      if (i == 13) {
+        const double r[3] = {blk[t], blk[ld + t], blk[2 * ld + t]};
+        const double v[3] = {blk[3 * ld + t], blk[4 * ld + t], blk[5 * ld + t]};
+        om = orbit_rate(r, v);
+      } else {
+        om = __uint_as_float(sig_aux[n + t]);
+      }
+      bool cl = false;
+      mine = substeps_from_rate(om, dt, &cl);
+      if (i == 0 && cl) sig_aux[t] |= PC_FLAG_SUBSTEP_CLAMP;
+    }
+    const int key = mine < kSortBuckets - 1 ? mine : kSortBuckets - 1;
+    const int w = tid >> 5, lane = tid & 31;
+    int rank = 0;
+#pragma unroll
+    for (int b = 0; b < kSortBuckets; ++b) {
+      const unsigned m = __ballot_sync(0xffffffffu, key == b);
+      if (key == b) rank = __popc(m & ((1u << lane) - 1u));
+      if (lane == 0) s_wcnt[w][b] = __popc(m);
+    }
+    s_nsub[tid] = mine;
+    __syncthreads();
+    int pos = rank;
+#pragma unroll
+    for (int b = 0; b < kSortBuckets; ++b)
+#pragma unroll
+      for (int ww = 0; ww < kPropThreads / 32; ++ww)
+        if (b < key || (b == key && ww < w)) pos += s_wcnt[ww][b];
+    s_perm[pos] = (uint16_t)tid;
+    __syncthreads();
+    slot = s_perm[tid];
+    nsub = s_nsub[slot];
+    if (nsub == 0) return;  // past the end of the catalog
+  } else if (t0 + tid >= n) {
+    return;
+  }
+  double* base = blk + t0 + slot;
   double r[3], v[3];
 #pragma unroll
   for (int c = 0; c < 3; ++c) {
     r[c] = base[(int64_t)c * ld];
     v[c] = base[(int64_t)(c + 3) * ld];
-  }
-  int nsub = substeps;
-  if (nsub <= 0) {
-    // blocks 0..12 use the orbit rate stored with the sigma points (computed from the centre point
-    // when they were generated); the truth state (13) uses its own
-    bool cl = false;
-    const float om = (i == 13) ? orbit_rate(r, v) : __uint_as_float(sig_aux[n + t]);
-    nsub = substeps_from_rate(om, dt, &cl);
-    if (i == 0 && cl) sig_aux[t] |= PC_FLAG_SUBSTEP_CLAMP;
   }
   propagate_state<J2>(r, v, dt, nsub);
 #pragma unroll
@@ -89,11 +138,11 @@ cudaError_t launch_propagate_sigma(double* sb, int64_t n, int64_t ld, int have_t
                                    double tf, int substeps, int force_model, uint32_t* sig_flags,
                                    cudaStream_t stream) {
   if (n <= 0) return cudaSuccess;
-  const dim3 grid((unsigned)((n + 127) / 128), have_truth ? 14 : 13);
+  const dim3 grid((unsigned)((n + kPropThreads - 1) / kPropThreads), have_truth ? 14 : 13);
   if (force_model == PC_FORCE_TWOBODY_J2)
-    propagate_sigma_kernel<true><<<grid, 128, 0, stream>>>(sb, n, ld, tf - t0, substeps, sig_flags);
+    propagate_sigma_kernel<true><<<grid, kPropThreads, 0, stream>>>(sb, n, ld, tf - t0, substeps, sig_flags);
   else
-    propagate_sigma_kernel<false><<<grid, 128, 0, stream>>>(sb, n, ld, tf - t0, substeps, sig_flags);
+    propagate_sigma_kernel<false><<<grid, kPropThreads, 0, stream>>>(sb, n, ld, tf - t0, substeps, sig_flags);
   return cudaGetLastError();
 }
 

@@ -274,48 +274,100 @@ sigma_gen_kernel(const double* __restrict__ est_x, const double* __restrict__ es
   sig_flags[n + t] = __float_as_uint(orbit_rate(r0, v0));  // substep rule input for all 13 points
 }
 
-__global__ void __launch_bounds__(128)
+// Coalesced store of one warp's 32 symmetric 6x6 matrices into an (N, 36) row-major array.
+// Each lane owns one matrix (packed upper triangle E); a direct store would be 36 STG.64 per lane
+// at a 288-byte lane stride (32 sectors per instruction).  Instead the warp transposes through a
+// padded shared-memory tile (row stride 37 doubles: conflict-free for 64-bit lanes) and writes its
+// 32 x 288 B = 9216 contiguous bytes with fully coalesced 256-byte rows.
+constexpr int kStageRow = 37;
+constexpr int kStageDoubles = 32 * kStageRow;
+
+__device__ __forceinline__ void store_sym36_warp(double* __restrict__ g, int64_t warp_t0, int64_t n,
+                                                 const double (&E)[21], double* __restrict__ stage,
+                                                 int lane) {
+  double* mine = stage + lane * kStageRow;
+#pragma unroll
+  for (int ra = 0; ra < 6; ++ra)
+#pragma unroll
+    for (int rb = 0; rb < 6; ++rb) mine[ra * 6 + rb] = E[ra <= rb ? uidx(ra, rb) : uidx(rb, ra)];
+  __syncwarp();
+  const int64_t rows = n - warp_t0 < 32 ? n - warp_t0 : 32;
+  const int valid = (int)rows * 36;
+  double* out = g + warp_t0 * 36;
+#pragma unroll 4
+  for (int k = lane; k < 32 * 36; k += 32) {
+    const int row = k / 36, e = k - row * 36;
+    if (k < valid) out[k] = stage[row * kStageRow + e];
+  }
+  __syncwarp();
+}
+
+constexpr int kVisTile = 256;  // sensors staged per pass of the fused visibility phase (8 KB)
+
+__device__ __forceinline__ void load_sensor_tile(double4* __restrict__ tile,
+                                                 const double4* __restrict__ sens_q, int64_t j0,
+                                                 int64_t M, int tpb) {
+  const double nan = __longlong_as_double(0x7ff8000000000000LL);
+  for (int j = threadIdx.x; j < kVisTile; j += tpb)
+    tile[j] = (j0 + j < M) ? sens_q[j0 + j] : make_double4(0.0, 0.0, 0.0, nan);  // NaN horizon: never visible
+}
+
+// Stage 3 of the step, one THREAD per target: unscented transform, measurement update, outputs,
+// next step's sigma points and -- fused, because the new estimate and the truth position are in
+// registers and the kernel is otherwise HBM-latency bound -- the target's row of BOTH visibility
+// maps (env.py:455-462) against the sensor tile staged in shared memory.
+template <int TPB>
+__global__ void __launch_bounds__(TPB, TPB == 128 ? 3 : (TPB == 64 ? 6 : 8))
 ukf_finish_kernel(const __grid_constant__ UkfArgs a) {
-  const int64_t t = (int64_t)blockIdx.x * 128 + threadIdx.x;
+  extern __shared__ __align__(32) double smem[];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  double* stage = smem + warp * kStageDoubles;
+  double4* tile = reinterpret_cast<double4*>(smem + (TPB / 32) * kStageDoubles);
+  const int64_t t = (int64_t)blockIdx.x * TPB + threadIdx.x;
   if (a.clock && a.advance_clock && t == 0) {
     // nobody reads t_now / step during this launch (kernels read the t_cur / step_cur copies)
     a.clock->t_now += a.dt;
     a.clock->step += 1;
   }
-  if (t >= a.n) return;
+  const bool live = t < a.n;
+  const int64_t tc = live ? t : a.n - 1;  // dead lanes shadow the last target and store nothing
+  const int64_t warp_t0 = t - lane;
   const int64_t ld = a.ld, blk = 6 * a.ld;
   const double* __restrict__ sb = a.sb;
+  const bool vis = a.vis_truth != nullptr;
+  if (vis) load_sensor_tile(tile, a.sens_q, 0, a.M, TPB);
 
   // ---- unscented transform (predictStateEstimate / predictCovariance, ukf_v2.py:261-292) ------
-  double X0[6];
+  double X0[6], tr[3];
 #pragma unroll
-  for (int c = 0; c < 6; ++c) X0[c] = sb[(int64_t)c * ld + t];
-  double Sb[6], Ebb[21], EDD[21];
+  for (int c = 0; c < 6; ++c) X0[c] = sb[(int64_t)c * ld + tc];
+  if (vis) {
+#pragma unroll
+    for (int c = 0; c < 3; ++c) tr[c] = sb[13 * blk + (int64_t)c * ld + tc];
+  }
+  double Sb[6], F[21];  // F = sum_j 2 b_j b_j^T + D_j D_j^T / 2
 #pragma unroll
   for (int c = 0; c < 6; ++c) Sb[c] = 0.0;
 #pragma unroll
-  for (int k = 0; k < 21; ++k) {
-    Ebb[k] = 0.0;
-    EDD[k] = 0.0;
-  }
-#pragma unroll 2
+  for (int k = 0; k < 21; ++k) F[k] = 0.0;
+#pragma unroll 3
   for (int j = 0; j < 6; ++j) {
-    double b[6], D[6];
+    double b[6], D[6], b2[6], Dh[6];
 #pragma unroll
     for (int c = 0; c < 6; ++c) {
-      const double xp = sb[(1 + j) * blk + (int64_t)c * ld + t];
-      const double xm = sb[(7 + j) * blk + (int64_t)c * ld + t];
+      const double xp = sb[(1 + j) * blk + (int64_t)c * ld + tc];
+      const double xm = sb[(7 + j) * blk + (int64_t)c * ld + tc];
       b[c] = 0.5 * ((xp - X0[c]) + (xm - X0[c]));  // (x+ + x-)/2 - X_0
       D[c] = xp - xm;
       Sb[c] += b[c];
+      b2[c] = b[c] + b[c];
+      Dh[c] = 0.5 * D[c];
     }
 #pragma unroll
     for (int ra = 0; ra < 6; ++ra)
 #pragma unroll
-      for (int rb = ra; rb < 6; ++rb) {
-        Ebb[uidx(ra, rb)] = fma(b[ra], b[rb], Ebb[uidx(ra, rb)]);
-        EDD[uidx(ra, rb)] = fma(D[ra], D[rb], EDD[uidx(ra, rb)]);
-      }
+      for (int rb = ra; rb < 6; ++rb)
+        F[uidx(ra, rb)] = fma(Dh[ra], D[rb], fma(b2[ra], b[rb], F[uidx(ra, rb)]));
   }
   double m[6], px[6];
 #pragma unroll
@@ -329,27 +381,21 @@ ukf_finish_kernel(const __grid_constant__ UkfArgs a) {
 #pragma unroll
     for (int rb = ra; rb < 6; ++rb) {
       const int k = uidx(ra, rb);
-      // sum_j a_j a_j^T with a_j = b_j - m
-      const double aa = fma(6.0 * m[ra], m[rb], Ebb[k] - (Sb[ra] * m[rb] + m[ra] * Sb[rb]));
-      E[k] = fma(a.p.wi, fma(2.0, aa, 0.5 * EDD[k]), fma(a.p.wc0 * m[ra], m[rb], a.p.Q[ra * 6 + rb]));
+      // sum_j a_j a_j^T with a_j = b_j - m:  Ebb - (Sb m^T + m Sb^T) + 6 m m^T
+      const double cross = fma(6.0 * m[ra], m[rb], -(Sb[ra] * m[rb] + m[ra] * Sb[rb]));
+      E[k] = fma(a.p.wi, fma(2.0, cross, F[k]), fma(a.p.wc0 * m[ra], m[rb], a.p.Q[ra * 6 + rb]));
     }
 
   // ---- update ----------------------------------------------------------------------------------
   int tasked = 0;
-  if (a.tasked) {
+  if (a.tasked && live) {
     tasked = a.tasked[t] != 0;
     if (tasked && a.clear_tasked) a.tasked[t] = 0;
   }
-  uint32_t flags = a.sig_flags ? a.sig_flags[t] : 0u;
+  uint32_t flags = a.sig_flags ? a.sig_flags[tc] : 0u;
   double xe[6], PE[21];
   double nis = __longlong_as_double(0x7ff8000000000000LL);
-  if (a.out_pred_p) {
-    double* gq = a.out_pred_p + t * 36;
-#pragma unroll
-    for (int ra = 0; ra < 6; ++ra)
-#pragma unroll
-      for (int rb = 0; rb < 6; ++rb) gq[ra * 6 + rb] = E[ra <= rb ? uidx(ra, rb) : uidx(rb, ra)];
-  }
+  if (a.out_pred_p) store_sym36_warp(a.out_pred_p, warp_t0, a.n, E, stage, lane);
   if (tasked) {
     const double t_now = a.clock ? a.clock->t_cur + a.dt : a.t_now;
     const uint64_t rng_step = a.clock ? a.clock->step_cur : a.rng_step;
@@ -408,41 +454,68 @@ ukf_finish_kernel(const __grid_constant__ UkfArgs a) {
   }
 
   // ---- outputs -----------------------------------------------------------------------------------
-  {
-    double* ge = a.est_p + t * 36;
-#pragma unroll
-    for (int ra = 0; ra < 6; ++ra)
-#pragma unroll
-      for (int rb = 0; rb < 6; ++rb) ge[ra * 6 + rb] = PE[ra <= rb ? uidx(ra, rb) : uidx(rb, ra)];
-  }
+  store_sym36_warp(a.est_p, warp_t0, a.n, PE, stage, lane);
   double chk = 0.0;
 #pragma unroll
   for (int c = 0; c < 6; ++c) chk += xe[c] + PE[uidx(c, c)];
   if (!isfinite(chk)) flags |= PC_FLAG_NONFINITE;
-  if (a.out_flags) a.out_flags[t] = flags;
-  if (a.out_nis) a.out_nis[t] = nis;
-  // scheduler summaries (env.py:599-609: traces of the float32 est_cov blocks)
-  if (a.tr_pos) a.tr_pos[t] = ((float)PE[uidx(0, 0)] + (float)PE[uidx(1, 1)]) + (float)PE[uidx(2, 2)];
-  if (a.tr_vel) a.tr_vel[t] = ((float)PE[uidx(3, 3)] + (float)PE[uidx(4, 4)]) + (float)PE[uidx(5, 5)];
-  if (a.out_pred_x) {
+  if (live) {
+    if (a.out_flags) a.out_flags[t] = flags;
+    if (a.out_nis) a.out_nis[t] = nis;
+    // scheduler summaries (env.py:599-609: traces of the float32 est_cov blocks)
+    if (a.tr_pos) a.tr_pos[t] = ((float)PE[uidx(0, 0)] + (float)PE[uidx(1, 1)]) + (float)PE[uidx(2, 2)];
+    if (a.tr_vel) a.tr_vel[t] = ((float)PE[uidx(3, 3)] + (float)PE[uidx(4, 4)]) + (float)PE[uidx(5, 5)];
+    if (a.out_pred_x) {
 #pragma unroll
-    for (int c = 0; c < 6; ++c) a.out_pred_x[(int64_t)c * ld + t] = px[c];
+      for (int c = 0; c < 6; ++c) a.out_pred_x[(int64_t)c * ld + t] = px[c];
+    }
+    if (a.truth_out) {
+#pragma unroll
+      for (int c = 0; c < 6; ++c) a.truth_out[(int64_t)c * ld + t] = sb[13 * blk + (int64_t)c * ld + t];
+    }
+    if (a.gen_next) {
+      // factor the NEW estimate and lay out next step's sigma points (block 0 = est_x)
+      double U[21];
+      const bool ok = chol_upper6_packed(PE, U);
+      write_sigma_blocks(a.sb, ld, t, xe, U, a.p.gamma);
+      a.sig_flags[t] = ok ? 0u : (uint32_t)PC_FLAG_NONPD_EST;
+      const double r0[3] = {xe[0], xe[1], xe[2]}, v0[3] = {xe[3], xe[4], xe[5]};
+      a.sig_flags[a.n + t] = __float_as_uint(orbit_rate(r0, v0));
+    } else if (a.est_x_out) {
+#pragma unroll
+      for (int c = 0; c < 6; ++c) a.est_x_out[(int64_t)c * ld + t] = xe[c];
+    }
   }
-  if (a.truth_out) {
-#pragma unroll
-    for (int c = 0; c < 6; ++c) a.truth_out[(int64_t)c * ld + t] = sb[13 * blk + (int64_t)c * ld + t];
-  }
-  if (a.gen_next) {
-    // factor the NEW estimate and lay out next step's sigma points (block 0 = est_x)
-    double U[21];
-    const bool ok = chol_upper6_packed(PE, U);
-    write_sigma_blocks(a.sb, ld, t, xe, U, a.p.gamma);
-    a.sig_flags[t] = ok ? 0u : (uint32_t)PC_FLAG_NONPD_EST;
-    const double r0[3] = {xe[0], xe[1], xe[2]}, v0[3] = {xe[3], xe[4], xe[5]};
-    a.sig_flags[a.n + t] = __float_as_uint(orbit_rate(r0, v0));
-  } else if (a.est_x_out) {
-#pragma unroll
-    for (int c = 0; c < 6; ++c) a.est_x_out[(int64_t)c * ld + t] = xe[c];
+
+  // ---- both visibility rows of this target for the next step (calcVisMap, visibility.py:56-116)
+  if (vis) {
+    const double RE2 = a.body_radius * a.body_radius;
+    const double tq = horizon_q(tr[0], tr[1], tr[2], a.body_radius, a.vis_tol);
+    const double eq = horizon_q(xe[0], xe[1], xe[2], a.body_radius, a.vis_tol);
+    const int64_t wpr = a.wpr;
+    for (int64_t j0 = 0; j0 < wpr * 32; j0 += kVisTile) {
+      if (j0) {
+        __syncthreads();
+        load_sensor_tile(tile, a.sens_q, j0, a.M, TPB);
+      }
+      __syncthreads();
+      const int64_t w0 = j0 >> 5;
+      const int nw = (int)(wpr - w0 < kVisTile / 32 ? wpr - w0 : kVisTile / 32);
+      for (int w = 0; w < nw; ++w) {
+        uint32_t wa = 0, wb = 0;
+        const double4* __restrict__ row = tile + w * 32;
+#pragma unroll 8
+        for (int b = 0; b < 32; ++b) {
+          const double4 s = row[b];
+          wa |= (uint32_t)sees(s, tr[0], tr[1], tr[2], tq, RE2) << b;
+          wb |= (uint32_t)sees(s, xe[0], xe[1], xe[2], eq, RE2) << b;
+        }
+        if (live) {
+          a.vis_truth[t * wpr + w0 + w] = wa;
+          a.vis_est[t * wpr + w0 + w] = wb;
+        }
+      }
+    }
   }
 }
 
@@ -455,10 +528,21 @@ cudaError_t launch_sigma_gen(const double* est_x, const double* est_p, const dou
   return cudaGetLastError();
 }
 
+template <int TPB>
+static cudaError_t launch_finish_tpb(const UkfArgs& a, cudaStream_t stream) {
+  const size_t smem = (size_t)(TPB / 32) * kStageDoubles * sizeof(double) + kVisTile * sizeof(double4);
+  ukf_finish_kernel<TPB><<<(unsigned)((a.n + TPB - 1) / TPB), TPB, smem, stream>>>(a);
+  return cudaGetLastError();
+}
+
+// Small catalogs cannot fill the machine with one thread per target, so they get one-warp CTAs
+// spread over every SM (each warp then owns a scheduler and its share of L1/LSU); large ones
+// get 128-thread CTAs (sensor tile amortised over 4 warps).
 cudaError_t launch_ukf_finish(const UkfArgs& a, cudaStream_t stream) {
   if (a.n <= 0) return cudaSuccess;
-  ukf_finish_kernel<<<(unsigned)((a.n + 127) / 128), 128, 0, stream>>>(a);
-  return cudaGetLastError();
+  if (a.n <= 32 * 1024) return launch_finish_tpb<32>(a, stream);
+  if (a.n <= 128 * 1024) return launch_finish_tpb<64>(a, stream);
+  return launch_finish_tpb<128>(a, stream);
 }
 
 }  // namespace pc

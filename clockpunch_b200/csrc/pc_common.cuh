@@ -20,6 +20,11 @@ constexpr double kJ2 = 1.08262668e-3;
 // kTheta is chosen so that the truncation error stays at the FP64 round-off
 // floor of the state (measured: DESIGN.md "integrator").
 constexpr double kTheta = 0.12;
+// Orbit rates above kOmegaMax belong to osculating orbits whose perigee lies deep below the
+// surface (a surface-grazing e -> 1 orbit has Omega = 5e-3 rad/s; 2e-2 rad/s is a perigee radius
+// of ~2500 km): diverged filter estimates.  Their rate is clamped and the target flagged
+// (PC_FLAG_SUBSTEP_CLAMP) instead of integrating a meaningless trajectory to tolerance.
+constexpr float kOmegaMax = 2.0e-2f;
 constexpr int kMaxAutoSubsteps = 1 << 16;
 
 struct UkfWeights {

@@ -28,6 +28,13 @@ struct UkfArgs {
   int gen_next;            // write the next step's sigma points (est_x = block 0) instead of est_x_out
   double* est_x_out;       // (6, ld) when !gen_next
   double* truth_out;       // (6, ld) copy of block 13, or NULL
+  // fused visibility phase (vis_truth == NULL: skipped): sensor positions + horizon terms at the
+  // end of the step, as written by the pre-step kernel
+  const double4* sens_q;
+  int64_t M, wpr;
+  uint32_t* vis_truth;
+  uint32_t* vis_est;
+  double body_radius, vis_tol;
   pc_ukf_params p;
 };
 

@@ -63,6 +63,7 @@ class CatalogEngine:
         self.truth_x.copy_(state_buf(target_states, self.ld))
         self.est_x.copy_(state_buf(np.asarray(est_x, dtype=np.float64).reshape(6, -1), self.ld))
         self.sig_flags = torch.zeros((2, self.N), dtype=torch.int32, device=dev)
+        self.sens_q = torch.zeros((self.ld_s, 4), dtype=f64, device=dev)   # double4 per sensor
         self._sigma_valid = False   # blocks 1..12 match (est_x, est_p)?
         self.est_p = torch.from_numpy(np.ascontiguousarray(est_p, dtype=np.float64).reshape(self.N, 36)).to(dev)
         self.pred_p = self.est_p.clone()
@@ -88,6 +89,8 @@ class CatalogEngine:
         # device-resident step clock (pc_clock: t_now, step, t_cur, step_cur) for graph replay
         self.clock = torch.zeros((32,), dtype=torch.uint8, device=dev)
         self._graph = None
+        self._hs_dt = None
+        self._hs_io = _lib.StepIO()
         self._sync_clock()
         self.compute_vis()
         self.snapshot()
@@ -121,6 +124,7 @@ class CatalogEngine:
         a.actions = None if actions is None else actions.data_ptr()
         a.policy_probes, a.policy_seed = int(policy_probes), int(policy_seed)
         a.sigma_ws, a.sig_flags = self.sigma.data_ptr(), self.sig_flags.data_ptr()
+        a.sens_q = self.sens_q.data_ptr()
         a.sigma_valid = 1 if self._sigma_valid else 0
         return a
 
@@ -170,7 +174,7 @@ class CatalogEngine:
         self._sigma_valid = True
         self.time = float(t_next)
         self.step_count += 1
-        if self._graph is not None:
+        if self._graph is not None or self._hs_dt is not None:
             self._sync_clock()
 
     # -- CUDA-graph replay of the whole step ------------------------------------------
@@ -219,6 +223,40 @@ class CatalogEngine:
         self.ensure_sigma()
         g.replay()
         self.time += g.pc_dt
+        self.step_count += 1
+
+    # -- the reference-facing step: host actions in, host observation out ------------------
+    def host_buffers(self, pinned: bool = True):
+        """Host-side (pinned) buffers for step_host: actions (M,) int64 in; obs float32
+        [eci_state (6, M+N) | est_cov (N, 6, 6) | obs_staleness (N)], packed estimated vis map
+        (N, wpr) and num_tasked (N,) out."""
+        torch = self.torch
+        mk = (lambda *a, **k: torch.empty(*a, **k).pin_memory()) if pinned else torch.empty
+        return {"actions": mk((max(1, self.M),), dtype=torch.int64),
+                "obs": mk((sum(self._obs_sizes),), dtype=torch.float32),
+                "vis_est": mk((self.N, self.wpr), dtype=torch.int32),
+                "num_tasked": mk((self.N,), dtype=torch.int64)}
+
+    def step_host(self, hb: dict, dt: float, policy_probes: int = 0, policy_seed: int = 0):
+        """One SSAScheduler.step for the whole catalog through pc_step_host: copies hb["actions"]
+        to the device, runs the step (a CUDA graph inside the library after the first call),
+        packs the float32 observation and copies it, the packed estimated vis map and num_tasked
+        into hb.  One C call per step; returns when the host buffers are filled."""
+        self.ensure_sigma()
+        if self._hs_dt != dt:
+            self.tasked.zero_()
+            self._sync_clock()
+            self._hs_dt = dt
+            self.torch.cuda.current_stream(self.dev).synchronize()
+        a = self._fill_args(0.0, float(dt), None, self.tasked, use_clock=True, actions=self.actions,
+                            policy_probes=policy_probes, policy_seed=policy_seed)
+        io = self._hs_io
+        io.h_actions = hb["actions"].data_ptr() if policy_probes == 0 else None
+        io.d_obs, io.h_obs = self.obs_f32.data_ptr(), hb["obs"].data_ptr()
+        io.h_vis_est, io.h_num_tasked = hb["vis_est"].data_ptr(), hb["num_tasked"].data_ptr()
+        c = self.ctx
+        c.check(c.lib.pc_step_host(c.handle, C.byref(a), C.byref(self.params), C.byref(io), self._stream()))
+        self.time += float(dt)
         self.step_count += 1
 
     def pack_obs(self, use_clock: bool = False):

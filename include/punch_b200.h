@@ -250,9 +250,32 @@ typedef struct pc_step_args {
    * With sigma_ws == NULL a context-owned buffer is used and est_x / truth_x are ordinary arrays. */
   double* sigma_ws;
   uint32_t* sig_flags;
+  /* (4, M) workspace, 32-byte aligned: sensor positions + horizon terms at the end of the step,
+   * written by the sensor kernel and read by the visibility phase of the target kernel.  NULL: a
+   * context-owned buffer is used (allocated on demand, so not usable under stream capture). */
+  double* sens_q;
 } pc_step_args;
 int pc_step_fused(pc_ctx* ctx, const pc_step_args* args, const pc_ukf_params* params,
                   pc_stream stream);
+
+/* ---- the step as the reference's caller sees it: host actions in, host observation out -------
+ * Replaces one SSAScheduler.step(action) (env.py:533-597) for the whole catalog: copies the M
+ * MultiDiscrete actions (target index per sensor, N = inaction; utilities.py:147-172) to the device,
+ * runs pc_step_fused, packs the float32 observation (pc_obs_pack: eci_state (6, M+N) | est_cov
+ * (N, 6, 6) | obs_staleness (N), env.py:261-270) and copies it, the packed estimated vis map and
+ * num_tasked back to the host, then synchronises.  When the argument block is replayable (device
+ * clock, caller-owned sigma buffer with sigma_valid, measurements drawn on device) the step + pack
+ * is captured into a CUDA graph on first use and replayed while the same buffers keep being passed.
+ * Host buffers may be pageable; pinned ones make the copies asynchronous to the kernels' tail. */
+typedef struct pc_step_io {
+  const int64_t* h_actions;  /* (M) host or NULL (actions already in args->actions) */
+  float* d_obs;              /* device workspace, 6(M+N) + 37N floats, or NULL (no observation) */
+  float* h_obs;              /* host destination of the same size, or NULL */
+  uint32_t* h_vis_est;       /* host (N, words_per_row) or NULL */
+  int64_t* h_num_tasked;     /* host (N) or NULL */
+} pc_step_io;
+int pc_step_host(pc_ctx* ctx, const pc_step_args* args, const pc_ukf_params* params,
+                 const pc_step_io* io, pc_stream stream);
 
 #ifdef __cplusplus
 }

@@ -395,3 +395,41 @@ def test_full_size_properties():
     # GEO targets see ~40% of ground sites, LEO far fewer; antipodal check
     vt = eng.host("vis_truth")
     assert vt[cat.regime == 2].mean() > 3 * vt[cat.regime == 0].mean() > 0
+
+
+def test_step_host_matches_graph_replay():
+    """pc_step_host (host actions in, float32 observation + packed vis map + num_tasked out, graph
+    cached inside the library) produces exactly what the device-resident replay path produces,
+    and its observation is the float32 cast of the device state (env.py:261-270, 419-452, 508-530)."""
+    import torch
+    cat, eng, _ = _engine_and_oracle(37, 6, seed=13)
+    rng = np.random.default_rng(3)
+    acts = [rng.integers(0, cat.N + 1, size=cat.M) for _ in range(4)]
+    gr = eng.build_graph(100.0, pack_obs=True)
+    ref = []
+    for a in acts:
+        eng.actions[: cat.M].copy_(torch.from_numpy(a))
+        eng.replay(gr)
+        ref.append((eng.obs_f32.cpu().numpy().copy(), eng.vis_est.cpu().numpy().copy(), eng.host("num_tasked").copy()))
+    eng.reset()
+    eng._graph = None
+    for pinned in (True, False):
+        eng.reset()
+        hb = eng.host_buffers(pinned=pinned)
+        for k, a in enumerate(acts):
+            hb["actions"][: cat.M].copy_(torch.from_numpy(a))
+            eng.step_host(hb, 100.0)
+            np.testing.assert_array_equal(hb["obs"].numpy(), ref[k][0])
+            np.testing.assert_array_equal(hb["vis_est"].numpy(), ref[k][1])
+            np.testing.assert_array_equal(hb["num_tasked"].numpy(), ref[k][2])
+        assert eng.time == 400.0
+    # the observation block is the float32 cast of the float64 device state
+    A = cat.M + cat.N
+    obs = hb["obs"].numpy()
+    eci = obs[: 6 * A].reshape(6, A)
+    np.testing.assert_array_equal(eci[:, : cat.M], eng.host("sens_x").astype(np.float32))
+    np.testing.assert_array_equal(eci[:, cat.M:], eng.host("est_x").astype(np.float32))
+    np.testing.assert_array_equal(obs[6 * A: 6 * A + 36 * cat.N].reshape(cat.N, 6, 6), eng.host("est_p").astype(np.float32))
+    stale = obs[6 * A + 36 * cat.N:]
+    np.testing.assert_array_equal(stale, (eng.time - eng.host("last_time_tasked").astype(np.float64)).astype(np.float32))
+    assert eng.host("num_tasked").sum() > 0
