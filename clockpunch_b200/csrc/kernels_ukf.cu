@@ -232,6 +232,88 @@ __device__ __forceinline__ bool chol_upper6_packed(const double (&E)[21], double
   return ok;
 }
 
+// The same measurement update with everything in registers (inlined): used by the quad kernel,
+// where occupancy is not the constraint and the latency of the local-memory version above would be
+// the critical path of the whole step.  Same operations in the same order as measurement_update,
+// so both produce identical bits.
+__device__ __forceinline__ uint32_t measurement_update_reg(
+    const double* __restrict__ sb, int64_t ld, int64_t blk, int64_t t, const double (&px)[6],
+    const double (&m)[6], const double (&E)[21], const double (&z)[6], const pc_ukf_params& p,
+    double (&xe)[6], double (&PE)[21], double& nis_out) {
+  uint32_t flags = 0;
+  double U2[21];
+  if (!chol_upper6_packed(E, U2)) flags |= PC_FLAG_NONPD_PRED;
+  const double c3 = p.wc0 - p.wm0;
+  const double cuu = 2.0 * p.wi * p.gamma * p.gamma;
+  const double cdd = p.wc0 + 12.0 * p.wi;
+  const double wg = p.wi * p.gamma;
+  double delta[6], nu[6];
+#pragma unroll
+  for (int c = 0; c < 6; ++c) {
+    delta[c] = p.eps_w * px[c];
+    nu[c] = z[c] - (px[c] + delta[c]);
+  }
+  double Sm[21];
+#pragma unroll
+  for (int a = 0; a < 6; ++a)
+#pragma unroll
+    for (int b = a; b < 6; ++b) {
+      double acc = 0.0;
+#pragma unroll
+      for (int j = b; j < 6; ++j) acc = fma(U2[uidx(a, j)], U2[uidx(b, j)], acc);
+      Sm[uidx(a, b)] = fma(cuu, acc, fma(cdd * delta[a], delta[b], p.R[a * 6 + b]));
+    }
+  double Us[21];
+  if (!chol_upper6_packed(Sm, Us)) flags |= PC_FLAG_NONPD_INNOV;
+  double dinv[6];
+#pragma unroll
+  for (int b = 0; b < 6; ++b) dinv[b] = 1.0 / Us[uidx(b, b)];
+  double y[6];
+  double nis = 0.0;
+#pragma unroll
+  for (int b = 0; b < 6; ++b) {
+    double acc = nu[b];
+#pragma unroll
+    for (int k = 0; k < b; ++k) acc = fma(-Us[uidx(k, b)], y[k], acc);
+    y[b] = acc * dinv[b];
+    nis = fma(y[b], y[b], nis);
+  }
+  nis_out = nis;
+  double G[6][6];
+#pragma unroll
+  for (int a = 0; a < 6; ++a) {
+    double D[6];
+#pragma unroll
+    for (int j = 0; j < 6; ++j)
+      D[j] = sb[(1 + j) * blk + (int64_t)a * ld + t] - sb[(7 + j) * blk + (int64_t)a * ld + t];
+    const double sa = delta[a] + c3 * m[a];
+#pragma unroll
+    for (int b = 0; b < 6; ++b) {
+      double acc = 0.0;
+#pragma unroll
+      for (int j = b; j < 6; ++j) acc = fma(D[j], U2[uidx(b, j)], acc);
+      double cab = fma(wg, acc, sa * delta[b]);
+#pragma unroll
+      for (int k = 0; k < b; ++k) cab = fma(-G[a][k], Us[uidx(k, b)], cab);
+      G[a][b] = cab * dinv[b];
+    }
+    double x = px[a];
+#pragma unroll
+    for (int b = 0; b < 6; ++b) x = fma(G[a][b], y[b], x);
+    xe[a] = x;
+  }
+#pragma unroll
+  for (int a = 0; a < 6; ++a)
+#pragma unroll
+    for (int b = a; b < 6; ++b) {
+      double acc = E[uidx(a, b)];
+#pragma unroll
+      for (int k = 0; k < 6; ++k) acc = fma(-G[a][k], G[b][k], acc);
+      PE[uidx(a, b)] = acc;
+    }
+  return flags;
+}
+
 // generateSigmaPoints (ukf_v2.py:158-183): x + gamma * [0, U, -U], COLUMNS of the upper factor.
 __device__ __forceinline__ void write_sigma_blocks(double* __restrict__ sb, int64_t ld, int64_t t,
                                                    const double (&x)[6], const double (&U)[21],
@@ -303,13 +385,55 @@ __device__ __forceinline__ void store_sym36_warp(double* __restrict__ g, int64_t
 }
 
 constexpr int kVisTile = 256;  // sensors staged per pass of the fused visibility phase (8 KB)
+// Each 32-sensor word occupies 33 double4 slots: lanes that work on different words of the same
+// tile (the quad kernel) then read shared-memory addresses 33 * 32 B apart, i.e. 8 banks apart,
+// and a 128-bit LDS with four distinct addresses is served in one wavefront instead of four.
+constexpr int kVisRow = 33;
+constexpr int kVisTileSlots = (kVisTile / 32) * kVisRow;
 
+// Asynchronous (cp.async, LDGSTS) copy of one sensor chunk into shared memory: issued at kernel
+// entry, waited for only when the visibility phase starts, so its latency hides behind the filter
+// algebra.  Slots past M get a NaN horizon term (never visible).
 __device__ __forceinline__ void load_sensor_tile(double4* __restrict__ tile,
                                                  const double4* __restrict__ sens_q, int64_t j0,
                                                  int64_t M, int tpb) {
   const double nan = __longlong_as_double(0x7ff8000000000000LL);
-  for (int j = threadIdx.x; j < kVisTile; j += tpb)
-    tile[j] = (j0 + j < M) ? sens_q[j0 + j] : make_double4(0.0, 0.0, 0.0, nan);  // NaN horizon: never visible
+  for (int j = threadIdx.x; j < kVisTile; j += tpb) {
+    const int slot = (j >> 5) * kVisRow + (j & 31);
+    if (j0 + j < M) {
+      const unsigned dst = (unsigned)__cvta_generic_to_shared(tile + slot);
+      const double4* src = sens_q + j0 + j;
+      asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+      asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(dst + 16), "l"((const char*)src + 16) : "memory");
+    } else {
+      tile[slot] = make_double4(0.0, 0.0, 0.0, nan);
+    }
+  }
+  asm volatile("cp.async.commit_group;" ::: "memory");
+}
+__device__ __forceinline__ void wait_sensor_tile() {
+  asm volatile("cp.async.wait_group 0;" ::: "memory");
+  __syncthreads();
+}
+
+// One 32-sensor word of both visibility rows of a target.  Sensors are fetched from shared memory
+// eight at a time before they are tested, so that the LDS latency is paid once per batch.
+__device__ __forceinline__ void vis_word(const double4* __restrict__ row, const double (&tr)[3], double tq,
+                                         const double (&xe)[6], double eq, double RE2, uint32_t& wa,
+                                         uint32_t& wb) {
+  wa = 0;
+  wb = 0;
+#pragma unroll
+  for (int b0 = 0; b0 < 32; b0 += 8) {
+    double4 s[8];
+#pragma unroll
+    for (int b = 0; b < 8; ++b) s[b] = row[b0 + b];
+#pragma unroll
+    for (int b = 0; b < 8; ++b) {
+      if (sees(s[b], tr[0], tr[1], tr[2], tq, RE2)) wa |= 1u << (b0 + b);
+      if (sees(s[b], xe[0], xe[1], xe[2], eq, RE2)) wb |= 1u << (b0 + b);
+    }
+  }
 }
 
 // Stage 3 of the step, one THREAD per target: unscented transform, measurement update, outputs,
@@ -498,18 +622,12 @@ ukf_finish_kernel(const __grid_constant__ UkfArgs a) {
         __syncthreads();
         load_sensor_tile(tile, a.sens_q, j0, a.M, TPB);
       }
-      __syncthreads();
+      wait_sensor_tile();
       const int64_t w0 = j0 >> 5;
       const int nw = (int)(wpr - w0 < kVisTile / 32 ? wpr - w0 : kVisTile / 32);
       for (int w = 0; w < nw; ++w) {
-        uint32_t wa = 0, wb = 0;
-        const double4* __restrict__ row = tile + w * 32;
-#pragma unroll 8
-        for (int b = 0; b < 32; ++b) {
-          const double4 s = row[b];
-          wa |= (uint32_t)sees(s, tr[0], tr[1], tr[2], tq, RE2) << b;
-          wb |= (uint32_t)sees(s, xe[0], xe[1], xe[2], eq, RE2) << b;
-        }
+        uint32_t wa, wb;
+        vis_word(tile + w * kVisRow, tr, tq, xe, eq, RE2, wa, wb);
         if (live) {
           a.vis_truth[t * wpr + w0 + w] = wa;
           a.vis_est[t * wpr + w0 + w] = wb;
@@ -528,19 +646,247 @@ cudaError_t launch_sigma_gen(const double* est_x, const double* est_p, const dou
   return cudaGetLastError();
 }
 
+// The same stage for SMALL catalogs, four lanes per target.  With one thread per target a 10k
+// catalog is 313 warps of ~6000 dependent instructions each on a 592-scheduler machine: pure
+// latency.  Here a quad shares one target: the six (+,-) sigma pairs are split over the lanes and
+// their partial sums combined with two xor-shuffles (every lane ends up with bit-identical sums,
+// so the 6x6 algebra that follows is simply replicated), stores and sigma-point writes are
+// distributed by lane, and each lane packs every fourth 32-sensor word of both visibility rows.
+constexpr int kQuadThreads = 64;
+constexpr int64_t kQuadMaxTargets = 32 * 1024;  // above this one thread per target fills the machine
+
+__device__ __forceinline__ double quad_sum(double v) {
+  v += __shfl_xor_sync(0xffffffffu, v, 1);
+  v += __shfl_xor_sync(0xffffffffu, v, 2);
+  return v;
+}
+
+__device__ __forceinline__ void store_sym36_quad(double* __restrict__ g, const double (&E)[21], int q) {
+  double2* row = reinterpret_cast<double2*>(g);
+#pragma unroll
+  for (int c = 0; c < 18; ++c) {
+    const int ra = (2 * c) / 6, rb = (2 * c) % 6;  // elements (ra, rb) and (ra, rb + 1)
+    if ((c & 3) == q)
+      row[c] = make_double2(E[ra <= rb ? uidx(ra, rb) : uidx(rb, ra)],
+                            E[ra <= rb + 1 ? uidx(ra, rb + 1) : uidx(rb + 1, ra)]);
+  }
+}
+
+__global__ void __launch_bounds__(kQuadThreads, 5)
+ukf_finish_quad_kernel(const __grid_constant__ UkfArgs a) {
+  __shared__ __align__(32) double4 tile[kVisTileSlots];
+  const int q = threadIdx.x & 3;
+  const int64_t t = ((int64_t)blockIdx.x * kQuadThreads + threadIdx.x) >> 2;
+  if (a.clock && a.advance_clock && blockIdx.x == 0 && threadIdx.x == 0) {
+    a.clock->t_now += a.dt;
+    a.clock->step += 1;
+  }
+  const bool live = t < a.n;
+  const int64_t tc = live ? t : a.n - 1;
+  const int64_t ld = a.ld, blk = 6 * a.ld;
+  const double* __restrict__ sb = a.sb;
+  const bool vis = a.vis_truth != nullptr;
+  if (vis) load_sensor_tile(tile, a.sens_q, 0, a.M, kQuadThreads);
+
+  // ---- unscented transform: lane q takes pairs q and q + 4 ------------------------------------
+  double X0[6], tr[3];
+#pragma unroll
+  for (int c = 0; c < 6; ++c) X0[c] = sb[(int64_t)c * ld + tc];
+  if (vis) {
+#pragma unroll
+    for (int c = 0; c < 3; ++c) tr[c] = sb[13 * blk + (int64_t)c * ld + tc];
+  }
+  double Sb[6], F[21];
+#pragma unroll
+  for (int c = 0; c < 6; ++c) Sb[c] = 0.0;
+#pragma unroll
+  for (int k = 0; k < 21; ++k) F[k] = 0.0;
+#pragma unroll
+  for (int h = 0; h < 2; ++h) {
+    const int j = q + 4 * h;
+    if (j < 6) {
+      double b[6], D[6], b2[6], Dh[6];
+#pragma unroll
+      for (int c = 0; c < 6; ++c) {
+        const double xp = sb[(1 + j) * blk + (int64_t)c * ld + tc];
+        const double xm = sb[(7 + j) * blk + (int64_t)c * ld + tc];
+        b[c] = 0.5 * ((xp - X0[c]) + (xm - X0[c]));
+        D[c] = xp - xm;
+        Sb[c] += b[c];
+        b2[c] = b[c] + b[c];
+        Dh[c] = 0.5 * D[c];
+      }
+#pragma unroll
+      for (int ra = 0; ra < 6; ++ra)
+#pragma unroll
+        for (int rb = ra; rb < 6; ++rb)
+          F[uidx(ra, rb)] = fma(Dh[ra], D[rb], fma(b2[ra], b[rb], F[uidx(ra, rb)]));
+    }
+  }
+#pragma unroll
+  for (int c = 0; c < 6; ++c) Sb[c] = quad_sum(Sb[c]);
+#pragma unroll
+  for (int k = 0; k < 21; ++k) F[k] = quad_sum(F[k]);
+
+  double m[6], px[6];
+#pragma unroll
+  for (int c = 0; c < 6; ++c) {
+    m[c] = fma(2.0 * a.p.wi, Sb[c], a.p.eps_w * X0[c]);
+    px[c] = X0[c] + m[c];
+  }
+  double E[21];
+#pragma unroll
+  for (int ra = 0; ra < 6; ++ra)
+#pragma unroll
+    for (int rb = ra; rb < 6; ++rb) {
+      const int k = uidx(ra, rb);
+      const double cross = fma(6.0 * m[ra], m[rb], -(Sb[ra] * m[rb] + m[ra] * Sb[rb]));
+      E[k] = fma(a.p.wi, fma(2.0, cross, F[k]), fma(a.p.wc0 * m[ra], m[rb], a.p.Q[ra * 6 + rb]));
+    }
+
+  // ---- update (replicated over the quad: identical inputs, identical results) -------------------
+  // every lane reads the flag (dead lanes shadow the last target) before lane 0 of a quad clears it
+  const int tflag = a.tasked ? (int)a.tasked[tc] : 0;
+  __syncwarp();
+  const int tasked = live && tflag != 0;
+  if (tasked && a.clear_tasked && q == 0) a.tasked[t] = 0;
+  uint32_t flags = a.sig_flags ? a.sig_flags[tc] : 0u;
+  double xe[6], PE[21];
+  double nis = __longlong_as_double(0x7ff8000000000000LL);
+  if (a.out_pred_p && live) store_sym36_quad(a.out_pred_p + t * 36, E, q);
+  if (tasked) {
+    const double t_now = a.clock ? a.clock->t_cur + a.dt : a.t_now;
+    const uint64_t rng_step = a.clock ? a.clock->step_cur : a.rng_step;
+    double z[6];
+    if (a.z) {
+#pragma unroll
+      for (int c = 0; c < 6; ++c) z[c] = a.z[(int64_t)c * ld + t];
+    } else {
+      // Target.getMeasurement (agents.py:173-183): z ~ N(truth', R)
+      double nrm[6];
+      normal6(a.rng_seed, rng_step, (uint64_t)t, nrm);
+#pragma unroll
+      for (int c = 0; c < 6; ++c) {
+        double acc = sb[13 * blk + (int64_t)c * ld + t];
+#pragma unroll
+        for (int k = 0; k <= c; ++k) acc = fma(a.p.Lr[c * 6 + k], nrm[k], acc);
+        z[c] = acc;
+      }
+    }
+    flags |= measurement_update_reg(sb, ld, blk, t, px, m, E, z, a.p, xe, PE, nis);
+    if (q == 0) {
+      if (a.out_z) {
+#pragma unroll
+        for (int c = 0; c < 6; ++c) a.out_z[(int64_t)c * ld + t] = z[c];
+      }
+      if (a.num_tasked) a.num_tasked[t] += 1;
+      if (a.last_time_tasked) a.last_time_tasked[t] = (float)t_now;
+    }
+  } else {
+#pragma unroll
+    for (int c = 0; c < 6; ++c) xe[c] = X0[c];
+#pragma unroll
+    for (int k = 0; k < 21; ++k) PE[k] = E[k];
+  }
+
+  // ---- outputs, distributed over the quad ----------------------------------------------------------
+  double chk = 0.0;
+#pragma unroll
+  for (int c = 0; c < 6; ++c) chk += xe[c] + PE[uidx(c, c)];
+  if (!isfinite(chk)) flags |= PC_FLAG_NONFINITE;
+  if (live) {
+    store_sym36_quad(a.est_p + t * 36, PE, q);
+    if (q == 1) {
+      if (a.out_flags) a.out_flags[t] = flags;
+      if (a.out_nis) a.out_nis[t] = nis;
+      if (a.tr_pos) a.tr_pos[t] = ((float)PE[uidx(0, 0)] + (float)PE[uidx(1, 1)]) + (float)PE[uidx(2, 2)];
+      if (a.tr_vel) a.tr_vel[t] = ((float)PE[uidx(3, 3)] + (float)PE[uidx(4, 4)]) + (float)PE[uidx(5, 5)];
+    }
+    if (a.out_pred_x && q == 2) {
+#pragma unroll
+      for (int c = 0; c < 6; ++c) a.out_pred_x[(int64_t)c * ld + t] = px[c];
+    }
+    if (a.truth_out && q == 3) {
+#pragma unroll
+      for (int c = 0; c < 6; ++c) a.truth_out[(int64_t)c * ld + t] = sb[13 * blk + (int64_t)c * ld + t];
+    }
+    if (a.gen_next) {
+      double U[21];
+      const bool ok = chol_upper6_packed(PE, U);
+      // block 0 (centre) and the 12 offset blocks, block i written by lane i & 3
+      if (q == 0) {
+#pragma unroll
+        for (int c = 0; c < 6; ++c) a.sb[(int64_t)c * ld + t] = xe[c];
+        a.sig_flags[t] = ok ? 0u : (uint32_t)PC_FLAG_NONPD_EST;
+        const double r0[3] = {xe[0], xe[1], xe[2]}, v0[3] = {xe[3], xe[4], xe[5]};
+        a.sig_flags[a.n + t] = __float_as_uint(orbit_rate(r0, v0));
+      }
+#pragma unroll
+      for (int j = 0; j < 6; ++j) {
+        // blocks 1 + j and 7 + j: x +- gamma U[:, j]
+        if (((1 + j) & 3) == q) {
+#pragma unroll
+          for (int c = 0; c < 6; ++c) {
+            const double gq = (c <= j) ? a.p.gamma * U[uidx(c <= j ? c : j, j)] : 0.0;
+            a.sb[(1 + j) * blk + (int64_t)c * ld + t] = xe[c] + gq;
+          }
+        }
+        if (((7 + j) & 3) == q) {
+#pragma unroll
+          for (int c = 0; c < 6; ++c) {
+            const double gq = (c <= j) ? a.p.gamma * U[uidx(c <= j ? c : j, j)] : 0.0;
+            a.sb[(7 + j) * blk + (int64_t)c * ld + t] = xe[c] - gq;
+          }
+        }
+      }
+    } else if (a.est_x_out && q == 0) {
+#pragma unroll
+      for (int c = 0; c < 6; ++c) a.est_x_out[(int64_t)c * ld + t] = xe[c];
+    }
+  }
+
+  // ---- visibility: lane q packs words q, q + 4, ... of both rows ---------------------------------
+  if (vis) {
+    const double RE2 = a.body_radius * a.body_radius;
+    const double tq = horizon_q(tr[0], tr[1], tr[2], a.body_radius, a.vis_tol);
+    const double eq = horizon_q(xe[0], xe[1], xe[2], a.body_radius, a.vis_tol);
+    const int64_t wpr = a.wpr;
+    for (int64_t j0 = 0; j0 < wpr * 32; j0 += kVisTile) {
+      if (j0) {
+        __syncthreads();
+        load_sensor_tile(tile, a.sens_q, j0, a.M, kQuadThreads);
+      }
+      wait_sensor_tile();
+      const int64_t w0 = j0 >> 5;
+      const int nw = (int)(wpr - w0 < kVisTile / 32 ? wpr - w0 : kVisTile / 32);
+      for (int w = q; w < nw; w += 4) {
+        uint32_t wa, wb;
+        vis_word(tile + w * kVisRow, tr, tq, xe, eq, RE2, wa, wb);
+        if (live) {
+          a.vis_truth[t * wpr + w0 + w] = wa;
+          a.vis_est[t * wpr + w0 + w] = wb;
+        }
+      }
+    }
+  }
+}
+
 template <int TPB>
 static cudaError_t launch_finish_tpb(const UkfArgs& a, cudaStream_t stream) {
-  const size_t smem = (size_t)(TPB / 32) * kStageDoubles * sizeof(double) + kVisTile * sizeof(double4);
+  const size_t smem = (size_t)(TPB / 32) * kStageDoubles * sizeof(double) + kVisTileSlots * sizeof(double4);
   ukf_finish_kernel<TPB><<<(unsigned)((a.n + TPB - 1) / TPB), TPB, smem, stream>>>(a);
   return cudaGetLastError();
 }
 
-// Small catalogs cannot fill the machine with one thread per target, so they get one-warp CTAs
-// spread over every SM (each warp then owns a scheduler and its share of L1/LSU); large ones
-// get 128-thread CTAs (sensor tile amortised over 4 warps).
+// Small catalogs cannot fill the machine with one thread per target: they take the quad kernel
+// (four lanes per target); large ones get one thread per target with 64- or 128-thread CTAs
+// (sensor tile amortised over more warps).
 cudaError_t launch_ukf_finish(const UkfArgs& a, cudaStream_t stream) {
   if (a.n <= 0) return cudaSuccess;
-  if (a.n <= 32 * 1024) return launch_finish_tpb<32>(a, stream);
+  if (a.n <= kQuadMaxTargets) {
+    ukf_finish_quad_kernel<<<(unsigned)((4 * a.n + kQuadThreads - 1) / kQuadThreads), kQuadThreads, 0, stream>>>(a);
+    return cudaGetLastError();
+  }
   if (a.n <= 128 * 1024) return launch_finish_tpb<64>(a, stream);
   return launch_finish_tpb<128>(a, stream);
 }

@@ -21,6 +21,10 @@ namespace pc {
 
 constexpr int kVisThreads = 128;
 constexpr int kSensTile = 1024;  // sensors staged per pass: 1024 * 32 B = 32 KB
+// 33 slots per 32-sensor word: threads of a warp own different words, and without the pad their
+// 128-bit LDS addresses are 1 KB apart (same banks, 4- to 32-way conflicts)
+constexpr int kSensRow = 33;
+constexpr int kSensSlots = (kSensTile / 32) * kSensRow;
 
 // One thread per output word: (target i, sensors 32w .. 32w+31), both maps.
 template <bool TWO>
@@ -30,7 +34,7 @@ vismap_packed_kernel(const double* __restrict__ sens, int64_t M, int64_t ld_s,
                      const double* __restrict__ ta, const double* __restrict__ tb, int64_t N,
                      int64_t ld_t, double RE, double tol, uint32_t* __restrict__ out_a,
                      uint32_t* __restrict__ out_b, int64_t wpr) {
-  __shared__ double4 tile[kSensTile];
+  __shared__ double4 tile[kSensSlots];
   const int64_t idx = (int64_t)blockIdx.x * kVisThreads + threadIdx.x;
   const bool live = idx < N * wpr;
   const int64_t i = live ? idx / wpr : 0;
@@ -59,15 +63,16 @@ vismap_packed_kernel(const double* __restrict__ sens, int64_t M, int64_t ld_s,
         y = sn * x + cs * y;
         x = xr;
       }
-      tile[j] = make_double4(x, y, z, horizon_q(x, y, z, RE, tol));
+      tile[(j >> 5) * kSensRow + (j & 31)] = make_double4(x, y, z, horizon_q(x, y, z, RE, tol));
     }
     __syncthreads();
     const int64_t s0 = w * 32 - j0;  // first sensor of this word, relative to the tile
     if (live && s0 >= 0 && s0 < cnt) {
       const int lim = min(32, cnt - (int)s0);
+      const double4* __restrict__ row = tile + (s0 >> 5) * kSensRow;
 #pragma unroll 4
       for (int b = 0; b < lim; ++b) {
-        const double4 s = tile[s0 + b];
+        const double4 s = row[b];
         const double da = fma(s.z, az, fma(s.y, ay, s.x * ax));
         wa |= (uint32_t)(da > fma(-s.w, aq, RE2)) << b;
         if (TWO) {
