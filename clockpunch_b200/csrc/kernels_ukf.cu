@@ -36,6 +36,11 @@
 #include "ukf_args.cuh"
 #include "vis.cuh"
 
+// Phase stamps for tools/microbench/finish_phases.cu (no-ops in the library build).
+#ifndef PC_PHASE_CLOCK
+#define PC_PHASE_CLOCK(i)
+#endif
+
 namespace pc {
 
 struct TargetSmem {   // scratch of the measurement update (thread-local for tasked targets)
@@ -681,6 +686,7 @@ ukf_finish_quad_kernel(const __grid_constant__ UkfArgs a) {
     a.clock->t_now += a.dt;
     a.clock->step += 1;
   }
+  PC_PHASE_CLOCK(0);
   const bool live = t < a.n;
   const int64_t tc = live ? t : a.n - 1;
   const int64_t ld = a.ld, blk = 6 * a.ld;
@@ -688,14 +694,29 @@ ukf_finish_quad_kernel(const __grid_constant__ UkfArgs a) {
   const bool vis = a.vis_truth != nullptr;
   if (vis) load_sensor_tile(tile, a.sens_q, 0, a.M, kQuadThreads);
 
-  // ---- unscented transform: lane q takes pairs q and q + 4 ------------------------------------
-  double X0[6], tr[3];
+  // ---- every global load of the untasked path is issued here, before any arithmetic -------------
+  // (one round trip to HBM instead of four: at this occupancy latency is the whole cost)
+  double X0[6], tr[3], xp[2][6], xm[2][6];
 #pragma unroll
   for (int c = 0; c < 6; ++c) X0[c] = sb[(int64_t)c * ld + tc];
+#pragma unroll
+  for (int h = 0; h < 2; ++h) {
+    const int j = (q + 4 * h < 6) ? q + 4 * h : 5;  // lanes 2, 3 have no second pair: shadow pair 5
+#pragma unroll
+    for (int c = 0; c < 6; ++c) {
+      xp[h][c] = sb[(1 + j) * blk + (int64_t)c * ld + tc];
+      xm[h][c] = sb[(7 + j) * blk + (int64_t)c * ld + tc];
+    }
+  }
   if (vis) {
 #pragma unroll
     for (int c = 0; c < 3; ++c) tr[c] = sb[13 * blk + (int64_t)c * ld + tc];
   }
+  const int tflag = a.tasked ? (int)a.tasked[tc] : 0;
+  uint32_t flags = a.sig_flags ? a.sig_flags[tc] : 0u;
+  PC_PHASE_CLOCK(1);
+
+  // ---- unscented transform: lane q takes pairs q and q + 4 ------------------------------------
   double Sb[6], F[21];
 #pragma unroll
   for (int c = 0; c < 6; ++c) Sb[c] = 0.0;
@@ -703,15 +724,12 @@ ukf_finish_quad_kernel(const __grid_constant__ UkfArgs a) {
   for (int k = 0; k < 21; ++k) F[k] = 0.0;
 #pragma unroll
   for (int h = 0; h < 2; ++h) {
-    const int j = q + 4 * h;
-    if (j < 6) {
+    if (q + 4 * h < 6) {
       double b[6], D[6], b2[6], Dh[6];
 #pragma unroll
       for (int c = 0; c < 6; ++c) {
-        const double xp = sb[(1 + j) * blk + (int64_t)c * ld + tc];
-        const double xm = sb[(7 + j) * blk + (int64_t)c * ld + tc];
-        b[c] = 0.5 * ((xp - X0[c]) + (xm - X0[c]));
-        D[c] = xp - xm;
+        b[c] = 0.5 * ((xp[h][c] - X0[c]) + (xm[h][c] - X0[c]));
+        D[c] = xp[h][c] - xm[h][c];
         Sb[c] += b[c];
         b2[c] = b[c] + b[c];
         Dh[c] = 0.5 * D[c];
@@ -723,11 +741,13 @@ ukf_finish_quad_kernel(const __grid_constant__ UkfArgs a) {
           F[uidx(ra, rb)] = fma(Dh[ra], D[rb], fma(b2[ra], b[rb], F[uidx(ra, rb)]));
     }
   }
+  PC_PHASE_CLOCK(2);
 #pragma unroll
   for (int c = 0; c < 6; ++c) Sb[c] = quad_sum(Sb[c]);
 #pragma unroll
   for (int k = 0; k < 21; ++k) F[k] = quad_sum(F[k]);
 
+  PC_PHASE_CLOCK(3);
   double m[6], px[6];
 #pragma unroll
   for (int c = 0; c < 6; ++c) {
@@ -745,12 +765,11 @@ ukf_finish_quad_kernel(const __grid_constant__ UkfArgs a) {
     }
 
   // ---- update (replicated over the quad: identical inputs, identical results) -------------------
-  // every lane reads the flag (dead lanes shadow the last target) before lane 0 of a quad clears it
-  const int tflag = a.tasked ? (int)a.tasked[tc] : 0;
+  PC_PHASE_CLOCK(4);
+  // every lane has read the flag (dead lanes shadow the last target) before lane 0 of a quad clears it
   __syncwarp();
   const int tasked = live && tflag != 0;
   if (tasked && a.clear_tasked && q == 0) a.tasked[t] = 0;
-  uint32_t flags = a.sig_flags ? a.sig_flags[tc] : 0u;
   double xe[6], PE[21];
   double nis = __longlong_as_double(0x7ff8000000000000LL);
   if (a.out_pred_p && live) store_sym36_quad(a.out_pred_p + t * 36, E, q);
@@ -789,6 +808,7 @@ ukf_finish_quad_kernel(const __grid_constant__ UkfArgs a) {
     for (int k = 0; k < 21; ++k) PE[k] = E[k];
   }
 
+  PC_PHASE_CLOCK(5);
   // ---- outputs, distributed over the quad ----------------------------------------------------------
   double chk = 0.0;
 #pragma unroll
@@ -810,6 +830,7 @@ ukf_finish_quad_kernel(const __grid_constant__ UkfArgs a) {
 #pragma unroll
       for (int c = 0; c < 6; ++c) a.truth_out[(int64_t)c * ld + t] = sb[13 * blk + (int64_t)c * ld + t];
     }
+    PC_PHASE_CLOCK(6);
     if (a.gen_next) {
       double U[21];
       const bool ok = chol_upper6_packed(PE, U);
@@ -845,6 +866,7 @@ ukf_finish_quad_kernel(const __grid_constant__ UkfArgs a) {
     }
   }
 
+  PC_PHASE_CLOCK(7);
   // ---- visibility: lane q packs words q, q + 4, ... of both rows ---------------------------------
   if (vis) {
     const double RE2 = a.body_radius * a.body_radius;
@@ -857,6 +879,7 @@ ukf_finish_quad_kernel(const __grid_constant__ UkfArgs a) {
         load_sensor_tile(tile, a.sens_q, j0, a.M, kQuadThreads);
       }
       wait_sensor_tile();
+      PC_PHASE_CLOCK(8);
       const int64_t w0 = j0 >> 5;
       const int nw = (int)(wpr - w0 < kVisTile / 32 ? wpr - w0 : kVisTile / 32);
       for (int w = q; w < nw; w += 4) {
@@ -869,6 +892,7 @@ ukf_finish_quad_kernel(const __grid_constant__ UkfArgs a) {
       }
     }
   }
+  PC_PHASE_CLOCK(9);
 }
 
 template <int TPB>
