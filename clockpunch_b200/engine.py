@@ -285,6 +285,28 @@ class CatalogEngine:
         self.time, self.step_count, self._sigma_valid = t, sc, sv
         self._sync_clock()
 
+    def clone(self) -> "CatalogEngine":
+        """Independent copy: device buffers cloned, library context shared (deepcopy of an env)."""
+        torch = self.torch
+        new = object.__new__(CatalogEngine)
+        for k, v in self.__dict__.items():
+            if isinstance(v, torch.Tensor):
+                setattr(new, k, v.clone())
+            elif k in ("_args", "_hs_io", "_graph", "_snapshot", "est_x", "truth_x"):
+                continue
+            else:
+                setattr(new, k, v)
+        new.est_x, new.truth_x = new.sigma[0], new.sigma[13]      # views into the cloned sigma buffer
+        new._args, new._hs_io = _lib.StepArgs(), _lib.StepIO()
+        new._graph, new._hs_dt = None, None
+        bufs, t, sc, sv = self._snapshot
+        new._snapshot = ({k: v.clone() for k, v in bufs.items()}, t, sc, sv)
+        new._sync_clock()
+        return new
+
+    def __deepcopy__(self, memo):
+        return self.clone()
+
     # -- host views --------------------------------------------------------------
     def host(self, name: str) -> np.ndarray:
         t = getattr(self, name)

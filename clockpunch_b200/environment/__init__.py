@@ -1,0 +1,1 @@
+"""Environment layer on the CUDA step: SSAScheduler mirror and its helpers."""
