@@ -172,6 +172,8 @@ def run_own(args):
         raise SystemExit("bench.py needs a CUDA device (no CPU fallback); use --impl reference for the CPU arm")
     torch.cuda.set_device(local)
     if world > 1:
+        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
+            os.environ["NCCL_DEBUG"] = "WARN"       # keep stdout to the one JSON line
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     dev = torch.device("cuda", local)
 
@@ -189,18 +191,19 @@ def run_own(args):
     # buffers the kernels write (equal shards: no staging copy)
     sg = None
     if world > 1:
-        from clockpunch_b200.sharding import StepGather, TargetPartition
-        sg = StepGather(TargetPartition(world * N, world), rank,
-                        {"vis_est": eng.vis_est, "tr_pos": eng.tr_pos, "tr_vel": eng.tr_vel,
-                         "last_time_tasked": eng.last_time_tasked, "num_tasked": eng.num_tasked})
+        from clockpunch_b200.sharding import PackedGather
+        sg = PackedGather(world, rank, eng.summary, N, eng.wpr)
+    gather_in_graph = sg is not None and not args.eager_gather
+    post = sg.gather if gather_in_graph else None
 
-    # policy -> tasking mask -> sensors -> truth + UKF -> vis maps, captured once, replayed per step
+    # policy -> tasking mask -> sensors -> truth + UKF -> vis maps [-> all-gather], captured once,
+    # replayed per step
     g_value = None
 
     def device_step():
         eng.replay(g_value)
-        if sg is not None:
-            sg.gather(unpad=False)
+        if sg is not None and not gather_in_graph:
+            sg.gather()
 
     def barrier():
         torch.cuda.synchronize(dev)
@@ -209,7 +212,10 @@ def run_own(args):
             torch.cuda.synchronize(dev)
 
     # ---------------- device-resident throughput (`value`) ----------------
-    g_value = eng.build_graph(DT, policy_probes=64, policy_seed=SEED)
+    if sg is not None:
+        sg.gather()                      # first NCCL call (communicator set-up) outside any capture
+        torch.cuda.synchronize(dev)
+    g_value = eng.build_graph(DT, policy_probes=64, policy_seed=SEED, post=post)
     for k in range(args.warmup):
         device_step()
     peak_tf = C.c_double()
@@ -246,7 +252,7 @@ def run_own(args):
     # Every pass (value, roofline, e2e) starts from the same catalog state: reset + warm-up.
     eng.reset()
     ctx.check(lib.pc_set_timing(ctx.handle, 1))        # before capture: the event pair is part of the graph
-    g_timed = eng.build_graph(DT, policy_probes=64, policy_seed=SEED)
+    g_timed = eng.build_graph(DT, policy_probes=64, policy_seed=SEED, post=post)
     for k in range(args.warmup):
         eng.replay(g_timed)
     inv_theta = np.float32(1.0 / 0.12)
@@ -333,7 +339,7 @@ def run_own(args):
         host_policy(k)
         eng.step_host(hb, DT)
         if world > 1:
-            sg.gather(unpad=False)
+            sg.gather()
             torch.cuda.current_stream(dev).synchronize()
 
     hb["vis_est"].copy_(eng.vis_est)
@@ -356,9 +362,18 @@ def run_own(args):
                    "-> [CUDA graph: pc_step_fused + pc_obs_pack] -> pinned host float32 obs + packed vis map + "
                    "num_tasked, stream sync; timed by the host clock around the loop"}
 
-    if rank != 0:
+    def leave():
+        # Ranks leave together and without tearing NCCL down: destroying a process group whose
+        # collectives live inside instantiated CUDA graphs can block at exit.
         if world > 1:
-            dist.destroy_process_group()
+            sys.stdout.flush()
+            torch.cuda.synchronize(dev)
+            dist.barrier()
+            torch.cuda.synchronize(dev)
+            os._exit(0)
+
+    if rank != 0:
+        leave()
         return
 
     # ---------------- CPU baseline beside it (rank 0, N = 1 only) ----------------
@@ -379,8 +394,7 @@ def run_own(args):
                       "wall_s_timed_region": wall, "launches_per_step": launches / args.steps, "cuda_graph": True,
                       "target_propagation_steps_per_s": 14 * value}}
     print(json.dumps(line))
-    if world > 1:
-        dist.destroy_process_group()
+    leave()
 
 
 def main():
@@ -395,6 +409,7 @@ def main():
     ap.add_argument("--cpu-sample-per-core", type=int, default=0, help="0 = sized for the time budget")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--l2", default="flush", choices=["flush", "none"])
+    ap.add_argument("--eager-gather", action="store_true", help="N > 1: all-gather outside the step's CUDA graph")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "own" else args.warmup
     if args.impl == "reference":

@@ -70,15 +70,17 @@ class CatalogEngine:
         self.nis = torch.full((self.N,), float("nan"), dtype=f64, device=dev)
         self.flags = torch.zeros((self.N,), dtype=torch.int32, device=dev)
         self.vis_truth = torch.zeros((self.N, self.wpr), dtype=torch.int32, device=dev)
-        self.vis_est = torch.zeros((self.N, self.wpr), dtype=torch.int32, device=dev)
+        # what every other shard's scheduler needs from this one each step lives in
+        # ONE buffer, so that the per-step exchange is a single all-gather: num_tasked (int64) |
+        # packed estimated vis map (int32 words) | tr_pos | tr_vel | last_time_tasked (float32)
+        self.summary = torch.zeros((self.N * (8 + 4 * self.wpr + 12),), dtype=torch.uint8, device=dev)
+        self._bind_summary_views()
         self.tasked = torch.zeros((self.N,), dtype=torch.uint8, device=dev)
         self.z = torch.zeros((6, self.ld), dtype=f64, device=dev)
         nt = np.zeros(self.N, np.int64) if init_num_tasked is None else np.asarray(init_num_tasked, np.int64)
         lt = np.zeros(self.N, np.float32) if init_last_time_tasked is None else np.asarray(init_last_time_tasked, np.float32)
-        self.num_tasked = torch.from_numpy(nt.copy()).to(dev)
-        self.last_time_tasked = torch.from_numpy(lt.copy()).to(dev)
-        self.tr_pos = torch.zeros((self.N,), dtype=torch.float32, device=dev)
-        self.tr_vel = torch.zeros((self.N,), dtype=torch.float32, device=dev)
+        self.num_tasked.copy_(torch.from_numpy(nt.copy()))
+        self.last_time_tasked.copy_(torch.from_numpy(lt.copy()))
         self.actions = torch.zeros((max(1, self.M),), dtype=torch.int64, device=dev)
         # float32 observation block (one contiguous buffer -> one D2H copy)
         A = self.M + self.N
@@ -94,6 +96,26 @@ class CatalogEngine:
         self._sync_clock()
         self.compute_vis()
         self.snapshot()
+
+    def _bind_summary_views(self):
+        torch, N, w = self.torch, self.N, self.wpr
+        b, o = self.summary, 0
+        self.num_tasked = b[o: o + 8 * N].view(torch.int64); o += 8 * N
+        self.vis_est = b[o: o + 4 * w * N].view(torch.int32).view(N, w); o += 4 * w * N
+        self.tr_pos = b[o: o + 4 * N].view(torch.float32); o += 4 * N
+        self.tr_vel = b[o: o + 4 * N].view(torch.float32); o += 4 * N
+        self.last_time_tasked = b[o: o + 4 * N].view(torch.float32)
+
+    @staticmethod
+    def summary_views(block, N: int, wpr: int) -> dict:
+        """Field views of one shard's summary block (as received from the all-gather)."""
+        import torch
+        o, out = 0, {}
+        out["num_tasked"] = block[o: o + 8 * N].view(torch.int64); o += 8 * N
+        out["vis_est"] = block[o: o + 4 * wpr * N].view(torch.int32).view(N, wpr); o += 4 * wpr * N
+        for k in ("tr_pos", "tr_vel", "last_time_tasked"):
+            out[k] = block[o: o + 4 * N].view(torch.float32); o += 4 * N
+        return out
 
     # -- helpers -----------------------------------------------------------
     def _stream(self):
@@ -178,7 +200,8 @@ class CatalogEngine:
             self._sync_clock()
 
     # -- CUDA-graph replay of the whole step ------------------------------------------
-    def build_graph(self, dt: float, policy_probes: int = 0, policy_seed: int = 0, pack_obs: bool = False):
+    def build_graph(self, dt: float, policy_probes: int = 0, policy_seed: int = 0, pack_obs: bool = False,
+                    post=None):
         """Capture pc_step_fused (tasking from self.actions -- or the stand-in policy when
         policy_probes > 0 -- masked by the previous estimated vis map, sensors, truth + UKF, both
         vis maps) [+ obs pack] into one CUDA graph.  Times and RNG counters come from the device
@@ -198,6 +221,8 @@ class CatalogEngine:
                 c.check(c.lib.pc_step_fused(c.handle, C.byref(a), C.byref(self.params), self._stream()))
                 if pack_obs:
                     self.pack_obs(use_clock=True)
+                if post is not None:
+                    post()          # e.g. the shard all-gather, captured into the same graph
         torch.cuda.current_stream(self.dev).wait_stream(side)
         g.pc_dt, g.pc_launches = float(dt), c.launch_count - before
         self._graph = g
@@ -271,8 +296,7 @@ class CatalogEngine:
         return self.obs_f32
 
     # -- reset snapshot (env.py:142,208: deepcopy of the agent list) ---------------
-    _STATE = ("sens_x", "sigma", "sig_flags", "est_p", "pred_p", "nis", "flags", "vis_truth", "vis_est",
-              "num_tasked", "last_time_tasked", "tr_pos", "tr_vel")
+    _STATE = ("sens_x", "sigma", "sig_flags", "est_p", "pred_p", "nis", "flags", "vis_truth", "summary")
 
     def snapshot(self):
         self._snapshot = ({k: getattr(self, k).clone() for k in self._STATE}, self.time, self.step_count,
@@ -292,11 +316,13 @@ class CatalogEngine:
         for k, v in self.__dict__.items():
             if isinstance(v, torch.Tensor):
                 setattr(new, k, v.clone())
-            elif k in ("_args", "_hs_io", "_graph", "_snapshot", "est_x", "truth_x"):
+            elif k in ("_args", "_hs_io", "_graph", "_snapshot", "est_x", "truth_x", "num_tasked", "vis_est",
+                       "tr_pos", "tr_vel", "last_time_tasked"):
                 continue
             else:
                 setattr(new, k, v)
         new.est_x, new.truth_x = new.sigma[0], new.sigma[13]      # views into the cloned sigma buffer
+        new._bind_summary_views()
         new._args, new._hs_io = _lib.StepArgs(), _lib.StepIO()
         new._graph, new._hs_dt = None, None
         bufs, t, sc, sv = self._snapshot

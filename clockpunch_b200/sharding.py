@@ -110,6 +110,37 @@ class StepGather:
         return {k: self.part.unpad(v) for k, v in self.recv.items()}
 
 
+class PackedGather:
+    """One all-gather per step for equal shards: every rank contributes its engine's `summary`
+    buffer (num_tasked | packed estimated vis map | tr_pos | tr_vel | last_time_tasked, one
+    contiguous uint8 tensor written in place by the step kernels) and receives (world, nbytes).
+    `fields(r)` gives typed views of rank r's block.  The collective can be captured into the
+    step's CUDA graph (NCCL supports stream capture), which removes its host launch cost."""
+
+    def __init__(self, world: int, rank: int, summary, n_local: int, wpr: int, group=None):
+        import torch
+        import torch.distributed as dist
+        self.torch, self.dist = torch, dist
+        self.world, self.rank, self.group = world, rank, group
+        self.send, self.n_local, self.wpr = summary, n_local, wpr
+        self.recv = torch.empty((world, summary.numel()), dtype=summary.dtype, device=summary.device)
+
+    @property
+    def bytes_per_step(self) -> int:
+        return self.recv.numel() * self.recv.element_size()
+
+    def gather(self):
+        if self.world == 1:
+            self.recv[0].copy_(self.send)
+        else:
+            self.dist.all_gather_into_tensor(self.recv.view(-1), self.send, group=self.group)
+        return self.recv
+
+    def fields(self, r: int) -> dict:
+        from .engine import CatalogEngine
+        return CatalogEngine.summary_views(self.recv[r], self.n_local, self.wpr)
+
+
 def shard_catalog(cat, part: TargetPartition, rank: int):
     """This rank's slice of a synthetic catalog (sensors replicated)."""
     lo, hi = part.bounds(rank)

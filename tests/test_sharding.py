@@ -65,6 +65,22 @@ def _worker(rank, world, port, n_total, m, out_dir):
             for k, v in glob.items():
                 np.testing.assert_array_equal(out[k].numpy(), v, err_msg=f"{k} rank {rank} it {it}")
         assert sg.bytes_per_step == world * part.cap * (4 * wpr + 4 + 4 + 4 + 8)
+        # the packed single-collective form used by bench.py (one summary buffer per shard)
+        from clockpunch_b200.engine import CatalogEngine
+        from clockpunch_b200.sharding import PackedGather
+        if n_total % world == 0:
+            n = n_total // world
+            buf = torch.zeros(n * (8 + 4 * wpr + 12), dtype=torch.uint8)
+            v = CatalogEngine.summary_views(buf, n, wpr)
+            for k in v:
+                v[k].copy_(torch.from_numpy(glob[k][lo:hi].copy()))
+            pg = PackedGather(world, rank, buf, n, wpr)
+            pg.gather()
+            for r in range(world):
+                a, b = part.bounds(r)
+                for k, t in pg.fields(r).items():
+                    np.testing.assert_array_equal(t.numpy(), glob[k][a:b], err_msg=f"packed {k} from rank {r}")
+            assert pg.bytes_per_step == world * n * (8 + 4 * wpr + 12)
         # max-over-ranks timing reduction used by bench.py
         t = torch.tensor([float(rank + 1)], dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
