@@ -55,6 +55,23 @@ def calcVisMap(sensor_states: ndarray, target_states: ndarray, body_radius: floa
     return out
 
 
+def calcVisMapAndDerivative(sensor_states: ndarray, target_states: ndarray, body_radius: float = None,
+                            binary=True) -> tuple[ndarray, ndarray]:
+    """(N, M) visibility map and (N, M) time derivative of the visibility function
+    (visibility.py:119-180).  binary=True turns the map (not the derivative) into 0/1.  Aligned
+    position vectors give +-Inf / NaN derivatives, as in the reference."""
+    body_radius, M, N, sens, targ = _prepVisMapInputs(sensor_states, target_states, body_radius)
+    sens = np.ascontiguousarray(sens, dtype=np.float64)
+    targ = np.ascontiguousarray(targ, dtype=np.float64)
+    vis, der = np.zeros((N, M)), np.zeros((N, M))
+    ctx = _lib.get_ctx()
+    ctx.check(ctx.lib.pc_vismap_der_host(ctx.handle, sens.ctypes.data, M, targ.ctypes.data, N,
+                                         float(body_radius), CONTINUOUS_TOL, vis.ctypes.data, der.ctypes.data))
+    if binary is True:
+        vis = np.where(vis > 0, 1, 0)
+    return vis, der
+
+
 def unpack_vis_words(words: ndarray, M: int) -> ndarray:
     """(N, ceil(M/32)) uint32 packed map -> (N, M) int64, host-side view helper."""
     words = np.ascontiguousarray(words, dtype=np.uint32)

@@ -17,6 +17,8 @@ cudaError_t launch_vismap_packed(const double*, int64_t, int64_t, const uint8_t*
                                  uint32_t*, uint32_t*, int64_t, cudaStream_t);
 cudaError_t launch_vismap_value(const double*, int64_t, int64_t, const double*, int64_t, int64_t,
                                 double, double, double*, cudaStream_t);
+cudaError_t launch_vismap_der(const double*, int64_t, int64_t, const double*, int64_t, int64_t, double,
+                              double, double*, double*, cudaStream_t);
 cudaError_t launch_pre_step(double* sens_x, const uint8_t* sens_kind, int64_t M, int64_t ld_s, double t0,
                             double tf, int substeps, int force_model, double* sens_q,
                             double body_radius, double vis_tol, pc_clock* clock, int64_t* actions,
@@ -359,6 +361,47 @@ int pc_vismap_host(pc_ctx* ctx, const double* h_sens, int64_t M, const double* h
     if (rc) return rc;
     PC_CUDA_TRY(ctx, cudaMemcpyAsync(out_f64, d_o, (size_t)N * M * 8, cudaMemcpyDeviceToHost, s));
   }
+  PC_CUDA_TRY(ctx, cudaStreamSynchronize(s));
+  return PC_OK;
+}
+
+int pc_vismap_der(pc_ctx* ctx, const double* sens, int64_t M, int64_t ld_s, const double* targ,
+                  int64_t N, int64_t ld_t, double body_radius, double tol, double* out_v,
+                  double* out_dv, pc_stream stream) {
+  PC_REQUIRE(ctx, ctx != nullptr, "null context");
+  PC_REQUIRE(ctx, M >= 0 && N >= 0 && ld_s >= M && ld_t >= N, "bad sizes");
+  if (M == 0 || N == 0) return PC_OK;
+  PC_REQUIRE(ctx, sens && targ && out_v && out_dv, "null pointer");
+  DeviceGuard g(ctx->device);
+  PC_CUDA_TRY(ctx, pc::launch_vismap_der(sens, M, ld_s, targ, N, ld_t, body_radius, tol, out_v, out_dv,
+                                         (cudaStream_t)stream));
+  ctx->launches += 1;
+  return PC_OK;
+}
+
+int pc_vismap_der_host(pc_ctx* ctx, const double* h_sens, int64_t M, const double* h_targ, int64_t N,
+                       double body_radius, double tol, double* out_v, double* out_dv) {
+  PC_REQUIRE(ctx, ctx != nullptr, "null context");
+  PC_REQUIRE(ctx, M >= 0 && N >= 0, "bad sizes");
+  if (M == 0 || N == 0) return PC_OK;
+  PC_REQUIRE(ctx, h_sens && h_targ && out_v && out_dv, "null pointer");
+  DeviceGuard g(ctx->device);
+  const size_t sb = align256(6 * (size_t)M * 8), tb = align256(6 * (size_t)N * 8);
+  const size_t ob = align256((size_t)N * M * 8);
+  int rc = ensure_ws(ctx, sb + tb + 2 * ob);
+  if (rc) return rc;
+  char* base = (char*)ctx->ws;
+  double* d_s = (double*)base;
+  double* d_t = (double*)(base + sb);
+  double* d_v = (double*)(base + sb + tb);
+  double* d_d = (double*)(base + sb + tb + ob);
+  cudaStream_t s = ctx->host_stream;
+  PC_CUDA_TRY(ctx, cudaMemcpyAsync(d_s, h_sens, 6 * (size_t)M * 8, cudaMemcpyHostToDevice, s));
+  PC_CUDA_TRY(ctx, cudaMemcpyAsync(d_t, h_targ, 6 * (size_t)N * 8, cudaMemcpyHostToDevice, s));
+  rc = pc_vismap_der(ctx, d_s, M, M, d_t, N, N, body_radius, tol, d_v, d_d, s);
+  if (rc) return rc;
+  PC_CUDA_TRY(ctx, cudaMemcpyAsync(out_v, d_v, (size_t)N * M * 8, cudaMemcpyDeviceToHost, s));
+  PC_CUDA_TRY(ctx, cudaMemcpyAsync(out_dv, d_d, (size_t)N * M * 8, cudaMemcpyDeviceToHost, s));
   PC_CUDA_TRY(ctx, cudaStreamSynchronize(s));
   return PC_OK;
 }

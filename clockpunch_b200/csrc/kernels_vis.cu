@@ -107,6 +107,57 @@ vismap_value_kernel(const double* __restrict__ sens, int64_t M, int64_t ld_s,
   out[idx] = acos(RE / m1) + acos(RE / m2) - acos(c);
 }
 
+// Visibility value AND its time derivative (calcVisMapAndDerivative, visibility.py:119-180 ->
+// satvis.calcVisAndDerVis, restated in oracle/visibility.py; parity unpinned):
+//   dV/dt = da1/dt + da2/dt - dphi/dt,
+//   da/dt = RE |r|' / (|r|^2 sqrt(1 - (RE/|r|)^2)),
+//   dphi/dt = -[(r1'.r2 + r1.r2') / (|r1||r2|) - cos(phi) (|r1|'/|r1| + |r2|'/|r2|)] / sin(phi).
+// The radial rate |r|' is r.v/|r|; the reference reaches the same number through the orbit-element
+// chain of orbits.py:39-69 (max difference 5e-14 km/s over tests/golden/orbits.npz).
+// Aligned position vectors give +-Inf / NaN exactly as the reference documents (visibility.py:141-143).
+__global__ void __launch_bounds__(kVisThreads)
+vismap_der_kernel(const double* __restrict__ sens, int64_t M, int64_t ld_s,
+                  const double* __restrict__ targ, int64_t N, int64_t ld_t, double RE, double tol,
+                  double* __restrict__ out_v, double* __restrict__ out_dv) {
+  const int64_t idx = (int64_t)blockIdx.x * kVisThreads + threadIdx.x;
+  if (idx >= N * M) return;
+  const int64_t i = idx / M, j = idx - i * M;
+  double s[6], t[6];
+#pragma unroll
+  for (int c = 0; c < 6; ++c) {
+    s[c] = sens[(int64_t)c * ld_s + j];
+    t[c] = targ[(int64_t)c * ld_t + i];
+  }
+  const double n1 = sqrt(fma(s[2], s[2], fma(s[1], s[1], s[0] * s[0])));
+  const double n2 = sqrt(fma(t[2], t[2], fma(t[1], t[1], t[0] * t[0])));
+  double m1 = n1, m2 = n2;  // magnitudes as the visibility function sees them (surface clamp)
+  if (m1 < RE && RE - m1 <= tol) m1 = RE;
+  if (m2 < RE && RE - m2 <= tol) m2 = RE;
+  const double dot12 = fma(s[2], t[2], fma(s[1], t[1], s[0] * t[0]));
+  double c = dot12 / (m1 * m2);
+  c = fmin(1.0, fmax(-1.0, c));
+  out_v[idx] = acos(RE / m1) + acos(RE / m2) - acos(c);
+  const double rd1 = fma(s[2], s[5], fma(s[1], s[4], s[0] * s[3])) / n1;
+  const double rd2 = fma(t[2], t[5], fma(t[1], t[4], t[0] * t[3])) / n2;
+  const double q1 = RE / n1, q2 = RE / n2;
+  const double a1dot = RE * rd1 / (n1 * n1 * sqrt(1.0 - q1 * q1));
+  const double a2dot = RE * rd2 / (n2 * n2 * sqrt(1.0 - q2 * q2));
+  const double cu = dot12 / (n1 * n2);
+  const double cross = fma(s[5], t[2], fma(s[4], t[1], s[3] * t[0])) + fma(s[2], t[5], fma(s[1], t[4], s[0] * t[3]));
+  const double cdot = cross / (n1 * n2) - cu * (rd1 / n1 + rd2 / n2);
+  const double phidot = -cdot / sqrt(1.0 - cu * cu);
+  out_dv[idx] = a1dot + a2dot - phidot;
+}
+
+cudaError_t launch_vismap_der(const double* sens, int64_t M, int64_t ld_s, const double* targ,
+                              int64_t N, int64_t ld_t, double RE, double tol, double* out_v,
+                              double* out_dv, cudaStream_t stream) {
+  if (N <= 0 || M <= 0) return cudaSuccess;
+  const unsigned blocks = (unsigned)((N * M + kVisThreads - 1) / kVisThreads);
+  vismap_der_kernel<<<blocks, kVisThreads, 0, stream>>>(sens, M, ld_s, targ, N, ld_t, RE, tol, out_v, out_dv);
+  return cudaGetLastError();
+}
+
 // Expand packed words to the reference's (N, M) int64 map (visibility.py:112-114).
 __global__ void __launch_bounds__(256)
 unpack_bits_kernel(const uint32_t* __restrict__ words, int64_t N, int64_t M, int64_t wpr,

@@ -137,6 +137,15 @@ int pc_vismap_value(pc_ctx* ctx, const double* sens, int64_t M, int64_t ld_s, co
 int pc_vismap_host(pc_ctx* ctx, const double* h_sens, int64_t M, const double* h_targ, int64_t N,
                    double body_radius, double tol, int binary, int64_t* out_i64, double* out_f64);
 
+/* pc_vismap_der replaces calcVisMapAndDerivative (common/visibility.py:119-180): continuous
+ * visibility value and its time derivative for every pair, (N, M) float64 each (states need their
+ * velocity rows; the radial rates of orbits.py:39-69 are formed in the kernel). */
+int pc_vismap_der(pc_ctx* ctx, const double* sens, int64_t M, int64_t ld_s, const double* targ,
+                  int64_t N, int64_t ld_t, double body_radius, double tol, double* out_v,
+                  double* out_dv, pc_stream stream);
+int pc_vismap_der_host(pc_ctx* ctx, const double* h_sens, int64_t M, const double* h_targ, int64_t N,
+                       double body_radius, double tol, double* out_v, double* out_dv);
+
 /* ---- K4: UKF predict + update -------------------------------------------
  * Replaces UnscentedKalmanFilter.predictAndUpdate for the 6-D identity-measurement
  * filter built by ezUKF (ukf_v2.py:185-375, ez_ukf.py:17-95), one filter per target.

@@ -12,93 +12,14 @@ The environment, agents, filters, propagator and metrics tracker are the referen
 Measurement noise comes from numpy's legacy global RNG (agents.py:181); it is seeded and every
 drawn z is recorded so that the CUDA env can be fed the same measurements.
 """
-import importlib.abc
-import importlib.machinery
 import os
 import sys
-import types
 
 import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-ROOT = os.path.dirname(os.path.dirname(HERE))
-sys.path.insert(0, ROOT)
-np.Inf = np.inf
-
-STUB_ROOTS = ("gymnasium", "ray", "satvis", "intervaltree", "matplotlib", "tensorflow", "pygame", "sklearn",
-              "pandas", "torch", "tabulate", "tqdm", "scipy.stats")
-
-
-class _Anything:
-    """Permissive class: any attribute, call or subscript works."""
-    def __init__(self, *a, **k):
-        pass
-
-    def __call__(self, *a, **k):
-        return _Anything()
-
-    def __getattr__(self, name):
-        if name.startswith("__"):
-            raise AttributeError(name)
-        return _Anything()
-
-    def __class_getitem__(cls, item):
-        return cls
-
-    def __mro_entries__(self, bases):
-        return (_Anything,)
-
-
-class _StubModule(types.ModuleType):
-    def __getattr__(self, name):
-        if name.startswith("__"):
-            raise AttributeError(name)
-        cls = type(name, (_Anything,), {})
-        setattr(self, name, cls)
-        return cls
-
-
-class _Finder(importlib.abc.MetaPathFinder, importlib.abc.Loader):
-    def find_spec(self, fullname, path, target=None):
-        if fullname.split(".")[0] in ("gymnasium", "ray", "satvis", "intervaltree", "matplotlib", "tensorflow",
-                                      "pygame"):
-            return importlib.machinery.ModuleSpec(fullname, self, is_package=True)
-        return None
-
-    def create_module(self, spec):
-        m = _StubModule(spec.name)
-        m.__path__ = []
-        return m
-
-    def exec_module(self, module):
-        pass
-
-
-sys.meta_path.insert(0, _Finder())
-pkg = types.ModuleType("punchclock")
-pkg.__path__ = ["/root/reference/punchclock"]
-sys.modules["punchclock"] = pkg
-
-# gymnasium pieces the env actually uses
-import gymnasium  # noqa: E402
-
-
-class _Env:
-    def reset(self, seed=None, options=None):
-        return None
-
-
-gymnasium.Env = _Env
-# satvis arithmetic -> oracle restatement
-import satvis.visibility_func as svf  # noqa: E402
-from oracle.visibility import is_vis, visibility_func  # noqa: E402
-
-svf.isVis = lambda r1, r2, RE, hg=0: is_vis(r1, r2, RE, hg)
-svf.visibilityFunc = lambda r1, r2, RE, hg=0, tol=1e-13: visibility_func(r1, r2, RE, hg, tol)
-# policy builders drag RLlib + torch nets in (sim_utils.py:13-15): stub those two modules
-for name in ("punchclock.ray.build_ray_policy", "punchclock.policies.policy_builder",
-             "punchclock.policies.policy_base_class_v2"):
-    sys.modules[name] = _StubModule(name)
+sys.path.insert(0, HERE)
+import _ref_stubs  # noqa: E402,F401  (registers the stand-ins and the bare `punchclock` package)
 
 from punchclock.common import agents as ref_agents  # noqa: E402
 from punchclock.common.transforms import ecef2eci  # noqa: E402

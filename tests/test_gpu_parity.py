@@ -433,3 +433,30 @@ def test_step_host_matches_graph_replay():
     stale = obs[6 * A + 36 * cat.N:]
     np.testing.assert_array_equal(stale, (eng.time - eng.host("last_time_tasked").astype(np.float64)).astype(np.float32))
     assert eng.host("num_tasked").sum() > 0
+
+
+def test_vismap_derivative_matches_oracle(golden):
+    """calcVisMapAndDerivative (visibility.py:119-180) through pc_vismap_der_host against the oracle
+    restatement (radial rate pinned to the live reference; satvis derivative formula unpinned)."""
+    from clockpunch_b200.common.visibility import calcVisMapAndDerivative
+    from oracle.visibility import calc_vis_map_and_derivative
+    g = golden("orbits")
+    X = g["x"]
+    sens, targ = np.concatenate([X[:, 48:], X[:, :5]], axis=1), X[:, 5:48]     # ground + space sensors
+    vis, der = calcVisMapAndDerivative(sens, targ)
+    vis_o, der_o = calc_vis_map_and_derivative(sens, targ)
+    assert vis.shape == der.shape == (43, 13)
+    np.testing.assert_array_equal(vis, vis_o)
+    # d/dt of the angle sum: scale is the orbital angular rate (~1e-3 rad/s); ground sites sit
+    # 1e-6 km above the surface, where da/dt divides a 1e-16 radial rate by sqrt(3e-10)
+    np.testing.assert_allclose(der, der_o, rtol=1e-9, atol=1e-11)
+    cont, _ = calcVisMapAndDerivative(sens, targ, binary=False)
+    vo, _ = calc_vis_map_and_derivative(sens, targ, binary=False)
+    np.testing.assert_allclose(cont, vo, rtol=0, atol=1e-12)
+    # aligned position vectors: infinite (or NaN) derivative, as the reference documents
+    a = np.array([[7000.0, 0, 0, 0, 7.5, 0]]).T
+    b = np.array([[14000.0, 0, 0, 0.1, 5.0, 0]]).T
+    _, d = calcVisMapAndDerivative(a, b)
+    assert not np.isfinite(d[0, 0])
+    with pytest.raises(ValueError):
+        calcVisMapAndDerivative(np.zeros((5, 2)), targ)

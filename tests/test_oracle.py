@@ -114,3 +114,27 @@ def test_visibility_analytic_cases():
     assert np.isnan(ov.visibility_func(below, r1, RE)[0])
     with pytest.raises(ValueError):
         ov.calc_vis_map(np.zeros((5, 2)), np.zeros((6, 2)))
+
+
+def test_radial_rate_and_vis_derivative(golden):
+    """Oracle restatements behind calcVisMapAndDerivative: radial rate pinned against the live
+    reference (orbits.py:39-69), derivative checked against a central difference of the visibility
+    function along two-body motion (the satvis formula itself is unpinned)."""
+    from oracle.dynamics import propagate_satellite
+    from oracle.visibility import calc_vis_and_der_vis, calc_vis_map_and_derivative, radial_rate, visibility_func
+    g = golden("orbits")
+    X = g["x"]
+    got = np.array([radial_rate(X[:3, i], X[3:, i]) for i in range(X.shape[1])])
+    np.testing.assert_allclose(got, g["rdot"], rtol=0, atol=1e-15)
+    np.testing.assert_allclose(got, (X[:3] * X[3:]).sum(0) / np.linalg.norm(X[:3], axis=0), rtol=0, atol=1e-13)
+    RE, h = 6378.1363, 0.5
+    for a, b in ((3, 17), (5, 40), (11, 29)):
+        xa, xb = X[:, a], X[:, b]
+        v0, d0 = calc_vis_and_der_vis(xa[:3], xa[3:], radial_rate(xa[:3], xa[3:]), xb[:3], xb[3:],
+                                      radial_rate(xb[:3], xb[3:]), RE)
+        vp = visibility_func(propagate_satellite(xa, 0, h)[:3], propagate_satellite(xb, 0, h)[:3], RE)[0]
+        vm = visibility_func(propagate_satellite(xa, 0, -h)[:3], propagate_satellite(xb, 0, -h)[:3], RE)[0]
+        assert d0 == pytest.approx((vp - vm) / (2 * h), rel=1e-6, abs=1e-12)
+        assert v0 == visibility_func(xa[:3], xb[:3], RE, 0.0, 1e-6)[0]
+    vm, dm = calc_vis_map_and_derivative(X[:, 48:52], X[:, :6])
+    assert vm.shape == dm.shape == (6, 4) and set(np.unique(vm)) <= {0, 1}
