@@ -26,6 +26,7 @@ _MIRRORED = [
     "estimation", "estimation.filter_base_class", "estimation.ukf_v2", "estimation.ez_ukf",
     "simulation", "simulation.sim_utils",
     "environment", "environment.env", "environment.env_utils",
+    "schedule_tree", "schedule_tree.access_windows",
 ]
 
 

@@ -75,6 +75,9 @@ _SIGNATURES = {
     "pc_vismap_host": ([_vp, _vp, _i64, _vp, _i64, _dbl, _dbl, _int, _vp, _vp], _int),
     "pc_vismap_der": ([_vp, _vp, _i64, _i64, _vp, _i64, _i64, _dbl, _dbl, _vp, _vp, _vp], _int),
     "pc_vismap_der_host": ([_vp, _vp, _i64, _vp, _i64, _dbl, _dbl, _vp, _vp], _int),
+    "pc_vis_history": ([_vp, _vp, _vp, _i64, _i64, _vp, _vp, _i64, _i64, _dbl, _vp, _i64, _int, _int, _dbl, _dbl,
+                        _vp, _vp], _int),
+    "pc_vis_history_host": ([_vp, _vp, _vp, _i64, _vp, _vp, _i64, _dbl, _vp, _i64, _int, _int, _dbl, _dbl, _vp], _int),
     "pc_ukf_predict_update": ([_vp, _vp, _vp, _vp, _vp, _vp, _i64, _i64, _dbl, _dbl, _int, _int,
                                C.POINTER(UkfParams), _u64, _u64, _vp, _vp, _vp, _vp, _vp, _vp], _int),
     "pc_sigma_points": ([_vp, _vp, _vp, _i64, _i64, _dbl, _vp, _vp, _vp], _int),

@@ -406,6 +406,69 @@ int pc_vismap_der_host(pc_ctx* ctx, const double* h_sens, int64_t M, const doubl
   return PC_OK;
 }
 
+/* ---- visibility history over a time axis (access windows) --------------------------------- */
+int pc_vis_history(pc_ctx* ctx, double* sens, const uint8_t* sens_kind, int64_t M, int64_t ld_s,
+                   double* targ, const uint8_t* targ_kind, int64_t N, int64_t ld_t, double t_now,
+                   const double* h_times, int64_t T, int substeps, int force_model,
+                   double body_radius, double tol, uint32_t* out_words, pc_stream stream) {
+  PC_REQUIRE(ctx, ctx != nullptr, "null context");
+  PC_REQUIRE(ctx, M >= 0 && N >= 0 && ld_s >= M && ld_t >= N && T >= 0, "bad sizes");
+  if (T == 0 || M == 0 || N == 0) return PC_OK;
+  PC_REQUIRE(ctx, sens && targ && h_times && out_words, "null pointer");
+  DeviceGuard g(ctx->device);
+  cudaStream_t s = (cudaStream_t)stream;
+  const int64_t wpr = (M + 31) / 32;
+  double t_cur = t_now;
+  for (int64_t i = 0; i < T; ++i) {
+    if (h_times[i] != t_cur) {
+      PC_CUDA_TRY(ctx, pc::launch_propagate_agents(sens, sens, sens_kind, PC_KIND_SATELLITE, M, ld_s, t_cur,
+                                                   h_times[i], substeps, force_model, s));
+      PC_CUDA_TRY(ctx, pc::launch_propagate_agents(targ, targ, targ_kind, PC_KIND_SATELLITE, N, ld_t, t_cur,
+                                                   h_times[i], substeps, force_model, s));
+      ctx->launches += 2;
+      t_cur = h_times[i];
+    }
+    PC_CUDA_TRY(ctx, pc::launch_vismap_packed(sens, M, ld_s, nullptr, 0.0, targ, nullptr, N, ld_t, body_radius,
+                                              tol, out_words + i * N * wpr, nullptr, wpr, s));
+    ctx->launches += 1;
+  }
+  return PC_OK;
+}
+
+int pc_vis_history_host(pc_ctx* ctx, const double* h_sens, const uint8_t* h_sens_kind, int64_t M,
+                        const double* h_targ, const uint8_t* h_targ_kind, int64_t N, double t_now,
+                        const double* h_times, int64_t T, int substeps, int force_model,
+                        double body_radius, double tol, uint32_t* h_out_words) {
+  PC_REQUIRE(ctx, ctx != nullptr, "null context");
+  PC_REQUIRE(ctx, M >= 0 && N >= 0 && T >= 0, "bad sizes");
+  if (T == 0 || M == 0 || N == 0) return PC_OK;
+  PC_REQUIRE(ctx, h_sens && h_targ && h_times && h_out_words, "null pointer");
+  DeviceGuard g(ctx->device);
+  const int64_t wpr = (M + 31) / 32;
+  const size_t sb = align256(6 * (size_t)M * 8), tb = align256(6 * (size_t)N * 8);
+  const size_t skb = align256((size_t)M), tkb = align256((size_t)N);
+  const size_t ob = align256((size_t)T * N * wpr * 4);
+  int rc = ensure_ws(ctx, sb + tb + skb + tkb + ob);
+  if (rc) return rc;
+  char* b = (char*)ctx->ws;
+  double* d_s = (double*)b;            b += sb;
+  double* d_t = (double*)b;            b += tb;
+  uint8_t* d_sk = (uint8_t*)b;         b += skb;
+  uint8_t* d_tk = (uint8_t*)b;         b += tkb;
+  uint32_t* d_o = (uint32_t*)b;
+  cudaStream_t s = ctx->host_stream;
+  PC_CUDA_TRY(ctx, cudaMemcpyAsync(d_s, h_sens, 6 * (size_t)M * 8, cudaMemcpyHostToDevice, s));
+  PC_CUDA_TRY(ctx, cudaMemcpyAsync(d_t, h_targ, 6 * (size_t)N * 8, cudaMemcpyHostToDevice, s));
+  if (h_sens_kind) PC_CUDA_TRY(ctx, cudaMemcpyAsync(d_sk, h_sens_kind, (size_t)M, cudaMemcpyHostToDevice, s));
+  if (h_targ_kind) PC_CUDA_TRY(ctx, cudaMemcpyAsync(d_tk, h_targ_kind, (size_t)N, cudaMemcpyHostToDevice, s));
+  rc = pc_vis_history(ctx, d_s, h_sens_kind ? d_sk : nullptr, M, M, d_t, h_targ_kind ? d_tk : nullptr, N, N,
+                      t_now, h_times, T, substeps, force_model, body_radius, tol, d_o, s);
+  if (rc) return rc;
+  PC_CUDA_TRY(ctx, cudaMemcpyAsync(h_out_words, d_o, (size_t)T * N * wpr * 4, cudaMemcpyDeviceToHost, s));
+  PC_CUDA_TRY(ctx, cudaStreamSynchronize(s));
+  return PC_OK;
+}
+
 /* ---- K4 ---------------------------------------------------------------- */
 static int ukf_check(pc_ctx* ctx, const double* est_x, const double* est_p, const double* truth_x,
                      const double* z, const uint8_t* tasked, int64_t n, int64_t ld, double t0,

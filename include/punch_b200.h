@@ -146,6 +146,21 @@ int pc_vismap_der(pc_ctx* ctx, const double* sens, int64_t M, int64_t ld_s, cons
 int pc_vismap_der_host(pc_ctx* ctx, const double* h_sens, int64_t M, const double* h_targ, int64_t N,
                        double body_radius, double tol, double* out_v, double* out_dv);
 
+/* pc_vis_history replaces AccessWindowCalculator.calcVisHist (schedule_tree/access_windows.py:148-195,
+ * 382-402): the packed visibility map at each of T epochs.  Agents (kind per agent, NULL = all
+ * satellites) are advanced IN PLACE from t_now through h_times[0..T-1] (a HOST array; an epoch equal
+ * to the current time is evaluated without propagating) -- the reference's own chained
+ * Agent.propagate calls -- and out_words receives (T, N, ceil(M/32)) uint32.  T x (N + M) solve_ivp
+ * calls and T N M Python pair tests in the reference; 3 T launches here. */
+int pc_vis_history(pc_ctx* ctx, double* sens, const uint8_t* sens_kind, int64_t M, int64_t ld_s,
+                   double* targ, const uint8_t* targ_kind, int64_t N, int64_t ld_t, double t_now,
+                   const double* h_times, int64_t T, int substeps, int force_model,
+                   double body_radius, double tol, uint32_t* out_words, pc_stream stream);
+int pc_vis_history_host(pc_ctx* ctx, const double* h_sens, const uint8_t* h_sens_kind, int64_t M,
+                        const double* h_targ, const uint8_t* h_targ_kind, int64_t N, double t_now,
+                        const double* h_times, int64_t T, int substeps, int force_model,
+                        double body_radius, double tol, uint32_t* h_out_words);
+
 /* ---- K4: UKF predict + update -------------------------------------------
  * Replaces UnscentedKalmanFilter.predictAndUpdate for the 6-D identity-measurement
  * filter built by ezUKF (ukf_v2.py:185-375, ez_ukf.py:17-95), one filter per target.
