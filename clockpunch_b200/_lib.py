@@ -45,7 +45,7 @@ class StepArgs(C.Structure):
         ("tr_vel", C.c_void_p), ("clock", C.c_void_p),
         ("actions", C.c_void_p), ("policy_probes", C.c_int), ("sigma_valid", C.c_int),
         ("policy_seed", C.c_uint64), ("sigma_ws", C.c_void_p), ("sig_flags", C.c_void_p),
-        ("sens_q", C.c_void_p),
+        ("sens_q", C.c_void_p), ("env_targets", C.c_int64), ("env_sensors", C.c_int64),
     ]
 
 
@@ -73,6 +73,8 @@ _SIGNATURES = {
                           _i64, _vp], _int),
     "pc_vismap_value": ([_vp, _vp, _i64, _i64, _vp, _i64, _i64, _dbl, _dbl, _vp, _vp], _int),
     "pc_vismap_host": ([_vp, _vp, _i64, _vp, _i64, _dbl, _dbl, _int, _vp, _vp], _int),
+    "pc_vismap_packed_envs": ([_vp, _vp, _i64, _vp, _vp, _i64, _i64, _i64, _i64, _dbl, _dbl, _vp, _vp, _vp], _int),
+    "pc_obs_pack_envs": ([_vp, _vp, _i64, _vp, _vp, _i64, _vp, _dbl, _vp, _i64, _i64, _i64, _vp, _vp, _vp, _vp], _int),
     "pc_vismap_der": ([_vp, _vp, _i64, _i64, _vp, _i64, _i64, _dbl, _dbl, _vp, _vp, _vp], _int),
     "pc_vismap_der_host": ([_vp, _vp, _i64, _vp, _i64, _dbl, _dbl, _vp, _vp], _int),
     "pc_vis_history": ([_vp, _vp, _vp, _i64, _i64, _vp, _vp, _i64, _i64, _dbl, _vp, _i64, _int, _int, _dbl, _dbl,

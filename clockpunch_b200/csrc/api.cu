@@ -17,13 +17,19 @@ cudaError_t launch_vismap_packed(const double*, int64_t, int64_t, const uint8_t*
                                  uint32_t*, uint32_t*, int64_t, cudaStream_t);
 cudaError_t launch_vismap_value(const double*, int64_t, int64_t, const double*, int64_t, int64_t,
                                 double, double, double*, cudaStream_t);
+cudaError_t launch_vismap_envs(const double*, int64_t, const double*, const double*, int64_t, int64_t, int64_t,
+                               int64_t, double, double, uint32_t*, uint32_t*, cudaStream_t);
+cudaError_t launch_obs_pack_envs(const double*, int64_t, const double*, const double*, int64_t, int64_t,
+                                 const float*, double, const pc_clock*, int64_t, int64_t, int64_t, float*,
+                                 float*, float*, cudaStream_t);
 cudaError_t launch_vismap_der(const double*, int64_t, int64_t, const double*, int64_t, int64_t, double,
                               double, double*, double*, cudaStream_t);
 cudaError_t launch_pre_step(double* sens_x, const uint8_t* sens_kind, int64_t M, int64_t ld_s, double t0,
                             double tf, int substeps, int force_model, double* sens_q,
                             double body_radius, double vis_tol, pc_clock* clock, int64_t* actions,
                             const uint32_t* vis_est, uint8_t* tasked, int64_t N, int64_t wpr,
-                            int probes, uint64_t seed, uint64_t step, cudaStream_t s);
+                            int probes, uint64_t seed, uint64_t step, int64_t env_targets,
+                            int64_t env_sensors, cudaStream_t s);
 
 cudaError_t launch_frame_change(const double*, double*, int64_t, int64_t, double, double, cudaStream_t);
 cudaError_t launch_coe2eci(const double*, double*, int64_t, int64_t, double, cudaStream_t);
@@ -365,6 +371,42 @@ int pc_vismap_host(pc_ctx* ctx, const double* h_sens, int64_t M, const double* h
   return PC_OK;
 }
 
+int pc_vismap_packed_envs(pc_ctx* ctx, const double* sens, int64_t ld_s, const double* targ_a,
+                          const double* targ_b, int64_t ld_t, int64_t E, int64_t env_sensors,
+                          int64_t env_targets, double body_radius, double tol, uint32_t* out_a,
+                          uint32_t* out_b, pc_stream stream) {
+  PC_REQUIRE(ctx, ctx != nullptr, "null context");
+  PC_REQUIRE(ctx, E >= 0 && env_sensors >= 0 && env_targets >= 0, "bad sizes");
+  PC_REQUIRE(ctx, ld_s >= E * env_sensors && ld_t >= E * env_targets, "leading dimensions too small");
+  if (E == 0 || env_sensors == 0 || env_targets == 0) return PC_OK;
+  PC_REQUIRE(ctx, sens && targ_a && out_a, "null pointer");
+  PC_REQUIRE(ctx, (targ_b == nullptr) == (out_b == nullptr), "targ_b and out_b go together");
+  DeviceGuard g(ctx->device);
+  PC_CUDA_TRY(ctx, pc::launch_vismap_envs(sens, ld_s, targ_a, targ_b, E * env_targets, ld_t, env_targets,
+                                          env_sensors, body_radius, tol, out_a, out_b, (cudaStream_t)stream));
+  ctx->launches += 1;
+  return PC_OK;
+}
+
+int pc_obs_pack_envs(pc_ctx* ctx, const double* sens_x, int64_t ld_s, const double* est_x,
+                     const double* est_p, int64_t ld, const float* last_time_tasked, double t_now,
+                     const pc_clock* clock, int64_t E, int64_t env_sensors, int64_t env_targets,
+                     float* out_eci, float* out_cov, float* out_stale, pc_stream stream) {
+  PC_REQUIRE(ctx, ctx != nullptr, "null context");
+  PC_REQUIRE(ctx, E >= 0 && env_sensors >= 0 && env_targets >= 0, "bad sizes");
+  PC_REQUIRE(ctx, ld_s >= E * env_sensors && ld >= E * env_targets, "leading dimensions too small");
+  PC_REQUIRE(ctx, out_eci && out_cov && out_stale, "null output");
+  if (E == 0) return PC_OK;
+  PC_REQUIRE(ctx, (env_sensors == 0 || sens_x) && (env_targets == 0 || (est_x && est_p && last_time_tasked)),
+             "null input");
+  DeviceGuard g(ctx->device);
+  PC_CUDA_TRY(ctx, pc::launch_obs_pack_envs(sens_x, ld_s, est_x, est_p, E * env_targets, ld, last_time_tasked,
+                                            t_now, clock, E, env_sensors, env_targets, out_eci, out_cov,
+                                            out_stale, (cudaStream_t)stream));
+  ctx->launches += 1;
+  return PC_OK;
+}
+
 int pc_vismap_der(pc_ctx* ctx, const double* sens, int64_t M, int64_t ld_s, const double* targ,
                   int64_t N, int64_t ld_t, double body_radius, double tol, double* out_v,
                   double* out_dv, pc_stream stream) {
@@ -700,7 +742,13 @@ int pc_step_fused(pc_ctx* ctx, const pc_step_args* a, const pc_ukf_params* param
   PC_REQUIRE(ctx, a->M == 0 || (a->sens_x && a->sens_kind), "null sensor pointer");
   const bool want_vis = a->vis_truth || a->vis_est;
   PC_REQUIRE(ctx, !want_vis || (a->vis_truth && a->vis_est), "vis_truth and vis_est go together");
-  PC_REQUIRE(ctx, !want_vis || a->words_per_row == (a->M + 31) / 32, "words_per_row must be ceil(M/32)");
+  const int64_t Ne = a->env_targets > 0 ? a->env_targets : a->N;
+  const int64_t Me = a->env_sensors > 0 ? a->env_sensors : a->M;
+  PC_REQUIRE(ctx, (a->env_targets > 0) == (a->env_sensors > 0), "env_targets and env_sensors go together");
+  PC_REQUIRE(ctx, a->env_targets <= 0 || (a->N % Ne == 0 && a->M % Me == 0 && a->N / Ne == a->M / Me),
+             "a batch of environments needs N = E env_targets and M = E env_sensors");
+  PC_REQUIRE(ctx, !want_vis || a->words_per_row == (Me + 31) / 32,
+             "words_per_row must be ceil(M/32) (ceil(env_sensors/32) for a batch of environments)");
   PC_REQUIRE(ctx, !a->actions || (a->tasked && (a->vis_est || a->M == 0)),
              "actions need a tasked workspace and the estimated vis map");
   PC_REQUIRE(ctx, a->policy_probes >= 0 && a->policy_probes <= 4096, "bad policy_probes");
@@ -741,7 +789,7 @@ int pc_step_fused(pc_ctx* ctx, const pc_step_args* a, const pc_ukf_params* param
                                          a->force_model, fuse_vis ? sq : nullptr, a->body_radius, a->vis_tol,
                                          a->clock, a->actions, a->vis_est, const_cast<uint8_t*>(a->tasked),
                                          a->N, a->words_per_row, a->policy_probes, a->policy_seed,
-                                         a->rng_step, ps));
+                                         a->rng_step, Ne, Me, ps));
     ctx->launches += 1;
     if (fork) PC_CUDA_TRY(ctx, cudaEventRecord(ctx->ev_join, ps));
   }
@@ -794,6 +842,8 @@ int pc_step_fused(pc_ctx* ctx, const pc_step_args* a, const pc_ukf_params* param
       u.sens_q = reinterpret_cast<const double4*>(sq);
       u.M = a->M;
       u.wpr = a->words_per_row;
+      u.env_targets = Ne > 0 ? Ne : 1;
+      u.env_sensors = Me;
       u.vis_truth = a->vis_truth;
       u.vis_est = a->vis_est;
       u.body_radius = a->body_radius;
@@ -816,8 +866,13 @@ static int step_and_pack(pc_ctx* ctx, const pc_step_args* a, const pc_ukf_params
   if (rc) return rc;
   if (d_obs) {
     const int64_t n0 = 6 * (a->M + a->N), n1 = 36 * a->N;
-    rc = pc_obs_pack(ctx, a->sens_x, a->M, a->ld_s, a->est_x, a->est_p, a->N, a->ld,
-                     a->last_time_tasked, a->tf, a->clock, d_obs, d_obs + n0, d_obs + n0 + n1, s);
+    if (a->env_targets > 0)
+      rc = pc_obs_pack_envs(ctx, a->sens_x, a->ld_s, a->est_x, a->est_p, a->ld, a->last_time_tasked, a->tf,
+                            a->clock, a->N / a->env_targets, a->env_sensors, a->env_targets, d_obs, d_obs + n0,
+                            d_obs + n0 + n1, s);
+    else
+      rc = pc_obs_pack(ctx, a->sens_x, a->M, a->ld_s, a->est_x, a->est_p, a->N, a->ld,
+                       a->last_time_tasked, a->tf, a->clock, d_obs, d_obs + n0, d_obs + n0 + n1, s);
   }
   return rc;
 }

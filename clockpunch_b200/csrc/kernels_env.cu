@@ -43,6 +43,44 @@ obs_pack_kernel(const double* __restrict__ sens_x, int64_t M, int64_t ld_s,
   }
 }
 
+// The same observation for a batch of E environments, one block per environment:
+// eci_state (E, 6, Me + Ne) = per environment [its sensors' truth | its targets' estimates];
+// est_cov (E, Ne, 6, 6) and obs_staleness (E, Ne) coincide with the flat layouts.
+__global__ void __launch_bounds__(256)
+obs_pack_envs_kernel(const double* __restrict__ sens_x, int64_t ld_s, const double* __restrict__ est_x,
+                     const double* __restrict__ est_p, int64_t N, int64_t ld,
+                     const float* __restrict__ last_time_tasked, double t_now_arg,
+                     const pc_clock* __restrict__ clock, int64_t E, int64_t Me, int64_t Ne,
+                     float* __restrict__ out_eci, float* __restrict__ out_cov,
+                     float* __restrict__ out_stale) {
+  const double t_now = clock ? clock->t_now : t_now_arg;
+  const int64_t idx = (int64_t)blockIdx.x * 256 + threadIdx.x;
+  const int64_t Ae = Me + Ne;
+  const int64_t n_eci = 6 * E * Ae, n_cov = 36 * N;
+  if (idx < n_eci) {
+    const int64_t e = idx / (6 * Ae), rem = idx - e * 6 * Ae;
+    const int64_t c = rem / Ae, k = rem - c * Ae;
+    out_eci[idx] = (float)(k < Me ? sens_x[c * ld_s + e * Me + k] : est_x[c * ld + e * Ne + (k - Me)]);
+  } else if (idx < n_eci + n_cov) {
+    const int64_t k = idx - n_eci;
+    out_cov[k] = (float)est_p[k];
+  } else if (idx < n_eci + n_cov + N) {
+    const int64_t k = idx - n_eci - n_cov;
+    out_stale[k] = (float)(t_now - (double)last_time_tasked[k]);
+  }
+}
+
+cudaError_t launch_obs_pack_envs(const double* sens_x, int64_t ld_s, const double* est_x,
+                                 const double* est_p, int64_t N, int64_t ld, const float* last_time_tasked,
+                                 double t_now, const pc_clock* clock, int64_t E, int64_t Me, int64_t Ne,
+                                 float* out_eci, float* out_cov, float* out_stale, cudaStream_t s) {
+  const int64_t total = 6 * E * (Me + Ne) + 36 * N + N;
+  if (total <= 0) return cudaSuccess;
+  obs_pack_envs_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(
+      sens_x, ld_s, est_x, est_p, N, ld, last_time_tasked, t_now, clock, E, Me, Ne, out_eci, out_cov, out_stale);
+  return cudaGetLastError();
+}
+
 // Stand-in scheduler policy for benchmarks (SURVEY.md section 8d "Actions"): every sensor probes up to
 // `probes` uniformly random targets and takes the first one its column of the estimated map
 // shows visible, else inaction (action = N).  Counter-based hash, no state.
@@ -136,6 +174,7 @@ struct PreStepArgs {
   int probes;
   uint64_t seed, step_arg;
   int nb_sens;
+  int64_t env_targets, env_sensors;  // batch of environments (single catalog: N, M)
 };
 
 template <bool J2>
@@ -169,29 +208,33 @@ pre_step_kernel(const __grid_constant__ PreStepArgs a) {
       a.sens_q[j] = make_double4(r[0], r[1], r[2], horizon_q(r[0], r[1], r[2], a.body_radius, a.vis_tol));
     return;
   }
-  // tasking
+  // tasking: sensor j of environment e = j / env_sensors addresses that environment's targets
+  // with LOCAL indices 0 .. env_targets (env_targets = inaction), exactly the MultiDiscrete action
+  // space of one SSAScheduler (env.py:172-179)
   const int lane = threadIdx.x & 31;
   const int64_t j = (int64_t)((int)blockIdx.x - a.nb_sens) * 4 + (threadIdx.x >> 5);
   if (j >= a.M || a.actions == nullptr) return;
-  int64_t pick = a.N;
+  const int64_t Ne = a.env_targets, Me = a.env_sensors;
+  const int64_t e = j / Me, jl = j - e * Me, t0 = e * Ne;
+  int64_t pick = Ne;
   if (a.probes > 0) {
     const uint64_t step = a.clock ? a.clock->step : a.step_arg;
     const uint64_t base = splitmix64(a.seed ^ splitmix64(step * 0x100000001B3ull + (uint64_t)j));
-    for (int k0 = 0; k0 < a.probes && pick == a.N; k0 += 32) {
+    for (int k0 = 0; k0 < a.probes && pick == Ne; k0 += 32) {
       const int k = k0 + lane;
-      const int64_t i = (int64_t)(splitmix64(base + (uint64_t)k) % (uint64_t)a.N);
-      const bool hit = k < a.probes && ((a.vis_est[i * a.wpr + (j >> 5)] >> (j & 31)) & 1u);
+      const int64_t i = (int64_t)(splitmix64(base + (uint64_t)k) % (uint64_t)Ne);
+      const bool hit = k < a.probes && ((a.vis_est[(t0 + i) * a.wpr + (jl >> 5)] >> (jl & 31)) & 1u);
       const unsigned m = __ballot_sync(0xffffffffu, hit);
       if (m) pick = __shfl_sync(0xffffffffu, i, __ffs(m) - 1);
     }
     if (lane == 0) {
       a.actions[j] = pick;
-      if (pick < a.N) a.tasked[pick] = 1;  // visible by construction
+      if (pick < Ne) a.tasked[t0 + pick] = 1;  // visible by construction
     }
   } else if (lane == 0) {
     pick = a.actions[j];
-    if (pick >= 0 && pick < a.N && ((a.vis_est[pick * a.wpr + (j >> 5)] >> (j & 31)) & 1u))
-      a.tasked[pick] = 1;
+    if (pick >= 0 && pick < Ne && ((a.vis_est[(t0 + pick) * a.wpr + (jl >> 5)] >> (jl & 31)) & 1u))
+      a.tasked[t0 + pick] = 1;
   }
 }
 
@@ -199,9 +242,12 @@ cudaError_t launch_pre_step(double* sens_x, const uint8_t* sens_kind, int64_t M,
                             double tf, int substeps, int force_model, double* sens_q,
                             double body_radius, double vis_tol, pc_clock* clock, int64_t* actions,
                             const uint32_t* vis_est, uint8_t* tasked, int64_t N, int64_t wpr,
-                            int probes, uint64_t seed, uint64_t step, cudaStream_t s) {
+                            int probes, uint64_t seed, uint64_t step, int64_t env_targets,
+                            int64_t env_sensors, cudaStream_t s) {
   if (M <= 0 && clock == nullptr) return cudaSuccess;
   PreStepArgs a;
+  a.env_targets = env_targets > 0 ? env_targets : N;
+  a.env_sensors = env_sensors > 0 ? env_sensors : M;
   a.sens_x = sens_x;
   a.sens_kind = sens_kind;
   a.M = M;

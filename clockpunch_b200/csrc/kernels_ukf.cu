@@ -396,18 +396,24 @@ constexpr int kVisTile = 256;  // sensors staged per pass of the fused visibilit
 constexpr int kVisRow = 33;
 constexpr int kVisTileSlots = (kVisTile / 32) * kVisRow;
 
-// Asynchronous (cp.async, LDGSTS) copy of one sensor chunk into shared memory: issued at kernel
-// entry, waited for only when the visibility phase starts, so its latency hides behind the filter
-// algebra.  Slots past M get a NaN horizon term (never visible).
+// Asynchronous (cp.async, LDGSTS) copy of one chunk of sensor ROWS into shared memory: issued at
+// kernel entry, waited for only when the visibility phase starts, so its latency hides behind the
+// filter algebra.  A row is one 32-sensor word of one environment: global row r belongs to
+// environment r / wpr and holds its sensors (r % wpr) * 32 .. + 31 (single catalog: one
+// environment).  Slots past the environment's sensor count get a NaN horizon term (never visible).
 __device__ __forceinline__ void load_sensor_tile(double4* __restrict__ tile,
-                                                 const double4* __restrict__ sens_q, int64_t j0,
-                                                 int64_t M, int tpb) {
+                                                 const double4* __restrict__ sens_q, int64_t r0,
+                                                 int64_t row_end, int64_t Me, int64_t wpr, int tpb) {
   const double nan = __longlong_as_double(0x7ff8000000000000LL);
   for (int j = threadIdx.x; j < kVisTile; j += tpb) {
-    const int slot = (j >> 5) * kVisRow + (j & 31);
-    if (j0 + j < M) {
+    const int rr = j >> 5;
+    const int slot = rr * kVisRow + (j & 31);
+    const int64_t r = r0 + rr;
+    const int64_t e = r / wpr;
+    const int64_t sl = (r - e * wpr) * 32 + (j & 31);
+    if (r < row_end && sl < Me) {
       const unsigned dst = (unsigned)__cvta_generic_to_shared(tile + slot);
-      const double4* src = sens_q + j0 + j;
+      const double4* src = sens_q + e * Me + sl;
       asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
       asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(dst + 16), "l"((const char*)src + 16) : "memory");
     } else {
@@ -464,7 +470,12 @@ ukf_finish_kernel(const __grid_constant__ UkfArgs a) {
   const int64_t ld = a.ld, blk = 6 * a.ld;
   const double* __restrict__ sb = a.sb;
   const bool vis = a.vis_truth != nullptr;
-  if (vis) load_sensor_tile(tile, a.sens_q, 0, a.M, TPB);
+  // sensor rows this CTA's targets need (one environment unless the catalog is a batch of envs)
+  const int64_t cta_t0 = (int64_t)blockIdx.x * TPB;
+  const int64_t cta_t1 = cta_t0 + TPB - 1 < a.n - 1 ? cta_t0 + TPB - 1 : a.n - 1;
+  const int64_t row_first = vis ? (cta_t0 / a.env_targets) * a.wpr : 0;
+  const int64_t row_end = vis ? (cta_t1 / a.env_targets + 1) * a.wpr : 0;
+  if (vis) load_sensor_tile(tile, a.sens_q, row_first, row_end, a.env_sensors, a.wpr, TPB);
 
   // ---- unscented transform (predictStateEstimate / predictCovariance, ukf_v2.py:261-292) ------
   double X0[6], tr[3];
@@ -622,20 +633,23 @@ ukf_finish_kernel(const __grid_constant__ UkfArgs a) {
     const double tq = horizon_q(tr[0], tr[1], tr[2], a.body_radius, a.vis_tol);
     const double eq = horizon_q(xe[0], xe[1], xe[2], a.body_radius, a.vis_tol);
     const int64_t wpr = a.wpr;
-    for (int64_t j0 = 0; j0 < wpr * 32; j0 += kVisTile) {
-      if (j0) {
+    const int64_t my_row0 = (tc / a.env_targets) * wpr;
+    for (int64_t r0 = row_first; r0 < row_end; r0 += kVisTile / 32) {
+      if (r0 != row_first) {
         __syncthreads();
-        load_sensor_tile(tile, a.sens_q, j0, a.M, TPB);
+        load_sensor_tile(tile, a.sens_q, r0, row_end, a.env_sensors, wpr, TPB);
       }
       wait_sensor_tile();
-      const int64_t w0 = j0 >> 5;
-      const int nw = (int)(wpr - w0 < kVisTile / 32 ? wpr - w0 : kVisTile / 32);
-      for (int w = 0; w < nw; ++w) {
-        uint32_t wa, wb;
-        vis_word(tile + w * kVisRow, tr, tq, xe, eq, RE2, wa, wb);
-        if (live) {
-          a.vis_truth[t * wpr + w0 + w] = wa;
-          a.vis_est[t * wpr + w0 + w] = wb;
+      const int nrows = (int)(row_end - r0 < kVisTile / 32 ? row_end - r0 : kVisTile / 32);
+      for (int rr = 0; rr < nrows; ++rr) {
+        const int64_t w = r0 + rr - my_row0;
+        if (w >= 0 && w < wpr) {
+          uint32_t wa, wb;
+          vis_word(tile + rr * kVisRow, tr, tq, xe, eq, RE2, wa, wb);
+          if (live) {
+            a.vis_truth[t * wpr + w] = wa;
+            a.vis_est[t * wpr + w] = wb;
+          }
         }
       }
     }
@@ -692,7 +706,11 @@ ukf_finish_quad_kernel(const __grid_constant__ UkfArgs a) {
   const int64_t ld = a.ld, blk = 6 * a.ld;
   const double* __restrict__ sb = a.sb;
   const bool vis = a.vis_truth != nullptr;
-  if (vis) load_sensor_tile(tile, a.sens_q, 0, a.M, kQuadThreads);
+  const int64_t cta_t0 = (int64_t)blockIdx.x * (kQuadThreads / 4);
+  const int64_t cta_t1 = cta_t0 + kQuadThreads / 4 - 1 < a.n - 1 ? cta_t0 + kQuadThreads / 4 - 1 : a.n - 1;
+  const int64_t row_first = vis ? (cta_t0 / a.env_targets) * a.wpr : 0;
+  const int64_t row_end = vis ? (cta_t1 / a.env_targets + 1) * a.wpr : 0;
+  if (vis) load_sensor_tile(tile, a.sens_q, row_first, row_end, a.env_sensors, a.wpr, kQuadThreads);
 
   // ---- every global load of the untasked path is issued here, before any arithmetic -------------
   // (one round trip to HBM instead of four: at this occupancy latency is the whole cost)
@@ -873,21 +891,24 @@ ukf_finish_quad_kernel(const __grid_constant__ UkfArgs a) {
     const double tq = horizon_q(tr[0], tr[1], tr[2], a.body_radius, a.vis_tol);
     const double eq = horizon_q(xe[0], xe[1], xe[2], a.body_radius, a.vis_tol);
     const int64_t wpr = a.wpr;
-    for (int64_t j0 = 0; j0 < wpr * 32; j0 += kVisTile) {
-      if (j0) {
+    const int64_t my_row0 = (tc / a.env_targets) * wpr;
+    for (int64_t r0 = row_first; r0 < row_end; r0 += kVisTile / 32) {
+      if (r0 != row_first) {
         __syncthreads();
-        load_sensor_tile(tile, a.sens_q, j0, a.M, kQuadThreads);
+        load_sensor_tile(tile, a.sens_q, r0, row_end, a.env_sensors, wpr, kQuadThreads);
       }
       wait_sensor_tile();
       PC_PHASE_CLOCK(8);
-      const int64_t w0 = j0 >> 5;
-      const int nw = (int)(wpr - w0 < kVisTile / 32 ? wpr - w0 : kVisTile / 32);
-      for (int w = q; w < nw; w += 4) {
-        uint32_t wa, wb;
-        vis_word(tile + w * kVisRow, tr, tq, xe, eq, RE2, wa, wb);
-        if (live) {
-          a.vis_truth[t * wpr + w0 + w] = wa;
-          a.vis_est[t * wpr + w0 + w] = wb;
+      const int nrows = (int)(row_end - r0 < kVisTile / 32 ? row_end - r0 : kVisTile / 32);
+      for (int rr = 0; rr < nrows; ++rr) {
+        const int64_t w = r0 + rr - my_row0;
+        if (w >= 0 && w < wpr && (w & 3) == q) {       // lane q packs words q, q + 4, ...
+          uint32_t wa, wb;
+          vis_word(tile + rr * kVisRow, tr, tq, xe, eq, RE2, wa, wb);
+          if (live) {
+            a.vis_truth[t * wpr + w] = wa;
+            a.vis_est[t * wpr + w] = wb;
+          }
         }
       }
     }

@@ -158,6 +158,54 @@ cudaError_t launch_vismap_der(const double* sens, int64_t M, int64_t ld_s, const
   return cudaGetLastError();
 }
 
+// Block-diagonal map of a batch of E environments (reset path of the vectorised env): target i
+// belongs to environment i / Ne and is tested against that environment's Me sensors only.  One
+// thread per output word; sensors are read straight from global memory (L1-resident: Me is small).
+template <bool TWO>
+__global__ void __launch_bounds__(kVisThreads)
+vismap_envs_kernel(const double* __restrict__ sens, int64_t ld_s, const double* __restrict__ ta,
+                   const double* __restrict__ tb, int64_t N, int64_t ld_t, int64_t Ne, int64_t Me,
+                   double RE, double tol, uint32_t* __restrict__ out_a, uint32_t* __restrict__ out_b,
+                   int64_t wpr) {
+  const int64_t idx = (int64_t)blockIdx.x * kVisThreads + threadIdx.x;
+  if (idx >= N * wpr) return;
+  const int64_t i = idx / wpr, w = idx - i * wpr, e = i / Ne;
+  const double RE2 = RE * RE;
+  const double ax = ta[i], ay = ta[ld_t + i], az = ta[2 * ld_t + i];
+  const double aq = horizon_q(ax, ay, az, RE, tol);
+  double bx = 0, by = 0, bz = 0, bq = 0;
+  if (TWO) {
+    bx = tb[i];
+    by = tb[ld_t + i];
+    bz = tb[2 * ld_t + i];
+    bq = horizon_q(bx, by, bz, RE, tol);
+  }
+  uint32_t wa = 0, wb = 0;
+  const int lim = (int)min((int64_t)32, Me - w * 32);
+  for (int b = 0; b < lim; ++b) {
+    const int64_t j = e * Me + w * 32 + b;
+    const double x = sens[j], y = sens[ld_s + j], z = sens[2 * ld_s + j];
+    const double4 s = make_double4(x, y, z, horizon_q(x, y, z, RE, tol));
+    if (sees(s, ax, ay, az, aq, RE2)) wa |= 1u << b;
+    if (TWO && sees(s, bx, by, bz, bq, RE2)) wb |= 1u << b;
+  }
+  out_a[idx] = wa;
+  if (TWO) out_b[idx] = wb;
+}
+
+cudaError_t launch_vismap_envs(const double* sens, int64_t ld_s, const double* ta, const double* tb,
+                               int64_t N, int64_t ld_t, int64_t Ne, int64_t Me, double RE, double tol,
+                               uint32_t* out_a, uint32_t* out_b, cudaStream_t stream) {
+  const int64_t wpr = (Me + 31) / 32;
+  if (N <= 0 || Me <= 0) return cudaSuccess;
+  const unsigned blocks = (unsigned)((N * wpr + kVisThreads - 1) / kVisThreads);
+  if (tb)
+    vismap_envs_kernel<true><<<blocks, kVisThreads, 0, stream>>>(sens, ld_s, ta, tb, N, ld_t, Ne, Me, RE, tol, out_a, out_b, wpr);
+  else
+    vismap_envs_kernel<false><<<blocks, kVisThreads, 0, stream>>>(sens, ld_s, ta, nullptr, N, ld_t, Ne, Me, RE, tol, out_a, nullptr, wpr);
+  return cudaGetLastError();
+}
+
 // Expand packed words to the reference's (N, M) int64 map (visibility.py:112-114).
 __global__ void __launch_bounds__(256)
 unpack_bits_kernel(const uint32_t* __restrict__ words, int64_t N, int64_t M, int64_t wpr,

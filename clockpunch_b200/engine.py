@@ -33,7 +33,7 @@ class CatalogEngine:
                  device: int | None = None, substeps: int = 0, force_model: int = _lib.FORCE_TWOBODY,
                  seed: int = 0, alpha: float = 0.001, beta: float = 2.0, kappa=None,
                  body_radius: float = RE, vis_tol: float = BINARY_TOL,
-                 init_num_tasked=None, init_last_time_tasked=None):
+                 init_num_tasked=None, init_last_time_tasked=None, num_envs: int = 1):
         torch = B.torch_mod()
         self.ctx = _lib.get_ctx(device)
         self.dev = B.device_of(self.ctx)
@@ -42,7 +42,13 @@ class CatalogEngine:
         target_states = np.asarray(target_states, dtype=np.float64).reshape(6, -1)
         self.M, self.N = sensor_states.shape[1], target_states.shape[1]
         self.ld_s, self.ld = _pad(self.M), _pad(self.N)
-        self.wpr = max(1, (self.M + 31) // 32)
+        # a batch of `num_envs` independent environments stored environment-major: each target is
+        # tested against its own environment's sensors only (vectorised SSAScheduler envs)
+        self.E = int(num_envs)
+        if self.E < 1 or self.M % self.E or self.N % self.E:
+            raise ValueError("num_envs must divide both the sensor and the target count")
+        self.Me, self.Ne = self.M // self.E, self.N // self.E
+        self.wpr = max(1, (self.Me + 31) // 32)
         self.time = float(time)
         self.step_count = 0
         self.substeps, self.force_model, self.seed = int(substeps), int(force_model), int(seed)
@@ -147,6 +153,7 @@ class CatalogEngine:
         a.policy_probes, a.policy_seed = int(policy_probes), int(policy_seed)
         a.sigma_ws, a.sig_flags = self.sigma.data_ptr(), self.sig_flags.data_ptr()
         a.sens_q = self.sens_q.data_ptr()
+        a.env_targets, a.env_sensors = (self.Ne, self.Me) if self.E > 1 else (0, 0)
         a.sigma_valid = 1 if self._sigma_valid else 0
         return a
 
@@ -154,6 +161,12 @@ class CatalogEngine:
     def compute_vis(self):
         """Both packed maps from the current states (reset path, env.py:212)."""
         c = self.ctx
+        if self.E > 1:
+            c.check(c.lib.pc_vismap_packed_envs(c.handle, self.sens_x.data_ptr(), self.ld_s, self.truth_x.data_ptr(),
+                                                self.est_x.data_ptr(), self.ld, self.E, self.Me, self.Ne,
+                                                self.body_radius, self.vis_tol, self.vis_truth.data_ptr(),
+                                                self.vis_est.data_ptr(), self._stream()))
+            return
         c.check(c.lib.pc_vismap_packed(c.handle, self.sens_x.data_ptr(), self.M, self.ld_s, None, 0.0,
                                        self.truth_x.data_ptr(), self.est_x.data_ptr(), self.N, self.ld,
                                        self.body_radius, self.vis_tol, self.vis_truth.data_ptr(),
@@ -289,6 +302,13 @@ class CatalogEngine:
         c = self.ctx
         n0, n1, _ = self._obs_sizes
         base = self.obs_f32.data_ptr()
+        if self.E > 1:
+            c.check(c.lib.pc_obs_pack_envs(c.handle, self.sens_x.data_ptr(), self.ld_s, self.est_x.data_ptr(),
+                                           self.est_p.data_ptr(), self.ld, self.last_time_tasked.data_ptr(),
+                                           self.time, self.clock.data_ptr() if use_clock else None, self.E,
+                                           self.Me, self.Ne, base, base + 4 * n0, base + 4 * (n0 + n1),
+                                           self._stream()))
+            return self.obs_f32
         c.check(c.lib.pc_obs_pack(c.handle, self.sens_x.data_ptr(), self.M, self.ld_s, self.est_x.data_ptr(),
                                   self.est_p.data_ptr(), self.N, self.ld, self.last_time_tasked.data_ptr(),
                                   self.time, self.clock.data_ptr() if use_clock else None,
@@ -343,5 +363,5 @@ class CatalogEngine:
         if name in ("est_p", "pred_p"):
             return t.cpu().numpy().reshape(self.N, 6, 6)
         if name in ("vis_truth", "vis_est"):
-            return unpack_vis_words(t.cpu().numpy().view(np.uint32), self.M)
+            return unpack_vis_words(t.cpu().numpy().view(np.uint32), self.Me)      # (N, Me): own env's sensors
         return t.cpu().numpy()

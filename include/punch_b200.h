@@ -137,6 +137,20 @@ int pc_vismap_value(pc_ctx* ctx, const double* sens, int64_t M, int64_t ld_s, co
 int pc_vismap_host(pc_ctx* ctx, const double* h_sens, int64_t M, const double* h_targ, int64_t N,
                    double body_radius, double tol, int binary, int64_t* out_i64, double* out_f64);
 
+/* Batch-of-environments forms (vectorised SSAScheduler envs, BASELINE.json configs[2]): E
+ * environments stored environment-major, each with env_sensors sensors and env_targets targets.
+ * pc_vismap_packed_envs: the E block-diagonal maps, out words (E env_targets, ceil(env_sensors/32)).
+ * pc_obs_pack_envs: eci_state (E, 6, env_sensors + env_targets) | est_cov (E, env_targets, 6, 6) |
+ * obs_staleness (E, env_targets), i.e. E reference observations back to back. */
+int pc_vismap_packed_envs(pc_ctx* ctx, const double* sens, int64_t ld_s, const double* targ_a,
+                          const double* targ_b, int64_t ld_t, int64_t E, int64_t env_sensors,
+                          int64_t env_targets, double body_radius, double tol, uint32_t* out_a,
+                          uint32_t* out_b, pc_stream stream);
+int pc_obs_pack_envs(pc_ctx* ctx, const double* sens_x, int64_t ld_s, const double* est_x,
+                     const double* est_p, int64_t ld, const float* last_time_tasked, double t_now,
+                     const pc_clock* clock, int64_t E, int64_t env_sensors, int64_t env_targets,
+                     float* out_eci, float* out_cov, float* out_stale, pc_stream stream);
+
 /* pc_vismap_der replaces calcVisMapAndDerivative (common/visibility.py:119-180): continuous
  * visibility value and its time derivative for every pair, (N, M) float64 each (states need their
  * velocity rows; the radial rates of orbits.py:39-69 are formed in the kernel). */
@@ -278,6 +292,12 @@ typedef struct pc_step_args {
    * written by the sensor kernel and read by the visibility phase of the target kernel.  NULL: a
    * context-owned buffer is used (allocated on demand, so not usable under stream capture). */
   double* sens_q;
+  /* A batch of E independent environments in one catalog (vectorised SSAScheduler envs): targets
+   * and sensors are stored environment-major, N = E env_targets, M = E env_sensors; target i is
+   * tested only against the sensors of environment i / env_targets, words_per_row =
+   * ceil(env_sensors / 32), and actions[j] is LOCAL to the environment of sensor j (0 ..
+   * env_targets, env_targets = inaction).  Both 0: one environment (N targets, M sensors). */
+  int64_t env_targets, env_sensors;
 } pc_step_args;
 int pc_step_fused(pc_ctx* ctx, const pc_step_args* args, const pc_ukf_params* params,
                   pc_stream stream);
