@@ -356,11 +356,12 @@ def run_own(args):
         dist.all_reduce(e2e_ms, op=dist.ReduceOp.MAX)
     e2e_value = world * N * args.steps / (float(e2e_ms.item()) * 1e-3)
     e2e = {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(M * 8),
-           "d2h_bytes_per_step": int(hb["obs"].numel() * 4 + hb["vis_est"].numel() * 4 + hb["num_tasked"].numel() * 8),
+           "d2h_bytes_per_step": int(hb["block"].numel()),     # float32 obs | num_tasked | packed vis | traces, one copy
            "ms_per_step": float(e2e_ms.item()) / args.steps,
            "path": "host policy (numpy, previous obs) -> CatalogEngine.step_host -> pc_step_host: pinned host actions "
-                   "-> [CUDA graph: pc_step_fused + pc_obs_pack] -> pinned host float32 obs + packed vis map + "
-                   "num_tasked, stream sync; timed by the host clock around the loop"}
+                   "-> [CUDA graph: pc_step_fused + pc_obs_pack] -> ONE copy of the output block (float32 obs | num_tasked | "
+                   "packed vis map | covariance traces | last_time_tasked) to pinned host memory, stream sync; timed by the "
+                   "host clock around the loop"}
 
     def leave():
         # Ranks leave together and without tearing NCCL down: destroying a process group whose

@@ -52,7 +52,8 @@ class StepArgs(C.Structure):
 class StepIO(C.Structure):
     """pc_step_io."""
     _fields_ = [("h_actions", C.c_void_p), ("d_obs", C.c_void_p), ("h_obs", C.c_void_p),
-                ("h_vis_est", C.c_void_p), ("h_num_tasked", C.c_void_p)]
+                ("h_vis_est", C.c_void_p), ("h_num_tasked", C.c_void_p),
+                ("d_block", C.c_void_p), ("h_block", C.c_void_p), ("block_bytes", C.c_int64)]
 
 
 _vp, _i64, _dbl, _int, _u64 = C.c_void_p, C.c_int64, C.c_double, C.c_int, C.c_uint64

@@ -937,6 +937,11 @@ int pc_step_host(pc_ctx* ctx, const pc_step_args* a, const pc_ukf_params* params
     PC_CUDA_TRY(ctx, cudaGraphLaunch(ctx->hs_exec, s));
     ctx->launches += ctx->hs_launches;
   }
+  if (io->d_block && io->h_block && io->block_bytes > 0) {
+    PC_CUDA_TRY(ctx, cudaMemcpyAsync(io->h_block, io->d_block, (size_t)io->block_bytes, cudaMemcpyDeviceToHost, s));
+    PC_CUDA_TRY(ctx, cudaStreamSynchronize(s));
+    return PC_OK;
+  }
   if (io->h_obs)
     PC_CUDA_TRY(ctx, cudaMemcpyAsync(io->h_obs, io->d_obs,
                                      (size_t)(6 * (a->M + a->N) + 37 * a->N) * sizeof(float),

@@ -79,7 +79,15 @@ class CatalogEngine:
         # what every other shard's scheduler needs from this one each step lives in
         # ONE buffer, so that the per-step exchange is a single all-gather: num_tasked (int64) |
         # packed estimated vis map (int32 words) | tr_pos | tr_vel | last_time_tasked (float32)
-        self.summary = torch.zeros((self.N * (8 + 4 * self.wpr + 12),), dtype=torch.uint8, device=dev)
+        # ... and that buffer sits right behind the float32 observation in ONE output block, so that
+        # the per-step device-to-host transfer of step_host is a single copy
+        A = self.M + self.N
+        self._obs_sizes = (6 * A, 36 * self.N, self.N)
+        self._obs_bytes = (4 * sum(self._obs_sizes) + 255) // 256 * 256
+        self._sum_bytes = self.N * (8 + 4 * self.wpr + 12)
+        self.out_block = torch.zeros((self._obs_bytes + self._sum_bytes,), dtype=torch.uint8, device=dev)
+        self.obs_f32 = self.out_block[: 4 * sum(self._obs_sizes)].view(torch.float32)
+        self.summary = self.out_block[self._obs_bytes:]
         self._bind_summary_views()
         self.tasked = torch.zeros((self.N,), dtype=torch.uint8, device=dev)
         self.z = torch.zeros((6, self.ld), dtype=f64, device=dev)
@@ -88,10 +96,6 @@ class CatalogEngine:
         self.num_tasked.copy_(torch.from_numpy(nt.copy()))
         self.last_time_tasked.copy_(torch.from_numpy(lt.copy()))
         self.actions = torch.zeros((max(1, self.M),), dtype=torch.int64, device=dev)
-        # float32 observation block (one contiguous buffer -> one D2H copy)
-        A = self.M + self.N
-        self._obs_sizes = (6 * A, 36 * self.N, self.N)
-        self.obs_f32 = torch.zeros((sum(self._obs_sizes),), dtype=torch.float32, device=dev)
         self._args = _lib.StepArgs()
         self._snapshot = None
         # device-resident step clock (pc_clock: t_now, step, t_cur, step_cur) for graph replay
@@ -270,10 +274,12 @@ class CatalogEngine:
         (N, wpr) and num_tasked (N,) out."""
         torch = self.torch
         mk = (lambda *a, **k: torch.empty(*a, **k).pin_memory()) if pinned else torch.empty
-        return {"actions": mk((max(1, self.M),), dtype=torch.int64),
-                "obs": mk((sum(self._obs_sizes),), dtype=torch.float32),
-                "vis_est": mk((self.N, self.wpr), dtype=torch.int32),
-                "num_tasked": mk((self.N,), dtype=torch.int64)}
+        block = mk((self.out_block.numel(),), dtype=torch.uint8)        # mirror of self.out_block
+        v = self.summary_views(block[self._obs_bytes:], self.N, self.wpr)
+        return {"actions": mk((max(1, self.M),), dtype=torch.int64), "block": block,
+                "obs": block[: 4 * sum(self._obs_sizes)].view(torch.float32),
+                "vis_est": v["vis_est"], "num_tasked": v["num_tasked"], "tr_pos": v["tr_pos"],
+                "tr_vel": v["tr_vel"], "last_time_tasked": v["last_time_tasked"]}
 
     def step_host(self, hb: dict, dt: float, policy_probes: int = 0, policy_seed: int = 0):
         """One SSAScheduler.step for the whole catalog through pc_step_host: copies hb["actions"]
@@ -292,6 +298,8 @@ class CatalogEngine:
         io.h_actions = hb["actions"].data_ptr() if policy_probes == 0 else None
         io.d_obs, io.h_obs = self.obs_f32.data_ptr(), hb["obs"].data_ptr()
         io.h_vis_est, io.h_num_tasked = hb["vis_est"].data_ptr(), hb["num_tasked"].data_ptr()
+        if "block" in hb:      # obs | summary in one device block -> one D2H copy
+            io.d_block, io.h_block, io.block_bytes = self.out_block.data_ptr(), hb["block"].data_ptr(), self.out_block.numel()
         c = self.ctx
         c.check(c.lib.pc_step_host(c.handle, C.byref(a), C.byref(self.params), C.byref(io), self._stream()))
         self.time += float(dt)
@@ -336,12 +344,13 @@ class CatalogEngine:
         for k, v in self.__dict__.items():
             if isinstance(v, torch.Tensor):
                 setattr(new, k, v.clone())
-            elif k in ("_args", "_hs_io", "_graph", "_snapshot", "est_x", "truth_x", "num_tasked", "vis_est",
-                       "tr_pos", "tr_vel", "last_time_tasked"):
+            elif k in ("_args", "_hs_io", "_graph", "_snapshot", "est_x", "truth_x"):
                 continue
             else:
                 setattr(new, k, v)
         new.est_x, new.truth_x = new.sigma[0], new.sigma[13]      # views into the cloned sigma buffer
+        new.obs_f32 = new.out_block[: 4 * sum(new._obs_sizes)].view(torch.float32)
+        new.summary = new.out_block[new._obs_bytes:]
         new._bind_summary_views()
         new._args, new._hs_io = _lib.StepArgs(), _lib.StepIO()
         new._graph, new._hs_dt = None, None

@@ -274,7 +274,10 @@ class SSAScheduler(_EnvBase):
             if k == "_engine":
                 new._engine = v.clone()
             elif k == "_hb":
-                new._hb = {n: t.clone().pin_memory() for n, t in v.items()}
+                continue
             else:
                 setattr(new, k, deepcopy(v, memo))
+        new._hb = new._engine.host_buffers(pinned=True)          # views of one pinned block: rebuild, then fill
+        new._hb["block"].copy_(self._hb["block"])
+        new._hb["actions"].copy_(self._hb["actions"])
         return new

@@ -317,6 +317,13 @@ typedef struct pc_step_io {
   float* h_obs;              /* host destination of the same size, or NULL */
   uint32_t* h_vis_est;       /* host (N, words_per_row) or NULL */
   int64_t* h_num_tasked;     /* host (N) or NULL */
+  /* One-copy form: when the caller has laid its outputs out in ONE device block (e.g. d_obs, the
+   * packed vis map and the summaries as adjacent sub-buffers), d_block / h_block / block_bytes make
+   * the whole device-to-host transfer a single copy (each small copy costs ~12 us of fixed latency);
+   * h_obs / h_vis_est / h_num_tasked are then ignored. */
+  const void* d_block;
+  void* h_block;
+  int64_t block_bytes;
 } pc_step_io;
 int pc_step_host(pc_ctx* ctx, const pc_step_args* args, const pc_ukf_params* params,
                  const pc_step_io* io, pc_stream stream);
