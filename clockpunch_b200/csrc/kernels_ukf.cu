@@ -122,6 +122,8 @@ __device__ __forceinline__ void normal6(uint64_t seed, uint64_t step, uint64_t t
   }
 }
 
+__device__ bool repair_chol6(const double* __restrict__ Ein, double* __restrict__ Uout);  // below
+
 // Measurement update for one tasked target, everything addressed in shared memory.
 // forecast / calculateKalmanGain / updateCovariance / calculateInnovations /
 // updateStateEstimate (ukf_v2.py:211-228, 294-375).
@@ -129,7 +131,15 @@ __device__ __noinline__ void measurement_update(TargetSmem* __restrict__ S, cons
   uint32_t flags = 0;
   // STEP 1: re-sample around (pred_x, pred_p): U2 = chol_upper(pred_p)
   double* U2 = S->U;
-  if (!chol_upper6(S->P, U2)) flags |= PC_FLAG_NONPD_PRED;
+  if (!chol_upper6(S->P, U2)) {
+    flags |= PC_FLAG_NONPD_PRED;
+    double Ep[21];
+#pragma unroll
+    for (int i = 0; i < 6; ++i)
+#pragma unroll
+      for (int j = i; j < 6; ++j) Ep[uidx(i, j)] = S->P[i * 6 + j];
+    repair_chol6(Ep, U2);
+  }
 
   const double c3 = p.wc0 - p.wm0;
   const double cuu = 2.0 * p.wi * p.gamma * p.gamma;
@@ -247,7 +257,10 @@ __device__ __forceinline__ uint32_t measurement_update_reg(
     double (&xe)[6], double (&PE)[21], double& nis_out) {
   uint32_t flags = 0;
   double U2[21];
-  if (!chol_upper6_packed(E, U2)) flags |= PC_FLAG_NONPD_PRED;
+  if (!chol_upper6_packed(E, U2)) {
+    flags |= PC_FLAG_NONPD_PRED;
+    repair_chol6(E, U2);
+  }
   const double c3 = p.wc0 - p.wm0;
   const double cuu = 2.0 * p.wi * p.gamma * p.gamma;
   const double cdd = p.wc0 + 12.0 * p.wi;
@@ -319,6 +332,98 @@ __device__ __forceinline__ uint32_t measurement_update_reg(
   return flags;
 }
 
+// Nearest-positive-definite repair of a symmetric 6x6 whose Cholesky factorisation failed
+// (findNearestPositiveDefiniteMatrix / nearestPD, estimation/ukf_utils.py:155-198,242-256, called
+// from generateSigmaPoints on LinAlgError, ukf_v2.py:170-176).  The reference takes the symmetric
+// polar factor H of B = (A + A^T)/2 from an SVD, forms (B + H)/2 -- for symmetric B that is
+// Q max(Lambda, 0) Q^T, the projection onto the PSD cone -- and then adds multiples of
+// spacing(|A|_F) to the diagonal until Cholesky succeeds.  Here: cyclic Jacobi eigen-decomposition,
+// clamp, reconstruct, and the same kind of diagonal shift (k^2 spacing at attempt k).  The shift
+// sequence is not bit-reproducible between LAPACK and this code; the resulting factors agree to
+// ~1e-7 in the repaired (null) directions, i.e. 1e-10 km in the sigma points.  Rare path: noinline,
+// arrays in local memory.
+__device__ __noinline__ bool repair_chol6(const double* __restrict__ Ein, double* __restrict__ Uout) {
+  double A[6][6], V[6][6];
+  double fro = 0.0;
+#pragma unroll 1
+  for (int i = 0; i < 6; ++i)
+#pragma unroll 1
+    for (int j = 0; j < 6; ++j) {
+      A[i][j] = Ein[i <= j ? uidx(i, j) : uidx(j, i)];
+      V[i][j] = i == j ? 1.0 : 0.0;
+      fro = fma(A[i][j], A[i][j], fro);
+    }
+  fro = sqrt(fro);
+  if (!isfinite(fro)) return false;
+#pragma unroll 1
+  for (int sweep = 0; sweep < 12; ++sweep) {
+    double off = 0.0;
+#pragma unroll 1
+    for (int p = 0; p < 5; ++p)
+#pragma unroll 1
+      for (int q = p + 1; q < 6; ++q) off = fma(A[p][q], A[p][q], off);
+    if (off <= 1e-32 * fro * fro) break;
+#pragma unroll 1
+    for (int p = 0; p < 5; ++p)
+#pragma unroll 1
+      for (int q = p + 1; q < 6; ++q) {
+        const double apq = A[p][q];
+        if (apq == 0.0) continue;
+        const double theta = (A[q][q] - A[p][p]) / (2.0 * apq);
+        const double t = (theta >= 0.0 ? 1.0 : -1.0) / (fabs(theta) + sqrt(fma(theta, theta, 1.0)));
+        const double c = 1.0 / sqrt(fma(t, t, 1.0)), sn = t * c;
+#pragma unroll 1
+        for (int k = 0; k < 6; ++k) {  // A <- A J
+          const double akp = A[k][p], akq = A[k][q];
+          A[k][p] = c * akp - sn * akq;
+          A[k][q] = sn * akp + c * akq;
+        }
+#pragma unroll 1
+        for (int k = 0; k < 6; ++k) {  // A <- J^T A ; V <- V J
+          const double apk = A[p][k], aqk = A[q][k];
+          A[p][k] = c * apk - sn * aqk;
+          A[q][k] = sn * apk + c * aqk;
+          const double vkp = V[k][p], vkq = V[k][q];
+          V[k][p] = c * vkp - sn * vkq;
+          V[k][q] = sn * vkp + c * vkq;
+        }
+      }
+  }
+  double lam[6];
+#pragma unroll 1
+  for (int i = 0; i < 6; ++i) lam[i] = A[i][i] > 0.0 ? A[i][i] : 0.0;
+  double P[21];
+#pragma unroll 1
+  for (int i = 0; i < 6; ++i)
+#pragma unroll 1
+    for (int j = i; j < 6; ++j) {
+      double acc = 0.0;
+#pragma unroll 1
+      for (int k = 0; k < 6; ++k) acc = fma(V[i][k] * lam[k], V[j][k], acc);
+      P[uidx(i, j)] = acc;
+    }
+  const double spacing = __longlong_as_double(__double_as_longlong(fro) + 1) - fro;
+  double shift = 0.0;
+#pragma unroll 1
+  for (int k = 0; k <= 64; ++k) {
+    double Es[21], U[21];
+#pragma unroll
+    for (int e = 0; e < 21; ++e) Es[e] = P[e];
+#pragma unroll
+    for (int i = 0; i < 6; ++i) Es[uidx(i, i)] += shift;
+    bool ok = chol_upper6_packed(Es, U);
+#pragma unroll
+    for (int e = 0; e < 21; ++e) ok = ok && isfinite(U[e]);
+    if (ok) {
+#pragma unroll
+      for (int e = 0; e < 21; ++e) Uout[e] = U[e];
+      return true;
+    }
+    shift += spacing * (double)((k + 1) * (k + 1));
+  }
+  return false;
+}
+
 // generateSigmaPoints (ukf_v2.py:158-183): x + gamma * [0, U, -U], COLUMNS of the upper factor.
 __device__ __forceinline__ void write_sigma_blocks(double* __restrict__ sb, int64_t ld, int64_t t,
                                                    const double (&x)[6], const double (&U)[21],
@@ -351,6 +456,7 @@ sigma_gen_kernel(const double* __restrict__ est_x, const double* __restrict__ es
 #pragma unroll
     for (int j = i; j < 6; ++j) E[uidx(i, j)] = P[i * 6 + j];
   const bool ok = chol_upper6_packed(E, U);
+  if (!ok) repair_chol6(E, U);  // reference: nearest-PD fallback; the target stays flagged
   write_sigma_blocks(sb, ld, t, x, U, gamma);
   if (truth_x && truth_x != sb + 13 * 6 * ld) {
 #pragma unroll
@@ -617,6 +723,7 @@ ukf_finish_kernel(const __grid_constant__ UkfArgs a) {
       // factor the NEW estimate and lay out next step's sigma points (block 0 = est_x)
       double U[21];
       const bool ok = chol_upper6_packed(PE, U);
+      if (!ok) repair_chol6(PE, U);
       write_sigma_blocks(a.sb, ld, t, xe, U, a.p.gamma);
       a.sig_flags[t] = ok ? 0u : (uint32_t)PC_FLAG_NONPD_EST;
       const double r0[3] = {xe[0], xe[1], xe[2]}, v0[3] = {xe[3], xe[4], xe[5]};
@@ -852,6 +959,7 @@ ukf_finish_quad_kernel(const __grid_constant__ UkfArgs a) {
     if (a.gen_next) {
       double U[21];
       const bool ok = chol_upper6_packed(PE, U);
+      if (!ok) repair_chol6(PE, U);
       // block 0 (centre) and the 12 offset blocks, block i written by lane i & 3
       if (q == 0) {
 #pragma unroll

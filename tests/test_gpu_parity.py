@@ -236,18 +236,46 @@ def test_ukf_object_api_golden(golden):
         UnscentedKalmanFilter(0, np.zeros(2), np.eye(2), SatDynamicsModel(), lambda s: s, np.eye(2), np.eye(2))
 
 
-def test_ukf_nonpd_is_flagged_not_fatal(golden):
-    from clockpunch_b200 import _lib
+def test_ukf_nonpd_is_flagged_and_repaired(golden):
+    """A non-PD covariance is DATA (flag), and -- like the reference's nearest-PD fallback
+    (ukf_v2.py:170-176, ukf_utils.py:155-198) -- the filter keeps going on the repaired factor."""
+    import ctypes as C
+    import torch
+    from clockpunch_b200 import _lib, _buffers as B
     from clockpunch_b200.estimation.ukf_v2 import ukf_batch_host
+    from oracle.ukf import OracleUKF
     g = golden("ukf")
     params = _lib.make_ukf_params(g["cat_Q"], g["cat_R"])
     x = g["cat_truth0"][:, :3]
     p = np.broadcast_to(g["cat_P0"], (3, 6, 6)).copy()
     p[1] = g["npd_cov"]
+    # sigma points of the repaired factor against the LIVE reference's own (generateSigmaPoints on
+    # the same matrix, tests/golden/make_golden.py): the repaired direction agrees to ~1e-10 km
+    ctx = _lib.get_ctx()
+    dev = B.device_of(ctx)
+    dx = torch.from_numpy(np.ascontiguousarray(g["cat_truth0"][:, :1])).to(dev)
+    dp = torch.from_numpy(g["npd_cov"].reshape(1, 36).copy()).to(dev)
+    ws = torch.zeros((14, 6, 1), dtype=torch.float64, device=dev)
+    fl = torch.zeros((2, 1), dtype=torch.int32, device=dev)
+    ctx.check(ctx.lib.pc_sigma_points(ctx.handle, dx.data_ptr(), dp.data_ptr(), 1, 1, params.gamma, ws.data_ptr(),
+                                      fl.data_ptr(), None))
+    sig = ws[:13, :, 0].cpu().numpy().T
+    assert fl[0, 0].item() & _lib.FLAG_NONPD_EST
+    np.testing.assert_allclose(sig, g["npd_sigma"], rtol=0, atol=1e-8)
+    # one full predict step: flagged, finite, and equal to the oracle (which took its nearest-PD path)
     out = ukf_batch_host(x, p, None, None, 0.0, 60.0, params)
-    assert out["flags"][1] & _lib.FLAG_NONPD_EST and out["flags"][1] & _lib.FLAG_NONFINITE
+    assert out["flags"][1] & _lib.FLAG_NONPD_EST and not out["flags"][1] & _lib.FLAG_NONFINITE
     assert out["flags"][0] == 0 and out["flags"][2] == 0
-    assert np.isfinite(out["est_p"][[0, 2]]).all()
+    assert np.isfinite(out["est_p"]).all() and np.isfinite(out["est_x"]).all()
+    f = OracleUKF(0.0, x[:, 1], p[1], g["cat_Q"], g["cat_R"])
+    f.predict_and_update(60.0, None)
+    assert f.used_nearest_pd
+    assert np.abs(out["est_x"][:, 1] - f.est_x).max() <= 1e-8
+    assert cov_close(out["pred_p"][1], f.pred_p, 1e-7)
+    # NaN input: flagged non-finite, neighbours untouched
+    p2 = p.copy(); p2[1, 2, 2] = np.nan
+    out = ukf_batch_host(x, p2, None, None, 0.0, 60.0, params)
+    assert out["flags"][1] & _lib.FLAG_NONFINITE and out["flags"][0] == 0 and out["flags"][2] == 0
 
 
 def _engine_and_oracle(n, m, seed, space_frac=0.25):
