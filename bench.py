@@ -43,6 +43,8 @@ UNIT = "target-steps/s"
 FLOP_DOP853_STEP = 1150.0          # one fixed DOP853 step: 12 RHS + stage sums + final combination
 FLOP_UKF_NOMEAS, FLOP_UKF_MEAS = 1500.0, 5600.0
 FLOP_VIS_PAIR = 8.0
+# DRAM traffic per launch of propagate_sigma_kernel from the committed ncu captures: (targets, sensors) -> bytes
+TRAFFIC_NCU = {(10_000, 100): 6.784e6 + 0.0, (1_000_000, 100): 680.1e6 + 614.4e6}
 BYTES_TARGET_STEP = 1130.0         # truth/est_x/est_p r+w, pred_p w, z r (+ M/4 vis bits)
 
 
@@ -301,7 +303,9 @@ def run_own(args):
     hbm_ach = 14 * 96.0 * N / (ukf_ms_avg * 1e-3) * 1e-9
     roofline = {"bound": "fp64", "kernel": "propagate_sigma_kernel", "achieved": achieved_tf, "peak": peak_tf.value,
                 "unit": "TFLOP/s", "frac": achieved_tf / peak_tf.value if peak_tf.value else None,
-                "traffic": None, "peak_source": "FP64 DFMA probe measured live in this run (pc_fp64_peak); "
+                "traffic": TRAFFIC_NCU.get((N, M)), "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum of this "
+                "kernel in the committed ncu --set full capture of this workload (profiles/r1b_ncu_full_step_*_metrics.csv); "
+                "null for other sizes", "peak_source": "FP64 DFMA probe measured live in this run (pc_fp64_peak); "
                 "MEASURED_PEAKS.json has no FP64 entry (HBM/bf16 only); nominal 37 TFLOP/s",
                 "flop_per_launch": flop_per_launch, "dop853_steps_per_launch": state_steps,
                 "mean_substeps_per_sigma_propagate": substeps_used,
