@@ -842,7 +842,7 @@ int pc_step_fused(pc_ctx* ctx, const pc_step_args* a, const pc_ukf_params* param
       u.sens_q = reinterpret_cast<const double4*>(sq);
       u.M = a->M;
       u.wpr = a->words_per_row;
-      u.env_targets = Ne > 0 ? Ne : 1;
+      u.env_targets = a->env_targets > 0 ? Ne : 0;   // 0: one environment (no index divisions)
       u.env_sensors = Me;
       u.vis_truth = a->vis_truth;
       u.vis_est = a->vis_est;

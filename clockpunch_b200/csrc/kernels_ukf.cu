@@ -502,34 +502,85 @@ constexpr int kVisTile = 256;  // sensors staged per pass of the fused visibilit
 constexpr int kVisRow = 33;
 constexpr int kVisTileSlots = (kVisTile / 32) * kVisRow;
 
-// Asynchronous (cp.async, LDGSTS) copy of one chunk of sensor ROWS into shared memory: issued at
-// kernel entry, waited for only when the visibility phase starts, so its latency hides behind the
+// Asynchronous copy of one chunk of sensor ROWS into shared memory with the bulk-copy engine
+// (cp.async.bulk + mbarrier transaction count; UBLKCP in SASS): ONE thread issues one copy per row
+// (a row's sensors are contiguous in global memory) at kernel entry, nobody touches the LSU, and
+// the tile is waited for only when the visibility phase starts, so its latency hides behind the
 // filter algebra.  A row is one 32-sensor word of one environment: global row r belongs to
 // environment r / wpr and holds its sensors (r % wpr) * 32 .. + 31 (single catalog: one
-// environment).  Slots past the environment's sensor count get a NaN horizon term (never visible).
-__device__ __forceinline__ void load_sensor_tile(double4* __restrict__ tile,
+// environment).  Slots past the environment's sensor count are filled with a NaN horizon term
+// (never visible) by the other threads through the generic proxy.
+// Environment of a target / of a sensor row.  A single catalog (env_targets == 0) skips the 64-bit
+// divisions, which cost more than the whole visibility phase of a small tile.
+__device__ __forceinline__ int64_t env_of_target(int64_t t, int64_t env_targets) {
+  return env_targets > 0 ? t / env_targets : 0;
+}
+__device__ __forceinline__ void row_split(int64_t r, int64_t wpr, bool single, int64_t& e, int64_t& w) {
+  if (single) {
+    e = 0;
+    w = r;
+  } else {
+    e = r / wpr;
+    w = r - e * wpr;
+  }
+}
+
+__device__ __forceinline__ void sensor_tile_init(uint64_t* mbar) {
+  if (threadIdx.x == 0) {
+    const unsigned mb = (unsigned)__cvta_generic_to_shared(mbar);
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(mb) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+}
+
+__device__ __forceinline__ void load_sensor_tile(double4* __restrict__ tile, uint64_t* mbar,
                                                  const double4* __restrict__ sens_q, int64_t r0,
-                                                 int64_t row_end, int64_t Me, int64_t wpr, int tpb) {
+                                                 int64_t row_end, int64_t Me, int64_t wpr, bool single,
+                                                 int tpb) {
   const double nan = __longlong_as_double(0x7ff8000000000000LL);
-  for (int j = threadIdx.x; j < kVisTile; j += tpb) {
-    const int rr = j >> 5;
-    const int slot = rr * kVisRow + (j & 31);
-    const int64_t r = r0 + rr;
-    const int64_t e = r / wpr;
-    const int64_t sl = (r - e * wpr) * 32 + (j & 31);
-    if (r < row_end && sl < Me) {
-      const unsigned dst = (unsigned)__cvta_generic_to_shared(tile + slot);
-      const double4* src = sens_q + e * Me + sl;
-      asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
-      asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(dst + 16), "l"((const char*)src + 16) : "memory");
-    } else {
-      tile[slot] = make_double4(0.0, 0.0, 0.0, nan);
+  const int nrows = (int)(row_end - r0 < kVisTile / 32 ? row_end - r0 : kVisTile / 32);
+  if (threadIdx.x == 0) {
+    const unsigned mb = (unsigned)__cvta_generic_to_shared(mbar);
+    // earlier generic-proxy reads of the tile (previous chunk) are ordered before the async writes
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    unsigned total = 0;
+    for (int rr = 0; rr < nrows; ++rr) {
+      int64_t e, w;
+      row_split(r0 + rr, wpr, single, e, w);
+      const int64_t cnt = Me - w * 32 < 32 ? Me - w * 32 : 32;
+      total += (unsigned)cnt * 32u;
+    }
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mb), "r"(total) : "memory");
+    for (int rr = 0; rr < nrows; ++rr) {
+      int64_t e, w;
+      row_split(r0 + rr, wpr, single, e, w);
+      const int64_t s0 = w * 32;
+      const int64_t cnt = Me - s0 < 32 ? Me - s0 : 32;
+      const unsigned dst = (unsigned)__cvta_generic_to_shared(tile + rr * kVisRow);
+      const double4* src = sens_q + e * Me + s0;
+      asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                   ::"r"(dst), "l"(src), "r"((unsigned)cnt * 32u), "r"(mb) : "memory");
     }
   }
-  asm volatile("cp.async.commit_group;" ::: "memory");
+  for (int j = threadIdx.x; j < kVisTile; j += tpb) {
+    const int rr = j >> 5;
+    int64_t e, w;
+    row_split(r0 + rr, wpr, single, e, w);
+    const int64_t sl = w * 32 + (j & 31);
+    if (!(rr < nrows && sl < Me)) tile[rr * kVisRow + (j & 31)] = make_double4(0.0, 0.0, 0.0, nan);
+  }
 }
-__device__ __forceinline__ void wait_sensor_tile() {
-  asm volatile("cp.async.wait_group 0;" ::: "memory");
+
+// Wait for the chunk whose copies were issued `phase` chunks ago modulo 2 (mbarrier phase parity),
+// then make the NaN padding written by the other threads visible to everybody.
+__device__ __forceinline__ void wait_sensor_tile(uint64_t* mbar, unsigned phase) {
+  const unsigned mb = (unsigned)__cvta_generic_to_shared(mbar);
+  unsigned done = 0;
+  for (int spin = 0; !done && spin < (1 << 22); ++spin) {   // bounded: a lost transaction must not hang the GPU
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                 : "=r"(done) : "r"(mb), "r"(phase) : "memory");
+  }
   __syncthreads();
 }
 
@@ -564,6 +615,7 @@ ukf_finish_kernel(const __grid_constant__ UkfArgs a) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   double* stage = smem + warp * kStageDoubles;
   double4* tile = reinterpret_cast<double4*>(smem + (TPB / 32) * kStageDoubles);
+  uint64_t* mbar = reinterpret_cast<uint64_t*>(tile + kVisTileSlots);
   const int64_t t = (int64_t)blockIdx.x * TPB + threadIdx.x;
   if (a.clock && a.advance_clock && t == 0) {
     // nobody reads t_now / step during this launch (kernels read the t_cur / step_cur copies)
@@ -579,9 +631,13 @@ ukf_finish_kernel(const __grid_constant__ UkfArgs a) {
   // sensor rows this CTA's targets need (one environment unless the catalog is a batch of envs)
   const int64_t cta_t0 = (int64_t)blockIdx.x * TPB;
   const int64_t cta_t1 = cta_t0 + TPB - 1 < a.n - 1 ? cta_t0 + TPB - 1 : a.n - 1;
-  const int64_t row_first = vis ? (cta_t0 / a.env_targets) * a.wpr : 0;
-  const int64_t row_end = vis ? (cta_t1 / a.env_targets + 1) * a.wpr : 0;
-  if (vis) load_sensor_tile(tile, a.sens_q, row_first, row_end, a.env_sensors, a.wpr, TPB);
+  const bool single = a.env_targets <= 0;
+  const int64_t row_first = vis ? env_of_target(cta_t0, a.env_targets) * a.wpr : 0;
+  const int64_t row_end = vis ? (env_of_target(cta_t1, a.env_targets) + 1) * a.wpr : 0;
+  if (vis) {
+    sensor_tile_init(mbar);
+    load_sensor_tile(tile, mbar, a.sens_q, row_first, row_end, a.env_sensors, a.wpr, single, TPB);
+  }
 
   // ---- unscented transform (predictStateEstimate / predictCovariance, ukf_v2.py:261-292) ------
   double X0[6], tr[3];
@@ -740,17 +796,18 @@ ukf_finish_kernel(const __grid_constant__ UkfArgs a) {
     const double tq = horizon_q(tr[0], tr[1], tr[2], a.body_radius, a.vis_tol);
     const double eq = horizon_q(xe[0], xe[1], xe[2], a.body_radius, a.vis_tol);
     const int64_t wpr = a.wpr;
-    const int64_t my_row0 = (tc / a.env_targets) * wpr;
-    for (int64_t r0 = row_first; r0 < row_end; r0 += kVisTile / 32) {
+    const int64_t my_row0 = env_of_target(tc, a.env_targets) * wpr;
+    unsigned phase = 0;
+    for (int64_t r0 = row_first; r0 < row_end; r0 += kVisTile / 32, phase ^= 1u) {
       if (r0 != row_first) {
         __syncthreads();
-        load_sensor_tile(tile, a.sens_q, r0, row_end, a.env_sensors, wpr, TPB);
+        load_sensor_tile(tile, mbar, a.sens_q, r0, row_end, a.env_sensors, wpr, single, TPB);
       }
-      wait_sensor_tile();
+      wait_sensor_tile(mbar, phase);
       const int nrows = (int)(row_end - r0 < kVisTile / 32 ? row_end - r0 : kVisTile / 32);
-      for (int rr = 0; rr < nrows; ++rr) {
-        const int64_t w = r0 + rr - my_row0;
-        if (w >= 0 && w < wpr) {
+      for (int64_t w = 0; w < wpr; ++w) {
+        const int64_t rr = my_row0 + w - r0;
+        if (rr >= 0 && rr < nrows) {
           uint32_t wa, wb;
           vis_word(tile + rr * kVisRow, tr, tq, xe, eq, RE2, wa, wb);
           if (live) {
@@ -801,6 +858,8 @@ __device__ __forceinline__ void store_sym36_quad(double* __restrict__ g, const d
 __global__ void __launch_bounds__(kQuadThreads, 5)
 ukf_finish_quad_kernel(const __grid_constant__ UkfArgs a) {
   __shared__ __align__(32) double4 tile[kVisTileSlots];
+  __shared__ uint64_t mbar_store;
+  uint64_t* mbar = &mbar_store;
   const int q = threadIdx.x & 3;
   const int64_t t = ((int64_t)blockIdx.x * kQuadThreads + threadIdx.x) >> 2;
   if (a.clock && a.advance_clock && blockIdx.x == 0 && threadIdx.x == 0) {
@@ -815,9 +874,13 @@ ukf_finish_quad_kernel(const __grid_constant__ UkfArgs a) {
   const bool vis = a.vis_truth != nullptr;
   const int64_t cta_t0 = (int64_t)blockIdx.x * (kQuadThreads / 4);
   const int64_t cta_t1 = cta_t0 + kQuadThreads / 4 - 1 < a.n - 1 ? cta_t0 + kQuadThreads / 4 - 1 : a.n - 1;
-  const int64_t row_first = vis ? (cta_t0 / a.env_targets) * a.wpr : 0;
-  const int64_t row_end = vis ? (cta_t1 / a.env_targets + 1) * a.wpr : 0;
-  if (vis) load_sensor_tile(tile, a.sens_q, row_first, row_end, a.env_sensors, a.wpr, kQuadThreads);
+  const bool single = a.env_targets <= 0;
+  const int64_t row_first = vis ? env_of_target(cta_t0, a.env_targets) * a.wpr : 0;
+  const int64_t row_end = vis ? (env_of_target(cta_t1, a.env_targets) + 1) * a.wpr : 0;
+  if (vis) {
+    sensor_tile_init(mbar);
+    load_sensor_tile(tile, mbar, a.sens_q, row_first, row_end, a.env_sensors, a.wpr, single, kQuadThreads);
+  }
 
   // ---- every global load of the untasked path is issued here, before any arithmetic -------------
   // (one round trip to HBM instead of four: at this occupancy latency is the whole cost)
@@ -999,18 +1062,21 @@ ukf_finish_quad_kernel(const __grid_constant__ UkfArgs a) {
     const double tq = horizon_q(tr[0], tr[1], tr[2], a.body_radius, a.vis_tol);
     const double eq = horizon_q(xe[0], xe[1], xe[2], a.body_radius, a.vis_tol);
     const int64_t wpr = a.wpr;
-    const int64_t my_row0 = (tc / a.env_targets) * wpr;
-    for (int64_t r0 = row_first; r0 < row_end; r0 += kVisTile / 32) {
+    const int64_t my_row0 = env_of_target(tc, a.env_targets) * wpr;
+    unsigned phase = 0;
+    for (int64_t r0 = row_first; r0 < row_end; r0 += kVisTile / 32, phase ^= 1u) {
       if (r0 != row_first) {
         __syncthreads();
-        load_sensor_tile(tile, a.sens_q, r0, row_end, a.env_sensors, wpr, kQuadThreads);
+        load_sensor_tile(tile, mbar, a.sens_q, r0, row_end, a.env_sensors, wpr, single, kQuadThreads);
       }
-      wait_sensor_tile();
+      wait_sensor_tile(mbar, phase);
       PC_PHASE_CLOCK(8);
       const int nrows = (int)(row_end - r0 < kVisTile / 32 ? row_end - r0 : kVisTile / 32);
-      for (int rr = 0; rr < nrows; ++rr) {
-        const int64_t w = r0 + rr - my_row0;
-        if (w >= 0 && w < wpr && (w & 3) == q) {       // lane q packs words q, q + 4, ...
+      // lane q packs words q, q + 4, ... of ITS target: the four lanes of a quad work on four
+      // different tile rows at the same time (hence the 33-slot rows)
+      for (int64_t w = q; w < wpr; w += 4) {
+        const int64_t rr = my_row0 + w - r0;
+        if (rr >= 0 && rr < nrows) {
           uint32_t wa, wb;
           vis_word(tile + rr * kVisRow, tr, tq, xe, eq, RE2, wa, wb);
           if (live) {
@@ -1026,7 +1092,7 @@ ukf_finish_quad_kernel(const __grid_constant__ UkfArgs a) {
 
 template <int TPB>
 static cudaError_t launch_finish_tpb(const UkfArgs& a, cudaStream_t stream) {
-  const size_t smem = (size_t)(TPB / 32) * kStageDoubles * sizeof(double) + kVisTileSlots * sizeof(double4);
+  const size_t smem = (size_t)(TPB / 32) * kStageDoubles * sizeof(double) + kVisTileSlots * sizeof(double4) + 16;
   ukf_finish_kernel<TPB><<<(unsigned)((a.n + TPB - 1) / TPB), TPB, smem, stream>>>(a);
   return cudaGetLastError();
 }

@@ -33,7 +33,7 @@ struct UkfArgs {
   const double4* sens_q;
   int64_t M, wpr;
   // batch of environments: target i belongs to environment i / env_targets and is tested against
-  // that environment's env_sensors sensors; a single catalog has env_targets = n, env_sensors = M
+  // that environment's env_sensors sensors; a single catalog has env_targets = 0, env_sensors = M
   int64_t env_targets, env_sensors;
   uint32_t* vis_truth;
   uint32_t* vis_est;

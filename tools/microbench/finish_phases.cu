@@ -50,7 +50,7 @@ int main(int argc, char** argv) {
   UkfArgs u{};
   u.sb = d_sb; u.est_p = d_P; u.tasked = d_task; u.n = n; u.ld = ld; u.dt = 100; u.t_now = 100; u.out_pred_p = d_pp;
   u.num_tasked = d_nt; u.last_time_tasked = d_f3; u.tr_pos = d_f1; u.tr_vel = d_f2; u.sig_flags = d_sf; u.gen_next = 1;
-  u.sens_q = (const double4*)d_sq; u.M = M; u.wpr = wpr; u.env_targets = n; u.env_sensors = M; u.vis_truth = d_vt; u.vis_est = d_ve; u.body_radius = 6378.1363; u.vis_tol = 1e-13; u.p = prm;
+  u.sens_q = (const double4*)d_sq; u.M = M; u.wpr = wpr; u.env_targets = 0; u.env_sensors = M; u.vis_truth = d_vt; u.vis_est = d_ve; u.body_radius = 6378.1363; u.vis_tol = 1e-13; u.p = prm;
   char* flush; cudaMalloc(&flush, 256 << 20);
   cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
   for (int rep = 0; rep < 4; ++rep) {
