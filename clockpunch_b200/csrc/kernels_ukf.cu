@@ -124,6 +124,21 @@ __device__ __forceinline__ void normal6(uint64_t seed, uint64_t step, uint64_t t
 
 __device__ bool repair_chol6(const double* __restrict__ Ein, double* __restrict__ Uout);  // below
 
+// Call wrapper that keeps the caller's register arrays out of local memory: only the two
+// temporaries below have their address taken.
+__device__ __forceinline__ void repair_chol6_regs(const double (&E)[21], double (&U)[21]) {
+  double Ein[21], Uo[21];
+#pragma unroll
+  for (int k = 0; k < 21; ++k) {
+    Ein[k] = E[k];
+    Uo[k] = U[k];
+  }
+  repair_chol6(Ein, Uo);
+#pragma unroll
+  for (int k = 0; k < 21; ++k) U[k] = Uo[k];
+}
+
+
 // Measurement update for one tasked target, everything addressed in shared memory.
 // forecast / calculateKalmanGain / updateCovariance / calculateInnovations /
 // updateStateEstimate (ukf_v2.py:211-228, 294-375).
@@ -259,7 +274,7 @@ __device__ __forceinline__ uint32_t measurement_update_reg(
   double U2[21];
   if (!chol_upper6_packed(E, U2)) {
     flags |= PC_FLAG_NONPD_PRED;
-    repair_chol6(E, U2);
+    repair_chol6_regs(E, U2);
   }
   const double c3 = p.wc0 - p.wm0;
   const double cuu = 2.0 * p.wi * p.gamma * p.gamma;
@@ -456,7 +471,7 @@ sigma_gen_kernel(const double* __restrict__ est_x, const double* __restrict__ es
 #pragma unroll
     for (int j = i; j < 6; ++j) E[uidx(i, j)] = P[i * 6 + j];
   const bool ok = chol_upper6_packed(E, U);
-  if (!ok) repair_chol6(E, U);  // reference: nearest-PD fallback; the target stays flagged
+  if (!ok) repair_chol6_regs(E, U);  // reference: nearest-PD fallback; the target stays flagged
   write_sigma_blocks(sb, ld, t, x, U, gamma);
   if (truth_x && truth_x != sb + 13 * 6 * ld) {
 #pragma unroll
@@ -779,7 +794,7 @@ ukf_finish_kernel(const __grid_constant__ UkfArgs a) {
       // factor the NEW estimate and lay out next step's sigma points (block 0 = est_x)
       double U[21];
       const bool ok = chol_upper6_packed(PE, U);
-      if (!ok) repair_chol6(PE, U);
+      if (!ok) repair_chol6_regs(PE, U);
       write_sigma_blocks(a.sb, ld, t, xe, U, a.p.gamma);
       a.sig_flags[t] = ok ? 0u : (uint32_t)PC_FLAG_NONPD_EST;
       const double r0[3] = {xe[0], xe[1], xe[2]}, v0[3] = {xe[3], xe[4], xe[5]};
@@ -877,10 +892,6 @@ ukf_finish_quad_kernel(const __grid_constant__ UkfArgs a) {
   const bool single = a.env_targets <= 0;
   const int64_t row_first = vis ? env_of_target(cta_t0, a.env_targets) * a.wpr : 0;
   const int64_t row_end = vis ? (env_of_target(cta_t1, a.env_targets) + 1) * a.wpr : 0;
-  if (vis) {
-    sensor_tile_init(mbar);
-    load_sensor_tile(tile, mbar, a.sens_q, row_first, row_end, a.env_sensors, a.wpr, single, kQuadThreads);
-  }
 
   // ---- every global load of the untasked path is issued here, before any arithmetic -------------
   // (one round trip to HBM instead of four: at this occupancy latency is the whole cost)
@@ -902,6 +913,12 @@ ukf_finish_quad_kernel(const __grid_constant__ UkfArgs a) {
   }
   const int tflag = a.tasked ? (int)a.tasked[tc] : 0;
   uint32_t flags = a.sig_flags ? a.sig_flags[tc] : 0u;
+  // the sensor tile is requested AFTER the register loads are in flight (one thread issues the bulk
+  // copies; everybody else would otherwise wait for it at the barrier before issuing anything)
+  if (vis) {
+    sensor_tile_init(mbar);
+    load_sensor_tile(tile, mbar, a.sens_q, row_first, row_end, a.env_sensors, a.wpr, single, kQuadThreads);
+  }
   PC_PHASE_CLOCK(1);
 
   // ---- unscented transform: lane q takes pairs q and q + 4 ------------------------------------
@@ -1022,7 +1039,7 @@ ukf_finish_quad_kernel(const __grid_constant__ UkfArgs a) {
     if (a.gen_next) {
       double U[21];
       const bool ok = chol_upper6_packed(PE, U);
-      if (!ok) repair_chol6(PE, U);
+      if (!ok) repair_chol6_regs(PE, U);
       // block 0 (centre) and the 12 offset blocks, block i written by lane i & 3
       if (q == 0) {
 #pragma unroll
