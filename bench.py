@@ -247,16 +247,24 @@ def run_own(args):
     # ---------------- roofline of the dominant kernel (separate pass) ----------------
     # propagate_sigma_kernel: all 13 sigma points + the truth state of every target, one thread per
     # state.  Its launch is bracketed by a CUDA-event pair recorded by the library on the launch
-    # stream (event-record nodes inside the graph, so this pass is NOT the one `value` comes from).
+    # stream.  This pass launches the step's kernels one by one (not the graph `value` replays):
+    # inside a captured graph the pair would be two extra event-record NODES, whose latency (~4 us
+    # each) would be charged to a 14 us kernel.
     # Algorithmic work: SURVEY.md section 8(d), 1150 flop per fixed DOP853 step x the substeps each state
     # actually takes (read back from the per-target orbit rates the step itself uses); algorithmic
     # bytes: each 6-vector read and written once.
     # Every pass (value, roofline, e2e) starts from the same catalog state: reset + warm-up.
     eng.reset()
-    ctx.check(lib.pc_set_timing(ctx.handle, 1))        # before capture: the event pair is part of the graph
-    g_timed = eng.build_graph(DT, policy_probes=64, policy_seed=SEED, post=post)
+    ctx.check(lib.pc_set_timing(ctx.handle, 1))
+    eng._graph = None
+
+    def timed_step():
+        eng.step_policy_eager(DT, 64, SEED)         # same kernels, launched one by one: plain event records
+        if sg is not None:
+            sg.gather()
+
     for k in range(args.warmup):
-        eng.replay(g_timed)
+        timed_step()
     inv_theta = np.float32(1.0 / 0.12)
 
     def substeps_now():
@@ -275,8 +283,8 @@ def run_own(args):
         ss, es = substeps_now()
         if args.l2 == "flush":
             flush.zero_()
-        eng.replay(g_timed)
-        torch.cuda.synchronize(dev)                                   # both events are this replay's
+        timed_step()
+        torch.cuda.synchronize(dev)                                   # both events are this step's
         ctx.check(lib.pc_get_timing(ctx.handle, C.byref(ukf_last)))
         if k >= 2:
             ukf_ms_sum += ukf_last.value

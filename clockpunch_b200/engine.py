@@ -245,6 +245,23 @@ class CatalogEngine:
         self._graph = g
         return g
 
+    def step_policy_eager(self, dt: float, policy_probes: int, policy_seed: int = 0):
+        """The step of build_graph(policy_probes > 0) launched kernel by kernel instead of replayed
+        (device clock, stand-in policy, measurements drawn on device).  Used by bench.py's roofline
+        pass: plain cudaEventRecord calls around one kernel measure it without the latency of the
+        event-record NODES a captured graph needs."""
+        self.ensure_sigma()
+        if self._hs_dt is None and self._graph is None:
+            self.tasked.zero_()
+            self._sync_clock()
+            self._hs_dt = float(dt)
+        a = self._fill_args(0.0, float(dt), None, self.tasked, use_clock=True, actions=self.actions,
+                            policy_probes=policy_probes, policy_seed=policy_seed)
+        c = self.ctx
+        c.check(c.lib.pc_step_fused(c.handle, C.byref(a), C.byref(self.params), self._stream()))
+        self.time += float(dt)
+        self.step_count += 1
+
     def ensure_sigma(self):
         """(Re)generate sigma-point blocks 1..12 from the current (est_x, est_p) if stale."""
         if not self._sigma_valid:
