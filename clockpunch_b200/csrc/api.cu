@@ -62,10 +62,6 @@ struct pc_ctx {
   // optional per-kernel timing of pc_step_fused (bench.py roofline leg)
   bool timing = false;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;  // around the UKF kernel
-  // pc_step_fused: the sensor / tasking kernel runs on a side stream next to the target
-  // propagation (fork / join with two events; parallel branches when captured into a graph)
-  cudaStream_t side_stream = nullptr;
-  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   // sensor positions + horizon terms for the fused visibility phase when the caller brings no
   // pc_step_args.sens_q (not graph-capture safe)
   double* sq = nullptr;
@@ -160,10 +156,7 @@ int pc_ctx_create(int device_ordinal, pc_ctx** out) {
   if (!ctx) return PC_ERR_BAD_ARG;
   ctx->device = device_ordinal;
   DeviceGuard g(device_ordinal);
-  if (cudaStreamCreateWithFlags(&ctx->host_stream, cudaStreamNonBlocking) != cudaSuccess ||
-      cudaStreamCreateWithFlags(&ctx->side_stream, cudaStreamNonBlocking) != cudaSuccess ||
-      cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming) != cudaSuccess ||
-      cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming) != cudaSuccess) {
+  if (cudaStreamCreateWithFlags(&ctx->host_stream, cudaStreamNonBlocking) != cudaSuccess) {
     delete ctx;
     return PC_ERR_CUDA;
   }
@@ -179,9 +172,6 @@ int pc_ctx_destroy(pc_ctx* ctx) {
     if (ctx->sb) cudaFree(ctx->sb);
     if (ctx->sbf) cudaFree(ctx->sbf);
     if (ctx->host_stream) cudaStreamDestroy(ctx->host_stream);
-    if (ctx->side_stream) cudaStreamDestroy(ctx->side_stream);
-    if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
-    if (ctx->ev_join) cudaEventDestroy(ctx->ev_join);
     if (ctx->sq) cudaFree(ctx->sq);
     if (ctx->ev0) cudaEventDestroy(ctx->ev0);
     if (ctx->ev1) cudaEventDestroy(ctx->ev1);
@@ -545,7 +535,7 @@ int pc_ukf_predict_update(pc_ctx* ctx, double* est_x, double* est_p, double* tru
   PC_CUDA_TRY(ctx, pc::launch_sigma_gen(est_x, est_p, truth_x, ctx->sb, n, ld, params->gamma, ctx->sbf, st));
   // stage 2: all 13 (+1) n states
   PC_CUDA_TRY(ctx, pc::launch_propagate_sigma(ctx->sb, n, ld, truth_x != nullptr, t0, tf, substeps,
-                                              force_model, ctx->sbf, st));
+                                              force_model, ctx->sbf, false, st));
   // stage 3: unscented transform + update
   pc::UkfArgs u{};
   u.sb = ctx->sb;
@@ -775,32 +765,27 @@ int pc_step_fused(pc_ctx* ctx, const pc_step_args* a, const pc_ukf_params* param
   }
   // 1. sensors (Agent.propagate per sensor; terrestrial ones are a rotation), their horizon terms,
   //    tasking mask from the actions and the PREVIOUS estimated vis map, step clock latch.
-  //    Independent of the target propagation, so it runs beside it on the side stream.
+  //    Independent of the target propagation, which is launched programmatically behind it and
+  //    therefore runs beside it (no fork / join, no second stream).
   const bool pre = a->M > 0 || a->clock;
-  const bool fork = pre && a->N > 0;
   if (pre) {
-    cudaStream_t ps = s;
-    if (fork) {
-      PC_CUDA_TRY(ctx, cudaEventRecord(ctx->ev_fork, s));
-      PC_CUDA_TRY(ctx, cudaStreamWaitEvent(ctx->side_stream, ctx->ev_fork, 0));
-      ps = ctx->side_stream;
-    }
     PC_CUDA_TRY(ctx, pc::launch_pre_step(a->sens_x, a->sens_kind, a->M, a->ld_s, a->t0, a->tf, a->substeps,
                                          a->force_model, fuse_vis ? sq : nullptr, a->body_radius, a->vis_tol,
                                          a->clock, a->actions, a->vis_est, const_cast<uint8_t*>(a->tasked),
                                          a->N, a->words_per_row, a->policy_probes, a->policy_seed,
-                                         a->rng_step, Ne, Me, ps));
+                                         a->rng_step, Ne, Me, s));
     ctx->launches += 1;
-    if (fork) PC_CUDA_TRY(ctx, cudaEventRecord(ctx->ev_join, ps));
   }
   // 2. targets: sigma points (only when not carried over from the previous step), all 14 N
   //    states propagated, then transform + update + summaries + next step's sigma points + both
   //    visibility rows of every target (env.py:455-462)
   if (a->N > 0) {
+    bool beside = pre && !ctx->timing;  // the roofline pass wants the propagation alone between its events
     if (!own_sb || !a->sigma_valid) {
       PC_CUDA_TRY(ctx, pc::launch_sigma_gen(a->est_x, a->est_p, a->truth_x, sb, a->N, a->ld, params->gamma,
                                             sbf, s));
       ctx->launches += 1;
+      beside = false;  // the propagation reads what this kernel writes: ordinary dependency
     }
     unsigned evflags = cudaEventRecordDefault;
     if (ctx->timing) {
@@ -810,9 +795,8 @@ int pc_step_fused(pc_ctx* ctx, const pc_step_args* a, const pc_ukf_params* param
       PC_CUDA_TRY(ctx, cudaEventRecordWithFlags(ctx->ev0, s, evflags));
     }
     PC_CUDA_TRY(ctx, pc::launch_propagate_sigma(sb, a->N, a->ld, 1, a->t0, a->tf, a->substeps,
-                                                a->force_model, sbf, s));
+                                                a->force_model, sbf, beside, s));
     if (ctx->timing) PC_CUDA_TRY(ctx, cudaEventRecordWithFlags(ctx->ev1, s, evflags));
-    if (fork) PC_CUDA_TRY(ctx, cudaStreamWaitEvent(s, ctx->ev_join, 0));
     pc::UkfArgs u{};
     u.sb = sb;
     u.est_p = a->est_p;

@@ -26,6 +26,7 @@ obs_pack_kernel(const double* __restrict__ sens_x, int64_t M, int64_t ld_s,
                 int64_t ld, const float* __restrict__ last_time_tasked, double t_now_arg,
                 const pc_clock* __restrict__ clock, float* __restrict__ out_eci,
                 float* __restrict__ out_cov, float* __restrict__ out_stale) {
+  pdl_wait();  // launched programmatically behind the per-target stage
   const double t_now = clock ? clock->t_now : t_now_arg;
   const int64_t idx = (int64_t)blockIdx.x * 256 + threadIdx.x;
   const int64_t A = M + N;
@@ -180,6 +181,7 @@ struct PreStepArgs {
 template <bool J2>
 __global__ void __launch_bounds__(128)
 pre_step_kernel(const __grid_constant__ PreStepArgs a) {
+  pdl_trigger();  // the target propagation launched behind this kernel does not depend on it
   if ((int)blockIdx.x < a.nb_sens) {
     if (blockIdx.x == 0 && threadIdx.x == 0 && a.clock) {
       a.clock->t_cur = a.clock->t_now;
@@ -300,10 +302,8 @@ cudaError_t launch_obs_pack(const double* sens_x, int64_t M, int64_t ld_s, const
                             float* out_eci, float* out_cov, float* out_stale, cudaStream_t s) {
   const int64_t total = 6 * (M + N) + 36 * N + N;
   if (total <= 0) return cudaSuccess;
-  obs_pack_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(
-      sens_x, M, ld_s, est_x, est_p, N, ld, last_time_tasked, t_now, clock, out_eci, out_cov,
-      out_stale);
-  return cudaGetLastError();
+  return launch_pdl(obs_pack_kernel, dim3((unsigned)((total + 255) / 256)), dim3(256), 0, s, true, sens_x, M, ld_s,
+                    est_x, est_p, N, ld, last_time_tasked, t_now, clock, out_eci, out_cov, out_stale);
 }
 
 }  // namespace pc

@@ -72,6 +72,13 @@ propagate_sigma_kernel(double* __restrict__ sb, int64_t n, int64_t ld, double dt
   __shared__ uint16_t s_perm[kPropThreads];
   __shared__ int s_nsub[kPropThreads];
   const int tid = threadIdx.x;
+  // Programmatic dependent launch: this kernel needs nothing from its stream predecessor (the
+  // sensor / tasking kernel), so it runs beside it; its successor (the per-target stage) may be
+  // scheduled as soon as every CTA of this grid is resident.  One thread of the grid does wait for
+  // the predecessor, so that "this grid is done" implies "the sensor kernel is done" for the
+  // successor, which needs both.
+  pdl_trigger();
+  if (blockIdx.x == 0 && blockIdx.y == 0 && tid == 0) pdl_wait();
   const int64_t t0 = (int64_t)blockIdx.x * kPropThreads;
   const int i = blockIdx.y;
   double* blk = sb + (int64_t)i * 6 * ld;
@@ -136,14 +143,14 @@ propagate_sigma_kernel(double* __restrict__ sb, int64_t n, int64_t ld, double dt
 
 cudaError_t launch_propagate_sigma(double* sb, int64_t n, int64_t ld, int have_truth, double t0,
                                    double tf, int substeps, int force_model, uint32_t* sig_flags,
-                                   cudaStream_t stream) {
+                                   bool beside_predecessor, cudaStream_t stream) {
   if (n <= 0) return cudaSuccess;
   const dim3 grid((unsigned)((n + kPropThreads - 1) / kPropThreads), have_truth ? 14 : 13);
   if (force_model == PC_FORCE_TWOBODY_J2)
-    propagate_sigma_kernel<true><<<grid, kPropThreads, 0, stream>>>(sb, n, ld, tf - t0, substeps, sig_flags);
-  else
-    propagate_sigma_kernel<false><<<grid, kPropThreads, 0, stream>>>(sb, n, ld, tf - t0, substeps, sig_flags);
-  return cudaGetLastError();
+    return launch_pdl(propagate_sigma_kernel<true>, grid, dim3(kPropThreads), 0, stream, beside_predecessor, sb, n,
+                      ld, tf - t0, substeps, sig_flags);
+  return launch_pdl(propagate_sigma_kernel<false>, grid, dim3(kPropThreads), 0, stream, beside_predecessor, sb, n, ld,
+                    tf - t0, substeps, sig_flags);
 }
 
 // ---- frame transforms / initial-condition generation (transforms.py:34-292) -----------

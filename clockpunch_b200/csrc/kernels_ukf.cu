@@ -627,6 +627,8 @@ template <int TPB>
 __global__ void __launch_bounds__(TPB, TPB == 128 ? 3 : (TPB == 64 ? 6 : 8))
 ukf_finish_kernel(const __grid_constant__ UkfArgs a) {
   extern __shared__ __align__(32) double smem[];
+  pdl_wait();  // launched programmatically behind the propagation kernel: everything below reads its output
+  pdl_trigger();  // a programmatic successor (the observation pack) may be scheduled behind our last wave
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   double* stage = smem + warp * kStageDoubles;
   double4* tile = reinterpret_cast<double4*>(smem + (TPB / 32) * kStageDoubles);
@@ -875,6 +877,8 @@ ukf_finish_quad_kernel(const __grid_constant__ UkfArgs a) {
   __shared__ __align__(32) double4 tile[kVisTileSlots];
   __shared__ uint64_t mbar_store;
   uint64_t* mbar = &mbar_store;
+  pdl_wait();  // launched programmatically behind the propagation kernel: everything below reads its output
+  pdl_trigger();  // a programmatic successor (the observation pack) may be scheduled behind our last wave
   const int q = threadIdx.x & 3;
   const int64_t t = ((int64_t)blockIdx.x * kQuadThreads + threadIdx.x) >> 2;
   if (a.clock && a.advance_clock && blockIdx.x == 0 && threadIdx.x == 0) {
@@ -1110,8 +1114,7 @@ ukf_finish_quad_kernel(const __grid_constant__ UkfArgs a) {
 template <int TPB>
 static cudaError_t launch_finish_tpb(const UkfArgs& a, cudaStream_t stream) {
   const size_t smem = (size_t)(TPB / 32) * kStageDoubles * sizeof(double) + kVisTileSlots * sizeof(double4) + 16;
-  ukf_finish_kernel<TPB><<<(unsigned)((a.n + TPB - 1) / TPB), TPB, smem, stream>>>(a);
-  return cudaGetLastError();
+  return launch_pdl(ukf_finish_kernel<TPB>, dim3((unsigned)((a.n + TPB - 1) / TPB)), dim3(TPB), smem, stream, true, a);
 }
 
 // Small catalogs cannot fill the machine with one thread per target: they take the quad kernel
@@ -1120,8 +1123,8 @@ static cudaError_t launch_finish_tpb(const UkfArgs& a, cudaStream_t stream) {
 cudaError_t launch_ukf_finish(const UkfArgs& a, cudaStream_t stream) {
   if (a.n <= 0) return cudaSuccess;
   if (a.n <= kQuadMaxTargets) {
-    ukf_finish_quad_kernel<<<(unsigned)((4 * a.n + kQuadThreads - 1) / kQuadThreads), kQuadThreads, 0, stream>>>(a);
-    return cudaGetLastError();
+    return launch_pdl(ukf_finish_quad_kernel, dim3((unsigned)((4 * a.n + kQuadThreads - 1) / kQuadThreads)),
+                      dim3(kQuadThreads), 0, stream, true, a);
   }
   if (a.n <= 128 * 1024) return launch_finish_tpb<64>(a, stream);
   return launch_finish_tpb<128>(a, stream);

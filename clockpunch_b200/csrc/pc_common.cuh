@@ -37,6 +37,32 @@ struct UkfWeights {
 
 }  // namespace pc
 
+namespace pc {
+// Programmatic dependent launch (griddepcontrol): a kernel launched with the
+// programmatic-stream-serialization attribute may start while its stream predecessor is still
+// running; it must call pdl_wait() before touching anything the predecessor produces.  A kernel
+// calls pdl_trigger() to let its successor's CTAs be scheduled as soon as all of its own are
+// resident.  Both are no-ops for ordinary launches.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem,
+                              cudaStream_t stream, bool programmatic, Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = programmatic ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+}
+}  // namespace pc
+
 #define PC_CUDA_TRY(ctx, expr)                                        \
   do {                                                                \
     cudaError_t _e = (expr);                                          \

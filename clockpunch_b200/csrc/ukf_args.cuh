@@ -46,7 +46,7 @@ cudaError_t launch_sigma_gen(const double* est_x, const double* est_p, const dou
                              cudaStream_t stream);
 cudaError_t launch_propagate_sigma(double* sb, int64_t n, int64_t ld, int have_truth, double t0,
                                    double tf, int substeps, int force_model, uint32_t* sig_flags,
-                                   cudaStream_t stream);
+                                   bool beside_predecessor, cudaStream_t stream);
 cudaError_t launch_ukf_finish(const UkfArgs& a, cudaStream_t stream);
 
 }  // namespace pc

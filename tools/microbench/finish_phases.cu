@@ -17,7 +17,7 @@ __device__ long long g_stamp[16][2048];
 int pc_fail(pc_ctx*, int c, const char*) { return c; }
 int pc_fail_cuda(pc_ctx*, cudaError_t, const char*) { return -2; }
 namespace pc {
-cudaError_t launch_propagate_sigma(double*, int64_t, int64_t, int, double, double, int, int, uint32_t*, cudaStream_t) { return cudaSuccess; }
+cudaError_t launch_propagate_sigma(double*, int64_t, int64_t, int, double, double, int, int, uint32_t*, bool, cudaStream_t) { return cudaSuccess; }
 }
 using namespace pc;
 
