@@ -160,6 +160,18 @@ def run_reference(args):
 
 # ----------------------------------------------------------------------------- own arm
 def run_own(args):
+    # stdout carries exactly one JSON line: anything libraries print while we work (NCCL prints its
+    # version banner to fd 1) is routed to stderr, and fd 1 is restored for the final print
+    sys.stdout.flush()
+    saved_stdout = os.dup(1)
+    os.dup2(2, 1)
+
+    def emit(line):
+        sys.stdout.flush()
+        os.dup2(saved_stdout, 1)
+        print(json.dumps(line))
+        sys.stdout.flush()
+
     import torch
     import torch.distributed as dist
     from clockpunch_b200 import _lib
@@ -174,8 +186,6 @@ def run_own(args):
         raise SystemExit("bench.py needs a CUDA device (no CPU fallback); use --impl reference for the CPU arm")
     torch.cuda.set_device(local)
     if world > 1:
-        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
-            os.environ["NCCL_DEBUG"] = "WARN"       # keep stdout to the one JSON line
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     dev = torch.device("cuda", local)
 
@@ -406,7 +416,7 @@ def run_own(args):
             "extra": {"tasked_per_step": tasked_total / total_steps, "flagged_targets": flags_bad,
                       "wall_s_timed_region": wall, "launches_per_step": launches / args.steps, "cuda_graph": True,
                       "target_propagation_steps_per_s": 14 * value}}
-    print(json.dumps(line))
+    emit(line)
     leave()
 
 
