@@ -351,11 +351,14 @@ def run_own(args):
     h_vis_np = hb["vis_est"].numpy().view(np.uint32)
     h_act_np = hb["actions"].numpy()
 
+    flat_tab = probe_tab * eng.wpr + jw                # word index of every probe (same random table)
+    bit = (np.uint32(1) << jb)
+    h_vis_flat = h_vis_np.reshape(-1)
+
     def host_policy(k):
-        probes = probe_tab[k]
-        hit = (h_vis_np[probes, jw] >> jb) & 1
+        hit = (h_vis_flat.take(flat_tab[k]) & bit) != 0          # (M, 64): probe sees its target?
         first = hit.argmax(axis=1)
-        h_act_np[:M] = np.where(hit[rows, first] != 0, probes[rows, first], N)
+        h_act_np[:M] = np.where(hit[rows, first], probe_tab[k][rows, first], N)
 
     def e2e_step(k):
         host_policy(k)

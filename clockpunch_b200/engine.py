@@ -102,6 +102,7 @@ class CatalogEngine:
         self.clock = torch.zeros((32,), dtype=torch.uint8, device=dev)
         self._graph = None
         self._hs_dt = None
+        self._hs_key = None
         self._hs_io = _lib.StepIO()
         self._sync_clock()
         self.compute_vis()
@@ -139,6 +140,7 @@ class CatalogEngine:
     def _fill_args(self, t0, tf, z, tasked, want_vis=True, use_clock=False, actions=None, policy_probes=0,
                    policy_seed=0):
         a = self._args
+        self._hs_key = None          # the cached step_host call points at this block
         a.sens_x, a.sens_kind, a.M, a.ld_s = self.sens_x.data_ptr(), self.sens_kind.data_ptr(), self.M, self.ld_s
         a.truth_x, a.est_x, a.est_p = self.truth_x.data_ptr(), self.est_x.data_ptr(), self.est_p.data_ptr()
         a.z = None if z is None else z.data_ptr()
@@ -303,22 +305,31 @@ class CatalogEngine:
         to the device, runs the step (a CUDA graph inside the library after the first call),
         packs the float32 observation and copies it, the packed estimated vis map and num_tasked
         into hb.  One C call per step; returns when the host buffers are filled."""
-        self.ensure_sigma()
-        if self._hs_dt != dt:
-            self.tasked.zero_()
-            self._sync_clock()
-            self._hs_dt = dt
-            self.torch.cuda.current_stream(self.dev).synchronize()
-        a = self._fill_args(0.0, float(dt), None, self.tasked, use_clock=True, actions=self.actions,
+        key = (float(dt), int(policy_probes), int(policy_seed), id(hb), self._sigma_valid)
+        if self._hs_key != key:
+            # (re)build the argument blocks once; steady-state steps below are one C call
+            self.ensure_sigma()
+            if self._hs_dt != dt:
+                self.tasked.zero_()
+                self._sync_clock()
+                self._hs_dt = dt
+                self.torch.cuda.current_stream(self.dev).synchronize()
+            self._fill_args(0.0, float(dt), None, self.tasked, use_clock=True, actions=self.actions,
                             policy_probes=policy_probes, policy_seed=policy_seed)
-        io = self._hs_io
-        io.h_actions = hb["actions"].data_ptr() if policy_probes == 0 else None
-        io.d_obs, io.h_obs = self.obs_f32.data_ptr(), hb["obs"].data_ptr()
-        io.h_vis_est, io.h_num_tasked = hb["vis_est"].data_ptr(), hb["num_tasked"].data_ptr()
-        if "block" in hb:      # obs | summary in one device block -> one D2H copy
-            io.d_block, io.h_block, io.block_bytes = self.out_block.data_ptr(), hb["block"].data_ptr(), self.out_block.numel()
-        c = self.ctx
-        c.check(c.lib.pc_step_host(c.handle, C.byref(a), C.byref(self.params), C.byref(io), self._stream()))
+            io = self._hs_io
+            io.h_actions = hb["actions"].data_ptr() if policy_probes == 0 else None
+            io.d_obs, io.h_obs = self.obs_f32.data_ptr(), hb["obs"].data_ptr()
+            io.h_vis_est, io.h_num_tasked = hb["vis_est"].data_ptr(), hb["num_tasked"].data_ptr()
+            if "block" in hb:      # obs | summary in one device block -> one D2H copy
+                io.d_block, io.h_block, io.block_bytes = (self.out_block.data_ptr(), hb["block"].data_ptr(),
+                                                          self.out_block.numel())
+            self._hs_call = (self.ctx.lib.pc_step_host, self.ctx.handle, C.byref(self._args), C.byref(self.params),
+                             C.byref(io), self._stream())
+            self._hs_key = (float(dt), int(policy_probes), int(policy_seed), id(hb), True)
+        f, *cargs = self._hs_call
+        rc = f(*cargs)
+        if rc:
+            self.ctx.check(rc)
         self.time += float(dt)
         self.step_count += 1
 
@@ -370,7 +381,7 @@ class CatalogEngine:
         new.summary = new.out_block[new._obs_bytes:]
         new._bind_summary_views()
         new._args, new._hs_io = _lib.StepArgs(), _lib.StepIO()
-        new._graph, new._hs_dt = None, None
+        new._graph, new._hs_dt, new._hs_key = None, None, None
         bufs, t, sc, sv = self._snapshot
         new._snapshot = ({k: v.clone() for k, v in bufs.items()}, t, sc, sv)
         new._sync_clock()
