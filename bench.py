@@ -243,11 +243,24 @@ def run_own(args):
     # per-step summaries every rank needs from every other: packed est vis map,
     # trace(P_pos), trace(P_vel), last_time_tasked, num_tasked -- all-gathered straight out of the
     # buffers the kernels write (equal shards: no staging copy)
-    sg = None
+    # Exchange: by default the per-target kernel itself stores every summary into all peers'
+    # gathered buffers over NVLink (peer-mapped symmetric memory) and the step ends with a flag wait;
+    # --exchange nccl uses one all-gather of the summary buffer captured into the step's graph.
+    sg, exchange = None, "none"
     if world > 1:
         from clockpunch_b200.sharding import PackedGather
         sg = PackedGather(world, rank, eng.summary, N, eng.wpr)
-    gather_in_graph = sg is not None and not args.eager_gather
+        exchange = "nccl all_gather_into_tensor" + ("" if args.eager_gather else " (captured in the step graph)")
+        # measured on 8 GPUs: peer stores win while the step is latency-bound (10 000 targets per GPU:
+        # 61 vs 79 us per step), the bulk all-gather wins once a shard pushes megabytes (125 000: 0.28 vs 0.31 ms)
+        if args.exchange == "peer" or (args.exchange == "auto" and N <= 32768):
+            try:
+                eng.enable_peer_push()
+                exchange = "peer stores from the per-target kernel (symmetric memory over NVLink) + flag wait"
+            except Exception as exc:        # no symmetric memory on this box: keep the collective
+                print(f"peer push unavailable ({exc!r}); using NCCL", file=sys.stderr)
+    use_nccl = sg is not None and eng._peer is None
+    gather_in_graph = use_nccl and not args.eager_gather
     post = sg.gather if gather_in_graph else None
 
     # policy -> tasking mask -> sensors -> truth + UKF -> vis maps [-> all-gather], captured once,
@@ -256,7 +269,7 @@ def run_own(args):
 
     def device_step():
         eng.replay(g_value)
-        if sg is not None and not gather_in_graph:
+        if use_nccl and not gather_in_graph:
             sg.gather()
 
     def barrier():
@@ -272,6 +285,14 @@ def run_own(args):
     g_value = eng.build_graph(DT, policy_probes=64, policy_seed=SEED, post=post)
     for k in range(args.warmup):
         device_step()
+    if eng._peer is not None:
+        # check the pushed copies once against a plain all-gather of the same buffers (untimed)
+        ref = sg.gather().clone()
+        err, pushes = eng.peer_status()
+        got = eng._peer["gathered"][pushes & 1]
+        dist.barrier()
+        if err or not torch.equal(got, ref):
+            raise SystemExit(f"rank {rank}: peer-pushed summaries differ from the all-gather (error mask {err:#x})")
     peak_tf = C.c_double()
     ctx.check(lib.pc_fp64_peak(ctx.handle, 5, C.byref(peak_tf)))
     evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
@@ -315,7 +336,7 @@ def run_own(args):
 
     def timed_step():
         eng.step_policy_eager(DT, 64, SEED)         # same kernels, launched one by one: plain event records
-        if sg is not None:
+        if use_nccl:
             sg.gather()
 
     for k in range(args.warmup):
@@ -409,7 +430,7 @@ def run_own(args):
     def e2e_step(k):
         host_policy(k)
         eng.step_host(hb, DT)
-        if world > 1:
+        if use_nccl:
             sg.gather()
             torch.cuda.current_stream(dev).synchronize()
 
@@ -471,6 +492,7 @@ def run_own(args):
             "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu, "clocks": clocks,
             "extra": {"tasked_per_step": tasked_total / total_steps, "flagged_targets": flags_bad,
                       "wall_s_timed_region": wall, "launches_per_step": launches / args.steps, "cuda_graph": True,
+                      "exchange": exchange,
                       "target_propagation_steps_per_s": 14 * value}}
     emit(line)
     leave()
@@ -489,6 +511,8 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--l2", default="flush", choices=["flush", "none"])
     ap.add_argument("--eager-gather", action="store_true", help="N > 1: all-gather outside the step's CUDA graph")
+    ap.add_argument("--exchange", default="auto", choices=["auto", "peer", "nccl"],
+                    help="N > 1: summaries pushed into peers' memory by the step kernel, or one NCCL all-gather")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "own" else args.warmup
     if args.impl == "reference":

@@ -46,6 +46,8 @@ class StepArgs(C.Structure):
         ("actions", C.c_void_p), ("policy_probes", C.c_int), ("sigma_valid", C.c_int),
         ("policy_seed", C.c_uint64), ("sigma_ws", C.c_void_p), ("sig_flags", C.c_void_p),
         ("sens_q", C.c_void_p), ("env_targets", C.c_int64), ("env_sensors", C.c_int64),
+        ("peer_table", C.c_void_p), ("peer_world", C.c_int32), ("peer_rank", C.c_int32),
+        ("summary_base", C.c_void_p), ("summary_bytes", C.c_int64),
     ]
 
 
@@ -93,6 +95,7 @@ _SIGNATURES = {
     "pc_get_timing": ([_vp, C.POINTER(_dbl)], _int),
     "pc_fp64_peak": ([_vp, _int, C.POINTER(_dbl)], _int),
     "pc_step_fused": ([_vp, C.POINTER(StepArgs), C.POINTER(UkfParams), _vp], _int),
+    "pc_peer_status": ([_vp, C.POINTER(C.c_uint32), C.POINTER(C.c_uint64)], _int),
     "pc_step_host": ([_vp, C.POINTER(StepArgs), C.POINTER(UkfParams), C.POINTER(StepIO), _vp], _int),
 }
 EXPORTED_SYMBOLS = tuple(_SIGNATURES)

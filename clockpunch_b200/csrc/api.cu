@@ -66,6 +66,8 @@ struct pc_ctx {
   // pc_step_args.sens_q (not graph-capture safe)
   double* sq = nullptr;
   size_t sq_sensors = 0;
+  // peer push: "last CTA done" ticket and the wait kernel's error mask (device), see PeerPush
+  unsigned int* peer_dev = nullptr;   // [0] ticket, [1] error mask, [2..3] 64-bit push sequence number
   // pc_step_host: the captured step (pc_step_fused + pc_obs_pack) and the arguments it was
   // captured with; replayed while the caller keeps passing the same buffers
   cudaGraphExec_t hs_exec = nullptr;
@@ -160,6 +162,11 @@ int pc_ctx_create(int device_ordinal, pc_ctx** out) {
     delete ctx;
     return PC_ERR_CUDA;
   }
+  if (cudaMalloc(&ctx->peer_dev, 4 * sizeof(unsigned int)) != cudaSuccess ||
+      cudaMemset(ctx->peer_dev, 0, 4 * sizeof(unsigned int)) != cudaSuccess) {
+    delete ctx;
+    return PC_ERR_CUDA;
+  }
   *out = ctx;
   return PC_OK;
 }
@@ -173,6 +180,7 @@ int pc_ctx_destroy(pc_ctx* ctx) {
     if (ctx->sbf) cudaFree(ctx->sbf);
     if (ctx->host_stream) cudaStreamDestroy(ctx->host_stream);
     if (ctx->sq) cudaFree(ctx->sq);
+    if (ctx->peer_dev) cudaFree(ctx->peer_dev);
     if (ctx->ev0) cudaEventDestroy(ctx->ev0);
     if (ctx->ev1) cudaEventDestroy(ctx->ev1);
     if (ctx->hs_exec) cudaGraphExecDestroy(ctx->hs_exec);
@@ -742,6 +750,18 @@ int pc_step_fused(pc_ctx* ctx, const pc_step_args* a, const pc_ukf_params* param
   PC_REQUIRE(ctx, !a->actions || (a->tasked && (a->vis_est || a->M == 0)),
              "actions need a tasked workspace and the estimated vis map");
   PC_REQUIRE(ctx, a->policy_probes >= 0 && a->policy_probes <= 4096, "bad policy_probes");
+  if (a->peer_table) {
+    PC_REQUIRE(ctx, a->peer_world >= 1 && a->peer_world <= 64 && a->peer_rank >= 0 && a->peer_rank < a->peer_world,
+               "bad peer_world / peer_rank");
+    PC_REQUIRE(ctx, a->summary_base && a->summary_bytes > 0 && a->num_tasked && a->vis_est && a->tr_pos &&
+                        a->tr_vel && a->last_time_tasked,
+               "peer push needs the summary buffer and all five summary arrays");
+    const char* b0 = static_cast<const char*>(a->summary_base);
+    const char* b1 = b0 + a->summary_bytes;
+    const char* f[5] = {(const char*)a->num_tasked, (const char*)a->vis_est, (const char*)a->tr_pos,
+                        (const char*)a->tr_vel, (const char*)a->last_time_tasked};
+    for (const char* q : f) PC_REQUIRE(ctx, q >= b0 && q < b1, "summary arrays must lie inside summary_base");
+  }
   const bool own_sb = a->sigma_ws != nullptr;
   if (own_sb && a->N > 0) {
     PC_REQUIRE(ctx, a->sig_flags != nullptr, "sigma_ws needs sig_flags");
@@ -833,13 +853,44 @@ int pc_step_fused(pc_ctx* ctx, const pc_step_args* a, const pc_ukf_params* param
       u.body_radius = a->body_radius;
       u.vis_tol = a->vis_tol;
     }
+    if (a->peer_table) {
+      const char* base = static_cast<const char*>(a->summary_base);
+      u.pp.world = a->peer_world;
+      u.pp.rank = a->peer_rank;
+      u.pp.table = a->peer_table;
+      u.pp.slot_bytes = a->summary_bytes;
+      u.pp.off_num_tasked = reinterpret_cast<const char*>(a->num_tasked) - base;
+      u.pp.off_vis_est = reinterpret_cast<const char*>(a->vis_est) - base;
+      u.pp.off_tr_pos = reinterpret_cast<const char*>(a->tr_pos) - base;
+      u.pp.off_tr_vel = reinterpret_cast<const char*>(a->tr_vel) - base;
+      u.pp.off_ltt = reinterpret_cast<const char*>(a->last_time_tasked) - base;
+      u.pp.ticket = ctx->peer_dev;
+      u.pp.seq = reinterpret_cast<unsigned long long*>(ctx->peer_dev + 2);
+    }
     u.p = *params;
     PC_CUDA_TRY(ctx, pc::launch_ukf_finish(u, s));
     ctx->launches += 2;
+    if (a->peer_table) {
+      PC_CUDA_TRY(ctx, pc::launch_peer_wait(a->peer_table, a->peer_world, a->peer_rank,
+                                            reinterpret_cast<const unsigned long long*>(ctx->peer_dev + 2),
+                                            ctx->peer_dev + 1, s));
+      ctx->launches += 1;
+    }
   } else if (a->clock) {
     PC_CUDA_TRY(ctx, pc::launch_advance_clock(a->clock, a->tf - a->t0, s));
     ctx->launches += 1;
   }
+  return PC_OK;
+}
+
+int pc_peer_status(pc_ctx* ctx, uint32_t* out_error_mask, uint64_t* out_pushes) {
+  PC_REQUIRE(ctx, ctx != nullptr && out_error_mask && out_pushes, "null pointer");
+  DeviceGuard g(ctx->device);
+  unsigned int v[4] = {0, 0, 0, 0};
+  PC_CUDA_TRY(ctx, cudaMemcpy(v, ctx->peer_dev, sizeof(v), cudaMemcpyDeviceToHost));
+  PC_CUDA_TRY(ctx, cudaMemset(ctx->peer_dev + 1, 0, sizeof(unsigned int)));
+  *out_error_mask = v[1];
+  *out_pushes = (uint64_t)v[2] | ((uint64_t)v[3] << 32);
   return PC_OK;
 }
 

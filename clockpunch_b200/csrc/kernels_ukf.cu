@@ -619,6 +619,52 @@ __device__ __forceinline__ void vis_word(const double4* __restrict__ row, const 
   }
 }
 
+// ---- peer push helpers (see PeerPush in ukf_args.cuh) ---------------------------------------------
+template <typename T>
+__device__ __forceinline__ void peer_store(const PeerPush& pp, int parity, int64_t field_off, int64_t idx, T v) {
+  const int64_t off = ((int64_t)parity * pp.world + pp.rank) * pp.slot_bytes + field_off + idx * (int64_t)sizeof(T);
+  for (int r = 0; r < pp.world; ++r)
+    *reinterpret_cast<T*>(__ldg(pp.table + r) + off) = v;
+}
+
+// Called by every thread at the end of the kernel: make this CTA's remote stores visible system
+// wide, and let the last CTA of the grid publish `step` in every peer's flag array.
+__device__ __forceinline__ void peer_publish(const PeerPush& pp, uint64_t step) {
+  __threadfence_system();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const unsigned int done = atomicAdd(pp.ticket, 1u);
+    if (done == gridDim.x - 1) {
+      *pp.ticket = 0;                   // ready for the next launch (everybody else has already arrived)
+      *pp.seq = step;
+      __threadfence_system();
+      for (int r = 0; r < pp.world; ++r)
+        *reinterpret_cast<volatile uint64_t*>(__ldg(pp.table + pp.world + r) + 8 * (uint64_t)pp.rank) = step;
+    }
+  }
+}
+
+// One small CTA: hold the stream until every peer has published `step` (bounded spin: a lost peer
+// raises *err instead of hanging the GPU).
+__global__ void peer_wait_kernel(const uint64_t* __restrict__ table, int world, int rank,
+                                 const unsigned long long* __restrict__ seq, unsigned int* __restrict__ err) {
+  pdl_wait();
+  const int r = threadIdx.x;
+  if (r >= world) return;
+  const uint64_t want = *reinterpret_cast<const volatile unsigned long long*>(seq);   // pushes completed, this one included
+  const volatile uint64_t* flag = reinterpret_cast<const volatile uint64_t*>(__ldg(table + world + rank)) + r;
+  for (int spin = 0; spin < (1 << 22); ++spin) {
+    if (*flag >= want) return;
+    __nanosleep(100);
+  }
+  atomicOr(err, 1u << r);
+}
+
+cudaError_t launch_peer_wait(const uint64_t* table, int world, int rank, const unsigned long long* seq,
+                             unsigned int* err, cudaStream_t stream) {
+  return launch_pdl(peer_wait_kernel, dim3(1), dim3(64), 0, stream, true, table, world, rank, seq, err);
+}
+
 // Stage 3 of the step, one THREAD per target: unscented transform, measurement update, outputs,
 // next step's sigma points and -- fused, because the new estimate and the truth position are in
 // registers and the kernel is otherwise HBM-latency bound -- the target's row of BOTH visibility
@@ -641,6 +687,9 @@ ukf_finish_kernel(const __grid_constant__ UkfArgs a) {
   }
   const bool live = t < a.n;
   const int64_t tc = live ? t : a.n - 1;  // dead lanes shadow the last target and store nothing
+  // sequence number of this push (counts launches, survives engine resets) and the slot it goes to
+  const uint64_t step_done = a.pp.world ? *reinterpret_cast<const volatile unsigned long long*>(a.pp.seq) + 1 : 0;
+  const int parity = (int)(step_done & 1);
   const int64_t warp_t0 = t - lane;
   const int64_t ld = a.ld, blk = 6 * a.ld;
   const double* __restrict__ sb = a.sb;
@@ -782,8 +831,16 @@ ukf_finish_kernel(const __grid_constant__ UkfArgs a) {
     if (a.out_flags) a.out_flags[t] = flags;
     if (a.out_nis) a.out_nis[t] = nis;
     // scheduler summaries (env.py:599-609: traces of the float32 est_cov blocks)
-    if (a.tr_pos) a.tr_pos[t] = ((float)PE[uidx(0, 0)] + (float)PE[uidx(1, 1)]) + (float)PE[uidx(2, 2)];
-    if (a.tr_vel) a.tr_vel[t] = ((float)PE[uidx(3, 3)] + (float)PE[uidx(4, 4)]) + (float)PE[uidx(5, 5)];
+    const float trp = ((float)PE[uidx(0, 0)] + (float)PE[uidx(1, 1)]) + (float)PE[uidx(2, 2)];
+    const float trv = ((float)PE[uidx(3, 3)] + (float)PE[uidx(4, 4)]) + (float)PE[uidx(5, 5)];
+    if (a.tr_pos) a.tr_pos[t] = trp;
+    if (a.tr_vel) a.tr_vel[t] = trv;
+    if (a.pp.world) {
+      peer_store(a.pp, parity, a.pp.off_tr_pos, t, trp);
+      peer_store(a.pp, parity, a.pp.off_tr_vel, t, trv);
+      peer_store(a.pp, parity, a.pp.off_num_tasked, t, a.num_tasked[t]);
+      peer_store(a.pp, parity, a.pp.off_ltt, t, a.last_time_tasked[t]);
+    }
     if (a.out_pred_x) {
 #pragma unroll
       for (int c = 0; c < 6; ++c) a.out_pred_x[(int64_t)c * ld + t] = px[c];
@@ -830,11 +887,13 @@ ukf_finish_kernel(const __grid_constant__ UkfArgs a) {
           if (live) {
             a.vis_truth[t * wpr + w] = wa;
             a.vis_est[t * wpr + w] = wb;
+            if (a.pp.world) peer_store(a.pp, parity, a.pp.off_vis_est, t * wpr + w, wb);
           }
         }
       }
     }
   }
+  if (a.pp.world) peer_publish(a.pp, step_done);
 }
 
 cudaError_t launch_sigma_gen(const double* est_x, const double* est_p, const double* truth_x, double* sb,
@@ -888,6 +947,9 @@ ukf_finish_quad_kernel(const __grid_constant__ UkfArgs a) {
   PC_PHASE_CLOCK(0);
   const bool live = t < a.n;
   const int64_t tc = live ? t : a.n - 1;
+  // sequence number of this push (counts launches, survives engine resets) and the slot it goes to
+  const uint64_t step_done = a.pp.world ? *reinterpret_cast<const volatile unsigned long long*>(a.pp.seq) + 1 : 0;
+  const int parity = (int)(step_done & 1);
   const int64_t ld = a.ld, blk = 6 * a.ld;
   const double* __restrict__ sb = a.sb;
   const bool vis = a.vis_truth != nullptr;
@@ -1028,8 +1090,14 @@ ukf_finish_quad_kernel(const __grid_constant__ UkfArgs a) {
     if (q == 1) {
       if (a.out_flags) a.out_flags[t] = flags;
       if (a.out_nis) a.out_nis[t] = nis;
-      if (a.tr_pos) a.tr_pos[t] = ((float)PE[uidx(0, 0)] + (float)PE[uidx(1, 1)]) + (float)PE[uidx(2, 2)];
-      if (a.tr_vel) a.tr_vel[t] = ((float)PE[uidx(3, 3)] + (float)PE[uidx(4, 4)]) + (float)PE[uidx(5, 5)];
+      const float trp = ((float)PE[uidx(0, 0)] + (float)PE[uidx(1, 1)]) + (float)PE[uidx(2, 2)];
+      const float trv = ((float)PE[uidx(3, 3)] + (float)PE[uidx(4, 4)]) + (float)PE[uidx(5, 5)];
+      if (a.tr_pos) a.tr_pos[t] = trp;
+      if (a.tr_vel) a.tr_vel[t] = trv;
+      if (a.pp.world) {
+        peer_store(a.pp, parity, a.pp.off_tr_pos, t, trp);
+        peer_store(a.pp, parity, a.pp.off_tr_vel, t, trv);
+      }
     }
     if (a.out_pred_x && q == 2) {
 #pragma unroll
@@ -1077,6 +1145,11 @@ ukf_finish_quad_kernel(const __grid_constant__ UkfArgs a) {
   }
 
   PC_PHASE_CLOCK(7);
+  if (a.pp.world && live && q == 0) {   // lane 0 of the quad did the tasking bookkeeping above
+    peer_store(a.pp, parity, a.pp.off_num_tasked, t, a.num_tasked[t]);
+    peer_store(a.pp, parity, a.pp.off_ltt, t, a.last_time_tasked[t]);
+  }
+
   // ---- visibility: lane q packs words q, q + 4, ... of both rows ---------------------------------
   if (vis) {
     const double RE2 = a.body_radius * a.body_radius;
@@ -1103,12 +1176,14 @@ ukf_finish_quad_kernel(const __grid_constant__ UkfArgs a) {
           if (live) {
             a.vis_truth[t * wpr + w] = wa;
             a.vis_est[t * wpr + w] = wb;
+            if (a.pp.world) peer_store(a.pp, parity, a.pp.off_vis_est, t * wpr + w, wb);
           }
         }
       }
     }
   }
   PC_PHASE_CLOCK(9);
+  if (a.pp.world) peer_publish(a.pp, step_done);
 }
 
 template <int TPB>

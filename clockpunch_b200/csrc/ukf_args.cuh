@@ -4,6 +4,22 @@
 
 namespace pc {
 
+// Multi-GPU exchange fused into the per-target stage: every per-target summary the other shards'
+// schedulers need (num_tasked, packed estimated vis words, covariance traces, last_time_tasked) is
+// stored, as it is produced, into the corresponding slot of EVERY peer's gathered buffer over
+// NVLink (peer-mapped symmetric memory), instead of into a local buffer that a collective then
+// ships.  Layout of a gathered buffer: [step parity][rank][slot_bytes], a slot being a copy of the
+// shard's summary buffer.  The last CTA of the grid publishes the step number in every peer's flag
+// array; peer_wait_kernel then holds the stream until all peers' flags have arrived.
+struct PeerPush {
+  int world, rank;             // world == 0: disabled
+  const uint64_t* table;       // device array: [0, world) gathered bases, [world, 2 world) flag bases
+  int64_t slot_bytes;
+  int64_t off_num_tasked, off_vis_est, off_tr_pos, off_tr_vel, off_ltt;   // field offsets inside a slot
+  unsigned int* ticket;        // device counter for "last CTA done"
+  unsigned long long* seq;     // pushes completed so far (never reset: engine resets must not rewind the flags)
+};
+
 struct UkfArgs {
   double* sb;              // sigma buffer: 14 blocks of (6, ld)
   double* est_p;           // (N, 36) out
@@ -38,6 +54,7 @@ struct UkfArgs {
   uint32_t* vis_truth;
   uint32_t* vis_est;
   double body_radius, vis_tol;
+  PeerPush pp;
   pc_ukf_params p;
 };
 
@@ -48,5 +65,7 @@ cudaError_t launch_propagate_sigma(double* sb, int64_t n, int64_t ld, int have_t
                                    double tf, int substeps, int force_model, uint32_t* sig_flags,
                                    bool beside_predecessor, cudaStream_t stream);
 cudaError_t launch_ukf_finish(const UkfArgs& a, cudaStream_t stream);
+cudaError_t launch_peer_wait(const uint64_t* table, int world, int rank, const unsigned long long* seq,
+                             unsigned int* err, cudaStream_t stream);
 
 }  // namespace pc

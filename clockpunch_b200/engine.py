@@ -103,6 +103,7 @@ class CatalogEngine:
         self._graph = None
         self._hs_dt = None
         self._hs_key = None
+        self._peer = None
         self._hs_io = _lib.StepIO()
         self._sync_clock()
         self.compute_vis()
@@ -160,6 +161,11 @@ class CatalogEngine:
         a.sigma_ws, a.sig_flags = self.sigma.data_ptr(), self.sig_flags.data_ptr()
         a.sens_q = self.sens_q.data_ptr()
         a.env_targets, a.env_sensors = (self.Ne, self.Me) if self.E > 1 else (0, 0)
+        if self._peer is not None:
+            a.peer_table, a.peer_world, a.peer_rank = self._peer["table"].data_ptr(), self._peer["world"], self._peer["rank"]
+            a.summary_base, a.summary_bytes = self.summary.data_ptr(), self.summary.numel()
+        else:
+            a.peer_table, a.peer_world, a.peer_rank, a.summary_base, a.summary_bytes = None, 0, 0, None, 0
         a.sigma_valid = 1 if self._sigma_valid else 0
         return a
 
@@ -263,6 +269,45 @@ class CatalogEngine:
         c.check(c.lib.pc_step_fused(c.handle, C.byref(a), C.byref(self.params), self._stream()))
         self.time += float(dt)
         self.step_count += 1
+
+    # -- multi-GPU: summaries pushed into every peer's gathered buffer by the step itself ----------
+    def enable_peer_push(self, group=None):
+        """Allocate peer-mapped (symmetric-memory) gathered buffers on every rank of `group` and make
+        every following step store its per-target summaries straight into all of them (NVLink
+        stores from the per-target kernel + a flag per rank), replacing the per-step all-gather.
+        All ranks must call this together, with equal shard sizes.  Returns the local gathered
+        tensor, shape (2, world, summary_bytes) uint8: [step parity][source rank]."""
+        import torch.distributed as dist
+        import torch.distributed._symmetric_memory as symm
+        torch = self.torch
+        group = group or dist.group.WORLD
+        world, rank = dist.get_world_size(group), dist.get_rank(group)
+        gathered = symm.empty((2, world, self.summary.numel()), dtype=torch.uint8, device=self.dev)
+        flags = symm.empty((world,), dtype=torch.int64, device=self.dev)
+        gathered.zero_()
+        flags.zero_()
+        hg = symm.rendezvous(gathered, group)
+        hf = symm.rendezvous(flags, group)
+        ptrs = [int(p) for p in hg.buffer_ptrs] + [int(p) for p in hf.buffer_ptrs]
+        table = torch.tensor(np.array(ptrs, dtype=np.uint64).view(np.int64), dtype=torch.int64, device=self.dev)
+        torch.cuda.synchronize(self.dev)
+        dist.barrier(group)
+        self._peer = {"table": table, "world": world, "rank": rank, "gathered": gathered, "flags": flags,
+                      "handles": (hg, hf)}
+        self._hs_key = None
+        return gathered
+
+    def peer_fields(self, parity: int, src_rank: int) -> dict:
+        """Typed views of what `src_rank` pushed for steps of the given parity."""
+        return self.summary_views(self._peer["gathered"][parity, src_rank], self.N, self.wpr)
+
+    def peer_status(self) -> tuple[int, int]:
+        """(error mask: bit r = peer r's flag never arrived within the bounded wait; pushes done so
+        far -- its parity is the slot of `gathered` holding the latest step).  Synchronises."""
+        err, n = C.c_uint32(0), C.c_uint64(0)
+        self.torch.cuda.synchronize(self.dev)
+        self.ctx.check(self.ctx.lib.pc_peer_status(self.ctx.handle, C.byref(err), C.byref(n)))
+        return err.value, n.value
 
     def ensure_sigma(self):
         """(Re)generate sigma-point blocks 1..12 from the current (est_x, est_p) if stale."""
@@ -381,7 +426,7 @@ class CatalogEngine:
         new.summary = new.out_block[new._obs_bytes:]
         new._bind_summary_views()
         new._args, new._hs_io = _lib.StepArgs(), _lib.StepIO()
-        new._graph, new._hs_dt, new._hs_key = None, None, None
+        new._graph, new._hs_dt, new._hs_key, new._peer = None, None, None, None
         bufs, t, sc, sv = self._snapshot
         new._snapshot = ({k: v.clone() for k, v in bufs.items()}, t, sc, sv)
         new._sync_clock()

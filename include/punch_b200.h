@@ -298,9 +298,26 @@ typedef struct pc_step_args {
    * ceil(env_sensors / 32), and actions[j] is LOCAL to the environment of sensor j (0 ..
    * env_targets, env_targets = inaction).  Both 0: one environment (N targets, M sensors). */
   int64_t env_targets, env_sensors;
+  /* Multi-GPU exchange fused into the step (one process per GPU, targets partitioned, SURVEY.md
+   * section 8e).  peer_table is a DEVICE array of 2 * peer_world pointers: first the base address of every
+   * rank's gathered buffer, then of every rank's flag array (peer_world uint64), all peer-mapped
+   * (e.g. torch symmetric memory over NVLink).  A gathered buffer is [2][peer_world][summary_bytes]:
+   * parity of the step, source rank, a copy of that rank's summary buffer.  summary_base /
+   * summary_bytes describe the local buffer that contains num_tasked, vis_est, tr_pos, tr_vel and
+   * last_time_tasked (all five must point into it).  With peer_table != NULL the per-target kernel
+   * stores every summary value into the slot of this rank in EVERY peer's gathered buffer as it
+   * produces it, its last CTA publishes the step number in every peer's flag array, and the step ends
+   * with a kernel that waits (bounded) until all peers' flags for this step have arrived: no
+   * collective call.  pc_peer_status reports (and clears) a bit per peer whose flag never came, and the
+   * number of pushes done so far (its parity is the slot that holds the latest data). */
+  const uint64_t* peer_table;
+  int32_t peer_world, peer_rank;
+  const void* summary_base;
+  int64_t summary_bytes;
 } pc_step_args;
 int pc_step_fused(pc_ctx* ctx, const pc_step_args* args, const pc_ukf_params* params,
                   pc_stream stream);
+int pc_peer_status(pc_ctx* ctx, uint32_t* out_error_mask, uint64_t* out_pushes);
 
 /* ---- the step as the reference's caller sees it: host actions in, host observation out -------
  * Replaces one SSAScheduler.step(action) (env.py:533-597) for the whole catalog: copies the M

@@ -96,3 +96,22 @@ def test_step_gather_gloo_world2(tmp_path, n_total):
     world = 2
     mp.spawn(_worker, args=(world, _free_port(), n_total, 100, str(tmp_path)), nprocs=world, join=True)
     assert all((tmp_path / f"ok{r}").exists() for r in range(world))
+
+
+def test_peer_push_layout_matches_summary_views():
+    """The gathered buffer written by the peer-push path is [parity][rank][summary bytes]; its
+    slots are read with the same field views as a local summary buffer (host-side check of the
+    offsets pc_step_fused derives from the five summary pointers)."""
+    import torch
+    from clockpunch_b200.engine import CatalogEngine
+    n, wpr, world = 40, 4, 3
+    nbytes = n * (8 + 4 * wpr + 12)
+    gathered = torch.zeros((2, world, nbytes), dtype=torch.uint8)
+    base = gathered[1, 2]
+    v = CatalogEngine.summary_views(base, n, wpr)
+    offs = {k: t.data_ptr() - base.data_ptr() for k, t in v.items()}
+    assert offs == {"num_tasked": 0, "vis_est": 8 * n, "tr_pos": 8 * n + 4 * wpr * n,
+                    "tr_vel": 8 * n + 4 * wpr * n + 4 * n, "last_time_tasked": 8 * n + 4 * wpr * n + 8 * n}
+    assert sum(t.numel() * t.element_size() for t in v.values()) == nbytes       # no padding: slots compare bytewise
+    v["vis_est"][7, 3] = 0x55
+    assert gathered[1, 2, 8 * n + 4 * (7 * wpr + 3)].item() == 0x55
