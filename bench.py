@@ -286,13 +286,23 @@ def run_own(args):
     for k in range(args.warmup):
         device_step()
     if eng._peer is not None:
-        # check the pushed copies once against a plain all-gather of the same buffers (untimed)
+        # check the pushed copies once against a plain all-gather of the same buffers (untimed); if any
+        # rank disagrees, every rank falls back to the NCCL exchange
         ref = sg.gather().clone()
         err, pushes = eng.peer_status()
-        got = eng._peer["gathered"][pushes & 1]
-        dist.barrier()
-        if err or not torch.equal(got, ref):
-            raise SystemExit(f"rank {rank}: peer-pushed summaries differ from the all-gather (error mask {err:#x})")
+        bad = torch.tensor([int(bool(err) or not torch.equal(eng._peer["gathered"][pushes & 1], ref))], device=dev)
+        dist.all_reduce(bad, op=dist.ReduceOp.MAX)
+        if int(bad.item()):
+            print(f"rank {rank}: peer-pushed summaries differ from the all-gather (error mask {err:#x}); "
+                  "falling back to NCCL", file=sys.stderr)
+            eng._peer, eng._hs_key = None, None
+            use_nccl, gather_in_graph = True, not args.eager_gather
+            post = sg.gather if gather_in_graph else None
+            exchange = "nccl all_gather_into_tensor (fallback: peer push failed its check)"
+            eng.reset()
+            g_value = eng.build_graph(DT, policy_probes=64, policy_seed=SEED, post=post)
+            for k in range(args.warmup):
+                device_step()
     peak_tf = C.c_double()
     ctx.check(lib.pc_fp64_peak(ctx.handle, 5, C.byref(peak_tf)))
     evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
