@@ -636,3 +636,53 @@ def test_peer_push_single_rank_matches_summary():
             seen.append(gathered[pushes & 1, 0].clone())
         assert not torch.equal(seen[0], seen[1])          # the two parity slots hold different steps
         assert eng.host("num_tasked").sum() > 0
+
+
+def test_guard_bands_no_out_of_bounds_writes():
+    """compute-sanitizer is closed on this pool, so out-of-bounds writes are hunted the old way: every
+    buffer the step kernels write is re-homed inside a larger allocation whose margins hold a
+    sentinel, the step runs (all kernels: sensors, propagation, per-target stage with update and
+    visibility, observation pack, standalone maps) at sizes that do not divide any tile, and the
+    margins must come back untouched."""
+    import torch
+    from clockpunch_b200.engine import CatalogEngine
+    from clockpunch_b200.simulation.catalog import synth_catalog
+    G = 96
+    for n, m in ((77, 45), (33_001, 70), (130, 300)):
+        cat = synth_catalog(n, m, seed=7 * n + m, space_sensor_frac=0.3)
+        eng = CatalogEngine(cat.sensors, cat.sensor_kinds, cat.targets, cat.est_x, cat.est_p, cat.Q, cat.R, seed=1)
+        bands = {}
+
+        def guard(name):
+            t = getattr(eng, name)
+            flat = t.reshape(-1)
+            fill = 12345.678 if t.dtype.is_floating_point else 0x5A
+            big = torch.full((flat.numel() + 2 * G,), fill, dtype=t.dtype, device=t.device)
+            big[G: G + flat.numel()] = flat
+            setattr(eng, name, big[G: G + flat.numel()].view(t.shape))
+            bands[name] = (big, fill)
+
+        for name in ("sens_x", "sens_q", "sigma", "sig_flags", "est_p", "pred_p", "nis", "flags", "vis_truth",
+                     "out_block", "tasked", "z", "actions"):
+            guard(name)
+        eng.est_x, eng.truth_x = eng.sigma[0], eng.sigma[13]
+        eng.obs_f32 = eng.out_block[: 4 * sum(eng._obs_sizes)].view(torch.float32)
+        eng.summary = eng.out_block[eng._obs_bytes:]
+        eng._bind_summary_views()
+        eng.snapshot()
+        rng = np.random.default_rng(n)
+        eng.compute_vis()
+        for s in range(3):
+            eng.step(dt=100.0, actions=rng.integers(0, n + 1, size=m))
+            eng.pack_obs()
+        hb = eng.host_buffers()
+        hb["actions"][:m].copy_(torch.from_numpy(rng.integers(0, n + 1, size=m)))
+        eng.step_host(hb, 100.0)
+        eng.step_host(hb, 100.0)
+        torch.cuda.synchronize()
+        assert eng.host("num_tasked").sum() > 0 and (eng.host("flags") & ~np.uint32(16)).max() == 0
+        for name, (big, fill) in bands.items():
+            lo, hi = big[:G].cpu().numpy(), big[-G:].cpu().numpy()
+            ref = np.full(G, fill, dtype=lo.dtype)
+            np.testing.assert_array_equal(lo, ref, err_msg=f"{name}: wrote before the buffer (n={n}, m={m})")
+            np.testing.assert_array_equal(hi, ref, err_msg=f"{name}: wrote past the buffer (n={n}, m={m})")
