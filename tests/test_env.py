@@ -174,3 +174,43 @@ def test_env_device_draw_horizon_reset_and_deepcopy(golden):
     assert env.info["num_steps"] == 0 and env.info["time_now"] == 0.0
     # the twin kept its own state
     assert twin.info["num_steps"] == 3
+
+
+@pytest.mark.gpu
+def test_c1_default_env_full_episode():
+    """BASELINE.json configs[0] shape through the drop-in env: 3 ground sensors, 10 LEO targets
+    generated with the reference's own generator semantics (genInitStates LLA / COE), reference
+    default filter matrices, one 100-step episode at dt = 100 s with a greedy visible-target policy."""
+    from clockpunch_b200.common.agents import Sensor, Target
+    from clockpunch_b200.dynamics.dynamics_classes import SatDynamicsModel, StaticTerrestrial
+    from clockpunch_b200.environment.env import SSAScheduler
+    from clockpunch_b200.estimation.ez_ukf import ezUKF
+    from clockpunch_b200.simulation.sim_utils import genInitStates
+    RE = 6378.1363
+    sens = genInitStates(3, "uniform", [[-1.3, 1.3], [-np.pi, np.pi], [1e-6, 1e-6], [0, 0], [0, 0], [0, 0]], "LLA", seed=1)
+    targ = genInitStates(10, "uniform", [[RE + 400, RE + 1000], [0, 0.01], [0, np.pi], [0, 2 * np.pi], [0, 2 * np.pi],
+                                         [0, 2 * np.pi]], "COE", seed=2)
+    assert len(sens) == 3 and sens[0].shape == (6, 1)
+    D = np.diag([1, 1, 1, 0.01, 0.01, 0.01])
+    rng = np.random.default_rng(3)
+    agents = [Sensor(StaticTerrestrial(), s, agent_id=1000 + j) for j, s in enumerate(sens)]
+    for i, x in enumerate(targ):
+        x0 = x[:, 0] + rng.normal(size=6) * np.sqrt(np.diag(10 * D))
+        f = ezUKF({"x_init": x0, "p_init": 10 * D, "dynamics_type": "satellite", "Q": 0.1 * D, "R": 1.0 * D})
+        agents.append(Target(SatDynamicsModel(), x, f, agent_id=9000 + i))
+    env = SSAScheduler(_Params(100.0, 100, agents), seed=11)
+    obs, info = env.reset()
+    tasked_total, done = 0, False
+    for s in range(100):
+        vis = obs["vis_map_est"]
+        action = np.where(vis.any(axis=0), (vis * (1 + rng.random(vis.shape))).argmax(axis=0), env.num_targets)
+        obs, rew, done, trunc, info = env.step(action)
+        assert np.isfinite(obs["eci_state"]).all() and np.isfinite(obs["est_cov"]).all()
+        assert info["num_steps"] == s + 1 and info["time_now"] == pytest.approx(100.0 * (s + 1))
+        assert done == (s == 99)
+    assert info["num_unique_targets_tasked"] >= 1 and sum(info["num_tasked"]) >= info["num_unique_targets_tasked"]
+    # LEO targets seen from three ground sites: true positions stay on their orbits
+    r = np.linalg.norm(info["true_states"][:3, 3:].astype(np.float64), axis=0)
+    assert (r > RE + 300).all() and (r < RE + 1100).all()
+    # the episode ended: the env reset itself
+    assert env.info["num_steps"] == 0
