@@ -251,12 +251,14 @@ def run_own(args):
         from clockpunch_b200.sharding import PackedGather
         sg = PackedGather(world, rank, eng.summary, N, eng.wpr)
         exchange = "nccl all_gather_into_tensor" + ("" if args.eager_gather else " (captured in the step graph)")
-        # measured on 8 GPUs: peer stores win while the step is latency-bound (10 000 targets per GPU:
-        # 61 vs 79 us per step), the bulk all-gather wins once a shard pushes megabytes (125 000: 0.28 vs 0.31 ms)
-        if args.exchange == "peer" or (args.exchange == "auto" and N <= 32768):
+        # measured on 8 GPUs: 10 000 targets per GPU 61 us per step (stores from the per-target kernel)
+        # vs 79 us with the all-gather; 125 000 per GPU 0.264 ms (copy kernel behind it) vs 0.287 ms
+        if args.exchange in ("peer", "auto"):
             try:
                 eng.enable_peer_push()
-                exchange = "peer stores from the per-target kernel (symmetric memory over NVLink) + flag wait"
+                exchange = ("peer stores from the per-target kernel" if N <= 32768 else
+                            "summary pushed into every peer by a copy kernel behind the per-target kernel") + \
+                    " (symmetric memory over NVLink) + flag wait"
             except Exception as exc:        # no symmetric memory on this box: keep the collective
                 print(f"peer push unavailable ({exc!r}); using NCCL", file=sys.stderr)
     use_nccl = sg is not None and eng._peer is None

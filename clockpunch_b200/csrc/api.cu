@@ -1,5 +1,6 @@
 // C-ABI of libpunch_b200 (see include/punch_b200.h for the contract).
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 #include <string>
@@ -853,6 +854,18 @@ int pc_step_fused(pc_ctx* ctx, const pc_step_args* a, const pc_ukf_params* param
       u.body_radius = a->body_radius;
       u.vis_tol = a->vis_tol;
     }
+    // Two forms of the peer push.  Latency-bound shards (<= 32 k targets): the per-target kernel stores
+    // every summary value into all peers as it produces it.  Larger shards: it only fills the local
+    // summary buffer and a copy kernel, launched programmatically behind it, pushes the buffer with
+    // 16-byte stores (a shard then moves megabytes per step; per-thread 4-byte stores to 8 peers
+    // lose to a streaming copy: 0.307 vs 0.264 ms at 8 x 125 k targets, NCCL all-gather 0.287 ms).
+    // PC_PEER_MODE=store|copy overrides the size rule (experiments).
+    static const int peer_mode = [] {
+      const char* e = getenv("PC_PEER_MODE");
+      return !e ? 0 : (std::strcmp(e, "copy") == 0 ? 2 : (std::strcmp(e, "store") == 0 ? 1 : 0));
+    }();
+    const bool peer_copy = peer_mode == 2 || (peer_mode == 0 && a->N > 32768);
+    pc::PeerPush pp_copy{};
     if (a->peer_table) {
       const char* base = static_cast<const char*>(a->summary_base);
       u.pp.world = a->peer_world;
@@ -866,10 +879,18 @@ int pc_step_fused(pc_ctx* ctx, const pc_step_args* a, const pc_ukf_params* param
       u.pp.off_ltt = reinterpret_cast<const char*>(a->last_time_tasked) - base;
       u.pp.ticket = ctx->peer_dev;
       u.pp.seq = reinterpret_cast<unsigned long long*>(ctx->peer_dev + 2);
+      if (peer_copy && a->summary_bytes % 16 == 0) {
+        pp_copy = u.pp;
+        u.pp = pc::PeerPush{};
+      }
     }
     u.p = *params;
     PC_CUDA_TRY(ctx, pc::launch_ukf_finish(u, s));
     ctx->launches += 2;
+    if (pp_copy.world) {
+      PC_CUDA_TRY(ctx, pc::launch_peer_push(a->summary_base, a->summary_bytes, pp_copy, s));
+      ctx->launches += 1;
+    }
     if (a->peer_table) {
       PC_CUDA_TRY(ctx, pc::launch_peer_wait(a->peer_table, a->peer_world, a->peer_rank,
                                             reinterpret_cast<const unsigned long long*>(ctx->peer_dev + 2),

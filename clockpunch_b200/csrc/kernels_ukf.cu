@@ -660,6 +660,30 @@ __global__ void peer_wait_kernel(const uint64_t* __restrict__ table, int world, 
   atomicOr(err, 1u << r);
 }
 
+// Alternative to storing from the per-target kernel: one grid copies the finished local summary
+// buffer into this rank's slot of every peer's gathered buffer with 16-byte stores, then publishes.
+__global__ void __launch_bounds__(256)
+peer_push_kernel(const uint4* __restrict__ src, int64_t n16, PeerPush pp) {
+  pdl_wait();
+  pdl_trigger();
+  const uint64_t step_done = *reinterpret_cast<const volatile unsigned long long*>(pp.seq) + 1;
+  const int64_t off = ((int64_t)(step_done & 1) * pp.world + pp.rank) * pp.slot_bytes;
+  for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < n16; i += (int64_t)gridDim.x * 256) {
+    const uint4 v = src[i];
+    for (int r = 0; r < pp.world; ++r) reinterpret_cast<uint4*>(__ldg(pp.table + r) + off)[i] = v;
+  }
+  peer_publish(pp, step_done);
+}
+
+cudaError_t launch_peer_push(const void* summary, int64_t bytes, const PeerPush& pp, cudaStream_t stream) {
+  const int64_t n16 = bytes / 16;
+  int blocks = (int)((n16 + 255) / 256);
+  if (blocks > 296) blocks = 296;
+  if (blocks < 1) blocks = 1;
+  return launch_pdl(peer_push_kernel, dim3(blocks), dim3(256), 0, stream, true,
+                    reinterpret_cast<const uint4*>(summary), n16, pp);
+}
+
 cudaError_t launch_peer_wait(const uint64_t* table, int world, int rank, const unsigned long long* seq,
                              unsigned int* err, cudaStream_t stream) {
   return launch_pdl(peer_wait_kernel, dim3(1), dim3(64), 0, stream, true, table, world, rank, seq, err);

@@ -65,6 +65,7 @@ cudaError_t launch_propagate_sigma(double* sb, int64_t n, int64_t ld, int have_t
                                    double tf, int substeps, int force_model, uint32_t* sig_flags,
                                    bool beside_predecessor, cudaStream_t stream);
 cudaError_t launch_ukf_finish(const UkfArgs& a, cudaStream_t stream);
+cudaError_t launch_peer_push(const void* summary, int64_t bytes, const PeerPush& pp, cudaStream_t stream);
 cudaError_t launch_peer_wait(const uint64_t* table, int world, int rank, const unsigned long long* seq,
                              unsigned int* err, cudaStream_t stream);
 
