@@ -610,9 +610,15 @@ def test_peer_push_single_rank_matches_summary():
     from clockpunch_b200.engine import CatalogEngine
     from clockpunch_b200.simulation.catalog import synth_catalog
     if not dist.is_initialized():
-        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        os.environ.setdefault("MASTER_PORT", "29577")
-        dist.init_process_group("nccl", rank=0, world_size=1, device_id=torch.device("cuda", 0))
+        import socket
+        with socket.socket() as sock:
+            sock.bind(("127.0.0.1", 0))
+            port = sock.getsockname()[1]
+        os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+        try:
+            dist.init_process_group("nccl", rank=0, world_size=1, device_id=torch.device("cuda", 0))
+        except Exception as exc:
+            pytest.skip(f"cannot start a single-rank NCCL group here: {exc!r}")
     for n in (300, 40_000):                       # quad kernel / thread-per-target kernel
         cat = synth_catalog(n, 70, seed=50 + n)
         eng = CatalogEngine(cat.sensors, cat.sensor_kinds, cat.targets, cat.est_x, cat.est_p, cat.Q, cat.R, seed=6)
