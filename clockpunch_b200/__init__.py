@@ -25,7 +25,7 @@ _MIRRORED = [
     "dynamics", "dynamics.dynamics", "dynamics.propagator", "dynamics.dynamics_classes",
     "estimation", "estimation.filter_base_class", "estimation.ukf_v2", "estimation.ez_ukf",
     "simulation", "simulation.sim_utils",
-    "environment", "environment.env", "environment.env_utils",
+    "environment", "environment.env", "environment.env_utils", "environment.env_parameters",
     "schedule_tree", "schedule_tree.access_windows",
 ]
 

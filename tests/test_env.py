@@ -214,3 +214,57 @@ def test_c1_default_env_full_episode():
     assert (r > RE + 300).all() and (r < RE + 1100).all()
     # the episode ended: the env reset itself
     assert env.info["num_steps"] == 0
+
+
+def test_scheduler_params_reproduce_reference_scenario(golden):
+    """SSASchedulerParams with the reference's own test_env.py config (tests/environment/test_env.py:35-79)
+    and the same legacy-RNG seed the golden generator used: agents, IDs, filter matrices and the noisy
+    initial estimates equal the live reference's (tests/golden/env.npz).  CPU only: fixed ICs."""
+    from clockpunch_b200.common.agents import Sensor, Target
+    from clockpunch_b200.dynamics.dynamics_classes import SatDynamicsModel, StaticTerrestrial
+    from clockpunch_b200.environment.env_parameters import SSASchedulerParams
+    g = golden("env")
+    D = np.diag([1, 1, 1, 0.01, 0.01, 0.01])
+    agent_params = {"num_sensors": 3, "num_targets": 4, "sensor_starting_num": 1000, "target_starting_num": 9000,
+                    "sensor_dynamics": "terrestrial", "target_dynamics": "satellite",
+                    "fixed_sensors": g["test_env_sensors"].T.copy(), "fixed_targets": g["test_env_targets"].T.copy()}
+    np.random.seed(1234)
+    p = SSASchedulerParams(time_step=1.2, horizon=10, agent_params=agent_params,
+                           filter_params={"Q": 0.001 * D, "R": 0.01 * D, "p_init": 1 * D})
+    assert [type(a) for a in p.agents] == [Sensor] * 3 + [Target] * 4
+    assert [str(a.agent_id) for a in p.agents] == [str(i) for i in g["test_env_ids"]]
+    assert isinstance(p.agents[0].dynamics, StaticTerrestrial) and isinstance(p.agents[3].dynamics, SatDynamicsModel)
+    np.testing.assert_array_equal(np.stack([a.eci_state[:, 0] for a in p.agents[3:]], axis=1), g["test_env_targets"])
+    est0 = np.stack([np.asarray(a.target_filter.est_x).reshape(6) for a in p.agents[3:]], axis=1)
+    np.testing.assert_array_equal(est0, g["test_env_est_x0"])          # same global-RNG draws, same order
+    np.testing.assert_array_equal(p.agents[3].target_filter.est_p, D)
+    assert p.agents[3].num_tasked == 0 and p.agents[3].last_time_tasked == 0
+    # defaults and validation
+    q = SSASchedulerParams(horizon=5, agent_params={"fixed_sensors": [[7000.0, 0, 0, 0, 0, 0]],
+                                                    "fixed_targets": [[8000.0, 0, 0, 0, 7, 0]]})
+    assert q.time_step == 100 and q.agent_params["sensor_dist"] is None and q.agents[0].agent_id == "S1000"
+    np.testing.assert_array_equal(q.filter_params["p_init"], 10 * np.diag([1, 1, 1, 1e-2, 1e-2, 1e-2]))
+    with pytest.raises(ValueError):
+        SSASchedulerParams(horizon=5, agent_params={"num_sensors": 2, "fixed_sensors": [[7000.0, 0, 0, 0, 0, 0]],
+                                                    "fixed_targets": [[8000.0, 0, 0, 0, 7, 0]]})
+    with pytest.raises(ValueError):
+        SSASchedulerParams(horizon=5, agent_params={"sensor_dist": "uniform", "fixed_sensors": [[7000.0, 0, 0, 0, 0, 0]],
+                                                    "fixed_targets": [[8000.0, 0, 0, 0, 7, 0]]})
+
+
+@pytest.mark.gpu
+def test_default_scheduler_params_env_runs():
+    """SSAScheduler(SSASchedulerParams(...)) with everything defaulted but the counts: ground sensors
+    drawn in LLA, LEO targets in COE (defaults of env_parameters.py:505-531), reference-default filter."""
+    from clockpunch_b200.environment.env import SSAScheduler
+    from clockpunch_b200.environment.env_parameters import SSASchedulerParams
+    np.random.seed(7)
+    p = SSASchedulerParams(horizon=6, agent_params={"num_sensors": 3, "num_targets": 10}, seed=42)
+    r = np.linalg.norm(np.stack([a.eci_state[:3, 0] for a in p.agents]), axis=1)
+    assert np.allclose(r[:3], 6378.1363 + 1e-6) and (r[3:] > 6378.1363 + 399).all() and (r[3:] < 6378.1363 + 1001).all()
+    env = SSAScheduler(p)
+    obs, info = env.reset()
+    assert obs["eci_state"].shape == (6, 13) and info["vis_map_truth"].shape == (10, 3)
+    for s in range(6):
+        obs, rew, done, trunc, info = env.step(np.full(3, s % 10))
+    assert done and np.isfinite(obs["est_cov"]).all()
