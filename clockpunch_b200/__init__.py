@@ -40,3 +40,17 @@ def install_as_punchclock() -> None:
         except ModuleNotFoundError:
             continue
         sys.modules.setdefault(f"punchclock.{name}", mod)
+
+
+def _register_gym_env() -> None:
+    """`gym.make("SSAScheduler-v0")` as the reference registers it (punchclock/__init__.py:7-10),
+    pointing at the CUDA-backed env.  gymnasium is optional; without it this is a no-op."""
+    try:
+        from gymnasium.envs.registration import register, registry
+    except ModuleNotFoundError:
+        return
+    if "SSAScheduler-v0" not in registry:
+        register(id="SSAScheduler-v0", entry_point="clockpunch_b200.environment.env:SSAScheduler")
+
+
+_register_gym_env()
