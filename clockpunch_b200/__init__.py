@@ -21,7 +21,7 @@ import sys
 __version__ = "0.1.0"
 
 _MIRRORED = [
-    "common", "common.constants", "common.transforms", "common.visibility", "common.agents", "common.metrics",
+    "common", "common.constants", "common.transforms", "common.visibility", "common.agents", "common.metrics", "common.utilities",
     "dynamics", "dynamics.dynamics", "dynamics.propagator", "dynamics.dynamics_classes",
     "estimation", "estimation.filter_base_class", "estimation.ukf_v2", "estimation.ez_ukf",
     "simulation", "simulation.sim_utils",

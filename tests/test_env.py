@@ -54,6 +54,13 @@ def test_tracker_matches_reference_counts(golden):
         meanVarUncertainty(np.array(covs))
 
 
+def test_action_space_to_array():
+    from clockpunch_b200.common.utilities import actionSpace2Array
+    np.testing.assert_array_equal(actionSpace2Array(np.array([1, 3, 0]), 3, 3),
+                                  [[0, 0, 1], [1, 0, 0], [0, 0, 0], [0, 1, 0]])
+    assert actionSpace2Array(np.array([2, 2]), 2, 2).dtype == int
+
+
 def test_saturate_coes_and_partition_free_functions():
     from clockpunch_b200.simulation.sim_utils import saturateCOEs
     out = saturateCOEs([6000.0, 7000.0], [-0.1, 1.5], [4.0, 0.5], [7.0, -1.0], [0.1, 0.2], [6.3, 0.0], return_array=True)
