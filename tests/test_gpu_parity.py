@@ -692,3 +692,32 @@ def test_guard_bands_no_out_of_bounds_writes():
             ref = np.full(G, fill, dtype=lo.dtype)
             np.testing.assert_array_equal(lo, ref, err_msg=f"{name}: wrote before the buffer (n={n}, m={m})")
             np.testing.assert_array_equal(hi, ref, err_msg=f"{name}: wrote past the buffer (n={n}, m={m})")
+
+
+def test_empty_and_degenerate_inputs():
+    """Zero-length batches, t0 == tf, NaN states: the entry points return / raise like the reference
+    instead of launching on nothing."""
+    from clockpunch_b200 import _lib
+    from clockpunch_b200.common.visibility import calcVisMap, calcVisMapAndDerivative
+    from clockpunch_b200.dynamics.dynamics_classes import SatDynamicsModel, StaticTerrestrial
+    from clockpunch_b200.dynamics.propagator import propagate_batch
+    from clockpunch_b200.estimation.ukf_v2 import ukf_batch_host
+    assert propagate_batch(np.zeros((6, 0)), 0.0, 10.0).shape == (6, 0)
+    sens = np.array([[7000.0, 0, 0, 0, 7.5, 0]]).T
+    assert calcVisMap(sens, np.zeros((6, 0))).shape == (0, 1)
+    assert calcVisMap(np.zeros((6, 0)), sens).shape == (1, 0)
+    v, d = calcVisMapAndDerivative(sens, np.zeros((6, 0)))
+    assert v.shape == d.shape == (0, 1)
+    params = _lib.make_ukf_params(np.eye(6), np.eye(6))
+    out = ukf_batch_host(np.zeros((6, 0)), np.zeros((0, 6, 6)), None, None, 0.0, 60.0, params)
+    assert out["est_x"].shape == (6, 0) and out["flags"].shape == (0,)
+    with pytest.raises(ValueError):
+        SatDynamicsModel().propagate(sens, 3.0, 3.0)                      # propagator.py:40-41
+    np.testing.assert_array_equal(StaticTerrestrial().propagate(sens[:, 0], 3.0, 3.0), sens[:, 0])   # zero rotation
+    # a NaN state propagates to NaN (no hang in the substep rule) and is invisible
+    bad = sens.copy(); bad[1, 0] = np.nan
+    assert np.isnan(SatDynamicsModel().propagate(bad, 0.0, 100.0)).any()
+    assert calcVisMap(sens, bad)[0, 0] == 0
+    # a state at the origin-crossing extreme takes the clamped substep path and returns
+    fall = np.array([[6500.0, 0, 0, 0, 0.01, 0]]).T               # nearly radial plunge: orbit rate clamp
+    assert np.isfinite(SatDynamicsModel().propagate(fall, 0.0, 10.0)).all()
