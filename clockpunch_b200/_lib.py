@@ -48,6 +48,7 @@ class StepArgs(C.Structure):
         ("sens_q", C.c_void_p), ("env_targets", C.c_int64), ("env_sensors", C.c_int64),
         ("peer_table", C.c_void_p), ("peer_world", C.c_int32), ("peer_rank", C.c_int32),
         ("summary_base", C.c_void_p), ("summary_bytes", C.c_int64),
+        ("task_of", C.c_void_p),
     ]
 
 

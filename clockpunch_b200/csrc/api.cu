@@ -30,7 +30,7 @@ cudaError_t launch_pre_step(double* sens_x, const uint8_t* sens_kind, int64_t M,
                             double body_radius, double vis_tol, pc_clock* clock, int64_t* actions,
                             const uint32_t* vis_est, uint8_t* tasked, int64_t N, int64_t wpr,
                             int probes, uint64_t seed, uint64_t step, int64_t env_targets,
-                            int64_t env_sensors, cudaStream_t s);
+                            int64_t env_sensors, int64_t* task_of, cudaStream_t s);
 
 cudaError_t launch_frame_change(const double*, double*, int64_t, int64_t, double, double, cudaStream_t);
 cudaError_t launch_coe2eci(const double*, double*, int64_t, int64_t, double, cudaStream_t);
@@ -794,7 +794,7 @@ int pc_step_fused(pc_ctx* ctx, const pc_step_args* a, const pc_ukf_params* param
                                          a->force_model, fuse_vis ? sq : nullptr, a->body_radius, a->vis_tol,
                                          a->clock, a->actions, a->vis_est, const_cast<uint8_t*>(a->tasked),
                                          a->N, a->words_per_row, a->policy_probes, a->policy_seed,
-                                         a->rng_step, Ne, Me, s));
+                                         a->rng_step, Ne, Me, a->actions ? a->task_of : nullptr, s));
     ctx->launches += 1;
   }
   // 2. targets: sigma points (only when not carried over from the previous step), all 14 N
@@ -843,6 +843,11 @@ int pc_step_fused(pc_ctx* ctx, const pc_step_args* a, const pc_ukf_params* param
     u.gen_next = own_sb ? 1 : 0;
     u.est_x_out = own_sb ? nullptr : a->est_x;
     u.truth_out = own_sb ? nullptr : a->truth_x;
+    if (a->actions && a->task_of && a->M > 0) {
+      u.task_of = a->task_of;
+      u.task_sensors = a->M;
+      u.task_env_sensors = Me;
+    }
     if (fuse_vis) {
       u.sens_q = reinterpret_cast<const double4*>(sq);
       u.M = a->M;

@@ -176,6 +176,7 @@ struct PreStepArgs {
   uint64_t seed, step_arg;
   int nb_sens;
   int64_t env_targets, env_sensors;  // batch of environments (single catalog: N, M)
+  int64_t* task_of;         // may be NULL; [j] = global index of the target sensor j validly tasks, else -1
 };
 
 template <bool J2>
@@ -232,11 +233,14 @@ pre_step_kernel(const __grid_constant__ PreStepArgs a) {
     if (lane == 0) {
       a.actions[j] = pick;
       if (pick < Ne) a.tasked[t0 + pick] = 1;  // visible by construction
+      if (a.task_of) a.task_of[j] = pick < Ne ? t0 + pick : -1;
     }
   } else if (lane == 0) {
     pick = a.actions[j];
-    if (pick >= 0 && pick < Ne && ((a.vis_est[(t0 + pick) * a.wpr + (jl >> 5)] >> (jl & 31)) & 1u))
-      a.tasked[t0 + pick] = 1;
+    const bool valid =
+        pick >= 0 && pick < Ne && ((a.vis_est[(t0 + pick) * a.wpr + (jl >> 5)] >> (jl & 31)) & 1u);
+    if (valid) a.tasked[t0 + pick] = 1;
+    if (a.task_of) a.task_of[j] = valid ? t0 + pick : -1;
   }
 }
 
@@ -245,9 +249,10 @@ cudaError_t launch_pre_step(double* sens_x, const uint8_t* sens_kind, int64_t M,
                             double body_radius, double vis_tol, pc_clock* clock, int64_t* actions,
                             const uint32_t* vis_est, uint8_t* tasked, int64_t N, int64_t wpr,
                             int probes, uint64_t seed, uint64_t step, int64_t env_targets,
-                            int64_t env_sensors, cudaStream_t s) {
+                            int64_t env_sensors, int64_t* task_of, cudaStream_t s) {
   if (M <= 0 && clock == nullptr) return cudaSuccess;
   PreStepArgs a;
+  a.task_of = task_of;
   a.env_targets = env_targets > 0 ? env_targets : N;
   a.env_sensors = env_sensors > 0 ? env_sensors : M;
   a.sens_x = sens_x;

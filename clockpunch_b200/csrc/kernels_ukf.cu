@@ -32,6 +32,7 @@
 //   Xres+ Xres+^T + Xres- Xres-^T = 2 a_j a_j^T + D_j D_j^T / 2,
 //   a_j = (x+ + x-)/2 - pred_x,  D_j = x+ - x-,
 // which is how pred_p is accumulated (again algebraically identical to ukf_v2.py:286-292).
+#include <cstdlib>
 #include "propagate.cuh"
 #include "ukf_args.cuh"
 #include "vis.cuh"
@@ -39,6 +40,9 @@
 // Phase stamps for tools/microbench/finish_phases.cu (no-ops in the library build).
 #ifndef PC_PHASE_CLOCK
 #define PC_PHASE_CLOCK(i)
+#endif
+#ifndef PC_COOP_CLOCK
+#define PC_COOP_CLOCK(i)
 #endif
 
 namespace pc {
@@ -938,6 +942,348 @@ cudaError_t launch_sigma_gen(const double* est_x, const double* est_p, const dou
 constexpr int kQuadThreads = 64;
 constexpr int64_t kQuadMaxTargets = 32 * 1024;  // above this one thread per target fills the machine
 
+// ---- cooperative measurement update: one WARP per tasked target ------------------------------------
+// At catalogs of ~10^4 targets the per-target kernel is one wave of latency-bound warps that execute
+// straight-line code once: after the benchmark's L2 flush it is INSTRUCTION-FETCH bound (removing the
+// never-executed in-line update from the kernel made the untasked path 5 us faster, profiles/README.md),
+// and the few targets that received a measurement (at most one per sensor) lengthened the warps they
+// sit in by more than half the untasked path.  With pc_step_args.task_of the quad kernel is launched
+// with ceil(M / 2) extra CTAs in front of the grid; warp w of extra CTA c looks at sensor 2 c + w,
+// and if that sensor validly tasks a target (and no lower-numbered sensor of the same environment
+// tasks the same one) it does that target's WHOLE per-target stage -- transform, update, outputs,
+// next sigma points, estimated visibility row.  The target's own quad then only writes what does not
+// depend on the estimate (true visibility row).
+//
+// The update warp's code is written for SIZE, not for issue rate (one warp per SM runs it, so every
+// instruction line is a cold miss): all operands live in shared memory, loops stay rolled, the
+// Cholesky factorisation is one out-of-line routine called three times, and independent matrix
+// entries are spread over the lanes (lane k < 21 owns entry (ra, rb) of an upper triangle).  Same
+// equations as measurement_update_reg; the factorisations perform the same operations in the same
+// order, the sums of the unscented transform are taken in a different order (round-off level).
+struct CoopSmem {
+  double X[14][6];                       // propagated sigma points of the target: block, component
+  double P[36], W[36], U2[36], Us[36];   // pred_p; scratch; chol(pred_p); chol(innovation cvr)
+  double G[36], PE[36], Un[36];          // gain factor; est_p; chol(est_p)
+  double Sb[6], m[6], px[6], delta[6], nu[6], y[6], xe[6], dinv[6], nrm[6], z[6];
+};
+constexpr int kCoopMaxSensors = 256;
+
+__device__ __forceinline__ int tri_row(int k) { return (k >= 6) + (k >= 11) + (k >= 15) + (k >= 18) + (k >= 20); }
+
+// Upper Cholesky W = U^T U by one warp, right-looking: step i scales row i, then every lane that owns
+// an entry below it subtracts the rank-one term.  Entry (a, b) receives the same fma sequence as in
+// chol_upper6_packed, so the factor is bit-identical.  W's upper triangle is destroyed.
+__device__ __noinline__ bool chol6_warp(double* __restrict__ W, double* __restrict__ U, int lane) {
+  const int k = lane < 21 ? lane : 20;
+  const int ra = tri_row(k), rb = k - uidx(ra, ra) + ra;
+  bool ok = true;
+#pragma unroll 1
+  for (int i = 0; i < 6; ++i) {
+    const double s = W[i * 7];
+    ok = ok && (s > 0.0);
+    const double d = rsqrt_fast(s);
+    if (lane < 21 && ra == i) U[i * 6 + rb] = W[i * 6 + rb] * d;
+    __syncwarp();
+    if (lane < 21 && ra > i) W[ra * 6 + rb] = fma(-U[i * 6 + ra], U[i * 6 + rb], W[ra * 6 + rb]);
+    __syncwarp();
+  }
+  return ok;
+}
+
+// Rare: nearest-PD repair of the full symmetric matrix A, factor written to U (upper).
+__device__ __noinline__ void repair6_warp(const double* __restrict__ A, double* __restrict__ U, int lane) {
+  if (lane == 0) {
+    double Ein[21], Uo[21];
+#pragma unroll 1
+    for (int i = 0; i < 6; ++i)
+      for (int j = i; j < 6; ++j) {
+        Ein[uidx(i, j)] = A[i * 6 + j];
+        Uo[uidx(i, j)] = 0.0;
+      }
+    repair_chol6(Ein, Uo);
+#pragma unroll 1
+    for (int i = 0; i < 6; ++i)
+      for (int j = i; j < 6; ++j) U[i * 6 + j] = Uo[uidx(i, j)];
+  }
+  __syncwarp();
+}
+
+// Benign operands for the dry runs: identity factors, a state well above the surface.
+__device__ __forceinline__ void coop_scratch_init(CoopSmem& S) {
+  const int lane = threadIdx.x & 31;
+  double* f = reinterpret_cast<double*>(&S);
+  for (int i = lane; i < (int)(sizeof(CoopSmem) / sizeof(double)); i += 32) f[i] = 0.0;
+  __syncwarp();
+  if (lane < 6) {
+    S.U2[lane * 7] = 1.0;
+    S.Us[lane * 7] = 1.0;
+    S.P[lane * 7] = 1.0;
+    S.dinv[lane] = 1.0;
+    S.px[lane] = 7000.0;
+    S.X[0][lane] = 7000.0;
+  }
+  __syncwarp();
+}
+
+// First half: loads, measurement, unscented transform, both factorisations.  Returns the flags so far.
+__device__ __noinline__ uint32_t coop_part1(const UkfArgs& a, CoopSmem& S, int64_t t, int dry) {
+  const int lane = threadIdx.x & 31;
+  const bool wr = dry == 0;
+  const int64_t ld = a.ld, blk = 6 * a.ld;
+  const pc_ukf_params& p = a.p;
+  const int k = lane < 21 ? lane : 20;
+  const int ra = tri_row(k), rb = k - uidx(ra, ra) + ra;
+  double* Xf = &S.X[0][0];
+#pragma unroll
+  for (int i = lane; i < 84; i += 32) {
+    const int b = i / 6, c = i - 6 * b;
+    if (wr) Xf[i] = a.sb[(int64_t)b * blk + (int64_t)c * ld + t];
+  }
+  PC_COOP_CLOCK(1);
+  uint32_t flags = a.sig_flags && wr ? a.sig_flags[t] : 0u;
+  const uint64_t rng_step = a.clock ? a.clock->step_cur : a.rng_step;
+  if (a.z) {
+    if (lane < 6 && wr) S.z[lane] = a.z[(int64_t)lane * ld + t];
+  } else if (lane < 3) {
+    // the three Box-Muller pairs of normal6(), one per lane (same counters, same arithmetic)
+    uint32_t c[4] = {(uint32_t)t, (uint32_t)((uint64_t)t >> 32), (uint32_t)rng_step, (uint32_t)(rng_step >> 32)};
+    if (lane == 2) c[3] ^= 0x5bd1e995u + 1u;
+    uint32_t k0 = (uint32_t)a.rng_seed, k1 = (uint32_t)(a.rng_seed >> 32);
+#pragma unroll 1
+    for (int r = 0; r < 10; ++r) {
+      const uint32_t hi0 = __umulhi(0xD2511F53u, c[0]), lo0 = 0xD2511F53u * c[0];
+      const uint32_t hi1 = __umulhi(0xCD9E8D57u, c[2]), lo1 = 0xCD9E8D57u * c[2];
+      const uint32_t n0 = hi1 ^ c[1] ^ k0, n2 = hi0 ^ c[3] ^ k1;
+      c[0] = n0;
+      c[1] = lo1;
+      c[2] = n2;
+      c[3] = lo0;
+      k0 += 0x9E3779B9u;
+      k1 += 0xBB67AE85u;
+    }
+    const uint32_t ua = lane == 1 ? c[2] : c[0], ub = lane == 1 ? c[3] : c[1];
+    const double u1 = ((double)ua + 0.5) * (1.0 / 4294967296.0);
+    const double u2 = ((double)ub + 0.5) * (1.0 / 4294967296.0);
+    const double rad = sqrt(-2.0 * log(u1));
+    double sn, cs;
+    sincospi(2.0 * u2, &sn, &cs);
+    S.nrm[2 * lane] = rad * cs;
+    S.nrm[2 * lane + 1] = rad * sn;
+  }
+  __syncwarp();
+  PC_COOP_CLOCK(2);
+
+  // ---- unscented transform ----------------------------------------------------------------------
+  if (lane < 6) {
+    const double x0 = S.X[0][lane];
+    double sb_ = 0.0;
+#pragma unroll 1
+    for (int j = 0; j < 6; ++j) sb_ += 0.5 * ((S.X[1 + j][lane] - x0) + (S.X[7 + j][lane] - x0));
+    const double mm = fma(2.0 * p.wi, sb_, p.eps_w * x0);
+    const double pxx = x0 + mm;
+    S.Sb[lane] = sb_;
+    S.m[lane] = mm;
+    S.px[lane] = pxx;
+    S.delta[lane] = p.eps_w * pxx;
+    if (!a.z) {   // Target.getMeasurement (agents.py:173-183): z ~ N(truth', R)
+      double acc = S.X[13][lane];
+#pragma unroll 1
+      for (int i = 0; i <= lane; ++i) acc = fma(p.Lr[lane * 6 + i], S.nrm[i], acc);
+      S.z[lane] = acc;
+    }
+  }
+  double F = 0.0;
+  {
+    const double x0a = S.X[0][ra], x0b = S.X[0][rb];
+#pragma unroll 1
+    for (int j = 0; j < 6; ++j) {
+      const double pa = S.X[1 + j][ra], ma = S.X[7 + j][ra], pb = S.X[1 + j][rb], mb = S.X[7 + j][rb];
+      const double ba = 0.5 * ((pa - x0a) + (ma - x0a)), bb = 0.5 * ((pb - x0b) + (mb - x0b));
+      F = fma(0.5 * (pa - ma), pb - mb, fma(ba + ba, bb, F));
+    }
+  }
+  __syncwarp();
+  if (lane < 21) {
+    const double ma = S.m[ra], mb = S.m[rb];
+    const double cross = fma(6.0 * ma, mb, -(S.Sb[ra] * mb + ma * S.Sb[rb]));
+    const double e = fma(p.wi, fma(2.0, cross, F), fma(p.wc0 * ma, mb, p.Q[ra * 6 + rb]));
+    S.P[ra * 6 + rb] = e;
+    S.P[rb * 6 + ra] = e;
+    S.W[ra * 6 + rb] = e;
+  }
+  if (lane < 6) S.nu[lane] = S.z[lane] - (S.px[lane] + S.delta[lane]);
+  __syncwarp();
+  if (a.out_pred_p && wr) {
+#pragma unroll
+    for (int i = lane; i < 36; i += 32) a.out_pred_p[t * 36 + i] = S.P[i];
+  }
+  PC_COOP_CLOCK(3);
+  if (!chol6_warp(S.W, S.U2, lane) && wr) {
+    flags |= PC_FLAG_NONPD_PRED;
+    repair6_warp(S.P, S.U2, lane);
+  }
+  PC_COOP_CLOCK(4);
+
+  // ---- innovation covariance and its factor -------------------------------------------------------
+  const double cuu = 2.0 * p.wi * p.gamma * p.gamma;
+  const double cdd = p.wc0 + 12.0 * p.wi;
+  if (lane < 21) {
+    double acc = 0.0;
+#pragma unroll 1
+    for (int j = rb; j < 6; ++j) acc = fma(S.U2[ra * 6 + j], S.U2[rb * 6 + j], acc);
+    S.W[ra * 6 + rb] = fma(cuu, acc, fma(cdd * S.delta[ra], S.delta[rb], p.R[ra * 6 + rb]));
+  }
+  __syncwarp();
+  if (!chol6_warp(S.W, S.Us, lane)) flags |= PC_FLAG_NONPD_INNOV;
+  if (lane < 6) S.dinv[lane] = 1.0 / S.Us[lane * 7];
+  __syncwarp();
+  PC_COOP_CLOCK(5);
+  return flags;
+}
+
+// Second half: gain, new estimate, every output of the target, next sigma points, estimated
+// visibility row.  With dry != 0 nothing is written to global memory: the second warp of an update
+// CTA runs this half on scratch operands WHILE the first warp is in the first half, so that the
+// instruction lines are already in the SM's instruction cache when the real data arrives (the update
+// warp is alone on its code: every line it touches is otherwise a cold miss).
+__device__ __noinline__ void coop_part2(const UkfArgs& a, CoopSmem& S, int64_t t, int parity, uint32_t flags,
+                                        int dry) {
+  const unsigned full = 0xffffffffu;
+  const int lane = threadIdx.x & 31;
+  const int64_t ld = a.ld, blk = 6 * a.ld;
+  const pc_ukf_params& p = a.p;
+  const int k = lane < 21 ? lane : 20;
+  const int ra = tri_row(k), rb = k - uidx(ra, ra) + ra;
+  const bool wr = dry == 0;
+  const double t_now = a.clock ? a.clock->t_cur + a.dt : a.t_now;
+  const double c3 = p.wc0 - p.wm0;
+  const double wg = p.wi * p.gamma;
+
+  // ---- gain factor G = C Us^-1 (lane a < 6: row a) beside y = Us^-T nu (lane 6) -------------------
+  double nis = 0.0;
+  if (lane < 6) {
+    const double sa = S.delta[lane] + c3 * S.m[lane];
+#pragma unroll 1
+    for (int b = 0; b < 6; ++b) {
+      double acc = 0.0;
+#pragma unroll 1
+      for (int j = b; j < 6; ++j) acc = fma(S.X[1 + j][lane] - S.X[7 + j][lane], S.U2[b * 6 + j], acc);
+      double cab = fma(wg, acc, sa * S.delta[b]);
+#pragma unroll 1
+      for (int i = 0; i < b; ++i) cab = fma(-S.G[lane * 6 + i], S.Us[i * 6 + b], cab);
+      S.G[lane * 6 + b] = cab * S.dinv[b];
+    }
+  } else if (lane == 6) {
+#pragma unroll 1
+    for (int b = 0; b < 6; ++b) {
+      double acc = S.nu[b];
+#pragma unroll 1
+      for (int i = 0; i < b; ++i) acc = fma(-S.Us[i * 6 + b], S.y[i], acc);
+      const double yb = acc * S.dinv[b];
+      S.y[b] = yb;
+      nis = fma(yb, yb, nis);
+    }
+  }
+  nis = __shfl_sync(full, nis, 6);
+  __syncwarp();
+  if (lane < 6) {
+    double x = S.px[lane];
+#pragma unroll 1
+    for (int b = 0; b < 6; ++b) x = fma(S.G[lane * 6 + b], S.y[b], x);
+    S.xe[lane] = x;
+  }
+  if (lane < 21) {
+    double acc = S.P[ra * 6 + rb];
+#pragma unroll 1
+    for (int i = 0; i < 6; ++i) acc = fma(-S.G[ra * 6 + i], S.G[rb * 6 + i], acc);
+    S.PE[ra * 6 + rb] = acc;
+    S.PE[rb * 6 + ra] = acc;
+    S.W[ra * 6 + rb] = acc;
+  }
+  __syncwarp();
+
+  // ---- outputs ---------------------------------------------------------------------------------------
+  if (wr) PC_COOP_CLOCK(6);
+  double chk = 0.0;
+#pragma unroll 1
+  for (int c = 0; c < 6; ++c) chk += S.xe[c] + S.PE[c * 7];
+  if (!isfinite(chk)) flags |= PC_FLAG_NONFINITE;
+#pragma unroll
+  for (int i = lane; i < 36; i += 32)
+    if (wr) a.est_p[t * 36 + i] = S.PE[i];
+  if (lane == 0 && wr) {
+    if (a.out_flags) a.out_flags[t] = flags;
+    if (a.out_nis) a.out_nis[t] = nis;
+    const float trp = ((float)S.PE[0] + (float)S.PE[7]) + (float)S.PE[14];
+    const float trv = ((float)S.PE[21] + (float)S.PE[28]) + (float)S.PE[35];
+    if (a.tr_pos) a.tr_pos[t] = trp;
+    if (a.tr_vel) a.tr_vel[t] = trv;
+    int64_t nt = 0;
+    if (a.num_tasked) {
+      nt = a.num_tasked[t] + 1;
+      a.num_tasked[t] = nt;
+    }
+    if (a.last_time_tasked) a.last_time_tasked[t] = (float)t_now;
+    if (a.pp.world) {
+      peer_store(a.pp, parity, a.pp.off_tr_pos, t, trp);
+      peer_store(a.pp, parity, a.pp.off_tr_vel, t, trv);
+      peer_store(a.pp, parity, a.pp.off_num_tasked, t, nt);
+      peer_store(a.pp, parity, a.pp.off_ltt, t, (float)t_now);
+    }
+  }
+  if (lane < 6 && wr) {
+    if (a.out_z) a.out_z[(int64_t)lane * ld + t] = S.z[lane];
+    if (a.out_pred_x) a.out_pred_x[(int64_t)lane * ld + t] = S.px[lane];
+    if (a.truth_out) a.truth_out[(int64_t)lane * ld + t] = S.X[13][lane];
+  }
+  if (wr) PC_COOP_CLOCK(7);
+  if (a.gen_next) {
+    const bool ok = chol6_warp(S.W, S.Un, lane);
+    if (!ok && wr) repair6_warp(S.PE, S.Un, lane);
+    if (lane == 0) {
+      const double r0[3] = {S.xe[0], S.xe[1], S.xe[2]}, v0[3] = {S.xe[3], S.xe[4], S.xe[5]};
+      const uint32_t rate = __float_as_uint(orbit_rate(r0, v0));
+      if (wr) {
+        a.sig_flags[t] = ok ? 0u : (uint32_t)PC_FLAG_NONPD_EST;
+        a.sig_flags[a.n + t] = rate;
+      }
+    }
+#pragma unroll 1
+    for (int i = lane; i < 78; i += 32) {
+      const int b = i / 6, c = i - 6 * b;
+      double v = S.xe[c];
+      if (b > 0) {
+        const int j = b <= 6 ? b - 1 : b - 7;
+        const double gq = c <= j ? p.gamma * S.Un[c * 6 + j] : 0.0;
+        v = b <= 6 ? v + gq : v - gq;
+      }
+      if (wr) a.sb[(int64_t)b * blk + (int64_t)c * ld + t] = v;
+    }
+  } else if (a.est_x_out && lane < 6 && wr) {
+    a.est_x_out[(int64_t)lane * ld + t] = S.xe[lane];
+  }
+  if (wr) PC_COOP_CLOCK(8);
+  if (a.vis_est) {
+    const double RE2 = a.body_radius * a.body_radius;
+    const double ex = S.xe[0], ey = S.xe[1], ez = S.xe[2];
+    const double eq = horizon_q(ex, ey, ez, a.body_radius, a.vis_tol);
+    const int64_t e = env_of_target(t, a.env_targets);
+#pragma unroll 1
+    for (int64_t w = 0; w < a.wpr; ++w) {
+      const int64_t sl = w * 32 + lane;
+      bool v = false;
+      if (sl < a.env_sensors) v = sees(a.sens_q[e * a.env_sensors + sl], ex, ey, ez, eq, RE2);
+      const uint32_t word = __ballot_sync(full, v);
+      if (lane == 0 && wr) {
+        a.vis_est[t * a.wpr + w] = word;
+        if (a.pp.world) peer_store(a.pp, parity, a.pp.off_vis_est, t * a.wpr + w, word);
+      }
+    }
+  }
+  if (wr) PC_COOP_CLOCK(9);
+  else PC_COOP_CLOCK(10);
+}
+
 __device__ __forceinline__ double quad_sum(double v) {
   v += __shfl_xor_sync(0xffffffffu, v, 1);
   v += __shfl_xor_sync(0xffffffffu, v, 2);
@@ -955,29 +1301,69 @@ __device__ __forceinline__ void store_sym36_quad(double* __restrict__ g, const d
   }
 }
 
+template <bool COOP>
 __global__ void __launch_bounds__(kQuadThreads, 5)
 ukf_finish_quad_kernel(const __grid_constant__ UkfArgs a) {
+  constexpr bool ROLE = COOP;
   __shared__ __align__(32) double4 tile[kVisTileSlots];
   __shared__ uint64_t mbar_store;
+  static_assert(sizeof(CoopSmem) * (kQuadThreads / 32) <= sizeof(double4) * kVisTileSlots, "update warps reuse the tile");
   uint64_t* mbar = &mbar_store;
+  if (ROLE && (int64_t)blockIdx.x < a.task_sensors && threadIdx.x >= 32) {
+    // Second warp of an update CTA, BEFORE the dependency wait: these CTAs are the first of the grid, so
+    // they become resident while the propagation kernel's last wave is still running.  The warp uses
+    // that time to run the second half of the update on scratch operands (nothing is written to
+    // global memory, whatever it reads may be stale): its instruction lines are then in this SM's
+    // instruction cache when the real update gets there.
+    CoopSmem* S = reinterpret_cast<CoopSmem*>(tile);
+    coop_scratch_init(S[1]);
+    coop_part2(a, S[1], 0, 0, 0u, 1);
+  }
   pdl_wait();  // launched programmatically behind the propagation kernel: everything below reads its output
   pdl_trigger();  // a programmatic successor (the observation pack) may be scheduled behind our last wave
   const int q = threadIdx.x & 3;
-  const int64_t t = ((int64_t)blockIdx.x * kQuadThreads + threadIdx.x) >> 2;
   if (a.clock && a.advance_clock && blockIdx.x == 0 && threadIdx.x == 0) {
     a.clock->t_now += a.dt;
     a.clock->step += 1;
   }
-  PC_PHASE_CLOCK(0);
-  const bool live = t < a.n;
-  const int64_t tc = live ? t : a.n - 1;
   // sequence number of this push (counts launches, survives engine resets) and the slot it goes to
   const uint64_t step_done = a.pp.world ? *reinterpret_cast<const volatile unsigned long long*>(a.pp.seq) + 1 : 0;
   const int parity = (int)(step_done & 1);
+  // the first M CTAs are update CTAs (one per sensor, see above), the rest take 16 targets each
+  const int64_t nb_upd = ROLE ? a.task_sensors : 0;
+  if (ROLE && (int64_t)blockIdx.x < nb_upd) {
+    const int lane = threadIdx.x & 31;
+    const int64_t j = (int64_t)blockIdx.x;
+    int64_t tt = a.task_of[j];
+    const int64_t j0 = (j / a.task_env_sensors) * a.task_env_sensors;
+    bool dup = false;   // a lower-numbered sensor of the same environment already owns this target
+    for (int64_t jj = j0 + lane; jj < j; jj += 32) dup |= a.task_of[jj] == tt;
+    if (__any_sync(0xffffffffu, dup)) tt = -1;
+    if (tt >= 0 && tt < a.n) {
+      CoopSmem* S = reinterpret_cast<CoopSmem*>(tile);
+      PC_COOP_CLOCK(0);
+      if (threadIdx.x < 32) {
+        const uint32_t fl = coop_part1(a, S[0], tt, 0);
+        coop_part2(a, S[0], tt, parity, fl, 0);
+      } else {
+        // after the wait: warm the first half's transform / factorisation code while warp 0 is still
+        // waiting for its loads
+        coop_scratch_init(S[1]);
+        coop_part1(a, S[1], tt, 1);
+      }
+    }
+    if (a.pp.world) peer_publish(a.pp, step_done);
+    return;
+  }
+  const int64_t cta = (int64_t)blockIdx.x - nb_upd;
+  const int64_t t = (cta * kQuadThreads + threadIdx.x) >> 2;
+  PC_PHASE_CLOCK(0);
+  const bool live = t < a.n;
+  const int64_t tc = live ? t : a.n - 1;
   const int64_t ld = a.ld, blk = 6 * a.ld;
   const double* __restrict__ sb = a.sb;
   const bool vis = a.vis_truth != nullptr;
-  const int64_t cta_t0 = (int64_t)blockIdx.x * (kQuadThreads / 4);
+  const int64_t cta_t0 = cta * (kQuadThreads / 4);
   const int64_t cta_t1 = cta_t0 + kQuadThreads / 4 - 1 < a.n - 1 ? cta_t0 + kQuadThreads / 4 - 1 : a.n - 1;
   const bool single = a.env_targets <= 0;
   const int64_t row_first = vis ? env_of_target(cta_t0, a.env_targets) * a.wpr : 0;
@@ -1065,10 +1451,14 @@ ukf_finish_quad_kernel(const __grid_constant__ UkfArgs a) {
   __syncwarp();
   const int tasked = live && tflag != 0;
   if (tasked && a.clear_tasked && q == 0) a.tasked[t] = 0;
+  // with update warps, a tasked target's quad leaves everything that depends on the estimate to its
+  // update warp (which may already be overwriting the target's sigma points: nothing loaded above
+  // is used for it) and only packs the true visibility row
+  const bool mine = live && !(COOP && tasked);
   double xe[6], PE[21];
   double nis = __longlong_as_double(0x7ff8000000000000LL);
-  if (a.out_pred_p && live) store_sym36_quad(a.out_pred_p + t * 36, E, q);
-  if (tasked) {
+  if (a.out_pred_p && mine) store_sym36_quad(a.out_pred_p + t * 36, E, q);
+  if (!COOP && tasked) {
     const double t_now = a.clock ? a.clock->t_cur + a.dt : a.t_now;
     const uint64_t rng_step = a.clock ? a.clock->step_cur : a.rng_step;
     double z[6];
@@ -1109,7 +1499,11 @@ ukf_finish_quad_kernel(const __grid_constant__ UkfArgs a) {
 #pragma unroll
   for (int c = 0; c < 6; ++c) chk += xe[c] + PE[uidx(c, c)];
   if (!isfinite(chk)) flags |= PC_FLAG_NONFINITE;
-  if (live) {
+  if (live && !mine && a.truth_out && q == 3) {
+#pragma unroll
+    for (int c = 0; c < 6; ++c) a.truth_out[(int64_t)c * ld + t] = sb[13 * blk + (int64_t)c * ld + t];
+  }
+  if (mine) {
     store_sym36_quad(a.est_p + t * 36, PE, q);
     if (q == 1) {
       if (a.out_flags) a.out_flags[t] = flags;
@@ -1169,7 +1563,7 @@ ukf_finish_quad_kernel(const __grid_constant__ UkfArgs a) {
   }
 
   PC_PHASE_CLOCK(7);
-  if (a.pp.world && live && q == 0) {   // lane 0 of the quad did the tasking bookkeeping above
+  if (a.pp.world && mine && q == 0) {   // lane 0 of the quad did the tasking bookkeeping above
     peer_store(a.pp, parity, a.pp.off_num_tasked, t, a.num_tasked[t]);
     peer_store(a.pp, parity, a.pp.off_ltt, t, a.last_time_tasked[t]);
   }
@@ -1197,8 +1591,8 @@ ukf_finish_quad_kernel(const __grid_constant__ UkfArgs a) {
         if (rr >= 0 && rr < nrows) {
           uint32_t wa, wb;
           vis_word(tile + rr * kVisRow, tr, tq, xe, eq, RE2, wa, wb);
-          if (live) {
-            a.vis_truth[t * wpr + w] = wa;
+          if (live) a.vis_truth[t * wpr + w] = wa;
+          if (mine) {
             a.vis_est[t * wpr + w] = wb;
             if (a.pp.world) peer_store(a.pp, parity, a.pp.off_vis_est, t * wpr + w, wb);
           }
@@ -1222,8 +1616,13 @@ static cudaError_t launch_finish_tpb(const UkfArgs& a, cudaStream_t stream) {
 cudaError_t launch_ukf_finish(const UkfArgs& a, cudaStream_t stream) {
   if (a.n <= 0) return cudaSuccess;
   if (a.n <= kQuadMaxTargets) {
-    return launch_pdl(ukf_finish_quad_kernel, dim3((unsigned)((4 * a.n + kQuadThreads - 1) / kQuadThreads)),
-                      dim3(kQuadThreads), 0, stream, true, a);
+    const unsigned ctas = (unsigned)((4 * a.n + kQuadThreads - 1) / kQuadThreads);
+    static const bool no_coop = getenv("PC_NO_COOP") != nullptr;   // experiments: in-line update everywhere
+    if (!no_coop && a.task_of && a.task_sensors > 0 && a.task_sensors <= kCoopMaxSensors) {
+      const unsigned upd = (unsigned)a.task_sensors;   // one update CTA per sensor
+      return launch_pdl(ukf_finish_quad_kernel<true>, dim3(upd + ctas), dim3(kQuadThreads), 0, stream, true, a);
+    }
+    return launch_pdl(ukf_finish_quad_kernel<false>, dim3(ctas), dim3(kQuadThreads), 0, stream, true, a);
   }
   if (a.n <= 128 * 1024) return launch_finish_tpb<64>(a, stream);
   return launch_finish_tpb<128>(a, stream);

@@ -54,6 +54,11 @@ struct UkfArgs {
   uint32_t* vis_truth;
   uint32_t* vis_est;
   double body_radius, vis_tol;
+  // cooperative measurement updates (quad kernel only; task_of == NULL: in-line update): task_of[j]
+  // = global index of the target sensor j validly tasks this step, or -1 (written by the pre-step
+  // kernel); sensors of one environment are task_env_sensors consecutive entries
+  const int64_t* task_of;
+  int64_t task_sensors, task_env_sensors;
   PeerPush pp;
   pc_ukf_params p;
 };

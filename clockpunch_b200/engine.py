@@ -70,6 +70,7 @@ class CatalogEngine:
         self.est_x.copy_(state_buf(np.asarray(est_x, dtype=np.float64).reshape(6, -1), self.ld))
         self.sig_flags = torch.zeros((2, self.N), dtype=torch.int32, device=dev)
         self.sens_q = torch.zeros((self.ld_s, 4), dtype=f64, device=dev)   # double4 per sensor
+        self.task_of = torch.full((max(self.ld_s, 1),), -1, dtype=torch.int64, device=dev)   # pc_step_args.task_of
         self._sigma_valid = False   # blocks 1..12 match (est_x, est_p)?
         self.est_p = torch.from_numpy(np.ascontiguousarray(est_p, dtype=np.float64).reshape(self.N, 36)).to(dev)
         self.pred_p = self.est_p.clone()
@@ -160,6 +161,7 @@ class CatalogEngine:
         a.policy_probes, a.policy_seed = int(policy_probes), int(policy_seed)
         a.sigma_ws, a.sig_flags = self.sigma.data_ptr(), self.sig_flags.data_ptr()
         a.sens_q = self.sens_q.data_ptr()
+        a.task_of = self.task_of.data_ptr()
         a.env_targets, a.env_sensors = (self.Ne, self.Me) if self.E > 1 else (0, 0)
         if self._peer is not None:
             a.peer_table, a.peer_world, a.peer_rank = self._peer["table"].data_ptr(), self._peer["world"], self._peer["rank"]

@@ -314,6 +314,13 @@ typedef struct pc_step_args {
   int32_t peer_world, peer_rank;
   const void* summary_base;
   int64_t summary_bytes;
+  /* (M) int64 workspace or NULL.  With actions != NULL the sensor kernel records here which target
+   * each sensor validly tasks (-1: none), and -- for catalogs small enough that the step is latency
+   * bound (N <= 32768, M <= 256) -- the measurement updates of the few tasked targets are done by
+   * dedicated warps of the per-target kernel (one warp per tasked target, work split over its lanes)
+   * beside the untasked targets instead of lengthening the warps those targets sit in.  Results are
+   * the same filter equations either way; without the workspace the in-line update is used. */
+  int64_t* task_of;
 } pc_step_args;
 int pc_step_fused(pc_ctx* ctx, const pc_step_args* args, const pc_ukf_params* params,
                   pc_stream stream);

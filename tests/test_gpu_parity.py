@@ -323,7 +323,7 @@ def test_engine_steps_match_oracle():
         np.testing.assert_array_equal(eng.host("num_tasked"), orc.num_tasked)
         np.testing.assert_array_equal(eng.host("last_time_tasked"), orc.last_time_tasked)
     assert (eng.host("flags") == 0).all()
-    # the same steps through a captured CUDA graph (device clock, actions buffer) are bit-identical
+    # the same steps through a captured CUDA graph (device clock, actions buffer) give the same results
     eng.reset()
     rng = np.random.default_rng(5)
     direct = {}
@@ -339,7 +339,12 @@ def test_engine_steps_match_oracle():
         eng.actions[: cat.M].copy_(__import__("torch").from_numpy(a))
         eng.replay(gr)
     for k, v in direct.items():
-        np.testing.assert_array_equal(eng.host(k), v, err_msg=k)
+        if k in ("est_x", "est_p"):
+            # with an actions buffer the few tasked targets are updated by dedicated warps (pc_step_args.task_of):
+            # same equations as the in-line update of the mask path, sums in a different order
+            np.testing.assert_allclose(eng.host(k), v, rtol=1e-11, atol=1e-13, err_msg=k)
+        else:
+            np.testing.assert_array_equal(eng.host(k), v, err_msg=k)
     assert eng.time == 300.0
     # reset restores the construction-time snapshot exactly
     eng.reset()
