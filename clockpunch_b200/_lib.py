@@ -9,7 +9,7 @@ from fractions import Fraction
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libpunch_b200.so")
+LIB_PATH = os.environ.get("PUNCH_B200_LIB") or os.path.join(_HERE, "libpunch_b200.so")   # override: experiments only
 
 PC_OK, PC_ERR_BAD_ARG, PC_ERR_CUDA, PC_ERR_EQUAL_TIMES, PC_ERR_NO_DEVICE = 0, -1, -2, -3, -4
 KIND_SATELLITE, KIND_TERRESTRIAL = 0, 1

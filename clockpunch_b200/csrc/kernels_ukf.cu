@@ -531,16 +531,19 @@ constexpr int kVisTileSlots = (kVisTile / 32) * kVisRow;
 // (never visible) by the other threads through the generic proxy.
 // Environment of a target / of a sensor row.  A single catalog (env_targets == 0) skips the 64-bit
 // divisions, which cost more than the whole visibility phase of a small tile.
+// (32-bit divisions: target and row indices are below 2^32, and a 64-bit division is ~100 instructions
+// at every inlined site of kernels whose cost at small catalogs is instruction fetch)
 __device__ __forceinline__ int64_t env_of_target(int64_t t, int64_t env_targets) {
-  return env_targets > 0 ? t / env_targets : 0;
+  return env_targets > 0 ? (int64_t)((uint32_t)t / (uint32_t)env_targets) : 0;
 }
 __device__ __forceinline__ void row_split(int64_t r, int64_t wpr, bool single, int64_t& e, int64_t& w) {
   if (single) {
     e = 0;
     w = r;
   } else {
-    e = r / wpr;
-    w = r - e * wpr;
+    const uint32_t eq = (uint32_t)r / (uint32_t)wpr;
+    e = eq;
+    w = (int64_t)((uint32_t)r - eq * (uint32_t)wpr);
   }
 }
 
@@ -553,40 +556,47 @@ __device__ __forceinline__ void sensor_tile_init(uint64_t* mbar) {
   __syncthreads();
 }
 
+// (rolled loops, 32-bit index arithmetic: unrolled over the 8 rows with 64-bit divisions this was 600
+// instructions, inlined twice, on the path of kernels that are instruction-fetch bound at small N)
 __device__ __forceinline__ void load_sensor_tile(double4* __restrict__ tile, uint64_t* mbar,
                                                  const double4* __restrict__ sens_q, int64_t r0,
-                                                 int64_t row_end, int64_t Me, int64_t wpr, bool single,
+                                                 int64_t row_end, int64_t Me64, int64_t wpr64, bool single,
                                                  int tpb) {
   const double nan = __longlong_as_double(0x7ff8000000000000LL);
   const int nrows = (int)(row_end - r0 < kVisTile / 32 ? row_end - r0 : kVisTile / 32);
+  const uint32_t Me = (uint32_t)Me64, wpr = (uint32_t)wpr64, rbase = (uint32_t)r0;
   if (threadIdx.x == 0) {
     const unsigned mb = (unsigned)__cvta_generic_to_shared(mbar);
     // earlier generic-proxy reads of the tile (previous chunk) are ordered before the async writes
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     unsigned total = 0;
+#pragma unroll 1
     for (int rr = 0; rr < nrows; ++rr) {
-      int64_t e, w;
-      row_split(r0 + rr, wpr, single, e, w);
-      const int64_t cnt = Me - w * 32 < 32 ? Me - w * 32 : 32;
-      total += (unsigned)cnt * 32u;
+      const uint32_t r = rbase + (uint32_t)rr;
+      const uint32_t w = single ? r : r % wpr;
+      const uint32_t left = Me - w * 32u;
+      total += (left < 32u ? left : 32u) * 32u;
     }
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mb), "r"(total) : "memory");
+#pragma unroll 1
     for (int rr = 0; rr < nrows; ++rr) {
-      int64_t e, w;
-      row_split(r0 + rr, wpr, single, e, w);
-      const int64_t s0 = w * 32;
-      const int64_t cnt = Me - s0 < 32 ? Me - s0 : 32;
+      const uint32_t r = rbase + (uint32_t)rr;
+      const uint32_t e = single ? 0u : r / wpr;
+      const uint32_t w = r - e * wpr;
+      const uint32_t left = Me - w * 32u;
+      const unsigned bytes = (left < 32u ? left : 32u) * 32u;
       const unsigned dst = (unsigned)__cvta_generic_to_shared(tile + rr * kVisRow);
-      const double4* src = sens_q + e * Me + s0;
+      const double4* src = sens_q + ((uint64_t)e * Me + w * 32u);
       asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                   ::"r"(dst), "l"(src), "r"((unsigned)cnt * 32u), "r"(mb) : "memory");
+                   ::"r"(dst), "l"(src), "r"(bytes), "r"(mb) : "memory");
     }
   }
+#pragma unroll 1
   for (int j = threadIdx.x; j < kVisTile; j += tpb) {
     const int rr = j >> 5;
-    int64_t e, w;
-    row_split(r0 + rr, wpr, single, e, w);
-    const int64_t sl = w * 32 + (j & 31);
+    const uint32_t r = rbase + (uint32_t)rr;
+    const uint32_t w = single ? r : r % wpr;
+    const uint32_t sl = w * 32u + (uint32_t)(j & 31);
     if (!(rr < nrows && sl < Me)) tile[rr * kVisRow + (j & 31)] = make_double4(0.0, 0.0, 0.0, nan);
   }
 }
@@ -610,7 +620,11 @@ __device__ __forceinline__ void vis_word(const double4* __restrict__ row, const 
                                          uint32_t& wb) {
   wa = 0;
   wb = 0;
+#ifdef PC_V_UNROLL_VIS
 #pragma unroll
+#else
+#pragma unroll 1
+#endif
   for (int b0 = 0; b0 < 32; b0 += 8) {
     double4 s[8];
 #pragma unroll
@@ -624,8 +638,15 @@ __device__ __forceinline__ void vis_word(const double4* __restrict__ row, const 
 }
 
 // ---- peer push helpers (see PeerPush in ukf_args.cuh) ---------------------------------------------
+// (out of line: the peer loop would otherwise be inlined at every store site of kernels that mostly run
+// without peers)
 template <typename T>
-__device__ __forceinline__ void peer_store(const PeerPush& pp, int parity, int64_t field_off, int64_t idx, T v) {
+#ifdef PC_V_INLINE_PEER
+__device__ __forceinline__ void peer_store(
+#else
+__device__ __noinline__ void peer_store(
+#endif
+    const PeerPush& pp, int parity, int64_t field_off, int64_t idx, T v) {
   const int64_t off = ((int64_t)parity * pp.world + pp.rank) * pp.slot_bytes + field_off + idx * (int64_t)sizeof(T);
   for (int r = 0; r < pp.world; ++r)
     *reinterpret_cast<T*>(__ldg(pp.table + r) + off) = v;
@@ -939,7 +960,7 @@ cudaError_t launch_sigma_gen(const double* est_x, const double* est_p, const dou
 // their partial sums combined with two xor-shuffles (every lane ends up with bit-identical sums,
 // so the 6x6 algebra that follows is simply replicated), stores and sigma-point writes are
 // distributed by lane, and each lane packs every fourth 32-sensor word of both visibility rows.
-constexpr int kQuadThreads = 64;
+constexpr int kQuadThreads = 128;
 constexpr int64_t kQuadMaxTargets = 32 * 1024;  // above this one thread per target fills the machine
 
 // ---- cooperative measurement update: one WARP per tasked target ------------------------------------
@@ -970,23 +991,25 @@ constexpr int kCoopMaxSensors = 256;
 
 __device__ __forceinline__ int tri_row(int k) { return (k >= 6) + (k >= 11) + (k >= 15) + (k >= 18) + (k >= 20); }
 
-// Upper Cholesky W = U^T U by one warp, right-looking: step i scales row i, then every lane that owns
-// an entry below it subtracts the rank-one term.  Entry (a, b) receives the same fma sequence as in
-// chol_upper6_packed, so the factor is bit-identical.  W's upper triangle is destroyed.
-__device__ __noinline__ bool chol6_warp(double* __restrict__ W, double* __restrict__ U, int lane) {
-  const int k = lane < 21 ? lane : 20;
-  const int ra = tri_row(k), rb = k - uidx(ra, ra) + ra;
-  bool ok = true;
-#pragma unroll 1
-  for (int i = 0; i < 6; ++i) {
-    const double s = W[i * 7];
-    ok = ok && (s > 0.0);
-    const double d = rsqrt_fast(s);
-    if (lane < 21 && ra == i) U[i * 6 + rb] = W[i * 6 + rb] * d;
-    __syncwarp();
-    if (lane < 21 && ra > i) W[ra * 6 + rb] = fma(-U[i * 6 + ra], U[i * 6 + rb], W[ra * 6 + rb]);
-    __syncwarp();
+// Upper Cholesky of the symmetric 6x6 whose upper triangle is in W (row-major full-matrix layout),
+// factor written to U's upper triangle.  Every lane factors the whole matrix in registers (the
+// factorisation is one dependent chain: spreading it over lanes only adds shared-memory round trips
+// -- 2.4 k cycles against 0.8 k) with chol_upper6_packed itself, so the factor is bit-identical to
+// the in-line update's.  One copy of the code, called three times per update.
+__device__ __noinline__ bool chol6_warp(const double* __restrict__ W, double* __restrict__ U, int lane) {
+  double E[21], Ur[21];
+#pragma unroll
+  for (int i = 0; i < 6; ++i)
+#pragma unroll
+    for (int j = i; j < 6; ++j) E[uidx(i, j)] = W[i * 6 + j];
+  const bool ok = chol_upper6_packed(E, Ur);
+  if (lane == 0) {
+#pragma unroll
+    for (int i = 0; i < 6; ++i)
+#pragma unroll
+      for (int j = i; j < 6; ++j) U[i * 6 + j] = Ur[uidx(i, j)];
   }
+  __syncwarp();
   return ok;
 }
 
@@ -1039,7 +1062,7 @@ __device__ __noinline__ uint32_t coop_part1(const UkfArgs& a, CoopSmem& S, int64
     const int b = i / 6, c = i - 6 * b;
     if (wr) Xf[i] = a.sb[(int64_t)b * blk + (int64_t)c * ld + t];
   }
-  PC_COOP_CLOCK(1);
+  if (wr) PC_COOP_CLOCK(1);
   uint32_t flags = a.sig_flags && wr ? a.sig_flags[t] : 0u;
   const uint64_t rng_step = a.clock ? a.clock->step_cur : a.rng_step;
   if (a.z) {
@@ -1071,13 +1094,13 @@ __device__ __noinline__ uint32_t coop_part1(const UkfArgs& a, CoopSmem& S, int64
     S.nrm[2 * lane + 1] = rad * sn;
   }
   __syncwarp();
-  PC_COOP_CLOCK(2);
+  if (wr) PC_COOP_CLOCK(2);
 
   // ---- unscented transform ----------------------------------------------------------------------
   if (lane < 6) {
     const double x0 = S.X[0][lane];
     double sb_ = 0.0;
-#pragma unroll 1
+#pragma unroll
     for (int j = 0; j < 6; ++j) sb_ += 0.5 * ((S.X[1 + j][lane] - x0) + (S.X[7 + j][lane] - x0));
     const double mm = fma(2.0 * p.wi, sb_, p.eps_w * x0);
     const double pxx = x0 + mm;
@@ -1087,15 +1110,16 @@ __device__ __noinline__ uint32_t coop_part1(const UkfArgs& a, CoopSmem& S, int64
     S.delta[lane] = p.eps_w * pxx;
     if (!a.z) {   // Target.getMeasurement (agents.py:173-183): z ~ N(truth', R)
       double acc = S.X[13][lane];
-#pragma unroll 1
-      for (int i = 0; i <= lane; ++i) acc = fma(p.Lr[lane * 6 + i], S.nrm[i], acc);
+#pragma unroll
+      for (int i = 0; i < 6; ++i)
+        if (i <= lane) acc = fma(p.Lr[lane * 6 + i], S.nrm[i], acc);
       S.z[lane] = acc;
     }
   }
   double F = 0.0;
   {
     const double x0a = S.X[0][ra], x0b = S.X[0][rb];
-#pragma unroll 1
+#pragma unroll
     for (int j = 0; j < 6; ++j) {
       const double pa = S.X[1 + j][ra], ma = S.X[7 + j][ra], pb = S.X[1 + j][rb], mb = S.X[7 + j][rb];
       const double ba = 0.5 * ((pa - x0a) + (ma - x0a)), bb = 0.5 * ((pb - x0b) + (mb - x0b));
@@ -1109,7 +1133,6 @@ __device__ __noinline__ uint32_t coop_part1(const UkfArgs& a, CoopSmem& S, int64
     const double e = fma(p.wi, fma(2.0, cross, F), fma(p.wc0 * ma, mb, p.Q[ra * 6 + rb]));
     S.P[ra * 6 + rb] = e;
     S.P[rb * 6 + ra] = e;
-    S.W[ra * 6 + rb] = e;
   }
   if (lane < 6) S.nu[lane] = S.z[lane] - (S.px[lane] + S.delta[lane]);
   __syncwarp();
@@ -1117,27 +1140,28 @@ __device__ __noinline__ uint32_t coop_part1(const UkfArgs& a, CoopSmem& S, int64
 #pragma unroll
     for (int i = lane; i < 36; i += 32) a.out_pred_p[t * 36 + i] = S.P[i];
   }
-  PC_COOP_CLOCK(3);
-  if (!chol6_warp(S.W, S.U2, lane) && wr) {
+  if (wr) PC_COOP_CLOCK(3);
+  if (!chol6_warp(S.P, S.U2, lane) && wr) {
     flags |= PC_FLAG_NONPD_PRED;
     repair6_warp(S.P, S.U2, lane);
   }
-  PC_COOP_CLOCK(4);
+  if (wr) PC_COOP_CLOCK(4);
 
   // ---- innovation covariance and its factor -------------------------------------------------------
   const double cuu = 2.0 * p.wi * p.gamma * p.gamma;
   const double cdd = p.wc0 + 12.0 * p.wi;
   if (lane < 21) {
     double acc = 0.0;
-#pragma unroll 1
-    for (int j = rb; j < 6; ++j) acc = fma(S.U2[ra * 6 + j], S.U2[rb * 6 + j], acc);
+#pragma unroll
+    for (int j = 0; j < 6; ++j)
+      if (j >= rb) acc = fma(S.U2[ra * 6 + j], S.U2[rb * 6 + j], acc);
     S.W[ra * 6 + rb] = fma(cuu, acc, fma(cdd * S.delta[ra], S.delta[rb], p.R[ra * 6 + rb]));
   }
   __syncwarp();
   if (!chol6_warp(S.W, S.Us, lane)) flags |= PC_FLAG_NONPD_INNOV;
   if (lane < 6) S.dinv[lane] = 1.0 / S.Us[lane * 7];
   __syncwarp();
-  PC_COOP_CLOCK(5);
+  if (wr) PC_COOP_CLOCK(5);
   return flags;
 }
 
@@ -1163,49 +1187,53 @@ __device__ __noinline__ void coop_part2(const UkfArgs& a, CoopSmem& S, int64_t t
   double nis = 0.0;
   if (lane < 6) {
     const double sa = S.delta[lane] + c3 * S.m[lane];
-#pragma unroll 1
+    double D[6], g[6];
+#pragma unroll
+    for (int j = 0; j < 6; ++j) D[j] = S.X[1 + j][lane] - S.X[7 + j][lane];
+#pragma unroll
     for (int b = 0; b < 6; ++b) {
       double acc = 0.0;
-#pragma unroll 1
-      for (int j = b; j < 6; ++j) acc = fma(S.X[1 + j][lane] - S.X[7 + j][lane], S.U2[b * 6 + j], acc);
+#pragma unroll
+      for (int j = b; j < 6; ++j) acc = fma(D[j], S.U2[b * 6 + j], acc);
       double cab = fma(wg, acc, sa * S.delta[b]);
-#pragma unroll 1
-      for (int i = 0; i < b; ++i) cab = fma(-S.G[lane * 6 + i], S.Us[i * 6 + b], cab);
-      S.G[lane * 6 + b] = cab * S.dinv[b];
+#pragma unroll
+      for (int i = 0; i < b; ++i) cab = fma(-g[i], S.Us[i * 6 + b], cab);
+      g[b] = cab * S.dinv[b];
+      S.G[lane * 6 + b] = g[b];
     }
   } else if (lane == 6) {
-#pragma unroll 1
+    double y[6];
+#pragma unroll
     for (int b = 0; b < 6; ++b) {
       double acc = S.nu[b];
-#pragma unroll 1
-      for (int i = 0; i < b; ++i) acc = fma(-S.Us[i * 6 + b], S.y[i], acc);
-      const double yb = acc * S.dinv[b];
-      S.y[b] = yb;
-      nis = fma(yb, yb, nis);
+#pragma unroll
+      for (int i = 0; i < b; ++i) acc = fma(-S.Us[i * 6 + b], y[i], acc);
+      y[b] = acc * S.dinv[b];
+      S.y[b] = y[b];
+      nis = fma(y[b], y[b], nis);
     }
   }
   nis = __shfl_sync(full, nis, 6);
   __syncwarp();
   if (lane < 6) {
     double x = S.px[lane];
-#pragma unroll 1
+#pragma unroll
     for (int b = 0; b < 6; ++b) x = fma(S.G[lane * 6 + b], S.y[b], x);
     S.xe[lane] = x;
   }
   if (lane < 21) {
     double acc = S.P[ra * 6 + rb];
-#pragma unroll 1
+#pragma unroll
     for (int i = 0; i < 6; ++i) acc = fma(-S.G[ra * 6 + i], S.G[rb * 6 + i], acc);
     S.PE[ra * 6 + rb] = acc;
     S.PE[rb * 6 + ra] = acc;
-    S.W[ra * 6 + rb] = acc;
   }
   __syncwarp();
 
   // ---- outputs ---------------------------------------------------------------------------------------
   if (wr) PC_COOP_CLOCK(6);
   double chk = 0.0;
-#pragma unroll 1
+#pragma unroll
   for (int c = 0; c < 6; ++c) chk += S.xe[c] + S.PE[c * 7];
   if (!isfinite(chk)) flags |= PC_FLAG_NONFINITE;
 #pragma unroll
@@ -1237,8 +1265,17 @@ __device__ __noinline__ void coop_part2(const UkfArgs& a, CoopSmem& S, int64_t t
     if (a.truth_out) a.truth_out[(int64_t)lane * ld + t] = S.X[13][lane];
   }
   if (wr) PC_COOP_CLOCK(7);
+}
+
+// Third piece: factor of the new covariance, next step's sigma points, estimated visibility row.
+__device__ __noinline__ void coop_part3(const UkfArgs& a, CoopSmem& S, int64_t t, int parity, int dry) {
+  const unsigned full = 0xffffffffu;
+  const int lane = threadIdx.x & 31;
+  const int64_t ld = a.ld, blk = 6 * a.ld;
+  const pc_ukf_params& p = a.p;
+  const bool wr = dry == 0;
   if (a.gen_next) {
-    const bool ok = chol6_warp(S.W, S.Un, lane);
+    const bool ok = chol6_warp(S.PE, S.Un, lane);
     if (!ok && wr) repair6_warp(S.PE, S.Un, lane);
     if (lane == 0) {
       const double r0[3] = {S.xe[0], S.xe[1], S.xe[2]}, v0[3] = {S.xe[3], S.xe[4], S.xe[5]};
@@ -1248,7 +1285,7 @@ __device__ __noinline__ void coop_part2(const UkfArgs& a, CoopSmem& S, int64_t t
         a.sig_flags[a.n + t] = rate;
       }
     }
-#pragma unroll 1
+#pragma unroll
     for (int i = lane; i < 78; i += 32) {
       const int b = i / 6, c = i - 6 * b;
       double v = S.xe[c];
@@ -1269,19 +1306,27 @@ __device__ __noinline__ void coop_part2(const UkfArgs& a, CoopSmem& S, int64_t t
     const double eq = horizon_q(ex, ey, ez, a.body_radius, a.vis_tol);
     const int64_t e = env_of_target(t, a.env_targets);
 #pragma unroll 1
-    for (int64_t w = 0; w < a.wpr; ++w) {
-      const int64_t sl = w * 32 + lane;
-      bool v = false;
-      if (sl < a.env_sensors) v = sees(a.sens_q[e * a.env_sensors + sl], ex, ey, ez, eq, RE2);
-      const uint32_t word = __ballot_sync(full, v);
-      if (lane == 0 && wr) {
-        a.vis_est[t * a.wpr + w] = word;
-        if (a.pp.world) peer_store(a.pp, parity, a.pp.off_vis_est, t * a.wpr + w, word);
+    for (int64_t w0 = 0; w0 < a.wpr; w0 += 4) {   // four words' sensors in flight at a time
+      double4 sv[4];
+      bool have[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int64_t sl = (w0 + u) * 32 + lane;
+        have[u] = w0 + u < a.wpr && sl < a.env_sensors;
+        if (have[u]) sv[u] = a.sens_q[e * a.env_sensors + sl];
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const bool v = have[u] && sees(sv[u], ex, ey, ez, eq, RE2);
+        const uint32_t word = __ballot_sync(full, v);
+        if (lane == 0 && wr && w0 + u < a.wpr) {
+          a.vis_est[t * a.wpr + w0 + u] = word;
+          if (a.pp.world) peer_store(a.pp, parity, a.pp.off_vis_est, t * a.wpr + w0 + u, word);
+        }
       }
     }
   }
   if (wr) PC_COOP_CLOCK(9);
-  else PC_COOP_CLOCK(10);
 }
 
 __device__ __forceinline__ double quad_sum(double v) {
@@ -1301,23 +1346,29 @@ __device__ __forceinline__ void store_sym36_quad(double* __restrict__ g, const d
   }
 }
 
+constexpr size_t kQuadSmem = sizeof(double4) * kVisTileSlots > 4 * sizeof(CoopSmem) ? sizeof(double4) * kVisTileSlots
+                                                                                    : 4 * sizeof(CoopSmem);
 template <bool COOP>
-__global__ void __launch_bounds__(kQuadThreads, 5)
+__global__ void __launch_bounds__(kQuadThreads, 3)
 ukf_finish_quad_kernel(const __grid_constant__ UkfArgs a) {
   constexpr bool ROLE = COOP;
-  __shared__ __align__(32) double4 tile[kVisTileSlots];
+  __shared__ __align__(32) unsigned char smem_raw[kQuadSmem];
   __shared__ uint64_t mbar_store;
-  static_assert(sizeof(CoopSmem) * (kQuadThreads / 32) <= sizeof(double4) * kVisTileSlots, "update warps reuse the tile");
+  static_assert(kQuadThreads == 128, "an update CTA is one real warp and three warm-up warps");
+  double4* tile = reinterpret_cast<double4*>(smem_raw);
   uint64_t* mbar = &mbar_store;
   if (ROLE && (int64_t)blockIdx.x < a.task_sensors && threadIdx.x >= 32) {
-    // Second warp of an update CTA, BEFORE the dependency wait: these CTAs are the first of the grid, so
-    // they become resident while the propagation kernel's last wave is still running.  The warp uses
-    // that time to run the second half of the update on scratch operands (nothing is written to
-    // global memory, whatever it reads may be stale): its instruction lines are then in this SM's
-    // instruction cache when the real update gets there.
-    CoopSmem* S = reinterpret_cast<CoopSmem*>(tile);
-    coop_scratch_init(S[1]);
-    coop_part2(a, S[1], 0, 0, 0u, 1);
+    // Warps 1..3 of an update CTA, BEFORE the dependency wait: these CTAs are the first of the grid, so
+    // they become resident while the propagation kernel's last wave is still running.  Each warp runs
+    // one piece of the update on scratch operands (nothing is written to global memory, whatever it
+    // reads may be stale): the instruction lines of that piece are then in this SM's instruction
+    // cache when warp 0 gets there with the real data.  (If the CTA only becomes resident after the
+    // propagation has finished, the three pieces are fetched in parallel beside warp 0's first one.)
+    CoopSmem& S = reinterpret_cast<CoopSmem*>(smem_raw)[threadIdx.x >> 5];
+    coop_scratch_init(S);
+    if (threadIdx.x < 64) coop_part1(a, S, 0, 1);
+    else if (threadIdx.x < 96) coop_part2(a, S, 0, 0, 0u, 1);
+    else coop_part3(a, S, 0, 0, 1);
   }
   pdl_wait();  // launched programmatically behind the propagation kernel: everything below reads its output
   pdl_trigger();  // a programmatic successor (the observation pack) may be scheduled behind our last wave
@@ -1335,22 +1386,17 @@ ukf_finish_quad_kernel(const __grid_constant__ UkfArgs a) {
     const int lane = threadIdx.x & 31;
     const int64_t j = (int64_t)blockIdx.x;
     int64_t tt = a.task_of[j];
-    const int64_t j0 = (j / a.task_env_sensors) * a.task_env_sensors;
+    const int j0 = (int)(((uint32_t)j / (uint32_t)a.task_env_sensors) * (uint32_t)a.task_env_sensors);
     bool dup = false;   // a lower-numbered sensor of the same environment already owns this target
-    for (int64_t jj = j0 + lane; jj < j; jj += 32) dup |= a.task_of[jj] == tt;
+#pragma unroll 1
+    for (int jj = j0 + lane; jj < (int)j; jj += 32) dup |= a.task_of[jj] == tt;
     if (__any_sync(0xffffffffu, dup)) tt = -1;
-    if (tt >= 0 && tt < a.n) {
-      CoopSmem* S = reinterpret_cast<CoopSmem*>(tile);
+    if (tt >= 0 && tt < a.n && threadIdx.x < 32) {
+      CoopSmem& S = reinterpret_cast<CoopSmem*>(smem_raw)[0];
       PC_COOP_CLOCK(0);
-      if (threadIdx.x < 32) {
-        const uint32_t fl = coop_part1(a, S[0], tt, 0);
-        coop_part2(a, S[0], tt, parity, fl, 0);
-      } else {
-        // after the wait: warm the first half's transform / factorisation code while warp 0 is still
-        // waiting for its loads
-        coop_scratch_init(S[1]);
-        coop_part1(a, S[1], tt, 1);
-      }
+      const uint32_t fl = coop_part1(a, S, tt, 0);
+      coop_part2(a, S, tt, parity, fl, 0);
+      coop_part3(a, S, tt, parity, 0);
     }
     if (a.pp.world) peer_publish(a.pp, step_done);
     return;

@@ -1,0 +1,13 @@
+#!/bin/bash
+# Build a variant of the library with extra -D flags on kernels_ukf.cu (experiments):
+#   tools/build_variant.sh NAME -DPC_V_...   ->  variants/libpunch_NAME.so   (use with PUNCH_B200_LIB=...)
+set -e
+cd "$(dirname "$0")/.."
+name=$1; shift
+mkdir -p variants
+F="-gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -std=c++17 -Xcompiler -fPIC --expt-relaxed-constexpr -Iinclude"
+nvcc $F "$@" -c clockpunch_b200/csrc/kernels_ukf.cu -o variants/ukf_$name.o
+nvcc -shared -o variants/libpunch_$name.so variants/ukf_$name.o clockpunch_b200/build/kernels_propagate.o \
+  clockpunch_b200/build/kernels_vis.o clockpunch_b200/build/kernels_env.o clockpunch_b200/build/api.o \
+  -gencode arch=compute_100a,code=sm_100a -cudart static
+echo variants/libpunch_$name.so
