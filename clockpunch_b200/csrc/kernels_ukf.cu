@@ -38,6 +38,35 @@
 #include "vis.cuh"
 
 // Phase stamps for tools/microbench/finish_phases.cu (no-ops in the library build).
+#ifdef PC_COOP_STAMPS   // tools/build_variant.sh stamps -DPC_COOP_STAMPS: in-pipeline timeline (tools/debug/coop_timeline.py)
+__device__ long long g_cstamp[12][256];
+__device__ unsigned long long g_gt[8];   // globaltimer: [0] min regular entry, [1] max regular exit, [2] min update entry, [3] max update exit
+__device__ __forceinline__ unsigned long long gtimer() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+  return t;
+}
+#define PC_COOP_CLOCK(i)                                                                     \
+  do {                                                                                       \
+    if ((threadIdx.x & 31) == 0 && blockIdx.x < 256) g_cstamp[i][blockIdx.x] = clock64();    \
+    if ((threadIdx.x & 31) == 0 && (i) == 0) atomicMin(&g_gt[2], gtimer());                  \
+    if ((threadIdx.x & 31) == 0 && (i) == 9) atomicMax(&g_gt[3], gtimer());                  \
+  } while (0)
+#define PC_PHASE_CLOCK(i)                                                                    \
+  do {                                                                                       \
+    if ((threadIdx.x & 31) == 0 && (i) == 0) atomicMin(&g_gt[0], gtimer());                  \
+    if ((threadIdx.x & 31) == 0 && (i) == 9) atomicMax(&g_gt[1], gtimer());                  \
+  } while (0)
+extern "C" int pc_debug_stamps(long long* cst, unsigned long long* gt, int reset) {
+  if (cst) cudaMemcpyFromSymbol(cst, g_cstamp, sizeof(g_cstamp));
+  if (gt) cudaMemcpyFromSymbol(gt, g_gt, sizeof(g_gt));
+  if (reset) {
+    unsigned long long z[8] = {~0ull, 0, ~0ull, 0, ~0ull, 0, ~0ull, 0};
+    cudaMemcpyToSymbol(g_gt, z, sizeof(z));
+  }
+  return 0;
+}
+#endif
 #ifndef PC_PHASE_CLOCK
 #define PC_PHASE_CLOCK(i)
 #endif
@@ -986,6 +1015,7 @@ struct CoopSmem {
   double P[36], W[36], U2[36], Us[36];   // pred_p; scratch; chol(pred_p); chol(innovation cvr)
   double G[36], PE[36], Un[36];          // gain factor; est_p; chol(est_p)
   double Sb[6], m[6], px[6], delta[6], nu[6], y[6], xe[6], dinv[6], nrm[6], z[6];
+  long long nt;                          // num_tasked[t], fetched with the sigma points
 };
 constexpr int kCoopMaxSensors = 256;
 
@@ -1057,12 +1087,16 @@ __device__ __noinline__ uint32_t coop_part1(const UkfArgs& a, CoopSmem& S, int64
   const int k = lane < 21 ? lane : 20;
   const int ra = tri_row(k), rb = k - uidx(ra, ra) + ra;
   double* Xf = &S.X[0][0];
+  // every global load of the update is issued here; the measurement draw below runs in their shadow
+  double xin[3] = {0.0, 0.0, 0.0};
 #pragma unroll
-  for (int i = lane; i < 84; i += 32) {
+  for (int u = 0; u < 3; ++u) {
+    const int i = lane + 32 * u;
     const int b = i / 6, c = i - 6 * b;
-    if (wr) Xf[i] = a.sb[(int64_t)b * blk + (int64_t)c * ld + t];
+    if (wr && i < 84) xin[u] = a.sb[(int64_t)b * blk + (int64_t)c * ld + t];
   }
-  if (wr) PC_COOP_CLOCK(1);
+  long long nt_in = 0;
+  if (wr && lane == 0 && a.num_tasked) nt_in = a.num_tasked[t];
   uint32_t flags = a.sig_flags && wr ? a.sig_flags[t] : 0u;
   const uint64_t rng_step = a.clock ? a.clock->step_cur : a.rng_step;
   if (a.z) {
@@ -1093,6 +1127,11 @@ __device__ __noinline__ uint32_t coop_part1(const UkfArgs& a, CoopSmem& S, int64
     S.nrm[2 * lane] = rad * cs;
     S.nrm[2 * lane + 1] = rad * sn;
   }
+  if (wr) PC_COOP_CLOCK(1);
+#pragma unroll
+  for (int u = 0; u < 3; ++u)
+    if (wr && lane + 32 * u < 84) Xf[lane + 32 * u] = xin[u];
+  if (lane == 0) S.nt = nt_in;
   __syncwarp();
   if (wr) PC_COOP_CLOCK(2);
 
@@ -1246,11 +1285,8 @@ __device__ __noinline__ void coop_part2(const UkfArgs& a, CoopSmem& S, int64_t t
     const float trv = ((float)S.PE[21] + (float)S.PE[28]) + (float)S.PE[35];
     if (a.tr_pos) a.tr_pos[t] = trp;
     if (a.tr_vel) a.tr_vel[t] = trv;
-    int64_t nt = 0;
-    if (a.num_tasked) {
-      nt = a.num_tasked[t] + 1;
-      a.num_tasked[t] = nt;
-    }
+    const int64_t nt = S.nt + 1;
+    if (a.num_tasked) a.num_tasked[t] = nt;
     if (a.last_time_tasked) a.last_time_tasked[t] = (float)t_now;
     if (a.pp.world) {
       peer_store(a.pp, parity, a.pp.off_tr_pos, t, trp);
@@ -1274,6 +1310,15 @@ __device__ __noinline__ void coop_part3(const UkfArgs& a, CoopSmem& S, int64_t t
   const int64_t ld = a.ld, blk = 6 * a.ld;
   const pc_ukf_params& p = a.p;
   const bool wr = dry == 0;
+  // the first four words' sensors are pulled into L1 before the factorisation (no register is tied up
+  // across the call)
+  const int64_t env = a.vis_est ? env_of_target(t, a.env_targets) : 0;
+#pragma unroll
+  for (int u = 0; u < 4; ++u) {
+    const int64_t sl = (int64_t)u * 32 + lane;
+    if (a.vis_est != nullptr && u < a.wpr && sl < a.env_sensors)
+      asm volatile("prefetch.global.L1 [%0];" ::"l"(a.sens_q + env * a.env_sensors + sl));
+  }
   if (a.gen_next) {
     const bool ok = chol6_warp(S.PE, S.Un, lane);
     if (!ok && wr) repair6_warp(S.PE, S.Un, lane);
@@ -1304,7 +1349,6 @@ __device__ __noinline__ void coop_part3(const UkfArgs& a, CoopSmem& S, int64_t t
     const double RE2 = a.body_radius * a.body_radius;
     const double ex = S.xe[0], ey = S.xe[1], ez = S.xe[2];
     const double eq = horizon_q(ex, ey, ez, a.body_radius, a.vis_tol);
-    const int64_t e = env_of_target(t, a.env_targets);
 #pragma unroll 1
     for (int64_t w0 = 0; w0 < a.wpr; w0 += 4) {   // four words' sensors in flight at a time
       double4 sv[4];
@@ -1313,7 +1357,7 @@ __device__ __noinline__ void coop_part3(const UkfArgs& a, CoopSmem& S, int64_t t
       for (int u = 0; u < 4; ++u) {
         const int64_t sl = (w0 + u) * 32 + lane;
         have[u] = w0 + u < a.wpr && sl < a.env_sensors;
-        if (have[u]) sv[u] = a.sens_q[e * a.env_sensors + sl];
+        if (have[u]) sv[u] = a.sens_q[env * a.env_sensors + sl];
       }
 #pragma unroll
       for (int u = 0; u < 4; ++u) {
