@@ -333,8 +333,9 @@ def run_own(args):
     value = world * N / (ms_per_step * 1e-3)
 
     # ---------------- roofline of the dominant kernel (separate pass) ----------------
-    # propagate_sigma_kernel: all 13 sigma points + the truth state of every target, one thread per
-    # state.  Its launch is bracketed by a CUDA-event pair recorded by the library on the launch
+    # propagate_sigma_kernel (two states per thread out of a sorted 256-target window; catalogs up to
+    # 16 k targets: propagate_sigma_single_kernel, one state per thread): all 13 sigma points + the
+    # truth state of every target.  Its launch is bracketed by a CUDA-event pair recorded by the library on the launch
     # stream.  This pass launches the step's kernels one by one (not the graph `value` replays):
     # inside a captured graph the pair would be two extra event-record NODES, whose latency (~4 us
     # each) would be charged to a 14 us kernel.
@@ -397,7 +398,8 @@ def run_own(args):
         pass
     hbm_peak = peaks.get("hbm_gbs", 6650.0)
     hbm_ach = 14 * 96.0 * N / (ukf_ms_avg * 1e-3) * 1e-9
-    roofline = {"bound": "fp64", "kernel": "propagate_sigma_kernel", "achieved": achieved_tf, "peak": peak_tf.value,
+    roofline = {"bound": "fp64", "kernel": "propagate_sigma_kernel" if N > 16 * 1024 else "propagate_sigma_single_kernel",
+                "achieved": achieved_tf, "peak": peak_tf.value,
                 "unit": "TFLOP/s", "frac": achieved_tf / peak_tf.value if peak_tf.value else None,
                 "traffic": TRAFFIC_NCU.get((N, M)), "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum of this "
                 "kernel in the committed ncu --set full capture of this workload (profiles/r1b_ncu_full_step_*_metrics.csv); "

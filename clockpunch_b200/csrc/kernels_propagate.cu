@@ -1,5 +1,6 @@
 // K1 / K2: batched agent propagation, one thread per state vector.
 // Layout: SoA (6, ld) FP64 -> each component row is read/written fully coalesced.
+#include <cstdlib>
 #include "propagate.cuh"
 
 namespace pc {
@@ -61,12 +62,37 @@ cudaError_t launch_propagate_agents(const double* x_in, double* x_out, const uin
 // and every thread then takes the target at its sorted position: warps become homogeneous
 // (at most one mixed warp per count boundary) while all accesses stay inside the CTA's own
 // 128-target window of each component row, so DRAM traffic is unchanged.
+#ifdef PC_COOP_STAMPS   // variant build: kernel entry / exit on the global timer (tools/debug/coop_timeline.py)
+__device__ unsigned long long g_pt[4];
+__device__ unsigned long long g_cta[2048][4];   // per CTA: entry, loads landed (thread 0), exit, max substeps
+__device__ __forceinline__ unsigned long long gtimer_p() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+  return t;
+}
+#define PC_PROP_STAMP(i, op) do { if ((threadIdx.x & 31) == 0) op(&g_pt[i], gtimer_p()); } while (0)
+extern "C" int pc_debug_prop_ctas(unsigned long long* out) {
+  return (int)cudaMemcpyFromSymbol(out, g_cta, sizeof(g_cta));
+}
+extern "C" int pc_debug_prop_stamps(unsigned long long* out, int reset) {
+  if (out) cudaMemcpyFromSymbol(out, g_pt, sizeof(g_pt));
+  if (reset) {
+    unsigned long long z[4] = {~0ull, 0, ~0ull, 0};
+    cudaMemcpyToSymbol(g_pt, z, sizeof(z));
+  }
+  return 0;
+}
+#else
+#define PC_PROP_STAMP(i, op)
+#endif
 constexpr int kPropThreads = 128;
 constexpr int kSortBuckets = 6;  // 0 = no work (past n), 1..4 = that many substeps, 5 = more
 
+// One state per thread, 128-target windows: used for catalogs of at most a few waves (see
+// launch_propagate_sigma), where CTAs that exit early matter more than balance inside a CTA.
 template <bool J2>
 __global__ void __launch_bounds__(kPropThreads, 4)
-propagate_sigma_kernel(double* __restrict__ sb, int64_t n, int64_t ld, double dt, int substeps,
+propagate_sigma_single_kernel(double* __restrict__ sb, int64_t n, int64_t ld, double dt, int substeps,
                        uint32_t* __restrict__ sig_aux) {
   __shared__ int s_wcnt[kPropThreads / 32][kSortBuckets];
   __shared__ uint16_t s_perm[kPropThreads];
@@ -141,12 +167,192 @@ propagate_sigma_kernel(double* __restrict__ sb, int64_t n, int64_t ld, double dt
   }
 }
 
+constexpr int kPropWindow = 2 * kPropThreads;   // targets per CTA: every thread advances two states
+constexpr int64_t kFoldMinTargets = 16 * 1024;  // below: one state per thread (see launch_propagate_sigma)
+
+template <bool J2>
+__global__ void __launch_bounds__(kPropThreads, 4)
+propagate_sigma_kernel(double* __restrict__ sb, int64_t n, int64_t ld, double dt, int substeps,
+                       uint32_t* __restrict__ sig_aux) {
+  __shared__ int s_cnt[2][kPropThreads / 32][kSortBuckets];
+  __shared__ uint16_t s_perm[kPropWindow];
+  __shared__ uint8_t s_nsub[kPropWindow];
+  __shared__ double s_x[6][kPropWindow];   // the window's states, copied asynchronously while the sort runs
+  const int tid = threadIdx.x;
+  // Programmatic dependent launch: this kernel needs nothing from its stream predecessor (the
+  // sensor / tasking kernel), so it runs beside it; its successor (the per-target stage) may be
+  // scheduled as soon as every CTA of this grid is resident.  One thread of the grid does wait for
+  // the predecessor, so that "this grid is done" implies "the sensor kernel is done" for the
+  // successor, which needs both.
+  pdl_trigger();
+  PC_PROP_STAMP(0, atomicMin);
+#ifdef PC_COOP_STAMPS
+  const int cta_id = blockIdx.y * gridDim.x + blockIdx.x;
+  if (tid == 0 && cta_id < 2048) { g_cta[cta_id][0] = gtimer_p(); g_cta[cta_id][3] = 0; }
+#endif
+  if (blockIdx.x == 0 && blockIdx.y == 0 && tid == 0) pdl_wait();
+  const int64_t t0 = (int64_t)blockIdx.x * kPropWindow;
+  const int i = blockIdx.y;
+  double* blk = sb + (int64_t)i * 6 * ld;
+  int slot[2] = {tid, kPropThreads + tid};
+  int nsub[2] = {substeps, substeps};
+  // Both states at this thread's own positions are requested first (global -> shared, no registers):
+  // they travel while the rates are fetched and the window is sorted -- one trip to HBM instead of
+  // two (rates, then the sorted slots' states) -- and change hands through shared memory afterwards.
+#pragma unroll
+  for (int h = 0; h < 2; ++h) {
+    const int64_t t = t0 + h * kPropThreads + tid;
+    if (t < n) {
+#pragma unroll
+      for (int c = 0; c < 6; ++c) {
+        const unsigned dst = (unsigned)__cvta_generic_to_shared(&s_x[c][h * kPropThreads + tid]);
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst), "l"(blk + (int64_t)c * ld + t) : "memory");
+      }
+    }
+  }
+  asm volatile("cp.async.commit_group;" ::: "memory");
+  if (substeps <= 0) {
+    // blocks 0..12 use the orbit rate stored with the sigma points (computed from the centre point
+    // when they were generated); the truth state (13) uses its own
+    int mine[2], key[2];
+    if (i == 13) asm volatile("cp.async.wait_group 0;" ::: "memory");   // own copies: visible to this thread
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const int64_t t = t0 + h * kPropThreads + tid;
+      mine[h] = 0;
+      if (t < n) {
+        float om;
+        if (i == 13) {
+          const int o = h * kPropThreads + tid;
+          const double r[3] = {s_x[0][o], s_x[1][o], s_x[2][o]};
+          const double v[3] = {s_x[3][o], s_x[4][o], s_x[5][o]};
+          om = orbit_rate(r, v);
+        } else {
+          om = __uint_as_float(sig_aux[n + t]);
+        }
+        bool cl = false;
+        mine[h] = substeps_from_rate(om, dt, &cl);
+        if (i == 0 && cl) sig_aux[t] |= PC_FLAG_SUBSTEP_CLAMP;
+      }
+      key[h] = mine[h] < kSortBuckets - 1 ? mine[h] : kSortBuckets - 1;
+    }
+    // Stable counting sort of the window's 256 states by substep count, HEAVIEST FIRST (ballot + popc,
+    // one shared-memory round trip).  Thread j then takes sorted positions j and 255 - j: the j-th
+    // heaviest state and the j-th lightest.  Neighbouring lanes get equal counts in both rounds (no
+    // divergence inside a warp), and every thread of the CTA does about the same total work, so no
+    // warp sits idle holding registers while the CTA's slowest one finishes (with one state per
+    // thread the CTA lasted 3 substeps where the mean is 1.5: half the FP64 issue slots of a
+    // 10^4-target catalog were empty).  All accesses stay inside the CTA's own window of each
+    // component row, so DRAM traffic is unchanged.
+    const int w = tid >> 5, lane = tid & 31;
+    int rank[2] = {0, 0};
+#pragma unroll
+    for (int h = 0; h < 2; ++h)
+#pragma unroll
+      for (int b = 0; b < kSortBuckets; ++b) {
+        const unsigned m = __ballot_sync(0xffffffffu, key[h] == b);
+        if (key[h] == b) rank[h] = __popc(m & ((1u << lane) - 1u));
+        if (lane == 0) s_cnt[h][w][b] = __popc(m);
+      }
+    s_nsub[tid] = (uint8_t)(mine[0] < 255 ? mine[0] : 255);
+    s_nsub[kPropThreads + tid] = (uint8_t)(mine[1] < 255 ? mine[1] : 255);
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    __syncthreads();
+    int pos[2] = {rank[0], rank[1]};
+#pragma unroll
+    for (int b = 0; b < kSortBuckets; ++b)
+#pragma unroll
+      for (int hh = 0; hh < 2; ++hh)
+#pragma unroll
+        for (int ww = 0; ww < kPropThreads / 32; ++ww) {
+          const int c = s_cnt[hh][ww][b];
+#pragma unroll
+          for (int h = 0; h < 2; ++h)
+            if (b > key[h] || (b == key[h] && (hh < h || (hh == h && ww < w)))) pos[h] += c;
+        }
+    s_perm[pos[0]] = (uint16_t)tid;
+    s_perm[pos[1]] = (uint16_t)(kPropThreads + tid);
+    __syncthreads();
+    slot[0] = s_perm[tid];
+    slot[1] = s_perm[kPropWindow - 1 - tid];
+    nsub[0] = s_nsub[slot[0]];
+    nsub[1] = s_nsub[slot[1]];
+    // counts above 254 (clamped orbit rates, extreme steps) are rare: take them from the rule again
+    if (nsub[0] == 255 || nsub[1] == 255) {
+#pragma unroll
+      for (int h = 0; h < 2; ++h)
+        if (nsub[h] == 255) {
+          const int64_t t = t0 + slot[h];
+          float om;
+          if (i == 13) {
+            const double r[3] = {s_x[0][slot[h]], s_x[1][slot[h]], s_x[2][slot[h]]};
+            const double v[3] = {s_x[3][slot[h]], s_x[4][slot[h]], s_x[5][slot[h]]};
+            om = orbit_rate(r, v);
+          } else {
+            om = __uint_as_float(sig_aux[n + t]);
+          }
+          nsub[h] = substeps_from_rate(om, dt, nullptr);
+        }
+    }
+  } else {
+    if (t0 + tid >= n) nsub[0] = 0;
+    if (t0 + kPropThreads + tid >= n) nsub[1] = 0;
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    __syncthreads();
+  }
+#pragma unroll 1
+  for (int h = 0; h < 2; ++h) {
+    if (nsub[h] == 0) continue;  // past the end of the catalog
+    double* base = blk + t0 + slot[h];
+    double r[3], v[3];
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      r[c] = s_x[c][slot[h]];
+      v[c] = s_x[c + 3][slot[h]];
+    }
+#ifdef PC_COOP_STAMPS
+    if (cta_id < 2048 && h == 0) {
+      if (r[0] + v[0] != 1e300 && tid == 0) g_cta[cta_id][1] = gtimer_p();
+      atomicMax(&g_cta[cta_id][3], (unsigned long long)nsub[0]);
+    }
+#endif
+    propagate_state<J2>(r, v, dt, nsub[h]);
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      base[(int64_t)c * ld] = r[c];
+      base[(int64_t)(c + 3) * ld] = v[c];
+    }
+  }
+  PC_PROP_STAMP(1, atomicMax);
+#ifdef PC_COOP_STAMPS
+  if (cta_id < 2048) atomicMax(&g_cta[cta_id][2], gtimer_p());
+#endif
+}
+
 cudaError_t launch_propagate_sigma(double* sb, int64_t n, int64_t ld, int have_truth, double t0,
                                    double tf, int substeps, int force_model, uint32_t* sig_flags,
                                    bool beside_predecessor, cudaStream_t stream) {
   if (n <= 0) return cudaSuccess;
-  const dim3 grid((unsigned)((n + kPropThreads - 1) / kPropThreads), have_truth ? 14 : 13);
-  if (force_model == PC_FORCE_TWOBODY_J2)
+  const unsigned blocks = have_truth ? 14 : 13;
+  const bool j2 = force_model == PC_FORCE_TWOBODY_J2;
+  // Two mappings.  Large catalogs: two states per thread out of a sorted 256-target window (every thread
+  // of a CTA does about the same work: 93 % of the measured FP64 peak at 10^6 targets against 81 % with
+  // one state per thread).  Catalogs of a wave or two of CTAs: one state per thread -- the grid is two
+  // waves of short CTAs, the second of which frees SM slots one by one, and the per-target kernel
+  // launched programmatically behind this one uses exactly that window to bring its update warps'
+  // code into the instruction caches (36.5 vs 33.9 us per step at 10^4 targets).
+  static const int force = getenv("PC_PROP_FOLD") ? atoi(getenv("PC_PROP_FOLD")) : 0;   // experiments: 1 / 2
+  const bool fold = force ? force == 2 : n > kFoldMinTargets;
+  if (!fold) {
+    const dim3 grid((unsigned)((n + kPropThreads - 1) / kPropThreads), blocks);
+    if (j2)
+      return launch_pdl(propagate_sigma_single_kernel<true>, grid, dim3(kPropThreads), 0, stream, beside_predecessor,
+                        sb, n, ld, tf - t0, substeps, sig_flags);
+    return launch_pdl(propagate_sigma_single_kernel<false>, grid, dim3(kPropThreads), 0, stream, beside_predecessor,
+                      sb, n, ld, tf - t0, substeps, sig_flags);
+  }
+  const dim3 grid((unsigned)((n + kPropWindow - 1) / kPropWindow), blocks);
+  if (j2)
     return launch_pdl(propagate_sigma_kernel<true>, grid, dim3(kPropThreads), 0, stream, beside_predecessor, sb, n,
                       ld, tf - t0, substeps, sig_flags);
   return launch_pdl(propagate_sigma_kernel<false>, grid, dim3(kPropThreads), 0, stream, beside_predecessor, sb, n, ld,

@@ -1101,8 +1101,9 @@ __device__ __noinline__ uint32_t coop_part1(const UkfArgs& a, CoopSmem& S, int64
   const uint64_t rng_step = a.clock ? a.clock->step_cur : a.rng_step;
   if (a.z) {
     if (lane < 6 && wr) S.z[lane] = a.z[(int64_t)lane * ld + t];
-  } else if (lane < 3) {
-    // the three Box-Muller pairs of normal6(), one per lane (same counters, same arithmetic)
+  } else if (lane < 3 && wr) {
+    // the three Box-Muller pairs of normal6(), one per lane (same counters, same arithmetic); runs in
+    // the shadow of the loads above, so the warm-up warp skips it and starts ahead at the transform
     uint32_t c[4] = {(uint32_t)t, (uint32_t)((uint64_t)t >> 32), (uint32_t)rng_step, (uint32_t)(rng_step >> 32)};
     if (lane == 2) c[3] ^= 0x5bd1e995u + 1u;
     uint32_t k0 = (uint32_t)a.rng_seed, k1 = (uint32_t)(a.rng_seed >> 32);
@@ -1310,15 +1311,7 @@ __device__ __noinline__ void coop_part3(const UkfArgs& a, CoopSmem& S, int64_t t
   const int64_t ld = a.ld, blk = 6 * a.ld;
   const pc_ukf_params& p = a.p;
   const bool wr = dry == 0;
-  // the first four words' sensors are pulled into L1 before the factorisation (no register is tied up
-  // across the call)
   const int64_t env = a.vis_est ? env_of_target(t, a.env_targets) : 0;
-#pragma unroll
-  for (int u = 0; u < 4; ++u) {
-    const int64_t sl = (int64_t)u * 32 + lane;
-    if (a.vis_est != nullptr && u < a.wpr && sl < a.env_sensors)
-      asm volatile("prefetch.global.L1 [%0];" ::"l"(a.sens_q + env * a.env_sensors + sl));
-  }
   if (a.gen_next) {
     const bool ok = chol6_warp(S.PE, S.Un, lane);
     if (!ok && wr) repair6_warp(S.PE, S.Un, lane);

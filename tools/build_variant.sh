@@ -6,8 +6,10 @@ cd "$(dirname "$0")/.."
 name=$1; shift
 mkdir -p variants
 F="-gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -std=c++17 -Xcompiler -fPIC --expt-relaxed-constexpr -Iinclude"
-nvcc $F "$@" -c clockpunch_b200/csrc/kernels_ukf.cu -o variants/ukf_$name.o
-nvcc -shared -o variants/libpunch_$name.so variants/ukf_$name.o clockpunch_b200/build/kernels_propagate.o \
+nvcc $F "$@" -c clockpunch_b200/csrc/kernels_ukf.cu -o variants/ukf_$name.o &
+nvcc $F "$@" -c clockpunch_b200/csrc/kernels_propagate.cu -o variants/prop_$name.o &
+wait
+nvcc -shared -o variants/libpunch_$name.so variants/ukf_$name.o variants/prop_$name.o \
   clockpunch_b200/build/kernels_vis.o clockpunch_b200/build/kernels_env.o clockpunch_b200/build/api.o \
   -gencode arch=compute_100a,code=sm_100a -cudart static
 echo variants/libpunch_$name.so
