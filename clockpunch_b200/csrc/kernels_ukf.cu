@@ -644,16 +644,15 @@ __device__ __forceinline__ void wait_sensor_tile(uint64_t* mbar, unsigned phase)
 
 // One 32-sensor word of both visibility rows of a target.  Sensors are fetched from shared memory
 // eight at a time before they are tested, so that the LDS latency is paid once per batch.
+// (ROLLED: the small-catalog kernel is bound by instruction fetch and takes the loop; the large-catalog
+// kernels are bound by issue slots and take the straight-line form)
+template <bool ROLLED>
 __device__ __forceinline__ void vis_word(const double4* __restrict__ row, const double (&tr)[3], double tq,
                                          const double (&xe)[6], double eq, double RE2, uint32_t& wa,
                                          uint32_t& wb) {
   wa = 0;
   wb = 0;
-#ifdef PC_V_UNROLL_VIS
-#pragma unroll
-#else
-#pragma unroll 1
-#endif
+#pragma unroll(ROLLED ? 1 : 4)
   for (int b0 = 0; b0 < 32; b0 += 8) {
     double4 s[8];
 #pragma unroll
@@ -961,7 +960,7 @@ ukf_finish_kernel(const __grid_constant__ UkfArgs a) {
         const int64_t rr = my_row0 + w - r0;
         if (rr >= 0 && rr < nrows) {
           uint32_t wa, wb;
-          vis_word(tile + rr * kVisRow, tr, tq, xe, eq, RE2, wa, wb);
+          vis_word<false>(tile + rr * kVisRow, tr, tq, xe, eq, RE2, wa, wb);
           if (live) {
             a.vis_truth[t * wpr + w] = wa;
             a.vis_est[t * wpr + w] = wb;
@@ -1673,7 +1672,7 @@ ukf_finish_quad_kernel(const __grid_constant__ UkfArgs a) {
         const int64_t rr = my_row0 + w - r0;
         if (rr >= 0 && rr < nrows) {
           uint32_t wa, wb;
-          vis_word(tile + rr * kVisRow, tr, tq, xe, eq, RE2, wa, wb);
+          vis_word<true>(tile + rr * kVisRow, tr, tq, xe, eq, RE2, wa, wb);
           if (live) a.vis_truth[t * wpr + w] = wa;
           if (mine) {
             a.vis_est[t * wpr + w] = wb;
