@@ -726,3 +726,41 @@ def test_empty_and_degenerate_inputs():
     # a state at the origin-crossing extreme takes the clamped substep path and returns
     fall = np.array([[6500.0, 0, 0, 0, 0.01, 0]]).T               # nearly radial plunge: orbit rate clamp
     assert np.isfinite(SatDynamicsModel().propagate(fall, 0.0, 10.0)).all()
+
+
+@pytest.mark.parametrize("given_z", [False, True])
+def test_update_warps_equal_inline_update(given_z):
+    """With an actions buffer the tasked targets are updated by dedicated warps of the per-target kernel
+    (pc_step_args.task_of); with a tasking mask by the in-line update of the target's own lanes.  Same
+    equations: results agree to round-off, bookkeeping exactly -- also when several sensors task the
+    same target (one update, num_tasked + 1) and when the measurement is drawn on the device (both
+    paths key the draw by (seed, step, target))."""
+    from clockpunch_b200.engine import CatalogEngine
+    from clockpunch_b200.simulation.catalog import synth_catalog
+    cat = synth_catalog(150, 24, seed=77, space_sensor_frac=0.3)
+    mk = lambda: CatalogEngine(cat.sensors, cat.sensor_kinds, cat.targets, cat.est_x, cat.est_p, cat.Q, cat.R, seed=9)
+    a, b = mk(), mk()
+    rng = np.random.default_rng(3)
+    n_upd = 0
+    for s in range(4):
+        vis = a.host("vis_est")                                       # (N, M) estimated map of the previous step
+        acts = np.full(cat.M, cat.N, np.int64)
+        for j in range(cat.M):
+            seen = np.flatnonzero(vis[:, j])
+            if len(seen):
+                acts[j] = seen[rng.integers(0, min(3, len(seen)))]   # few distinct picks: duplicates on purpose
+        acts[::5] = rng.integers(0, cat.N + 1, size=len(acts[::5]))  # and some actions on invisible targets / inaction
+        z = (cat.targets + rng.normal(size=cat.targets.shape)) if given_z else None
+        a.step(dt=100.0, actions=acts, z=z)
+        b.task_from_actions(acts)
+        b.step(dt=100.0, tasked=b.tasked, z=z)
+        for k in ("truth_x", "vis_truth", "vis_est", "num_tasked", "last_time_tasked", "flags"):
+            np.testing.assert_array_equal(a.host(k), b.host(k), err_msg=f"{k} step {s}")
+        # (the transform's weights are -2e6 / +1.7e5: a different summation order moves pred_p by ~1e-10
+        # relative, inside the bar of SURVEY.md section 8d -- covariances 1e-8, est_x 1e-5 km per step)
+        assert (np.abs(a.host("est_x") - b.host("est_x")).max(axis=0) <= estx_tol(b.host("est_x")) * (s + 1)).all(), f"est_x step {s}"
+        assert cov_close(a.host("est_p"), b.host("est_p"), 1e-8 * (s + 1)), f"est_p step {s}"
+        assert cov_close(a.host("pred_p"), b.host("pred_p"), 1e-8 * (s + 1)), f"pred_p step {s}"
+        np.testing.assert_allclose(a.host("nis"), b.host("nis"), rtol=1e-6, equal_nan=True, err_msg=f"nis step {s}")
+        n_upd = int(a.host("num_tasked").sum())
+    assert n_upd > 8 and a.host("num_tasked").max() <= 4      # updates happened; never two in one step
