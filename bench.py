@@ -256,7 +256,9 @@ def run_own(args):
         if args.exchange in ("peer", "auto"):
             try:
                 eng.enable_peer_push()
-                exchange = ("peer stores from the per-target kernel" if N <= 32768 else
+                mode = os.environ.get("PC_PEER_MODE", "")
+                by_copy = mode == "copy" or (mode != "store" and (N > 32768 or world >= 8))
+                exchange = ("peer stores from the per-target kernel" if not by_copy else
                             "summary pushed into every peer by a copy kernel behind the per-target kernel") + \
                     " (symmetric memory over NVLink) + flag wait"
             except Exception as exc:        # no symmetric memory on this box: keep the collective

@@ -869,7 +869,9 @@ int pc_step_fused(pc_ctx* ctx, const pc_step_args* a, const pc_ukf_params* param
       const char* e = getenv("PC_PEER_MODE");
       return !e ? 0 : (std::strcmp(e, "copy") == 0 ? 2 : (std::strcmp(e, "store") == 0 ? 1 : 0));
     }();
-    const bool peer_copy = peer_mode == 2 || (peer_mode == 0 && a->N > 32768);
+    // (8 peers: 72 remote 4-byte stores per target from the latency-critical kernel lose to the copy
+    // kernel also at 10 k targets per shard, 55.0 vs 57.2 us per step)
+    const bool peer_copy = peer_mode == 2 || (peer_mode == 0 && (a->N > 32768 || a->peer_world >= 8));
     pc::PeerPush pp_copy{};
     if (a->peer_table) {
       const char* base = static_cast<const char*>(a->summary_base);

@@ -52,11 +52,17 @@ __device__ __forceinline__ unsigned long long gtimer() {
     if ((threadIdx.x & 31) == 0 && (i) == 0) atomicMin(&g_gt[2], gtimer());                  \
     if ((threadIdx.x & 31) == 0 && (i) == 9) atomicMax(&g_gt[3], gtimer());                  \
   } while (0)
+__device__ long long g_pstamp[10][2048];   // regular path: per-warp phase stamps (clock64)
 #define PC_PHASE_CLOCK(i)                                                                    \
   do {                                                                                       \
     if ((threadIdx.x & 31) == 0 && (i) == 0) atomicMin(&g_gt[0], gtimer());                  \
     if ((threadIdx.x & 31) == 0 && (i) == 9) atomicMax(&g_gt[1], gtimer());                  \
+    if ((threadIdx.x & 31) == 0) {                                                           \
+      const int wid_ = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;                         \
+      if (wid_ < 2048) g_pstamp[i][wid_] = clock64();                                        \
+    }                                                                                        \
   } while (0)
+extern "C" int pc_debug_phase_stamps(long long* out) { return (int)cudaMemcpyFromSymbol(out, g_pstamp, sizeof(g_pstamp)); }
 extern "C" int pc_debug_stamps(long long* cst, unsigned long long* gt, int reset) {
   if (cst) cudaMemcpyFromSymbol(cst, g_cstamp, sizeof(g_cstamp));
   if (gt) cudaMemcpyFromSymbol(gt, g_gt, sizeof(g_gt));

@@ -52,3 +52,13 @@ print("propagation CTAs (last replay): %d; entry times: %.2f us median, %d enter
 for k in sorted(set(ns)):
     m = ns == k
     print("  max substeps %d: %4d CTAs, entry -> loads landed %.2f us, entry -> exit %.2f us (max %.2f)" % (k, m.sum(), ld[m].mean(), ex[m].mean(), ex[m].max()))
+ps = np.zeros((10, 2048), np.int64)
+lib.pc_debug_phase_stamps(ps.ctypes.data_as(C.c_void_p))
+w0, w1 = 100 * 4, 100 * 4 + 4 * ((N + 31) // 32)         # warps of the regular CTAs (behind the M update CTAs)
+pn = ["", "entry, loads + tile issued", "pair loads + F accumulate", "quad reduce", "m, pred_p", "tasked flag", "outputs (P stores)",
+      "chol + sigma writes", "tile wait", "vis words"]
+d = np.diff(ps[:, w0:min(w1, 2048)], axis=0)
+print("regular warps (last replay), cycles per phase:")
+for i in range(1, 10):
+    print(f"  {i} {pn[i]:28s} mean {d[i - 1].mean():8.0f}  max {d[i - 1].max():8.0f}")
+print("  total mean %.0f" % d.sum(axis=0).mean())
