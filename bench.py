@@ -47,7 +47,10 @@ FLOP_DOP853_STEP = 1150.0          # one fixed DOP853 step: 12 RHS + stage sums 
 FLOP_UKF_NOMEAS, FLOP_UKF_MEAS = 1500.0, 5600.0
 FLOP_VIS_PAIR = 8.0
 # DRAM traffic per launch of propagate_sigma_kernel from the committed ncu captures: (targets, sensors) -> bytes
-TRAFFIC_NCU = {(10_000, 100): 6.784e6 + 0.0, (1_000_000, 100): 680.1e6 + 614.4e6}
+TRAFFIC_NCU = {(10_000, 100): 6.784e6 + 0.0, (1_000_000, 100): 680.5e6 + 614.8e6}
+# the same kernel's gpu__time_duration.sum (ms, mean of 26 launches) in the committed launch lists
+# profiles/r1d_launches_bench_{10k,1M}.csv: what the kernel itself takes, without the event pair's ~8 us
+NCU_KERNEL_MS = {(10_000, 100): 0.013758, (1_000_000, 100): 0.724994}
 BYTES_TARGET_STEP = 1130.0         # truth/est_x/est_p r+w, pred_p w, z r (+ M/4 vis bits)
 
 
@@ -404,12 +407,18 @@ def run_own(args):
                 "achieved": achieved_tf, "peak": peak_tf.value,
                 "unit": "TFLOP/s", "frac": achieved_tf / peak_tf.value if peak_tf.value else None,
                 "traffic": TRAFFIC_NCU.get((N, M)), "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum of this "
-                "kernel in the committed ncu --set full capture of this workload (profiles/r1b_ncu_full_step_*_metrics.csv); "
+                "kernel in the committed ncu --set full capture of this workload (profiles/r1d_ncu_full_step_*_metrics.csv); "
                 "null for other sizes", "peak_source": "FP64 DFMA probe measured live in this run (pc_fp64_peak); "
                 "MEASURED_PEAKS.json has no FP64 entry (HBM/bf16 only); nominal 37 TFLOP/s",
                 "flop_per_launch": flop_per_launch, "dop853_steps_per_launch": state_steps,
                 "mean_substeps_per_sigma_propagate": substeps_used,
                 "kernel_ms": ukf_ms_avg, "kernel_share_of_step": ukf_ms_avg / ms_per_step,
+                "kernel_ms_ncu": NCU_KERNEL_MS.get((N, M)),
+                "frac_on_ncu_duration": (flop_per_launch / (NCU_KERNEL_MS[(N, M)] * 1e-3) * 1e-12 / peak_tf.value
+                                         if (N, M) in NCU_KERNEL_MS and peak_tf.value else None),
+                "frac_note": "frac uses kernel_ms, a CUDA-event pair around ONE launch per step (the pair itself "
+                "costs ~8 us, which matters for a 14 us kernel at 10 000 targets and not at 1 M); frac_on_ncu_duration "
+                "divides the same live flop count by the kernel's committed ncu duration (profiles/r1d_launches_*.csv)",
                 "whole_step_flop_per_target_step": flop_per_target_step,
                 "whole_step_achieved": flop_per_target_step * N / (ms_per_step * 1e-3) * 1e-12,
                 "hbm": {"achieved": hbm_ach, "peak": hbm_peak, "unit": "GB/s", "frac": hbm_ach / hbm_peak,

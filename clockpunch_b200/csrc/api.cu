@@ -74,6 +74,7 @@ struct pc_ctx {
   cudaGraphExec_t hs_exec = nullptr;
   pc_step_args hs_args;
   pc_ukf_params hs_params;
+  pc_step_io hs_io;
   float* hs_dobs = nullptr;
   cudaStream_t hs_stream = nullptr;
   int64_t hs_launches = 0;
@@ -950,18 +951,22 @@ int pc_step_host(pc_ctx* ctx, const pc_step_args* a, const pc_ukf_params* params
   PC_REQUIRE(ctx, !io->h_num_tasked || a->num_tasked, "h_num_tasked needs num_tasked in the step args");
   DeviceGuard g(ctx->device);
   cudaStream_t s = stream ? (cudaStream_t)stream : ctx->host_stream;
-  if (io->h_actions && a->M > 0)
-    PC_CUDA_TRY(ctx, cudaMemcpyAsync(a->actions, io->h_actions, (size_t)a->M * sizeof(int64_t),
-                                     cudaMemcpyHostToDevice, s));
   // Replayable only when nothing in the argument block changes from step to step: device clock,
   // caller-owned sigma buffer already holding the current sigma points, measurements drawn on device.
   const bool replayable = a->clock && a->sigma_ws && a->sigma_valid && !a->z && !ctx->timing;
+  const bool have_block = io->d_block && io->h_block && io->block_bytes > 0;
+  const bool copy_actions = io->h_actions && a->M > 0;
   int rc = PC_OK;
   pc_step_args key;
   if (!replayable) {
+    if (copy_actions)
+      PC_CUDA_TRY(ctx, cudaMemcpyAsync(a->actions, io->h_actions, (size_t)a->M * sizeof(int64_t),
+                                       cudaMemcpyHostToDevice, s));
     rc = step_and_pack(ctx, a, params, io->d_obs, s);
     if (rc) return rc;
   } else {
+    // the two host copies (actions in, output block out) are nodes of the same graph: one launch and
+    // one synchronise per step
     // with a device clock the kernels take the step's start time and RNG counter from it; only
     // tf - t0 matters, so the key is normalised and a caller that advances t0 / rng_step still hits
     key = *a;
@@ -970,6 +975,7 @@ int pc_step_host(pc_ctx* ctx, const pc_step_args* a, const pc_ukf_params* params
     key.rng_step = 0;
     a = &key;
     const bool hit = ctx->hs_exec && ctx->hs_stream == s && ctx->hs_dobs == io->d_obs &&
+                     std::memcmp(&ctx->hs_io, io, sizeof(*io)) == 0 &&
                      std::memcmp(&ctx->hs_args, a, sizeof(*a)) == 0 &&
                      std::memcmp(&ctx->hs_params, params, sizeof(*params)) == 0;
     if (!hit) {
@@ -980,8 +986,14 @@ int pc_step_host(pc_ctx* ctx, const pc_step_args* a, const pc_ukf_params* params
       const int64_t before = ctx->launches;
       cudaGraph_t graph = nullptr;
       PC_CUDA_TRY(ctx, cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal));
-      rc = step_and_pack(ctx, a, params, io->d_obs, s);
+      cudaError_t ec = cudaSuccess;
+      if (copy_actions)
+        ec = cudaMemcpyAsync(a->actions, io->h_actions, (size_t)a->M * sizeof(int64_t), cudaMemcpyHostToDevice, s);
+      rc = ec == cudaSuccess ? step_and_pack(ctx, a, params, io->d_obs, s) : PC_ERR_CUDA;
+      if (rc == PC_OK && have_block)
+        ec = cudaMemcpyAsync(io->h_block, io->d_block, (size_t)io->block_bytes, cudaMemcpyDeviceToHost, s);
       cudaError_t e = cudaStreamEndCapture(s, &graph);
+      if (rc == PC_OK && ec != cudaSuccess) e = ec;
       ctx->hs_launches = ctx->launches - before;
       ctx->launches = before;
       if (rc) {
@@ -994,13 +1006,18 @@ int pc_step_host(pc_ctx* ctx, const pc_step_args* a, const pc_ukf_params* params
       PC_CUDA_TRY(ctx, e);
       std::memcpy(&ctx->hs_args, a, sizeof(*a));
       std::memcpy(&ctx->hs_params, params, sizeof(*params));
+      std::memcpy(&ctx->hs_io, io, sizeof(*io));
       ctx->hs_dobs = io->d_obs;
       ctx->hs_stream = s;
     }
     PC_CUDA_TRY(ctx, cudaGraphLaunch(ctx->hs_exec, s));
     ctx->launches += ctx->hs_launches;
+    if (have_block) {
+      PC_CUDA_TRY(ctx, cudaStreamSynchronize(s));
+      return PC_OK;
+    }
   }
-  if (io->d_block && io->h_block && io->block_bytes > 0) {
+  if (have_block) {
     PC_CUDA_TRY(ctx, cudaMemcpyAsync(io->h_block, io->d_block, (size_t)io->block_bytes, cudaMemcpyDeviceToHost, s));
     PC_CUDA_TRY(ctx, cudaStreamSynchronize(s));
     return PC_OK;
