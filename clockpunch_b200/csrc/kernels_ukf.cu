@@ -675,12 +675,7 @@ __device__ __forceinline__ void vis_word(const double4* __restrict__ row, const 
 // (out of line: the peer loop would otherwise be inlined at every store site of kernels that mostly run
 // without peers)
 template <typename T>
-#ifdef PC_V_INLINE_PEER
-__device__ __forceinline__ void peer_store(
-#else
-__device__ __noinline__ void peer_store(
-#endif
-    const PeerPush& pp, int parity, int64_t field_off, int64_t idx, T v) {
+__device__ __noinline__ void peer_store(const PeerPush& pp, int parity, int64_t field_off, int64_t idx, T v) {
   const int64_t off = ((int64_t)parity * pp.world + pp.rank) * pp.slot_bytes + field_off + idx * (int64_t)sizeof(T);
   for (int r = 0; r < pp.world; ++r)
     *reinterpret_cast<T*>(__ldg(pp.table + r) + off) = v;

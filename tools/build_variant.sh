@@ -1,6 +1,6 @@
 #!/bin/bash
 # Build a variant of the library with extra -D flags on kernels_ukf.cu (experiments):
-#   tools/build_variant.sh NAME -DPC_V_...   ->  variants/libpunch_NAME.so   (use with PUNCH_B200_LIB=...)
+#   tools/build_variant.sh stamps -DPC_COOP_STAMPS   ->  variants/libpunch_stamps.so   (use with PUNCH_B200_LIB=...)
 set -e
 cd "$(dirname "$0")/.."
 name=$1; shift
