@@ -433,24 +433,18 @@ def run_own(args):
     eng.reset()
     eng._graph = None
     hb = eng.host_buffers()
-    rng = np.random.default_rng(SEED + rank)
-    n_tab = min(args.warmup + args.steps, 256)          # random probe table, reused cyclically
-    probe_tab = rng.integers(0, N, size=(n_tab, M, 64))
-    jcol = np.arange(M)[:, None]
-    jw, jb = jcol >> 5, (jcol & 31).astype(np.uint32)
-    rows = np.arange(M)
-    h_vis_np = hb["vis_est"].numpy().view(np.uint32)
-    h_act_np = hb["actions"].numpy()
-
-    flat_tab = probe_tab * eng.wpr + jw                # word index of every probe (same random table)
-    bit = (np.uint32(1) << jb)
-    h_vis_flat = h_vis_np.reshape(-1)
+    # Host-side scheduler: the stand-in policy of the `value` pass (first estimated-visible target among 64
+    # hashed probes per sensor, else inaction) in its host form, reading the packed estimated map that the
+    # previous pc_step_host copied out and writing the pinned actions buffer of the next one.
+    import ctypes as C
+    h_vis_ptr = C.c_void_p(hb["vis_est"].data_ptr())
+    h_act_ptr = C.c_void_p(hb["actions"].data_ptr())
+    host_policy_fn = eng.ctx.lib.pc_policy_random_visible_host
 
     def host_policy(k):
-        k %= n_tab
-        hit = (h_vis_flat.take(flat_tab[k]) & bit) != 0          # (M, 64): probe sees its target?
-        first = hit.argmax(axis=1)
-        h_act_np[:M] = np.where(hit[rows, first], probe_tab[k][rows, first], N)
+        rc = host_policy_fn(h_vis_ptr, N, M, eng.wpr, SEED + rank, k, 64, h_act_ptr)
+        if rc:
+            raise RuntimeError(f"pc_policy_random_visible_host status {rc}")
 
     def e2e_step(k):
         host_policy(k)
@@ -482,7 +476,7 @@ def run_own(args):
     e2e = {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(M * 8),
            "d2h_bytes_per_step": int(hb["block"].numel()),     # float32 obs | num_tasked | packed vis | traces, one copy
            "ms_per_step": float(e2e_ms.item()) / args.steps,
-           "path": "host policy (numpy, previous obs) -> CatalogEngine.step_host -> pc_step_host: pinned host actions "
+           "path": "host policy (pc_policy_random_visible_host on the previous step's packed map) -> CatalogEngine.step_host -> pc_step_host: pinned host actions "
                    "-> [CUDA graph: pc_step_fused + pc_obs_pack] -> ONE copy of the output block (float32 obs | num_tasked | "
                    "packed vis map | covariance traces | last_time_tasked) to pinned host memory, stream sync; timed by the "
                    "host clock around the loop"}

@@ -92,6 +92,7 @@ _SIGNATURES = {
     "pc_task_from_actions": ([_vp, _vp, _i64, _vp, _i64, _i64, _vp, _vp], _int),
     "pc_obs_pack": ([_vp, _vp, _i64, _i64, _vp, _vp, _i64, _i64, _vp, _dbl, _vp, _vp, _vp, _vp, _vp], _int),
     "pc_policy_random_visible": ([_vp, _vp, _i64, _i64, _i64, _u64, _u64, _vp, _int, _vp, _vp], _int),
+    "pc_policy_random_visible_host": ([_vp, _i64, _i64, _i64, _u64, _u64, _int, _vp], _int),
     "pc_set_timing": ([_vp, _int], _int),
     "pc_get_timing": ([_vp, C.POINTER(_dbl)], _int),
     "pc_fp64_peak": ([_vp, _int, C.POINTER(_dbl)], _int),

@@ -673,6 +673,32 @@ int pc_policy_random_visible(pc_ctx* ctx, const uint32_t* vis_est, int64_t N, in
   return PC_OK;
 }
 
+static inline uint64_t splitmix64_host(uint64_t x) {
+  x += 0x9E3779B97F4A7C15ull;
+  x = (x ^ (x >> 30)) * 0xBF58476D1CE4E5B9ull;
+  x = (x ^ (x >> 27)) * 0x94D049BB133111EBull;
+  return x ^ (x >> 31);
+}
+
+int pc_policy_random_visible_host(const uint32_t* vis_est, int64_t N, int64_t M, int64_t words_per_row,
+                                  uint64_t seed, uint64_t step, int probes, int64_t* actions) {
+  if (N <= 0 || M < 0 || probes < 0 || words_per_row != (M + 31) / 32) return PC_ERR_BAD_ARG;
+  if (M > 0 && (!vis_est || !actions)) return PC_ERR_BAD_ARG;
+  for (int64_t j = 0; j < M; ++j) {   // policy_random_visible_kernel, one sensor at a time
+    const uint64_t base = splitmix64_host(seed ^ splitmix64_host(step * 0x100000001B3ull + (uint64_t)j));
+    int64_t pick = N;
+    for (int k = 0; k < probes; ++k) {
+      const int64_t i = (int64_t)(splitmix64_host(base + (uint64_t)k) % (uint64_t)N);
+      if ((vis_est[i * words_per_row + (j >> 5)] >> (j & 31)) & 1u) {
+        pick = i;
+        break;
+      }
+    }
+    actions[j] = pick;
+  }
+  return PC_OK;
+}
+
 /* ---- measurement helpers ------------------------------------------------ */
 int pc_set_timing(pc_ctx* ctx, int enabled) {
   PC_REQUIRE(ctx, ctx != nullptr, "null context");

@@ -222,6 +222,12 @@ int pc_policy_random_visible(pc_ctx* ctx, const uint32_t* vis_est, int64_t N, in
                              int64_t words_per_row, uint64_t seed, uint64_t step,
                              const pc_clock* clock /* device, or NULL: use `step` */, int probes,
                              int64_t* actions, pc_stream stream);
+/* The same policy on the HOST, for a caller that schedules from the observation it received (bench.py's
+ * end-to-end loop): vis_est and actions are host arrays (the packed estimated map as copied out by
+ * pc_step_host, the M actions handed to the next pc_step_host).  Same probe sequence as the device form
+ * for equal (seed, step).  No context, no device work; returns PC_ERR_BAD_ARG on bad sizes. */
+int pc_policy_random_visible_host(const uint32_t* vis_est, int64_t N, int64_t M, int64_t words_per_row,
+                                  uint64_t seed, uint64_t step, int probes, int64_t* actions);
 
 /* ---- measurement helpers (bench.py) ------------------------------------
  * pc_set_timing(1) makes pc_step_fused bracket its UKF kernel with one pair of CUDA events on the

@@ -111,3 +111,42 @@ def test_install_as_punchclock():
     import punchclock.dynamics.dynamics_classes as dc
     from punchclock.estimation.ez_ukf import ezUKF  # noqa: F401
     assert dc.SatDynamicsModel.__module__.startswith("clockpunch_b200")
+
+
+def test_host_policy_matches_restatement():
+    """pc_policy_random_visible_host (no device needed): first visible of `probes` hashed probes per sensor,
+    else inaction -- against a plain restatement of the same counter-based hash."""
+    import ctypes as C
+    import numpy as np
+    from clockpunch_b200 import _lib
+    lib = _lib.load_library()
+    M64 = (1 << 64) - 1
+
+    def sm(x):
+        x = (x + 0x9E3779B97F4A7C15) & M64
+        x = ((x ^ (x >> 30)) * 0xBF58476D1CE4E5B9) & M64
+        x = ((x ^ (x >> 27)) * 0x94D049BB133111EB) & M64
+        return x ^ (x >> 31)
+
+    rng = np.random.default_rng(4)
+    for N, M, probes, dens in ((50, 7, 8, 0.2), (1000, 100, 64, 0.05), (33, 40, 4, 0.0), (9, 3, 16, 1.0)):
+        wpr = (M + 31) // 32
+        dense = rng.random((N, M)) < dens
+        packed = np.zeros((N, wpr), np.uint32)
+        for j in range(M):
+            packed[:, j >> 5] |= dense[:, j].astype(np.uint32) << np.uint32(j & 31)
+        out = np.full(M, -7, np.int64)
+        seed, step = 20240627, 11
+        rc = lib.pc_policy_random_visible_host(packed.ctypes.data_as(C.c_void_p), N, M, wpr, seed, step, probes,
+                                               out.ctypes.data_as(C.c_void_p))
+        assert rc == 0
+        for j in range(M):
+            base = sm(seed ^ sm((step * 0x100000001B3 + j) & M64))
+            want = N
+            for k in range(probes):
+                i = sm((base + k) & M64) % N
+                if dense[i, j]:
+                    want = i
+                    break
+            assert out[j] == want, (N, M, j)
+    assert lib.pc_policy_random_visible_host(None, 10, 3, 5, 0, 0, 4, None) == -1      # wrong words_per_row

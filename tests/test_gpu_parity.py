@@ -764,3 +764,28 @@ def test_update_warps_equal_inline_update(given_z):
         np.testing.assert_allclose(a.host("nis"), b.host("nis"), rtol=1e-6, equal_nan=True, err_msg=f"nis step {s}")
         n_upd = int(a.host("num_tasked").sum())
     assert n_upd > 8 and a.host("num_tasked").max() <= 4      # updates happened; never two in one step
+
+
+def test_host_policy_equals_device_policy():
+    """The stand-in policy has a device form (pc_policy_random_visible, also inside the step's sensor kernel)
+    and a host form (pc_policy_random_visible_host, bench.py's end-to-end loop): same picks."""
+    import ctypes as C
+    import torch
+    from clockpunch_b200 import _lib
+    ctx = _lib.get_ctx(0)
+    rng = np.random.default_rng(8)
+    N, M, probes = 700, 45, 32
+    wpr = (M + 31) // 32
+    packed = rng.integers(0, 2**32, size=(N, wpr), dtype=np.uint64).astype(np.uint32) \
+        & rng.integers(0, 2**32, size=(N, wpr), dtype=np.uint64).astype(np.uint32) \
+        & rng.integers(0, 2**32, size=(N, wpr), dtype=np.uint64).astype(np.uint32)       # ~12 % visible
+    d_vis = torch.from_numpy(packed.view(np.int32)).cuda()
+    d_act = torch.zeros(M, dtype=torch.int64, device="cuda")
+    host = np.zeros(M, np.int64)
+    for step in (0, 5, 123456789):
+        ctx.check(ctx.lib.pc_policy_random_visible(ctx.handle, d_vis.data_ptr(), N, M, wpr, 99, step, None, probes,
+                                                   d_act.data_ptr(), torch.cuda.current_stream().cuda_stream))
+        assert ctx.lib.pc_policy_random_visible_host(packed.ctypes.data_as(C.c_void_p), N, M, wpr, 99, step, probes,
+                                                     host.ctypes.data_as(C.c_void_p)) == 0
+        np.testing.assert_array_equal(d_act.cpu().numpy(), host)
+        assert (host < N).sum() > M // 2
