@@ -49,6 +49,8 @@ class StepArgs(C.Structure):
         ("peer_table", C.c_void_p), ("peer_world", C.c_int32), ("peer_rank", C.c_int32),
         ("summary_base", C.c_void_p), ("summary_bytes", C.c_int64),
         ("task_of", C.c_void_p),
+        ("mirror_dev", C.c_void_p), ("mirror_host", C.c_void_p), ("mirror_bytes", C.c_int64),
+        ("obs_cov_host", C.c_void_p),
     ]
 
 
@@ -56,7 +58,8 @@ class StepIO(C.Structure):
     """pc_step_io."""
     _fields_ = [("h_actions", C.c_void_p), ("d_obs", C.c_void_p), ("h_obs", C.c_void_p),
                 ("h_vis_est", C.c_void_p), ("h_num_tasked", C.c_void_p),
-                ("d_block", C.c_void_p), ("h_block", C.c_void_p), ("block_bytes", C.c_int64)]
+                ("d_block", C.c_void_p), ("h_block", C.c_void_p), ("block_bytes", C.c_int64),
+                ("zero_copy", C.c_int32)]
 
 
 _vp, _i64, _dbl, _int, _u64 = C.c_void_p, C.c_int64, C.c_double, C.c_int, C.c_uint64

@@ -650,7 +650,7 @@ int pc_obs_pack(pc_ctx* ctx, const double* sens_x, int64_t M, int64_t ld_s, cons
                 float* out_stale, pc_stream stream) {
   PC_REQUIRE(ctx, ctx != nullptr, "null context");
   PC_REQUIRE(ctx, M >= 0 && N >= 0 && ld_s >= M && ld >= N, "bad sizes");
-  PC_REQUIRE(ctx, out_eci && out_cov && out_stale, "null output");
+  PC_REQUIRE(ctx, out_eci && out_stale, "null output");   // out_cov may be NULL (est_cov written elsewhere)
   PC_REQUIRE(ctx, (M == 0 || sens_x) && (N == 0 || (est_x && est_p && last_time_tasked)), "null input");
   DeviceGuard g(ctx->device);
   PC_CUDA_TRY(ctx, pc::launch_obs_pack(sens_x, M, ld_s, est_x, est_p, N, ld, last_time_tasked, t_now,
@@ -874,6 +874,21 @@ int pc_step_fused(pc_ctx* ctx, const pc_step_args* a, const pc_ukf_params* param
       u.task_of = a->task_of;
       u.task_sensors = a->M;
       u.task_env_sensors = Me;
+      if (a->mirror_host && a->mirror_dev && a->mirror_bytes > 0 && pc::finish_fills_host_mirrors(a->N, a->M)) {
+        // host mirrors of the summary arrays that live inside the caller's device block
+        const char* d0 = static_cast<const char*>(a->mirror_dev);
+        char* h0 = static_cast<char*>(a->mirror_host);
+        auto mirror = [&](const void* p) -> char* {
+          const char* q = static_cast<const char*>(p);
+          return (p && q >= d0 && q < d0 + a->mirror_bytes) ? h0 + (q - d0) : nullptr;
+        };
+        u.h_num_tasked = reinterpret_cast<int64_t*>(mirror(a->num_tasked));
+        u.h_vis_est = reinterpret_cast<uint32_t*>(mirror(a->vis_est));
+        u.h_tr_pos = reinterpret_cast<float*>(mirror(a->tr_pos));
+        u.h_tr_vel = reinterpret_cast<float*>(mirror(a->tr_vel));
+        u.h_ltt = reinterpret_cast<float*>(mirror(a->last_time_tasked));
+      }
+      if (pc::finish_fills_host_mirrors(a->N, a->M)) u.h_cov = a->obs_cov_host;
     }
     if (fuse_vis) {
       u.sens_q = reinterpret_cast<const double4*>(sq);
@@ -954,6 +969,14 @@ static int step_and_pack(pc_ctx* ctx, const pc_step_args* a, const pc_ukf_params
                          float* d_obs, cudaStream_t s) {
   int rc = pc_step_fused(ctx, a, params, s);
   if (rc) return rc;
+  if (d_obs && a->obs_cov_host && a->env_targets <= 0) {
+    // zero-copy form: est_cov was written by the per-target kernel; eci_state and obs_staleness go
+    // straight to the host block as well (obs_cov_host sits 6 (M + N) floats into it)
+    const int64_t n0 = 6 * (a->M + a->N), n1 = 36 * a->N;
+    float* h_obs = a->obs_cov_host - n0;
+    return pc_obs_pack(ctx, a->sens_x, a->M, a->ld_s, a->est_x, a->est_p, a->N, a->ld, a->last_time_tasked,
+                       a->tf, a->clock, h_obs, nullptr, h_obs + n0 + n1, s);
+  }
   if (d_obs) {
     const int64_t n0 = 6 * (a->M + a->N), n1 = 36 * a->N;
     if (a->env_targets > 0)
@@ -982,6 +1005,11 @@ int pc_step_host(pc_ctx* ctx, const pc_step_args* a, const pc_ukf_params* params
   const bool replayable = a->clock && a->sigma_ws && a->sigma_valid && !a->z && !ctx->timing;
   const bool have_block = io->d_block && io->h_block && io->block_bytes > 0;
   const bool copy_actions = io->h_actions && a->M > 0;
+  // zero-copy form: the kernels store the outputs into the (device-accessible) host block themselves
+  const int64_t obs_floats = 6 * (a->M + a->N) + 37 * a->N;
+  const bool zero_copy = io->zero_copy && replayable && have_block && io->d_obs && a->env_targets <= 0 &&
+                         a->actions && a->task_of && !a->peer_table && pc::finish_fills_host_mirrors(a->N, a->M) &&
+                         io->d_obs == io->d_block && io->block_bytes >= obs_floats * (int64_t)sizeof(float);
   int rc = PC_OK;
   pc_step_args key;
   if (!replayable) {
@@ -999,6 +1027,17 @@ int pc_step_host(pc_ctx* ctx, const pc_step_args* a, const pc_ukf_params* params
     key.tf = a->tf - a->t0;
     key.t0 = 0.0;
     key.rng_step = 0;
+    if (zero_copy) {
+      key.mirror_dev = io->d_block;
+      key.mirror_host = io->h_block;
+      key.mirror_bytes = io->block_bytes;
+      key.obs_cov_host = static_cast<float*>(io->h_block) + 6 * (a->M + a->N);
+    } else {
+      key.mirror_dev = nullptr;
+      key.mirror_host = nullptr;
+      key.mirror_bytes = 0;
+      key.obs_cov_host = nullptr;
+    }
     a = &key;
     const bool hit = ctx->hs_exec && ctx->hs_stream == s && ctx->hs_dobs == io->d_obs &&
                      std::memcmp(&ctx->hs_io, io, sizeof(*io)) == 0 &&
@@ -1016,7 +1055,7 @@ int pc_step_host(pc_ctx* ctx, const pc_step_args* a, const pc_ukf_params* params
       if (copy_actions)
         ec = cudaMemcpyAsync(a->actions, io->h_actions, (size_t)a->M * sizeof(int64_t), cudaMemcpyHostToDevice, s);
       rc = ec == cudaSuccess ? step_and_pack(ctx, a, params, io->d_obs, s) : PC_ERR_CUDA;
-      if (rc == PC_OK && have_block)
+      if (rc == PC_OK && have_block && !zero_copy)
         ec = cudaMemcpyAsync(io->h_block, io->d_block, (size_t)io->block_bytes, cudaMemcpyDeviceToHost, s);
       cudaError_t e = cudaStreamEndCapture(s, &graph);
       if (rc == PC_OK && ec != cudaSuccess) e = ec;
@@ -1035,6 +1074,9 @@ int pc_step_host(pc_ctx* ctx, const pc_step_args* a, const pc_ukf_params* params
       std::memcpy(&ctx->hs_io, io, sizeof(*io));
       ctx->hs_dobs = io->d_obs;
       ctx->hs_stream = s;
+      // the kernels only store what changes: start from a full copy of the device block
+      if (zero_copy)
+        PC_CUDA_TRY(ctx, cudaMemcpyAsync(io->h_block, io->d_block, (size_t)io->block_bytes, cudaMemcpyDeviceToHost, s));
     }
     PC_CUDA_TRY(ctx, cudaGraphLaunch(ctx->hs_exec, s));
     ctx->launches += ctx->hs_launches;

@@ -30,7 +30,7 @@ obs_pack_kernel(const double* __restrict__ sens_x, int64_t M, int64_t ld_s,
   const double t_now = clock ? clock->t_now : t_now_arg;
   const int64_t idx = (int64_t)blockIdx.x * 256 + threadIdx.x;
   const int64_t A = M + N;
-  const int64_t n_eci = 6 * A, n_cov = 36 * N;
+  const int64_t n_eci = 6 * A, n_cov = out_cov ? 36 * N : 0;   // out_cov == NULL: written elsewhere
   if (idx < n_eci) {
     const int64_t c = idx / A, k = idx - c * A;
     out_eci[idx] = (float)(k < M ? sens_x[c * ld_s + k] : est_x[c * ld + (k - M)]);
@@ -305,7 +305,7 @@ cudaError_t launch_obs_pack(const double* sens_x, int64_t M, int64_t ld_s, const
                             const double* est_p, int64_t N, int64_t ld,
                             const float* last_time_tasked, double t_now, const pc_clock* clock,
                             float* out_eci, float* out_cov, float* out_stale, cudaStream_t s) {
-  const int64_t total = 6 * (M + N) + 36 * N + N;
+  const int64_t total = 6 * (M + N) + (out_cov ? 36 * N : 0) + N;
   if (total <= 0) return cudaSuccess;
   return launch_pdl(obs_pack_kernel, dim3((unsigned)((total + 255) / 256)), dim3(256), 0, s, true, sens_x, M, ld_s,
                     est_x, est_p, N, ld, last_time_tasked, t_now, clock, out_eci, out_cov, out_stale);

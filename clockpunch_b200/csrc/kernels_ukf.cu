@@ -1210,6 +1210,7 @@ __device__ __noinline__ uint32_t coop_part1(const UkfArgs& a, CoopSmem& S, int64
 // CTA runs this half on scratch operands WHILE the first warp is in the first half, so that the
 // instruction lines are already in the SM's instruction cache when the real data arrives (the update
 // warp is alone on its code: every line it touches is otherwise a cold miss).
+template <bool HOST>
 __device__ __noinline__ void coop_part2(const UkfArgs& a, CoopSmem& S, int64_t t, int parity, uint32_t flags,
                                         int dry) {
   const unsigned full = 0xffffffffu;
@@ -1278,7 +1279,10 @@ __device__ __noinline__ void coop_part2(const UkfArgs& a, CoopSmem& S, int64_t t
   if (!isfinite(chk)) flags |= PC_FLAG_NONFINITE;
 #pragma unroll
   for (int i = lane; i < 36; i += 32)
-    if (wr) a.est_p[t * 36 + i] = S.PE[i];
+    if (wr) {
+      a.est_p[t * 36 + i] = S.PE[i];
+      if (HOST && a.h_cov) a.h_cov[t * 36 + i] = (float)S.PE[i];
+    }
   if (lane == 0 && wr) {
     if (a.out_flags) a.out_flags[t] = flags;
     if (a.out_nis) a.out_nis[t] = nis;
@@ -1289,6 +1293,12 @@ __device__ __noinline__ void coop_part2(const UkfArgs& a, CoopSmem& S, int64_t t
     const int64_t nt = S.nt + 1;
     if (a.num_tasked) a.num_tasked[t] = nt;
     if (a.last_time_tasked) a.last_time_tasked[t] = (float)t_now;
+    if (HOST) {
+      if (a.h_tr_pos) a.h_tr_pos[t] = trp;
+      if (a.h_tr_vel) a.h_tr_vel[t] = trv;
+      if (a.h_num_tasked) a.h_num_tasked[t] = nt;
+      if (a.h_ltt) a.h_ltt[t] = (float)t_now;
+    }
     if (a.pp.world) {
       peer_store(a.pp, parity, a.pp.off_tr_pos, t, trp);
       peer_store(a.pp, parity, a.pp.off_tr_vel, t, trv);
@@ -1305,6 +1315,7 @@ __device__ __noinline__ void coop_part2(const UkfArgs& a, CoopSmem& S, int64_t t
 }
 
 // Third piece: factor of the new covariance, next step's sigma points, estimated visibility row.
+template <bool HOST>
 __device__ __noinline__ void coop_part3(const UkfArgs& a, CoopSmem& S, int64_t t, int parity, int dry) {
   const unsigned full = 0xffffffffu;
   const int lane = threadIdx.x & 31;
@@ -1358,6 +1369,7 @@ __device__ __noinline__ void coop_part3(const UkfArgs& a, CoopSmem& S, int64_t t
         const uint32_t word = __ballot_sync(full, v);
         if (lane == 0 && wr && w0 + u < a.wpr) {
           a.vis_est[t * a.wpr + w0 + u] = word;
+          if (HOST && a.h_vis_est) a.h_vis_est[t * a.wpr + w0 + u] = word;
           if (a.pp.world) peer_store(a.pp, parity, a.pp.off_vis_est, t * a.wpr + w0 + u, word);
         }
       }
@@ -1383,9 +1395,34 @@ __device__ __forceinline__ void store_sym36_quad(double* __restrict__ g, const d
   }
 }
 
-constexpr size_t kQuadSmem = sizeof(double4) * kVisTileSlots > 4 * sizeof(CoopSmem) ? sizeof(double4) * kVisTileSlots
-                                                                                    : 4 * sizeof(CoopSmem);
-template <bool COOP>
+// regular CTAs: sensor tile, then (host-mirror form) a 1 152-byte float32 covariance stage per warp;
+// update CTAs: four CoopSmem
+constexpr size_t kQuadTileBytes = sizeof(double4) * kVisTileSlots;
+constexpr size_t kQuadStageBytes = (kQuadThreads / 32) * 8 * 36 * sizeof(float);
+constexpr size_t kQuadSmem = kQuadTileBytes + kQuadStageBytes > 4 * sizeof(CoopSmem) ? kQuadTileBytes + kQuadStageBytes
+                                                                                   : 4 * sizeof(CoopSmem);
+// float32 copy of the same matrix (the observation's est_cov) as nine 16-byte chunks over the quad
+__device__ __forceinline__ void store_sym36_quad_f32(float* __restrict__ g, const double (&E)[21], int q) {
+  float4* row = reinterpret_cast<float4*>(g);
+#pragma unroll
+  for (int c = 0; c < 9; ++c) {
+    if ((c & 3) == q) {
+      float v[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int e = 4 * c + u, r = e / 6, cc = e % 6;
+        v[u] = (float)E[r <= cc ? uidx(r, cc) : uidx(cc, r)];
+      }
+      row[c] = make_float4(v[0], v[1], v[2], v[3]);
+    }
+  }
+}
+
+// HOST: also store what the caller reads on the host (float32 est_cov, covariance traces, estimated
+// visibility words) into mapped host memory as it is produced (pc_step_host's zero-copy form): the
+// PCIe transfer then runs under this kernel instead of behind it.  A separate instantiation, so that the
+// device-only step does not carry the code.
+template <bool COOP, bool HOST>
 __global__ void __launch_bounds__(kQuadThreads, 3)
 ukf_finish_quad_kernel(const __grid_constant__ UkfArgs a) {
   constexpr bool ROLE = COOP;
@@ -1404,8 +1441,8 @@ ukf_finish_quad_kernel(const __grid_constant__ UkfArgs a) {
     CoopSmem& S = reinterpret_cast<CoopSmem*>(smem_raw)[threadIdx.x >> 5];
     coop_scratch_init(S);
     if (threadIdx.x < 64) coop_part1(a, S, 0, 1);
-    else if (threadIdx.x < 96) coop_part2(a, S, 0, 0, 0u, 1);
-    else coop_part3(a, S, 0, 0, 1);
+    else if (threadIdx.x < 96) coop_part2<HOST>(a, S, 0, 0, 0u, 1);
+    else coop_part3<HOST>(a, S, 0, 0, 1);
   }
   pdl_wait();  // launched programmatically behind the propagation kernel: everything below reads its output
   pdl_trigger();  // a programmatic successor (the observation pack) may be scheduled behind our last wave
@@ -1432,8 +1469,8 @@ ukf_finish_quad_kernel(const __grid_constant__ UkfArgs a) {
       CoopSmem& S = reinterpret_cast<CoopSmem*>(smem_raw)[0];
       PC_COOP_CLOCK(0);
       const uint32_t fl = coop_part1(a, S, tt, 0);
-      coop_part2(a, S, tt, parity, fl, 0);
-      coop_part3(a, S, tt, parity, 0);
+      coop_part2<HOST>(a, S, tt, parity, fl, 0);
+      coop_part3<HOST>(a, S, tt, parity, 0);
     }
     if (a.pp.world) peer_publish(a.pp, step_done);
     return;
@@ -1472,6 +1509,14 @@ ukf_finish_quad_kernel(const __grid_constant__ UkfArgs a) {
   }
   const int tflag = a.tasked ? (int)a.tasked[tc] : 0;
   uint32_t flags = a.sig_flags ? a.sig_flags[tc] : 0u;
+  // host mirror: the bookkeeping of an unmeasured target does not change, but the host block is
+  // rewritten in full every step (no state to keep consistent across resets)
+  int64_t nt0 = 0;
+  float ltt0 = 0.0f;
+  if (HOST && q == 0) {
+    if (a.h_num_tasked) nt0 = a.num_tasked[tc];
+    if (a.h_ltt) ltt0 = a.last_time_tasked[tc];
+  }
   // the sensor tile is requested AFTER the register loads are in flight (one thread issues the bulk
   // copies; everybody else would otherwise wait for it at the barrier before issuing anything)
   if (vis) {
@@ -1586,6 +1631,21 @@ ukf_finish_quad_kernel(const __grid_constant__ UkfArgs a) {
 #pragma unroll
     for (int c = 0; c < 6; ++c) a.truth_out[(int64_t)c * ld + t] = sb[13 * blk + (int64_t)c * ld + t];
   }
+  if (HOST && a.h_cov) {
+    // float32 est_cov of the warp's 8 targets: staged in shared memory, then written to the host block
+    // as 16-byte stores at consecutive addresses (scattered 16-byte stores become one PCIe packet each:
+    // measured 17 GB/s against ~50 for full lines)
+    const int lane = threadIdx.x & 31;
+    float* stg = reinterpret_cast<float*>(smem_raw + kQuadTileBytes) + (threadIdx.x >> 5) * (8 * 36);
+    store_sym36_quad_f32(stg + (lane >> 2) * 36, PE, q);
+    const unsigned mm = __ballot_sync(0xffffffffu, mine);
+    __syncwarp();
+    const int64_t tw0 = t - (lane >> 2);
+    float* dst = a.h_cov + tw0 * 36;     // (4-byte stores: the block's covariance section is not 16-byte aligned in general)
+#pragma unroll
+    for (int i = lane; i < 288; i += 32)
+      if ((mm >> (4 * (i / 36))) & 1u) dst[i] = stg[i];
+  }
   if (mine) {
     store_sym36_quad(a.est_p + t * 36, PE, q);
     if (q == 1) {
@@ -1595,10 +1655,18 @@ ukf_finish_quad_kernel(const __grid_constant__ UkfArgs a) {
       const float trv = ((float)PE[uidx(3, 3)] + (float)PE[uidx(4, 4)]) + (float)PE[uidx(5, 5)];
       if (a.tr_pos) a.tr_pos[t] = trp;
       if (a.tr_vel) a.tr_vel[t] = trv;
+      if (HOST) {
+        if (a.h_tr_pos) a.h_tr_pos[t] = trp;
+        if (a.h_tr_vel) a.h_tr_vel[t] = trv;
+      }
       if (a.pp.world) {
         peer_store(a.pp, parity, a.pp.off_tr_pos, t, trp);
         peer_store(a.pp, parity, a.pp.off_tr_vel, t, trv);
       }
+    }
+    if (HOST && q == 0) {
+      if (a.h_num_tasked) a.h_num_tasked[t] = nt0;
+      if (a.h_ltt) a.h_ltt[t] = ltt0;
     }
     if (a.out_pred_x && q == 2) {
 #pragma unroll
@@ -1677,6 +1745,7 @@ ukf_finish_quad_kernel(const __grid_constant__ UkfArgs a) {
           if (live) a.vis_truth[t * wpr + w] = wa;
           if (mine) {
             a.vis_est[t * wpr + w] = wb;
+            if (HOST && a.h_vis_est) a.h_vis_est[t * wpr + w] = wb;
             if (a.pp.world) peer_store(a.pp, parity, a.pp.off_vis_est, t * wpr + w, wb);
           }
         }
@@ -1696,6 +1765,11 @@ static cudaError_t launch_finish_tpb(const UkfArgs& a, cudaStream_t stream) {
 // Small catalogs cannot fill the machine with one thread per target: they take the quad kernel
 // (four lanes per target); large ones get one thread per target with 64- or 128-thread CTAs
 // (sensor tile amortised over more warps).
+// Does launch_ukf_finish take the update-warp kernel (the only one that fills the host mirrors)?
+bool finish_fills_host_mirrors(int64_t n, int64_t sensors) {
+  return getenv("PC_NO_COOP") == nullptr && n > 0 && n <= kQuadMaxTargets && sensors > 0 && sensors <= kCoopMaxSensors;
+}
+
 cudaError_t launch_ukf_finish(const UkfArgs& a, cudaStream_t stream) {
   if (a.n <= 0) return cudaSuccess;
   if (a.n <= kQuadMaxTargets) {
@@ -1703,9 +1777,11 @@ cudaError_t launch_ukf_finish(const UkfArgs& a, cudaStream_t stream) {
     static const bool no_coop = getenv("PC_NO_COOP") != nullptr;   // experiments: in-line update everywhere
     if (!no_coop && a.task_of && a.task_sensors > 0 && a.task_sensors <= kCoopMaxSensors) {
       const unsigned upd = (unsigned)a.task_sensors;   // one update CTA per sensor
-      return launch_pdl(ukf_finish_quad_kernel<true>, dim3(upd + ctas), dim3(kQuadThreads), 0, stream, true, a);
+      if (a.h_cov || a.h_vis_est || a.h_tr_pos)
+        return launch_pdl(ukf_finish_quad_kernel<true, true>, dim3(upd + ctas), dim3(kQuadThreads), 0, stream, true, a);
+      return launch_pdl(ukf_finish_quad_kernel<true, false>, dim3(upd + ctas), dim3(kQuadThreads), 0, stream, true, a);
     }
-    return launch_pdl(ukf_finish_quad_kernel<false>, dim3(ctas), dim3(kQuadThreads), 0, stream, true, a);
+    return launch_pdl(ukf_finish_quad_kernel<false, false>, dim3(ctas), dim3(kQuadThreads), 0, stream, true, a);
   }
   if (a.n <= 128 * 1024) return launch_finish_tpb<64>(a, stream);
   return launch_finish_tpb<128>(a, stream);

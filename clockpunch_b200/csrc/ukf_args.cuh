@@ -59,6 +59,14 @@ struct UkfArgs {
   // kernel); sensors of one environment are task_env_sensors consecutive entries
   const int64_t* task_of;
   int64_t task_sensors, task_env_sensors;
+  // host mirrors (mapped pinned memory, NULL = off; update-warp kernel only): values are stored here
+  // as well as in the device arrays, so that the PCIe transfer runs under the kernel
+  float* h_cov;              // (N, 36) float32 est_cov
+  int64_t* h_num_tasked;
+  uint32_t* h_vis_est;
+  float* h_tr_pos;
+  float* h_tr_vel;
+  float* h_ltt;
   PeerPush pp;
   pc_ukf_params p;
 };
@@ -70,6 +78,7 @@ cudaError_t launch_propagate_sigma(double* sb, int64_t n, int64_t ld, int have_t
                                    double tf, int substeps, int force_model, uint32_t* sig_flags,
                                    bool beside_predecessor, cudaStream_t stream);
 cudaError_t launch_ukf_finish(const UkfArgs& a, cudaStream_t stream);
+bool finish_fills_host_mirrors(int64_t n, int64_t sensors);
 cudaError_t launch_peer_push(const void* summary, int64_t bytes, const PeerPush& pp, cudaStream_t stream);
 cudaError_t launch_peer_wait(const uint64_t* table, int world, int rank, const unsigned long long* seq,
                              unsigned int* err, cudaStream_t stream);

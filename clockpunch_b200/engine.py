@@ -347,12 +347,12 @@ class CatalogEngine:
                 "vis_est": v["vis_est"], "num_tasked": v["num_tasked"], "tr_pos": v["tr_pos"],
                 "tr_vel": v["tr_vel"], "last_time_tasked": v["last_time_tasked"]}
 
-    def step_host(self, hb: dict, dt: float, policy_probes: int = 0, policy_seed: int = 0):
+    def step_host(self, hb: dict, dt: float, policy_probes: int = 0, policy_seed: int = 0, zero_copy: bool = True):
         """One SSAScheduler.step for the whole catalog through pc_step_host: copies hb["actions"]
         to the device, runs the step (a CUDA graph inside the library after the first call),
         packs the float32 observation and copies it, the packed estimated vis map and num_tasked
         into hb.  One C call per step; returns when the host buffers are filled."""
-        key = (float(dt), int(policy_probes), int(policy_seed), id(hb), self._sigma_valid)
+        key = (float(dt), int(policy_probes), int(policy_seed), id(hb), self._sigma_valid, bool(zero_copy))
         if self._hs_key != key:
             # (re)build the argument blocks once; steady-state steps below are one C call
             self.ensure_sigma()
@@ -370,9 +370,13 @@ class CatalogEngine:
             if "block" in hb:      # obs | summary in one device block -> one D2H copy
                 io.d_block, io.h_block, io.block_bytes = (self.out_block.data_ptr(), hb["block"].data_ptr(),
                                                           self.out_block.numel())
+                # pinned block: the kernels store the outputs into it themselves while they run (no copy);
+                # the library falls back to the single copy when the catalog does not qualify.  The device
+                # observation (self.obs_f32) is not refreshed on that path: pack_obs() does that.
+                io.zero_copy = 1 if (zero_copy and hb["block"].is_pinned()) else 0
             self._hs_call = (self.ctx.lib.pc_step_host, self.ctx.handle, C.byref(self._args), C.byref(self.params),
                              C.byref(io), self._stream())
-            self._hs_key = (float(dt), int(policy_probes), int(policy_seed), id(hb), True)
+            self._hs_key = (float(dt), int(policy_probes), int(policy_seed), id(hb), True, bool(zero_copy))
         f, *cargs = self._hs_call
         rc = f(*cargs)
         if rc:

@@ -327,6 +327,20 @@ typedef struct pc_step_args {
    * beside the untasked targets instead of lengthening the warps those targets sit in.  Results are
    * the same filter equations either way; without the workspace the in-line update is used. */
   int64_t* task_of;
+  /* Host mirror of the step's outputs (used by pc_step_host's zero-copy form; leave NULL otherwise).
+   * mirror_host is DEVICE-ACCESSIBLE host memory (cudaHostAlloc / cudaHostRegister, e.g. a pinned torch
+   * tensor) laid out like the device block [mirror_dev, mirror_dev + mirror_bytes): every summary
+   * array of this struct that lies inside the device block (num_tasked, vis_est, tr_pos, tr_vel,
+   * last_time_tasked) is ALSO stored, value by value as the per-target kernel produces it, at the
+   * same offset of the host block; obs_cov_host (N, 36) receives the float32 est_cov the same way.
+   * Only values that change are written (num_tasked / last_time_tasked of targets that were not
+   * measured are not): the caller initialises the host block with one copy of the device block.
+   * Supported by the small-catalog kernel with update warps (task_of given, N <= 32768, M <= 256);
+   * ignored otherwise. */
+  const void* mirror_dev;
+  void* mirror_host;
+  int64_t mirror_bytes;
+  float* obs_cov_host;
 } pc_step_args;
 int pc_step_fused(pc_ctx* ctx, const pc_step_args* args, const pc_ukf_params* params,
                   pc_stream stream);
@@ -354,6 +368,14 @@ typedef struct pc_step_io {
   const void* d_block;
   void* h_block;
   int64_t block_bytes;
+  /* Zero-copy form of the one-copy form: with zero_copy != 0, a device-accessible h_block (see
+   * pc_step_args.mirror_host) whose first 6(M+N) + 37N floats mirror d_obs, a replayable argument block and
+   * a catalog the update-warp kernel handles (single environment, task_of, N <= 32768, M <= 256), the
+   * kernels store the observation and the summaries straight into h_block while they run -- the
+   * transfer overlaps the per-target kernel instead of following it -- and no copy is issued (one
+   * initialising copy when the graph is (re)built).  The device observation d_obs is then NOT refreshed.
+   * Falls back to the one-copy form when any condition fails. */
+  int32_t zero_copy;
 } pc_step_io;
 int pc_step_host(pc_ctx* ctx, const pc_step_args* args, const pc_ukf_params* params,
                  const pc_step_io* io, pc_stream stream);
