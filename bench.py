@@ -477,9 +477,11 @@ def run_own(args):
            "d2h_bytes_per_step": int(hb["block"].numel()),     # float32 obs | num_tasked | packed vis | traces, one copy
            "ms_per_step": float(e2e_ms.item()) / args.steps,
            "path": "host policy (pc_policy_random_visible_host on the previous step's packed map) -> CatalogEngine.step_host -> pc_step_host: pinned host actions "
-                   "-> [CUDA graph: pc_step_fused + pc_obs_pack] -> ONE copy of the output block (float32 obs | num_tasked | "
-                   "packed vis map | covariance traces | last_time_tasked) to pinned host memory, stream sync; timed by the "
-                   "host clock around the loop"}
+                   "-> [CUDA graph: H2D actions, pc_step_fused + pc_obs_pack] -> output block (float32 obs | num_tasked | packed vis "
+                   "map | covariance traces | last_time_tasked) in pinned host memory, stream sync; timed by the host clock "
+                   "around the loop.  Up to 32768 targets x 256 sensors per GPU and without a peer exchange the kernels store "
+                   "the block into the (mapped) host buffer themselves while they run (zero-copy form of pc_step_host, every "
+                   "byte rewritten every step); otherwise ONE device-to-host copy node at the end of the graph"}
 
     def leave():
         # Ranks leave together and without tearing NCCL down: destroying a process group whose
