@@ -75,6 +75,8 @@ struct pc_ctx {
   pc_step_args hs_args;
   pc_ukf_params hs_params;
   pc_step_io hs_io;
+  const void* hs_zc_ptr = nullptr;   // last host block checked for device accessibility (zero-copy form)
+  bool hs_zc_ok = false;
   float* hs_dobs = nullptr;
   cudaStream_t hs_stream = nullptr;
   int64_t hs_launches = 0;
@@ -1007,9 +1009,20 @@ int pc_step_host(pc_ctx* ctx, const pc_step_args* a, const pc_ukf_params* params
   const bool copy_actions = io->h_actions && a->M > 0;
   // zero-copy form: the kernels store the outputs into the (device-accessible) host block themselves
   const int64_t obs_floats = 6 * (a->M + a->N) + 37 * a->N;
-  const bool zero_copy = io->zero_copy && replayable && have_block && io->d_obs && a->env_targets <= 0 &&
-                         a->actions && a->task_of && !a->peer_table && pc::finish_fills_host_mirrors(a->N, a->M) &&
-                         io->d_obs == io->d_block && io->block_bytes >= obs_floats * (int64_t)sizeof(float);
+  bool zero_copy = io->zero_copy && replayable && have_block && io->d_obs && a->env_targets <= 0 &&
+                   a->actions && a->task_of && !a->peer_table && pc::finish_fills_host_mirrors(a->N, a->M) &&
+                   io->d_obs == io->d_block && io->block_bytes >= obs_floats * (int64_t)sizeof(float);
+  if (zero_copy) {
+    // the kernels will dereference h_block: it must be pinned / registered host memory (checked once per buffer)
+    if (ctx->hs_zc_ptr != io->h_block) {
+      cudaPointerAttributes at{};
+      const cudaError_t e = cudaPointerGetAttributes(&at, io->h_block);
+      if (e != cudaSuccess) cudaGetLastError();
+      ctx->hs_zc_ok = e == cudaSuccess && at.type == cudaMemoryTypeHost && at.devicePointer == io->h_block;
+      ctx->hs_zc_ptr = io->h_block;
+    }
+    zero_copy = ctx->hs_zc_ok;
+  }
   int rc = PC_OK;
   pc_step_args key;
   if (!replayable) {
