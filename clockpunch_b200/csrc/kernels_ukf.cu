@@ -17,7 +17,13 @@
 //   ukf_finish_kernel     one THREAD per target: unscented transform streamed over the 6 (+,-)
 //                         pairs, measurement update for tasked targets, outputs, and -- so that
 //                         the next step starts at the propagation stage -- the Cholesky factor and
-//                         sigma points of the NEW estimate (gen_next)
+//                         sigma points of the NEW estimate (gen_next); fused with the target's row
+//                         of both visibility maps
+//   ukf_finish_quad_kernel  the same stage for catalogs up to 32 k targets, where one thread per
+//                         target cannot fill the machine: FOUR lanes per target, and (with
+//                         pc_step_args.task_of) one extra CTA per sensor whose first warp does the
+//                         whole stage of the target that sensor tasks (coop_part1/2/3) while the
+//                         other three pre-run that code for the instruction caches
 // In steady state a step is therefore propagate -> finish; est_x IS block 0 and the truth state IS
 // block 13 of SB, so nothing is copied.
 //
