@@ -33,18 +33,20 @@ def test_struct_layouts_match_header():
     import ctypes as C
     import subprocess
     import tempfile
-    src = ('#include "%s"\n#include <cstdio>\n#include <cstddef>\nint main(){printf("%%zu %%zu %%zu %%zu %%zu %%zu",'
+    src = ('#include "%s"\n#include <cstdio>\n#include <cstddef>\nint main(){printf("%%zu %%zu %%zu %%zu %%zu %%zu %%zu %%zu %%zu %%zu",'
            'sizeof(pc_step_args), sizeof(pc_ukf_params), offsetof(pc_step_args, rng_seed),'
-           'offsetof(pc_step_args, words_per_row), offsetof(pc_step_args, tr_vel), offsetof(pc_ukf_params, R));}'
+           'offsetof(pc_step_args, words_per_row), offsetof(pc_step_args, tr_vel), offsetof(pc_ukf_params, R),'
+           'sizeof(pc_step_io), offsetof(pc_step_io, zero_copy), offsetof(pc_step_args, task_of),'
+           'offsetof(pc_step_args, obs_cov_host));}'
            % os.path.join(ROOT, "include", "punch_b200.h"))
     with tempfile.TemporaryDirectory() as d:
         cpp, exe = os.path.join(d, "a.cpp"), os.path.join(d, "a.out")
         open(cpp, "w").write(src)
         subprocess.check_call(["g++", cpp, "-o", exe])
         got = [int(v) for v in subprocess.check_output([exe]).split()]
-    S, U = _lib.StepArgs, _lib.UkfParams
+    S, U, IO = _lib.StepArgs, _lib.UkfParams, _lib.StepIO
     assert got == [C.sizeof(S), C.sizeof(U), S.rng_seed.offset, S.words_per_row.offset, S.tr_vel.offset,
-                   U.R.offset]
+                   U.R.offset, C.sizeof(IO), IO.zero_copy.offset, S.task_of.offset, S.obs_cov_host.offset]
 
 
 def test_reference_weights_bit_exact(golden):
