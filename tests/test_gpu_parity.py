@@ -789,3 +789,32 @@ def test_host_policy_equals_device_policy():
                                                      host.ctypes.data_as(C.c_void_p)) == 0
         np.testing.assert_array_equal(d_act.cpu().numpy(), host)
         assert (host < N).sum() > M // 2
+
+
+def test_folded_propagation_equals_single_state_kernel():
+    """Above 16 k targets the sigma points are advanced two per thread out of a sorted 256-target window
+    (propagate_sigma_kernel), below one per thread (propagate_sigma_single_kernel): the same arithmetic per
+    state, so the first targets of a large batch must come out bit-identical to the same targets run
+    alone -- including states whose substep count exceeds the 8-bit field of the window sort (the rule is
+    then evaluated again) and the clamp flag."""
+    from clockpunch_b200 import _lib
+    from clockpunch_b200.estimation.ukf_v2 import ukf_batch_host
+    from clockpunch_b200.simulation.catalog import synth_catalog
+    cat = synth_catalog(17_000, 4, seed=31)
+    x, p = cat.est_x.copy(), cat.est_p.copy()
+    mu = 398600.0
+    for k in range(24):                                   # eccentric orbits at perigee: orbit rates up to the clamp
+        rp, e = 6600.0 + 40.0 * k, 0.05 + 0.035 * k
+        vp = np.sqrt(mu * (1 + e) / rp)
+        x[:, 7 * k] = [rp, 0.0, 0.0, 0.0, vp * np.cos(0.3), vp * np.sin(0.3)]
+    params = _lib.make_ukf_params(cat.Q, cat.R)
+    dt = 30_000.0
+    big = ukf_batch_host(x, p, None, None, 0.0, dt, params)
+    m = 300
+    small = ukf_batch_host(x[:, :m], p[:m], None, None, 0.0, dt, params)
+    for k in ("est_x", "pred_x"):
+        np.testing.assert_array_equal(big[k][:, :m], small[k], err_msg=k)
+    for k in ("est_p", "pred_p", "flags"):
+        np.testing.assert_array_equal(big[k][:m], small[k], err_msg=k)
+    assert np.isfinite(small["pred_x"]).all()
+
