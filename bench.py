@@ -55,8 +55,11 @@ BYTES_TARGET_STEP = 1130.0         # truth/est_x/est_p r+w, pred_p w, z r (+ M/4
 
 
 def workload_config(n_targets, n_sensors):
+    which = ("BASELINE.json configs[1]" if (n_targets, n_sensors) == (N_TARGETS, N_SENSORS) else
+             "BASELINE.json configs[3] shard (1 M targets over 8 GPUs)" if (n_targets, n_sensors) == (125_000, 100) else
+             "other size of the configs[1] workload")
     return {"workload": f"{n_sensors} ground sensors x {n_targets} mixed LEO/MEO/GEO targets, two-body, "
-                        f"dt={DT:.0f}s, UKF per target (BASELINE.json configs[1])",
+                        f"dt={DT:.0f}s, UKF per target ({which})",
             "targets_per_gpu": n_targets, "sensors": n_sensors, "dt_s": DT,
             "tasking": "each sensor tasks a random estimated-visible target (<= M per step)",
             "episode": f"catalog reset to its initial state every {EPISODE} steps (outside the timed events)",
