@@ -138,3 +138,38 @@ def test_radial_rate_and_vis_derivative(golden):
         assert v0 == visibility_func(xa[:3], xb[:3], RE, 0.0, 1e-6)[0]
     vm, dm = calc_vis_map_and_derivative(X[:, 48:52], X[:, :6])
     assert vm.shape == dm.shape == (6, 4) and set(np.unique(vm)) <= {0, 1}
+
+
+def test_ez_ukf_parameter_forms_without_gpu():
+    """ezUKF / getRandomParams (ez_ukf.py:17-119): float -> v I6, (6,6) ndarray as given, {dist, params, seed}
+    -> diag of numpy's default_rng draw; time defaults to 0; weights as in ukf_v2.py:58-128.  Building a
+    filter touches no device."""
+    import numpy as np
+    import pytest
+    from numpy.random import default_rng
+    from clockpunch_b200.dynamics.dynamics_classes import SatDynamicsModel, StaticTerrestrial
+    from clockpunch_b200.estimation.ez_ukf import ezUKF, getRandomParams
+    x = np.array([8000.0, 0, 0, 0, 8, 0])
+    spec = {"dist": "uniform", "params": [[0.1] * 6, [1.0] * 6], "seed": 2}
+    R = np.diag([1, 1, 1, 0.01, 0.01, 0.01])
+    f = ezUKF({"x_init": x, "p_init": 0.1, "dynamics_type": "satellite", "Q": spec, "R": R})
+    np.testing.assert_array_equal(f.est_p, 0.1 * np.eye(6))
+    np.testing.assert_array_equal(f.q_matrix, np.diag(default_rng(2).uniform([0.1] * 6, [1.0] * 6)))
+    np.testing.assert_array_equal(f.r_matrix, R)
+    assert f.time == 0 and f.x_dim == 6 and f.y_dim == 6 and isinstance(f.dynamics, SatDynamicsModel)
+    n, alpha, beta, kappa = 6, 1e-3, 2.0, 3 - 6
+    lam = alpha**2 * (n + kappa) - n
+    assert f.gamma == np.sqrt(n + lam)
+    assert f.mean_weight[0] == lam / (n + lam) and f.mean_weight[1] == 1 / (2 * (n + lam))
+    assert f.cvr_weight[0, 0] == lam / (n + lam) + 1 - alpha**2 + beta
+    g = ezUKF({"time": 7, "x_init": x, "p_init": np.eye(6), "dynamics_type": "satellite", "Q": 2, "R": 0.5})
+    assert g.time == 7
+    np.testing.assert_array_equal(g.q_matrix, 2 * np.eye(6))
+    np.testing.assert_array_equal(g.r_matrix, 0.5 * np.eye(6))
+    # a filter on Earth-fixed dynamics is not on the hot path: it fails loudly instead of running on the CPU
+    with pytest.raises(NotImplementedError):
+        ezUKF({"x_init": x, "p_init": 1, "dynamics_type": "terrestrial", "Q": 2, "R": 0.5})
+    assert StaticTerrestrial is not None
+    np.testing.assert_array_equal(getRandomParams("normal", [[0, 0], [1, 2]], seed=5), default_rng(5).normal([0, 0], [1, 2]))
+    with pytest.raises(AssertionError):
+        ezUKF({"x_init": x, "p_init": 1, "dynamics_type": "satellite", "Q": {"dist": "uniform", "params": [[0] * 5, [1] * 5]}, "R": 1})
