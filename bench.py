@@ -262,8 +262,9 @@ def run_own(args):
         if args.exchange in ("peer", "auto"):
             try:
                 eng.enable_peer_push()
-                mode = os.environ.get("PC_PEER_MODE", "")
-                by_copy = mode == "copy" or (mode != "store" and (N > 32768 or world >= 8))
+                mode = {"auto": 0, "store": 1, "copy": 2}[args.peer_push]
+                ctx_opt = eng.ctx.set_option(_lib.OPT_PEER_PUSH, mode)
+                by_copy = mode == 2 or (mode == 0 and (N > 32768 or world >= 8))
                 exchange = ("peer stores from the per-target kernel" if not by_copy else
                             "summary pushed into every peer by a copy kernel behind the per-target kernel") + \
                     " (symmetric memory over NVLink) + flag wait"
@@ -535,6 +536,8 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--l2", default="flush", choices=["flush", "none"])
     ap.add_argument("--eager-gather", action="store_true", help="N > 1: all-gather outside the step's CUDA graph")
+    ap.add_argument("--peer-push", default="auto", choices=["auto", "store", "copy"],
+                    help="N > 1, peer exchange: stores from the per-target kernel or a copy kernel behind it (auto: size rule)")
     ap.add_argument("--exchange", default="auto", choices=["auto", "peer", "nccl"],
                     help="N > 1: summaries pushed into peers' memory by the step kernel, or one NCCL all-gather")
     args = ap.parse_args()

@@ -34,3 +34,18 @@ def empty(shape, ctx, dtype=None):
 def stream_ptr(ctx) -> int:
     torch = torch_mod()
     return torch.cuda.current_stream(device_of(ctx)).cuda_stream
+
+
+class _RawDeviceBytes:
+    """__cuda_array_interface__ over memory the library owns (pc_comm_table's gathered buffer)."""
+
+    def __init__(self, ptr: int, nbytes: int):
+        self.__cuda_array_interface__ = {"shape": (int(nbytes),), "typestr": "|u1", "data": (int(ptr), False),
+                                         "version": 2, "strides": None}
+
+
+def device_view(ptr: int, nbytes: int, device):
+    """uint8 tensor aliasing `nbytes` of device memory at `ptr` (no copy, no ownership)."""
+    torch = torch_mod()
+    with torch.cuda.device(device):
+        return torch.as_tensor(_RawDeviceBytes(ptr, nbytes), device=device)

@@ -9,12 +9,16 @@ from fractions import Fraction
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.environ.get("PUNCH_B200_LIB") or os.path.join(_HERE, "libpunch_b200.so")   # override: experiments only
+# (PUNCH_B200_LIB: variant builds of tools/build_variant.sh, e.g. the phase-stamp library of tools/debug)
+LIB_PATH = os.environ.get("PUNCH_B200_LIB") or os.path.join(_HERE, "libpunch_b200.so")
 
 PC_OK, PC_ERR_BAD_ARG, PC_ERR_CUDA, PC_ERR_EQUAL_TIMES, PC_ERR_NO_DEVICE = 0, -1, -2, -3, -4
 KIND_SATELLITE, KIND_TERRESTRIAL = 0, 1
 FORCE_TWOBODY, FORCE_TWOBODY_J2 = 0, 1
 FLAG_NONPD_EST, FLAG_NONPD_PRED, FLAG_NONPD_INNOV, FLAG_NONFINITE, FLAG_SUBSTEP_CLAMP = 1, 2, 4, 8, 16
+OPT_FINISH_KERNEL, OPT_PROPAGATE_KERNEL, OPT_PEER_PUSH = 1, 2, 3          # pc_option
+FINISH_AUTO, FINISH_QUAD_UPDATE_WARPS, FINISH_QUAD_INLINE, FINISH_THREAD_64, FINISH_THREAD_128 = 0, 1, 2, 3, 4
+COMM_HANDLE_BYTES = 64
 
 c_dp = C.POINTER(C.c_double)
 c_u8p = C.POINTER(C.c_uint8)
@@ -69,6 +73,8 @@ _SIGNATURES = {
     "pc_ctx_destroy": ([_vp], _int),
     "pc_last_error": ([_vp], C.c_char_p),
     "pc_launch_count": ([_vp], _i64),
+    "pc_set_option": ([_vp, _int, _int], _int),
+    "pc_get_option": ([_vp, _int, C.POINTER(_int)], _int),
     "pc_propagate_twobody": ([_vp, _vp, _vp, _i64, _i64, _dbl, _dbl, _int, _int, _vp], _int),
     "pc_rotate_terrestrial": ([_vp, _vp, _vp, _i64, _i64, _dbl, _dbl, _vp], _int),
     "pc_propagate_agents": ([_vp, _vp, _vp, _vp, _i64, _i64, _dbl, _dbl, _int, _int, _vp], _int),
@@ -101,6 +107,13 @@ _SIGNATURES = {
     "pc_fp64_peak": ([_vp, _int, C.POINTER(_dbl)], _int),
     "pc_step_fused": ([_vp, C.POINTER(StepArgs), C.POINTER(UkfParams), _vp], _int),
     "pc_peer_status": ([_vp, C.POINTER(C.c_uint32), C.POINTER(C.c_uint64)], _int),
+    "pc_peer_wait": ([_vp, _vp, C.c_int32, C.c_int32, _vp], _int),
+    "pc_comm_init": ([_vp, C.c_int32, C.c_int32, _i64, _vp], _int),
+    "pc_comm_attach": ([_vp, _vp], _int),
+    "pc_comm_table": ([_vp, C.POINTER(_vp), C.POINTER(_vp), C.POINTER(C.c_int32), C.POINTER(C.c_int32),
+                       C.POINTER(_i64)], _int),
+    "pc_allgather_step": ([_vp, _vp, _vp], _int),
+    "pc_comm_destroy": ([_vp], _int),
     "pc_step_host": ([_vp, C.POINTER(StepArgs), C.POINTER(UkfParams), C.POINTER(StepIO), _vp], _int),
 }
 EXPORTED_SYMBOLS = tuple(_SIGNATURES)
@@ -159,6 +172,13 @@ class Context:
     @property
     def launch_count(self) -> int:
         return int(self.lib.pc_launch_count(self.handle))
+
+    def set_option(self, option: int, value: int) -> int:
+        """pc_set_option; returns the previous value (kernel-mapping overrides: tests, tuning)."""
+        old = C.c_int(0)
+        self.check(self.lib.pc_get_option(self.handle, option, C.byref(old)))
+        self.check(self.lib.pc_set_option(self.handle, option, value))
+        return old.value
 
     def close(self):
         if self.handle:

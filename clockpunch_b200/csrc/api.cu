@@ -30,7 +30,9 @@ cudaError_t launch_pre_step(double* sens_x, const uint8_t* sens_kind, int64_t M,
                             double body_radius, double vis_tol, pc_clock* clock, int64_t* actions,
                             const uint32_t* vis_est, uint8_t* tasked, int64_t N, int64_t wpr,
                             int probes, uint64_t seed, uint64_t step, int64_t env_targets,
-                            int64_t env_sensors, int64_t* task_of, cudaStream_t s);
+                            int64_t env_sensors, int64_t* task_of, const uint64_t* peer_table,
+                            int peer_world, int peer_rank, const unsigned long long* peer_seq,
+                            unsigned int* peer_err, cudaStream_t s);
 
 cudaError_t launch_frame_change(const double*, double*, int64_t, int64_t, double, double, cudaStream_t);
 cudaError_t launch_coe2eci(const double*, double*, int64_t, int64_t, double, cudaStream_t);
@@ -69,17 +71,36 @@ struct pc_ctx {
   size_t sq_sensors = 0;
   // peer push: "last CTA done" ticket and the wait kernel's error mask (device), see PeerPush
   unsigned int* peer_dev = nullptr;   // [0] ticket, [1] error mask, [2..3] 64-bit push sequence number
-  // pc_step_host: the captured step (pc_step_fused + pc_obs_pack) and the arguments it was
-  // captured with; replayed while the caller keeps passing the same buffers
-  cudaGraphExec_t hs_exec = nullptr;
-  pc_step_args hs_args;
-  pc_ukf_params hs_params;
-  pc_step_io hs_io;
+  // pc_step_host: captured steps (pc_step_fused + pc_obs_pack) and the arguments each was captured
+  // with, replayed while a caller keeps passing the same buffers.  Several engines share one context
+  // (deep-copied environments do: the reference's wrappers and SimRunner copy the env every step), so
+  // the cache holds a few graphs, least recently used one evicted.
+  struct HsEntry {
+    cudaGraphExec_t exec = nullptr;
+    pc_step_args args;
+    pc_ukf_params params;
+    pc_step_io io;
+    cudaStream_t stream = nullptr;
+    int64_t launches = 0;
+    uint64_t last_use = 0;
+  };
+  static constexpr int kHsEntries = 8;
+  HsEntry hs[kHsEntries];
+  uint64_t hs_tick = 0;
   const void* hs_zc_ptr = nullptr;   // last host block checked for device accessibility (zero-copy form)
   bool hs_zc_ok = false;
-  float* hs_dobs = nullptr;
-  cudaStream_t hs_stream = nullptr;
-  int64_t hs_launches = 0;
+  // kernel-mapping overrides (pc_set_option)
+  int opt_finish = 0, opt_prop = 0, opt_peer = 0;
+  // pc_comm_*: this rank's gathered buffer + flags (one cudaMalloc, shared by CUDA IPC), the peers'
+  // mappings and the device table pc_step_args.peer_table points at
+  struct Comm {
+    int world = 0, rank = 0;
+    int64_t slot_bytes = 0;
+    void* base = nullptr;              // [flags: 64 x uint64][gathered: 2 x world x slot_bytes]
+    std::vector<void*> opened;         // peers' bases as mapped here (own rank: base)
+    uint64_t* table = nullptr;         // device: [world] gathered bases, [world] flag bases
+    bool attached = false;
+  } comm;
 };
 
 int pc_fail(pc_ctx* ctx, int code, const char* msg) {
@@ -187,7 +208,9 @@ int pc_ctx_destroy(pc_ctx* ctx) {
     if (ctx->peer_dev) cudaFree(ctx->peer_dev);
     if (ctx->ev0) cudaEventDestroy(ctx->ev0);
     if (ctx->ev1) cudaEventDestroy(ctx->ev1);
-    if (ctx->hs_exec) cudaGraphExecDestroy(ctx->hs_exec);
+    for (auto& e : ctx->hs)
+      if (e.exec) cudaGraphExecDestroy(e.exec);
+    pc_comm_destroy(ctx);
   }
   delete ctx;
   return PC_OK;
@@ -195,6 +218,34 @@ int pc_ctx_destroy(pc_ctx* ctx) {
 
 const char* pc_last_error(pc_ctx* ctx) { return ctx ? ctx->err.c_str() : "null context"; }
 int64_t pc_launch_count(pc_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+static int* option_slot(pc_ctx* ctx, int option, int* max_value) {
+  switch (option) {
+    case PC_OPT_FINISH_KERNEL: *max_value = 4; return &ctx->opt_finish;
+    case PC_OPT_PROPAGATE_KERNEL: *max_value = 2; return &ctx->opt_prop;
+    case PC_OPT_PEER_PUSH: *max_value = 2; return &ctx->opt_peer;
+    default: return nullptr;
+  }
+}
+
+int pc_set_option(pc_ctx* ctx, int option, int value) {
+  PC_REQUIRE(ctx, ctx != nullptr, "null context");
+  int mx = 0;
+  int* slot = option_slot(ctx, option, &mx);
+  PC_REQUIRE(ctx, slot != nullptr, "unknown option");
+  PC_REQUIRE(ctx, value >= 0 && value <= mx, "option value out of range");
+  *slot = value;
+  return PC_OK;
+}
+
+int pc_get_option(pc_ctx* ctx, int option, int* value) {
+  PC_REQUIRE(ctx, ctx != nullptr && value != nullptr, "null pointer");
+  int mx = 0;
+  int* slot = option_slot(ctx, option, &mx);
+  PC_REQUIRE(ctx, slot != nullptr, "unknown option");
+  *value = *slot;
+  return PC_OK;
+}
 
 /* ---- K1 ---------------------------------------------------------------- */
 static int propagate_common(pc_ctx* ctx, const double* x_in, double* x_out, const uint8_t* kind,
@@ -547,7 +598,7 @@ int pc_ukf_predict_update(pc_ctx* ctx, double* est_x, double* est_p, double* tru
   PC_CUDA_TRY(ctx, pc::launch_sigma_gen(est_x, est_p, truth_x, ctx->sb, n, ld, params->gamma, ctx->sbf, st));
   // stage 2: all 13 (+1) n states
   PC_CUDA_TRY(ctx, pc::launch_propagate_sigma(ctx->sb, n, ld, truth_x != nullptr, t0, tf, substeps,
-                                              force_model, ctx->sbf, false, st));
+                                              force_model, ctx->sbf, false, ctx->opt_prop, st));
   // stage 3: unscented transform + update
   pc::UkfArgs u{};
   u.sb = ctx->sb;
@@ -568,6 +619,7 @@ int pc_ukf_predict_update(pc_ctx* ctx, double* est_x, double* est_p, double* tru
   u.sig_flags = ctx->sbf;
   u.est_x_out = est_x;
   u.truth_out = truth_x;
+  u.variant = ctx->opt_finish;
   u.p = *params;
   PC_CUDA_TRY(ctx, pc::launch_ukf_finish(u, st));
   ctx->launches += 2;
@@ -817,13 +869,17 @@ int pc_step_fused(pc_ctx* ctx, const pc_step_args* a, const pc_ukf_params* param
   //    tasking mask from the actions and the PREVIOUS estimated vis map, step clock latch.
   //    Independent of the target propagation, which is launched programmatically behind it and
   //    therefore runs beside it (no fork / join, no second stream).
-  const bool pre = a->M > 0 || a->clock;
+  //    Multi-GPU: the same kernel waits for the peers' summaries of the PREVIOUS step (see PeerPush).
+  const bool pre = a->M > 0 || a->clock || (a->peer_table && a->N > 0);
   if (pre) {
     PC_CUDA_TRY(ctx, pc::launch_pre_step(a->sens_x, a->sens_kind, a->M, a->ld_s, a->t0, a->tf, a->substeps,
                                          a->force_model, fuse_vis ? sq : nullptr, a->body_radius, a->vis_tol,
                                          a->clock, a->actions, a->vis_est, const_cast<uint8_t*>(a->tasked),
                                          a->N, a->words_per_row, a->policy_probes, a->policy_seed,
-                                         a->rng_step, Ne, Me, a->actions ? a->task_of : nullptr, s));
+                                         a->rng_step, Ne, Me, a->actions ? a->task_of : nullptr,
+                                         a->N > 0 ? a->peer_table : nullptr, a->peer_world, a->peer_rank,
+                                         reinterpret_cast<const unsigned long long*>(ctx->peer_dev + 2),
+                                         ctx->peer_dev + 1, s));
     ctx->launches += 1;
   }
   // 2. targets: sigma points (only when not carried over from the previous step), all 14 N
@@ -845,7 +901,7 @@ int pc_step_fused(pc_ctx* ctx, const pc_step_args* a, const pc_ukf_params* param
       PC_CUDA_TRY(ctx, cudaEventRecordWithFlags(ctx->ev0, s, evflags));
     }
     PC_CUDA_TRY(ctx, pc::launch_propagate_sigma(sb, a->N, a->ld, 1, a->t0, a->tf, a->substeps,
-                                                a->force_model, sbf, beside, s));
+                                                a->force_model, sbf, beside, ctx->opt_prop, s));
     if (ctx->timing) PC_CUDA_TRY(ctx, cudaEventRecordWithFlags(ctx->ev1, s, evflags));
     pc::UkfArgs u{};
     u.sb = sb;
@@ -876,7 +932,7 @@ int pc_step_fused(pc_ctx* ctx, const pc_step_args* a, const pc_ukf_params* param
       u.task_of = a->task_of;
       u.task_sensors = a->M;
       u.task_env_sensors = Me;
-      if (a->mirror_host && a->mirror_dev && a->mirror_bytes > 0 && pc::finish_fills_host_mirrors(a->N, a->M)) {
+      if (a->mirror_host && a->mirror_dev && a->mirror_bytes > 0 && pc::finish_fills_host_mirrors(a->N, a->M, ctx->opt_finish)) {
         // host mirrors of the summary arrays that live inside the caller's device block
         const char* d0 = static_cast<const char*>(a->mirror_dev);
         char* h0 = static_cast<char*>(a->mirror_host);
@@ -890,7 +946,7 @@ int pc_step_fused(pc_ctx* ctx, const pc_step_args* a, const pc_ukf_params* param
         u.h_tr_vel = reinterpret_cast<float*>(mirror(a->tr_vel));
         u.h_ltt = reinterpret_cast<float*>(mirror(a->last_time_tasked));
       }
-      if (pc::finish_fills_host_mirrors(a->N, a->M)) u.h_cov = a->obs_cov_host;
+      if (pc::finish_fills_host_mirrors(a->N, a->M, ctx->opt_finish)) u.h_cov = a->obs_cov_host;
     }
     if (fuse_vis) {
       u.sens_q = reinterpret_cast<const double4*>(sq);
@@ -908,14 +964,9 @@ int pc_step_fused(pc_ctx* ctx, const pc_step_args* a, const pc_ukf_params* param
     // summary buffer and a copy kernel, launched programmatically behind it, pushes the buffer with
     // 16-byte stores (a shard then moves megabytes per step; per-thread 4-byte stores to 8 peers
     // lose to a streaming copy: 0.307 vs 0.264 ms at 8 x 125 k targets, NCCL all-gather 0.287 ms).
-    // PC_PEER_MODE=store|copy overrides the size rule (experiments).
-    static const int peer_mode = [] {
-      const char* e = getenv("PC_PEER_MODE");
-      return !e ? 0 : (std::strcmp(e, "copy") == 0 ? 2 : (std::strcmp(e, "store") == 0 ? 1 : 0));
-    }();
     // (8 peers: 72 remote 4-byte stores per target from the latency-critical kernel lose to the copy
-    // kernel also at 10 k targets per shard, 55.0 vs 57.2 us per step)
-    const bool peer_copy = peer_mode == 2 || (peer_mode == 0 && (a->N > 32768 || a->peer_world >= 8));
+    // kernel also at 10 k targets per shard, 55.0 vs 57.2 us per step.)  pc_option PC_OPT_PEER_PUSH pins it.
+    const bool peer_copy = ctx->opt_peer == 2 || (ctx->opt_peer == 0 && (a->N > 32768 || a->peer_world >= 8));
     pc::PeerPush pp_copy{};
     if (a->peer_table) {
       const char* base = static_cast<const char*>(a->summary_base);
@@ -935,19 +986,15 @@ int pc_step_fused(pc_ctx* ctx, const pc_step_args* a, const pc_ukf_params* param
         u.pp = pc::PeerPush{};
       }
     }
+    u.variant = ctx->opt_finish;
     u.p = *params;
     PC_CUDA_TRY(ctx, pc::launch_ukf_finish(u, s));
     ctx->launches += 2;
     if (pp_copy.world) {
-      PC_CUDA_TRY(ctx, pc::launch_peer_push(a->summary_base, a->summary_bytes, pp_copy, s));
+      PC_CUDA_TRY(ctx, pc::launch_peer_push(a->summary_base, a->summary_bytes, pp_copy, true, s));
       ctx->launches += 1;
     }
-    if (a->peer_table) {
-      PC_CUDA_TRY(ctx, pc::launch_peer_wait(a->peer_table, a->peer_world, a->peer_rank,
-                                            reinterpret_cast<const unsigned long long*>(ctx->peer_dev + 2),
-                                            ctx->peer_dev + 1, s));
-      ctx->launches += 1;
-    }
+    // (no wait here: the next step's sensor kernel waits for the peers, beside its propagation)
   } else if (a->clock) {
     PC_CUDA_TRY(ctx, pc::launch_advance_clock(a->clock, a->tf - a->t0, s));
     ctx->launches += 1;
@@ -963,6 +1010,121 @@ int pc_peer_status(pc_ctx* ctx, uint32_t* out_error_mask, uint64_t* out_pushes) 
   PC_CUDA_TRY(ctx, cudaMemset(ctx->peer_dev + 1, 0, sizeof(unsigned int)));
   *out_error_mask = v[1];
   *out_pushes = (uint64_t)v[2] | ((uint64_t)v[3] << 32);
+  return PC_OK;
+}
+
+int pc_peer_wait(pc_ctx* ctx, const uint64_t* peer_table, int32_t peer_world, int32_t peer_rank,
+                 pc_stream stream) {
+  PC_REQUIRE(ctx, ctx != nullptr && peer_table != nullptr, "null pointer");
+  PC_REQUIRE(ctx, peer_world >= 1 && peer_world <= 64 && peer_rank >= 0 && peer_rank < peer_world,
+             "bad peer_world / peer_rank");
+  DeviceGuard g(ctx->device);
+  PC_CUDA_TRY(ctx, pc::launch_peer_wait(peer_table, peer_world, peer_rank,
+                                        reinterpret_cast<const unsigned long long*>(ctx->peer_dev + 2),
+                                        ctx->peer_dev + 1, false, (cudaStream_t)stream));
+  ctx->launches += 1;
+  return PC_OK;
+}
+
+/* ---- peer exchange set-up over CUDA IPC (no framework needed) ----------------------------------- */
+static constexpr size_t kCommFlagBytes = 64 * sizeof(uint64_t);
+
+int pc_comm_init(pc_ctx* ctx, int32_t world, int32_t rank, int64_t summary_bytes,
+                 uint8_t handle_out[PC_COMM_HANDLE_BYTES]) {
+  PC_REQUIRE(ctx, ctx != nullptr && handle_out != nullptr, "null pointer");
+  PC_REQUIRE(ctx, world >= 1 && world <= 64 && rank >= 0 && rank < world, "bad world / rank");
+  PC_REQUIRE(ctx, summary_bytes > 0, "summary_bytes must be positive");
+  static_assert(sizeof(cudaIpcMemHandle_t) == PC_COMM_HANDLE_BYTES, "handle size");
+  DeviceGuard g(ctx->device);
+  int rc = pc_comm_destroy(ctx);
+  if (rc) return rc;
+  auto& c = ctx->comm;
+  const size_t bytes = kCommFlagBytes + 2 * (size_t)world * (size_t)summary_bytes;
+  PC_CUDA_TRY(ctx, cudaMalloc(&c.base, bytes));
+  PC_CUDA_TRY(ctx, cudaMemset(c.base, 0, bytes));
+  // the push counter restarts with the (zeroed) flags
+  PC_CUDA_TRY(ctx, cudaMemset(ctx->peer_dev, 0, 4 * sizeof(unsigned int)));
+  PC_CUDA_TRY(ctx, cudaDeviceSynchronize());
+  cudaIpcMemHandle_t h;
+  PC_CUDA_TRY(ctx, cudaIpcGetMemHandle(&h, c.base));
+  std::memcpy(handle_out, &h, sizeof(h));
+  c.world = world;
+  c.rank = rank;
+  c.slot_bytes = summary_bytes;
+  return PC_OK;
+}
+
+int pc_comm_attach(pc_ctx* ctx, const uint8_t* all_handles) {
+  PC_REQUIRE(ctx, ctx != nullptr && all_handles != nullptr, "null pointer");
+  auto& c = ctx->comm;
+  PC_REQUIRE(ctx, c.base != nullptr && !c.attached, "pc_comm_init first (and attach once)");
+  DeviceGuard g(ctx->device);
+  c.opened.assign((size_t)c.world, nullptr);
+  for (int r = 0; r < c.world; ++r) {
+    if (r == c.rank) {
+      c.opened[r] = c.base;
+      continue;
+    }
+    cudaIpcMemHandle_t h;
+    std::memcpy(&h, all_handles + (size_t)r * PC_COMM_HANDLE_BYTES, sizeof(h));
+    PC_CUDA_TRY(ctx, cudaIpcOpenMemHandle(&c.opened[r], h, cudaIpcMemLazyEnablePeerAccess));
+  }
+  std::vector<uint64_t> tab(2 * (size_t)c.world);
+  for (int r = 0; r < c.world; ++r) {
+    tab[r] = reinterpret_cast<uint64_t>(static_cast<char*>(c.opened[r]) + kCommFlagBytes);
+    tab[c.world + r] = reinterpret_cast<uint64_t>(c.opened[r]);
+  }
+  PC_CUDA_TRY(ctx, cudaMalloc(&c.table, tab.size() * sizeof(uint64_t)));
+  PC_CUDA_TRY(ctx, cudaMemcpy(c.table, tab.data(), tab.size() * sizeof(uint64_t), cudaMemcpyHostToDevice));
+  c.attached = true;
+  return PC_OK;
+}
+
+int pc_comm_table(pc_ctx* ctx, const uint64_t** out_table, void** out_gathered, int32_t* out_world,
+                  int32_t* out_rank, int64_t* out_summary_bytes) {
+  PC_REQUIRE(ctx, ctx != nullptr, "null context");
+  auto& c = ctx->comm;
+  PC_REQUIRE(ctx, c.attached, "no attached peer exchange on this context");
+  if (out_table) *out_table = c.table;
+  if (out_gathered) *out_gathered = static_cast<char*>(c.base) + kCommFlagBytes;
+  if (out_world) *out_world = c.world;
+  if (out_rank) *out_rank = c.rank;
+  if (out_summary_bytes) *out_summary_bytes = c.slot_bytes;
+  return PC_OK;
+}
+
+int pc_allgather_step(pc_ctx* ctx, const void* summary, pc_stream stream) {
+  PC_REQUIRE(ctx, ctx != nullptr && summary != nullptr, "null pointer");
+  auto& c = ctx->comm;
+  PC_REQUIRE(ctx, c.attached, "no attached peer exchange on this context");
+  PC_REQUIRE(ctx, c.slot_bytes % 16 == 0 && reinterpret_cast<uintptr_t>(summary) % 16 == 0,
+             "pc_allgather_step needs a 16-byte aligned summary buffer and size");
+  DeviceGuard g(ctx->device);
+  cudaStream_t s = (cudaStream_t)stream;
+  pc::PeerPush pp{};
+  pp.world = c.world;
+  pp.rank = c.rank;
+  pp.table = c.table;
+  pp.slot_bytes = c.slot_bytes;
+  pp.ticket = ctx->peer_dev;
+  pp.seq = reinterpret_cast<unsigned long long*>(ctx->peer_dev + 2);
+  PC_CUDA_TRY(ctx, pc::launch_peer_push(summary, c.slot_bytes, pp, false, s));
+  PC_CUDA_TRY(ctx, pc::launch_peer_wait(c.table, c.world, c.rank, pp.seq, ctx->peer_dev + 1, false, s));
+  ctx->launches += 2;
+  return PC_OK;
+}
+
+int pc_comm_destroy(pc_ctx* ctx) {
+  if (!ctx) return PC_OK;
+  auto& c = ctx->comm;
+  if (!c.base) return PC_OK;
+  DeviceGuard g(ctx->device);
+  cudaDeviceSynchronize();
+  for (int r = 0; r < (int)c.opened.size(); ++r)
+    if (r != c.rank && c.opened[r]) cudaIpcCloseMemHandle(c.opened[r]);
+  if (c.table) cudaFree(c.table);
+  cudaFree(c.base);
+  c = pc_ctx::Comm{};
   return PC_OK;
 }
 
@@ -1010,7 +1172,7 @@ int pc_step_host(pc_ctx* ctx, const pc_step_args* a, const pc_ukf_params* params
   // zero-copy form: the kernels store the outputs into the (device-accessible) host block themselves
   const int64_t obs_floats = 6 * (a->M + a->N) + 37 * a->N;
   bool zero_copy = io->zero_copy && replayable && have_block && io->d_obs && a->env_targets <= 0 &&
-                   a->actions && a->task_of && !a->peer_table && pc::finish_fills_host_mirrors(a->N, a->M) &&
+                   a->actions && a->task_of && pc::finish_fills_host_mirrors(a->N, a->M, ctx->opt_finish) &&
                    io->d_obs == io->d_block && io->block_bytes >= obs_floats * (int64_t)sizeof(float);
   if (zero_copy) {
     // the kernels will dereference h_block: it must be pinned / registered host memory (checked once per buffer)
@@ -1052,14 +1214,29 @@ int pc_step_host(pc_ctx* ctx, const pc_step_args* a, const pc_ukf_params* params
       key.obs_cov_host = nullptr;
     }
     a = &key;
-    const bool hit = ctx->hs_exec && ctx->hs_stream == s && ctx->hs_dobs == io->d_obs &&
-                     std::memcmp(&ctx->hs_io, io, sizeof(*io)) == 0 &&
-                     std::memcmp(&ctx->hs_args, a, sizeof(*a)) == 0 &&
-                     std::memcmp(&ctx->hs_params, params, sizeof(*params)) == 0;
-    if (!hit) {
-      if (ctx->hs_exec) {
-        cudaGraphExecDestroy(ctx->hs_exec);
-        ctx->hs_exec = nullptr;
+    pc_ctx::HsEntry* ent = nullptr;
+    for (auto& e : ctx->hs)
+      if (e.exec && e.stream == s && std::memcmp(&e.io, io, sizeof(*io)) == 0 &&
+          std::memcmp(&e.args, a, sizeof(*a)) == 0 && std::memcmp(&e.params, params, sizeof(*params)) == 0) {
+        ent = &e;
+        break;
+      }
+    if (!ent) {
+      // a free slot, else the slot of the same engine (same sigma buffer: its old graph is stale), else
+      // the least recently used one
+      for (auto& e : ctx->hs)
+        if (!e.exec) { ent = &e; break; }
+      if (!ent)
+        for (auto& e : ctx->hs)
+          if (e.args.sigma_ws == a->sigma_ws) { ent = &e; break; }
+      if (!ent) {
+        ent = &ctx->hs[0];
+        for (auto& e : ctx->hs)
+          if (e.last_use < ent->last_use) ent = &e;
+      }
+      if (ent->exec) {
+        cudaGraphExecDestroy(ent->exec);
+        ent->exec = nullptr;
       }
       const int64_t before = ctx->launches;
       cudaGraph_t graph = nullptr;
@@ -1072,27 +1249,28 @@ int pc_step_host(pc_ctx* ctx, const pc_step_args* a, const pc_ukf_params* params
         ec = cudaMemcpyAsync(io->h_block, io->d_block, (size_t)io->block_bytes, cudaMemcpyDeviceToHost, s);
       cudaError_t e = cudaStreamEndCapture(s, &graph);
       if (rc == PC_OK && ec != cudaSuccess) e = ec;
-      ctx->hs_launches = ctx->launches - before;
+      ent->launches = ctx->launches - before;
       ctx->launches = before;
       if (rc) {
         if (graph) cudaGraphDestroy(graph);
         return rc;
       }
       PC_CUDA_TRY(ctx, e);
-      e = cudaGraphInstantiate(&ctx->hs_exec, graph, 0);
+      e = cudaGraphInstantiate(&ent->exec, graph, 0);
       cudaGraphDestroy(graph);
+      if (e != cudaSuccess) ent->exec = nullptr;
       PC_CUDA_TRY(ctx, e);
-      std::memcpy(&ctx->hs_args, a, sizeof(*a));
-      std::memcpy(&ctx->hs_params, params, sizeof(*params));
-      std::memcpy(&ctx->hs_io, io, sizeof(*io));
-      ctx->hs_dobs = io->d_obs;
-      ctx->hs_stream = s;
+      std::memcpy(&ent->args, a, sizeof(*a));
+      std::memcpy(&ent->params, params, sizeof(*params));
+      std::memcpy(&ent->io, io, sizeof(*io));
+      ent->stream = s;
       // the kernels only store what changes: start from a full copy of the device block
       if (zero_copy)
         PC_CUDA_TRY(ctx, cudaMemcpyAsync(io->h_block, io->d_block, (size_t)io->block_bytes, cudaMemcpyDeviceToHost, s));
     }
-    PC_CUDA_TRY(ctx, cudaGraphLaunch(ctx->hs_exec, s));
-    ctx->launches += ctx->hs_launches;
+    ent->last_use = ++ctx->hs_tick;
+    PC_CUDA_TRY(ctx, cudaGraphLaunch(ent->exec, s));
+    ctx->launches += ent->launches;
     if (have_block) {
       PC_CUDA_TRY(ctx, cudaStreamSynchronize(s));
       return PC_OK;

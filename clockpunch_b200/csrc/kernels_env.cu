@@ -157,6 +157,11 @@ cudaError_t launch_advance_clock(pc_clock* clock, double dt, cudaStream_t s) {
 //       stand-in policy: the first of `probes` random targets its column of the PREVIOUS
 //       estimated map shows visible, probed 32 at a time) marks tasked[target]
 //   block 0 thread 0 also latches the step clock (t_cur / step_cur) for the kernels that follow.
+//   Multi-GPU: thread r of block 0 then waits (bounded) until peer r's summaries of the PREVIOUS step
+//   have all arrived in this rank's gathered buffer.  The target propagation runs beside this kernel
+//   and only the per-target stage waits for it, so the exchange of step k overlaps the propagation
+//   of step k + 1 instead of ending step k; it also orders this rank's next push (into the slot of
+//   parity k + 1) behind every peer's reads of that slot.
 struct PreStepArgs {
   double* sens_x;
   const uint8_t* sens_kind;
@@ -177,6 +182,11 @@ struct PreStepArgs {
   int nb_sens;
   int64_t env_targets, env_sensors;  // batch of environments (single catalog: N, M)
   int64_t* task_of;         // may be NULL; [j] = global index of the target sensor j validly tasks, else -1
+  // multi-GPU (peer_world == 0: off): wait here for every peer's push of the PREVIOUS step
+  const uint64_t* peer_table;
+  int peer_world, peer_rank;
+  const unsigned long long* peer_seq;
+  unsigned int* peer_err;
 };
 
 template <bool J2>
@@ -189,26 +199,29 @@ pre_step_kernel(const __grid_constant__ PreStepArgs a) {
       a.clock->step_cur = a.clock->step;
     }
     const int64_t j = (int64_t)blockIdx.x * 128 + threadIdx.x;
-    if (j >= a.M) return;
-    double r[3], v[3];
+    if (j < a.M) {
+      double r[3], v[3];
 #pragma unroll
-    for (int c = 0; c < 3; ++c) {
-      r[c] = a.sens_x[(int64_t)c * a.ld_s + j];
-      v[c] = a.sens_x[(int64_t)(c + 3) * a.ld_s + j];
-    }
-    if (a.sens_kind[j] == PC_KIND_TERRESTRIAL) {
-      rotate_z(r, v, a.cs, a.sn);
-    } else {
-      const int nsub = a.substeps > 0 ? a.substeps : auto_substeps(r, v, a.dt, nullptr);
-      propagate_state<J2>(r, v, a.dt, nsub);
-    }
+      for (int c = 0; c < 3; ++c) {
+        r[c] = a.sens_x[(int64_t)c * a.ld_s + j];
+        v[c] = a.sens_x[(int64_t)(c + 3) * a.ld_s + j];
+      }
+      if (a.sens_kind[j] == PC_KIND_TERRESTRIAL) {
+        rotate_z(r, v, a.cs, a.sn);
+      } else {
+        const int nsub = a.substeps > 0 ? a.substeps : auto_substeps(r, v, a.dt, nullptr);
+        propagate_state<J2>(r, v, a.dt, nsub);
+      }
 #pragma unroll
-    for (int c = 0; c < 3; ++c) {
-      a.sens_x[(int64_t)c * a.ld_s + j] = r[c];
-      a.sens_x[(int64_t)(c + 3) * a.ld_s + j] = v[c];
+      for (int c = 0; c < 3; ++c) {
+        a.sens_x[(int64_t)c * a.ld_s + j] = r[c];
+        a.sens_x[(int64_t)(c + 3) * a.ld_s + j] = v[c];
+      }
+      if (a.sens_q)
+        a.sens_q[j] = make_double4(r[0], r[1], r[2], horizon_q(r[0], r[1], r[2], a.body_radius, a.vis_tol));
     }
-    if (a.sens_q)
-      a.sens_q[j] = make_double4(r[0], r[1], r[2], horizon_q(r[0], r[1], r[2], a.body_radius, a.vis_tol));
+    if (blockIdx.x == 0 && (int)threadIdx.x < a.peer_world)
+      peer_wait_thread(a.peer_table, a.peer_world, a.peer_rank, a.peer_seq, a.peer_err, (int)threadIdx.x);
     return;
   }
   // tasking: sensor j of environment e = j / env_sensors addresses that environment's targets
@@ -249,10 +262,17 @@ cudaError_t launch_pre_step(double* sens_x, const uint8_t* sens_kind, int64_t M,
                             double body_radius, double vis_tol, pc_clock* clock, int64_t* actions,
                             const uint32_t* vis_est, uint8_t* tasked, int64_t N, int64_t wpr,
                             int probes, uint64_t seed, uint64_t step, int64_t env_targets,
-                            int64_t env_sensors, int64_t* task_of, cudaStream_t s) {
-  if (M <= 0 && clock == nullptr) return cudaSuccess;
+                            int64_t env_sensors, int64_t* task_of, const uint64_t* peer_table,
+                            int peer_world, int peer_rank, const unsigned long long* peer_seq,
+                            unsigned int* peer_err, cudaStream_t s) {
+  if (M <= 0 && clock == nullptr && peer_world <= 0) return cudaSuccess;
   PreStepArgs a;
   a.task_of = task_of;
+  a.peer_table = peer_table;
+  a.peer_world = peer_table ? peer_world : 0;
+  a.peer_rank = peer_rank;
+  a.peer_seq = peer_seq;
+  a.peer_err = peer_err;
   a.env_targets = env_targets > 0 ? env_targets : N;
   a.env_sensors = env_sensors > 0 ? env_sensors : M;
   a.sens_x = sens_x;

@@ -62,28 +62,14 @@ cudaError_t launch_propagate_agents(const double* x_in, double* x_out, const uin
 // and every thread then takes the target at its sorted position: warps become homogeneous
 // (at most one mixed warp per count boundary) while all accesses stay inside the CTA's own
 // 128-target window of each component row, so DRAM traffic is unchanged.
-#ifdef PC_COOP_STAMPS   // variant build: kernel entry / exit on the global timer (tools/debug/coop_timeline.py)
-__device__ unsigned long long g_pt[4];
-__device__ unsigned long long g_cta[2048][4];   // per CTA: entry, loads landed (thread 0), exit, max substeps
-__device__ __forceinline__ unsigned long long gtimer_p() {
-  unsigned long long t;
-  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
-  return t;
-}
-#define PC_PROP_STAMP(i, op) do { if ((threadIdx.x & 31) == 0) op(&g_pt[i], gtimer_p()); } while (0)
-extern "C" int pc_debug_prop_ctas(unsigned long long* out) {
-  return (int)cudaMemcpyFromSymbol(out, g_cta, sizeof(g_cta));
-}
-extern "C" int pc_debug_prop_stamps(unsigned long long* out, int reset) {
-  if (out) cudaMemcpyFromSymbol(out, g_pt, sizeof(g_pt));
-  if (reset) {
-    unsigned long long z[4] = {~0ull, 0, ~0ull, 0};
-    cudaMemcpyToSymbol(g_pt, z, sizeof(z));
-  }
-  return 0;
-}
+#ifdef PC_STAMPS_HEADER   // variant builds only (tools/build_variant.sh); the product library has no stamps
+#define PC_STAMPS_PROP
+#include PC_STAMPS_HEADER
 #else
 #define PC_PROP_STAMP(i, op)
+#define PC_PROP_CTA_ENTRY()
+#define PC_PROP_CTA_LOADED(h, r0, v0, ns)
+#define PC_PROP_CTA_EXIT()
 #endif
 constexpr int kPropThreads = 128;
 constexpr int kSortBuckets = 6;  // 0 = no work (past n), 1..4 = that many substeps, 5 = more
@@ -186,10 +172,7 @@ propagate_sigma_kernel(double* __restrict__ sb, int64_t n, int64_t ld, double dt
   // successor, which needs both.
   pdl_trigger();
   PC_PROP_STAMP(0, atomicMin);
-#ifdef PC_COOP_STAMPS
-  const int cta_id = blockIdx.y * gridDim.x + blockIdx.x;
-  if (tid == 0 && cta_id < 2048) { g_cta[cta_id][0] = gtimer_p(); g_cta[cta_id][3] = 0; }
-#endif
+  PC_PROP_CTA_ENTRY();
   if (blockIdx.x == 0 && blockIdx.y == 0 && tid == 0) pdl_wait();
   const int64_t t0 = (int64_t)blockIdx.x * kPropWindow;
   const int i = blockIdx.y;
@@ -310,12 +293,7 @@ propagate_sigma_kernel(double* __restrict__ sb, int64_t n, int64_t ld, double dt
       r[c] = s_x[c][slot[h]];
       v[c] = s_x[c + 3][slot[h]];
     }
-#ifdef PC_COOP_STAMPS
-    if (cta_id < 2048 && h == 0) {
-      if (r[0] + v[0] != 1e300 && tid == 0) g_cta[cta_id][1] = gtimer_p();
-      atomicMax(&g_cta[cta_id][3], (unsigned long long)nsub[0]);
-    }
-#endif
+    PC_PROP_CTA_LOADED(h, r[0], v[0], nsub[0]);
     propagate_state<J2>(r, v, dt, nsub[h]);
 #pragma unroll
     for (int c = 0; c < 3; ++c) {
@@ -324,14 +302,12 @@ propagate_sigma_kernel(double* __restrict__ sb, int64_t n, int64_t ld, double dt
     }
   }
   PC_PROP_STAMP(1, atomicMax);
-#ifdef PC_COOP_STAMPS
-  if (cta_id < 2048) atomicMax(&g_cta[cta_id][2], gtimer_p());
-#endif
+  PC_PROP_CTA_EXIT();
 }
 
 cudaError_t launch_propagate_sigma(double* sb, int64_t n, int64_t ld, int have_truth, double t0,
                                    double tf, int substeps, int force_model, uint32_t* sig_flags,
-                                   bool beside_predecessor, cudaStream_t stream) {
+                                   bool beside_predecessor, int mapping, cudaStream_t stream) {
   if (n <= 0) return cudaSuccess;
   const unsigned blocks = have_truth ? 14 : 13;
   const bool j2 = force_model == PC_FORCE_TWOBODY_J2;
@@ -341,8 +317,8 @@ cudaError_t launch_propagate_sigma(double* sb, int64_t n, int64_t ld, int have_t
   // waves of short CTAs, the second of which frees SM slots one by one, and the per-target kernel
   // launched programmatically behind this one uses exactly that window to bring its update warps'
   // code into the instruction caches (36.5 vs 33.9 us per step at 10^4 targets).
-  static const int force = getenv("PC_PROP_FOLD") ? atoi(getenv("PC_PROP_FOLD")) : 0;   // experiments: 1 / 2
-  const bool fold = force ? force == 2 : n > kFoldMinTargets;
+  // (mapping: pc_option PC_OPT_PROPAGATE_KERNEL -- 1 / 2 pin the choice, 0 = the size rule)
+  const bool fold = mapping ? mapping == 2 : n > kFoldMinTargets;
   if (!fold) {
     const dim3 grid((unsigned)((n + kPropThreads - 1) / kPropThreads), blocks);
     if (j2)

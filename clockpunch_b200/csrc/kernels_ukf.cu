@@ -7,7 +7,7 @@
 // Agent.propagate for the truth state (agents.py:59-71).
 //
 // Mapping -- a staged pipeline, each stage with the thread mapping that suits it (measured:
-// profiles/r1_notes.md; single fused kernels with 16 or 4 lanes per target spent 2/3 of their
+// profiles/README.md; single fused kernels with 16 or 4 lanes per target spent 2/3 of their
 // issue slots on cross-lane scaffolding and thrashed the instruction cache):
 //   sigma_gen_kernel      one THREAD per target: upper Cholesky of est_p, 13 sigma points written
 //                         to the sigma buffer SB (14 blocks of (6, ld) SoA: block 0 = centre =
@@ -43,41 +43,9 @@
 #include "ukf_args.cuh"
 #include "vis.cuh"
 
-// Phase stamps for tools/microbench/finish_phases.cu (no-ops in the library build).
-#ifdef PC_COOP_STAMPS   // tools/build_variant.sh stamps -DPC_COOP_STAMPS: in-pipeline timeline (tools/debug/coop_timeline.py)
-__device__ long long g_cstamp[12][256];
-__device__ unsigned long long g_gt[8];   // globaltimer: [0] min regular entry, [1] max regular exit, [2] min update entry, [3] max update exit
-__device__ __forceinline__ unsigned long long gtimer() {
-  unsigned long long t;
-  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
-  return t;
-}
-#define PC_COOP_CLOCK(i)                                                                     \
-  do {                                                                                       \
-    if ((threadIdx.x & 31) == 0 && blockIdx.x < 256) g_cstamp[i][blockIdx.x] = clock64();    \
-    if ((threadIdx.x & 31) == 0 && (i) == 0) atomicMin(&g_gt[2], gtimer());                  \
-    if ((threadIdx.x & 31) == 0 && (i) == 9) atomicMax(&g_gt[3], gtimer());                  \
-  } while (0)
-__device__ long long g_pstamp[10][2048];   // regular path: per-warp phase stamps (clock64)
-#define PC_PHASE_CLOCK(i)                                                                    \
-  do {                                                                                       \
-    if ((threadIdx.x & 31) == 0 && (i) == 0) atomicMin(&g_gt[0], gtimer());                  \
-    if ((threadIdx.x & 31) == 0 && (i) == 9) atomicMax(&g_gt[1], gtimer());                  \
-    if ((threadIdx.x & 31) == 0) {                                                           \
-      const int wid_ = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;                         \
-      if (wid_ < 2048) g_pstamp[i][wid_] = clock64();                                        \
-    }                                                                                        \
-  } while (0)
-extern "C" int pc_debug_phase_stamps(long long* out) { return (int)cudaMemcpyFromSymbol(out, g_pstamp, sizeof(g_pstamp)); }
-extern "C" int pc_debug_stamps(long long* cst, unsigned long long* gt, int reset) {
-  if (cst) cudaMemcpyFromSymbol(cst, g_cstamp, sizeof(g_cstamp));
-  if (gt) cudaMemcpyFromSymbol(gt, g_gt, sizeof(g_gt));
-  if (reset) {
-    unsigned long long z[8] = {~0ull, 0, ~0ull, 0, ~0ull, 0, ~0ull, 0};
-    cudaMemcpyToSymbol(g_gt, z, sizeof(z));
-  }
-  return 0;
-}
+#ifdef PC_STAMPS_HEADER   // variant builds only (tools/build_variant.sh); the product library has no stamps
+#define PC_STAMPS_UKF
+#include PC_STAMPS_HEADER
 #endif
 #ifndef PC_PHASE_CLOCK
 #define PC_PHASE_CLOCK(i)
@@ -704,20 +672,14 @@ __device__ __forceinline__ void peer_publish(const PeerPush& pp, uint64_t step) 
   }
 }
 
-// One small CTA: hold the stream until every peer has published `step` (bounded spin: a lost peer
-// raises *err instead of hanging the GPU).
+// One small CTA: hold the stream until every peer has published this rank's current push number
+// (bounded spin: a lost peer raises *err instead of hanging the GPU).  The step itself does this wait
+// inside the NEXT step's sensor kernel (peer_wait_thread, pc_common.cuh); this is the stand-alone form
+// for callers that read the gathered buffer from the host (pc_peer_wait, pc_allgather_step).
 __global__ void peer_wait_kernel(const uint64_t* __restrict__ table, int world, int rank,
                                  const unsigned long long* __restrict__ seq, unsigned int* __restrict__ err) {
   pdl_wait();
-  const int r = threadIdx.x;
-  if (r >= world) return;
-  const uint64_t want = *reinterpret_cast<const volatile unsigned long long*>(seq);   // pushes completed, this one included
-  const volatile uint64_t* flag = reinterpret_cast<const volatile uint64_t*>(__ldg(table + world + rank)) + r;
-  for (int spin = 0; spin < (1 << 22); ++spin) {
-    if (*flag >= want) return;
-    __nanosleep(100);
-  }
-  atomicOr(err, 1u << r);
+  if ((int)threadIdx.x < world) peer_wait_thread(table, world, rank, seq, err, (int)threadIdx.x);
 }
 
 // Alternative to storing from the per-target kernel: one grid copies the finished local summary
@@ -735,18 +697,19 @@ peer_push_kernel(const uint4* __restrict__ src, int64_t n16, PeerPush pp) {
   peer_publish(pp, step_done);
 }
 
-cudaError_t launch_peer_push(const void* summary, int64_t bytes, const PeerPush& pp, cudaStream_t stream) {
+cudaError_t launch_peer_push(const void* summary, int64_t bytes, const PeerPush& pp, bool programmatic,
+                             cudaStream_t stream) {
   const int64_t n16 = bytes / 16;
   int blocks = (int)((n16 + 255) / 256);
   if (blocks > 296) blocks = 296;
   if (blocks < 1) blocks = 1;
-  return launch_pdl(peer_push_kernel, dim3(blocks), dim3(256), 0, stream, true,
+  return launch_pdl(peer_push_kernel, dim3(blocks), dim3(256), 0, stream, programmatic,
                     reinterpret_cast<const uint4*>(summary), n16, pp);
 }
 
 cudaError_t launch_peer_wait(const uint64_t* table, int world, int rank, const unsigned long long* seq,
-                             unsigned int* err, cudaStream_t stream) {
-  return launch_pdl(peer_wait_kernel, dim3(1), dim3(64), 0, stream, true, table, world, rank, seq, err);
+                             unsigned int* err, bool programmatic, cudaStream_t stream) {
+  return launch_pdl(peer_wait_kernel, dim3(1), dim3(64), 0, stream, programmatic, table, world, rank, seq, err);
 }
 
 // Stage 3 of the step, one THREAD per target: unscented transform, measurement update, outputs,
@@ -1770,18 +1733,26 @@ static cudaError_t launch_finish_tpb(const UkfArgs& a, cudaStream_t stream) {
 
 // Small catalogs cannot fill the machine with one thread per target: they take the quad kernel
 // (four lanes per target); large ones get one thread per target with 64- or 128-thread CTAs
-// (sensor tile amortised over more warps).
+// (sensor tile amortised over more warps).  `variant` (pc_option PC_OPT_FINISH_KERNEL) pins the choice:
+// 1 quad + update warps (when task_of is given), 2 quad with the in-line update, 3 / 4 one thread per
+// target with 64- / 128-thread CTAs; 0 = the size rule.
+static int finish_mapping(int64_t n, int variant) {
+  if (variant >= 1 && variant <= 4) return variant;
+  if (n <= kQuadMaxTargets) return 1;
+  return n <= 128 * 1024 ? 3 : 4;
+}
+
 // Does launch_ukf_finish take the update-warp kernel (the only one that fills the host mirrors)?
-bool finish_fills_host_mirrors(int64_t n, int64_t sensors) {
-  return getenv("PC_NO_COOP") == nullptr && n > 0 && n <= kQuadMaxTargets && sensors > 0 && sensors <= kCoopMaxSensors;
+bool finish_fills_host_mirrors(int64_t n, int64_t sensors, int variant) {
+  return n > 0 && finish_mapping(n, variant) == 1 && sensors > 0 && sensors <= kCoopMaxSensors;
 }
 
 cudaError_t launch_ukf_finish(const UkfArgs& a, cudaStream_t stream) {
   if (a.n <= 0) return cudaSuccess;
-  if (a.n <= kQuadMaxTargets) {
+  const int mapping = finish_mapping(a.n, a.variant);
+  if (mapping <= 2) {
     const unsigned ctas = (unsigned)((4 * a.n + kQuadThreads - 1) / kQuadThreads);
-    static const bool no_coop = getenv("PC_NO_COOP") != nullptr;   // experiments: in-line update everywhere
-    if (!no_coop && a.task_of && a.task_sensors > 0 && a.task_sensors <= kCoopMaxSensors) {
+    if (mapping == 1 && a.task_of && a.task_sensors > 0 && a.task_sensors <= kCoopMaxSensors) {
       const unsigned upd = (unsigned)a.task_sensors;   // one update CTA per sensor
       if (a.h_cov || a.h_vis_est || a.h_tr_pos)
         return launch_pdl(ukf_finish_quad_kernel<true, true>, dim3(upd + ctas), dim3(kQuadThreads), 0, stream, true, a);
@@ -1789,7 +1760,7 @@ cudaError_t launch_ukf_finish(const UkfArgs& a, cudaStream_t stream) {
     }
     return launch_pdl(ukf_finish_quad_kernel<false, false>, dim3(ctas), dim3(kQuadThreads), 0, stream, true, a);
   }
-  if (a.n <= 128 * 1024) return launch_finish_tpb<64>(a, stream);
+  if (mapping == 3) return launch_finish_tpb<64>(a, stream);
   return launch_finish_tpb<128>(a, stream);
 }
 

@@ -10,7 +10,9 @@ namespace pc {
 // NVLink (peer-mapped symmetric memory), instead of into a local buffer that a collective then
 // ships.  Layout of a gathered buffer: [step parity][rank][slot_bytes], a slot being a copy of the
 // shard's summary buffer.  The last CTA of the grid publishes the step number in every peer's flag
-// array; peer_wait_kernel then holds the stream until all peers' flags have arrived.
+// array.  Nobody waits at the end of the step: the sensor kernel of the NEXT step waits (bounded) for
+// every peer's flag of this push, beside the target propagation (the gathered summaries are only
+// consumed by the next step's scheduler); peer_wait_kernel is the stand-alone form of that wait.
 struct PeerPush {
   int world, rank;             // world == 0: disabled
   const uint64_t* table;       // device array: [0, world) gathered bases, [world, 2 world) flag bases
@@ -68,6 +70,7 @@ struct UkfArgs {
   float* h_tr_vel;
   float* h_ltt;
   PeerPush pp;
+  int variant;             // pc_option PC_OPT_FINISH_KERNEL (0 = choose by catalog size)
   pc_ukf_params p;
 };
 
@@ -76,11 +79,12 @@ cudaError_t launch_sigma_gen(const double* est_x, const double* est_p, const dou
                              cudaStream_t stream);
 cudaError_t launch_propagate_sigma(double* sb, int64_t n, int64_t ld, int have_truth, double t0,
                                    double tf, int substeps, int force_model, uint32_t* sig_flags,
-                                   bool beside_predecessor, cudaStream_t stream);
+                                   bool beside_predecessor, int mapping, cudaStream_t stream);
 cudaError_t launch_ukf_finish(const UkfArgs& a, cudaStream_t stream);
-bool finish_fills_host_mirrors(int64_t n, int64_t sensors);
-cudaError_t launch_peer_push(const void* summary, int64_t bytes, const PeerPush& pp, cudaStream_t stream);
+bool finish_fills_host_mirrors(int64_t n, int64_t sensors, int variant);
+cudaError_t launch_peer_push(const void* summary, int64_t bytes, const PeerPush& pp, bool programmatic,
+                             cudaStream_t stream);
 cudaError_t launch_peer_wait(const uint64_t* table, int world, int rank, const unsigned long long* seq,
-                             unsigned int* err, cudaStream_t stream);
+                             unsigned int* err, bool programmatic, cudaStream_t stream);
 
 }  // namespace pc

@@ -51,6 +51,10 @@ class CatalogEngine:
         self.wpr = max(1, (self.Me + 31) // 32)
         self.time = float(time)
         self.step_count = 0
+        # counter of the measurement / stand-in-policy random streams (Philox and splitmix are keyed by
+        # (seed, rng_step, target)).  It keeps running across reset(): the reference draws from numpy's
+        # global RNG (agents.py:173-183), which does not rewind between episodes either.
+        self.rng_step = 0
         self.substeps, self.force_model, self.seed = int(substeps), int(force_model), int(seed)
         self.body_radius, self.vis_tol = float(body_radius), float(vis_tol)
         self.params = _lib.make_ukf_params(Q, R, alpha, beta, kappa)
@@ -106,6 +110,10 @@ class CatalogEngine:
         self._hs_key = None
         self._peer = None
         self._hs_io = _lib.StepIO()
+        # work enqueued on torch's stream since the last step_host (which runs on the library's own
+        # stream when torch's is the legacy default stream, see _order_streams)
+        self._torch_stream_dirty = True
+        self._tasked_dirty = False     # self.tasked holds a caller's mask (steps with actions need it zeroed)
         self._sync_clock()
         self.compute_vis()
         self.snapshot()
@@ -136,8 +144,25 @@ class CatalogEngine:
 
     def _sync_clock(self):
         rec = np.zeros(1, dtype=[("t", "<f8"), ("s", "<u8"), ("tc", "<f8"), ("sc", "<u8")])
-        rec["t"], rec["s"] = self.time, self.step_count
+        rec["t"], rec["s"] = self.time, self.rng_step
         self.clock.copy_(self.torch.from_numpy(rec.view(np.uint8).copy()))
+        self._torch_stream_dirty = True
+
+    def _zero_tasked(self):
+        self.tasked.zero_()
+        self._tasked_dirty = False
+        self._torch_stream_dirty = True
+
+    def _order_streams(self):
+        """pc_step_host captures and replays its graph on the library's own (non-blocking) stream when
+        torch's current stream is the legacy default stream, which cannot be captured; that stream is
+        not ordered against torch's.  Everything else the engine does (reset, step, sigma generation,
+        clock writes, observation packs) is enqueued on torch's stream, so the first step_host after any
+        of it waits for that work (a host-side wait, paid only on such transitions); step_host itself
+        returns only when its stream is idle, so nothing is needed in the other direction."""
+        if self._torch_stream_dirty:
+            self.torch.cuda.current_stream(self.dev).synchronize()
+            self._torch_stream_dirty = False
 
     def _fill_args(self, t0, tf, z, tasked, want_vis=True, use_clock=False, actions=None, policy_probes=0,
                    policy_seed=0):
@@ -149,7 +174,7 @@ class CatalogEngine:
         a.tasked = None if tasked is None else tasked.data_ptr()
         a.N, a.ld, a.t0, a.tf = self.N, self.ld, float(t0), float(tf)
         a.substeps, a.force_model = self.substeps, self.force_model
-        a.rng_seed, a.rng_step = self.seed, self.step_count
+        a.rng_seed, a.rng_step = self.seed, self.rng_step
         a.pred_p, a.nis, a.flags = self.pred_p.data_ptr(), self.nis.data_ptr(), self.flags.data_ptr()
         a.vis_truth = self.vis_truth.data_ptr() if want_vis else None
         a.vis_est = self.vis_est.data_ptr() if want_vis else None
@@ -164,7 +189,7 @@ class CatalogEngine:
         a.task_of = self.task_of.data_ptr()
         a.env_targets, a.env_sensors = (self.Ne, self.Me) if self.E > 1 else (0, 0)
         if self._peer is not None:
-            a.peer_table, a.peer_world, a.peer_rank = self._peer["table"].data_ptr(), self._peer["world"], self._peer["rank"]
+            a.peer_table, a.peer_world, a.peer_rank = self._peer["table"], self._peer["world"], self._peer["rank"]
             a.summary_base, a.summary_bytes = self.summary.data_ptr(), self.summary.numel()
         else:
             a.peer_table, a.peer_world, a.peer_rank, a.summary_base, a.summary_bytes = None, 0, 0, None, 0
@@ -175,6 +200,7 @@ class CatalogEngine:
     def compute_vis(self):
         """Both packed maps from the current states (reset path, env.py:212)."""
         c = self.ctx
+        self._torch_stream_dirty = True
         if self.E > 1:
             c.check(c.lib.pc_vismap_packed_envs(c.handle, self.sens_x.data_ptr(), self.ld_s, self.truth_x.data_ptr(),
                                                 self.est_x.data_ptr(), self.ld, self.E, self.Me, self.Ne,
@@ -194,6 +220,7 @@ class CatalogEngine:
                                          non_blocking=True)
             actions = self.actions
         c = self.ctx
+        self._torch_stream_dirty, self._tasked_dirty = True, True
         c.check(c.lib.pc_task_from_actions(c.handle, actions.data_ptr(), self.M, self.vis_est.data_ptr(),
                                            self.N, self.wpr, self.tasked.data_ptr(), self._stream()))
         return self.tasked
@@ -209,11 +236,16 @@ class CatalogEngine:
             if not hasattr(actions, "data_ptr"):
                 self.actions[: self.M].copy_(self.torch.from_numpy(np.ascontiguousarray(actions, dtype=np.int64)))
                 actions = self.actions
-            self.tasked.zero_()
+            self._zero_tasked()
             tasked = self.tasked
-        if tasked is not None and not hasattr(tasked, "data_ptr"):
-            self.tasked.copy_(self.torch.from_numpy(np.ascontiguousarray(tasked, dtype=np.uint8)))
-            tasked = self.tasked
+        elif tasked is not None:
+            if not hasattr(tasked, "data_ptr"):
+                self.tasked.copy_(self.torch.from_numpy(np.ascontiguousarray(tasked, dtype=np.uint8)))
+                tasked = self.tasked
+            # a caller's mask is left in place by the step: steps that build the mask from actions must
+            # start from zeros (their update warps own exactly the targets pc_step_args.task_of names)
+            self._tasked_dirty = self._tasked_dirty or tasked is self.tasked
+        self._torch_stream_dirty = True
         if z is not None and not hasattr(z, "data_ptr"):
             self.z[:, : self.N].copy_(self.torch.from_numpy(np.ascontiguousarray(z, dtype=np.float64)))
             z = self.z
@@ -223,6 +255,7 @@ class CatalogEngine:
         self._sigma_valid = True
         self.time = float(t_next)
         self.step_count += 1
+        self.rng_step += 1
         if self._graph is not None or self._hs_dt is not None:
             self._sync_clock()
 
@@ -233,7 +266,7 @@ class CatalogEngine:
         policy_probes > 0 -- masked by the previous estimated vis map, sensors, truth + UKF, both
         vis maps) [+ obs pack] into one CUDA graph.  Times and RNG counters come from the device
         clock, so replay() needs no argument updates.  Measurements are drawn on device."""
-        self.tasked.zero_()
+        self._zero_tasked()
         torch, c = self.torch, self.ctx
         self._sync_clock()
         self.ensure_sigma()
@@ -261,43 +294,58 @@ class CatalogEngine:
         pass: plain cudaEventRecord calls around one kernel measure it without the latency of the
         event-record NODES a captured graph needs."""
         self.ensure_sigma()
+        if self._tasked_dirty:
+            self._zero_tasked()
         if self._hs_dt is None and self._graph is None:
-            self.tasked.zero_()
             self._sync_clock()
             self._hs_dt = float(dt)
         a = self._fill_args(0.0, float(dt), None, self.tasked, use_clock=True, actions=self.actions,
                             policy_probes=policy_probes, policy_seed=policy_seed)
         c = self.ctx
+        self._torch_stream_dirty = True
         c.check(c.lib.pc_step_fused(c.handle, C.byref(a), C.byref(self.params), self._stream()))
         self.time += float(dt)
         self.step_count += 1
+        self.rng_step += 1
 
     # -- multi-GPU: summaries pushed into every peer's gathered buffer by the step itself ----------
     def enable_peer_push(self, group=None):
-        """Allocate peer-mapped (symmetric-memory) gathered buffers on every rank of `group` and make
-        every following step store its per-target summaries straight into all of them (NVLink
-        stores from the per-target kernel + a flag per rank), replacing the per-step all-gather.
-        All ranks must call this together, with equal shard sizes.  Returns the local gathered
-        tensor, shape (2, world, summary_bytes) uint8: [step parity][source rank]."""
+        """Set up the peer exchange of the step (pc_comm_init / pc_comm_attach: every rank allocates its
+        gathered buffer, the 64-byte CUDA IPC handles are all-gathered through `group`, every rank maps
+        every peer's buffer over NVLink) and make every following step push its per-target summaries
+        straight into all of them, replacing the per-step all-gather.  All ranks must call this
+        together, with equal shard sizes.  torch.distributed is only the transport of the handles;
+        a non-torch caller does the same three C calls with its own transport.
+        Returns the local gathered tensor, shape (2, world, summary_bytes) uint8: [step parity][source rank]."""
         import torch.distributed as dist
-        import torch.distributed._symmetric_memory as symm
-        torch = self.torch
+        torch, c = self.torch, self.ctx
         group = group or dist.group.WORLD
         world, rank = dist.get_world_size(group), dist.get_rank(group)
-        gathered = symm.empty((2, world, self.summary.numel()), dtype=torch.uint8, device=self.dev)
-        flags = symm.empty((world,), dtype=torch.int64, device=self.dev)
-        gathered.zero_()
-        flags.zero_()
-        hg = symm.rendezvous(gathered, group)
-        hf = symm.rendezvous(flags, group)
-        ptrs = [int(p) for p in hg.buffer_ptrs] + [int(p) for p in hf.buffer_ptrs]
-        table = torch.tensor(np.array(ptrs, dtype=np.uint64).view(np.int64), dtype=torch.int64, device=self.dev)
+        nbytes = self.summary.numel()
+        mine = np.zeros(_lib.COMM_HANDLE_BYTES, np.uint8)
+        c.check(c.lib.pc_comm_init(c.handle, world, rank, nbytes, mine.ctypes.data))
+        on_gpu = dist.get_backend(group) == "nccl"
+        send = torch.from_numpy(mine).to(self.dev) if on_gpu else torch.from_numpy(mine)
+        recv = torch.empty((world, _lib.COMM_HANDLE_BYTES), dtype=torch.uint8, device=send.device)
+        dist.all_gather_into_tensor(recv, send, group=group)
+        handles = np.ascontiguousarray(recv.cpu().numpy())
+        c.check(c.lib.pc_comm_attach(c.handle, handles.ctypes.data))
+        table, gathered = C.c_void_p(), C.c_void_p()
+        c.check(c.lib.pc_comm_table(c.handle, C.byref(table), C.byref(gathered), None, None, None))
+        view = B.device_view(gathered.value, 2 * world * nbytes, self.dev).view(2, world, nbytes)
         torch.cuda.synchronize(self.dev)
-        dist.barrier(group)
-        self._peer = {"table": table, "world": world, "rank": rank, "gathered": gathered, "flags": flags,
-                      "handles": (hg, hf)}
+        dist.barrier(group)              # everybody attached before anybody's first push
+        self._peer = {"table": table.value, "world": world, "rank": rank, "gathered": view}
         self._hs_key = None
-        return gathered
+        return view
+
+    def peer_sync(self):
+        """Enqueue the wait for every peer's latest push on torch's stream: what follows on the stream
+        (or the host, after a synchronise) may read `gathered` of the latest parity.  Steps do not end
+        with this wait -- the NEXT step's sensor kernel waits, beside its propagation."""
+        p, c = self._peer, self.ctx
+        self._torch_stream_dirty = True
+        c.check(c.lib.pc_peer_wait(c.handle, p["table"], p["world"], p["rank"], self._stream()))
 
     def peer_fields(self, parity: int, src_rank: int) -> dict:
         """Typed views of what `src_rank` pushed for steps of the given parity."""
@@ -305,8 +353,10 @@ class CatalogEngine:
 
     def peer_status(self) -> tuple[int, int]:
         """(error mask: bit r = peer r's flag never arrived within the bounded wait; pushes done so
-        far -- its parity is the slot of `gathered` holding the latest step).  Synchronises."""
+        far -- its parity is the slot of `gathered` holding the latest step).  Waits for the peers'
+        latest push and synchronises."""
         err, n = C.c_uint32(0), C.c_uint64(0)
+        self.peer_sync()
         self.torch.cuda.synchronize(self.dev)
         self.ctx.check(self.ctx.lib.pc_peer_status(self.ctx.handle, C.byref(err), C.byref(n)))
         return err.value, n.value
@@ -315,6 +365,7 @@ class CatalogEngine:
         """(Re)generate sigma-point blocks 1..12 from the current (est_x, est_p) if stale."""
         if not self._sigma_valid:
             c = self.ctx
+            self._torch_stream_dirty = True
             c.check(c.lib.pc_sigma_points(c.handle, self.est_x.data_ptr(), self.est_p.data_ptr(), self.N,
                                           self.ld, self.params.gamma, self.sigma.data_ptr(),
                                           self.sig_flags.data_ptr(), self._stream()))
@@ -329,9 +380,13 @@ class CatalogEngine:
         graph contains the stand-in policy)."""
         g = graph or self._graph
         self.ensure_sigma()
+        if self._tasked_dirty:
+            self._zero_tasked()
+        self._torch_stream_dirty = True
         g.replay()
         self.time += g.pc_dt
         self.step_count += 1
+        self.rng_step += 1
 
     # -- the reference-facing step: host actions in, host observation out ------------------
     def host_buffers(self, pinned: bool = True):
@@ -357,10 +412,8 @@ class CatalogEngine:
             # (re)build the argument blocks once; steady-state steps below are one C call
             self.ensure_sigma()
             if self._hs_dt != dt:
-                self.tasked.zero_()
                 self._sync_clock()
                 self._hs_dt = dt
-                self.torch.cuda.current_stream(self.dev).synchronize()
             self._fill_args(0.0, float(dt), None, self.tasked, use_clock=True, actions=self.actions,
                             policy_probes=policy_probes, policy_seed=policy_seed)
             io = self._hs_io
@@ -377,16 +430,22 @@ class CatalogEngine:
             self._hs_call = (self.ctx.lib.pc_step_host, self.ctx.handle, C.byref(self._args), C.byref(self.params),
                              C.byref(io), self._stream())
             self._hs_key = (float(dt), int(policy_probes), int(policy_seed), id(hb), True, bool(zero_copy))
+        if self._tasked_dirty:
+            self._zero_tasked()
+        if self._torch_stream_dirty:
+            self._order_streams()
         f, *cargs = self._hs_call
         rc = f(*cargs)
         if rc:
             self.ctx.check(rc)
         self.time += float(dt)
         self.step_count += 1
+        self.rng_step += 1
 
     def pack_obs(self, use_clock: bool = False):
         """float32 eci_state / est_cov / obs_staleness into self.obs_f32 (device)."""
         c = self.ctx
+        self._torch_stream_dirty = True
         n0, n1, _ = self._obs_sizes
         base = self.obs_f32.data_ptr()
         if self.E > 1:
@@ -408,12 +467,25 @@ class CatalogEngine:
     def snapshot(self):
         self._snapshot = ({k: getattr(self, k).clone() for k in self._STATE}, self.time, self.step_count,
                           self._sigma_valid)
+        self._snapshot_rng_step = self.rng_step
 
-    def reset(self):
+    def reset(self, seed: int | None = None, rewind_rng: bool = False):
+        """Back to the snapshot (env.py:208).  The random streams of the measurement noise and of the
+        stand-in policy keep running -- a new episode sees new noise, as with the reference's global numpy
+        RNG -- unless a new `seed` is given (the streams then restart under it) or `rewind_rng` asks for
+        a bit-identical replay of the snapshot's episode."""
+        if seed is not None and int(seed) != self.seed and self._graph is not None:
+            raise ValueError("the seed is part of the captured step: drop the graph (build_graph again) to reseed")
         bufs, t, sc, sv = self._snapshot
         for k, v in bufs.items():
             getattr(self, k).copy_(v)
         self.time, self.step_count, self._sigma_valid = t, sc, sv
+        if seed is not None:
+            self.seed, self.rng_step = int(seed), 0
+            self._hs_key = None          # the seed is part of the cached argument block
+        elif rewind_rng:
+            self.rng_step = self._snapshot_rng_step
+        self._zero_tasked()
         self._sync_clock()
 
     def clone(self) -> "CatalogEngine":

@@ -81,6 +81,20 @@ const char* pc_last_error(pc_ctx* ctx);
 /* number of kernels this ctx has launched since creation (bench.py: gpu_launches) */
 int64_t pc_launch_count(pc_ctx* ctx);
 
+/* Kernel-mapping overrides.  The library picks the thread mapping of two kernels from the catalog size;
+ * tests (cross-kernel parity at sizes the oracle can follow) and tuning runs can pin the choice per
+ * context.  Every mapping evaluates the same equations; value 0 restores the size rule.
+ *   PC_OPT_FINISH_KERNEL     per-target stage (transform + update + next sigma points + vis rows):
+ *       1 four lanes per target, measurement updates by dedicated warps when pc_step_args.task_of is given
+ *       2 four lanes per target, update in line
+ *       3 one thread per target, 64-thread CTAs      4 one thread per target, 128-thread CTAs
+ *   PC_OPT_PROPAGATE_KERNEL  sigma-point propagation: 1 one state per thread, 2 two states per thread
+ *       out of a sorted 256-target window
+ *   PC_OPT_PEER_PUSH         multi-GPU exchange: 1 stores from the per-target kernel, 2 copy kernel behind it */
+enum pc_option { PC_OPT_FINISH_KERNEL = 1, PC_OPT_PROPAGATE_KERNEL = 2, PC_OPT_PEER_PUSH = 3 };
+int pc_set_option(pc_ctx* ctx, int option, int value);
+int pc_get_option(pc_ctx* ctx, int option, int* value);
+
 /* ---- K1: propagation -------------------------------------------------
  * pc_propagate_twobody   replaces SatDynamicsModel.propagate / simplePropagate(satelliteDynamics)
  *                        (dynamics_classes.py:51-76, propagator.py:12-81, dynamics.py:16-40,71-86)
@@ -312,10 +326,16 @@ typedef struct pc_step_args {
    * summary_bytes describe the local buffer that contains num_tasked, vis_est, tr_pos, tr_vel and
    * last_time_tasked (all five must point into it).  With peer_table != NULL the per-target kernel
    * stores every summary value into the slot of this rank in EVERY peer's gathered buffer as it
-   * produces it, its last CTA publishes the step number in every peer's flag array, and the step ends
-   * with a kernel that waits (bounded) until all peers' flags for this step have arrived: no
-   * collective call.  pc_peer_status reports (and clears) a bit per peer whose flag never came, and the
-   * number of pushes done so far (its parity is the slot that holds the latest data). */
+   * produces it (or, for shards above 32768 targets and with 8 or more peers, a copy kernel behind it
+   * streams the finished summary buffer), and its last CTA publishes the push number in every peer's
+   * flag array: no collective call.  The gathered summaries of step k are only needed by the
+   * scheduler of step k + 1, so nothing waits for the peers at the end of step k: the wait (bounded)
+   * for every peer's push k sits in the SENSOR kernel of step k + 1, beside the target propagation,
+   * which also keeps any rank from overwriting a parity slot a slower peer may still read.  A caller
+   * that reads the gathered buffer on the host enqueues pc_peer_wait first.  pc_peer_status reports
+   * (and clears) a bit per peer whose flag never came, and the number of pushes done so far (its
+   * parity is the slot that holds the latest data).  All ranks must step in lockstep (same number
+   * of pc_step_fused calls). */
   const uint64_t* peer_table;
   int32_t peer_world, peer_rank;
   const void* summary_base;
@@ -345,6 +365,30 @@ typedef struct pc_step_args {
 int pc_step_fused(pc_ctx* ctx, const pc_step_args* args, const pc_ukf_params* params,
                   pc_stream stream);
 int pc_peer_status(pc_ctx* ctx, uint32_t* out_error_mask, uint64_t* out_pushes);
+/* Enqueue the (bounded) wait for every peer's latest push on `stream`; what follows on the stream
+ * may read the gathered buffer.  table / world / rank as in pc_step_args. */
+int pc_peer_wait(pc_ctx* ctx, const uint64_t* peer_table, int32_t peer_world, int32_t peer_rank,
+                 pc_stream stream);
+
+/* ---- peer exchange set-up without any framework (pc_comm_init / pc_allgather_step) --
+ * One process per GPU on one node.  pc_comm_init allocates this rank's gathered buffer
+ * [2][world][summary_bytes] and flag array on the context's device and returns a 64-byte handle
+ * (CUDA IPC) for it.  The caller gathers the handles of all ranks with whatever transport it has
+ * (MPI, files, torch.distributed, ...) -- the exchange is also the barrier that orders every rank's
+ * allocation before anybody's first push -- and hands the world x 64 bytes to pc_comm_attach,
+ * which maps every peer's buffer over NVLink and builds the device table.  pc_comm_table then
+ * yields what pc_step_args.peer_table / peer_world / peer_rank expect, and the local gathered
+ * buffer.  pc_allgather_step pushes an arbitrary summary buffer (summary_bytes of it, 16-byte
+ * aligned) into every peer and waits for all peers' pushes: the stand-alone form of what the step
+ * does in-kernel.  pc_comm_destroy unmaps and frees (no peer may still be pushing). */
+#define PC_COMM_HANDLE_BYTES 64
+int pc_comm_init(pc_ctx* ctx, int32_t world, int32_t rank, int64_t summary_bytes,
+                 uint8_t handle_out[PC_COMM_HANDLE_BYTES]);
+int pc_comm_attach(pc_ctx* ctx, const uint8_t* all_handles /* world x PC_COMM_HANDLE_BYTES */);
+int pc_comm_table(pc_ctx* ctx, const uint64_t** out_table, void** out_gathered, int32_t* out_world,
+                  int32_t* out_rank, int64_t* out_summary_bytes);
+int pc_allgather_step(pc_ctx* ctx, const void* summary, pc_stream stream);
+int pc_comm_destroy(pc_ctx* ctx);
 
 /* ---- the step as the reference's caller sees it: host actions in, host observation out -------
  * Replaces one SSAScheduler.step(action) (env.py:533-597) for the whole catalog: copies the M

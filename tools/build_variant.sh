@@ -1,6 +1,8 @@
 #!/bin/bash
 # Build a variant of the library with extra -D flags on kernels_ukf.cu (experiments):
-#   tools/build_variant.sh stamps -DPC_COOP_STAMPS   ->  variants/libpunch_stamps.so   (use with PUNCH_B200_LIB=...)
+#   tools/build_variant.sh stamps -DPC_STAMPS_HEADER='"../../tools/debug/stamps.cuh"'
+#       ->  variants/libpunch_stamps.so   (use with PUNCH_B200_LIB=...; phase stamps of tools/debug/stamps.cuh,
+#           which the product library never includes)
 set -e
 cd "$(dirname "$0")/.."
 name=$1; shift

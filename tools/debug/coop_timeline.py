@@ -1,5 +1,5 @@
-"""In-pipeline timeline of the per-target kernel (variant library built with -DPC_COOP_STAMPS):
-   tools/build_variant.sh stamps -DPC_COOP_STAMPS
+"""In-pipeline timeline of the per-target kernel (variant library built with -DPC_STAMPS_HEADER):
+   tools/build_variant.sh stamps -DPC_STAMPS_HEADER
    PUNCH_B200_LIB=$PWD/variants/libpunch_stamps.so python tools/debug/coop_timeline.py"""
 import sys, os, ctypes as C
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
