@@ -29,19 +29,20 @@ def propagate_batch(x0: ndarray, t0: float, tf: float, kind=None, substeps: int 
 def simplePropagate(func: Callable, x0: ndarray, t0: float, tf: float) -> ndarray:
     """Propagate (N,) | (N,M) state(s) from t0 to tf; returns the input's (squeezed) shape.
 
-    ``func`` must be the built-in two-body ``satelliteDynamics``: that is the path the
-    CUDA propagator implements (fixed-step DOP853, see csrc/propagate.cuh).  Arbitrary
-    Python right-hand sides are outside this package's scope and are rejected loudly
-    rather than integrated on the CPU.
+    The built-in two-body ``satelliteDynamics`` is the path the CUDA propagator implements
+    (fixed-step DOP853, see csrc/propagate.cuh).  An arbitrary Python right-hand side
+    (tests/dynamics/test_propagator.py:10-68 integrates a toy linear ODE) is a Python callback
+    per RHS evaluation, i.e. host work by nature: it is handed to the reference's own
+    simplePropagate when the reference tree is available (clockpunch_b200._reference), and
+    raises NotImplementedError otherwise.  The two-body path has no CPU fallback.
 
     Raises ValueError if t0 == tf (propagator.py:40-41).
     """
     if t0 == tf:
         raise ValueError("Woah buddy, t0 and tf are equal.")
     if func is not satelliteDynamics:
-        raise NotImplementedError(
-            "clockpunch_b200.simplePropagate only accelerates the reference's satelliteDynamics; "
-            "custom dynamics functions have no GPU path (and there is no CPU fallback).")
+        from .. import _reference
+        return _reference.load("dynamics.propagator").simplePropagate(func, x0, t0, tf)
     x0 = np.asarray(x0, dtype=np.float64).squeeze()
     if x0.shape[0] != 6:
         raise ValueError("state vectors must have 6 components")

@@ -15,9 +15,13 @@ and 2 N M Python pair tests.
 reads the list after a step.  gymnasium is optional: when importable the class is a
 ``gymnasium.Env`` with the reference's spaces, otherwise a plain class with the same methods.
 
-Measurement noise: the reference draws from numpy's legacy global RNG (agents.py:181); here it
-is drawn on device (Philox, seeded).  ``step(action, measurements=z)`` injects a (6, N) array
-instead -- that is how tests/test_env.py replays rollouts of the live reference.
+Measurement noise: the reference draws from numpy's legacy global RNG (agents.py:181), which is
+never reseeded by the env: every episode and every worker process sees different noise.  Here it
+is drawn on device (Philox keyed by (seed, step counter, target)); the step counter keeps running
+across ``reset()`` (also the horizon reset inside ``step``), ``seed=None`` (default) takes a fresh
+seed per env instance from the OS, and ``reset(seed=s)`` restarts the stream under ``s`` (the
+Gymnasium convention).  ``step(action, measurements=z)`` injects a (6, N) array instead -- that is
+how tests/test_env.py replays rollouts of the live reference.
 """
 from __future__ import annotations
 
@@ -33,6 +37,7 @@ from ..common.metrics import TaskingMetricTracker
 from ..common.visibility import unpack_vis_words
 from ..dynamics.dynamics_classes import StaticTerrestrial
 from ..engine import CatalogEngine
+from .env_parameters import SSASchedulerParams  # noqa: F401  (ray/build_env.py:24 imports it from this module)
 from .env_utils import buildAgentInfoMap
 
 try:  # gymnasium is not part of this image; the env does not need it to run
@@ -59,10 +64,18 @@ class _Space:
         return rng.normal(size=self.shape).astype(self.dtype)
 
 
+def fresh_seed() -> int:
+    """63 bits from the OS: distinct per env instance and per (Ray) worker process."""
+    import os
+    return int.from_bytes(os.urandom(8), "little") >> 1
+
+
 class SSAScheduler(_EnvBase):
     metadata = {"render_modes": [None]}
 
-    def __init__(self, scenario_params, device: int | None = None, seed: int = 0):
+    def __init__(self, scenario_params, device: int | None = None, seed: int | None = None):
+        if seed is None:
+            seed = fresh_seed()
         self.time_step = scenario_params.time_step
         self.horizon = scenario_params.horizon
         self._agents = deepcopy(list(scenario_params.agents))
@@ -152,7 +165,7 @@ class SSAScheduler(_EnvBase):
         self.info["time_now"] = 0.0
         self.info["num_tasked"] = np.zeros(self.num_targets, dtype=int).tolist()
         self._copy_tracker_to_info()
-        self._engine.reset()
+        self._engine.reset(seed=seed)
         self._agents = deepcopy(list(self.reset_params.agents))
         self._agents_stale = False
         self._engine.pack_obs()

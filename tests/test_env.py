@@ -73,10 +73,13 @@ def test_saturate_coes_and_partition_free_functions():
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("kind", ["test_env", "default"])
+@pytest.mark.parametrize("kind", ["test_env", "default", "seam"])
 def test_env_rollout_matches_live_reference(golden, kind):
+    """Rollouts of the LIVE reference env replayed on the GPU env with the same actions and injected
+    measurements.  "seam" is the base env underneath the wrapper stack of tests/test_seam.py (built by the
+    reference's buildEnv from the gen_config_env.py configuration, tests/golden/make_golden_seam.py)."""
     from clockpunch_b200.environment.env import SSAScheduler
-    g = golden("env")
+    g = golden("seam" if kind == "seam" else "env")
     dt = float(g[f"{kind}_dt"])
     acts, Z = g[f"{kind}_action"], g[f"{kind}_z"]
     env = SSAScheduler(_Params(dt, len(acts) + 5, _agents_from_golden(g, kind)))
@@ -275,3 +278,40 @@ def test_default_scheduler_params_env_runs():
     for s in range(6):
         obs, rew, done, trunc, info = env.step(np.full(3, s % 10))
     assert done and np.isfinite(obs["est_cov"]).all()
+
+
+@pytest.mark.gpu
+def test_measurement_noise_is_new_every_episode_and_every_env(golden):
+    """agents.py:173-183 draws measurement noise from numpy's global RNG, which no reset rewinds and which
+    differs between worker processes.  The device draw must behave the same way: a new episode (explicit
+    reset or the horizon reset inside step) and a second env built with default arguments see different
+    noise; reset(seed=s) restarts the stream reproducibly (Gymnasium's reset contract)."""
+    from clockpunch_b200.environment.env import SSAScheduler
+    g = golden("env")
+
+    def episode(env, steps=3):
+        out = []
+        vis = env.info["vis_map_est"]
+        for _ in range(steps):
+            a = np.array([int(np.flatnonzero(vis[:, j])[0]) if vis[:, j].any() else env.num_targets
+                          for j in range(env.num_sensors)])
+            obs, *_, info = env.step(a)
+            vis = info["vis_map_est"]
+            out.append(obs["eci_state"].copy())
+        return np.stack(out), int(np.sum(info["num_tasked"]))
+
+    mk = lambda **kw: SSAScheduler(_Params(100.0, 50, _agents_from_golden(g, "default")), **kw)
+    env = mk(seed=5)
+    env.reset()
+    e1, tasked = episode(env)
+    assert tasked > 0                                   # measurements were taken: the noise matters
+    env.reset()
+    e2, _ = episode(env)
+    assert np.abs(e1 - e2).max() > 1e-3                 # same actions, same initial state, NEW noise
+    env.reset(seed=5)
+    e3, _ = episode(env)
+    np.testing.assert_array_equal(e3, e1)               # reseeding restarts the stream
+    a, b = mk(), mk()                                   # default seed: from the OS, distinct per instance
+    a.reset(); b.reset()
+    assert a._engine.seed != b._engine.seed
+    assert np.abs(episode(a)[0] - episode(b)[0]).max() > 1e-3

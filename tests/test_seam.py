@@ -1,0 +1,250 @@
+"""The drop-in seam: `clockpunch_b200.install_as_punchclock()` must let the reference's OWN callers run
+unmodified on top of the mirrored hot-path modules (ray/build_env.py:33-165 `buildEnv`,
+the Gymnasium wrappers, simulation/sim_runner.py, policies).
+
+These tests need the reference tree (/root/reference or $PUNCHCLOCK_REFERENCE) and run on the CPU: the
+build container has the reference but no GPU, the GPU box has a GPU but no reference.  The environment
+built through the seam therefore steps on tests/_oracle_engine.OracleEngine -- a test-only double of
+CatalogEngine on the oracle -- which exercises everything between the reference's wrappers and the
+engine call; the engine itself is checked against the same oracle by the `-m gpu` tests, and the BASE env of
+the very scenario used here is replayed on the GPU by tests/test_env.py (kind "seam").  Missing
+third-party packages (gymnasium, ray, satvis ...) are the test-only stand-ins of tests/golden/_ref_stubs.py.
+"""
+import ast
+import importlib
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+REF = os.environ.get("PUNCHCLOCK_REFERENCE", "/root/reference")
+needs_ref = pytest.mark.skipif(not os.path.isfile(os.path.join(REF, "punchclock", "environment", "env.py")),
+                               reason="reference tree not available on this box")
+
+
+def _run(code: str) -> str:
+    """Run a snippet in a fresh interpreter (the seam rewrites sys.modules: keep it out of this process)."""
+    env = dict(os.environ, PYTHONPATH=os.pathsep.join([ROOT, os.path.join(ROOT, "tests"), os.path.join(ROOT, "tests", "golden")]),
+               PUNCHCLOCK_REFERENCE=REF)
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env=env, cwd="/tmp", timeout=600)
+    assert r.returncode == 0, r.stdout[-3000:] + "\n" + r.stderr[-6000:]
+    return r.stdout
+
+
+@needs_ref
+def test_mirrors_define_every_name_the_reference_imports_from_them():
+    """Every `from punchclock.<mirrored module> import name` anywhere in the reference (package, tests,
+    issues) must resolve on the mirror -- otherwise swapping the module breaks an un-mirrored caller."""
+    import clockpunch_b200 as cpb
+    need = {m: {} for m in cpb._MIRRORED}
+    for root, _, files in os.walk(REF):
+        for f in files:
+            if not f.endswith(".py"):
+                continue
+            path = os.path.join(root, f)
+            try:
+                tree = ast.parse(open(path, encoding="utf-8", errors="ignore").read())
+            except SyntaxError:
+                continue
+            for node in ast.walk(tree):
+                if isinstance(node, ast.ImportFrom) and node.module and node.module.startswith("punchclock."):
+                    m = node.module[len("punchclock."):]
+                    if m in need:
+                        for a in node.names:
+                            need[m].setdefault(a.name, os.path.relpath(path, REF))
+    missing = []
+    for m, names in need.items():
+        mod = importlib.import_module("clockpunch_b200." + m)
+        missing += [(m, n, src) for n, src in names.items() if not hasattr(mod, n)]
+    # tests/common/test_transforms.py:13 imports a function the reference itself does not define
+    missing = [x for x in missing if x[:2] != ("common.transforms", "ecef2eci_test")]
+    assert not missing, missing
+    assert sum(len(v) for v in need.values()) >= 30
+
+
+@needs_ref
+def test_unmirrored_reference_modules_import_on_top_of_the_mirrors():
+    out = _run('''
+import _ref_stubs                                   # stand-ins; also pre-registers the REFERENCE as `punchclock`
+import punchclock.dynamics.dynamics_classes as early      # the reference's own module, imported BEFORE the swap
+assert "reference" in early.__file__
+import clockpunch_b200 as cpb
+ref = cpb.install_as_punchclock()
+assert ref and ref.endswith("punchclock"), ref
+import _ref_stubs as st, sys
+sys.modules["punchclock.ray.build_ray_policy"] = st._StubModule("punchclock.ray.build_ray_policy")   # RLlib nets: stubbed
+import importlib
+# mirrored: ours, under the reference's names -- and they win over what was imported before
+import punchclock.dynamics.dynamics_classes as dc, punchclock.estimation.ukf_v2 as ukf, punchclock.common.visibility as vis
+import punchclock.environment.env as env
+for m in (dc, ukf, vis, env):
+    assert m.__name__.startswith("clockpunch_b200."), m
+assert dc is not early
+# un-mirrored: the reference's files, importing the mirrors through the same names
+names = ["punchclock.common.math", "punchclock.common.utilities", "punchclock.common.orbits", "punchclock.common.custody_tracker",
+         "punchclock.policies.greedy_cov_v2", "punchclock.policies.random_policy", "punchclock.policies.policy_builder",
+         "punchclock.environment.info_wrappers", "punchclock.environment.obs_wrappers", "punchclock.environment.misc_wrappers",
+         "punchclock.environment.reward_wrappers", "punchclock.environment.wrapper_utils", "punchclock.ray.build_env",
+         "punchclock.simulation.sim_runner", "punchclock.simulation.mc", "punchclock.schedule_tree.schedule_tree"]
+for n in names:
+    m = importlib.import_module(n)
+    assert m.__file__.startswith(ref), (n, m.__file__)
+be = importlib.import_module("punchclock.ray.build_env")
+iw = importlib.import_module("punchclock.environment.info_wrappers")
+sr = importlib.import_module("punchclock.simulation.sim_runner")
+import clockpunch_b200.environment.env as ours, clockpunch_b200.common.agents as oa, clockpunch_b200.common.visibility as ov
+assert be.SSAScheduler is ours.SSAScheduler and be.SSASchedulerParams is ours.SSASchedulerParams
+assert iw.Target is oa.Target and iw.calcVisMap is ov.calcVisMap
+assert iw.AccessWindowCalculator.__module__ == "clockpunch_b200.schedule_tree.access_windows"
+import punchclock
+assert punchclock.__version__ == "0.8.5" and punchclock.environment.env is ours
+print("SEAM_OK", len(names))
+''')
+    assert "SEAM_OK" in out
+
+
+@needs_ref
+def test_without_a_reference_tree_only_the_mirrors_resolve():
+    out = _run('''
+import os, sys
+os.environ.pop("PUNCHCLOCK_REFERENCE", None)
+import clockpunch_b200 as cpb
+assert cpb.install_as_punchclock() is None
+from punchclock.dynamics.dynamics_classes import SatDynamicsModel
+from punchclock.common.utilities import actionSpace2Array          # partial mirror: aliased when nothing better exists
+try:
+    import punchclock.common.math
+except ModuleNotFoundError:
+    print("NOREF_OK")
+''')
+    assert "NOREF_OK" in out
+
+
+@needs_ref
+def test_wrapped_env_built_by_the_reference_buildenv_matches_the_live_reference(golden):
+    """The reference's buildEnv with the wrapper stack of its own tests/simulation/data/gen_config_env.py
+    (FilterObservation, CopyObsInfoItem, VisMap2ActionMask, CopyObsInfoItem, NestObsItems, IdentityWrapper,
+    FlatDict), imported THROUGH install_as_punchclock(), builds the mirrored SSASchedulerParams /
+    SSAScheduler / agents / filters, wraps them with the reference's wrapper classes, and an 8-step rollout
+    reproduces the golden rollout of the all-reference stack (tests/golden/make_golden_seam.py): wrapped
+    observation, action mask, info."""
+    out = _run('''
+import numpy as np
+import _ref_stubs, sys
+import clockpunch_b200 as cpb
+ref = cpb.install_as_punchclock()
+sys.modules["punchclock.ray.build_ray_policy"] = _ref_stubs._StubModule("punchclock.ray.build_ray_policy")
+import _oracle_engine
+import clockpunch_b200.environment.env as ours
+_oracle_engine.install_cpu_doubles()          # engine, IC conversions and calcVisMap -> oracle (no GPU in this container)
+import make_golden_seam as mk
+from punchclock.ray.build_env import buildEnv
+import punchclock.common.agents as agents
+got, env = mk.rollout(buildEnv, agents.Target)
+chain = str(env)
+assert chain.startswith("<FlatDict<IdentityWrapper<NestObsItems<CopyObsInfoItem<VisMap2ActionMask<CopyObsInfoItem<FilterObservation<"), chain
+assert type(env.unwrapped) is ours.SSAScheduler and type(env.unwrapped._engine) is _oracle_engine.OracleEngine
+for w, mod in (("FlatDict", "obs_wrappers"), ("VisMap2ActionMask", "misc_wrappers")):
+    import importlib
+    m = importlib.import_module("punchclock.environment." + mod)
+    assert m.__file__.startswith(ref)
+np.savez("/tmp/seam_got.npz", **{k.replace("/", "|"): v for k, v in got.items()})
+print("ROLLOUT_OK")
+''')
+    assert "ROLLOUT_OK" in out
+    g = golden("seam")
+    got = {k.replace("|", "/"): v for k, v in np.load("/tmp/seam_got.npz").items()}
+    want = {k[len("wrapped/"):]: g[k] for k in g.files if k.startswith("wrapped/")}
+    assert set(want) <= set(got), sorted(set(want) - set(got))
+    np.testing.assert_array_equal(got["actions"], want["actions"])
+    assert got["step_obs/observations"].shape[0] == 8 and want["step_info/num_tasked"].sum() >= 4
+    checked = 0
+    for k, w in want.items():
+        a = got[k]
+        assert a.shape == w.shape and a.dtype == w.dtype, (k, a.shape, w.shape, a.dtype, w.dtype)
+        if w.dtype.kind in "iub":
+            np.testing.assert_array_equal(a, w, err_msg=k)
+        else:
+            # both sides integrate with scipy's DOP853 and draw the same measurements; what differs is
+            # the mirrored filter's summation order
+            np.testing.assert_allclose(a, w, rtol=2e-6, atol=1e-6, err_msg=k, equal_nan=True)
+        checked += 1
+    assert checked >= 25, checked
+
+
+@needs_ref
+def test_generic_filter_and_custom_dynamics_are_served_by_the_reference_classes():
+    """tests/estimation/test_ukf_v2.py:54-170 of the reference (2-state filter, custom DynamicsModel subclass,
+    pass-through measurement) and tests/dynamics/test_propagator.py:10-68 (toy linear ODE) through the
+    SWAPPED package: not hot-path configurations, so the mirrored constructors hand them to the reference's
+    own classes; results equal the oracle's generic UKF.  No CUDA call is made (this runs without a GPU)."""
+    out = _run('''
+import numpy as np
+import _ref_stubs
+import clockpunch_b200 as cpb
+ref = cpb.install_as_punchclock()
+from punchclock.dynamics.dynamics_classes import DynamicsModel
+from punchclock.dynamics.propagator import simplePropagate
+from punchclock.estimation.ukf_v2 import UnscentedKalmanFilter
+import clockpunch_b200.estimation.ukf_v2 as ours
+assert UnscentedKalmanFilter is ours.UnscentedKalmanFilter
+
+def passThruMeasurement(state):
+    return state
+
+def simpleDynamicsFunc(state, start_time, stop_time):
+    return state + (stop_time - start_time) * np.ones(state.shape)
+
+class SimpleDynamicsModel(DynamicsModel):
+    def __init__(self):
+        super().__init__(simpleDynamicsFunc)
+    def propagate(self, start_time, end_time, start_state, **kwargs):
+        return self._dynamics_func(start_state, start_time, end_time, **kwargs)
+
+dyn = SimpleDynamicsModel()
+f = UnscentedKalmanFilter(time=0, est_x=np.array([0, 0]), est_p=np.eye(2), dynamics_model=dyn,
+                          measurement_model=passThruMeasurement, q_matrix=np.eye(2), r_matrix=np.eye(2))
+assert type(f).__module__.startswith("clockpunch_b200._reference_modules"), type(f)
+assert f.x_dim == 2 and f.num_sigmas == 5 and f.cvr_weight.shape == (5, 5)
+from punchclock.estimation.filter_base_class import Filter
+assert isinstance(f, Filter)
+f.predict(final_time=10)
+assert f.time == 10 and f.sigma_points.shape == (2, 5)
+z = np.array([10.2, 9.7])
+f.update(measurement=z)
+from oracle.ukf import OracleUKF
+o = OracleUKF(0, np.array([0.0, 0.0]), np.eye(2), np.eye(2), np.eye(2),
+              dynamics=lambda x, t0, tf: x + (tf - t0), measurement_model=passThruMeasurement)
+o.predict_and_update(10, z)
+np.testing.assert_allclose(f.est_x, o.est_x, rtol=1e-12)
+np.testing.assert_allclose(f.est_p, o.est_p, rtol=1e-12)
+np.testing.assert_allclose(f.nis, o.nis, rtol=1e-10)
+f.reset()
+assert f.time == 0 and f.nis.size == 0
+# toy linear ODE through simplePropagate (tests/dynamics/test_propagator.py:17-45): dx/dt = -x
+got = simplePropagate(lambda t, x: -x, np.array([1.0, 2.0]), 0.0, 1.0)
+np.testing.assert_allclose(got, np.array([1.0, 2.0]) * np.exp(-1.0), rtol=1e-8)
+try:
+    simplePropagate(lambda t, x: -x, np.array([1.0, 2.0]), 1.0, 1.0)
+except ValueError:
+    print("GENERIC_OK")
+''')
+    assert "GENERIC_OK" in out
+
+
+def test_generic_filter_without_a_reference_tree_raises():
+    out = _run('''
+import os, numpy as np
+os.environ.pop("PUNCHCLOCK_REFERENCE", None)
+from clockpunch_b200.estimation.ukf_v2 import UnscentedKalmanFilter
+from clockpunch_b200.dynamics.dynamics_classes import SatDynamicsModel
+try:
+    UnscentedKalmanFilter(0, np.zeros(2), np.eye(2), SatDynamicsModel(), lambda s: s, np.eye(2), np.eye(2))
+except NotImplementedError as e:
+    assert "no reference tree" in str(e)
+    print("RAISES_OK")
+''')
+    assert "RAISES_OK" in out
