@@ -46,12 +46,12 @@ UNIT = "target-steps/s"
 FLOP_DOP853_STEP = 1150.0          # one fixed DOP853 step: 12 RHS + stage sums + final combination
 FLOP_UKF_NOMEAS, FLOP_UKF_MEAS = 1500.0, 5600.0
 FLOP_VIS_PAIR = 8.0
-# DRAM traffic per launch of propagate_sigma_kernel from the committed ncu captures: (targets, sensors) -> bytes
-TRAFFIC_NCU = {(10_000, 100): 6.784e6 + 0.0, (1_000_000, 100): 680.5e6 + 614.8e6}
-# the same kernel's gpu__time_duration.sum (ms, mean of 26 launches) in the committed launch lists
-# profiles/r1d_launches_bench_{10k,1M}.csv: what the kernel itself takes, without the event pair's ~8 us
-NCU_KERNEL_MS = {(10_000, 100): 0.013758, (1_000_000, 100): 0.724994}
+FLOP_NEXT_CHOL = 110.0             # Cholesky of the new est_p (next step's sigma points)
+FP64_INSTR_DOP853_STEP = 435.0     # FP64 instructions the kernel executes per DOP853 step (320 DFMA + 109 DMUL + 6 DADD;
+                                   # tools/sass_mix.py on the built library)
 BYTES_TARGET_STEP = 1130.0         # truth/est_x/est_p r+w, pred_p w, z r (+ M/4 vis bits)
+BYTES_FINISH_TARGET = 1824.0       # per-target kernel: 13 states read (624), est_p + pred_p written (576), next sigma
+                                   # points written (624) (+ M/4 vis bits)
 
 
 def workload_config(n_targets, n_sensors):
@@ -207,6 +207,73 @@ def run_reference(args):
 
 
 # ----------------------------------------------------------------------------- own arm
+def kernel_sources_sha256():
+    """Content hash of the CUDA sources: profile summaries under profiles/ are only trusted for the exact
+    kernels they were captured from."""
+    import hashlib
+    h = hashlib.sha256()
+    d = os.path.join(ROOT, "clockpunch_b200", "csrc")
+    for f in sorted(os.listdir(d)):
+        if f.endswith((".cu", ".cuh")):
+            h.update(f.encode())
+            h.update(open(os.path.join(d, f), "rb").read())
+    return h.hexdigest()
+
+
+def load_profile_summary(n_targets, n_sensors):
+    """profiles/r2_kernel_summary_<N>.json (tools/kernel_profile_summary.py: per-kernel ncu durations and
+    DRAM traffic of this workload) -- or None when absent or captured from other kernel sources."""
+    path = os.path.join(ROOT, "profiles", f"r2_kernel_summary_{n_targets}.json")
+    try:
+        d = json.load(open(path))
+    except (OSError, ValueError):
+        return None
+    if d.get("sources_sha256") != kernel_sources_sha256() or d.get("sensors") != n_sensors:
+        return None
+    d["file"] = os.path.relpath(path, ROOT)
+    return d
+
+
+def pin_rank_to_cores(local, world_local):
+    """Give every rank of a multi-rank run its own slice of the host cores, on the NUMA node of its GPU
+    when sysfs tells (eight processes sharing one core set made the end-to-end step 2x slower at N = 8)."""
+    try:
+        cores = sorted(os.sched_getaffinity(0))
+    except AttributeError:
+        return None
+    if world_local <= 1 or len(cores) < 2 * world_local:
+        return None
+    node_cores = None
+    try:
+        import pynvml as nv
+        nv.nvmlInit()
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+        phys = int(vis.split(",")[local]) if vis and vis.split(",")[local].isdigit() else local
+        bus = nv.nvmlDeviceGetPciInfo(nv.nvmlDeviceGetHandleByIndex(phys)).busId
+        bus = (bus.decode() if isinstance(bus, bytes) else bus).lower()
+        bus = bus[4:] if len(bus) > 12 else bus
+        node = int(open(f"/sys/bus/pci/devices/{bus}/numa_node").read())
+        if node >= 0:
+            txt = open(f"/sys/devices/system/node/node{node}/cpulist").read().strip()
+            nc = set()
+            for part in txt.split(","):
+                lo, _, hi = part.partition("-")
+                nc.update(range(int(lo), int(hi or lo) + 1))
+            node_cores = [c for c in cores if c in nc]
+    except Exception:
+        node_cores = None
+    per = max(1, len(cores) // world_local)
+    mine = cores[local * per:(local + 1) * per]
+    if node_cores and len(node_cores) >= per:
+        k = local % max(1, len(node_cores) // per)
+        mine = node_cores[k * per:(k + 1) * per] or mine
+    try:
+        os.sched_setaffinity(0, mine)
+    except OSError:
+        return None
+    return mine
+
+
 def run_own(args):
     # stdout carries exactly one JSON line: anything libraries print while we work (NCCL prints its
     # version banner to fd 1) is routed to stderr, and fd 1 is restored for the final print
@@ -220,6 +287,11 @@ def run_own(args):
         print(json.dumps(line))
         sys.stdout.flush()
 
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    pinned_cores = pin_rank_to_cores(local, int(os.environ.get("LOCAL_WORLD_SIZE", str(world))))
+
     import torch
     import torch.distributed as dist
     from clockpunch_b200 import _lib
@@ -227,61 +299,24 @@ def run_own(args):
     from clockpunch_b200.simulation.catalog import synth_catalog
     import ctypes as C
 
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device (no CPU fallback); use --impl reference for the CPU arm")
     torch.cuda.set_device(local)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     dev = torch.device("cuda", local)
-
-    N, M = args.targets, args.sensors
-    # every rank owns its own shard of targets; the sensor network is replicated
-    cat = synth_catalog(N, M, seed=SEED + 1000 * rank, sensor_seed=SEED)
-    eng = CatalogEngine(cat.sensors, cat.sensor_kinds, cat.targets, cat.est_x, cat.est_p, cat.Q, cat.R,
-                        device=local, seed=SEED + rank)
-    ctx, lib = eng.ctx, eng.ctx.lib
-    stream = torch.cuda.current_stream(dev).cuda_stream
+    ctx = _lib.get_ctx(local)
+    lib = ctx.lib
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
-
-    # per-step summaries every rank needs from every other: packed est vis map,
-    # trace(P_pos), trace(P_vel), last_time_tasked, num_tasked -- all-gathered straight out of the
-    # buffers the kernels write (equal shards: no staging copy)
-    # Exchange: by default the per-target kernel itself stores every summary into all peers'
-    # gathered buffers over NVLink (peer-mapped symmetric memory) and the step ends with a flag wait;
-    # --exchange nccl uses one all-gather of the summary buffer captured into the step's graph.
-    sg, exchange = None, "none"
-    if world > 1:
-        from clockpunch_b200.sharding import PackedGather
-        sg = PackedGather(world, rank, eng.summary, N, eng.wpr)
-        exchange = "nccl all_gather_into_tensor" + ("" if args.eager_gather else " (captured in the step graph)")
-        # measured on 8 GPUs: 10 000 targets per GPU 61 us per step (stores from the per-target kernel)
-        # vs 79 us with the all-gather; 125 000 per GPU 0.264 ms (copy kernel behind it) vs 0.287 ms
-        if args.exchange in ("peer", "auto"):
-            try:
-                eng.enable_peer_push()
-                mode = {"auto": 0, "store": 1, "copy": 2}[args.peer_push]
-                ctx_opt = eng.ctx.set_option(_lib.OPT_PEER_PUSH, mode)
-                by_copy = mode == 2 or (mode == 0 and (N > 32768 or world >= 8))
-                exchange = ("peer stores from the per-target kernel" if not by_copy else
-                            "summary pushed into every peer by a copy kernel behind the per-target kernel") + \
-                    " (symmetric memory over NVLink) + flag wait"
-            except Exception as exc:        # no symmetric memory on this box: keep the collective
-                print(f"peer push unavailable ({exc!r}); using NCCL", file=sys.stderr)
-    use_nccl = sg is not None and eng._peer is None
-    gather_in_graph = use_nccl and not args.eager_gather
-    post = sg.gather if gather_in_graph else None
-
-    # policy -> tasking mask -> sensors -> truth + UKF -> vis maps [-> all-gather], captured once,
-    # replayed per step
-    g_value = None
-
-    def device_step():
-        eng.replay(g_value)
-        if use_nccl and not gather_in_graph:
-            sg.gather()
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except OSError:
+        pass
+    hbm_peak = peaks.get("hbm_gbs", 6650.0)
+    peak_tf = C.c_double()
+    ctx.check(lib.pc_fp64_peak(ctx.handle, 5, C.byref(peak_tf)))
+    peak_tf = peak_tf.value
 
     def barrier():
         torch.cuda.synchronize(dev)
@@ -289,203 +324,337 @@ def run_own(args):
             dist.barrier()
             torch.cuda.synchronize(dev)
 
-    # ---------------- device-resident throughput (`value`) ----------------
-    if sg is not None:
-        sg.gather()                      # first NCCL call (communicator set-up) outside any capture
-        torch.cuda.synchronize(dev)
-    g_value = eng.build_graph(DT, policy_probes=64, policy_seed=SEED, post=post)
-    for k in range(args.warmup):
-        device_step()
-    if eng._peer is not None:
-        # check the pushed copies once against a plain all-gather of the same buffers (untimed); if any
-        # rank disagrees, every rank falls back to the NCCL exchange
-        ref = sg.gather().clone()
-        err, pushes = eng.peer_status()
-        bad = torch.tensor([int(bool(err) or not torch.equal(eng._peer["gathered"][pushes & 1], ref))], device=dev)
-        dist.all_reduce(bad, op=dist.ReduceOp.MAX)
-        if int(bad.item()):
-            print(f"rank {rank}: peer-pushed summaries differ from the all-gather (error mask {err:#x}); "
-                  "falling back to NCCL", file=sys.stderr)
-            eng._peer, eng._hs_key = None, None
-            use_nccl, gather_in_graph = True, not args.eager_gather
-            post = sg.gather if gather_in_graph else None
-            exchange = "nccl all_gather_into_tensor (fallback: peer push failed its check)"
-            eng.reset()
-            g_value = eng.build_graph(DT, policy_probes=64, policy_seed=SEED, post=post)
-            for k in range(args.warmup):
-                device_step()
-    peak_tf = C.c_double()
-    ctx.check(lib.pc_fp64_peak(ctx.handle, 5, C.byref(peak_tf)))
-    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    def max_over_ranks(x):
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    # ------------------------------------------------------------------ one workload on this rank
+    class Workload:
+        """A catalog shard on this rank + its exchange + its step graph."""
+
+        def __init__(self, n, m, dt, seed, all_tasked=False, num_envs=1, mix="mixed"):
+            self.n, self.m, self.dt, self.all_tasked, self.E = n, m, dt, all_tasked, num_envs
+            # every rank owns its own shard of targets; the sensor network is replicated
+            self.cat = synth_catalog(n, m, seed=seed + 1000 * rank, sensor_seed=seed, mix=mix)
+            c = self.cat
+            self.eng = CatalogEngine(c.sensors, c.sensor_kinds, c.targets, c.est_x, c.est_p, c.Q, c.R, device=local,
+                                     seed=seed + rank, num_envs=num_envs)
+            self.sg, self.exchange, self.use_nccl, self.post = None, "none", False, None
+            # per-step summaries every rank needs from every other (SURVEY.md section 8e): packed est vis map,
+            # trace(P_pos), trace(P_vel), last_time_tasked, num_tasked.  Default: the NEXT step's sensor kernel copies
+            # them into every peer's gathered buffer over NVLink (pc_comm_*: CUDA IPC) and waits for the peers,
+            # beside the target propagation; --exchange nccl: one all-gather of the
+            # summary buffer captured into the step's graph.  Environments (num_envs > 1) are independent
+            # replicas: nothing is exchanged.
+            if world > 1 and num_envs == 1:
+                from clockpunch_b200.sharding import PackedGather
+                self.sg = PackedGather(world, rank, self.eng.summary, n, self.eng.wpr)
+                self.exchange = "nccl all_gather_into_tensor" + ("" if args.eager_gather else " (captured in the step graph)")
+                if args.exchange in ("peer", "auto"):
+                    try:
+                        self.eng.enable_peer_push()
+                        self.exchange = ("the NEXT step's sensor kernel copies this step's summary buffer into every peer's "
+                                         "gathered buffer (pc_comm_*: CUDA IPC over NVLink) and waits for the peers' flags, "
+                                         "beside the target propagation")
+                    except Exception as exc:        # no peer access on this box: keep the collective
+                        print(f"peer push unavailable ({exc!r}); using NCCL", file=sys.stderr)
+                self.use_nccl = self.eng._peer is None
+                if self.use_nccl and not args.eager_gather:
+                    self.post = self.sg.gather
+            self.graph = None
+
+        def build(self):
+            if self.sg is not None:
+                self.sg.gather()                 # first NCCL call (communicator set-up) outside any capture
+                torch.cuda.synchronize(dev)
+            self.graph = self.eng.build_graph(self.dt, policy_probes=0 if self.all_tasked else 64, policy_seed=SEED,
+                                              post=self.post, all_tasked=self.all_tasked)
+
+        def step(self):
+            self.eng.replay(self.graph)
+            if self.use_nccl and self.post is None:
+                self.sg.gather()
+
+        def verify_exchange(self):
+            """The pushed copies once against a plain all-gather of the same buffers (untimed); if any rank
+            disagrees, every rank falls back to the NCCL exchange."""
+            if self.eng._peer is None:
+                return
+            ref = self.sg.gather().clone()
+            err, pushes = self.eng.peer_status()
+            bad = torch.tensor([int(bool(err) or not torch.equal(self.eng._peer["gathered"][pushes & 1], ref))], device=dev)
+            dist.all_reduce(bad, op=dist.ReduceOp.MAX)
+            if int(bad.item()):
+                print(f"rank {rank}: peer-pushed summaries differ from the all-gather (error mask {err:#x}); "
+                      "falling back to NCCL", file=sys.stderr)
+                self.eng._peer, self.eng._hs_key = None, None
+                self.use_nccl = True
+                self.post = None if args.eager_gather else self.sg.gather
+                self.exchange = "nccl all_gather_into_tensor (fallback: peer push failed its check)"
+                self.eng.reset()
+                self.build()
+
+        def timed(self, steps, warmup, episode=EPISODE):
+            """Device-resident pass: graph replay, CUDA events per step, L2 flushed between steps; max over
+            ranks.  The last step's exchange completes inside the timed region (the deferred wait of the
+            peer push is enqueued before the final event)."""
+            for _ in range(warmup):
+                self.step()
+            self.verify_exchange()
+            evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+            barrier()
+            wall0 = time.perf_counter()
+            for k in range(steps):
+                if k and k % episode == 0:         # a new episode, as the env does at its horizon (untimed)
+                    self.eng.reset()
+                    self.eng.ensure_sigma()
+                if args.l2 == "flush":
+                    flush.zero_()                  # L2 flush, outside the timed events
+                evs[k][0].record()
+                self.step()
+                if self.eng._peer is not None and k == steps - 1:
+                    self.eng.peer_sync()           # the exchange a following step would have done
+                evs[k][1].record()
+            barrier()
+            wall = time.perf_counter() - wall0
+            ms = max_over_ranks(sum(a.elapsed_time(b) for a, b in evs)) / steps
+            return ms, wall, self.graph.pc_launches * steps
+
+    def roofline_kernels(w, steps_done_before, warmup, n_roof):
+        """Per-kernel rooflines of one workload (a separate pass): the step's kernels launched one by one (not the
+        graph), three CUDA events recorded by the library on the launch stream -- before the sigma-point
+        propagation, between it and the per-target kernel, after the per-target kernel.  Inside a captured
+        graph the events would be extra event-record NODES whose latency (~4 us each) would be charged to
+        kernels of 12-15 us.  Algorithmic work: SURVEY.md section 8(d)."""
+        eng, N, M, dt = w.eng, w.n, w.m, w.dt
+        eng.reset()
+        eng._graph = None
+        ctx.check(lib.pc_set_timing(ctx.handle, 1))
+
+        def timed_step():
+            if w.all_tasked:
+                eng.step(dt=dt, tasked=ones)
+            else:
+                eng.step_policy_eager(dt, 64, SEED)       # same kernels as the graph, launched one by one
+            if w.use_nccl:
+                w.sg.gather()
+
+        ones = torch.ones(N, dtype=torch.uint8, device=dev)
+        for _ in range(warmup):
+            timed_step()
+        inv_theta = np.float32(1.0 / 0.12)
+        tx = eng.host("truth_x")
+        hv = np.cross(tx[:3].T, tx[3:].T)
+        h2, r2, v2 = (hv * hv).sum(1), (tx[:3] ** 2).sum(0), (tx[3:] ** 2).sum(0)
+        e1 = 1.0 + np.sqrt(np.maximum(0.0, 1.0 + 2.0 * (0.5 * v2 - 398600.0 / np.sqrt(r2)) * h2 / 398600.0 ** 2))
+        truth_sub = np.maximum(1.0, np.ceil(dt * (398600.0 ** 2 * e1 ** 3.5 / h2 ** 1.5) / 0.12))
+
+        def substeps_now():
+            om = eng.sig_flags[1].cpu().numpy().view(np.float32)
+            est = np.maximum(1.0, np.ceil(np.float32(dt) * om * inv_theta)).astype(np.float64)
+            return 13.0 * est.sum() + truth_sub.sum(), est.mean()
+
+        p_ms, f_ms, state_steps_sum, est_sub_sum = 0.0, 0.0, 0.0, 0.0
+        a_ms, b_ms = C.c_double(), C.c_double()
+        nt0 = int(eng.num_tasked.sum().item())
+        for k in range(n_roof + 2):
+            ss, es = substeps_now()
+            if args.l2 == "flush":
+                flush.zero_()
+            timed_step()
+            torch.cuda.synchronize(dev)                                   # the events are this step's
+            ctx.check(lib.pc_get_kernel_timing(ctx.handle, C.byref(a_ms), C.byref(b_ms)))
+            if k >= 2:
+                p_ms += a_ms.value
+                f_ms += b_ms.value
+                state_steps_sum += ss
+                est_sub_sum += es
+        ctx.check(lib.pc_set_timing(ctx.handle, 0))
+        tasked_frac = (int(eng.num_tasked.sum().item()) - nt0) / max(1, N * (n_roof + 2))
+        flags_bad = int((eng.flags != 0).sum().item())
+        p_ms, f_ms = p_ms / n_roof, f_ms / n_roof
+        state_steps = state_steps_sum / n_roof                  # DOP853 steps per launch, summed over 14 N states
+        prof = load_profile_summary(N, M)
+
+        def from_profile(kernel, key):
+            if not prof:
+                return None
+            for name, v in prof.get("kernels", {}).items():
+                if kernel.startswith(name) or name.startswith(kernel.split("<")[0]):
+                    return v.get(key)
+            return None
+
+        # -- sigma-point propagation: FP64 bound
+        prop_name = "propagate_sigma_kernel" if N > 16 * 1024 else "propagate_sigma_single_kernel"
+        flop_prop = FLOP_DOP853_STEP * state_steps
+        ach = flop_prop / (p_ms * 1e-3) * 1e-12
+        instr = FP64_INSTR_DOP853_STEP * state_steps
+        prop_ncu_ms = from_profile("propagate_sigma", "ms_mean")
+        prop = {"kernel": prop_name, "bound": "fp64", "achieved": ach, "peak": peak_tf, "unit": "TFLOP/s",
+                "frac": ach / peak_tf, "kernel_ms": p_ms, "flop_per_launch": flop_prop,
+                "dop853_steps_per_launch": state_steps, "mean_substeps_per_sigma_propagate": est_sub_sum / n_roof,
+                "algorithmic_flop_per_unit": FLOP_DOP853_STEP, "unit_of_work": "one DOP853 step of one state",
+                # what the FP64 pipe actually executes: 435 FP64 instructions per DOP853 step (320 DFMA + 109 DMUL +
+                # 6 DADD, tools/sass_mix.py), against the pipe's issue rate = measured DFMA peak / 2 flop
+                "fp64_instr_per_launch": instr, "fp64_issue_frac": instr / (p_ms * 1e-3) / (peak_tf * 1e12 / 2.0),
+                "traffic": from_profile("propagate_sigma", "dram_bytes"), "kernel_ms_ncu": prop_ncu_ms,
+                "frac_on_ncu_duration": (flop_prop / (prop_ncu_ms * 1e-3) * 1e-12 / peak_tf) if prop_ncu_ms else None,
+                "hbm": {"achieved": 14 * 96.0 * N / (p_ms * 1e-3) * 1e-9, "peak": hbm_peak, "unit": "GB/s",
+                        "frac": 14 * 96.0 * N / (p_ms * 1e-3) * 1e-9 / hbm_peak, "bytes_per_launch": 14 * 96.0 * N}}
+        # -- per-target kernel: HBM bound at large catalogs, latency bound at small ones -- both fractions
+        fin_name = ("ukf_finish_quad_kernel" if N <= 32768 else "ukf_finish_kernel<64>" if N <= 131072 else "ukf_finish_kernel<128>")
+        bytes_fin = (BYTES_FINISH_TARGET + M / 4.0) * N
+        flop_fin = ((1 - tasked_frac) * FLOP_UKF_NOMEAS + tasked_frac * FLOP_UKF_MEAS + FLOP_NEXT_CHOL + 2 * M * FLOP_VIS_PAIR) * N
+        gbs = bytes_fin / (f_ms * 1e-3) * 1e-9
+        tfs = flop_fin / (f_ms * 1e-3) * 1e-12
+        fin_ncu_ms = from_profile("ukf_finish", "ms_mean")
+        fin = {"kernel": fin_name, "bound": "hbm", "achieved": gbs, "peak": hbm_peak, "unit": "GB/s", "frac": gbs / hbm_peak,
+               "kernel_ms": f_ms, "bytes_per_launch": bytes_fin, "algorithmic_bytes_per_unit": BYTES_FINISH_TARGET + M / 4.0,
+               "unit_of_work": "one target: 13 sigma points read, est_p / pred_p / next sigma points written, 2 vis rows",
+               "fp64": {"achieved": tfs, "peak": peak_tf, "unit": "TFLOP/s", "frac": tfs / peak_tf, "flop_per_launch": flop_fin},
+               "traffic": from_profile("ukf_finish", "dram_bytes"), "kernel_ms_ncu": fin_ncu_ms,
+               "frac_on_ncu_duration": (bytes_fin / (fin_ncu_ms * 1e-3) * 1e-9 / hbm_peak) if fin_ncu_ms else None,
+               "tasked_fraction": tasked_frac}
+        note = ("kernel_ms: CUDA events recorded by the library around each kernel of an eagerly launched step "
+                "(the events cost a few us, which matters for kernels of 12-15 us at 10 000 targets and not at 125 000+); "
+                "kernel_ms_ncu / traffic / frac_on_ncu_duration come from " +
+                (prof["file"] + " (ncu capture of these very kernel sources, hash checked)" if prof else
+                 "no profile summary matching the current kernel sources: null"))
+        return prop, fin, note, tasked_frac, flags_bad, flop_prop
+
+    # ------------------------------------------------------------------ headline: BASELINE.json configs[1]
+    N, M = args.targets, args.sensors
+    head = Workload(N, M, DT, SEED)
+    head.build()
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
-    barrier()
-    wall0 = time.perf_counter()
-    for k in range(args.steps):
-        if k and k % EPISODE == 0:         # a new episode, as the env does at its horizon (untimed)
-            eng.reset()
-            eng.ensure_sigma()
-        if args.l2 == "flush":
-            flush.zero_()                  # L2 flush, outside the timed events
-        evs[k][0].record()
-        device_step()
-        evs[k][1].record()
-    barrier()
-    wall = time.perf_counter() - wall0
-    ms = sum(a.elapsed_time(b) for a, b in evs)
-    launches = g_value.pc_launches * args.steps
-    t_ms = torch.tensor([ms], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t_ms, op=dist.ReduceOp.MAX)
-    ms_per_step = float(t_ms.item()) / args.steps
+    ms_per_step, wall, launches = head.timed(args.steps, args.warmup)
     value = world * N / (ms_per_step * 1e-3)
 
-    # ---------------- roofline of the dominant kernel (separate pass) ----------------
-    # propagate_sigma_kernel (two states per thread out of a sorted 256-target window; catalogs up to
-    # 16 k targets: propagate_sigma_single_kernel, one state per thread): all 13 sigma points + the
-    # truth state of every target.  Its launch is bracketed by a CUDA-event pair recorded by the library on the launch
-    # stream.  This pass launches the step's kernels one by one (not the graph `value` replays):
-    # inside a captured graph the pair would be two extra event-record NODES, whose latency (~4 us
-    # each) would be charged to a 14 us kernel.
-    # Algorithmic work: SURVEY.md section 8(d), 1150 flop per fixed DOP853 step x the substeps each state
-    # actually takes (read back from the per-target orbit rates the step itself uses); algorithmic
-    # bytes: each 6-vector read and written once.
-    # Every pass (value, roofline, e2e) starts from the same catalog state: reset + warm-up.
-    eng.reset()
-    ctx.check(lib.pc_set_timing(ctx.handle, 1))
-    eng._graph = None
-
-    def timed_step():
-        eng.step_policy_eager(DT, 64, SEED)         # same kernels, launched one by one: plain event records
-        if use_nccl:
-            sg.gather()
-
-    for k in range(args.warmup):
-        timed_step()
-    inv_theta = np.float32(1.0 / 0.12)
-
-    def substeps_now():
-        om = eng.sig_flags[1].cpu().numpy().view(np.float32)
-        est = np.maximum(1.0, np.ceil(np.float32(DT) * om * inv_theta)).astype(np.float64)
-        return 13.0 * est.sum() + truth_sub.sum(), est.mean()
-
-    tx = eng.host("truth_x")
-    hv = np.cross(tx[:3].T, tx[3:].T)
-    h2, r2, v2 = (hv * hv).sum(1), (tx[:3] ** 2).sum(0), (tx[3:] ** 2).sum(0)
-    e1 = 1.0 + np.sqrt(np.maximum(0.0, 1.0 + 2.0 * (0.5 * v2 - 398600.0 / np.sqrt(r2)) * h2 / 398600.0 ** 2))
-    truth_sub = np.maximum(1.0, np.ceil(DT * (398600.0 ** 2 * e1 ** 3.5 / h2 ** 1.5) / 0.12))
-    ukf_ms_sum, state_steps_sum, est_sub_sum, ukf_last = 0.0, 0.0, 0.0, C.c_double()
     n_roof = max(3, min(args.steps, 50))
-    for k in range(n_roof + 2):
-        ss, es = substeps_now()
-        if args.l2 == "flush":
-            flush.zero_()
-        timed_step()
-        torch.cuda.synchronize(dev)                                   # both events are this step's
-        ctx.check(lib.pc_get_timing(ctx.handle, C.byref(ukf_last)))
-        if k >= 2:
-            ukf_ms_sum += ukf_last.value
-            state_steps_sum += ss
-            est_sub_sum += es
-    ctx.check(lib.pc_set_timing(ctx.handle, 0))
-    tasked_total = int(eng.num_tasked.sum().item())
-    flags_bad = int((eng.flags != 0).sum().item())
-    total_steps = args.warmup + n_roof + 2
-    tasked_frac = tasked_total / max(1, N * total_steps)
-    state_steps = state_steps_sum / n_roof                  # DOP853 steps per launch, summed over 14 N states
-    substeps_used = est_sub_sum / n_roof
-    flop_per_launch = FLOP_DOP853_STEP * state_steps
-    flop_per_target_step = flop_per_launch / N + (1 - tasked_frac) * FLOP_UKF_NOMEAS + tasked_frac * FLOP_UKF_MEAS \
-        + 2 * M * FLOP_VIS_PAIR
-    ukf_ms_avg = ukf_ms_sum / n_roof
-    achieved_tf = flop_per_launch / (ukf_ms_avg * 1e-3) * 1e-12
-    peaks = {}
-    try:
-        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
-    except OSError:
-        pass
-    hbm_peak = peaks.get("hbm_gbs", 6650.0)
-    hbm_ach = 14 * 96.0 * N / (ukf_ms_avg * 1e-3) * 1e-9
-    roofline = {"bound": "fp64", "kernel": "propagate_sigma_kernel" if N > 16 * 1024 else "propagate_sigma_single_kernel",
-                "achieved": achieved_tf, "peak": peak_tf.value,
-                "unit": "TFLOP/s", "frac": achieved_tf / peak_tf.value if peak_tf.value else None,
-                "traffic": TRAFFIC_NCU.get((N, M)), "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum of this "
-                "kernel in the committed ncu --set full capture of this workload (profiles/r1d_ncu_full_step_*_metrics.csv); "
-                "null for other sizes", "peak_source": "FP64 DFMA probe measured live in this run (pc_fp64_peak); "
-                "MEASURED_PEAKS.json has no FP64 entry (HBM/bf16 only); nominal 37 TFLOP/s",
-                "flop_per_launch": flop_per_launch, "dop853_steps_per_launch": state_steps,
-                "mean_substeps_per_sigma_propagate": substeps_used,
-                "kernel_ms": ukf_ms_avg, "kernel_share_of_step": ukf_ms_avg / ms_per_step,
-                "kernel_ms_ncu": NCU_KERNEL_MS.get((N, M)),
-                "frac_on_ncu_duration": (flop_per_launch / (NCU_KERNEL_MS[(N, M)] * 1e-3) * 1e-12 / peak_tf.value
-                                         if (N, M) in NCU_KERNEL_MS and peak_tf.value else None),
-                "frac_note": "frac uses kernel_ms, a CUDA-event pair around ONE launch per step (the pair itself "
-                "costs ~8 us, which matters for a 14 us kernel at 10 000 targets and not at 1 M); frac_on_ncu_duration "
-                "divides the same live flop count by the kernel's committed ncu duration (profiles/r1d_launches_*.csv)",
-                "whole_step_flop_per_target_step": flop_per_target_step,
-                "whole_step_achieved": flop_per_target_step * N / (ms_per_step * 1e-3) * 1e-12,
-                "hbm": {"achieved": hbm_ach, "peak": hbm_peak, "unit": "GB/s", "frac": hbm_ach / hbm_peak,
-                        "bytes_per_launch": 14 * 96.0 * N,
-                        "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback"}}
+    prop, fin, roof_note, tasked_frac, flags_bad, flop_prop = roofline_kernels(head, 0, args.warmup, n_roof)
+    flop_per_target_step = flop_prop / N + (1 - tasked_frac) * FLOP_UKF_NOMEAS + tasked_frac * FLOP_UKF_MEAS \
+        + FLOP_NEXT_CHOL + 2 * M * FLOP_VIS_PAIR
+    # `roofline`: the dominant kernel of the step (the longer of the two, by its live duration), with every kernel
+    # of the step in `kernels`
+    roofline = dict(prop if prop["kernel_ms"] >= fin["kernel_ms"] else fin)
+    roofline.update({
+        "kernels": [prop, fin], "note": roof_note,
+        "peak_source": "FP64: DFMA probe measured live in this run (pc_fp64_peak; MEASURED_PEAKS.json has no FP64 entry, "
+                       "nominal 37 TFLOP/s); HBM: MEASURED_PEAKS.json" + ("" if peaks else " missing -> fallback"),
+        "kernel_share_of_step": {"propagate": prop["kernel_ms"] / ms_per_step, "finish": fin["kernel_ms"] / ms_per_step,
+                                 "note": "event-timed kernels of the eager pass over the graph-replayed step: shares can "
+                                         "exceed 1 in sum (events serialise what the graph overlaps)"},
+        "whole_step_flop_per_target_step": flop_per_target_step,
+        "whole_step_achieved_tflops": flop_per_target_step * N / (ms_per_step * 1e-3) * 1e-12,
+        "whole_step_bytes_per_target_step": BYTES_TARGET_STEP + M / 4.0})
     clocks = sampler.stop() if rank == 0 else None
 
-    # ---------------- end to end through the public API (`e2e`) ----------------
+    # ------------------------------------------------------------------ end to end through the public API (`e2e`)
     # CatalogEngine.step_host -> pc_step_host: pinned host actions -> device, the step + observation
     # pack (CUDA graph inside the library), observation + packed vis map + num_tasked -> pinned host,
     # stream synchronise.  The policy runs on the host from the previous step's observation.
-    eng.reset()
-    eng._graph = None
-    hb = eng.host_buffers()
-    # Host-side scheduler: the stand-in policy of the `value` pass (first estimated-visible target among 64
-    # hashed probes per sensor, else inaction) in its host form, reading the packed estimated map that the
-    # previous pc_step_host copied out and writing the pinned actions buffer of the next one.
-    import ctypes as C
-    h_vis_ptr = C.c_void_p(hb["vis_est"].data_ptr())
-    h_act_ptr = C.c_void_p(hb["actions"].data_ptr())
-    host_policy_fn = eng.ctx.lib.pc_policy_random_visible_host
+    def e2e_pass(w, steps, warmup):
+        eng = w.eng
+        eng.reset()
+        eng._graph = None
+        hb = eng.host_buffers()
+        h_vis_ptr = C.c_void_p(hb["vis_est"].data_ptr())
+        h_act_ptr = C.c_void_p(hb["actions"].data_ptr())
+        host_policy_fn = lib.pc_policy_random_visible_envs_host
+        Ne, Me, E = w.n // w.E, w.m // w.E, w.E
 
-    def host_policy(k):
-        rc = host_policy_fn(h_vis_ptr, N, M, eng.wpr, SEED + rank, k, 64, h_act_ptr)
-        if rc:
-            raise RuntimeError(f"pc_policy_random_visible_host status {rc}")
+        def host_policy(k):
+            # the stand-in policy of the `value` pass in its host form, on the packed estimated map the previous
+            # pc_step_host wrote
+            rc = host_policy_fn(h_vis_ptr, E, Ne, Me, eng.wpr, SEED + rank, k, 64, h_act_ptr)
+            if rc:
+                raise RuntimeError(f"pc_policy_random_visible_envs_host status {rc}")
 
-    def e2e_step(k):
-        host_policy(k)
-        eng.step_host(hb, DT)
-        if use_nccl:
-            sg.gather()
-            torch.cuda.current_stream(dev).synchronize()
+        def one(k):
+            host_policy(k)
+            eng.step_host(hb, w.dt)
+            if w.use_nccl:
+                w.sg.gather()
+                torch.cuda.current_stream(dev).synchronize()
 
-    hb["vis_est"].copy_(eng.vis_est)
-    for k in range(args.warmup):
-        e2e_step(k)
-    barrier()
-    e2e_wall = 0.0
-    for k0 in range(0, args.steps, EPISODE):            # episodes of EPISODE steps; the reset between them is untimed
-        if k0:
-            eng.reset()
-            eng.ensure_sigma()
-            hb["vis_est"].copy_(eng.vis_est)
-            torch.cuda.synchronize(dev)
-        tw = time.perf_counter()
-        for k in range(k0, min(args.steps, k0 + EPISODE)):
-            e2e_step(args.warmup + k)
-        e2e_wall += time.perf_counter() - tw            # every step ends in a stream synchronise
-    barrier()
-    e2e_ms = torch.tensor([e2e_wall * 1e3], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(e2e_ms, op=dist.ReduceOp.MAX)
-    e2e_value = world * N * args.steps / (float(e2e_ms.item()) * 1e-3)
-    e2e = {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(M * 8),
-           "d2h_bytes_per_step": int(hb["block"].numel()),     # float32 obs | num_tasked | packed vis | traces, one copy
-           "ms_per_step": float(e2e_ms.item()) / args.steps,
-           "path": "host policy (pc_policy_random_visible_host on the previous step's packed map) -> CatalogEngine.step_host -> pc_step_host: pinned host actions "
-                   "-> [CUDA graph: H2D actions, pc_step_fused + pc_obs_pack] -> output block (float32 obs | num_tasked | packed vis "
-                   "map | covariance traces | last_time_tasked) in pinned host memory, stream sync; timed by the host clock "
-                   "around the loop.  Up to 32768 targets x 256 sensors per GPU and without a peer exchange the kernels store "
-                   "the block into the (mapped) host buffer themselves while they run (zero-copy form of pc_step_host, every "
-                   "byte rewritten every step); otherwise ONE device-to-host copy node at the end of the graph"}
+        hb["vis_est"].copy_(eng.vis_est)
+        for k in range(warmup):
+            one(k)
+        barrier()
+        wall_s = 0.0
+        for k0 in range(0, steps, EPISODE):            # episodes of EPISODE steps; the reset between them is untimed
+            if k0:
+                eng.reset()
+                eng.ensure_sigma()
+                hb["vis_est"].copy_(eng.vis_est)
+                torch.cuda.synchronize(dev)
+            tw = time.perf_counter()
+            for k in range(k0, min(steps, k0 + EPISODE)):
+                one(warmup + k)
+            if eng._peer is not None:                   # the last step's exchange completes inside the timed region
+                eng.peer_sync()
+                torch.cuda.current_stream(dev).synchronize()
+            wall_s += time.perf_counter() - tw          # every step ends in a stream synchronise
+        barrier()
+        ms = max_over_ranks(wall_s * 1e3) / steps
+        return ms, hb
+
+    e2e_ms, hb = e2e_pass(head, args.steps, args.warmup)
+    e2e = {"value": world * N / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": int(M * 8),
+           "d2h_bytes_per_step": int(hb["block"].numel()),     # float32 obs | num_tasked | packed vis | traces, one block
+           "ms_per_step": e2e_ms, "host_cores_of_this_rank": pinned_cores,
+           "path": "host policy (pc_policy_random_visible_host on the previous step's packed map) -> CatalogEngine.step_host -> "
+                   "pc_step_host: pinned host actions -> [CUDA graph: H2D actions, pc_step_fused + pc_obs_pack] -> output block "
+                   "(float32 obs | num_tasked | packed vis map | covariance traces | last_time_tasked) in pinned host memory, "
+                   "stream sync; timed by the host clock around the loop.  Up to 32768 targets x 256 sensors per GPU the kernels "
+                   "store the block into the (mapped) host buffer themselves while they run (zero-copy form of pc_step_host, "
+                   "every byte rewritten every step; also beside a peer exchange); otherwise ONE device-to-host copy node "
+                   "at the end of the graph"}
+    head_exchange = head.exchange
+    del head, hb
+    torch.cuda.empty_cache()
+
+    # ------------------------------------------------------------------ the other BASELINE.json configurations
+    # (driver-visible numbers for the north-star sizes; fewer steps, same timing rules)
+    extra_cfgs = {}
+    if not args.no_extra_configs:
+        xs = max(20, min(100, args.steps))
+
+        def run_extra(key, desc, n, m, dt, total_units, unit_name, **kw):
+            w = Workload(n, m, dt, SEED + 7, **kw)
+            w.build()
+            ms, _, nl = w.timed(xs, args.warmup)
+            p2, f2, note2, tf2, bad2, _ = roofline_kernels(w, 0, args.warmup, min(20, xs))
+            e_ms, hb2 = e2e_pass(w, min(xs, 50), args.warmup)
+            out = {"workload": desc, "targets_per_gpu": n, "sensors": m, "dt_s": dt, "steps": xs, "ms_per_step": ms,
+                   "target_steps_per_s": world * n / (ms * 1e-3), "scaling": "weak",
+                   "launches_per_step": nl / xs, "exchange": w.exchange, "tasked_fraction": tf2, "flagged_targets": bad2,
+                   "e2e_ms_per_step": e_ms, "e2e_target_steps_per_s": world * n / (e_ms * 1e-3),
+                   "e2e_d2h_bytes_per_step": int(hb2["block"].numel()),
+                   "roofline": [p2, f2]}
+            if unit_name:
+                out[unit_name] = total_units / (ms * 1e-3)
+            extra_cfgs[key] = out
+            del w, hb2
+            torch.cuda.empty_cache()
+
+        run_extra("c4_shard", "BASELINE.json configs[3] shard: 125 000 debris targets per GPU x 100 sensors, 60 s steps "
+                  "(8 GPUs = the 1 M-object catalog)", 125_000, 100, 60.0, 0, None)
+        n5 = 100_000 // world
+        run_extra("c5", f"BASELINE.json configs[4]: 100 000 targets in total ({n5} per GPU), full 6x6 predict + measurement "
+                  "UPDATE on every target every step, 60 s steps", n5, 100, 60.0, 0, None, all_tasked=True)
+        extra_cfgs["c5"]["scaling"] = "strong"
+        extra_cfgs["c5"]["targets_total"] = n5 * world
+        e3 = 1024 // world
+        run_extra("c3", f"BASELINE.json configs[2]: 1024 vectorised SSAScheduler envs x 100 targets x 10 sensors in total "
+                  f"({e3} envs per GPU, independent replicas), dt = 100 s", e3 * 100, e3 * 10, 100.0, 1024, "env_steps_per_s",
+                  num_envs=e3, mix="LEO")
+        extra_cfgs["c3"]["scaling"] = "strong"
+        extra_cfgs["c3"]["e2e_env_steps_per_s"] = 1024 / (extra_cfgs["c3"]["e2e_ms_per_step"] * 1e-3)
 
     def leave():
         # Ranks leave together and without tearing NCCL down: destroying a process group whose
@@ -501,9 +670,10 @@ def run_own(args):
         leave()
         return
 
-    # ---------------- CPU baseline beside it (rank 0, N = 1 only) ----------------
+    # ------------------------------------------------------------------ CPU baseline beside it (rank 0, N = 1 only)
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
+        cat = synth_catalog(N, M, seed=SEED, sensor_seed=SEED)
         cores = host_cores()
         sample = min(N, max(cores, (args.cpu_sample_per_core or 640) * cores))    # ~15 s of CPU work
         v, s_step, sample = cpu_reference_run(cat, sample, 1, 0, cores)
@@ -515,10 +685,10 @@ def run_own(args):
             "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": workload_config(N, M),
             "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu, "clocks": clocks,
-            "extra": {"tasked_per_step": tasked_total / total_steps, "flagged_targets": flags_bad,
+            "extra": {"tasked_per_step": tasked_frac * N, "flagged_targets": flags_bad,
                       "wall_s_timed_region": wall, "launches_per_step": launches / args.steps, "cuda_graph": True,
-                      "exchange": exchange,
-                      "target_propagation_steps_per_s": 14 * value}}
+                      "exchange": head_exchange, "target_propagation_steps_per_s": 14 * value,
+                      "configs": extra_cfgs}}
     emit(line)
     leave()
 
@@ -534,10 +704,10 @@ def main():
     ap.add_argument("--substeps", type=int, default=0)
     ap.add_argument("--cpu-sample-per-core", type=int, default=0, help="0 = sized for the time budget")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extra-configs", action="store_true",
+                    help="skip the BASELINE.json configs[2..4] passes reported under extra.configs")
     ap.add_argument("--l2", default="flush", choices=["flush", "none"])
     ap.add_argument("--eager-gather", action="store_true", help="N > 1: all-gather outside the step's CUDA graph")
-    ap.add_argument("--peer-push", default="auto", choices=["auto", "store", "copy"],
-                    help="N > 1, peer exchange: stores from the per-target kernel or a copy kernel behind it (auto: size rule)")
     ap.add_argument("--exchange", default="auto", choices=["auto", "peer", "nccl"],
                     help="N > 1: summaries pushed into peers' memory by the step kernel, or one NCCL all-gather")
     args = ap.parse_args()

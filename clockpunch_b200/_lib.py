@@ -16,7 +16,7 @@ PC_OK, PC_ERR_BAD_ARG, PC_ERR_CUDA, PC_ERR_EQUAL_TIMES, PC_ERR_NO_DEVICE = 0, -1
 KIND_SATELLITE, KIND_TERRESTRIAL = 0, 1
 FORCE_TWOBODY, FORCE_TWOBODY_J2 = 0, 1
 FLAG_NONPD_EST, FLAG_NONPD_PRED, FLAG_NONPD_INNOV, FLAG_NONFINITE, FLAG_SUBSTEP_CLAMP = 1, 2, 4, 8, 16
-OPT_FINISH_KERNEL, OPT_PROPAGATE_KERNEL, OPT_PEER_PUSH = 1, 2, 3          # pc_option
+OPT_FINISH_KERNEL, OPT_PROPAGATE_KERNEL = 1, 2          # pc_option
 FINISH_AUTO, FINISH_QUAD_UPDATE_WARPS, FINISH_QUAD_INLINE, FINISH_THREAD_64, FINISH_THREAD_128 = 0, 1, 2, 3, 4
 COMM_HANDLE_BYTES = 64
 
@@ -102,17 +102,20 @@ _SIGNATURES = {
     "pc_obs_pack": ([_vp, _vp, _i64, _i64, _vp, _vp, _i64, _i64, _vp, _dbl, _vp, _vp, _vp, _vp, _vp], _int),
     "pc_policy_random_visible": ([_vp, _vp, _i64, _i64, _i64, _u64, _u64, _vp, _int, _vp, _vp], _int),
     "pc_policy_random_visible_host": ([_vp, _i64, _i64, _i64, _u64, _u64, _int, _vp], _int),
+    "pc_policy_random_visible_envs_host": ([_vp, _i64, _i64, _i64, _i64, _u64, _u64, _int, _vp], _int),
     "pc_set_timing": ([_vp, _int], _int),
     "pc_get_timing": ([_vp, C.POINTER(_dbl)], _int),
+    "pc_get_kernel_timing": ([_vp, C.POINTER(_dbl), C.POINTER(_dbl)], _int),
     "pc_fp64_peak": ([_vp, _int, C.POINTER(_dbl)], _int),
     "pc_step_fused": ([_vp, C.POINTER(StepArgs), C.POINTER(UkfParams), _vp], _int),
     "pc_peer_status": ([_vp, C.POINTER(C.c_uint32), C.POINTER(C.c_uint64)], _int),
-    "pc_peer_wait": ([_vp, _vp, C.c_int32, C.c_int32, _vp], _int),
+    "pc_peer_exchange": ([_vp, _vp, C.c_int32, C.c_int32, _vp, _i64, _vp], _int),
     "pc_comm_init": ([_vp, C.c_int32, C.c_int32, _i64, _vp], _int),
     "pc_comm_attach": ([_vp, _vp], _int),
     "pc_comm_table": ([_vp, C.POINTER(_vp), C.POINTER(_vp), C.POINTER(C.c_int32), C.POINTER(C.c_int32),
                        C.POINTER(_i64)], _int),
     "pc_allgather_step": ([_vp, _vp, _vp], _int),
+    "pc_comm_detach": ([_vp], _int),
     "pc_comm_destroy": ([_vp], _int),
     "pc_step_host": ([_vp, C.POINTER(StepArgs), C.POINTER(UkfParams), C.POINTER(StepIO), _vp], _int),
 }

@@ -30,9 +30,7 @@ cudaError_t launch_pre_step(double* sens_x, const uint8_t* sens_kind, int64_t M,
                             double body_radius, double vis_tol, pc_clock* clock, int64_t* actions,
                             const uint32_t* vis_est, uint8_t* tasked, int64_t N, int64_t wpr,
                             int probes, uint64_t seed, uint64_t step, int64_t env_targets,
-                            int64_t env_sensors, int64_t* task_of, const uint64_t* peer_table,
-                            int peer_world, int peer_rank, const unsigned long long* peer_seq,
-                            unsigned int* peer_err, cudaStream_t s);
+                            int64_t env_sensors, int64_t* task_of, const PeerPush& pp, cudaStream_t s);
 
 cudaError_t launch_frame_change(const double*, double*, int64_t, int64_t, double, double, cudaStream_t);
 cudaError_t launch_coe2eci(const double*, double*, int64_t, int64_t, double, cudaStream_t);
@@ -64,7 +62,7 @@ struct pc_ctx {
   size_t sb_states = 0;
   // optional per-kernel timing of pc_step_fused (bench.py roofline leg)
   bool timing = false;
-  cudaEvent_t ev0 = nullptr, ev1 = nullptr;  // around the UKF kernel
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev2 = nullptr;  // before / between / after the propagation and the per-target kernel
   // sensor positions + horizon terms for the fused visibility phase when the caller brings no
   // pc_step_args.sens_q (not graph-capture safe)
   double* sq = nullptr;
@@ -90,7 +88,7 @@ struct pc_ctx {
   const void* hs_zc_ptr = nullptr;   // last host block checked for device accessibility (zero-copy form)
   bool hs_zc_ok = false;
   // kernel-mapping overrides (pc_set_option)
-  int opt_finish = 0, opt_prop = 0, opt_peer = 0;
+  int opt_finish = 0, opt_prop = 0;
   // pc_comm_*: this rank's gathered buffer + flags (one cudaMalloc, shared by CUDA IPC), the peers'
   // mappings and the device table pc_step_args.peer_table points at
   struct Comm {
@@ -208,6 +206,7 @@ int pc_ctx_destroy(pc_ctx* ctx) {
     if (ctx->peer_dev) cudaFree(ctx->peer_dev);
     if (ctx->ev0) cudaEventDestroy(ctx->ev0);
     if (ctx->ev1) cudaEventDestroy(ctx->ev1);
+    if (ctx->ev2) cudaEventDestroy(ctx->ev2);
     for (auto& e : ctx->hs)
       if (e.exec) cudaGraphExecDestroy(e.exec);
     pc_comm_destroy(ctx);
@@ -223,7 +222,6 @@ static int* option_slot(pc_ctx* ctx, int option, int* max_value) {
   switch (option) {
     case PC_OPT_FINISH_KERNEL: *max_value = 4; return &ctx->opt_finish;
     case PC_OPT_PROPAGATE_KERNEL: *max_value = 2; return &ctx->opt_prop;
-    case PC_OPT_PEER_PUSH: *max_value = 2; return &ctx->opt_peer;
     default: return nullptr;
   }
 }
@@ -753,6 +751,28 @@ int pc_policy_random_visible_host(const uint32_t* vis_est, int64_t N, int64_t M,
   return PC_OK;
 }
 
+int pc_policy_random_visible_envs_host(const uint32_t* vis_est, int64_t E, int64_t env_targets, int64_t env_sensors,
+                                       int64_t words_per_row, uint64_t seed, uint64_t step, int probes,
+                                       int64_t* actions) {
+  if (E <= 0 || env_targets <= 0 || env_sensors < 0 || probes < 0 || words_per_row != (env_sensors + 31) / 32)
+    return PC_ERR_BAD_ARG;
+  if (env_sensors > 0 && (!vis_est || !actions)) return PC_ERR_BAD_ARG;
+  for (int64_t j = 0; j < E * env_sensors; ++j) {   // the tasking warps of pre_step_kernel, one sensor at a time
+    const int64_t e = j / env_sensors, jl = j - e * env_sensors, t0 = e * env_targets;
+    const uint64_t base = splitmix64_host(seed ^ splitmix64_host(step * 0x100000001B3ull + (uint64_t)j));
+    int64_t pick = env_targets;
+    for (int k = 0; k < probes; ++k) {
+      const int64_t i = (int64_t)(splitmix64_host(base + (uint64_t)k) % (uint64_t)env_targets);
+      if ((vis_est[(t0 + i) * words_per_row + (jl >> 5)] >> (jl & 31)) & 1u) {
+        pick = i;
+        break;
+      }
+    }
+    actions[j] = pick;
+  }
+  return PC_OK;
+}
+
 /* ---- measurement helpers ------------------------------------------------ */
 int pc_set_timing(pc_ctx* ctx, int enabled) {
   PC_REQUIRE(ctx, ctx != nullptr, "null context");
@@ -760,6 +780,7 @@ int pc_set_timing(pc_ctx* ctx, int enabled) {
   if (enabled && !ctx->ev0) {
     PC_CUDA_TRY(ctx, cudaEventCreate(&ctx->ev0));
     PC_CUDA_TRY(ctx, cudaEventCreate(&ctx->ev1));
+    PC_CUDA_TRY(ctx, cudaEventCreate(&ctx->ev2));
   }
   ctx->timing = enabled != 0;
   return PC_OK;
@@ -773,6 +794,19 @@ int pc_get_timing(pc_ctx* ctx, double* ukf_ms_last) {
   PC_CUDA_TRY(ctx, cudaEventSynchronize(ctx->ev1));
   PC_CUDA_TRY(ctx, cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
   *ukf_ms_last = ms;
+  return PC_OK;
+}
+
+int pc_get_kernel_timing(pc_ctx* ctx, double* propagate_ms_last, double* finish_ms_last) {
+  PC_REQUIRE(ctx, ctx != nullptr && propagate_ms_last && finish_ms_last, "null pointer");
+  PC_REQUIRE(ctx, ctx->ev0 != nullptr, "timing was never enabled");
+  DeviceGuard g(ctx->device);
+  float a = 0.f, b = 0.f;
+  PC_CUDA_TRY(ctx, cudaEventSynchronize(ctx->ev2));
+  PC_CUDA_TRY(ctx, cudaEventElapsedTime(&a, ctx->ev0, ctx->ev1));
+  PC_CUDA_TRY(ctx, cudaEventElapsedTime(&b, ctx->ev1, ctx->ev2));
+  *propagate_ms_last = a;
+  *finish_ms_last = b;
   return PC_OK;
 }
 
@@ -835,14 +869,13 @@ int pc_step_fused(pc_ctx* ctx, const pc_step_args* a, const pc_ukf_params* param
   if (a->peer_table) {
     PC_REQUIRE(ctx, a->peer_world >= 1 && a->peer_world <= 64 && a->peer_rank >= 0 && a->peer_rank < a->peer_world,
                "bad peer_world / peer_rank");
-    PC_REQUIRE(ctx, a->summary_base && a->summary_bytes > 0 && a->num_tasked && a->vis_est && a->tr_pos &&
-                        a->tr_vel && a->last_time_tasked,
-               "peer push needs the summary buffer and all five summary arrays");
-    const char* b0 = static_cast<const char*>(a->summary_base);
-    const char* b1 = b0 + a->summary_bytes;
-    const char* f[5] = {(const char*)a->num_tasked, (const char*)a->vis_est, (const char*)a->tr_pos,
-                        (const char*)a->tr_vel, (const char*)a->last_time_tasked};
-    for (const char* q : f) PC_REQUIRE(ctx, q >= b0 && q < b1, "summary arrays must lie inside summary_base");
+    PC_REQUIRE(ctx, a->summary_base && a->summary_bytes > 0 && a->summary_bytes % 4 == 0 &&
+                        reinterpret_cast<uintptr_t>(a->summary_base) % 16 == 0,
+               "peer push needs a 16-byte aligned summary buffer whose size is a multiple of 4");
+    PC_REQUIRE(ctx, !(ctx->comm.attached && a->peer_table == ctx->comm.table) ||
+                        (a->summary_bytes == ctx->comm.slot_bytes && a->peer_world == ctx->comm.world &&
+                         a->peer_rank == ctx->comm.rank),
+               "summary_bytes / peer_world / peer_rank differ from what pc_comm_init was given");
   }
   const bool own_sb = a->sigma_ws != nullptr;
   if (own_sb && a->N > 0) {
@@ -869,17 +902,26 @@ int pc_step_fused(pc_ctx* ctx, const pc_step_args* a, const pc_ukf_params* param
   //    tasking mask from the actions and the PREVIOUS estimated vis map, step clock latch.
   //    Independent of the target propagation, which is launched programmatically behind it and
   //    therefore runs beside it (no fork / join, no second stream).
-  //    Multi-GPU: the same kernel waits for the peers' summaries of the PREVIOUS step (see PeerPush).
-  const bool pre = a->M > 0 || a->clock || (a->peer_table && a->N > 0);
+  //    Multi-GPU: the same kernel pushes the summaries the PREVIOUS step left in the summary buffer into
+  //    every peer and waits for the peers' pushes (see PeerPush): the exchange runs beside the propagation.
+  pc::PeerPush pp{};
+  if (a->peer_table && a->N > 0) {
+    pp.world = a->peer_world;
+    pp.rank = a->peer_rank;
+    pp.table = a->peer_table;
+    pp.src = a->summary_base;
+    pp.bytes = a->summary_bytes;
+    pp.ticket = ctx->peer_dev;
+    pp.epoch = reinterpret_cast<unsigned long long*>(ctx->peer_dev + 2);
+    pp.err = ctx->peer_dev + 1;
+  }
+  const bool pre = a->M > 0 || a->clock || pp.world > 0;
   if (pre) {
     PC_CUDA_TRY(ctx, pc::launch_pre_step(a->sens_x, a->sens_kind, a->M, a->ld_s, a->t0, a->tf, a->substeps,
                                          a->force_model, fuse_vis ? sq : nullptr, a->body_radius, a->vis_tol,
                                          a->clock, a->actions, a->vis_est, const_cast<uint8_t*>(a->tasked),
                                          a->N, a->words_per_row, a->policy_probes, a->policy_seed,
-                                         a->rng_step, Ne, Me, a->actions ? a->task_of : nullptr,
-                                         a->N > 0 ? a->peer_table : nullptr, a->peer_world, a->peer_rank,
-                                         reinterpret_cast<const unsigned long long*>(ctx->peer_dev + 2),
-                                         ctx->peer_dev + 1, s));
+                                         a->rng_step, Ne, Me, a->actions ? a->task_of : nullptr, pp, s));
     ctx->launches += 1;
   }
   // 2. targets: sigma points (only when not carried over from the previous step), all 14 N
@@ -959,42 +1001,13 @@ int pc_step_fused(pc_ctx* ctx, const pc_step_args* a, const pc_ukf_params* param
       u.body_radius = a->body_radius;
       u.vis_tol = a->vis_tol;
     }
-    // Two forms of the peer push.  Latency-bound shards (<= 32 k targets): the per-target kernel stores
-    // every summary value into all peers as it produces it.  Larger shards: it only fills the local
-    // summary buffer and a copy kernel, launched programmatically behind it, pushes the buffer with
-    // 16-byte stores (a shard then moves megabytes per step; per-thread 4-byte stores to 8 peers
-    // lose to a streaming copy: 0.307 vs 0.264 ms at 8 x 125 k targets, NCCL all-gather 0.287 ms).
-    // (8 peers: 72 remote 4-byte stores per target from the latency-critical kernel lose to the copy
-    // kernel also at 10 k targets per shard, 55.0 vs 57.2 us per step.)  pc_option PC_OPT_PEER_PUSH pins it.
-    const bool peer_copy = ctx->opt_peer == 2 || (ctx->opt_peer == 0 && (a->N > 32768 || a->peer_world >= 8));
-    pc::PeerPush pp_copy{};
-    if (a->peer_table) {
-      const char* base = static_cast<const char*>(a->summary_base);
-      u.pp.world = a->peer_world;
-      u.pp.rank = a->peer_rank;
-      u.pp.table = a->peer_table;
-      u.pp.slot_bytes = a->summary_bytes;
-      u.pp.off_num_tasked = reinterpret_cast<const char*>(a->num_tasked) - base;
-      u.pp.off_vis_est = reinterpret_cast<const char*>(a->vis_est) - base;
-      u.pp.off_tr_pos = reinterpret_cast<const char*>(a->tr_pos) - base;
-      u.pp.off_tr_vel = reinterpret_cast<const char*>(a->tr_vel) - base;
-      u.pp.off_ltt = reinterpret_cast<const char*>(a->last_time_tasked) - base;
-      u.pp.ticket = ctx->peer_dev;
-      u.pp.seq = reinterpret_cast<unsigned long long*>(ctx->peer_dev + 2);
-      if (peer_copy && a->summary_bytes % 16 == 0) {
-        pp_copy = u.pp;
-        u.pp = pc::PeerPush{};
-      }
-    }
+    u.peer_epoch = pp.world > 0 ? pp.epoch : nullptr;
     u.variant = ctx->opt_finish;
     u.p = *params;
     PC_CUDA_TRY(ctx, pc::launch_ukf_finish(u, s));
+    if (ctx->timing) PC_CUDA_TRY(ctx, cudaEventRecordWithFlags(ctx->ev2, s, evflags));
     ctx->launches += 2;
-    if (pp_copy.world) {
-      PC_CUDA_TRY(ctx, pc::launch_peer_push(a->summary_base, a->summary_bytes, pp_copy, true, s));
-      ctx->launches += 1;
-    }
-    // (no wait here: the next step's sensor kernel waits for the peers, beside its propagation)
+    // (no exchange here: the next step's sensor kernel pushes these summaries and waits for the peers')
   } else if (a->clock) {
     PC_CUDA_TRY(ctx, pc::launch_advance_clock(a->clock, a->tf - a->t0, s));
     ctx->launches += 1;
@@ -1013,16 +1026,27 @@ int pc_peer_status(pc_ctx* ctx, uint32_t* out_error_mask, uint64_t* out_pushes) 
   return PC_OK;
 }
 
-int pc_peer_wait(pc_ctx* ctx, const uint64_t* peer_table, int32_t peer_world, int32_t peer_rank,
-                 pc_stream stream) {
-  PC_REQUIRE(ctx, ctx != nullptr && peer_table != nullptr, "null pointer");
+int pc_peer_exchange(pc_ctx* ctx, const uint64_t* peer_table, int32_t peer_world, int32_t peer_rank,
+                     const void* summary, int64_t summary_bytes, pc_stream stream) {
+  PC_REQUIRE(ctx, ctx != nullptr && peer_table != nullptr && summary != nullptr, "null pointer");
   PC_REQUIRE(ctx, peer_world >= 1 && peer_world <= 64 && peer_rank >= 0 && peer_rank < peer_world,
              "bad peer_world / peer_rank");
+  PC_REQUIRE(ctx, summary_bytes > 0 && summary_bytes % 4 == 0 && reinterpret_cast<uintptr_t>(summary) % 16 == 0,
+             "the summary buffer must be 16-byte aligned and a multiple of 4 bytes long");
   DeviceGuard g(ctx->device);
-  PC_CUDA_TRY(ctx, pc::launch_peer_wait(peer_table, peer_world, peer_rank,
-                                        reinterpret_cast<const unsigned long long*>(ctx->peer_dev + 2),
-                                        ctx->peer_dev + 1, false, (cudaStream_t)stream));
-  ctx->launches += 1;
+  cudaStream_t s = (cudaStream_t)stream;
+  pc::PeerPush pp{};
+  pp.world = peer_world;
+  pp.rank = peer_rank;
+  pp.table = peer_table;
+  pp.src = summary;
+  pp.bytes = summary_bytes;
+  pp.ticket = ctx->peer_dev;
+  pp.epoch = reinterpret_cast<unsigned long long*>(ctx->peer_dev + 2);
+  pp.err = ctx->peer_dev + 1;
+  PC_CUDA_TRY(ctx, pc::launch_peer_push(pp, s));
+  PC_CUDA_TRY(ctx, pc::launch_peer_wait(peer_table, peer_world, peer_rank, pp.epoch, pp.err, 1, s));
+  ctx->launches += 2;
   return PC_OK;
 }
 
@@ -1097,24 +1121,10 @@ int pc_allgather_step(pc_ctx* ctx, const void* summary, pc_stream stream) {
   PC_REQUIRE(ctx, ctx != nullptr && summary != nullptr, "null pointer");
   auto& c = ctx->comm;
   PC_REQUIRE(ctx, c.attached, "no attached peer exchange on this context");
-  PC_REQUIRE(ctx, c.slot_bytes % 16 == 0 && reinterpret_cast<uintptr_t>(summary) % 16 == 0,
-             "pc_allgather_step needs a 16-byte aligned summary buffer and size");
-  DeviceGuard g(ctx->device);
-  cudaStream_t s = (cudaStream_t)stream;
-  pc::PeerPush pp{};
-  pp.world = c.world;
-  pp.rank = c.rank;
-  pp.table = c.table;
-  pp.slot_bytes = c.slot_bytes;
-  pp.ticket = ctx->peer_dev;
-  pp.seq = reinterpret_cast<unsigned long long*>(ctx->peer_dev + 2);
-  PC_CUDA_TRY(ctx, pc::launch_peer_push(summary, c.slot_bytes, pp, false, s));
-  PC_CUDA_TRY(ctx, pc::launch_peer_wait(c.table, c.world, c.rank, pp.seq, ctx->peer_dev + 1, false, s));
-  ctx->launches += 2;
-  return PC_OK;
+  return pc_peer_exchange(ctx, c.table, c.world, c.rank, summary, c.slot_bytes, stream);
 }
 
-int pc_comm_destroy(pc_ctx* ctx) {
+int pc_comm_detach(pc_ctx* ctx) {
   if (!ctx) return PC_OK;
   auto& c = ctx->comm;
   if (!c.base) return PC_OK;
@@ -1122,7 +1132,19 @@ int pc_comm_destroy(pc_ctx* ctx) {
   cudaDeviceSynchronize();
   for (int r = 0; r < (int)c.opened.size(); ++r)
     if (r != c.rank && c.opened[r]) cudaIpcCloseMemHandle(c.opened[r]);
+  c.opened.clear();
   if (c.table) cudaFree(c.table);
+  c.table = nullptr;
+  c.attached = false;
+  return PC_OK;
+}
+
+int pc_comm_destroy(pc_ctx* ctx) {
+  if (!ctx) return PC_OK;
+  auto& c = ctx->comm;
+  if (!c.base) return PC_OK;
+  pc_comm_detach(ctx);
+  DeviceGuard g(ctx->device);
   cudaFree(c.base);
   c = pc_ctx::Comm{};
   return PC_OK;

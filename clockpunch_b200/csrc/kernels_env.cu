@@ -5,6 +5,7 @@
 //   * float32 observation buffers exactly as SSAScheduler emits them
 //     (getEstStates env.py:508-530, est_cov env.py:419-429, obs_staleness env.py:446-452)
 #include "propagate.cuh"
+#include "ukf_args.cuh"
 #include "vis.cuh"
 
 namespace pc {
@@ -157,11 +158,13 @@ cudaError_t launch_advance_clock(pc_clock* clock, double dt, cudaStream_t s) {
 //       stand-in policy: the first of `probes` random targets its column of the PREVIOUS
 //       estimated map shows visible, probed 32 at a time) marks tasked[target]
 //   block 0 thread 0 also latches the step clock (t_cur / step_cur) for the kernels that follow.
-//   Multi-GPU: thread r of block 0 then waits (bounded) until peer r's summaries of the PREVIOUS step
-//   have all arrived in this rank's gathered buffer.  The target propagation runs beside this kernel
-//   and only the per-target stage waits for it, so the exchange of step k overlaps the propagation
-//   of step k + 1 instead of ending step k; it also orders this rank's next push (into the slot of
-//   parity k + 1) behind every peer's reads of that slot.
+//   Multi-GPU: blocks [nb_sens + nb_task, ...) copy this rank's summary buffer -- the per-target
+//   summaries the PREVIOUS step left there -- into every peer's gathered buffer and publish the push
+//   number; thread r of block 0 then waits (bounded) until peer r's push of the same number has arrived.
+//   The target propagation runs beside this kernel and only the per-target stage waits for it, so the
+//   whole exchange of step k overlaps the propagation of step k + 1 instead of ending step k.  (A
+//   peer that is a step ahead writes the OTHER parity slot; it cannot be two steps ahead, because its
+//   own wait needs this rank's push of the step in between.)
 struct PreStepArgs {
   double* sens_x;
   const uint8_t* sens_kind;
@@ -182,11 +185,10 @@ struct PreStepArgs {
   int nb_sens;
   int64_t env_targets, env_sensors;  // batch of environments (single catalog: N, M)
   int64_t* task_of;         // may be NULL; [j] = global index of the target sensor j validly tasks, else -1
-  // multi-GPU (peer_world == 0: off): wait here for every peer's push of the PREVIOUS step
-  const uint64_t* peer_table;
-  int peer_world, peer_rank;
-  const unsigned long long* peer_seq;
-  unsigned int* peer_err;
+  // multi-GPU (pp.world == 0: off): push the summaries of the PREVIOUS step into every peer (blocks
+  // [nb_sens + nb_task, + nb_push)) and wait for every peer's push (threads [0, world) of block 0)
+  PeerPush pp;
+  int nb_task, nb_push;
 };
 
 template <bool J2>
@@ -220,8 +222,12 @@ pre_step_kernel(const __grid_constant__ PreStepArgs a) {
       if (a.sens_q)
         a.sens_q[j] = make_double4(r[0], r[1], r[2], horizon_q(r[0], r[1], r[2], a.body_radius, a.vis_tol));
     }
-    if (blockIdx.x == 0 && (int)threadIdx.x < a.peer_world)
-      peer_wait_thread(a.peer_table, a.peer_world, a.peer_rank, a.peer_seq, a.peer_err, (int)threadIdx.x);
+    if (blockIdx.x == 0 && (int)threadIdx.x < a.pp.world)
+      peer_wait_thread(a.pp.table, a.pp.world, a.pp.rank, a.pp.epoch, a.pp.err, (int)threadIdx.x);
+    return;
+  }
+  if ((int)blockIdx.x >= a.nb_sens + a.nb_task) {
+    peer_push_block(a.pp, (int)blockIdx.x - a.nb_sens - a.nb_task, a.nb_push);
     return;
   }
   // tasking: sensor j of environment e = j / env_sensors addresses that environment's targets
@@ -262,17 +268,11 @@ cudaError_t launch_pre_step(double* sens_x, const uint8_t* sens_kind, int64_t M,
                             double body_radius, double vis_tol, pc_clock* clock, int64_t* actions,
                             const uint32_t* vis_est, uint8_t* tasked, int64_t N, int64_t wpr,
                             int probes, uint64_t seed, uint64_t step, int64_t env_targets,
-                            int64_t env_sensors, int64_t* task_of, const uint64_t* peer_table,
-                            int peer_world, int peer_rank, const unsigned long long* peer_seq,
-                            unsigned int* peer_err, cudaStream_t s) {
-  if (M <= 0 && clock == nullptr && peer_world <= 0) return cudaSuccess;
+                            int64_t env_sensors, int64_t* task_of, const PeerPush& pp, cudaStream_t s) {
+  if (M <= 0 && clock == nullptr && pp.world <= 0) return cudaSuccess;
   PreStepArgs a;
   a.task_of = task_of;
-  a.peer_table = peer_table;
-  a.peer_world = peer_table ? peer_world : 0;
-  a.peer_rank = peer_rank;
-  a.peer_seq = peer_seq;
-  a.peer_err = peer_err;
+  a.pp = pp;
   a.env_targets = env_targets > 0 ? env_targets : N;
   a.env_sensors = env_sensors > 0 ? env_sensors : M;
   a.sens_x = sens_x;
@@ -297,11 +297,13 @@ cudaError_t launch_pre_step(double* sens_x, const uint8_t* sens_kind, int64_t M,
   a.step_arg = step;
   a.nb_sens = (int)((M + 127) / 128);
   if (a.nb_sens < 1) a.nb_sens = 1;
-  const int nb_task = actions ? (int)((M + 3) / 4) : 0;
+  a.nb_task = actions ? (int)((M + 3) / 4) : 0;
+  a.nb_push = pp.world > 0 ? peer_push_blocks(pp.bytes) : 0;
+  const int blocks = a.nb_sens + a.nb_task + a.nb_push;
   if (force_model == PC_FORCE_TWOBODY_J2)
-    pre_step_kernel<true><<<a.nb_sens + nb_task, 128, 0, s>>>(a);
+    pre_step_kernel<true><<<blocks, 128, 0, s>>>(a);
   else
-    pre_step_kernel<false><<<a.nb_sens + nb_task, 128, 0, s>>>(a);
+    pre_step_kernel<false><<<blocks, 128, 0, s>>>(a);
   return cudaGetLastError();
 }
 

@@ -88,9 +88,10 @@ propagate_sigma_single_kernel(double* __restrict__ sb, int64_t n, int64_t ld, do
   // sensor / tasking kernel), so it runs beside it; its successor (the per-target stage) may be
   // scheduled as soon as every CTA of this grid is resident.  One thread of the grid does wait for
   // the predecessor, so that "this grid is done" implies "the sensor kernel is done" for the
-  // successor, which needs both.
+  // successor, which needs both -- thread 0 of the LAST CTA, AFTER its own work: a CTA that waited
+  // first and worked afterwards ended late whenever the sensor kernel is long (it carries the
+  // multi-GPU exchange) and stretched this kernel by that much (4.7 us per step at 2 GPUs).
   pdl_trigger();
-  if (blockIdx.x == 0 && blockIdx.y == 0 && tid == 0) pdl_wait();
   const int64_t t0 = (int64_t)blockIdx.x * kPropThreads;
   const int i = blockIdx.y;
   double* blk = sb + (int64_t)i * 6 * ld;
@@ -134,23 +135,25 @@ propagate_sigma_single_kernel(double* __restrict__ sb, int64_t n, int64_t ld, do
     __syncthreads();
     slot = s_perm[tid];
     nsub = s_nsub[slot];
-    if (nsub == 0) return;  // past the end of the catalog
   } else if (t0 + tid >= n) {
-    return;
+    nsub = 0;
   }
-  double* base = blk + t0 + slot;
-  double r[3], v[3];
+  if (nsub != 0) {  // 0: past the end of the catalog
+    double* base = blk + t0 + slot;
+    double r[3], v[3];
 #pragma unroll
-  for (int c = 0; c < 3; ++c) {
-    r[c] = base[(int64_t)c * ld];
-    v[c] = base[(int64_t)(c + 3) * ld];
-  }
-  propagate_state<J2>(r, v, dt, nsub);
+    for (int c = 0; c < 3; ++c) {
+      r[c] = base[(int64_t)c * ld];
+      v[c] = base[(int64_t)(c + 3) * ld];
+    }
+    propagate_state<J2>(r, v, dt, nsub);
 #pragma unroll
-  for (int c = 0; c < 3; ++c) {
-    base[(int64_t)c * ld] = r[c];
-    base[(int64_t)(c + 3) * ld] = v[c];
+    for (int c = 0; c < 3; ++c) {
+      base[(int64_t)c * ld] = r[c];
+      base[(int64_t)(c + 3) * ld] = v[c];
+    }
   }
+  if (blockIdx.x == gridDim.x - 1 && blockIdx.y == gridDim.y - 1 && threadIdx.x == 0) pdl_wait();
 }
 
 constexpr int kPropWindow = 2 * kPropThreads;   // targets per CTA: every thread advances two states
@@ -169,11 +172,12 @@ propagate_sigma_kernel(double* __restrict__ sb, int64_t n, int64_t ld, double dt
   // sensor / tasking kernel), so it runs beside it; its successor (the per-target stage) may be
   // scheduled as soon as every CTA of this grid is resident.  One thread of the grid does wait for
   // the predecessor, so that "this grid is done" implies "the sensor kernel is done" for the
-  // successor, which needs both.
+  // successor, which needs both -- thread 0 of the LAST CTA, AFTER its own work: a CTA that waited
+  // first and worked afterwards ended late whenever the sensor kernel is long (it carries the
+  // multi-GPU exchange) and stretched this kernel by that much (4.7 us per step at 2 GPUs).
   pdl_trigger();
   PC_PROP_STAMP(0, atomicMin);
   PC_PROP_CTA_ENTRY();
-  if (blockIdx.x == 0 && blockIdx.y == 0 && tid == 0) pdl_wait();
   const int64_t t0 = (int64_t)blockIdx.x * kPropWindow;
   const int i = blockIdx.y;
   double* blk = sb + (int64_t)i * 6 * ld;
@@ -303,6 +307,7 @@ propagate_sigma_kernel(double* __restrict__ sb, int64_t n, int64_t ld, double dt
   }
   PC_PROP_STAMP(1, atomicMax);
   PC_PROP_CTA_EXIT();
+  if (blockIdx.x == gridDim.x - 1 && blockIdx.y == gridDim.y - 1 && tid == 0) pdl_wait();
 }
 
 cudaError_t launch_propagate_sigma(double* sb, int64_t n, int64_t ld, int have_truth, double t0,

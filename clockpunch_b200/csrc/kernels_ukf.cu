@@ -645,71 +645,33 @@ __device__ __forceinline__ void vis_word(const double4* __restrict__ row, const 
   }
 }
 
-// ---- peer push helpers (see PeerPush in ukf_args.cuh) ---------------------------------------------
-// (out of line: the peer loop would otherwise be inlined at every store site of kernels that mostly run
-// without peers)
-template <typename T>
-__device__ __noinline__ void peer_store(const PeerPush& pp, int parity, int64_t field_off, int64_t idx, T v) {
-  const int64_t off = ((int64_t)parity * pp.world + pp.rank) * pp.slot_bytes + field_off + idx * (int64_t)sizeof(T);
-  for (int r = 0; r < pp.world; ++r)
-    *reinterpret_cast<T*>(__ldg(pp.table + r) + off) = v;
+// ---- stand-alone peer exchange (pc_allgather_step, pc_peer_wait): see PeerPush in ukf_args.cuh -------
+// Inside the step the push and the wait are part of the sensor kernel (kernels_env.cu); these two
+// kernels are the same operations for a caller that exchanges a summary buffer outside a step.
+__global__ void __launch_bounds__(128)
+peer_push_kernel(PeerPush pp) {
+  peer_push_block(pp, (int)blockIdx.x, (int)gridDim.x);
 }
 
-// Called by every thread at the end of the kernel: make this CTA's remote stores visible system
-// wide, and let the last CTA of the grid publish `step` in every peer's flag array.
-__device__ __forceinline__ void peer_publish(const PeerPush& pp, uint64_t step) {
-  __threadfence_system();
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    const unsigned int done = atomicAdd(pp.ticket, 1u);
-    if (done == gridDim.x - 1) {
-      *pp.ticket = 0;                   // ready for the next launch (everybody else has already arrived)
-      *pp.seq = step;
-      __threadfence_system();
-      for (int r = 0; r < pp.world; ++r)
-        *reinterpret_cast<volatile uint64_t*>(__ldg(pp.table + pp.world + r) + 8 * (uint64_t)pp.rank) = step;
-    }
-  }
-}
-
-// One small CTA: hold the stream until every peer has published this rank's current push number
-// (bounded spin: a lost peer raises *err instead of hanging the GPU).  The step itself does this wait
-// inside the NEXT step's sensor kernel (peer_wait_thread, pc_common.cuh); this is the stand-alone form
-// for callers that read the gathered buffer from the host (pc_peer_wait, pc_allgather_step).
+// One small CTA: hold the stream until every peer has published push number *epoch + 1 (bounded spin: a
+// lost peer raises *err instead of hanging the GPU), then count the push (advance != 0).
 __global__ void peer_wait_kernel(const uint64_t* __restrict__ table, int world, int rank,
-                                 const unsigned long long* __restrict__ seq, unsigned int* __restrict__ err) {
-  pdl_wait();
-  if ((int)threadIdx.x < world) peer_wait_thread(table, world, rank, seq, err, (int)threadIdx.x);
+                                 unsigned long long* __restrict__ epoch, unsigned int* __restrict__ err,
+                                 int advance) {
+  if ((int)threadIdx.x < world) peer_wait_thread(table, world, rank, epoch, err, (int)threadIdx.x);
+  __syncthreads();
+  if (advance && threadIdx.x == 0) *epoch += 1;
 }
 
-// Alternative to storing from the per-target kernel: one grid copies the finished local summary
-// buffer into this rank's slot of every peer's gathered buffer with 16-byte stores, then publishes.
-__global__ void __launch_bounds__(256)
-peer_push_kernel(const uint4* __restrict__ src, int64_t n16, PeerPush pp) {
-  pdl_wait();
-  pdl_trigger();
-  const uint64_t step_done = *reinterpret_cast<const volatile unsigned long long*>(pp.seq) + 1;
-  const int64_t off = ((int64_t)(step_done & 1) * pp.world + pp.rank) * pp.slot_bytes;
-  for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < n16; i += (int64_t)gridDim.x * 256) {
-    const uint4 v = src[i];
-    for (int r = 0; r < pp.world; ++r) reinterpret_cast<uint4*>(__ldg(pp.table + r) + off)[i] = v;
-  }
-  peer_publish(pp, step_done);
+cudaError_t launch_peer_push(const PeerPush& pp, cudaStream_t stream) {
+  peer_push_kernel<<<peer_push_blocks(pp.bytes), 128, 0, stream>>>(pp);
+  return cudaGetLastError();
 }
 
-cudaError_t launch_peer_push(const void* summary, int64_t bytes, const PeerPush& pp, bool programmatic,
-                             cudaStream_t stream) {
-  const int64_t n16 = bytes / 16;
-  int blocks = (int)((n16 + 255) / 256);
-  if (blocks > 296) blocks = 296;
-  if (blocks < 1) blocks = 1;
-  return launch_pdl(peer_push_kernel, dim3(blocks), dim3(256), 0, stream, programmatic,
-                    reinterpret_cast<const uint4*>(summary), n16, pp);
-}
-
-cudaError_t launch_peer_wait(const uint64_t* table, int world, int rank, const unsigned long long* seq,
-                             unsigned int* err, bool programmatic, cudaStream_t stream) {
-  return launch_pdl(peer_wait_kernel, dim3(1), dim3(64), 0, stream, programmatic, table, world, rank, seq, err);
+cudaError_t launch_peer_wait(const uint64_t* table, int world, int rank, unsigned long long* epoch,
+                             unsigned int* err, int advance, cudaStream_t stream) {
+  peer_wait_kernel<<<1, 64, 0, stream>>>(table, world, rank, epoch, err, advance);
+  return cudaGetLastError();
 }
 
 // Stage 3 of the step, one THREAD per target: unscented transform, measurement update, outputs,
@@ -734,9 +696,8 @@ ukf_finish_kernel(const __grid_constant__ UkfArgs a) {
   }
   const bool live = t < a.n;
   const int64_t tc = live ? t : a.n - 1;  // dead lanes shadow the last target and store nothing
-  // sequence number of this push (counts launches, survives engine resets) and the slot it goes to
-  const uint64_t step_done = a.pp.world ? *reinterpret_cast<const volatile unsigned long long*>(a.pp.seq) + 1 : 0;
-  const int parity = (int)(step_done & 1);
+  // multi-GPU: the sensor kernel of this step has pushed the summaries of the previous step; count it
+  if (a.peer_epoch && t == 0) *a.peer_epoch += 1;
   const int64_t warp_t0 = t - lane;
   const int64_t ld = a.ld, blk = 6 * a.ld;
   const double* __restrict__ sb = a.sb;
@@ -882,12 +843,6 @@ ukf_finish_kernel(const __grid_constant__ UkfArgs a) {
     const float trv = ((float)PE[uidx(3, 3)] + (float)PE[uidx(4, 4)]) + (float)PE[uidx(5, 5)];
     if (a.tr_pos) a.tr_pos[t] = trp;
     if (a.tr_vel) a.tr_vel[t] = trv;
-    if (a.pp.world) {
-      peer_store(a.pp, parity, a.pp.off_tr_pos, t, trp);
-      peer_store(a.pp, parity, a.pp.off_tr_vel, t, trv);
-      peer_store(a.pp, parity, a.pp.off_num_tasked, t, a.num_tasked[t]);
-      peer_store(a.pp, parity, a.pp.off_ltt, t, a.last_time_tasked[t]);
-    }
     if (a.out_pred_x) {
 #pragma unroll
       for (int c = 0; c < 6; ++c) a.out_pred_x[(int64_t)c * ld + t] = px[c];
@@ -934,13 +889,11 @@ ukf_finish_kernel(const __grid_constant__ UkfArgs a) {
           if (live) {
             a.vis_truth[t * wpr + w] = wa;
             a.vis_est[t * wpr + w] = wb;
-            if (a.pp.world) peer_store(a.pp, parity, a.pp.off_vis_est, t * wpr + w, wb);
           }
         }
       }
     }
   }
-  if (a.pp.world) peer_publish(a.pp, step_done);
 }
 
 cudaError_t launch_sigma_gen(const double* est_x, const double* est_p, const double* truth_x, double* sb,
@@ -1180,8 +1133,7 @@ __device__ __noinline__ uint32_t coop_part1(const UkfArgs& a, CoopSmem& S, int64
 // instruction lines are already in the SM's instruction cache when the real data arrives (the update
 // warp is alone on its code: every line it touches is otherwise a cold miss).
 template <bool HOST>
-__device__ __noinline__ void coop_part2(const UkfArgs& a, CoopSmem& S, int64_t t, int parity, uint32_t flags,
-                                        int dry) {
+__device__ __noinline__ void coop_part2(const UkfArgs& a, CoopSmem& S, int64_t t, uint32_t flags, int dry) {
   const unsigned full = 0xffffffffu;
   const int lane = threadIdx.x & 31;
   const int64_t ld = a.ld, blk = 6 * a.ld;
@@ -1268,12 +1220,6 @@ __device__ __noinline__ void coop_part2(const UkfArgs& a, CoopSmem& S, int64_t t
       if (a.h_num_tasked) a.h_num_tasked[t] = nt;
       if (a.h_ltt) a.h_ltt[t] = (float)t_now;
     }
-    if (a.pp.world) {
-      peer_store(a.pp, parity, a.pp.off_tr_pos, t, trp);
-      peer_store(a.pp, parity, a.pp.off_tr_vel, t, trv);
-      peer_store(a.pp, parity, a.pp.off_num_tasked, t, nt);
-      peer_store(a.pp, parity, a.pp.off_ltt, t, (float)t_now);
-    }
   }
   if (lane < 6 && wr) {
     if (a.out_z) a.out_z[(int64_t)lane * ld + t] = S.z[lane];
@@ -1285,7 +1231,7 @@ __device__ __noinline__ void coop_part2(const UkfArgs& a, CoopSmem& S, int64_t t
 
 // Third piece: factor of the new covariance, next step's sigma points, estimated visibility row.
 template <bool HOST>
-__device__ __noinline__ void coop_part3(const UkfArgs& a, CoopSmem& S, int64_t t, int parity, int dry) {
+__device__ __noinline__ void coop_part3(const UkfArgs& a, CoopSmem& S, int64_t t, int dry) {
   const unsigned full = 0xffffffffu;
   const int lane = threadIdx.x & 31;
   const int64_t ld = a.ld, blk = 6 * a.ld;
@@ -1339,7 +1285,6 @@ __device__ __noinline__ void coop_part3(const UkfArgs& a, CoopSmem& S, int64_t t
         if (lane == 0 && wr && w0 + u < a.wpr) {
           a.vis_est[t * a.wpr + w0 + u] = word;
           if (HOST && a.h_vis_est) a.h_vis_est[t * a.wpr + w0 + u] = word;
-          if (a.pp.world) peer_store(a.pp, parity, a.pp.off_vis_est, t * a.wpr + w0 + u, word);
         }
       }
     }
@@ -1410,8 +1355,8 @@ ukf_finish_quad_kernel(const __grid_constant__ UkfArgs a) {
     CoopSmem& S = reinterpret_cast<CoopSmem*>(smem_raw)[threadIdx.x >> 5];
     coop_scratch_init(S);
     if (threadIdx.x < 64) coop_part1(a, S, 0, 1);
-    else if (threadIdx.x < 96) coop_part2<HOST>(a, S, 0, 0, 0u, 1);
-    else coop_part3<HOST>(a, S, 0, 0, 1);
+    else if (threadIdx.x < 96) coop_part2<HOST>(a, S, 0, 0u, 1);
+    else coop_part3<HOST>(a, S, 0, 1);
   }
   pdl_wait();  // launched programmatically behind the propagation kernel: everything below reads its output
   pdl_trigger();  // a programmatic successor (the observation pack) may be scheduled behind our last wave
@@ -1420,9 +1365,8 @@ ukf_finish_quad_kernel(const __grid_constant__ UkfArgs a) {
     a.clock->t_now += a.dt;
     a.clock->step += 1;
   }
-  // sequence number of this push (counts launches, survives engine resets) and the slot it goes to
-  const uint64_t step_done = a.pp.world ? *reinterpret_cast<const volatile unsigned long long*>(a.pp.seq) + 1 : 0;
-  const int parity = (int)(step_done & 1);
+  // multi-GPU: the sensor kernel of this step has pushed the summaries of the previous step; count it
+  if (a.peer_epoch && blockIdx.x == 0 && threadIdx.x == 0) *a.peer_epoch += 1;
   // the first M CTAs are update CTAs (one per sensor, see above), the rest take 16 targets each
   const int64_t nb_upd = ROLE ? a.task_sensors : 0;
   if (ROLE && (int64_t)blockIdx.x < nb_upd) {
@@ -1438,10 +1382,9 @@ ukf_finish_quad_kernel(const __grid_constant__ UkfArgs a) {
       CoopSmem& S = reinterpret_cast<CoopSmem*>(smem_raw)[0];
       PC_COOP_CLOCK(0);
       const uint32_t fl = coop_part1(a, S, tt, 0);
-      coop_part2<HOST>(a, S, tt, parity, fl, 0);
-      coop_part3<HOST>(a, S, tt, parity, 0);
+      coop_part2<HOST>(a, S, tt, fl, 0);
+      coop_part3<HOST>(a, S, tt, 0);
     }
-    if (a.pp.world) peer_publish(a.pp, step_done);
     return;
   }
   const int64_t cta = (int64_t)blockIdx.x - nb_upd;
@@ -1628,10 +1571,6 @@ ukf_finish_quad_kernel(const __grid_constant__ UkfArgs a) {
         if (a.h_tr_pos) a.h_tr_pos[t] = trp;
         if (a.h_tr_vel) a.h_tr_vel[t] = trv;
       }
-      if (a.pp.world) {
-        peer_store(a.pp, parity, a.pp.off_tr_pos, t, trp);
-        peer_store(a.pp, parity, a.pp.off_tr_vel, t, trv);
-      }
     }
     if (HOST && q == 0) {
       if (a.h_num_tasked) a.h_num_tasked[t] = nt0;
@@ -1683,11 +1622,6 @@ ukf_finish_quad_kernel(const __grid_constant__ UkfArgs a) {
   }
 
   PC_PHASE_CLOCK(7);
-  if (a.pp.world && mine && q == 0) {   // lane 0 of the quad did the tasking bookkeeping above
-    peer_store(a.pp, parity, a.pp.off_num_tasked, t, a.num_tasked[t]);
-    peer_store(a.pp, parity, a.pp.off_ltt, t, a.last_time_tasked[t]);
-  }
-
   // ---- visibility: lane q packs words q, q + 4, ... of both rows ---------------------------------
   if (vis) {
     const double RE2 = a.body_radius * a.body_radius;
@@ -1715,14 +1649,12 @@ ukf_finish_quad_kernel(const __grid_constant__ UkfArgs a) {
           if (mine) {
             a.vis_est[t * wpr + w] = wb;
             if (HOST && a.h_vis_est) a.h_vis_est[t * wpr + w] = wb;
-            if (a.pp.world) peer_store(a.pp, parity, a.pp.off_vis_est, t * wpr + w, wb);
           }
         }
       }
     }
   }
   PC_PHASE_CLOCK(9);
-  if (a.pp.world) peer_publish(a.pp, step_done);
 }
 
 template <int TPB>

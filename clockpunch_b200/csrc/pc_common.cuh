@@ -46,15 +46,15 @@ namespace pc {
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 
-// Bounded wait of thread r for peer r's flag to reach this rank's push count (see PeerPush, ukf_args.cuh):
-// table[world + rank] is this rank's flag array, flag[r] the number of the last push peer r has
-// published here; *seq the number of pushes this rank itself has completed.  Ranks step in lockstep,
-// so "peer r has published my current push number" means its summaries of that step are all here.
+// Bounded wait of thread r for peer r's flag to reach the number of the push in flight (see PeerPush,
+// ukf_args.cuh): table[world + rank] is this rank's flag array, flag[r] the number of the last push
+// peer r has published here; *epoch the number of pushes this rank has completed, so the push in
+// flight is *epoch + 1 (nobody changes *epoch while a kernel that waits is running).  Ranks step in
+// lockstep, so "peer r has published push n" means its summaries of that push are all here.
 __device__ __forceinline__ void peer_wait_thread(const uint64_t* __restrict__ table, int world, int rank,
-                                                 const unsigned long long* __restrict__ seq,
+                                                 const unsigned long long* __restrict__ epoch,
                                                  unsigned int* __restrict__ err, int r) {
-  const uint64_t want = *reinterpret_cast<const volatile unsigned long long*>(seq);
-  if (want == 0) return;
+  const uint64_t want = *reinterpret_cast<const volatile unsigned long long*>(epoch) + 1;
   const volatile uint64_t* flag = reinterpret_cast<const volatile uint64_t*>(__ldg(table + world + rank)) + r;
   for (int spin = 0; spin < (1 << 22); ++spin) {
     if (*flag >= want) return;

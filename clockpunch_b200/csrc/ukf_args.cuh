@@ -4,22 +4,24 @@
 
 namespace pc {
 
-// Multi-GPU exchange fused into the per-target stage: every per-target summary the other shards'
-// schedulers need (num_tasked, packed estimated vis words, covariance traces, last_time_tasked) is
-// stored, as it is produced, into the corresponding slot of EVERY peer's gathered buffer over
-// NVLink (peer-mapped symmetric memory), instead of into a local buffer that a collective then
-// ships.  Layout of a gathered buffer: [step parity][rank][slot_bytes], a slot being a copy of the
-// shard's summary buffer.  The last CTA of the grid publishes the step number in every peer's flag
-// array.  Nobody waits at the end of the step: the sensor kernel of the NEXT step waits (bounded) for
-// every peer's flag of this push, beside the target propagation (the gathered summaries are only
-// consumed by the next step's scheduler); peer_wait_kernel is the stand-alone form of that wait.
+// Multi-GPU exchange of the per-target summaries (num_tasked, packed estimated vis words, covariance
+// traces, last_time_tasked -- one contiguous summary buffer per shard): every rank copies its summary
+// buffer into its slot of EVERY peer's gathered buffer over NVLink (peer-mapped memory, plain 16-byte
+// stores) and publishes the push number in every peer's flag array; a rank then waits (bounded) until
+// all peers' flags carry that number.  Layout of a gathered buffer: [push parity][rank][slot_bytes].
+// The summaries of step k are needed by the scheduler of step k + 1 and by nothing else of step
+// k + 1's physics, so both the push of step k's summaries and the wait for the peers' sit in the SENSOR
+// kernel of step k + 1, which runs beside the target propagation: the exchange is off the critical
+// path of the step (measured: 49 -> 37 us per step at 2 x 10 000 targets, profiles/README.md).
 struct PeerPush {
   int world, rank;             // world == 0: disabled
   const uint64_t* table;       // device array: [0, world) gathered bases, [world, 2 world) flag bases
-  int64_t slot_bytes;
-  int64_t off_num_tasked, off_vis_est, off_tr_pos, off_tr_vel, off_ltt;   // field offsets inside a slot
-  unsigned int* ticket;        // device counter for "last CTA done"
-  unsigned long long* seq;     // pushes completed so far (never reset: engine resets must not rewind the flags)
+  const void* src;             // this rank's summary buffer (16-byte aligned)
+  int64_t bytes;               // its size = slot size (multiple of 4)
+  unsigned int* ticket;        // device counter for "last push CTA done"
+  unsigned long long* epoch;   // pushes completed so far (never rewound: engine resets must not rewind the flags);
+                               // the push in flight is number *epoch + 1, counted by the per-target kernel
+  unsigned int* err;           // bit r: peer r's flag never arrived
 };
 
 struct UkfArgs {
@@ -69,7 +71,7 @@ struct UkfArgs {
   float* h_tr_pos;
   float* h_tr_vel;
   float* h_ltt;
-  PeerPush pp;
+  unsigned long long* peer_epoch;   // multi-GPU: push counter to advance (see PeerPush), or NULL
   int variant;             // pc_option PC_OPT_FINISH_KERNEL (0 = choose by catalog size)
   pc_ukf_params p;
 };
@@ -82,9 +84,47 @@ cudaError_t launch_propagate_sigma(double* sb, int64_t n, int64_t ld, int have_t
                                    bool beside_predecessor, int mapping, cudaStream_t stream);
 cudaError_t launch_ukf_finish(const UkfArgs& a, cudaStream_t stream);
 bool finish_fills_host_mirrors(int64_t n, int64_t sensors, int variant);
-cudaError_t launch_peer_push(const void* summary, int64_t bytes, const PeerPush& pp, bool programmatic,
-                             cudaStream_t stream);
-cudaError_t launch_peer_wait(const uint64_t* table, int world, int rank, const unsigned long long* seq,
-                             unsigned int* err, bool programmatic, cudaStream_t stream);
+cudaError_t launch_peer_push(const PeerPush& pp, cudaStream_t stream);
+cudaError_t launch_peer_wait(const uint64_t* table, int world, int rank, unsigned long long* epoch,
+                             unsigned int* err, int advance, cudaStream_t stream);
+
+// CTAs of a push: enough 16-byte stores in flight to fill NVLink for megabyte summaries, one CTA for small ones
+inline int peer_push_blocks(int64_t bytes) {
+  const int64_t want = (bytes / 16 + 128 * 8 - 1) / (128 * 8);
+  return (int)(want < 1 ? 1 : (want > 64 ? 64 : want));
+}
+
+// One CTA (128 threads) of a push: copy its share of the summary buffer into this rank's slot of every
+// peer's gathered buffer, make the stores visible system wide, and let the last CTA publish the push
+// number in every peer's flag array.
+__device__ __forceinline__ void peer_push_block(const PeerPush& pp, int block, int nblocks) {
+  const uint64_t n = *reinterpret_cast<const volatile unsigned long long*>(pp.epoch) + 1;
+  const int64_t off = ((int64_t)(n & 1) * pp.world + pp.rank) * pp.bytes;
+  const int64_t n16 = pp.bytes / 16;
+  const uint4* __restrict__ src = reinterpret_cast<const uint4*>(pp.src);
+  for (int64_t i = (int64_t)block * 128 + threadIdx.x; i < n16; i += (int64_t)nblocks * 128) {
+    const uint4 v = src[i];
+    for (int r = 0; r < pp.world; ++r) reinterpret_cast<uint4*>(__ldg(pp.table + r) + off)[i] = v;
+  }
+  if (block == 0) {   // tail words (slot sizes are multiples of 4 bytes, not always of 16)
+    const int64_t w0 = n16 * 4, nw = pp.bytes / 4;
+    const uint32_t* __restrict__ s32 = reinterpret_cast<const uint32_t*>(pp.src);
+    for (int64_t i = w0 + threadIdx.x; i < nw; i += 128) {
+      const uint32_t v = s32[i];
+      for (int r = 0; r < pp.world; ++r) reinterpret_cast<uint32_t*>(__ldg(pp.table + r) + off)[i] = v;
+    }
+  }
+  __threadfence_system();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const unsigned int done = atomicAdd(pp.ticket, 1u);
+    if (done == (unsigned)nblocks - 1) {
+      *pp.ticket = 0;                   // ready for the next push (everybody else has already arrived)
+      __threadfence_system();
+      for (int r = 0; r < pp.world; ++r)
+        *reinterpret_cast<volatile uint64_t*>(__ldg(pp.table + pp.world + r) + 8 * (uint64_t)pp.rank) = n;
+    }
+  }
+}
 
 }  // namespace pc

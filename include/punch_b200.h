@@ -89,9 +89,8 @@ int64_t pc_launch_count(pc_ctx* ctx);
  *       2 four lanes per target, update in line
  *       3 one thread per target, 64-thread CTAs      4 one thread per target, 128-thread CTAs
  *   PC_OPT_PROPAGATE_KERNEL  sigma-point propagation: 1 one state per thread, 2 two states per thread
- *       out of a sorted 256-target window
- *   PC_OPT_PEER_PUSH         multi-GPU exchange: 1 stores from the per-target kernel, 2 copy kernel behind it */
-enum pc_option { PC_OPT_FINISH_KERNEL = 1, PC_OPT_PROPAGATE_KERNEL = 2, PC_OPT_PEER_PUSH = 3 };
+ *       out of a sorted 256-target window */
+enum pc_option { PC_OPT_FINISH_KERNEL = 1, PC_OPT_PROPAGATE_KERNEL = 2 };
 int pc_set_option(pc_ctx* ctx, int option, int value);
 int pc_get_option(pc_ctx* ctx, int option, int* value);
 
@@ -242,16 +241,26 @@ int pc_policy_random_visible(pc_ctx* ctx, const uint32_t* vis_est, int64_t N, in
  * for equal (seed, step).  No context, no device work; returns PC_ERR_BAD_ARG on bad sizes. */
 int pc_policy_random_visible_host(const uint32_t* vis_est, int64_t N, int64_t M, int64_t words_per_row,
                                   uint64_t seed, uint64_t step, int probes, int64_t* actions);
+/* The same for a batch of E environments stored environment-major (pc_step_args.env_targets / env_sensors):
+ * actions[e * env_sensors + j] is LOCAL to environment e (env_targets = inaction); same picks as the device
+ * form inside the step for equal (seed, step). */
+int pc_policy_random_visible_envs_host(const uint32_t* vis_est, int64_t E, int64_t env_targets, int64_t env_sensors,
+                                       int64_t words_per_row, uint64_t seed, uint64_t step, int probes,
+                                       int64_t* actions);
 
 /* ---- measurement helpers (bench.py) ------------------------------------
- * pc_set_timing(1) makes pc_step_fused bracket its UKF kernel with one pair of CUDA events on the
- * launch stream (recorded as external event nodes when the stream is being captured, so the
- * pair is re-recorded by every replay of the graph); pc_get_timing waits for the pair and
- * returns the device time of the most recent UKF launch in milliseconds.  pc_fp64_peak runs a
+ * pc_set_timing(1) makes pc_step_fused record three CUDA events on the launch stream: before the
+ * sigma-point propagation kernel, between it and the per-target kernel, and after the per-target
+ * kernel (recorded as external event nodes when the stream is being captured, so they are re-recorded
+ * by every replay of the graph); the two kernels then run one after the other instead of chained by
+ * programmatic launch.  pc_get_timing waits and returns the device time of the most recent
+ * propagation launch in milliseconds, pc_get_kernel_timing that and the per-target kernel's.
+ * pc_fp64_peak runs a
  * register-resident DFMA probe and returns the best TFLOP/s of `repeats` launches: the FP64
  * roofline denominator. */
 int pc_set_timing(pc_ctx* ctx, int enabled);
 int pc_get_timing(pc_ctx* ctx, double* ukf_ms_last);
+int pc_get_kernel_timing(pc_ctx* ctx, double* propagate_ms_last, double* finish_ms_last);
 int pc_fp64_peak(pc_ctx* ctx, int repeats, double* tflops);
 
 /* ---- fused step ---------------------------------------------------------
@@ -320,22 +329,23 @@ typedef struct pc_step_args {
   int64_t env_targets, env_sensors;
   /* Multi-GPU exchange fused into the step (one process per GPU, targets partitioned, SURVEY.md
    * section 8e).  peer_table is a DEVICE array of 2 * peer_world pointers: first the base address of every
-   * rank's gathered buffer, then of every rank's flag array (peer_world uint64), all peer-mapped
-   * (e.g. torch symmetric memory over NVLink).  A gathered buffer is [2][peer_world][summary_bytes]:
-   * parity of the step, source rank, a copy of that rank's summary buffer.  summary_base /
-   * summary_bytes describe the local buffer that contains num_tasked, vis_est, tr_pos, tr_vel and
-   * last_time_tasked (all five must point into it).  With peer_table != NULL the per-target kernel
-   * stores every summary value into the slot of this rank in EVERY peer's gathered buffer as it
-   * produces it (or, for shards above 32768 targets and with 8 or more peers, a copy kernel behind it
-   * streams the finished summary buffer), and its last CTA publishes the push number in every peer's
-   * flag array: no collective call.  The gathered summaries of step k are only needed by the
-   * scheduler of step k + 1, so nothing waits for the peers at the end of step k: the wait (bounded)
-   * for every peer's push k sits in the SENSOR kernel of step k + 1, beside the target propagation,
-   * which also keeps any rank from overwriting a parity slot a slower peer may still read.  A caller
-   * that reads the gathered buffer on the host enqueues pc_peer_wait first.  pc_peer_status reports
-   * (and clears) a bit per peer whose flag never came, and the number of pushes done so far (its
-   * parity is the slot that holds the latest data).  All ranks must step in lockstep (same number
-   * of pc_step_fused calls). */
+   * rank's gathered buffer, then of every rank's flag array (peer_world uint64), all peer-mapped over
+   * NVLink (pc_comm_* below sets them up with CUDA IPC; any other peer-mapped memory works).  A gathered
+   * buffer is [2][peer_world][summary_bytes]: parity of the push, source rank, a copy of that rank's
+   * summary buffer.  summary_base / summary_bytes describe the local buffer (16-byte aligned, a multiple
+   * of 4 bytes) that contains num_tasked, vis_est, tr_pos, tr_vel and last_time_tasked -- everything
+   * another shard's scheduler needs (metrics.py:161, greedy_cov_v2.py:104-120, env.py:599-609).
+   * The summaries a step leaves there are needed by the scheduler of the NEXT step and by nothing else of
+   * its physics, so the exchange is not the end of step k but a side task of step k + 1: its sensor
+   * kernel copies the summary buffer into this rank's slot of EVERY peer's gathered buffer (16-byte
+   * stores over NVLink), publishes the push number in every peer's flag array and waits (bounded) until
+   * all peers' flags carry the same number -- beside the target propagation, which needs none of it;
+   * only the per-target kernel at the end of the step waits for the sensor kernel.  No collective call.
+   * After pc_step_fused number k the gathered buffers therefore hold the summaries of step k - 1 (parity
+   * slot = push count & 1); a caller that needs the summaries of step k before step k + 1 runs (a
+   * scheduler on the host) enqueues pc_peer_exchange, the same push + wait as two stand-alone kernels.
+   * pc_peer_status reports (and clears) a bit per peer whose flag never came, and the number of pushes
+   * completed so far.  All ranks must step in lockstep (same sequence of steps and exchanges). */
   const uint64_t* peer_table;
   int32_t peer_world, peer_rank;
   const void* summary_base;
@@ -365,10 +375,12 @@ typedef struct pc_step_args {
 int pc_step_fused(pc_ctx* ctx, const pc_step_args* args, const pc_ukf_params* params,
                   pc_stream stream);
 int pc_peer_status(pc_ctx* ctx, uint32_t* out_error_mask, uint64_t* out_pushes);
-/* Enqueue the (bounded) wait for every peer's latest push on `stream`; what follows on the stream
- * may read the gathered buffer.  table / world / rank as in pc_step_args. */
-int pc_peer_wait(pc_ctx* ctx, const uint64_t* peer_table, int32_t peer_world, int32_t peer_rank,
-                 pc_stream stream);
+/* Push `summary` (summary_bytes of it; 16-byte aligned, a multiple of 4) into this rank's slot of every
+ * peer's gathered buffer and wait (bounded) for every peer's push of the same number, as two kernels on
+ * `stream`; what follows on the stream may read the gathered buffer, parity slot = push count & 1.
+ * table / world / rank as in pc_step_args.  Every rank must call it (lockstep). */
+int pc_peer_exchange(pc_ctx* ctx, const uint64_t* peer_table, int32_t peer_world, int32_t peer_rank,
+                     const void* summary, int64_t summary_bytes, pc_stream stream);
 
 /* ---- peer exchange set-up without any framework (pc_comm_init / pc_allgather_step) --
  * One process per GPU on one node.  pc_comm_init allocates this rank's gathered buffer
@@ -378,9 +390,10 @@ int pc_peer_wait(pc_ctx* ctx, const uint64_t* peer_table, int32_t peer_world, in
  * allocation before anybody's first push -- and hands the world x 64 bytes to pc_comm_attach,
  * which maps every peer's buffer over NVLink and builds the device table.  pc_comm_table then
  * yields what pc_step_args.peer_table / peer_world / peer_rank expect, and the local gathered
- * buffer.  pc_allgather_step pushes an arbitrary summary buffer (summary_bytes of it, 16-byte
- * aligned) into every peer and waits for all peers' pushes: the stand-alone form of what the step
- * does in-kernel.  pc_comm_destroy unmaps and frees (no peer may still be pushing). */
+ * buffer.  pc_allgather_step is pc_peer_exchange on the attached buffers (summary_bytes of `summary`):
+ * the stand-alone form of what the step does in its sensor kernel.  Tear-down: pc_comm_detach on every rank (unmaps the peers' buffers; no rank may still
+ * be pushing), synchronise the ranks, then pc_comm_destroy (frees this rank's buffer; also detaches if
+ * that has not been done).  pc_ctx_destroy and a second pc_comm_init destroy an existing exchange. */
 #define PC_COMM_HANDLE_BYTES 64
 int pc_comm_init(pc_ctx* ctx, int32_t world, int32_t rank, int64_t summary_bytes,
                  uint8_t handle_out[PC_COMM_HANDLE_BYTES]);
@@ -388,6 +401,7 @@ int pc_comm_attach(pc_ctx* ctx, const uint8_t* all_handles /* world x PC_COMM_HA
 int pc_comm_table(pc_ctx* ctx, const uint64_t** out_table, void** out_gathered, int32_t* out_world,
                   int32_t* out_rank, int64_t* out_summary_bytes);
 int pc_allgather_step(pc_ctx* ctx, const void* summary, pc_stream stream);
+int pc_comm_detach(pc_ctx* ctx);
 int pc_comm_destroy(pc_ctx* ctx);
 
 /* ---- the step as the reference's caller sees it: host actions in, host observation out -------

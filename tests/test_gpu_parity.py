@@ -710,13 +710,14 @@ def test_peer_push_single_rank_matches_summary():
         gathered = eng.enable_peer_push()         # pc_comm_init / pc_comm_attach (CUDA IPC); one per context
         g = eng.build_graph(100.0, policy_probes=32, policy_seed=3)
         seen = []
-        base = eng.peer_status()[1]               # the push counter belongs to the library context
+        last = eng.peer_status()[1]               # the push counter belongs to the library context
         for s in range(5):
             if s == 3:
                 eng.reset()
-            eng.replay(g)
-            err, pushes = eng.peer_status()
-            assert err == 0 and pushes == base + s + 1
+            eng.replay(g)                             # its sensor kernel pushes the PREVIOUS step's summaries
+            err, pushes = eng.peer_status()           # exchanges the current ones, then reports
+            assert err == 0 and pushes == last + 2    # one push per step, one per explicit exchange
+            last = pushes
             torch.testing.assert_close(gathered[pushes & 1, 0], eng.summary, rtol=0, atol=0)
             f = eng.peer_fields(pushes & 1, 0)
             np.testing.assert_array_equal(f["vis_est"].cpu().numpy(), eng.vis_est.cpu().numpy())

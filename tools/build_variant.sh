@@ -1,5 +1,5 @@
 #!/bin/bash
-# Build a variant of the library with extra -D flags on kernels_ukf.cu (experiments):
+# Build a variant of the library with extra -D flags on the kernel sources (experiments):
 #   tools/build_variant.sh stamps -DPC_STAMPS_HEADER='"../../tools/debug/stamps.cuh"'
 #       ->  variants/libpunch_stamps.so   (use with PUNCH_B200_LIB=...; phase stamps of tools/debug/stamps.cuh,
 #           which the product library never includes)
@@ -10,8 +10,9 @@ mkdir -p variants
 F="-gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -std=c++17 -Xcompiler -fPIC --expt-relaxed-constexpr -Iinclude"
 nvcc $F "$@" -c clockpunch_b200/csrc/kernels_ukf.cu -o variants/ukf_$name.o &
 nvcc $F "$@" -c clockpunch_b200/csrc/kernels_propagate.cu -o variants/prop_$name.o &
+nvcc $F "$@" -c clockpunch_b200/csrc/kernels_env.cu -o variants/env_$name.o &
 wait
-nvcc -shared -o variants/libpunch_$name.so variants/ukf_$name.o variants/prop_$name.o \
-  clockpunch_b200/build/kernels_vis.o clockpunch_b200/build/kernels_env.o clockpunch_b200/build/api.o \
+nvcc -shared -o variants/libpunch_$name.so variants/ukf_$name.o variants/prop_$name.o variants/env_$name.o \
+  clockpunch_b200/build/kernels_vis.o clockpunch_b200/build/api.o \
   -gencode arch=compute_100a,code=sm_100a -cudart static
 echo variants/libpunch_$name.so
