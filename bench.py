@@ -307,6 +307,8 @@ def run_own(args):
     dev = torch.device("cuda", local)
     ctx = _lib.get_ctx(local)
     lib = ctx.lib
+    ctx.set_option(_lib.OPT_PROPAGATE_KERNEL, args.opt_propagate)
+    ctx.set_option(_lib.OPT_FINISH_KERNEL, args.opt_finish)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
     peaks = {}
     try:
@@ -445,15 +447,30 @@ def run_own(args):
         for _ in range(warmup):
             timed_step()
         inv_theta = np.float32(1.0 / 0.12)
-        tx = eng.host("truth_x")
-        hv = np.cross(tx[:3].T, tx[3:].T)
-        h2, r2, v2 = (hv * hv).sum(1), (tx[:3] ** 2).sum(0), (tx[3:] ** 2).sum(0)
-        e1 = 1.0 + np.sqrt(np.maximum(0.0, 1.0 + 2.0 * (0.5 * v2 - 398600.0 / np.sqrt(r2)) * h2 / 398600.0 ** 2))
-        truth_sub = np.maximum(1.0, np.ceil(dt * (398600.0 ** 2 * e1 ** 3.5 / h2 ** 1.5) / 0.12))
+
+        def step_rate(x):
+            """The substep rule's rate for a step of dt from state(s) x (csrc/propagate.cuh orbit_rates):
+            min(perigee rate with margin, angular rate at the smallest radius reachable within the step)."""
+            mu_ = 398600.0
+            r, v = x[:3], x[3:]
+            hv = np.cross(r.T, v.T)
+            h2, r2, v2 = (hv * hv).sum(1), (r * r).sum(0), (v * v).sum(0)
+            rn = np.sqrt(r2)
+            e1 = 1.0 + np.sqrt(np.maximum(0.0, 1.0 + 2.0 * (0.5 * v2 - mu_ / rn) * h2 / mu_ ** 2))
+            wp = mu_ ** 2 * e1 ** 3.5 / h2 ** 1.5
+            rmin = rn - np.abs((r * v).sum(0) / rn) * abs(dt) - 0.5 * mu_ / r2 * dt * dt
+            wl = np.sqrt(h2) / np.maximum(rmin, 1e-9) ** 2 * np.sqrt(e1)
+            return np.where((rmin > h2 / (mu_ * e1)) & (wl < wp), wl, wp)
+
+        truth_sub = np.maximum(1.0, np.ceil(abs(dt) * step_rate(eng.host("truth_x")) / 0.12))
 
         def substeps_now():
-            om = eng.sig_flags[1].cpu().numpy().view(np.float32)
-            est = np.maximum(1.0, np.ceil(np.float32(dt) * om * inv_theta)).astype(np.float64)
+            # the rates the kernels themselves stored with the sigma points (sig_flags row 1: two bfloat16,
+            # low half = bound for steps up to 128 s, high half = perigee rate)
+            w = eng.sig_flags[1].cpu().numpy().view(np.uint32)
+            half = (w & 0xFFFF) if abs(dt) <= 128.0 else (w >> 16)
+            om = (half.astype(np.uint32) << 16).view(np.float32)
+            est = np.maximum(1.0, np.ceil(np.float32(abs(dt)) * om * inv_theta)).astype(np.float64)
             return 13.0 * est.sum() + truth_sub.sum(), est.mean()
 
         p_ms, f_ms, state_steps_sum, est_sub_sum = 0.0, 0.0, 0.0, 0.0
@@ -708,6 +725,8 @@ def main():
                     help="skip the BASELINE.json configs[2..4] passes reported under extra.configs")
     ap.add_argument("--l2", default="flush", choices=["flush", "none"])
     ap.add_argument("--eager-gather", action="store_true", help="N > 1: all-gather outside the step's CUDA graph")
+    ap.add_argument("--opt-propagate", type=int, default=0, help="tuning: pc_option PC_OPT_PROPAGATE_KERNEL (0 = size rule)")
+    ap.add_argument("--opt-finish", type=int, default=0, help="tuning: pc_option PC_OPT_FINISH_KERNEL (0 = size rule)")
     ap.add_argument("--exchange", default="auto", choices=["auto", "peer", "nccl"],
                     help="N > 1: summaries pushed into peers' memory by the step kernel, or one NCCL all-gather")
     args = ap.parse_args()

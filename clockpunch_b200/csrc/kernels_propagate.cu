@@ -106,9 +106,9 @@ propagate_sigma_single_kernel(double* __restrict__ sb, int64_t n, int64_t ld, do
       if (i == 13) {
         const double r[3] = {blk[t], blk[ld + t], blk[2 * ld + t]};
         const double v[3] = {blk[3 * ld + t], blk[4 * ld + t], blk[5 * ld + t]};
-        om = orbit_rate(r, v);
+        om = orbit_rate(r, v, dt);
       } else {
-        om = __uint_as_float(sig_aux[n + t]);
+        om = packed_rate_for_step(sig_aux[n + t], dt);
       }
       bool cl = false;
       mine = substeps_from_rate(om, dt, &cl);
@@ -213,9 +213,9 @@ propagate_sigma_kernel(double* __restrict__ sb, int64_t n, int64_t ld, double dt
           const int o = h * kPropThreads + tid;
           const double r[3] = {s_x[0][o], s_x[1][o], s_x[2][o]};
           const double v[3] = {s_x[3][o], s_x[4][o], s_x[5][o]};
-          om = orbit_rate(r, v);
+          om = orbit_rate(r, v, dt);
         } else {
-          om = __uint_as_float(sig_aux[n + t]);
+          om = packed_rate_for_step(sig_aux[n + t], dt);
         }
         bool cl = false;
         mine[h] = substeps_from_rate(om, dt, &cl);
@@ -274,9 +274,9 @@ propagate_sigma_kernel(double* __restrict__ sb, int64_t n, int64_t ld, double dt
           if (i == 13) {
             const double r[3] = {s_x[0][slot[h]], s_x[1][slot[h]], s_x[2][slot[h]]};
             const double v[3] = {s_x[3][slot[h]], s_x[4][slot[h]], s_x[5][slot[h]]};
-            om = orbit_rate(r, v);
+            om = orbit_rate(r, v, dt);
           } else {
-            om = __uint_as_float(sig_aux[n + t]);
+            om = packed_rate_for_step(sig_aux[n + t], dt);
           }
           nsub[h] = substeps_from_rate(om, dt, nullptr);
         }

@@ -492,7 +492,7 @@ sigma_gen_kernel(const double* __restrict__ est_x, const double* __restrict__ es
   }
   sig_flags[t] = ok ? 0u : (uint32_t)PC_FLAG_NONPD_EST;
   const double r0[3] = {x[0], x[1], x[2]}, v0[3] = {x[3], x[4], x[5]};
-  sig_flags[n + t] = __float_as_uint(orbit_rate(r0, v0));  // substep rule input for all 13 points
+  sig_flags[n + t] = orbit_rates_packed(r0, v0);  // substep rule input for all 13 points
 }
 
 // Coalesced store of one warp's 32 symmetric 6x6 matrices into an (N, 36) row-major array.
@@ -859,7 +859,7 @@ ukf_finish_kernel(const __grid_constant__ UkfArgs a) {
       write_sigma_blocks(a.sb, ld, t, xe, U, a.p.gamma);
       a.sig_flags[t] = ok ? 0u : (uint32_t)PC_FLAG_NONPD_EST;
       const double r0[3] = {xe[0], xe[1], xe[2]}, v0[3] = {xe[3], xe[4], xe[5]};
-      a.sig_flags[a.n + t] = __float_as_uint(orbit_rate(r0, v0));
+      a.sig_flags[a.n + t] = orbit_rates_packed(r0, v0);
     } else if (a.est_x_out) {
 #pragma unroll
       for (int c = 0; c < 6; ++c) a.est_x_out[(int64_t)c * ld + t] = xe[c];
@@ -1243,7 +1243,7 @@ __device__ __noinline__ void coop_part3(const UkfArgs& a, CoopSmem& S, int64_t t
     if (!ok && wr) repair6_warp(S.PE, S.Un, lane);
     if (lane == 0) {
       const double r0[3] = {S.xe[0], S.xe[1], S.xe[2]}, v0[3] = {S.xe[3], S.xe[4], S.xe[5]};
-      const uint32_t rate = __float_as_uint(orbit_rate(r0, v0));
+      const uint32_t rate = orbit_rates_packed(r0, v0);
       if (wr) {
         a.sig_flags[t] = ok ? 0u : (uint32_t)PC_FLAG_NONPD_EST;
         a.sig_flags[a.n + t] = rate;
@@ -1595,7 +1595,7 @@ ukf_finish_quad_kernel(const __grid_constant__ UkfArgs a) {
         for (int c = 0; c < 6; ++c) a.sb[(int64_t)c * ld + t] = xe[c];
         a.sig_flags[t] = ok ? 0u : (uint32_t)PC_FLAG_NONPD_EST;
         const double r0[3] = {xe[0], xe[1], xe[2]}, v0[3] = {xe[3], xe[4], xe[5]};
-        a.sig_flags[a.n + t] = __float_as_uint(orbit_rate(r0, v0));
+        a.sig_flags[a.n + t] = orbit_rates_packed(r0, v0);
       }
 #pragma unroll
       for (int j = 0; j < 6; ++j) {

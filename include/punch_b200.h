@@ -206,7 +206,7 @@ int pc_ukf_predict_update(pc_ctx* ctx, double* est_x, double* est_p, double* tru
  * x + gamma [0, U, -U] (generateSigmaPoints, ukf_v2.py:158-183) into blocks 0..12 of a sigma
  * buffer (layout: pc_step_args.sigma_ws).  est_x may be block 0 of sigma_ws itself.  sig_flags is
  * the (2, N) uint32 companion: [i] receives PC_FLAG_NONPD_EST where the factorisation failed,
- * [N + i] the orbit rate used by the substep rule. */
+ * [N + i] the packed rates of the substep rule (see pc_step_args.sig_flags). */
 int pc_sigma_points(pc_ctx* ctx, const double* est_x, const double* est_p, int64_t n, int64_t ld,
                     double gamma, double* sigma_ws, uint32_t* sig_flags, pc_stream stream);
 int pc_ukf_predict_update_host(pc_ctx* ctx, double* h_est_x, double* h_est_p, const double* h_z,
@@ -312,8 +312,10 @@ typedef struct pc_step_args {
    * and finishes by laying out the sigma points of the new estimate for the next step).
    * sigma_valid != 0 promises that blocks 1..12 already hold the sigma points of the current
    * (est_x, est_p), i.e. nothing touched them since the previous pc_step_fused on these buffers;
-   * with 0 they are regenerated first.  sig_flags is a (2, N) uint32 companion workspace (flags
-   * raised while factoring / propagating, and the per-target orbit rate of the substep rule).
+   * with 0 they are regenerated first.  sig_flags is a (2, N) uint32 companion workspace: row 0 the
+   * flags raised while factoring / propagating, row 1 the per-target rates of the substep rule
+   * (two bfloat16: high half the perigee angular rate with its margin, low half the bound for steps
+   * of at most 128 s -- all 13 sigma points of a target take the same number of DOP853 substeps).
    * With sigma_ws == NULL a context-owned buffer is used and est_x / truth_x are ordinary arrays. */
   double* sigma_ws;
   uint32_t* sig_flags;

@@ -11,7 +11,8 @@ g = eng.build_graph(100.0, policy_probes=64, policy_seed=SEED)
 for k in range(300):
     eng.replay(g)
     if k % 20 == 19 or k < 3:
-        om = eng.sig_flags[1].cpu().numpy().view(np.float32)
+        w = eng.sig_flags[1].cpu().numpy().view(np.uint32)      # packed rates: low half = bound for steps <= 128 s
+        om = ((w & 0xFFFF).astype(np.uint32) << 16).view(np.float32)
         ns = np.maximum(1, np.ceil(np.float32(100.0) * om * np.float32(1 / 0.12)))
         top = np.argsort(ns)[-3:]
         nt = eng.host("num_tasked")
