@@ -69,6 +69,7 @@ struct pc_ctx {
   size_t sq_sensors = 0;
   // peer push: "last CTA done" ticket and the wait kernel's error mask (device), see PeerPush
   unsigned int* peer_dev = nullptr;   // [0] ticket, [1] error mask, [2..3] 64-bit push sequence number
+
   // pc_step_host: captured steps (pc_step_fused + pc_obs_pack) and the arguments each was captured
   // with, replayed while a caller keeps passing the same buffers.  Several engines share one context
   // (deep-copied environments do: the reference's wrappers and SimRunner copy the env every step), so
@@ -903,7 +904,9 @@ int pc_step_fused(pc_ctx* ctx, const pc_step_args* a, const pc_ukf_params* param
   //    Independent of the target propagation, which is launched programmatically behind it and
   //    therefore runs beside it (no fork / join, no second stream).
   //    Multi-GPU: the same kernel pushes the summaries the PREVIOUS step left in the summary buffer into
-  //    every peer and waits for the peers' pushes (see PeerPush): the exchange runs beside the propagation.
+  //    every peer (see PeerPush), beside the propagation; the wait for the peers' pushes of the same number
+  //    is the last thing the last CTA of the per-target kernel does, so that a rank only stalls when a
+  //    peer is a full step behind.
   pc::PeerPush pp{};
   if (a->peer_table && a->N > 0) {
     pp.world = a->peer_world;
@@ -1001,13 +1004,13 @@ int pc_step_fused(pc_ctx* ctx, const pc_step_args* a, const pc_ukf_params* param
       u.body_radius = a->body_radius;
       u.vis_tol = a->vis_tol;
     }
-    u.peer_epoch = pp.world > 0 ? pp.epoch : nullptr;
     u.variant = ctx->opt_finish;
+    u.peer = pp;     // its last CTA waits for the peers' pushes and counts the push
     u.p = *params;
     PC_CUDA_TRY(ctx, pc::launch_ukf_finish(u, s));
     if (ctx->timing) PC_CUDA_TRY(ctx, cudaEventRecordWithFlags(ctx->ev2, s, evflags));
     ctx->launches += 2;
-    // (no exchange here: the next step's sensor kernel pushes these summaries and waits for the peers')
+    // (no exchange here: the next step's sensor kernel pushes these summaries)
   } else if (a->clock) {
     PC_CUDA_TRY(ctx, pc::launch_advance_clock(a->clock, a->tf - a->t0, s));
     ctx->launches += 1;

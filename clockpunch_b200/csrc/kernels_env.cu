@@ -160,11 +160,10 @@ cudaError_t launch_advance_clock(pc_clock* clock, double dt, cudaStream_t s) {
 //   block 0 thread 0 also latches the step clock (t_cur / step_cur) for the kernels that follow.
 //   Multi-GPU: blocks [nb_sens + nb_task, ...) copy this rank's summary buffer -- the per-target
 //   summaries the PREVIOUS step left there -- into every peer's gathered buffer and publish the push
-//   number; thread r of block 0 then waits (bounded) until peer r's push of the same number has arrived.
-//   The target propagation runs beside this kernel and only the per-target stage waits for it, so the
-//   whole exchange of step k overlaps the propagation of step k + 1 instead of ending step k.  (A
-//   peer that is a step ahead writes the OTHER parity slot; it cannot be two steps ahead, because its
-//   own wait needs this rank's push of the step in between.)
+//   number.  The target propagation runs beside this kernel and only the per-target stage waits for it,
+//   so the push of step k's summaries overlaps the propagation of step k + 1 instead of ending step k;
+//   the wait for the peers' pushes is the last thing the last CTA of the per-target kernel does.  (A peer that is a step ahead writes the OTHER parity slot; it cannot be two
+//   steps ahead, because its own wait needs this rank's push of the step in between.)
 struct PreStepArgs {
   double* sens_x;
   const uint8_t* sens_kind;
@@ -186,7 +185,7 @@ struct PreStepArgs {
   int64_t env_targets, env_sensors;  // batch of environments (single catalog: N, M)
   int64_t* task_of;         // may be NULL; [j] = global index of the target sensor j validly tasks, else -1
   // multi-GPU (pp.world == 0: off): push the summaries of the PREVIOUS step into every peer (blocks
-  // [nb_sens + nb_task, + nb_push)) and wait for every peer's push (threads [0, world) of block 0)
+  // [nb_sens + nb_task, + nb_push)); the wait for the peers' pushes ends the per-target kernel's last CTA
   PeerPush pp;
   int nb_task, nb_push;
 };
@@ -222,8 +221,6 @@ pre_step_kernel(const __grid_constant__ PreStepArgs a) {
       if (a.sens_q)
         a.sens_q[j] = make_double4(r[0], r[1], r[2], horizon_q(r[0], r[1], r[2], a.body_radius, a.vis_tol));
     }
-    if (blockIdx.x == 0 && (int)threadIdx.x < a.pp.world)
-      peer_wait_thread(a.pp.table, a.pp.world, a.pp.rank, a.pp.epoch, a.pp.err, (int)threadIdx.x);
     return;
   }
   if ((int)blockIdx.x >= a.nb_sens + a.nb_task) {

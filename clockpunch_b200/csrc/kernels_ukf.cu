@@ -696,8 +696,6 @@ ukf_finish_kernel(const __grid_constant__ UkfArgs a) {
   }
   const bool live = t < a.n;
   const int64_t tc = live ? t : a.n - 1;  // dead lanes shadow the last target and store nothing
-  // multi-GPU: the sensor kernel of this step has pushed the summaries of the previous step; count it
-  if (a.peer_epoch && t == 0) *a.peer_epoch += 1;
   const int64_t warp_t0 = t - lane;
   const int64_t ld = a.ld, blk = 6 * a.ld;
   const double* __restrict__ sb = a.sb;
@@ -894,6 +892,7 @@ ukf_finish_kernel(const __grid_constant__ UkfArgs a) {
       }
     }
   }
+  if (a.peer.world && blockIdx.x == gridDim.x - 1) peer_wait_and_count(a.peer);
 }
 
 cudaError_t launch_sigma_gen(const double* est_x, const double* est_p, const double* truth_x, double* sb,
@@ -1365,8 +1364,6 @@ ukf_finish_quad_kernel(const __grid_constant__ UkfArgs a) {
     a.clock->t_now += a.dt;
     a.clock->step += 1;
   }
-  // multi-GPU: the sensor kernel of this step has pushed the summaries of the previous step; count it
-  if (a.peer_epoch && blockIdx.x == 0 && threadIdx.x == 0) *a.peer_epoch += 1;
   // the first M CTAs are update CTAs (one per sensor, see above), the rest take 16 targets each
   const int64_t nb_upd = ROLE ? a.task_sensors : 0;
   if (ROLE && (int64_t)blockIdx.x < nb_upd) {
@@ -1655,6 +1652,7 @@ ukf_finish_quad_kernel(const __grid_constant__ UkfArgs a) {
     }
   }
   PC_PHASE_CLOCK(9);
+  if (a.peer.world && blockIdx.x == gridDim.x - 1) peer_wait_and_count(a.peer);
 }
 
 template <int TPB>

@@ -10,9 +10,10 @@ namespace pc {
 // stores) and publishes the push number in every peer's flag array; a rank then waits (bounded) until
 // all peers' flags carry that number.  Layout of a gathered buffer: [push parity][rank][slot_bytes].
 // The summaries of step k are needed by the scheduler of step k + 1 and by nothing else of step
-// k + 1's physics, so both the push of step k's summaries and the wait for the peers' sit in the SENSOR
-// kernel of step k + 1, which runs beside the target propagation: the exchange is off the critical
-// path of the step (measured: 49 -> 37 us per step at 2 x 10 000 targets, profiles/README.md).
+// k + 1's physics, so the push of step k's summaries sits in the SENSOR kernel of step k + 1, which runs
+// beside the target propagation, and the wait for the peers' pushes is the last thing the LAST CTA of
+// step k + 1's per-target kernel does (after its own targets): a rank stalls only when a peer is a full
+// step behind, and the exchange is off the critical path of the step (profiles/README.md).
 struct PeerPush {
   int world, rank;             // world == 0: disabled
   const uint64_t* table;       // device array: [0, world) gathered bases, [world, 2 world) flag bases
@@ -20,7 +21,8 @@ struct PeerPush {
   int64_t bytes;               // its size = slot size (multiple of 4)
   unsigned int* ticket;        // device counter for "last push CTA done"
   unsigned long long* epoch;   // pushes completed so far (never rewound: engine resets must not rewind the flags);
-                               // the push in flight is number *epoch + 1, counted by the per-target kernel
+                               // the push in flight is number *epoch + 1, counted by whoever waited for it (the per-
+                               // target kernel's last CTA, or peer_wait_kernel) once every rank's flag carries it
   unsigned int* err;           // bit r: peer r's flag never arrived
 };
 
@@ -71,7 +73,7 @@ struct UkfArgs {
   float* h_tr_pos;
   float* h_tr_vel;
   float* h_ltt;
-  unsigned long long* peer_epoch;   // multi-GPU: push counter to advance (see PeerPush), or NULL
+  PeerPush peer;           // multi-GPU (world == 0: off): the kernel's last CTA ends with the wait for the peers' pushes
   int variant;             // pc_option PC_OPT_FINISH_KERNEL (0 = choose by catalog size)
   pc_ukf_params p;
 };
@@ -88,9 +90,18 @@ cudaError_t launch_peer_push(const PeerPush& pp, cudaStream_t stream);
 cudaError_t launch_peer_wait(const uint64_t* table, int world, int rank, unsigned long long* epoch,
                              unsigned int* err, int advance, cudaStream_t stream);
 
+// End of the per-target kernel, called by every thread of its LAST CTA after the CTA's own work: wait
+// (bounded) for every rank's flag of the push in flight, then count the push.  The sensor kernel that
+// pushed completed before this kernel started, so nobody else reads *epoch any more.
+static __device__ __noinline__ void peer_wait_and_count(const PeerPush& pp) {
+  if ((int)threadIdx.x < pp.world) peer_wait_thread(pp.table, pp.world, pp.rank, pp.epoch, pp.err, (int)threadIdx.x);
+  __syncthreads();
+  if (threadIdx.x == 0) *pp.epoch += 1;
+}
+
 // CTAs of a push: enough 16-byte stores in flight to fill NVLink for megabyte summaries, one CTA for small ones
 inline int peer_push_blocks(int64_t bytes) {
-  const int64_t want = (bytes / 16 + 128 * 8 - 1) / (128 * 8);
+  const int64_t want = (bytes / 16 + 128 * 8 - 1) / (128 * 8);   // eight 16-byte elements per thread and pass
   return (int)(want < 1 ? 1 : (want > 64 ? 64 : want));
 }
 
@@ -102,9 +113,20 @@ __device__ __forceinline__ void peer_push_block(const PeerPush& pp, int block, i
   const int64_t off = ((int64_t)(n & 1) * pp.world + pp.rank) * pp.bytes;
   const int64_t n16 = pp.bytes / 16;
   const uint4* __restrict__ src = reinterpret_cast<const uint4*>(pp.src);
-  for (int64_t i = (int64_t)block * 128 + threadIdx.x; i < n16; i += (int64_t)nblocks * 128) {
-    const uint4 v = src[i];
-    for (int r = 0; r < pp.world; ++r) reinterpret_cast<uint4*>(__ldg(pp.table + r) + off)[i] = v;
+  // eight loads in flight per thread before the first store: the buffer comes cold from HBM (~1 us per
+  // dependent round trip), and a load-store-load-store loop was the whole cost of the push (6 of 8 us)
+  const int64_t stride = (int64_t)nblocks * 128;
+  for (int64_t i0 = (int64_t)block * 128 + threadIdx.x; i0 < n16; i0 += 8 * stride) {
+    uint4 v[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u)
+      if (i0 + u * stride < n16) v[u] = src[i0 + u * stride];
+    for (int r = 0; r < pp.world; ++r) {
+      uint4* dst = reinterpret_cast<uint4*>(__ldg(pp.table + r) + off);
+#pragma unroll
+      for (int u = 0; u < 8; ++u)
+        if (i0 + u * stride < n16) dst[i0 + u * stride] = v[u];
+    }
   }
   if (block == 0) {   // tail words (slot sizes are multiples of 4 bytes, not always of 16)
     const int64_t w0 = n16 * 4, nw = pp.bytes / 4;

@@ -340,14 +340,15 @@ typedef struct pc_step_args {
    * The summaries a step leaves there are needed by the scheduler of the NEXT step and by nothing else of
    * its physics, so the exchange is not the end of step k but a side task of step k + 1: its sensor
    * kernel copies the summary buffer into this rank's slot of EVERY peer's gathered buffer (16-byte
-   * stores over NVLink), publishes the push number in every peer's flag array and waits (bounded) until
-   * all peers' flags carry the same number -- beside the target propagation, which needs none of it;
-   * only the per-target kernel at the end of the step waits for the sensor kernel.  No collective call.
-   * After pc_step_fused number k the gathered buffers therefore hold the summaries of step k - 1 (parity
-   * slot = push count & 1); a caller that needs the summaries of step k before step k + 1 runs (a
-   * scheduler on the host) enqueues pc_peer_exchange, the same push + wait as two stand-alone kernels.
-   * pc_peer_status reports (and clears) a bit per peer whose flag never came, and the number of pushes
-   * completed so far.  All ranks must step in lockstep (same sequence of steps and exchanges). */
+   * stores over NVLink) and publishes the push number in every peer's flag array -- beside the target
+   * propagation, which needs none of it -- and the last CTA of the per-target kernel, after its own
+   * targets, waits (bounded) until all ranks' flags carry that number.  No collective call; a rank stalls
+   * only when a peer is a full step behind.  When pc_step_fused number k completes, the gathered buffers hold every rank's
+   * summaries of step k - 1 (parity slot = push count & 1); a caller that needs the summaries of step k
+   * before step k + 1 runs (a scheduler on the host) enqueues pc_peer_exchange, the same push + wait as
+   * two stand-alone kernels.  pc_peer_status reports (and clears) a bit per peer whose flag never came,
+   * and the number of pushes completed so far.  All ranks must step in lockstep (same sequence of steps
+   * and exchanges). */
   const uint64_t* peer_table;
   int32_t peer_world, peer_rank;
   const void* summary_base;
