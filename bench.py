@@ -495,13 +495,8 @@ def run_own(args):
         state_steps = state_steps_sum / n_roof                  # DOP853 steps per launch, summed over 14 N states
         prof = load_profile_summary(N, M)
 
-        def from_profile(kernel, key):
-            if not prof:
-                return None
-            for name, v in prof.get("kernels", {}).items():
-                if kernel.startswith(name) or name.startswith(kernel.split("<")[0]):
-                    return v.get(key)
-            return None
+        def from_profile(family, key):
+            return (prof or {}).get("kernels", {}).get(family, {}).get(key)
 
         # -- sigma-point propagation: FP64 bound
         prop_name = "propagate_sigma_kernel" if N > 16 * 1024 else "propagate_sigma_single_kernel"

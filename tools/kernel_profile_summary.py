@@ -31,6 +31,8 @@ def sources_sha256():
 
 
 def family(name):
+    if "ukf_finish_quad_kernel" in name and re.search(r"<[^,>]*,\s*(\(bool\))?1>", name):
+        return "ukf_finish_hostblock"      # zero-copy form of pc_step_host: stores into mapped host memory (PCIe-bound)
     for f in FAMILIES:
         if f in name:
             return f
