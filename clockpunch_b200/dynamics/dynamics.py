@@ -1,4 +1,9 @@
-"""Dynamics functions (mirror of punchclock/dynamics/dynamics.py:16-86)."""
+"""Dynamics functions (mirror of punchclock/dynamics/dynamics.py:16-86).
+
+`a2body` and `satelliteDynamics` are the reference's right-hand side as plain numpy, kept because callers
+import them by name (`simplePropagate(satelliteDynamics, ...)` uses the function OBJECT as the tag that
+selects the CUDA propagator).  They are never evaluated on the step path: the integrator in
+csrc/propagate.cuh computes the same expression inside its stages, and nothing in this package calls them."""
 from __future__ import annotations
 
 import numpy as np
