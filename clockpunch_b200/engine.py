@@ -325,11 +325,18 @@ class CatalogEngine:
         together, with equal shard sizes.  torch.distributed is only the transport of the handles;
         a non-torch caller does the same three C calls with its own transport.
         Returns the local gathered tensor, shape (2, world, summary_bytes) uint8: [step parity][source rank]."""
+        import weakref
         import torch.distributed as dist
         torch, c = self.torch, self.ctx
         group = group or dist.group.WORLD
         world, rank = dist.get_world_size(group), dist.get_rank(group)
         nbytes = self.summary.numel()
+        # a library context owns ONE exchange: an engine that had it before loses it (its buffers are freed below)
+        prev = getattr(c, "_peer_engine", None)
+        prev = prev() if prev is not None else None
+        if prev is not None and prev is not self:
+            prev._peer, prev._hs_key, prev._graph = None, None, None
+        c._peer_engine = weakref.ref(self)
         mine = np.zeros(_lib.COMM_HANDLE_BYTES, np.uint8)
         # an exchange left on this context by an earlier engine: every rank unmaps its peers before
         # anybody frees (pc_comm_init frees the old buffer)
