@@ -516,7 +516,8 @@ def run_own(args):
                 "hbm": {"achieved": 14 * 96.0 * N / (p_ms * 1e-3) * 1e-9, "peak": hbm_peak, "unit": "GB/s",
                         "frac": 14 * 96.0 * N / (p_ms * 1e-3) * 1e-9 / hbm_peak, "bytes_per_launch": 14 * 96.0 * N}}
         # -- per-target kernel: HBM bound at large catalogs, latency bound at small ones -- both fractions
-        fin_name = ("ukf_finish_quad_kernel" if N <= 32768 else "ukf_finish_kernel<64>" if N <= 131072 else "ukf_finish_kernel<128>")
+        quad_max = 16384 if w.all_tasked else 32768     # the library's size rule (a tasking mask may be dense)
+        fin_name = ("ukf_finish_quad_kernel" if N <= quad_max else "ukf_finish_kernel<64>" if N <= 131072 else "ukf_finish_kernel<128>")
         bytes_fin = (BYTES_FINISH_TARGET + M / 4.0) * N
         flop_fin = ((1 - tasked_frac) * FLOP_UKF_NOMEAS + tasked_frac * FLOP_UKF_MEAS + FLOP_NEXT_CHOL + 2 * M * FLOP_VIS_PAIR) * N
         gbs = bytes_fin / (f_ms * 1e-3) * 1e-9

@@ -1666,9 +1666,14 @@ static cudaError_t launch_finish_tpb(const UkfArgs& a, cudaStream_t stream) {
 // (sensor tile amortised over more warps).  `variant` (pc_option PC_OPT_FINISH_KERNEL) pins the choice:
 // 1 quad + update warps (when task_of is given), 2 quad with the in-line update, 3 / 4 one thread per
 // target with 64- / 128-thread CTAs; 0 = the size rule.
-static int finish_mapping(int64_t n, int variant) {
+// (mask_only: the tasking comes as a caller's mask without an actions vector, so ANY number of targets may
+// be measured -- BASELINE.json configs[4] measures all of them -- and the four-lane kernel, which replicates
+// the update algebra over its lanes, loses to one thread per target from ~18 k targets on: measured with
+// every target measured, 12 500 targets 45 vs 60 us per step, 25 000 targets 78 vs 69, 32 768 targets 98 vs 75.
+// With an actions vector at most one target per sensor is measured and the crossover stays at 32 k.)
+static int finish_mapping(int64_t n, int variant, bool mask_only = false) {
   if (variant >= 1 && variant <= 4) return variant;
-  if (n <= kQuadMaxTargets) return 1;
+  if (n <= (mask_only ? kQuadMaxTargets / 2 : kQuadMaxTargets)) return 1;
   return n <= 128 * 1024 ? 3 : 4;
 }
 
@@ -1679,7 +1684,7 @@ bool finish_fills_host_mirrors(int64_t n, int64_t sensors, int variant) {
 
 cudaError_t launch_ukf_finish(const UkfArgs& a, cudaStream_t stream) {
   if (a.n <= 0) return cudaSuccess;
-  const int mapping = finish_mapping(a.n, a.variant);
+  const int mapping = finish_mapping(a.n, a.variant, a.tasked != nullptr && a.task_of == nullptr && !a.clear_tasked);
   if (mapping <= 2) {
     const unsigned ctas = (unsigned)((4 * a.n + kQuadThreads - 1) / kQuadThreads);
     if (mapping == 1 && a.task_of && a.task_sensors > 0 && a.task_sensors <= kCoopMaxSensors) {
