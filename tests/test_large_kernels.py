@@ -305,3 +305,41 @@ def test_full_size_oracle_sample():
     orc_filters = [OracleUKF(0.0, cat.est_x[:, i], cat.est_p[i], cat.Q, cat.R) for i in sample]
     orc_truth = cat.targets[:, sample].copy()
     _oracle_check(cat, sample, tk, z, dt, _outputs(eng), 0, orc_filters, orc_truth, eng.host("sens_x"))
+
+
+def test_step_host_zero_copy_at_bench_size_equals_device_path():
+    """configs[1] size through the reference-facing call (pc_step_host, zero-copy output block: the HOST
+    instantiation of the four-lane kernel stores the float32 observation and the summaries into mapped host
+    memory while it runs) against the device-resident graph replay of the same steps: the host block must be
+    the float32 / integer image of the device state, bit for bit, every step."""
+    import torch
+    from clockpunch_b200.simulation.catalog import synth_catalog
+    n, m, dt = 10_000, 100, 100.0
+    cat = synth_catalog(n, m, seed=20240627)
+    a, b = _engine(cat, seed=9), _engine(cat, seed=9)
+    rng = np.random.default_rng(0)
+    g = b.build_graph(dt)
+    hb = a.host_buffers(pinned=True)
+    A = n + m
+    for s in range(4):
+        vis = b.host("vis_est")
+        acts = np.full(m, n, np.int64)
+        for j in range(m):
+            seen = np.flatnonzero(vis[:, j])
+            if len(seen):
+                acts[j] = seen[rng.integers(0, len(seen))]
+        hb["actions"][:m].copy_(torch.from_numpy(acts))
+        a.step_host(hb, dt)
+        b.actions[:m].copy_(torch.from_numpy(acts))
+        b.replay(g)
+        obs = hb["obs"].numpy()
+        np.testing.assert_array_equal(obs[: 6 * A].reshape(6, A)[:, m:], b.host("est_x").astype(np.float32), err_msg=f"eci_state step {s}")
+        np.testing.assert_array_equal(obs[: 6 * A].reshape(6, A)[:, :m], b.host("sens_x").astype(np.float32))
+        np.testing.assert_array_equal(obs[6 * A: 6 * A + 36 * n].reshape(n, 6, 6), b.host("est_p").astype(np.float32), err_msg=f"est_cov step {s}")
+        np.testing.assert_array_equal(obs[6 * A + 36 * n:], (b.time - b.host("last_time_tasked").astype(np.float64)).astype(np.float32))
+        np.testing.assert_array_equal(hb["vis_est"].numpy(), b.vis_est.cpu().numpy(), err_msg=f"vis_est step {s}")
+        np.testing.assert_array_equal(hb["num_tasked"].numpy(), b.host("num_tasked"))
+        np.testing.assert_array_equal(hb["tr_pos"].numpy(), b.host("tr_pos"))
+        for k in ("truth_x", "est_x", "est_p", "pred_p", "vis_truth", "flags"):
+            np.testing.assert_array_equal(a.host(k), b.host(k), err_msg=f"{k} step {s}")
+    assert b.host("num_tasked").sum() > 2 * m
