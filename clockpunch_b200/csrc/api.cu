@@ -88,6 +88,8 @@ struct pc_ctx {
   uint64_t hs_tick = 0;
   const void* hs_zc_ptr = nullptr;   // last host block checked for device accessibility (zero-copy form)
   bool hs_zc_ok = false;
+  const void* hs_act_ptr = nullptr;  // the same for the host actions buffer
+  bool hs_act_ok = false;
   // kernel-mapping overrides (pc_set_option)
   int opt_finish = 0, opt_prop = 0;
   // pc_comm_*: this rank's gathered buffer + flags (one cudaMalloc, shared by CUDA IPC), the peers'
@@ -1210,6 +1212,20 @@ int pc_step_host(pc_ctx* ctx, const pc_step_args* a, const pc_ukf_params* params
     }
     zero_copy = ctx->hs_zc_ok;
   }
+  // ... and the sensor kernel reads the M actions straight from the (device-accessible) host buffer: 8 bytes
+  // per sensor over PCIe inside the tasking warps, off the critical path, instead of a copy node that the
+  // whole step -- propagation included -- would wait for
+  bool direct_actions = io->zero_copy && replayable && copy_actions && a->policy_probes == 0;
+  if (direct_actions) {
+    if (ctx->hs_act_ptr != io->h_actions) {
+      cudaPointerAttributes at{};
+      const cudaError_t e = cudaPointerGetAttributes(&at, io->h_actions);
+      if (e != cudaSuccess) cudaGetLastError();
+      ctx->hs_act_ok = e == cudaSuccess && at.type == cudaMemoryTypeHost && at.devicePointer == io->h_actions;
+      ctx->hs_act_ptr = io->h_actions;
+    }
+    direct_actions = ctx->hs_act_ok;
+  }
   int rc = PC_OK;
   pc_step_args key;
   if (!replayable) {
@@ -1238,6 +1254,7 @@ int pc_step_host(pc_ctx* ctx, const pc_step_args* a, const pc_ukf_params* params
       key.mirror_bytes = 0;
       key.obs_cov_host = nullptr;
     }
+    if (direct_actions) key.actions = const_cast<int64_t*>(io->h_actions);
     a = &key;
     pc_ctx::HsEntry* ent = nullptr;
     for (auto& e : ctx->hs)
@@ -1267,7 +1284,7 @@ int pc_step_host(pc_ctx* ctx, const pc_step_args* a, const pc_ukf_params* params
       cudaGraph_t graph = nullptr;
       PC_CUDA_TRY(ctx, cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal));
       cudaError_t ec = cudaSuccess;
-      if (copy_actions)
+      if (copy_actions && !direct_actions)
         ec = cudaMemcpyAsync(a->actions, io->h_actions, (size_t)a->M * sizeof(int64_t), cudaMemcpyHostToDevice, s);
       rc = ec == cudaSuccess ? step_and_pack(ctx, a, params, io->d_obs, s) : PC_ERR_CUDA;
       if (rc == PC_OK && have_block && !zero_copy)

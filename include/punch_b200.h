@@ -434,7 +434,9 @@ typedef struct pc_step_io {
    * a catalog the update-warp kernel handles (single environment, task_of, N <= 32768, M <= 256), the
    * kernels store the observation and the summaries straight into h_block while they run -- the
    * transfer overlaps the per-target kernel instead of following it -- and no copy is issued (one
-   * initialising copy when the graph is (re)built).  The device observation d_obs is then NOT refreshed.
+   * initialising copy when the graph is (re)built).  With zero_copy != 0 and a device-accessible h_actions
+   * the sensor kernel likewise reads the actions from the host buffer itself (args->actions is then not
+   * written), so that the step does not start behind a copy.  The device observation d_obs is then NOT refreshed.
    * Falls back to the one-copy form when any condition fails. */
   int32_t zero_copy;
 } pc_step_io;
