@@ -176,6 +176,47 @@ print("ROLLOUT_OK")
 
 
 @needs_ref
+def test_reference_simrunner_and_greedy_policy_run_on_the_swapped_env(golden):
+    """simulation/sim_runner.py:63-350 (`SimRunner.runSim`, which deep-copies the wrapped env every step and
+    reads `env.unwrapped._getObs()`, :168-175) with the reference's GreedyCovariance policy
+    (policies/greedy_cov_v2.py), both imported through install_as_punchclock(), on the scenario of the
+    reference's tests/simulation/test_sim_runner.py:86-345: the SimResults equal those of the all-reference
+    stack (tests/golden/make_golden_simrunner.py)."""
+    out = _run('''
+import numpy as np
+import _ref_stubs, sys
+import clockpunch_b200 as cpb
+ref = cpb.install_as_punchclock()
+sys.modules["punchclock.ray.build_ray_policy"] = _ref_stubs._StubModule("punchclock.ray.build_ray_policy")
+import _oracle_engine
+import clockpunch_b200.environment.env as ours
+_oracle_engine.install_cpu_doubles()
+import make_golden_simrunner as mk
+from punchclock.policies.greedy_cov_v2 import GreedyCovariance
+from punchclock.ray.build_env import buildEnv
+from punchclock.simulation.sim_runner import SimRunner
+import punchclock.simulation.sim_runner as sr, punchclock.policies.greedy_cov_v2 as gc
+assert sr.__file__.startswith(ref) and gc.__file__.startswith(ref)
+got, env = mk.run(buildEnv, GreedyCovariance, SimRunner)
+assert type(env.unwrapped) is ours.SSAScheduler and type(env.unwrapped._engine) is _oracle_engine.OracleEngine
+np.savez("/tmp/simrunner_got.npz", **got)
+print("SIMRUNNER_OK")
+''')
+    assert "SIMRUNNER_OK" in out
+    want = golden("simrunner")
+    got = np.load("/tmp/simrunner_got.npz")
+    assert set(want.files) == set(got.files)
+    assert want["info_num_tasked"][-1].sum() >= 5 and len(want["actions"]) == 10
+    for k in want.files:
+        a, w = got[k], want[k]
+        assert a.shape == w.shape and a.dtype == w.dtype, (k, a.shape, w.shape, a.dtype, w.dtype)
+        if w.dtype.kind in "iub":
+            np.testing.assert_array_equal(a, w, err_msg=k)
+        else:
+            np.testing.assert_allclose(a, w, rtol=2e-6, atol=1e-6, err_msg=k, equal_nan=True)
+
+
+@needs_ref
 def test_generic_filter_and_custom_dynamics_are_served_by_the_reference_classes():
     """tests/estimation/test_ukf_v2.py:54-170 of the reference (2-state filter, custom DynamicsModel subclass,
     pass-through measurement) and tests/dynamics/test_propagator.py:10-68 (toy linear ODE) through the
