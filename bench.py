@@ -518,13 +518,16 @@ def run_own(args):
         # -- per-target kernel: HBM bound at large catalogs, latency bound at small ones -- both fractions
         quad_max = 16384 if w.all_tasked else 32768     # the library's size rule (a tasking mask may be dense)
         fin_name = ("ukf_finish_quad_kernel" if N <= quad_max else "ukf_finish_kernel<64>" if N <= 131072 else "ukf_finish_kernel<128>")
-        bytes_fin = (BYTES_FINISH_TARGET + M / 4.0) * N
-        flop_fin = ((1 - tasked_frac) * FLOP_UKF_NOMEAS + tasked_frac * FLOP_UKF_MEAS + FLOP_NEXT_CHOL + 2 * M * FLOP_VIS_PAIR) * N
+        m_seen = M // w.E                               # sensors one target is tested against (its own environment's)
+        vis_bytes = 8.0 * ((m_seen + 31) // 32)         # two packed rows of 32-sensor words
+        bytes_fin = (BYTES_FINISH_TARGET + vis_bytes) * N
+        flop_fin = ((1 - tasked_frac) * FLOP_UKF_NOMEAS + tasked_frac * FLOP_UKF_MEAS + FLOP_NEXT_CHOL + 2 * m_seen * FLOP_VIS_PAIR) * N
         gbs = bytes_fin / (f_ms * 1e-3) * 1e-9
         tfs = flop_fin / (f_ms * 1e-3) * 1e-12
         fin_ncu_ms = from_profile("ukf_finish", "ms_mean")
         fin = {"kernel": fin_name, "bound": "hbm", "achieved": gbs, "peak": hbm_peak, "unit": "GB/s", "frac": gbs / hbm_peak,
-               "kernel_ms": f_ms, "bytes_per_launch": bytes_fin, "algorithmic_bytes_per_unit": BYTES_FINISH_TARGET + M / 4.0,
+               "kernel_ms": f_ms, "bytes_per_launch": bytes_fin, "algorithmic_bytes_per_unit": BYTES_FINISH_TARGET + vis_bytes,
+               "sensors_per_target": m_seen,
                "unit_of_work": "one target: 13 sigma points read, est_p / pred_p / next sigma points written, 2 vis rows",
                "fp64": {"achieved": tfs, "peak": peak_tf, "unit": "TFLOP/s", "frac": tfs / peak_tf, "flop_per_launch": flop_fin},
                "traffic": from_profile("ukf_finish", "dram_bytes"), "kernel_ms_ncu": fin_ncu_ms,

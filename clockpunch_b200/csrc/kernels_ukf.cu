@@ -56,20 +56,6 @@
 
 namespace pc {
 
-struct TargetSmem {   // scratch of the measurement update (thread-local for tasked targets)
-  double D[6][6];     // D[j][a] = (X_{1+j} - X_{7+j})[a]: difference of the propagated +/- pair j
-  double U[21];       // packed upper Cholesky factor (row-major, j >= i)
-  double px[6];       // pred_x
-  double m[6];        // pred_x - X_0
-  double z[6];
-  double xo[6];       // est_x out
-  double nis;
-  uint32_t flags;
-  int pad;
-  double P[36];       // pred_p
-  double PE[36];      // est_p out
-};
-
 __host__ __device__ constexpr int uidx(int i, int j) { return i * 6 - (i * (i - 1)) / 2 + (j - i); }
 
 // Upper Cholesky A = U^T U of a 6x6 symmetric matrix (scipy.linalg.cholesky default,
@@ -152,107 +138,6 @@ __device__ __forceinline__ void repair_chol6_regs(const double (&E)[21], double 
 }
 
 
-// Measurement update for one tasked target, everything addressed in shared memory.
-// forecast / calculateKalmanGain / updateCovariance / calculateInnovations /
-// updateStateEstimate (ukf_v2.py:211-228, 294-375).
-__device__ __noinline__ void measurement_update(TargetSmem* __restrict__ S, const pc_ukf_params& p) {
-  uint32_t flags = 0;
-  // STEP 1: re-sample around (pred_x, pred_p): U2 = chol_upper(pred_p)
-  double* U2 = S->U;
-  if (!chol_upper6(S->P, U2)) {
-    flags |= PC_FLAG_NONPD_PRED;
-    double Ep[21];
-#pragma unroll
-    for (int i = 0; i < 6; ++i)
-#pragma unroll
-      for (int j = i; j < 6; ++j) Ep[uidx(i, j)] = S->P[i * 6 + j];
-    repair_chol6(Ep, U2);
-  }
-
-  const double c3 = p.wc0 - p.wm0;
-  const double cuu = 2.0 * p.wi * p.gamma * p.gamma;
-  const double cdd = p.wc0 + 12.0 * p.wi;
-  const double wg = p.wi * p.gamma;
-  double delta[6], nu[6];
-#pragma unroll
-  for (int c = 0; c < 6; ++c) {
-    delta[c] = p.eps_w * S->px[c];                  // mean_pred_y - pred_x
-    nu[c] = S->z[c] - (S->px[c] + delta[c]);        // innovation (ukf_v2.py:341-343)
-  }
-  // Innovation covariance S = Yres Wc Yres^T + R  (ukf_v2.py:326-329), upper part.
-  double Sm[36];
-#pragma unroll
-  for (int a = 0; a < 6; ++a)
-#pragma unroll
-    for (int b = a; b < 6; ++b) {
-      double acc = 0.0;
-#pragma unroll
-      for (int j = b; j < 6; ++j) acc = fma(U2[uidx(a, j)], U2[uidx(b, j)], acc);
-      Sm[a * 6 + b] = fma(cuu, acc, fma(cdd * delta[a], delta[b], p.R[a * 6 + b]));
-    }
-  double Us[21];
-  if (!chol_upper6(Sm, Us)) flags |= PC_FLAG_NONPD_INNOV;
-  double dinv[6];
-#pragma unroll
-  for (int b = 0; b < 6; ++b) dinv[b] = 1.0 / Us[uidx(b, b)];
-
-  // y = Us^-T nu ; nis = |y|^2  (ukf_v2.py:344-346)
-  double y[6];
-  double nis = 0.0;
-#pragma unroll
-  for (int b = 0; b < 6; ++b) {
-    double acc = nu[b];
-#pragma unroll
-    for (int k = 0; k < b; ++k) acc = fma(-Us[uidx(k, b)], y[k], acc);
-    y[b] = acc * dinv[b];
-    nis = fma(y[b], y[b], nis);
-  }
-  S->nis = nis;
-
-  // Row by row: cross covariance C = Xres Wc Yres^T (ukf_v2.py:330-332), G = C Us^-1.
-  // K = G Us^-T, so K S K^T = G G^T and K nu = G y.
-#pragma unroll 1
-  for (int a = 0; a < 6; ++a) {
-    double D[6];
-#pragma unroll
-    for (int j = 0; j < 6; ++j) D[j] = S->D[j][a];
-    const double sa = delta[a] + c3 * S->m[a];
-    double g[6];
-#pragma unroll
-    for (int b = 0; b < 6; ++b) {
-      double acc = 0.0;
-#pragma unroll
-      for (int j = b; j < 6; ++j) acc = fma(D[j], U2[uidx(b, j)], acc);
-      double cab = fma(wg, acc, sa * delta[b]);
-#pragma unroll
-      for (int k = 0; k < b; ++k) cab = fma(-g[k], Us[uidx(k, b)], cab);
-      g[b] = cab * dinv[b];
-    }
-    double xe = S->px[a];
-#pragma unroll
-    for (int b = 0; b < 6; ++b) {
-      xe = fma(g[b], y[b], xe);
-      S->PE[a * 6 + b] = g[b];  // stash G row; est_p assembled below
-    }
-    S->xo[a] = xe;  // est_x = pred_x + K nu  (ukf_v2.py:373-375)
-  }
-  // est_p = pred_p - K S K^T = pred_p - G G^T  (ukf_v2.py:367-371)
-  double Gm[36];
-#pragma unroll
-  for (int k = 0; k < 36; ++k) Gm[k] = S->PE[k];
-#pragma unroll
-  for (int a = 0; a < 6; ++a)
-#pragma unroll
-    for (int b = a; b < 6; ++b) {
-      double acc = S->P[a * 6 + b];
-#pragma unroll
-      for (int k = 0; k < 6; ++k) acc = fma(-Gm[a * 6 + k], Gm[b * 6 + k], acc);
-      S->PE[a * 6 + b] = acc;
-      S->PE[b * 6 + a] = acc;
-    }
-  S->flags |= flags;
-}
-
 // Upper Cholesky of a symmetric 6x6 given by its packed upper triangle E (uidx order).
 __device__ __forceinline__ bool chol_upper6_packed(const double (&E)[21], double (&U)[21]) {
   bool ok = true;
@@ -275,10 +160,15 @@ __device__ __forceinline__ bool chol_upper6_packed(const double (&E)[21], double
   return ok;
 }
 
-// The same measurement update with everything in registers (inlined): used by the quad kernel,
-// where occupancy is not the constraint and the latency of the local-memory version above would be
-// the critical path of the whole step.  Same operations in the same order as measurement_update,
-// so both produce identical bits.
+// Measurement update for one tasked target: forecast / calculateKalmanGain / updateCovariance /
+// calculateInnovations / updateStateEstimate (ukf_v2.py:211-228, 294-375), every operand in registers
+// (inlined).  Used by the four-lane kernel and by the thread-per-target kernels alike: an out-of-line
+// version with its scratch in thread-local memory (round 1) kept the thread-per-target kernels at 168
+// registers either way and cost 33 us per step at 1024 environments (8 % of the targets measured: nearly
+// every warp holds one) and 16 us at 100 000 targets all measured (profiles/README.md).
+// Innovation covariance S = Yres Wc Yres^T + R (ukf_v2.py:326-329); y = Us^-T nu, nis = |y|^2 (:344-346);
+// cross covariance C = Xres Wc Yres^T (:330-332), G = C Us^-1, K = G Us^-T, so K S K^T = G G^T and
+// K nu = G y; est_x = pred_x + K nu (:373-375), est_p = pred_p - K S K^T (:367-371).
 __device__ __forceinline__ uint32_t measurement_update_reg(
     const double* __restrict__ sb, int64_t ld, int64_t blk, int64_t t, const double (&px)[6],
     const double (&m)[6], const double (&E)[21], const double (&z)[6], const pc_ukf_params& p,
@@ -773,25 +663,10 @@ ukf_finish_kernel(const __grid_constant__ UkfArgs a) {
   if (tasked) {
     const double t_now = a.clock ? a.clock->t_cur + a.dt : a.t_now;
     const uint64_t rng_step = a.clock ? a.clock->step_cur : a.rng_step;
-    TargetSmem L;
-#pragma unroll 1
-    for (int j = 0; j < 6; ++j)
-#pragma unroll
-      for (int c = 0; c < 6; ++c)
-        L.D[j][c] = sb[(1 + j) * blk + (int64_t)c * ld + t] - sb[(7 + j) * blk + (int64_t)c * ld + t];
-#pragma unroll
-    for (int c = 0; c < 6; ++c) {
-      L.px[c] = px[c];
-      L.m[c] = m[c];
-    }
-#pragma unroll
-    for (int ra = 0; ra < 6; ++ra)
-#pragma unroll
-      for (int rb = 0; rb < 6; ++rb) L.P[ra * 6 + rb] = E[ra <= rb ? uidx(ra, rb) : uidx(rb, ra)];
-    L.flags = 0;
+    double z[6];
     if (a.z) {
 #pragma unroll
-      for (int c = 0; c < 6; ++c) L.z[c] = a.z[(int64_t)c * ld + t];
+      for (int c = 0; c < 6; ++c) z[c] = a.z[(int64_t)c * ld + t];
     } else {
       // Target.getMeasurement (agents.py:173-183): z ~ N(truth', R)
       double nrm[6];
@@ -801,21 +676,13 @@ ukf_finish_kernel(const __grid_constant__ UkfArgs a) {
         double acc = sb[13 * blk + (int64_t)c * ld + t];
 #pragma unroll
         for (int k = 0; k <= c; ++k) acc = fma(a.p.Lr[c * 6 + k], nrm[k], acc);
-        L.z[c] = acc;
+        z[c] = acc;
       }
     }
-    measurement_update(&L, a.p);
-    flags |= L.flags;
-    nis = L.nis;
-#pragma unroll
-    for (int c = 0; c < 6; ++c) xe[c] = L.xo[c];
-#pragma unroll
-    for (int ra = 0; ra < 6; ++ra)
-#pragma unroll
-      for (int rb = ra; rb < 6; ++rb) PE[uidx(ra, rb)] = L.PE[ra * 6 + rb];
+    flags |= measurement_update_reg(sb, ld, blk, t, px, m, E, z, a.p, xe, PE, nis);
     if (a.out_z) {
 #pragma unroll
-      for (int c = 0; c < 6; ++c) a.out_z[(int64_t)c * ld + t] = L.z[c];
+      for (int c = 0; c < 6; ++c) a.out_z[(int64_t)c * ld + t] = z[c];
     }
     if (a.num_tasked) a.num_tasked[t] += 1;
     if (a.last_time_tasked) a.last_time_tasked[t] = (float)t_now;

@@ -1,6 +1,6 @@
 """Parity of the per-target kernels that run the LARGE configurations (BASELINE.json configs[2..4]):
-ukf_finish_kernel<64> (32 769 .. 131 072 targets) and ukf_finish_kernel<128> (above), the local-memory
-measurement_update they carry, their shared-memory covariance stores and the bulk-copied sensor tile
+ukf_finish_kernel<64> (32 769 .. 131 072 targets) and ukf_finish_kernel<128> (above), the in-line
+measurement update they carry, their shared-memory covariance stores and the bulk-copied sensor tile
 (clockpunch_b200/csrc/kernels_ukf.cu).  They evaluate UnscentedKalmanFilter.predictAndUpdate
 (punchclock/estimation/ukf_v2.py:185-375) + Target.updateNonPhysical (common/agents.py:144-171) + one row
 of both vis maps (common/visibility.py:56-116) with a different thread mapping than the four-lanes-per-
