@@ -516,7 +516,7 @@ def run_own(args):
                 "hbm": {"achieved": 14 * 96.0 * N / (p_ms * 1e-3) * 1e-9, "peak": hbm_peak, "unit": "GB/s",
                         "frac": 14 * 96.0 * N / (p_ms * 1e-3) * 1e-9 / hbm_peak, "bytes_per_launch": 14 * 96.0 * N}}
         # -- per-target kernel: HBM bound at large catalogs, latency bound at small ones -- both fractions
-        quad_max = 16384 if w.all_tasked else 32768     # the library's size rule (a tasking mask may be dense)
+        quad_max = 8192 if w.all_tasked else 32768     # the library's size rule (a tasking mask may be dense)
         heavy = w.all_tasked or M * 16 >= N             # many measured targets per step: the 255-register build
         fin_name = ("ukf_finish_quad_kernel" if N <= quad_max else "ukf_finish_kernel<64, 4>" if heavy else
                     "ukf_finish_kernel<64, 6>" if N <= 131072 else "ukf_finish_kernel<128, 3>")

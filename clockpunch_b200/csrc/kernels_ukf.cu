@@ -1207,7 +1207,7 @@ __device__ __forceinline__ void store_sym36_quad_f32(float* __restrict__ g, cons
 // PCIe transfer then runs under this kernel instead of behind it.  A separate instantiation, so that the
 // device-only step does not carry the code.
 template <bool COOP, bool HOST>
-__global__ void __launch_bounds__(kQuadThreads, 3)
+__global__ void __launch_bounds__(kQuadThreads, COOP ? 3 : 2)   // in-line update: 255 registers (168: 732 bytes of spills)
 ukf_finish_quad_kernel(const __grid_constant__ UkfArgs a) {
   constexpr bool ROLE = COOP;
   __shared__ __align__(32) unsigned char smem_raw[kQuadSmem];
@@ -1539,12 +1539,13 @@ static cudaError_t launch_finish_tpb(const UkfArgs& a, cudaStream_t stream) {
 // target with 64- / 128-thread CTAs; 0 = the size rule.
 // (mask_only: the tasking comes as a caller's mask without an actions vector, so ANY number of targets may
 // be measured -- BASELINE.json configs[4] measures all of them -- and the four-lane kernel, which replicates
-// the update algebra over its lanes, loses to one thread per target from ~18 k targets on: measured with
-// every target measured, 12 500 targets 45 vs 60 us per step, 25 000 targets 78 vs 69, 32 768 targets 98 vs 75.
+// the update algebra over its lanes, loses to one thread per target from ~10 k targets on: measured with
+// every target measured, us per step, four lanes (255-register build) vs one thread (255-register build):
+// 6 250 targets 30.7 vs 37.3, 12 500 targets 49.3 vs 41.0, 16 384 targets 52.5 vs 43.9.
 // With an actions vector at most one target per sensor is measured and the crossover stays at 32 k.)
 static int finish_mapping(int64_t n, int variant, bool mask_only = false) {
   if (variant >= 1 && variant <= 4) return variant;
-  if (n <= (mask_only ? kQuadMaxTargets / 2 : kQuadMaxTargets)) return 1;
+  if (n <= (mask_only ? kQuadMaxTargets / 4 : kQuadMaxTargets)) return 1;
   return n <= 128 * 1024 ? 3 : 4;
 }
 
