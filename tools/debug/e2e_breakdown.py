@@ -1,47 +1,60 @@
-"""Where the e2e step time goes at the bench size (host clock)."""
-import sys, os, time
+"""Where the end-to-end step of configs[1] goes (host clock, no L2 flush -- as bench.py's e2e pass):
+python tools/debug/e2e_breakdown.py"""
+import sys, os, time, ctypes as C
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import numpy as np, torch
+# optional: run on the cores of the GPU's NUMA node (E2E_NODE=local) or on the others (E2E_NODE=remote)
+if os.environ.get("E2E_NODE"):
+    import pynvml as nv
+    nv.nvmlInit()
+    bus = nv.nvmlDeviceGetPciInfo(nv.nvmlDeviceGetHandleByIndex(0)).busId
+    bus = (bus.decode() if isinstance(bus, bytes) else bus).lower()
+    bus = bus[4:] if len(bus) > 12 else bus
+    node = int(open(f"/sys/bus/pci/devices/{bus}/numa_node").read())
+    nodes = sorted(int(d[4:]) for d in os.listdir("/sys/devices/system/node") if d.startswith("node") and d[4:].isdigit())
+    def cpus(nd):
+        out = set()
+        for part in open(f"/sys/devices/system/node/node{nd}/cpulist").read().strip().split(","):
+            lo, _, hi = part.partition("-")
+            out.update(range(int(lo), int(hi or lo) + 1))
+        return out
+    allowed = set(os.sched_getaffinity(0))
+    local = cpus(node) & allowed if node >= 0 else set()
+    remote = allowed - local
+    pick = local if os.environ["E2E_NODE"] == "local" else remote
+    print(f"GPU 0 on NUMA node {node} of {nodes}; allowed cores {len(allowed)}, local {len(local)}, remote {len(remote)}; using {os.environ['E2E_NODE']}")
+    if pick:
+        os.sched_setaffinity(0, pick)
 from clockpunch_b200.engine import CatalogEngine
 from clockpunch_b200.simulation.catalog import synth_catalog
 SEED = 20240627
-N, M = int(sys.argv[1]) if len(sys.argv) > 1 else 10000, 100
+N, M, dt, K = 10000, 100, 100.0, 400
 cat = synth_catalog(N, M, seed=SEED, sensor_seed=SEED)
 eng = CatalogEngine(cat.sensors, cat.sensor_kinds, cat.targets, cat.est_x, cat.est_p, cat.Q, cat.R, device=0, seed=SEED)
+lib = eng.ctx.lib
 hb = eng.host_buffers()
-hb["actions"].fill_(N)
-def loop(fn, n=200):
-    for _ in range(20): fn()
-    t = time.perf_counter()
-    for _ in range(n): fn()
-    return (time.perf_counter() - t) / n * 1e6
-full = loop(lambda: eng.step_host(hb, 100.0))
-print(f"step_host (H2D actions, graph, D2H obs+vis+nt, sync): {full:.1f} us")
-hb2 = dict(hb)
-import ctypes as C
-# variants: drop outputs one at a time by passing smaller dicts is not supported; time raw copies instead
+hv, ha = C.c_void_p(hb["vis_est"].data_ptr()), C.c_void_p(hb["actions"].data_ptr())
+hb["vis_est"].copy_(eng.vis_est)
+def policy(k): lib.pc_policy_random_visible_envs_host(hv, 1, N, M, eng.wpr, SEED, k, 64, ha)
+def loop(fn, n=K, episode=50):
+    """Episodes of 50 steps from the initial catalog, like bench.py (the reset is untimed)."""
+    tot = 0.0
+    for k0 in range(0, n, episode):
+        eng.reset(); eng.ensure_sigma(); hb["vis_est"].copy_(eng.vis_est); torch.cuda.synchronize()
+        for k in range(5): fn(k)
+        torch.cuda.synchronize(); t = time.perf_counter()
+        for k in range(episode): fn(5 + k0 + k)
+        torch.cuda.synchronize(); tot += time.perf_counter() - t
+    return tot / n * 1e6
+print("host policy alone             %.1f us" % loop(policy))
+def full(k): policy(k); eng.step_host(hb, dt)
+print("policy + step_host (zero copy) %.1f us" % loop(full))
+print("step_host (zero copy)          %.1f us" % loop(lambda k: eng.step_host(hb, dt)))
+eng._hs_key = None
+print("step_host (one D2H copy node)  %.1f us" % loop(lambda k: eng.step_host(hb, dt, zero_copy=False)))
+g = eng.build_graph(dt)                      # tasking from eng.actions (device), no host block
 s = torch.cuda.current_stream()
-def d2h_obs():
-    hb["obs"].copy_(eng.obs_f32, non_blocking=True); s.synchronize()
-def d2h_vis():
-    hb["vis_est"].copy_(eng.vis_est, non_blocking=True); s.synchronize()
-def d2h_nt():
-    hb["num_tasked"].copy_(eng.num_tasked, non_blocking=True); s.synchronize()
-def sync_only():
-    s.synchronize()
-print(f"D2H obs ({hb['obs'].numel()*4/1e6:.2f} MB) + sync: {loop(d2h_obs):.1f} us; vis: {loop(d2h_vis):.1f} us; num_tasked: {loop(d2h_nt):.1f} us; bare sync {loop(sync_only):.1f} us")
-g = eng.build_graph(100.0, pack_obs=True)
-def graph_only():
-    eng.replay(g); s.synchronize()
-print(f"graph replay (step + obs pack) + sync: {loop(graph_only):.1f} us")
-rng = np.random.default_rng(0)
-probe_tab = rng.integers(0, N, size=(256, M, 64))
-jcol = np.arange(M)[:, None]; jw, jb = jcol >> 5, (jcol & 31).astype(np.uint32); rows = np.arange(M)
-h_vis_np = hb["vis_est"].numpy().view(np.uint32); h_act_np = hb["actions"].numpy()
-k = [0]
-def host_policy():
-    probes = probe_tab[k[0] % 256]; k[0] += 1
-    hit = (h_vis_np[probes, jw] >> jb) & 1
-    first = hit.argmax(axis=1)
-    h_act_np[:M] = np.where(hit[rows, first] != 0, probes[rows, first], N)
-print(f"host policy (numpy): {loop(host_policy):.1f} us")
+def dev(k): eng.replay(g); s.synchronize()
+print("graph replay + stream sync     %.1f us" % loop(dev))
+def dev2(k): eng.replay(g)
+print("graph replay back to back      %.1f us" % loop(dev2))
