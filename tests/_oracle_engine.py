@@ -142,17 +142,15 @@ class OracleEngine:
 
 
 def install_cpu_doubles():
-    """Route the CUDA entry points that BUILDING and stepping an SSAScheduler reaches to the oracle, for the
-    CPU-only seam test (see the module docstring): the engine, the frame / element conversions used for
-    initial conditions, and calcVisMap.  Everything else of clockpunch_b200 stays as shipped (and keeps
-    raising without a GPU)."""
+    """Route the CUDA entry points that the mirrored modules reach to the oracle, for the CPU-only seam tests
+    (see the module docstring): the engine, the frame / element conversions used for initial conditions as
+    Python functions; the host-buffer entry points of the library (propagation, filter step,
+    visibility map / value / derivative, visibility history) through an object with the library's own interface.
+    Returns that context (its `lib.calls` counts the entry points used)."""
     import clockpunch_b200.common.transforms as tr
-    import clockpunch_b200.common.visibility as vis
     import clockpunch_b200.environment.env as env
-    import clockpunch_b200.environment.env_utils as env_utils
     import clockpunch_b200.simulation.sim_utils as su
     from oracle import dynamics as od
-    from oracle.visibility import calc_vis_map
 
     def frame_change(x, JD, to_eci):
         x = tr._check_dimensions(x)
@@ -167,10 +165,14 @@ def install_cpu_doubles():
         lla = np.asarray(lla, dtype=np.float64)[:3]
         return np.stack([od.ecef2eci(od.lla2ecef(lla[:, i]), JD) for i in range(lla.shape[1])], axis=1)
 
-    def calcVisMap(sensor_states, target_states, body_radius=None, binary=True):
-        return calc_vis_map(sensor_states, target_states, binary=binary)
-
     tr._frame_change, tr.coe2eci_batch, tr.lla2eci_batch, tr.lla2ecef = frame_change, coe2eci_batch, lla2eci_batch, od.lla2ecef
     su.coe2eci_batch, su.lla2eci_batch = coe2eci_batch, lla2eci_batch
-    vis.calcVisMap = env_utils.calcVisMap = calcVisMap
     env.CatalogEngine = OracleEngine
+    # every other mirrored function reaches the library through `_lib.get_ctx().lib.pc_*_host(...)` with host
+    # buffers: those entry points are served by tests/_oracle_lib.OracleLib (same names, arguments and status
+    # codes), so that the mirrors' own marshalling code runs
+    import clockpunch_b200._lib as lib
+    from _oracle_lib import OracleContext
+    ctx = OracleContext()
+    lib.get_ctx = lambda device=None: ctx
+    return ctx

@@ -72,10 +72,12 @@ pkg.__path__ = ["/root/reference/punchclock"]
 sys.modules["punchclock"] = pkg
 # satvis arithmetic -> oracle restatement
 import satvis.visibility_func as svf  # noqa: E402
-from oracle.visibility import is_vis, visibility_func  # noqa: E402
+from oracle.visibility import calc_vis_and_der_vis, is_vis, visibility_func  # noqa: E402
 
 svf.isVis = lambda r1, r2, RE, hg=0: is_vis(r1, r2, RE, hg)
 svf.visibilityFunc = lambda r1, r2, RE, hg=0, tol=1e-13: visibility_func(r1, r2, RE, hg, tol)
+svf.calcVisAndDerVis = lambda r1, r1dot, r1mag_dot, r2, r2dot, r2mag_dot, RE, hg=0: calc_vis_and_der_vis(
+    r1, r1dot, r1mag_dot, r2, r2dot, r2mag_dot, RE, hg)
 # the Ray-checkpoint policy loader drags RLlib + the torch nets in (sim_utils.py:15 -> ray/build_ray_policy.py
 # -> nets/*: `torch, nn = try_import_torch()`): stub that one module; the custom-policy builder and the
 # policies themselves are the reference's own

@@ -217,6 +217,55 @@ print("SIMRUNNER_OK")
 
 
 @needs_ref
+def test_reference_info_wrappers_that_call_the_hot_path_run_on_the_mirrors(golden):
+    """environment/info_wrappers.py `NumWindows` (:163-637: AccessWindowCalculator forecast recalculated on every
+    step, from `env.agents` and their filters) and `VisMap` (:1572-1771: calcVisMapAndDerivative of the estimated
+    states), stacked by the reference's buildEnv -- the reference's wrapper classes, imported through
+    install_as_punchclock(), bind the MIRRORED AccessWindowCalculator / calcVisMapAndDerivative / agents, whose calls
+    reach the library's host entry points (pc_vis_history_host, pc_vismap_der_host; here tests/_oracle_lib.py).
+    The rollout equals the all-reference stack's (tests/golden/make_golden_infowrap.py)."""
+    out = _run('''
+import numpy as np
+import _ref_stubs, sys
+import clockpunch_b200 as cpb
+ref = cpb.install_as_punchclock()
+sys.modules["punchclock.ray.build_ray_policy"] = _ref_stubs._StubModule("punchclock.ray.build_ray_policy")
+import _oracle_engine
+ctx = _oracle_engine.install_cpu_doubles()
+import make_golden_infowrap as mk
+from punchclock.ray.build_env import buildEnv
+import punchclock.environment.info_wrappers as iw
+import clockpunch_b200.schedule_tree.access_windows as aw, clockpunch_b200.common.visibility as vis
+assert iw.__file__.startswith(ref)
+assert iw.AccessWindowCalculator is aw.AccessWindowCalculator and iw.calcVisMapAndDerivative is vis.calcVisMapAndDerivative
+got, env = mk.rollout(buildEnv)
+assert str(env).startswith("<VisMap<NumWindows<"), str(env)
+assert ctx.lib.calls.get("pc_vis_history_host", 0) >= mk.STEPS and ctx.lib.calls.get("pc_vismap_der_host", 0) >= mk.STEPS, ctx.lib.calls
+np.savez("/tmp/infowrap_got.npz", **got)
+print("INFOWRAP_OK", ctx.lib.calls)
+''')
+    assert "INFOWRAP_OK" in out
+    want = golden("infowrap")
+    got = np.load("/tmp/infowrap_got.npz")
+    # `vis_map_dot`: the VisMap wrapper hands the FLOAT32 info["est_x"] to calcVisMapAndDerivative, and the reference
+    # then evaluates its orbit-element chain for d|r|/dt (orbits.py:39-69) in float32 -- for an Earth-fixed sensor
+    # (e = 0.997, apogee) that is a catastrophic cancellation: on these very inputs the reference differs from ITSELF
+    # by up to 4e-3 rad/s between float32 and float64 arguments of equal value (asserted below from the golden, which
+    # holds both).  The library always computes in float64, so it is compared with the reference's float64 evaluation.
+    ref32, ref64 = want["step_vis_map_dot"], want["step_vis_map_dot64"]
+    assert np.abs(ref32 - ref64).max() > 1e-3
+    assert set(want.files) - {"reset_vis_map_dot64", "step_vis_map_dot64"} == set(got.files), set(want.files) ^ set(got.files)
+    assert want["step_num_tasked"][-1].sum() >= 3 and want["step_num_windows_left"].max() >= 3
+    for k in got.files:
+        a, w = got[k], want[k + "64" if k.endswith("vis_map_dot") else k]
+        assert a.shape == w.shape and a.dtype == w.dtype, (k, a.shape, w.shape, a.dtype, w.dtype)
+        if w.dtype.kind in "iub":
+            np.testing.assert_array_equal(a, w, err_msg=k)
+        else:
+            np.testing.assert_allclose(a, w, rtol=2e-6, atol=1e-6, err_msg=k, equal_nan=True)
+
+
+@needs_ref
 def test_generic_filter_and_custom_dynamics_are_served_by_the_reference_classes():
     """tests/estimation/test_ukf_v2.py:54-170 of the reference (2-state filter, custom DynamicsModel subclass,
     pass-through measurement) and tests/dynamics/test_propagator.py:10-68 (toy linear ODE) through the
