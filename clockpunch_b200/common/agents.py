@@ -126,11 +126,12 @@ def getRandomIC(satellite_terrestrial: str = "satellite", time: float = 0) -> nd
         lla = rng.uniform([-pi / 2, -pi, RE + 400], [pi / 2, pi, RE + 36000])
         r = lla2ecef(lla)[:3]
         v_mag = sqrt(getConstants()["mu"] / norm(r))          # getCircOrbitVel, orbits.py:26-36
-        a_hat = r / norm(r)                                     # normalVec, math.py:192-210
-        b = rng.uniform(size=3)
+        a_hat = r / norm(r)                                     # normalVec, math.py:192-210 (its own generator)
+        rng_b = default_rng()
+        b = rng_b.uniform(size=3)
         b_hat = b / norm(b)
         while a_hat @ b_hat == 1:
-            b = rng.uniform(size=3)
+            b = rng_b.uniform(size=3)
             b_hat = b / norm(b)
         return concatenate([r, v_mag * cross(a_hat, b_hat)])
     if satellite_terrestrial == "terrestrial":

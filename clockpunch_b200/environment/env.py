@@ -248,11 +248,17 @@ class SSAScheduler(_EnvBase):
         self.updateInfoPreTasking(action)
         e, hb = self._engine, self._hb
         hb["actions"][: self.num_sensors].copy_(e.torch.from_numpy(action.astype(np.int64)))
+        # the reference propagates every agent TO info["time_now"] (env.py:560-562), which is one time step
+        # ahead of the agents unless a caller has advanced the clock by hand (updateInfoPreTasking on its own,
+        # as tests/environment/test_env.py:113-126 does): then the interval is longer
+        dt = float(self.info["time_now"]) - float(e.time)
+        if abs(dt - self.time_step) <= 1e-9 * max(1.0, abs(float(self.info["time_now"]))):
+            dt = self.time_step
         if measurements is None:
-            e.step_host(hb, self.time_step)
+            e.step_host(hb, dt)
         else:
             z = np.where(np.isnan(measurements), 0.0, np.asarray(measurements, float))
-            e.step(dt=self.time_step, z=z, actions=hb["actions"][: self.num_sensors].numpy())
+            e.step(dt=dt, z=z, actions=hb["actions"][: self.num_sensors].numpy())
             e.pack_obs()
             hb["obs"].copy_(e.obs_f32)
             hb["vis_est"].copy_(e.vis_est)
@@ -268,6 +274,30 @@ class SSAScheduler(_EnvBase):
         else:
             done = False
         return observation, reward, done, False, info
+
+    # -- the two halves of the reference's step as separate calls (env.py:464-506; its own
+    #    tests/environment/test_env.py:157-163 drives them by hand between updateInfoPreTasking and
+    #    updateInfoPostTasking) -------------------------------------------------------------------------
+    def _propagateAgents(self, time):
+        """Propagate all agents to `time` (env.py:503-506).  The engine advances truth states and filters in ONE
+        launch, so this only records the instant; the `_taskAgents` call that follows it in the reference's step
+        (env.py:560-575) performs both.  `env.agents` read in between still shows the previous instant."""
+        self._pending_time = float(time)
+
+    def _taskAgents(self, actions_array, vis_map_est) -> None:
+        """(N, M) binary assignments, masked by the estimated map: a target with a 1 left in its row gets a
+        measurement, every other target's filter is advanced without one (env.py:464-501)."""
+        masked = np.multiply(np.asarray(actions_array), np.asarray(vis_map_est))
+        tasked = (masked == 1).any(axis=1).astype(np.uint8)
+        t_next = getattr(self, "_pending_time", None)
+        e, hb = self._engine, self._hb
+        e.step(t_next=float(self.info["time_now"]) if t_next is None else t_next, tasked=tasked)
+        self._pending_time = None
+        e.pack_obs()
+        hb["obs"].copy_(e.obs_f32)
+        hb["vis_est"].copy_(e.vis_est)
+        hb["num_tasked"].copy_(e.num_tasked)
+        self._agents_stale = True
 
     def _getVarMeans(self):
         est_cov = self.info["est_cov"]

@@ -117,6 +117,36 @@ class AccessWindowCalculator:
             out[i] = nxt - i
         return out
 
+    # -- helpers of the reference class that its own tests call (tests/schedule_tree/test_access_windows.py);
+    #    calcVisHist above does not need them: the whole history is one library call --------------------------
+    def _setup(self, x_sensors: ndarray, x_targets: ndarray, t: float):
+        """Time vector and surrogate agents (access_windows.py:337-366)."""
+        self.t_now = t
+        self.time_vec = self._genTime()
+        self.sensors = self._buildAgents(x=x_sensors, time=self.t_now, dynamics=self.dynamics_sensors)
+        self.targets = self._buildAgents(x=x_targets, time=self.t_now, dynamics=self.dynamics_targets)
+
+    def _getStates(self) -> ndarray:
+        """(6, M + N) current states of the surrogate agents (access_windows.py:368-380)."""
+        return np.asarray([agent.eci_state for agent in self.sensors + self.targets]).squeeze().transpose()
+
+    def _getVis(self, x_sensors: ndarray, x_targets: ndarray) -> ndarray:
+        """(N, M) binary visibility of the given states (access_windows.py:382-402)."""
+        from ..common.visibility import calcVisMap
+        return np.asarray(calcVisMap(np.asarray(x_sensors, dtype=np.float64).reshape(6, -1),
+                                     np.asarray(x_targets, dtype=np.float64).reshape(6, -1), body_radius=self.RE), dtype=int)
+
+    def _buildAgents(self, x: ndarray, time: float, dynamics) -> list:
+        """Generic agents at the columns of x (access_windows.py:431-477)."""
+        from ..common.agents import Agent
+        from ..dynamics.dynamics_classes import SatDynamicsModel, StaticTerrestrial
+        dynamics_model_map = {"terrestrial": StaticTerrestrial(), "satellite": SatDynamicsModel()}
+        if isinstance(dynamics, (str, DynamicsModel)):
+            dynamics = [dynamics for _ in range(x.shape[1])]
+        if isinstance(dynamics[0], str):
+            dynamics = [dynamics_model_map[d] for d in dynamics]
+        return [Agent(dynamics_model=dyn, init_eci_state=x[:, i], time=time) for i, dyn in zip(range(x.shape[1]), dynamics)]
+
     def sumWindows(self, vis_hist: ndarray, vis_hist_targets: ndarray, merge_windows: bool) -> ndarray:
         if merge_windows is False:
             return np.sum(np.sum(vis_hist, axis=2), axis=0)

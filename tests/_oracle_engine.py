@@ -149,7 +149,8 @@ def install_cpu_doubles():
     Returns that context (its `lib.calls` counts the entry points used)."""
     import clockpunch_b200.common.transforms as tr
     import clockpunch_b200.environment.env as env
-    import clockpunch_b200.simulation.sim_utils as su
+    import clockpunch_b200.common.agents  # noqa: F401  (binds lla2ecef by name)
+    import clockpunch_b200.simulation.sim_utils  # noqa: F401  (binds the batch conversions by name)
     from oracle import dynamics as od
 
     def frame_change(x, JD, to_eci):
@@ -165,8 +166,15 @@ def install_cpu_doubles():
         lla = np.asarray(lla, dtype=np.float64)[:3]
         return np.stack([od.ecef2eci(od.lla2ecef(lla[:, i]), JD) for i in range(lla.shape[1])], axis=1)
 
-    tr._frame_change, tr.coe2eci_batch, tr.lla2eci_batch, tr.lla2ecef = frame_change, coe2eci_batch, lla2eci_batch, od.lla2ecef
-    su.coe2eci_batch, su.lla2eci_batch = coe2eci_batch, lla2eci_batch
+    # (modules that bound these names with `from ... import` get the doubles as well)
+    import sys
+    swaps = {tr._frame_change: frame_change, tr.coe2eci_batch: coe2eci_batch, tr.lla2eci_batch: lla2eci_batch,
+             tr.lla2ecef: od.lla2ecef}
+    for name, mod in list(sys.modules.items()):
+        if name.startswith("clockpunch_b200") and mod is not None:
+            for attr, val in list(vars(mod).items()):
+                if callable(val) and val in swaps:
+                    setattr(mod, attr, swaps[val])
     env.CatalogEngine = OracleEngine
     # every other mirrored function reaches the library through `_lib.get_ctx().lib.pc_*_host(...)` with host
     # buffers: those entry points are served by tests/_oracle_lib.OracleLib (same names, arguments and status

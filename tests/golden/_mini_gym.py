@@ -529,7 +529,15 @@ def install():
     envs = module("gymnasium.envs", registration=registration, register=register, registry=registry)
     core = module("gymnasium.core", Env=Env, Wrapper=Wrapper, ObservationWrapper=ObservationWrapper,
                   RewardWrapper=RewardWrapper, ActionWrapper=ActionWrapper)
-    gym = module("gymnasium", Env=Env, Wrapper=Wrapper, ObservationWrapper=ObservationWrapper,
+    # gymnasium.utils.env_checker.check_env: the reference's tests/environment/test_env.py calls it; here it only
+    # resets and steps the env once with a sampled action
+    def check_env(env, *a, **k):
+        env.reset()
+        env.step(env.action_space.sample())
+
+    env_checker = module("gymnasium.utils.env_checker", check_env=check_env)
+    gutils = module("gymnasium.utils", env_checker=env_checker)
+    gym = module("gymnasium", utils=gutils, Env=Env, Wrapper=Wrapper, ObservationWrapper=ObservationWrapper,
                  RewardWrapper=RewardWrapper, ActionWrapper=ActionWrapper, Space=Space, spaces=spaces,
                  wrappers=wrappers, envs=envs, core=core, register=register, make=make, registry=registry,
                  __version__="0.26.3-mini", __mini_gym__=True)

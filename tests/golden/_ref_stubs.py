@@ -16,10 +16,24 @@ sys.path.insert(0, ROOT)
 np.Inf = np.inf
 
 
-class _Anything:
-    """Permissive class: any attribute, call or subscript works."""
+class _AnyMeta(type):
+    """Class-level attribute access on a fabricated class (`plt.subplots` where `plt` is one) works too."""
+    def __getattr__(cls, name):
+        if name.startswith("__"):
+            raise AttributeError(name)
+        return _Anything()
+
+
+class _Anything(metaclass=_AnyMeta):
+    """Permissive class: any attribute, call, subscript or two-way unpacking works."""
     def __init__(self, *a, **k):
         pass
+
+    def __getitem__(self, item):
+        return _Anything()
+
+    def __iter__(self):
+        return iter((_Anything(), _Anything()))
 
     def __call__(self, *a, **k):
         return _Anything()
