@@ -68,6 +68,20 @@ class TaskingMetricTracker:
         return (self.unique_tasks, self.targets_tasked, self.non_vis_tasked_est, self.non_vis_tasked_truth,
                 self.multiple_taskings, self.non_vis_by_sensor_est, self.non_vis_by_sensor_truth)
 
+    def _calcNonVisTaskings(self, vis_mask: ndarray, actions: ndarray) -> Tuple:
+        """(number of taskings of a non-visible target, the same per sensor (M,)) for one (N, M) mask and one
+        (M,) action vector (metrics.py:252-291) -- the O(M) form: a tasking is non-visible iff the mask entry
+        of its (target, sensor) pair is not 1."""
+        actions, vis_mask = np.asarray(actions), np.asarray(vis_mask)
+        assert len(actions) == self.num_sensors
+        assert vis_mask.shape == (self.num_targets, self.num_sensors)
+        sens = np.nonzero(actions < self.num_targets)[0]
+        # the reference forms (actions - actions * mask) and counts its ones
+        miss = (1 - vis_mask[actions[sens].astype(np.int64), sens]) == 1
+        by_sensor = zeros([self.num_sensors], dtype=int)
+        by_sensor[sens] = (1 - vis_mask[actions[sens].astype(np.int64), sens]).astype(int)
+        return int(np.count_nonzero(miss)), by_sensor
+
     def update(self, actions: ndarray, vis_mask_est: ndarray, vis_mask_truth: ndarray) -> Tuple:
         """Reference signature: dense (N, M) 0/1 masks (metrics.py:161-250)."""
         for m in (vis_mask_est, vis_mask_truth):

@@ -18,13 +18,16 @@ SCRIPTS = [
     "tests/dynamics/test_dynamics_classes.py", "tests/dynamics/test_propagator.py", "tests/estimation/test_ez_ukf.py",
     "tests/estimation/test_ukf_v2.py", "tests/estimation/test_filter_base_class.py", "tests/environment/test_env.py",
     "tests/environment/test_env_utils.py", "tests/environment/test_env_parameters.py",
-    "tests/schedule_tree/test_access_windows.py", "tests/simulation/test_sim_utils.py",
+    "tests/schedule_tree/test_access_windows.py", "tests/simulation/test_sim_utils.py", "tests/common/test_metrics.py",
+    "tests/common/test_utilities.py", "tests/common/test_orbits.py", "tests/policies/test_greedy_cov_v2.py",
+    "tests/policies/test_random_policy.py",
 ]
 
 
 def run(mode, script, ref=REF):
+    # (PYTHONHASHSEED: the scripts print lists made from sets)
     r = subprocess.run([sys.executable, os.path.join(HERE, "_run_ref_script.py"), mode, ref, script],
-                       capture_output=True, text=True, cwd="/tmp", timeout=900)
+                       capture_output=True, text=True, cwd="/tmp", timeout=900, env=dict(os.environ, PYTHONHASHSEED="0"))
     return r.returncode, r.stdout, r.stderr
 
 
