@@ -187,6 +187,50 @@ def test_env_device_draw_horizon_reset_and_deepcopy(golden):
 
 
 @pytest.mark.gpu
+def test_step_halves_by_hand_and_clock_advanced_by_hand(golden):
+    """The way the reference's own tests/environment/test_env.py:113-163 drives the env: (a) updateInfoPreTasking ->
+    _propagateAgents(info["time_now"]) -> _taskAgents(actions_array, vis_map) -> updateInfoPostTasking equals step()
+    with the same action (same seed, same step counter: same measurement draw); (b) a clock advanced by hand first
+    makes the next step propagate every agent TO info["time_now"], i.e. over two time steps (env.py:560-562)."""
+    from copy import deepcopy
+    from clockpunch_b200.common.utilities import actionSpace2Array
+    from clockpunch_b200.dynamics.propagator import propagate_batch
+    from clockpunch_b200.environment.env import SSAScheduler
+    g = golden("env")
+    env = SSAScheduler(_Params(100.0, 50, _agents_from_golden(g, "default")), seed=5)
+    env.reset()
+    N, M = env.num_targets, env.num_sensors
+    vm = env._getInfo()["vis_map_est"]
+    a = np.array([int(np.flatnonzero(vm[:, j])[0]) if vm[:, j].any() else N for j in range(M)])
+    assert (a < N).any()
+    whole, halves = deepcopy(env), deepcopy(env)
+    obs_w, _, _, _, info_w = whole.step(a)
+    halves.updateInfoPreTasking(a)
+    halves._propagateAgents(halves.info["time_now"])
+    halves._taskAgents(actionSpace2Array(a, M, N)[:-1, :], vm)
+    halves.updateInfoPostTasking()
+    info_h = halves._getInfo()
+    assert info_h["time_now"] == info_w["time_now"] == 100.0
+    np.testing.assert_array_equal(info_h["num_tasked"], info_w["num_tasked"])
+    assert sum(info_w["num_tasked"]) >= 1
+    np.testing.assert_array_equal(info_h["true_states"], info_w["true_states"])
+    np.testing.assert_array_equal(info_h["vis_map_truth"], info_w["vis_map_truth"])
+    # actions path (update warps) vs mask path (in-line update): same equations, sums in a different order
+    np.testing.assert_allclose(info_h["est_x"], info_w["est_x"], rtol=1e-6, atol=1e-4)
+    np.testing.assert_allclose(info_h["est_cov"], info_w["est_cov"], rtol=1e-5, atol=1e-9)
+    for t_h, t_w in zip(halves.agents, whole.agents):
+        assert t_h.time == t_w.time == 100.0
+    # (b)
+    late = deepcopy(env)
+    x0 = late._engine.host("truth_x")
+    late.updateInfoPreTasking(np.full(M, N))              # clock -> 100 s, agents stay at 0
+    _, _, _, _, info_l = late.step(np.full(M, N))         # clock -> 200 s: agents propagate 0 -> 200 in this step
+    assert info_l["time_now"] == 200.0 and late._engine.time == 200.0
+    np.testing.assert_array_equal(late._engine.host("truth_x"), propagate_batch(x0, 0.0, 200.0))
+    assert all(ag.time == 200.0 for ag in late.agents)
+
+
+@pytest.mark.gpu
 def test_c1_default_env_full_episode():
     """BASELINE.json configs[0] shape through the drop-in env: 3 ground sensors, 10 LEO targets
     generated with the reference's own generator semantics (genInitStates LLA / COE), reference
