@@ -336,13 +336,15 @@ def run_own(args):
     class Workload:
         """A catalog shard on this rank + its exchange + its step graph."""
 
-        def __init__(self, n, m, dt, seed, all_tasked=False, num_envs=1, mix="mixed"):
+        def __init__(self, n, m, dt, seed, all_tasked=False, num_envs=1, mix="mixed", space_sensor_frac=0.0,
+                     force_model=_lib.FORCE_TWOBODY):
             self.n, self.m, self.dt, self.all_tasked, self.E = n, m, dt, all_tasked, num_envs
             # every rank owns its own shard of targets; the sensor network is replicated
-            self.cat = synth_catalog(n, m, seed=seed + 1000 * rank, sensor_seed=seed, mix=mix)
+            self.cat = synth_catalog(n, m, seed=seed + 1000 * rank, sensor_seed=seed, mix=mix,
+                                     space_sensor_frac=space_sensor_frac)
             c = self.cat
             self.eng = CatalogEngine(c.sensors, c.sensor_kinds, c.targets, c.est_x, c.est_p, c.Q, c.R, device=local,
-                                     seed=seed + rank, num_envs=num_envs)
+                                     seed=seed + rank, num_envs=num_envs, force_model=force_model)
             self.sg, self.exchange, self.use_nccl, self.post = None, "none", False, None
             # per-step summaries every rank needs from every other (SURVEY.md section 8e): packed est vis map,
             # trace(P_pos), trace(P_vel), last_time_tasked, num_tasked.  Default: the NEXT step's sensor kernel copies
@@ -423,6 +425,28 @@ def run_own(args):
             wall = time.perf_counter() - wall0
             ms = max_over_ranks(sum(a.elapsed_time(b) for a, b in evs)) / steps
             return ms, wall, self.graph.pc_launches * steps
+
+    def back_to_back(w, steps, episode=EPISODE):
+        """The same graph replayed back to back, no L2 flush between steps (what a rollout does; the headline keeps
+        the flush the timing rules ask for): one event pair around each episode."""
+        tot = 0.0
+        for k0 in range(0, steps, episode):
+            w.eng.reset()
+            w.eng.ensure_sigma()
+            for _ in range(3):
+                w.step()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            barrier()
+            a.record()
+            n = min(episode, steps - k0)
+            for _ in range(n):
+                w.step()
+            if w.eng._peer is not None:
+                w.eng.peer_sync()
+            b.record()
+            torch.cuda.synchronize(dev)
+            tot += a.elapsed_time(b)
+        return max_over_ranks(tot) / steps
 
     def roofline_kernels(w, steps_done_before, warmup, n_roof):
         """Per-kernel rooflines of one workload (a separate pass): the step's kernels launched one by one (not the
@@ -552,6 +576,7 @@ def run_own(args):
     ms_per_step, wall, launches = head.timed(args.steps, args.warmup)
     value = world * N / (ms_per_step * 1e-3)
 
+    b2b_ms = back_to_back(head, min(args.steps, 200))
     n_roof = max(3, min(args.steps, 50))
     prop, fin, roof_note, tasked_frac, flags_bad, flop_prop = roofline_kernels(head, 0, args.warmup, n_roof)
     flop_per_target_step = flop_prop / N + (1 - tasked_frac) * FLOP_UKF_NOMEAS + tasked_frac * FLOP_UKF_MEAS \
@@ -656,10 +681,22 @@ def run_own(args):
                    "roofline": [p2, f2]}
             if unit_name:
                 out[unit_name] = total_units / (ms * 1e-3)
+            if kw.get("force_model", _lib.FORCE_TWOBODY) != _lib.FORCE_TWOBODY:
+                out["roofline_note"] = ("flop and FP64-instruction counts of the propagation kernel are the TWO-BODY figures "
+                                        "(1150 flop / 435 instructions per DOP853 step); the J2 term adds work that is not counted")
             extra_cfgs[key] = out
             del w, hb2
             torch.cuda.empty_cache()
 
+        # BASELINE.json words configs[1] as "100 ground/space sensors ... two-body+J2".  The reference's dynamics are
+        # two-body only (dynamics.py:16-40), so the headline -- which is compared with the
+        # reference's CPU path -- runs two-body with the reference's default ground sensors; this line is the same
+        # catalog with 20 of the 100 sensors in LEO and the J2 term switched on (no reference counterpart: J2 is
+        # checked against scipy in tests/test_gpu_parity.py)
+        if args.targets == 10_000 and args.sensors == 100:
+            run_extra("c2_j2_space_sensors", "BASELINE.json configs[1] as worded: 80 ground + 20 LEO space sensors x 10 000 mixed "
+                      "LEO/MEO/GEO targets, two-body + J2, dt = 100 s", 10_000, 100, DT, 0, None, space_sensor_frac=0.2,
+                      force_model=_lib.FORCE_TWOBODY_J2)
         run_extra("c4_shard", "BASELINE.json configs[3] shard: 125 000 debris targets per GPU x 100 sensors, 60 s steps "
                   "(8 GPUs = the 1 M-object catalog)", 125_000, 100, 60.0, 0, None)
         n5 = 100_000 // world
@@ -706,6 +743,9 @@ def run_own(args):
             "extra": {"tasked_per_step": tasked_frac * N, "flagged_targets": flags_bad,
                       "wall_s_timed_region": wall, "launches_per_step": launches / args.steps, "cuda_graph": True,
                       "exchange": head_exchange, "target_propagation_steps_per_s": 14 * value,
+                      "back_to_back": {"ms_per_step": b2b_ms, "target_steps_per_s": world * N / (b2b_ms * 1e-3),
+                                       "note": "the same step graph replayed back to back WITHOUT the L2 flush between steps "
+                                               "(a rollout); informational, the headline keeps the flush"},
                       "configs": extra_cfgs}}
     emit(line)
     leave()
