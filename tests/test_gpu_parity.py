@@ -104,6 +104,42 @@ def test_propagate_substep_override_and_j2(dyn):
     assert np.abs(out - tb)[:3].max() > 1e-3            # J2 really is on
 
 
+def test_step_with_j2_and_space_sensors():
+    """The bench's `c2_j2_space_sensors` line (BASELINE.json configs[1] as worded): the FUSED step with the J2 force
+    model and sensors in orbit.  No reference counterpart, so the step is checked against the library's own
+    stand-alone kernels, which test_propagate_substep_override_and_j2 pins to scipy: truth states and sensors equal
+    propagate_batch(J2) bit for bit, an unmeasured target's estimate is its J2-propagated centre point, the true
+    visibility map is the map of those states, and a measured target moves towards its measurement."""
+    from clockpunch_b200 import _lib
+    from clockpunch_b200.common.visibility import calcVisMap
+    from clockpunch_b200.dynamics.propagator import propagate_batch
+    from clockpunch_b200.engine import CatalogEngine
+    from clockpunch_b200.simulation.catalog import synth_catalog
+    cat = synth_catalog(3000, 40, seed=99, space_sensor_frac=0.25)
+    assert (cat.sensor_kinds == _lib.KIND_SATELLITE).sum() == 10
+    eng = CatalogEngine(cat.sensors, cat.sensor_kinds, cat.targets, cat.est_x, cat.est_p, cat.Q, cat.R, seed=3,
+                        force_model=_lib.FORCE_TWOBODY_J2)
+    two = CatalogEngine(cat.sensors, cat.sensor_kinds, cat.targets, cat.est_x, cat.est_p, cat.Q, cat.R, seed=3)
+    tasked = np.zeros(cat.N, np.uint8); tasked[::50] = 1
+    z = propagate_batch(cat.targets, 0.0, 100.0, force_model=_lib.FORCE_TWOBODY_J2)
+    eng.step(100.0, tasked=tasked, z=z)
+    two.step(100.0, tasked=tasked, z=z)
+    x1, s1 = eng.host("truth_x"), eng.host("sens_x")
+    np.testing.assert_array_equal(x1, z)
+    np.testing.assert_array_equal(s1, propagate_batch(cat.sensors, 0.0, 100.0, kind=cat.sensor_kinds, force_model=_lib.FORCE_TWOBODY_J2))
+    assert np.abs(x1 - two.host("truth_x"))[:3].max() > 1e-3          # J2 really is on in the step
+    un = tasked == 0
+    ex = eng.host("est_x")
+    np.testing.assert_array_equal(ex[:, un], propagate_batch(cat.est_x, 0.0, 100.0, force_model=_lib.FORCE_TWOBODY_J2)[:, un])
+    vt = eng.host("vis_truth")
+    np.testing.assert_array_equal(vt, calcVisMap(s1, x1))
+    # measured targets: pulled from the (noisy) prediction to the exact measurement
+    d0 = np.linalg.norm((propagate_batch(cat.est_x, 0.0, 100.0, force_model=_lib.FORCE_TWOBODY_J2) - z)[:3, ~un], axis=0)
+    d1 = np.linalg.norm((ex - z)[:3, ~un], axis=0)
+    assert (d1 < d0).all() and d1.mean() < 0.5 * d0.mean()
+    assert (eng.host("flags") & ~np.uint32(_lib.FLAG_SUBSTEP_CLAMP) == 0).all()
+
+
 def test_transforms_golden(golden, dyn):
     from clockpunch_b200.common import transforms as T
     _, ter = dyn
