@@ -2,6 +2,8 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <thread>
+#include <sched.h>
 #include <new>
 #include <string>
 #include <utility>
@@ -760,19 +762,40 @@ int pc_policy_random_visible_envs_host(const uint32_t* vis_est, int64_t E, int64
   if (E <= 0 || env_targets <= 0 || env_sensors < 0 || probes < 0 || words_per_row != (env_sensors + 31) / 32)
     return PC_ERR_BAD_ARG;
   if (env_sensors > 0 && (!vis_est || !actions)) return PC_ERR_BAD_ARG;
-  for (int64_t j = 0; j < E * env_sensors; ++j) {   // the tasking warps of pre_step_kernel, one sensor at a time
-    const int64_t e = j / env_sensors, jl = j - e * env_sensors, t0 = e * env_targets;
-    const uint64_t base = splitmix64_host(seed ^ splitmix64_host(step * 0x100000001B3ull + (uint64_t)j));
-    int64_t pick = env_targets;
-    for (int k = 0; k < probes; ++k) {
-      const int64_t i = (int64_t)(splitmix64_host(base + (uint64_t)k) % (uint64_t)env_targets);
-      if ((vis_est[(t0 + i) * words_per_row + (jl >> 5)] >> (jl & 31)) & 1u) {
-        pick = i;
-        break;
+  const int64_t total = E * env_sensors;
+  auto range = [=](int64_t j0, int64_t j1) {   // the tasking warps of pre_step_kernel, one sensor at a time
+    for (int64_t j = j0; j < j1; ++j) {
+      const int64_t e = j / env_sensors, jl = j - e * env_sensors, t0 = e * env_targets;
+      const uint64_t base = splitmix64_host(seed ^ splitmix64_host(step * 0x100000001B3ull + (uint64_t)j));
+      int64_t pick = env_targets;
+      for (int k = 0; k < probes; ++k) {
+        const int64_t i = (int64_t)(splitmix64_host(base + (uint64_t)k) % (uint64_t)env_targets);
+        if ((vis_est[(t0 + i) * words_per_row + (jl >> 5)] >> (jl & 31)) & 1u) {
+          pick = i;
+          break;
+        }
       }
+      actions[j] = pick;
     }
-    actions[j] = pick;
+  };
+  // sensors are independent: a batch of environments (10 240 sensors at BASELINE.json configs[2]: 0.9 ms on one
+  // core, more than the device step and the observation copy together) is split over the cores this process may use
+  int64_t threads = 1;
+  if (total >= 4096) {
+    cpu_set_t set;
+    CPU_ZERO(&set);
+    const int allowed = sched_getaffinity(0, sizeof(set), &set) == 0 ? CPU_COUNT(&set) : 1;
+    threads = std::min<int64_t>(std::min<int64_t>(allowed, 8), total / 1024);
   }
+  if (threads <= 1) {
+    range(0, total);
+    return PC_OK;
+  }
+  std::vector<std::thread> pool;
+  const int64_t per = (total + threads - 1) / threads;
+  for (int64_t t = 1; t < threads; ++t) pool.emplace_back(range, t * per, std::min(total, (t + 1) * per));
+  range(0, std::min(total, per));
+  for (auto& th : pool) th.join();
   return PC_OK;
 }
 

@@ -152,3 +152,48 @@ def test_host_policy_matches_restatement():
                     break
             assert out[j] == want, (N, M, j)
     assert lib.pc_policy_random_visible_host(None, 10, 3, 5, 0, 0, 4, None) == -1      # wrong words_per_row
+
+
+def test_host_policy_of_a_batch_of_environments_is_the_same_on_one_core_and_on_many():
+    """pc_policy_random_visible_envs_host splits the sensors of a large batch over the cores the process may use
+    (10 240 sensors at BASELINE.json configs[2]); every sensor's pick depends on its own counters only, so the
+    threaded result must equal the one-core result, and both the restatement of the hash for sampled sensors."""
+    import os
+    import numpy as np
+    from clockpunch_b200 import _lib
+    lib = _lib.load_library()
+    M64 = (1 << 64) - 1
+
+    def sm(x):
+        x = (x + 0x9E3779B97F4A7C15) & M64
+        x = ((x ^ (x >> 30)) * 0xBF58476D1CE4E5B9) & M64
+        x = ((x ^ (x >> 27)) * 0x94D049BB133111EB) & M64
+        return x ^ (x >> 31)
+
+    E, Ne, Me, probes, seed, step = 700, 100, 10, 32, 5, 9
+    rng = np.random.default_rng(1)
+    dense = rng.random((E * Ne, Me)) < 0.06
+    packed = np.zeros((E * Ne, 1), np.uint32)
+    for j in range(Me):
+        packed[:, 0] |= dense[:, j].astype(np.uint32) << np.uint32(j)
+    many = np.full(E * Me, -7, np.int64)
+    assert lib.pc_policy_random_visible_envs_host(packed.ctypes.data, E, Ne, Me, 1, seed, step, probes, many.ctypes.data) == 0
+    allowed = os.sched_getaffinity(0)
+    one = np.full(E * Me, -7, np.int64)
+    try:
+        os.sched_setaffinity(0, {min(allowed)})
+        assert lib.pc_policy_random_visible_envs_host(packed.ctypes.data, E, Ne, Me, 1, seed, step, probes, one.ctypes.data) == 0
+    finally:
+        os.sched_setaffinity(0, allowed)
+    np.testing.assert_array_equal(many, one)
+    assert 0.3 < (many < Ne).mean() < 1.0
+    for j in list(range(0, E * Me, 397)) + [E * Me - 1]:
+        e, jl = divmod(j, Me)
+        base = sm(seed ^ sm((step * 0x100000001B3 + j) & M64))
+        want = Ne
+        for k in range(probes):
+            i = sm((base + k) & M64) % Ne
+            if dense[e * Ne + i, jl]:
+                want = i
+                break
+        assert many[j] == want, j

@@ -1,5 +1,5 @@
-"""Where the end-to-end step of configs[1] goes (host clock, no L2 flush -- as bench.py's e2e pass):
-python tools/debug/e2e_breakdown.py"""
+"""Where the end-to-end step goes (host clock, no L2 flush -- as bench.py's e2e pass):
+python tools/debug/e2e_breakdown.py [targets sensors envs dt]      (default: configs[1]; configs[2]: 102400 10240 1024 100)"""
 import sys, os, time, ctypes as C
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import numpy as np, torch
@@ -28,14 +28,15 @@ if os.environ.get("E2E_NODE"):
 from clockpunch_b200.engine import CatalogEngine
 from clockpunch_b200.simulation.catalog import synth_catalog
 SEED = 20240627
-N, M, dt, K = 10000, 100, 100.0, 400
-cat = synth_catalog(N, M, seed=SEED, sensor_seed=SEED)
-eng = CatalogEngine(cat.sensors, cat.sensor_kinds, cat.targets, cat.est_x, cat.est_p, cat.Q, cat.R, device=0, seed=SEED)
+N, M, E, dt = (int(sys.argv[1]), int(sys.argv[2]), int(sys.argv[3]), float(sys.argv[4])) if len(sys.argv) > 4 else (10000, 100, 1, 100.0)
+K = 400 if N <= 20000 else 100
+cat = synth_catalog(N, M, seed=SEED, sensor_seed=SEED, mix="mixed" if E == 1 else "LEO")
+eng = CatalogEngine(cat.sensors, cat.sensor_kinds, cat.targets, cat.est_x, cat.est_p, cat.Q, cat.R, device=0, seed=SEED, num_envs=E)
 lib = eng.ctx.lib
 hb = eng.host_buffers()
 hv, ha = C.c_void_p(hb["vis_est"].data_ptr()), C.c_void_p(hb["actions"].data_ptr())
 hb["vis_est"].copy_(eng.vis_est)
-def policy(k): lib.pc_policy_random_visible_envs_host(hv, 1, N, M, eng.wpr, SEED, k, 64, ha)
+def policy(k): lib.pc_policy_random_visible_envs_host(hv, E, N // E, M // E, eng.wpr, SEED, k, 64, ha)
 def loop(fn, n=K, episode=50):
     """Episodes of 50 steps from the initial catalog, like bench.py (the reset is untimed)."""
     tot = 0.0
