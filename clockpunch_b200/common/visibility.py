@@ -75,5 +75,8 @@ def calcVisMapAndDerivative(sensor_states: ndarray, target_states: ndarray, body
 def unpack_vis_words(words: ndarray, M: int) -> ndarray:
     """(N, ceil(M/32)) uint32 packed map -> (N, M) int64, host-side view helper."""
     words = np.ascontiguousarray(words, dtype=np.uint32)
-    bits = np.unpackbits(words.view(np.uint8), axis=1, bitorder="little")
+    if words.shape[1] == 1 and M <= 24:      # few sensors (a batch of environments): only the bytes that hold them
+        bits = np.unpackbits(words.view(np.uint8)[:, : (M + 7) // 8], axis=1, bitorder="little")
+    else:
+        bits = np.unpackbits(words.view(np.uint8), axis=1, bitorder="little")
     return bits[:, :M].astype(np.int64)

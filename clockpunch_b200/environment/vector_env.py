@@ -23,7 +23,11 @@ class VectorSSAScheduler:
     (or one (6, 6) P0 for all), shared Q, R, time_step and horizon."""
 
     def __init__(self, sensors, sensor_kinds, targets, est_x, est_p, Q, R, time_step: float, horizon: int,
-                 device: int | None = None, seed: int | None = None):
+                 device: int | None = None, seed: int | None = None, copy: bool = True):
+        """copy (as gymnasium.vector.SyncVectorEnv's): True returns fresh observation arrays every step; False
+        returns views of the pinned host block the step writes (valid until the next step / reset) and saves the
+        16 MB of copies a 1024-environment observation costs."""
+        self.copy = bool(copy)
         if seed is None:
             from .env import fresh_seed
             seed = fresh_seed()
@@ -50,12 +54,13 @@ class VectorSSAScheduler:
         o = self._hb["obs"].numpy()
         n0, n1 = 6 * E * A, 36 * E * N
         words = self._hb["vis_est"].numpy().view(np.uint32)
+        own = (lambda a: a.copy()) if self.copy else (lambda a: a)
         return OrderedDict({
-            "eci_state": o[:n0].reshape(E, 6, A).copy(),
-            "est_cov": o[n0: n0 + n1].reshape(E, N, 6, 6).copy(),
+            "eci_state": own(o[:n0].reshape(E, 6, A)),
+            "est_cov": own(o[n0: n0 + n1].reshape(E, N, 6, 6)),
             "vis_map_est": unpack_vis_words(words, M).reshape(E, N, M),
-            "obs_staleness": o[n0 + n1:].reshape(E, 1, N).copy(),
-            "num_tasked": self._hb["num_tasked"].numpy().reshape(E, 1, N).copy()})
+            "obs_staleness": own(o[n0 + n1:].reshape(E, 1, N)),
+            "num_tasked": own(self._hb["num_tasked"].numpy().reshape(E, 1, N))})
 
     def reset(self, seed: int | None = None):
         """New episode; the measurement-noise stream keeps running unless `seed` restarts it."""
@@ -76,8 +81,11 @@ class VectorSSAScheduler:
         e, hb = self._engine, self._hb
         a = np.ascontiguousarray(np.asarray(actions, dtype=np.int64).reshape(E * M))
         hb["actions"][: E * M].copy_(e.torch.from_numpy(a))
+        traces = None
         if measurements is None:
             e.step_host(hb, self.time_step)
+            # float32 traces of the float32 covariance blocks, formed by the step kernel (env.py:599-609)
+            traces = (hb["tr_pos"].numpy().reshape(E, N), hb["tr_vel"].numpy().reshape(E, N))
         else:
             z = np.asarray(measurements, dtype=np.float64)               # (E, 6, N)
             z = np.where(np.isnan(z), 0.0, z).transpose(1, 0, 2).reshape(6, E * N)
@@ -88,10 +96,13 @@ class VectorSSAScheduler:
             hb["num_tasked"].copy_(e.num_tasked)
         self.num_steps += 1
         obs = self._obs()
+        if traces is None:
+            traces = (np.trace(obs["est_cov"][:, :, :3, :3], axis1=2, axis2=3), np.trace(obs["est_cov"][:, :, 3:, 3:], axis1=2, axis2=3))
         info = {"time_now": e.time, "num_steps": self.num_steps,
-                "mean_pos_var": np.trace(obs["est_cov"][:, :, :3, :3], axis1=2, axis2=3).mean(axis=1),
-                "mean_vel_var": np.trace(obs["est_cov"][:, :, 3:, 3:], axis1=2, axis2=3).mean(axis=1)}
+                "mean_pos_var": traces[0].mean(axis=1), "mean_vel_var": traces[1].mean(axis=1)}
         done = np.full(E, self.num_steps == self.horizon)
         if done[0]:
+            if not self.copy:      # the reset below rewrites the host block these views point into
+                obs = OrderedDict((k, v.copy()) for k, v in obs.items())
             self.reset()
         return obs, np.zeros(E), done, np.zeros(E, dtype=bool), info

@@ -57,7 +57,11 @@ def test_c3_shape_rollout_stepping():
     T = cat.targets.reshape(6, E, N).transpose(1, 0, 2)
     X = cat.est_x.reshape(6, E, N).transpose(1, 0, 2)
     venv = VectorSSAScheduler(S, cat.sensor_kinds.reshape(E, M), T, X, cat.est_p[0], cat.Q, cat.R, 100.0, horizon=4, seed=1)
+    # the same batch returning VIEWS of the pinned host block instead of copies (copy=False, as gymnasium's vector envs)
+    views = VectorSSAScheduler(S, cat.sensor_kinds.reshape(E, M), T, X, cat.est_p[0], cat.Q, cat.R, 100.0, horizon=4, seed=1,
+                               copy=False)
     obs0, _ = venv.reset()
+    views.reset()
     rng = np.random.default_rng(0)
     for s in range(4):
         vis = obs0["vis_map_est"] if s == 0 else obs["vis_map_est"]
@@ -65,6 +69,16 @@ def test_c3_shape_rollout_stepping():
         has = vis.any(axis=1)                                   # (E, M)
         actions = np.where(has, vis.argmax(axis=1), N)
         obs, rew, done, trunc, info = venv.step(actions)
+        obs_v, _, _, _, info_v = views.step(actions)
+        for k in obs:
+            np.testing.assert_array_equal(obs_v[k], obs[k], err_msg=k)
+        # (on the horizon step the env resets itself, which rewrites the block: that step returns copies)
+        assert np.shares_memory(obs_v["est_cov"], views._hb["obs"].numpy()) == (s < 3)
+        assert not np.shares_memory(obs["est_cov"], venv._hb["obs"].numpy())
+        np.testing.assert_array_equal(info_v["mean_pos_var"], info["mean_pos_var"])
+        # the kernel's float32 traces are the traces of the float32 observation (env.py:599-609)
+        np.testing.assert_allclose(info["mean_pos_var"], np.trace(obs["est_cov"][:, :, :3, :3], axis1=2, axis2=3).mean(axis=1), rtol=2e-6)
+        np.testing.assert_allclose(info["mean_vel_var"], np.trace(obs["est_cov"][:, :, 3:, 3:], axis1=2, axis2=3).mean(axis=1), rtol=2e-6)
         assert obs["eci_state"].shape == (E, 6, M + N) and obs["eci_state"].dtype == np.float32
         assert obs["est_cov"].shape == (E, N, 6, 6) and obs["vis_map_est"].shape == (E, N, M)
         assert obs["obs_staleness"].shape == (E, 1, N) and obs["num_tasked"].dtype == np.int64

@@ -27,5 +27,14 @@ t1 = time.perf_counter()
 for k in range(steps):                     # env-level: dict observation with the (E, N, M) int64 map
     venv.step(acts[5 + k])
 t2 = time.perf_counter()
+views = VectorSSAScheduler(S, cat.sensor_kinds.reshape(E, M), T, X, cat.est_p[0], cat.Q, cat.R, 100.0, horizon=10**9, seed=1, copy=False)
+views.reset()
+for k in range(5):
+    views.step(acts[k])
+t3 = time.perf_counter()
+for k in range(steps):                     # env-level, observation arrays as views of the pinned block
+    views.step(acts[5 + k])
+t4 = time.perf_counter()
+print(f"VectorSSAScheduler(copy=False).step {1e3*(t4-t3)/steps:.3f} ms/step = {E*steps/(t4-t3):.3g} env-steps/s")
 print(f"E={E} envs x {N} targets x {M} sensors: step_host {1e3*(t1-t0)/steps:.3f} ms/step = {E*steps/(t1-t0):.3g} env-steps/s "
       f"({E*N*steps/(t1-t0):.3g} target-steps/s); VectorSSAScheduler.step {1e3*(t2-t1)/steps:.3f} ms/step = {E*steps/(t2-t1):.3g} env-steps/s")
