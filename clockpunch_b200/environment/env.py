@@ -70,6 +70,30 @@ def fresh_seed() -> int:
     return int.from_bytes(os.urandom(8), "little") >> 1
 
 
+_IMMUTABLE = (int, float, str, bool, bytes, type(None), np.generic)
+
+
+def _independent_copy(v):
+    """What deepcopy(v) returns for the kinds of values the info dict holds, without visiting every scalar:
+    arrays are copied, lists of immutables are copied shallowly (their items cannot be changed in place), lists of
+    flat dicts (the agent map) entry by entry; anything else falls back to deepcopy."""
+    if isinstance(v, np.ndarray):
+        return v.copy()
+    if isinstance(v, _IMMUTABLE):
+        return v
+    if isinstance(v, list):
+        kinds = set(map(type, v))                       # (the distinct item types: a handful, found at C speed)
+        if all(issubclass(t, _IMMUTABLE) for t in kinds):
+            return list(v)
+        if kinds == {dict}:
+            inner = set()
+            for x in v:
+                inner.update(map(type, x.values()))
+            if all(issubclass(t, _IMMUTABLE) for t in inner):
+                return [dict(x) for x in v]
+    return deepcopy(v)
+
+
 class SSAScheduler(_EnvBase):
     metadata = {"render_modes": [None]}
 
@@ -215,13 +239,22 @@ class SSAScheduler(_EnvBase):
         self.info["vis_map_est"] = unpack_vis_words(self._hb["vis_est"].numpy().view(np.uint32), M)
 
     def _getObs(self) -> OrderedDict:
-        info = self._getInfo()
+        """env.py:261-270: five entries of (a copy of) the info."""
+        self._check_info()
+        info = self.info
         return OrderedDict({
-            "eci_state": info["est_x"], "est_cov": info["est_cov"], "vis_map_est": info["vis_map_est"],
+            "eci_state": info["est_x"].copy(), "est_cov": info["est_cov"].copy(), "vis_map_est": info["vis_map_est"].copy(),
             "obs_staleness": np.asarray(info["obs_staleness"], dtype=float32).reshape((1, -1)),
             "num_tasked": np.asarray(info["num_tasked"]).reshape((1, -1))})
 
     def _getInfo(self) -> dict:
+        """A deep copy of the info after the reference's shape / dtype checks (env.py:279-325).  `deepcopy` walks
+        every Python scalar of the per-target lists and every entry of the agent map (60 ms per step at 10 000
+        targets); the same independent copy is built per value kind instead."""
+        self._check_info()
+        return {k: _independent_copy(v) for k, v in self.info.items()}
+
+    def _check_info(self) -> None:
         i, N, M, A = self.info, self.num_targets, self.num_sensors, self.num_agents
         assert i["est_x"].shape == (6, A), "est_x must have shape (6, N+M)"
         assert i["est_cov"].shape == (N, 6, 6), "est_cov must have shape (N, 6, 6)"
@@ -236,7 +269,6 @@ class SSAScheduler(_EnvBase):
         assert isinstance(i["num_tasked"][0], int64), "Entries of num_tasked must be ints"
         assert len(i["obs_staleness"]) == N, "obs_staleness must be N-long list"
         assert isinstance(i["obs_staleness"][0], float), "Entries of obs_staleness must be floats"
-        return deepcopy(self.info)
 
     def _earnReward(self, actions) -> float:
         return 0
