@@ -711,6 +711,65 @@ def run_own(args):
         extra_cfgs["c3"]["scaling"] = "strong"
         extra_cfgs["c3"]["e2e_env_steps_per_s"] = 1024 / (extra_cfgs["c3"]["e2e_ms_per_step"] * 1e-3)
 
+    # BASELINE.json configs[0]: the reference's DEFAULT SSAScheduler env (3 ground sensors, 10 LEO targets, a UKF per
+    # target), one 100-step episode through the Gymnasium API of the drop-in env -- dict observation and info built
+    # every step, one library call per step.  The reference runs this episode on the CPU in 17.5 s.
+    if not args.no_extra_configs and rank == 0:
+        try:
+            from clockpunch_b200.environment.env import SSAScheduler
+            from clockpunch_b200.environment.env_parameters import SSASchedulerParams
+            env1 = SSAScheduler(SSASchedulerParams(horizon=100, agent_params={"num_sensors": 3, "num_targets": 10}, seed=3), seed=3)
+            assert env1.num_sensors == 3 and env1.num_targets == 10
+            obs1, _ = env1.reset()
+            rng1 = np.random.default_rng(0)
+            e1 = env1._engine
+            c1_state = dict(sens=e1.host("sens_x"), targ=e1.host("truth_x"), est_x=e1.host("est_x"), est_p=e1.host("est_p"),
+                            Q=np.array(e1.params.Q[:]).reshape(6, 6), R=np.array(e1.params.R[:]).reshape(6, 6))
+
+            def episode():
+                o = obs1
+                t0e = time.perf_counter()
+                for _ in range(100):
+                    vis = o["vis_map_est"]
+                    act = np.where(vis.any(axis=0), (vis * (1 + rng1.random(vis.shape))).argmax(axis=0), env1.num_targets)
+                    o, _, done1, _, info1 = env1.step(act)
+                return time.perf_counter() - t0e, done1, info1
+
+            episode()                                    # warm-up episode (graph capture); the env resets itself at the horizon
+            secs, done1, info1 = episode()
+            extra_cfgs["c1_default_env_episode"] = {
+                "workload": "BASELINE.json configs[0]: default SSAScheduler env (3 ground sensors x 10 LEO targets, UKF per "
+                            "target), one 100-step episode through env.step (dict observation + info every step)",
+                "episode_s": secs, "ms_per_env_step": 10.0 * secs, "env_steps_per_s": 100.0 / secs,
+                "target_steps_per_s": 1000.0 / secs, "episode_done": bool(done1), "sensors": 3, "targets": 10,
+                "reference_note": "the reference's own profile of this config: 17.5 s per episode (SURVEY.md section 8d, measured in "
+                                  "the build container); cpu_episode_s below is the oracle port of the same episode on this box"}
+            if world == 1 and not args.no_cpu_baseline:
+                # the same episode on one host core through the oracle port of the reference's step (one scipy DOP853
+                # solve per state, one filter object per target, one Python call per pair): SURVEY.md section 8(d)
+                from oracle.step import OracleCatalog
+                st = c1_state
+                orc = OracleCatalog(st["sens"], ["terrestrial"] * st["sens"].shape[1], st["targ"], st["est_x"], st["est_p"],
+                                    st["Q"], st["R"])
+                _, ve = orc.vis_maps()
+                rng2 = np.random.default_rng(0)
+                t0c = time.perf_counter()
+                for k in range(100):
+                    act = np.where(ve.any(axis=0), (ve * (1 + rng2.random(ve.shape))).argmax(axis=0), ve.shape[0])
+                    tk = np.zeros(ve.shape[0], bool)
+                    for j, a_ in enumerate(act):
+                        if a_ < ve.shape[0] and ve[a_, j]:
+                            tk[a_] = True
+                    z = orc.targets + rng2.normal(size=orc.targets.shape) * np.sqrt(np.diag(st["R"]))[:, None]
+                    # (the measurement of a tasked target is its propagated truth plus noise: drawn around the
+                    # pre-step truth here, the cost is the same)
+                    _, ve = orc.step(100.0 * (k + 1), tk, z)
+                extra_cfgs["c1_default_env_episode"]["cpu_episode_s"] = time.perf_counter() - t0c
+                extra_cfgs["c1_default_env_episode"]["cpu_kind"] = "oracle port, one core"
+            del env1
+        except Exception as exc:                         # informational line: never fail the bench on it
+            extra_cfgs["c1_default_env_episode"] = {"error": repr(exc)}
+
     def leave():
         # Ranks leave together and without tearing NCCL down: destroying a process group whose
         # collectives live inside instantiated CUDA graphs can block at exit.
