@@ -80,7 +80,7 @@ class Box(Space):
     def sample(self, mask=None):
         lo = np.where(self.bounded_below, self.low, -1e3).astype(np.float64)
         hi = np.where(self.bounded_above, self.high, 1e3).astype(np.float64)
-        return self.np_random.uniform(lo, hi).astype(self.dtype)
+        return np.asarray(self.np_random.uniform(lo, hi)).astype(self.dtype)
 
     def __eq__(self, other):
         return (isinstance(other, Box) and self.shape == other.shape and self.dtype == other.dtype
@@ -142,6 +142,9 @@ class MultiDiscrete(Space):
 
     def sample(self, mask=None):
         return (self.np_random.random(self.nvec.shape) * self.nvec).astype(self.dtype)
+
+    def __len__(self):
+        return len(self.nvec)
 
     def __eq__(self, other):
         return isinstance(other, MultiDiscrete) and np.array_equal(self.nvec, other.nvec)
@@ -525,6 +528,7 @@ def install():
     spaces = module("gymnasium.spaces", utils=utils, **space_names)
     wrappers = module("gymnasium.wrappers", FilterObservation=FilterObservation, FlattenObservation=FlattenObservation,
                       TransformReward=TransformReward, TransformObservation=TransformObservation)
+    wrappers.filter_observation = module("gymnasium.wrappers.filter_observation", FilterObservation=FilterObservation)
     registration = module("gymnasium.envs.registration", register=register, registry=registry, make=make)
     envs = module("gymnasium.envs", registration=registration, register=register, registry=registry)
     core = module("gymnasium.core", Env=Env, Wrapper=Wrapper, ObservationWrapper=ObservationWrapper,

@@ -81,6 +81,33 @@ import _mini_gym  # noqa: E402
 
 _mini_gym.install()
 sys.meta_path.insert(0, _Finder())
+
+
+class RandomEnv(sys.modules["gymnasium"].Env):
+    """Stand-in for ray.rllib.examples.env.random_env.RandomEnv (the reference's wrapper tests wrap it): spaces
+    from the config, observations / rewards sampled from them, never-ending episodes."""
+
+    def __init__(self, config=None):
+        gym = sys.modules["gymnasium"]
+        config = config or {}
+        self.action_space = config.get("action_space", gym.spaces.Discrete(2))
+        self.observation_space = config.get("observation_space", gym.spaces.Discrete(2))
+        self.reward_space = config.get("reward_space", gym.spaces.Box(low=-1.0, high=1.0, shape=(), dtype=np.float32))
+        self.steps = 0
+
+    def reset(self, *, seed=None, options=None):
+        self.steps = 0
+        return self.observation_space.sample(), {}
+
+    def step(self, action):
+        self.steps += 1
+        return self.observation_space.sample(), float(self.reward_space.sample()), False, False, {}
+
+
+_rand_mod = _StubModule("ray.rllib.examples.env.random_env")
+_rand_mod.__path__ = []
+_rand_mod.RandomEnv = RandomEnv
+sys.modules["ray.rllib.examples.env.random_env"] = _rand_mod
 pkg = types.ModuleType("punchclock")
 pkg.__path__ = ["/root/reference/punchclock"]
 sys.modules["punchclock"] = pkg

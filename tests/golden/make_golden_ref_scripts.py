@@ -20,7 +20,8 @@ SCRIPTS = [
     "tests/environment/test_env_utils.py", "tests/environment/test_env_parameters.py",
     "tests/schedule_tree/test_access_windows.py", "tests/simulation/test_sim_utils.py", "tests/common/test_metrics.py",
     "tests/common/test_utilities.py", "tests/common/test_orbits.py", "tests/policies/test_greedy_cov_v2.py",
-    "tests/policies/test_random_policy.py",
+    "tests/policies/test_random_policy.py", "tests/environment/test_info_wrappers.py",
+    "tests/environment/test_misc_wrappers.py", "tests/environment/test_reward_wrappers.py",
 ]
 
 
