@@ -352,7 +352,11 @@ def run_own(args):
             # beside the target propagation; --exchange nccl: one all-gather of the
             # summary buffer captured into the step's graph.  Environments (num_envs > 1) are independent
             # replicas: nothing is exchanged.
-            if world > 1 and num_envs == 1:
+            if world > 1 and num_envs == 1 and args.exchange == "none":
+                # attribution runs only (profiles/README.md): every rank steps its shard and nobody learns the others'
+                # summaries -- the difference to the default run is what the exchange costs
+                self.exchange = "NONE (--exchange none: independent shards, for attributing the cost of the exchange)"
+            elif world > 1 and num_envs == 1:
                 from clockpunch_b200.sharding import PackedGather
                 self.sg = PackedGather(world, rank, self.eng.summary, n, self.eng.wpr)
                 self.exchange = "nccl all_gather_into_tensor" + ("" if args.eager_gather else " (captured in the step graph)")
@@ -827,8 +831,9 @@ def main():
     ap.add_argument("--eager-gather", action="store_true", help="N > 1: all-gather outside the step's CUDA graph")
     ap.add_argument("--opt-propagate", type=int, default=0, help="tuning: pc_option PC_OPT_PROPAGATE_KERNEL (0 = size rule)")
     ap.add_argument("--opt-finish", type=int, default=0, help="tuning: pc_option PC_OPT_FINISH_KERNEL (0 = size rule)")
-    ap.add_argument("--exchange", default="auto", choices=["auto", "peer", "nccl"],
-                    help="N > 1: summaries pushed into peers' memory by the step kernel, or one NCCL all-gather")
+    ap.add_argument("--exchange", default="auto", choices=["auto", "peer", "nccl", "none"],
+                    help="N > 1: summaries pushed into peers' memory by the step kernel, or one NCCL all-gather "
+                         "(none: no exchange at all -- attribution runs only)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "own" else args.warmup
     if args.impl == "reference":
