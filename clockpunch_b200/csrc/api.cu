@@ -793,8 +793,14 @@ int pc_policy_random_visible_envs_host(const uint32_t* vis_est, int64_t E, int64
   }
   std::vector<std::thread> pool;
   const int64_t per = (total + threads - 1) / threads;
-  for (int64_t t = 1; t < threads; ++t) pool.emplace_back(range, t * per, std::min(total, (t + 1) * per));
+  int64_t started = 1;   // chunk 0 is this thread's
+  try {
+    for (; started < threads; ++started) pool.emplace_back(range, started * per, std::min(total, (started + 1) * per));
+  } catch (...) {
+    // no more threads to be had: this thread takes the chunks that were not started (no exception crosses the C ABI)
+  }
   range(0, std::min(total, per));
+  if (started < threads) range(started * per, total);
   for (auto& th : pool) th.join();
   return PC_OK;
 }
