@@ -103,6 +103,7 @@ _SIGNATURES = {
     "pc_policy_random_visible": ([_vp, _vp, _i64, _i64, _i64, _u64, _u64, _vp, _int, _vp, _vp], _int),
     "pc_policy_random_visible_host": ([_vp, _i64, _i64, _i64, _u64, _u64, _int, _vp], _int),
     "pc_policy_random_visible_envs_host": ([_vp, _i64, _i64, _i64, _i64, _u64, _u64, _int, _vp], _int),
+    "pc_unpack_vis_host": ([_vp, _i64, _i64, _i64, _vp], _int),
     "pc_set_timing": ([_vp, _int], _int),
     "pc_get_timing": ([_vp, C.POINTER(_dbl)], _int),
     "pc_get_kernel_timing": ([_vp, C.POINTER(_dbl), C.POINTER(_dbl)], _int),

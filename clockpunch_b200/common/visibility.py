@@ -75,8 +75,8 @@ def calcVisMapAndDerivative(sensor_states: ndarray, target_states: ndarray, body
 def unpack_vis_words(words: ndarray, M: int) -> ndarray:
     """(N, ceil(M/32)) uint32 packed map -> (N, M) int64, host-side view helper."""
     words = np.ascontiguousarray(words, dtype=np.uint32)
-    if words.shape[1] == 1 and M <= 24:      # few sensors (a batch of environments): only the bytes that hold them
-        bits = np.unpackbits(words.view(np.uint8)[:, : (M + 7) // 8], axis=1, bitorder="little")
-    else:
-        bits = np.unpackbits(words.view(np.uint8), axis=1, bitorder="little")
-    return bits[:, :M].astype(np.int64)
+    out = np.empty((words.shape[0], int(M)), dtype=np.int64)
+    rc = _lib.load_library().pc_unpack_vis_host(words.ctypes.data, words.shape[0], words.shape[1], int(M), out.ctypes.data)
+    if rc:
+        raise ValueError(f"packed map of shape {words.shape} does not hold {M} sensors per row")
+    return out

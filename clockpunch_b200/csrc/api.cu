@@ -730,6 +730,35 @@ int pc_policy_random_visible(pc_ctx* ctx, const uint32_t* vis_est, int64_t N, in
   return PC_OK;
 }
 
+// Work items [0, total) over the cores this process may use (at most 8 threads, at least min_per_thread items each);
+// no exception crosses the C ABI: chunks whose thread could not be started are taken by the caller.
+extern "C++" {
+template <typename F>
+static void host_parallel_for(int64_t total, int64_t min_per_thread, F range) {
+  int64_t threads = 1;
+  if (total >= 2 * min_per_thread) {
+    cpu_set_t set;
+    CPU_ZERO(&set);
+    const int allowed = sched_getaffinity(0, sizeof(set), &set) == 0 ? CPU_COUNT(&set) : 1;
+    threads = std::min<int64_t>(std::min<int64_t>(allowed, 8), total / min_per_thread);
+  }
+  if (threads <= 1) {
+    range(0, total);
+    return;
+  }
+  std::vector<std::thread> pool;
+  const int64_t per = (total + threads - 1) / threads;
+  int64_t started = 1;   // chunk 0 is this thread's
+  try {
+    for (; started < threads; ++started) pool.emplace_back(range, started * per, std::min(total, (started + 1) * per));
+  } catch (...) {
+  }
+  range(0, std::min(total, per));
+  if (started < threads) range(started * per, total);
+  for (auto& th : pool) th.join();
+}
+}  // extern "C++"
+
 static inline uint64_t splitmix64_host(uint64_t x) {
   x += 0x9E3779B97F4A7C15ull;
   x = (x ^ (x >> 30)) * 0xBF58476D1CE4E5B9ull;
@@ -780,28 +809,21 @@ int pc_policy_random_visible_envs_host(const uint32_t* vis_est, int64_t E, int64
   };
   // sensors are independent: a batch of environments (10 240 sensors at BASELINE.json configs[2]: 0.9 ms on one
   // core, more than the device step and the observation copy together) is split over the cores this process may use
-  int64_t threads = 1;
-  if (total >= 4096) {
-    cpu_set_t set;
-    CPU_ZERO(&set);
-    const int allowed = sched_getaffinity(0, sizeof(set), &set) == 0 ? CPU_COUNT(&set) : 1;
-    threads = std::min<int64_t>(std::min<int64_t>(allowed, 8), total / 1024);
-  }
-  if (threads <= 1) {
-    range(0, total);
-    return PC_OK;
-  }
-  std::vector<std::thread> pool;
-  const int64_t per = (total + threads - 1) / threads;
-  int64_t started = 1;   // chunk 0 is this thread's
-  try {
-    for (; started < threads; ++started) pool.emplace_back(range, started * per, std::min(total, (started + 1) * per));
-  } catch (...) {
-    // no more threads to be had: this thread takes the chunks that were not started (no exception crosses the C ABI)
-  }
-  range(0, std::min(total, per));
-  if (started < threads) range(started * per, total);
-  for (auto& th : pool) th.join();
+  host_parallel_for(total, 2048, range);
+  return PC_OK;
+}
+
+int pc_unpack_vis_host(const uint32_t* words, int64_t n, int64_t words_per_row, int64_t m, int64_t* out) {
+  if (n < 0 || m < 0 || words_per_row != (m + 31) / 32) return PC_ERR_BAD_ARG;
+  if (n == 0 || m == 0) return PC_OK;
+  if (!words || !out) return PC_ERR_BAD_ARG;
+  host_parallel_for(n, std::max<int64_t>(1, 262144 / m), [=](int64_t i0, int64_t i1) {
+    for (int64_t i = i0; i < i1; ++i) {
+      const uint32_t* w = words + i * words_per_row;
+      int64_t* o = out + i * m;
+      for (int64_t j = 0; j < m; ++j) o[j] = (w[j >> 5] >> (j & 31)) & 1u;
+    }
+  });
   return PC_OK;
 }
 

@@ -247,6 +247,10 @@ int pc_policy_random_visible_host(const uint32_t* vis_est, int64_t N, int64_t M,
 int pc_policy_random_visible_envs_host(const uint32_t* vis_est, int64_t E, int64_t env_targets, int64_t env_sensors,
                                        int64_t words_per_row, uint64_t seed, uint64_t step, int probes,
                                        int64_t* actions);
+/* Host-side expansion of a packed map into the (N, M) int64 array the reference's observation / info carry
+ * (`vis_map_est`, `vis_map_truth`: env.py:455-462, 508-530): out[i * M + j] = bit j % 32 of words[i * words_per_row
+ * + j / 32].  No device needed; large maps are split over the cores the process may use. */
+int pc_unpack_vis_host(const uint32_t* words, int64_t n, int64_t words_per_row, int64_t m, int64_t* out);
 
 /* ---- measurement helpers (bench.py) ------------------------------------
  * pc_set_timing(1) makes pc_step_fused record three CUDA events on the launch stream: before the

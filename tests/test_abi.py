@@ -197,3 +197,28 @@ def test_host_policy_of_a_batch_of_environments_is_the_same_on_one_core_and_on_m
                 want = i
                 break
         assert many[j] == want, j
+
+
+def test_unpack_vis_host_matches_numpy_on_ragged_shapes():
+    """pc_unpack_vis_host (no device needed): (N, ceil(M/32)) packed words -> the (N, M) int64 map of the reference's
+    observation, for sensor counts around the word boundaries, empty maps, and a map large enough to be split over
+    threads; a words_per_row that does not fit M is a bad argument."""
+    import numpy as np
+    from clockpunch_b200 import _lib
+    from clockpunch_b200.common.visibility import unpack_vis_words
+    lib = _lib.load_library()
+    rng = np.random.default_rng(3)
+    for N, M in ((0, 5), (3, 1), (7, 31), (7, 32), (7, 33), (5, 64), (9, 100), (120_000, 10), (4000, 300)):
+        wpr = (M + 31) // 32
+        dense = rng.random((N, M)) < 0.4
+        words = np.zeros((N, wpr), np.uint32)
+        for j in range(M):
+            words[:, j >> 5] |= dense[:, j].astype(np.uint32) << np.uint32(j & 31)
+        words[:, -1:] |= np.uint32(0) if M % 32 == 0 else np.uint32(1) << np.uint32(31)   # a stray padding bit is ignored
+        if M % 32 == 31:
+            words[:, -1:] &= ~(np.uint32(1) << np.uint32(31))
+        out = unpack_vis_words(words, M)
+        assert out.dtype == np.int64 and out.shape == (N, M)
+        np.testing.assert_array_equal(out, dense.astype(np.int64))
+    out = np.zeros((4, 40), np.int64)
+    assert lib.pc_unpack_vis_host(np.zeros((4, 1), np.uint32).ctypes.data, 4, 1, 40, out.ctypes.data) == -1
