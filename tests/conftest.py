@@ -20,3 +20,13 @@ def golden():
     def load(name):
         return np.load(os.path.join(GOLDEN, name + ".npz"))
     return load
+
+
+def pytest_sessionfinish(session, exitstatus):
+    """A test may have started a single-rank process group in this process (the peer-exchange test): close it."""
+    td = sys.modules.get("torch.distributed")
+    try:
+        if td is not None and td.is_available() and td.is_initialized():
+            td.destroy_process_group()
+    except Exception:
+        pass
