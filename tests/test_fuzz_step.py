@@ -84,3 +84,68 @@ def test_random_catalog_all_mappings_and_oracle_sample(n, m, dt, p_task, space_f
         sc = np.sqrt(np.abs(np.einsum("...ii,...jj->...ij", ep, ep)))
         assert np.max(np.abs(a["est_p"][sample] - ep) / sc) <= 1e-8 * (s + 1)
     assert (engines[0].host("num_tasked") >= 0).all()
+
+
+def _env_cases():
+    rng = np.random.default_rng(7)
+    out = []
+    for k in range(14):
+        out.append((int(rng.choice([1, 2, 3, 7, 16])), int(rng.choice([1, 5, 33, 100, 130])), int(rng.choice([1, 3, 10, 33, 40])),
+                    int(rng.integers(1, 1 << 30))))
+    return out
+
+
+@pytest.mark.parametrize("E, Ne, Me, seed", _env_cases())
+def test_random_batch_of_environments_actions_path(E, Ne, Me, seed):
+    """The ACTIONS path (tasking built by the sensor kernel from the previous estimated map; update warps in the
+    four-lane kernel) on random batches of environments: against the in-line mapping on the same batch, and against
+    E independent single-environment engines -- bookkeeping, truth and true visibility exactly, filter outputs to
+    round-off.  Actions include inaction, several sensors on one target and picks the map does not allow."""
+    from clockpunch_b200 import _lib
+    from clockpunch_b200.engine import CatalogEngine
+    from clockpunch_b200.simulation.catalog import synth_catalog
+    cat = synth_catalog(E * Ne, E * Me, seed=seed, mix="LEO")
+    rng = np.random.default_rng(seed)
+    ctx = _lib.get_ctx()
+
+    def make(variant, **kw):
+        old = ctx.set_option(_lib.OPT_FINISH_KERNEL, variant)
+        try:
+            return CatalogEngine(kw.get("s", cat.sensors), kw.get("k", cat.sensor_kinds), kw.get("t", cat.targets),
+                                 kw.get("x", cat.est_x), kw.get("p", cat.est_p), cat.Q, cat.R, seed=3, num_envs=kw.get("E", E))
+        finally:
+            ctx.set_option(_lib.OPT_FINISH_KERNEL, old)
+
+    auto, inline = make(_lib.FINISH_AUTO), make(_lib.FINISH_QUAD_INLINE)
+    solo = []
+    for e in range(min(E, 4)):
+        ts, ss = slice(e * Ne, (e + 1) * Ne), slice(e * Me, (e + 1) * Me)
+        solo.append(make(_lib.FINISH_AUTO, s=cat.sensors[:, ss], k=cat.sensor_kinds[ss], t=cat.targets[:, ts],
+                         x=cat.est_x[:, ts], p=cat.est_p[ts], E=1))
+    for s in range(3):
+        acts = rng.integers(0, Ne + 1, size=(E, Me))
+        if Me > 1:
+            acts[:, 1] = acts[:, 0]                                  # two sensors on one target
+        z = cat.targets + rng.normal(size=cat.targets.shape)
+        for eng, v in ((auto, _lib.FINISH_AUTO), (inline, _lib.FINISH_QUAD_INLINE)):
+            old = ctx.set_option(_lib.OPT_FINISH_KERNEL, v)
+            try:
+                eng.step(dt=100.0, actions=acts.reshape(-1), z=z)
+            finally:
+                ctx.set_option(_lib.OPT_FINISH_KERNEL, old)
+        a, b = {k: auto.host(k) for k in OUT}, {k: inline.host(k) for k in OUT}
+        for k in ("truth_x", "num_tasked", "last_time_tasked", "vis_truth", "flags"):
+            np.testing.assert_array_equal(a[k], b[k], err_msg=k)
+        assert np.abs(a["est_x"] - b["est_x"])[:3].max() <= 2e-5 * (s + 1)
+        scale = np.sqrt(np.abs(np.einsum("...ii,...jj->...ij", a["est_p"], a["est_p"])))
+        assert np.max(np.abs(a["est_p"] - b["est_p"]) / scale) <= 1e-8 * (s + 1)
+        for e, eng in enumerate(solo):
+            ts = slice(e * Ne, (e + 1) * Ne)
+            eng.step(dt=100.0, actions=acts[e], z=z[:, ts])
+            c = {k: eng.host(k) for k in OUT}
+            for k in ("num_tasked", "last_time_tasked", "vis_truth"):
+                np.testing.assert_array_equal(a[k][ts], c[k], err_msg=f"env {e} {k}")
+            np.testing.assert_array_equal(a["truth_x"][:, ts], c["truth_x"])
+            assert np.abs(a["est_x"][:, ts] - c["est_x"])[:3].max() <= 2e-5 * (s + 1)
+    # a target is measured at most once per step however many sensors point at it
+    assert (auto.host("num_tasked") <= 3).all()
