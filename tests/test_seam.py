@@ -266,6 +266,42 @@ print("INFOWRAP_OK", ctx.lib.calls)
 
 
 @needs_ref
+def test_reference_monte_carlo_runner_on_the_swapped_env(golden):
+    """simulation/mc.py `MonteCarloRunner` (serial mode): env from a JSON-able config through the reference's buildEnv,
+    policy from a config through buildCustomPolicy, two episodes run by SimRunner, results through the runner's own
+    DataFrame / pickle round trip and post-processing -- imported through install_as_punchclock(), the numeric columns
+    equal the all-reference run's (tests/golden/make_golden_mc.py)."""
+    out = _run('''
+import numpy as np
+import _ref_stubs, sys
+import clockpunch_b200 as cpb
+ref = cpb.install_as_punchclock()
+sys.modules["punchclock.ray.build_ray_policy"] = _ref_stubs._StubModule("punchclock.ray.build_ray_policy")
+import _oracle_engine
+_oracle_engine.install_cpu_doubles()
+import make_golden_mc as mk
+from punchclock.policies.policy_builder import buildSpaceConfig
+from punchclock.ray.build_env import buildEnv
+from punchclock.simulation.mc import MonteCarloRunner
+import punchclock.simulation.mc as mc, clockpunch_b200.environment.env as ours
+assert mc.__file__.startswith(ref)
+got = mk.run(buildEnv, buildSpaceConfig, MonteCarloRunner)
+np.savez("/tmp/mc_got.npz", **got)
+print("MC_OK")
+''')
+    assert "MC_OK" in out
+    want, got = golden("mc"), np.load("/tmp/mc_got.npz")
+    assert int(got["n_rows"]) == int(want["n_rows"]) == 10
+    np.testing.assert_array_equal(got["columns"], want["columns"])
+    assert want["info_num_tasked"][-1].sum() >= 3
+    for k in want.files:
+        if k in ("n_rows", "columns"):
+            continue
+        assert got[k].shape == want[k].shape, k
+        np.testing.assert_allclose(got[k], want[k], rtol=2e-6, atol=1e-6, err_msg=k, equal_nan=True)
+
+
+@needs_ref
 def test_generic_filter_and_custom_dynamics_are_served_by_the_reference_classes():
     """tests/estimation/test_ukf_v2.py:54-170 of the reference (2-state filter, custom DynamicsModel subclass,
     pass-through measurement) and tests/dynamics/test_propagator.py:10-68 (toy linear ODE) through the
