@@ -25,10 +25,11 @@ needs_ref = pytest.mark.skipif(not os.path.isfile(os.path.join(REF, "punchclock"
                                reason="reference tree not available on this box")
 
 
-def _run(code: str) -> str:
-    """Run a snippet in a fresh interpreter (the seam rewrites sys.modules: keep it out of this process)."""
+def _run(code: str, out=None) -> str:
+    """Run a snippet in a fresh interpreter (the seam rewrites sys.modules: keep it out of this process); `out`:
+    where the snippet saves its arrays (os.environ["SEAM_OUT"])."""
     env = dict(os.environ, PYTHONPATH=os.pathsep.join([ROOT, os.path.join(ROOT, "tests"), os.path.join(ROOT, "tests", "golden")]),
-               PUNCHCLOCK_REFERENCE=REF)
+               PUNCHCLOCK_REFERENCE=REF, SEAM_OUT=str(out or ""))
     r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env=env, cwd="/tmp", timeout=600)
     assert r.returncode == 0, r.stdout[-3000:] + "\n" + r.stderr[-6000:]
     return r.stdout
@@ -124,13 +125,14 @@ except ModuleNotFoundError:
 
 
 @needs_ref
-def test_wrapped_env_built_by_the_reference_buildenv_matches_the_live_reference(golden):
+def test_wrapped_env_built_by_the_reference_buildenv_matches_the_live_reference(golden, tmp_path):
     """The reference's buildEnv with the wrapper stack of its own tests/simulation/data/gen_config_env.py
     (FilterObservation, CopyObsInfoItem, VisMap2ActionMask, CopyObsInfoItem, NestObsItems, IdentityWrapper,
     FlatDict), imported THROUGH install_as_punchclock(), builds the mirrored SSASchedulerParams /
     SSAScheduler / agents / filters, wraps them with the reference's wrapper classes, and an 8-step rollout
     reproduces the golden rollout of the all-reference stack (tests/golden/make_golden_seam.py): wrapped
     observation, action mask, info."""
+    out_file = tmp_path / "got.npz"
     out = _run('''
 import numpy as np
 import _ref_stubs, sys
@@ -151,12 +153,12 @@ for w, mod in (("FlatDict", "obs_wrappers"), ("VisMap2ActionMask", "misc_wrapper
     import importlib
     m = importlib.import_module("punchclock.environment." + mod)
     assert m.__file__.startswith(ref)
-np.savez("/tmp/seam_got.npz", **{k.replace("/", "|"): v for k, v in got.items()})
+import os; np.savez(os.environ["SEAM_OUT"], **{k.replace("/", "|"): v for k, v in got.items()})
 print("ROLLOUT_OK")
-''')
+''', out_file)
     assert "ROLLOUT_OK" in out
     g = golden("seam")
-    got = {k.replace("|", "/"): v for k, v in np.load("/tmp/seam_got.npz").items()}
+    got = {k.replace("|", "/"): v for k, v in np.load(out_file).items()}
     want = {k[len("wrapped/"):]: g[k] for k in g.files if k.startswith("wrapped/")}
     assert set(want) <= set(got), sorted(set(want) - set(got))
     np.testing.assert_array_equal(got["actions"], want["actions"])
@@ -176,12 +178,13 @@ print("ROLLOUT_OK")
 
 
 @needs_ref
-def test_reference_simrunner_and_greedy_policy_run_on_the_swapped_env(golden):
+def test_reference_simrunner_and_greedy_policy_run_on_the_swapped_env(golden, tmp_path):
     """simulation/sim_runner.py:63-350 (`SimRunner.runSim`, which deep-copies the wrapped env every step and
     reads `env.unwrapped._getObs()`, :168-175) with the reference's GreedyCovariance policy
     (policies/greedy_cov_v2.py), both imported through install_as_punchclock(), on the scenario of the
     reference's tests/simulation/test_sim_runner.py:86-345: the SimResults equal those of the all-reference
     stack (tests/golden/make_golden_simrunner.py)."""
+    out_file = tmp_path / "got.npz"
     out = _run('''
 import numpy as np
 import _ref_stubs, sys
@@ -199,12 +202,12 @@ import punchclock.simulation.sim_runner as sr, punchclock.policies.greedy_cov_v2
 assert sr.__file__.startswith(ref) and gc.__file__.startswith(ref)
 got, env = mk.run(buildEnv, GreedyCovariance, SimRunner)
 assert type(env.unwrapped) is ours.SSAScheduler and type(env.unwrapped._engine) is _oracle_engine.OracleEngine
-np.savez("/tmp/simrunner_got.npz", **got)
+import os; np.savez(os.environ["SEAM_OUT"], **got)
 print("SIMRUNNER_OK")
-''')
+''', out_file)
     assert "SIMRUNNER_OK" in out
     want = golden("simrunner")
-    got = np.load("/tmp/simrunner_got.npz")
+    got = np.load(out_file)
     assert set(want.files) == set(got.files)
     assert want["info_num_tasked"][-1].sum() >= 5 and len(want["actions"]) == 10
     for k in want.files:
@@ -217,13 +220,14 @@ print("SIMRUNNER_OK")
 
 
 @needs_ref
-def test_reference_info_wrappers_that_call_the_hot_path_run_on_the_mirrors(golden):
+def test_reference_info_wrappers_that_call_the_hot_path_run_on_the_mirrors(golden, tmp_path):
     """environment/info_wrappers.py `NumWindows` (:163-637: AccessWindowCalculator forecast recalculated on every
     step, from `env.agents` and their filters) and `VisMap` (:1572-1771: calcVisMapAndDerivative of the estimated
     states), stacked by the reference's buildEnv -- the reference's wrapper classes, imported through
     install_as_punchclock(), bind the MIRRORED AccessWindowCalculator / calcVisMapAndDerivative / agents, whose calls
     reach the library's host entry points (pc_vis_history_host, pc_vismap_der_host; here tests/_oracle_lib.py).
     The rollout equals the all-reference stack's (tests/golden/make_golden_infowrap.py)."""
+    out_file = tmp_path / "got.npz"
     out = _run('''
 import numpy as np
 import _ref_stubs, sys
@@ -241,12 +245,12 @@ assert iw.AccessWindowCalculator is aw.AccessWindowCalculator and iw.calcVisMapA
 got, env = mk.rollout(buildEnv)
 assert str(env).startswith("<VisMap<NumWindows<"), str(env)
 assert ctx.lib.calls.get("pc_vis_history_host", 0) >= mk.STEPS and ctx.lib.calls.get("pc_vismap_der_host", 0) >= mk.STEPS, ctx.lib.calls
-np.savez("/tmp/infowrap_got.npz", **got)
+import os; np.savez(os.environ["SEAM_OUT"], **got)
 print("INFOWRAP_OK", ctx.lib.calls)
-''')
+''', out_file)
     assert "INFOWRAP_OK" in out
     want = golden("infowrap")
-    got = np.load("/tmp/infowrap_got.npz")
+    got = np.load(out_file)
     # `vis_map_dot`: the VisMap wrapper hands the FLOAT32 info["est_x"] to calcVisMapAndDerivative, and the reference
     # then evaluates its orbit-element chain for d|r|/dt (orbits.py:39-69) in float32 -- for an Earth-fixed sensor
     # (e = 0.997, apogee) that is a catastrophic cancellation: on these very inputs the reference differs from ITSELF
@@ -266,11 +270,12 @@ print("INFOWRAP_OK", ctx.lib.calls)
 
 
 @needs_ref
-def test_reference_monte_carlo_runner_on_the_swapped_env(golden):
+def test_reference_monte_carlo_runner_on_the_swapped_env(golden, tmp_path):
     """simulation/mc.py `MonteCarloRunner` (serial mode): env from a JSON-able config through the reference's buildEnv,
     policy from a config through buildCustomPolicy, two episodes run by SimRunner, results through the runner's own
     DataFrame / pickle round trip and post-processing -- imported through install_as_punchclock(), the numeric columns
     equal the all-reference run's (tests/golden/make_golden_mc.py)."""
+    out_file = tmp_path / "got.npz"
     out = _run('''
 import numpy as np
 import _ref_stubs, sys
@@ -286,11 +291,11 @@ from punchclock.simulation.mc import MonteCarloRunner
 import punchclock.simulation.mc as mc, clockpunch_b200.environment.env as ours
 assert mc.__file__.startswith(ref)
 got = mk.run(buildEnv, buildSpaceConfig, MonteCarloRunner)
-np.savez("/tmp/mc_got.npz", **got)
+import os; np.savez(os.environ["SEAM_OUT"], **got)
 print("MC_OK")
-''')
+''', out_file)
     assert "MC_OK" in out
-    want, got = golden("mc"), np.load("/tmp/mc_got.npz")
+    want, got = golden("mc"), np.load(out_file)
     assert int(got["n_rows"]) == int(want["n_rows"]) == 10
     np.testing.assert_array_equal(got["columns"], want["columns"])
     assert want["info_num_tasked"][-1].sum() >= 3
