@@ -63,7 +63,10 @@ def workload_config(n_targets, n_sensors):
             "targets_per_gpu": n_targets, "sensors": n_sensors, "dt_s": DT,
             "tasking": "each sensor tasks a random estimated-visible target (<= M per step)",
             "episode": f"catalog reset to its initial state every {EPISODE} steps (outside the timed events)",
-            "l2": "256 MiB flush between timed steps (state fits the 126 MB L2)"}
+            "l2": "256 MiB flush between timed steps (state fits the 126 MB L2)",
+            "physics": "the reference's: two-body, its default ground sensors (dynamics.py:16-40; the reference has no J2 "
+                       "and this line is compared with the reference's CPU path); BASELINE.json's wording of configs[1] "
+                       "(ground/space sensors, two-body + J2) is timed beside it as extra.configs.c2_j2_space_sensors"}
 
 
 # ----------------------------------------------------------------------------- clocks
