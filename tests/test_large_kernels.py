@@ -307,14 +307,16 @@ def test_full_size_oracle_sample():
     _oracle_check(cat, sample, tk, z, dt, _outputs(eng), 0, orc_filters, orc_truth, eng.host("sens_x"))
 
 
-def test_step_host_zero_copy_at_bench_size_equals_device_path():
-    """configs[1] size through the reference-facing call (pc_step_host, zero-copy output block: the HOST
-    instantiation of the four-lane kernel stores the float32 observation and the summaries into mapped host
-    memory while it runs) against the device-resident graph replay of the same steps: the host block must be
-    the float32 / integer image of the device state, bit for bit, every step."""
+@pytest.mark.parametrize("n, m", [(10_000, 100), (40_000, 70), (140_000, 50)])
+def test_step_host_zero_copy_at_bench_size_equals_device_path(n, m):
+    """configs[1] size through the reference-facing call (pc_step_host, zero-copy output block: the HOST instantiation
+    of the four-lane kernel stores the float32 observation and the summaries into mapped host memory while it runs),
+    and catalogs that take the thread-per-target kernels <64, 6> / <128, 3> (one device-to-host copy node behind the
+    kernels), against the device-resident graph replay of the same steps: the host block must be the float32 /
+    integer image of the device state, bit for bit, every step."""
     import torch
     from clockpunch_b200.simulation.catalog import synth_catalog
-    n, m, dt = 10_000, 100, 100.0
+    dt = 100.0
     cat = synth_catalog(n, m, seed=20240627)
     a, b = _engine(cat, seed=9), _engine(cat, seed=9)
     rng = np.random.default_rng(0)
@@ -343,3 +345,4 @@ def test_step_host_zero_copy_at_bench_size_equals_device_path():
         for k in ("truth_x", "est_x", "est_p", "pred_p", "vis_truth", "flags"):
             np.testing.assert_array_equal(a.host(k), b.host(k), err_msg=f"{k} step {s}")
     assert b.host("num_tasked").sum() > 2 * m
+    np.testing.assert_array_equal(hb["last_time_tasked"].numpy(), b.host("last_time_tasked"))
