@@ -11,8 +11,9 @@ F="-gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -std=c++17 -Xcompiler -
 nvcc $F "$@" -c clockpunch_b200/csrc/kernels_ukf.cu -o variants/ukf_$name.o &
 nvcc $F "$@" -c clockpunch_b200/csrc/kernels_propagate.cu -o variants/prop_$name.o &
 nvcc $F "$@" -c clockpunch_b200/csrc/kernels_env.cu -o variants/env_$name.o &
+nvcc $F "$@" -c clockpunch_b200/csrc/api.cu -o variants/api_$name.o &
 wait
 nvcc -shared -o variants/libpunch_$name.so variants/ukf_$name.o variants/prop_$name.o variants/env_$name.o \
-  clockpunch_b200/build/kernels_vis.o clockpunch_b200/build/api.o \
+  clockpunch_b200/build/kernels_vis.o variants/api_$name.o \
   -gencode arch=compute_100a,code=sm_100a -cudart static
 echo variants/libpunch_$name.so
