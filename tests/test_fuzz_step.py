@@ -72,7 +72,7 @@ def test_random_catalog_all_mappings_and_oracle_sample(n, m, dt, p_task, space_f
         ex = np.stack([f.est_x for f in filt], axis=1)
         ep = np.stack([f.est_p for f in filt])
         # The oracle is scipy's adaptive DOP853 at rtol = atol = 1e-10, as the reference.  Against a 3e-14-tolerance
-        # solution (tools/debug/long_step_accuracy.py, states of this very catalog) ITS error is 7e-12 km at 100 s,
+        # solution (tests/tools/long_step_accuracy.py, states of this very catalog) ITS error is 7e-12 km at 100 s,
         # 2.7e-8 km at 300 s and 7e-8 km at 600 s per step; the kernel's is 2e-11 / 2e-11 / 1e-10 km.  So the stated
         # gate (1e-9 km) holds up to 100 s, and at 300 s the comparison can only be as good as the reference's solver.
         pos_tol = 1e-9 if dt <= 100.0 else 5e-8

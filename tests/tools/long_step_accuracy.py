@@ -1,6 +1,6 @@
 """Who is off at long steps: the oracle (scipy DOP853 at the reference's rtol = atol = 1e-10) or the kernel (fixed-step DOP853,
-substep rule)?  Both against a 3e-14-tolerance solution: python tools/debug/long_step_accuracy.py"""
-import sys; sys.path.insert(0,'/root/repo')
+substep rule)?  Both against a 3e-14-tolerance solution: python tests/tools/long_step_accuracy.py"""
+import os, sys; sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import numpy as np
 from scipy.integrate import solve_ivp
 from clockpunch_b200.dynamics.propagator import propagate_batch

@@ -1,6 +1,6 @@
 """Achieved parity errors (not only pass / fail against the gates) of the fused step against the oracle, on the
 bench catalog and on the catalogs that take the other per-target kernels:
-    python tools/parity_report.py > profiles/r2_parity_report.json        (on a B200; ~1 min)
+    python tests/tools/parity_report.py > profiles/r2_parity_report.json        (on a B200; ~1 min)
 For each case: three steps of the whole catalog on the GPU with host-drawn measurements injected on both sides, a
 random sample of targets (every measured one of the sample included) through oracle.OracleUKF / the oracle's
 propagator and visibility restatement; the maxima over the sample and the steps are reported beside the gates of
@@ -10,7 +10,7 @@ import json
 import os
 import sys
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 import numpy as np  # noqa: E402
 
