@@ -222,3 +222,27 @@ def test_unpack_vis_host_matches_numpy_on_ragged_shapes():
         np.testing.assert_array_equal(out, dense.astype(np.int64))
     out = np.zeros((4, 40), np.int64)
     assert lib.pc_unpack_vis_host(np.zeros((4, 1), np.uint32).ctypes.data, 4, 1, 40, out.ctypes.data) == -1
+
+
+def test_only_tests_smoke_and_the_cpu_baseline_leg_touch_the_oracle():
+    """oracle/ is test infrastructure: nothing under clockpunch_b200/ or tools/ may import it (the product has no CPU
+    path), and outside tests/ only __graft_entry__ (build / smoke) and bench.py (cpu_baseline legs) do."""
+    import ast
+    import os
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    users = []
+    for base, dirs, files in os.walk(root):
+        dirs[:] = [d for d in dirs if d not in (".git", "gpurun_out", "__pycache__", "variants", "baseline")]
+        for f in files:
+            if not f.endswith(".py"):
+                continue
+            path = os.path.join(base, f)
+            rel = os.path.relpath(path, root)
+            if rel.startswith(("tests" + os.sep, "oracle" + os.sep)):
+                continue
+            for node in ast.walk(ast.parse(open(path, encoding="utf-8").read())):
+                mods = ([a.name for a in node.names] if isinstance(node, ast.Import) else
+                        [node.module or ""] if isinstance(node, ast.ImportFrom) else [])
+                if any(m == "oracle" or m.startswith("oracle.") for m in mods):
+                    users.append(rel)
+    assert sorted(set(users)) == ["__graft_entry__.py", "bench.py"], sorted(set(users))
